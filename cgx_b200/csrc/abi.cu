@@ -1,0 +1,406 @@
+// cgx-b200: extern "C" entry points (include/cgx_b200.h).  Thin: argument checks, H2D/D2H, stage
+// sequencing and CUDA-event timing.  No CPU fallback anywhere: every call needs the CUDA device.
+#include "context.h"
+#include <algorithm>
+#include <new>
+
+using namespace cgx;
+
+#define CGX_TRY(ctx, ...)                                   \
+    try {                                                   \
+        __VA_ARGS__;                                        \
+        return 0;                                           \
+    } catch (const CgxError &e) {                           \
+        if (ctx) (ctx)->err = e.msg;                        \
+        return 1;                                           \
+    } catch (const std::exception &e) {                     \
+        if (ctx) (ctx)->err = e.what();                     \
+        return 2;                                           \
+    }
+
+static thread_local std::string g_create_err;
+
+extern "C" int cgx_version(void) { return 100; }
+
+extern "C" int cgx_create(int device, cgx_ctx_t **out) {
+    *out = nullptr;
+    try {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0) throw CgxError{std::string("no CUDA device: ") + cudaGetErrorString(e)};
+        CGX_REQUIRE(device >= 0 && device < count, "device %d out of range (have %d)", device, count);
+        CUDA_CHECK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+        CGX_REQUIRE(prop.major >= 10, "cgx_b200 kernels are built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+        cgx_ctx *c = new cgx_ctx();
+        c->device = device;
+        CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        for (auto &ev : c->batch.ev) CUDA_CHECK(cudaEventCreate(&ev));
+        memset(&c->batch.info, 0, sizeof(c->batch.info));
+        *out = c;
+        return 0;
+    } catch (const CgxError &e) {
+        g_create_err = e.msg;
+        fprintf(stderr, "cgx_create: %s\n", e.msg.c_str());
+        return 1;
+    }
+}
+
+extern "C" void cgx_destroy(cgx_ctx_t *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    Index &ix = c->ix;
+    DevBuf *ib[] = {&ix.str, &ix.sa, &ix.inv[0], &ix.inv[1], &ix.inv[2], &ix.tok_start, &ix.RLP, &ix.L_tar, &ix.R_tar, &ix.tgt, &ix.freq_flag,
+                    &ix.lex_key, &ix.lex_v1, &ix.lex_v2};
+    for (auto *b : ib) b->release();
+    c->ws.release();
+    Batch &b = c->batch;
+    DevBuf *bb[] = {&b.q_tok, &b.q_off, &b.tok2q, &b.longest, &b.iv, &b.ph_keys, &b.ph_keys_tmp, &b.ph_vals, &b.ph_vals_tmp, &b.ph_flags, &b.phrase_id,
+                    &b.phrases, &b.e1_count, &b.e1_inst, &b.e1_keys, &b.e1_keys_tmp, &b.e1_vals, &b.e1_vals_tmp, &b.e1_flags, &b.e1_pid, &b.pat1,
+                    &b.pat1_dev, &b.pat1_pos, &b.ql_keys, &b.ql_keys_tmp, &b.q1_off, &b.q1_ids, &b.q2_off, &b.q2_ids, &b.j_tiles, &b.hit_keys,
+                    &b.hit_keys_tmp, &b.counters, &b.missing, &b.hits1_sorted, &b.hits2_sorted, &b.e2_count, &b.e2_keys, &b.e2_keys_tmp, &b.e2_vals,
+                    &b.e2_vals_tmp, &b.e2_flags, &b.pat2, &b.rec_hash, &b.rec_idx, &b.rec_idx_tmp, &b.rec_keys, &b.rec_keys_tmp, &b.rec_flags,
+                    &b.scratch, &b.scratch2, &b.radix.hist, &b.radix.status, &b.radix.counters};
+    for (auto *x : bb) x->release();
+    for (int k = 0; k < 3; k++) { b.slot_off[k].release(); b.rec[k].release(); b.rec_sorted[k].release(); b.rules[k].release(); b.updown[k].release(); b.id_count[k].release(); }
+    for (auto &l : b.scan.level) l.release();
+    if (b.h_pinned) cudaFreeHost(b.h_pinned);
+    for (auto &ev : b.ev) if (ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" const char *cgx_last_error(const cgx_ctx_t *c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+
+// ------------------------------------------------------------------------------------------------
+// index
+// ------------------------------------------------------------------------------------------------
+static int32_t max_token_of(const int32_t *src, int64_t n) {
+    int32_t mx = 0;
+    for (int64_t i = 0; i < n; i++) mx = std::max(mx, src[i]);
+    return mx;
+}
+
+static void build_index_device(cgx_ctx *c) {
+    Index &ix = c->ix;
+    cudaEvent_t e0, e1, e2;
+    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1)); CUDA_CHECK(cudaEventCreate(&e2));
+    CUDA_CHECK(cudaEventRecord(e0, c->stream));
+    build_suffix_array(ix.str.ptr<int32_t>(), ix.n, ix.maxtok, ix.sa.get<int32_t>(ix.n), c->ws, c->stream, &ix.sa_stats);
+    CUDA_CHECK(cudaEventRecord(e1, c->stream));
+    int launches = 0;
+    build_index_aux(ix, c->ws, c->stream, &launches);
+    CUDA_CHECK(cudaEventRecord(e2, c->stream));
+    CUDA_CHECK(cudaEventSynchronize(e2));
+    CUDA_CHECK(cudaEventElapsedTime(&ix.sa_stats.ms, e0, e1));
+    CUDA_CHECK(cudaEventElapsedTime(&c->aux_ms, e1, e2));
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    c->ws.release();                                  // the build workspace (32 B/token) is not needed at query time
+    ix.built = true;
+}
+
+extern "C" int cgx_index_build(cgx_ctx_t *c, const int32_t *src, int64_t n, const int32_t *tgt, int64_t m, const uint32_t *RLP,
+                               const uint8_t *L_tar, const uint8_t *R_tar) {
+    CGX_TRY(c, {
+        CGX_REQUIRE(c && src && tgt && RLP && L_tar && R_tar, "null argument");
+        CGX_REQUIRE(n >= 4 && m >= 1, "empty corpus");
+        CUDA_CHECK(cudaSetDevice(c->device));
+        Index &ix = c->ix;
+        ix.n = (size_t)n; ix.m = (size_t)m;
+        ix.maxtok = max_token_of(src, n);
+        CGX_REQUIRE(src[n] == 0 && src[n + 1] == 0 && src[n + 2] == 0, "source text must be followed by three zeros (Start.cu:354)");
+        CUDA_CHECK(cudaMemcpyAsync(ix.str.get<int32_t>(ix.n + 3), src, sizeof(int32_t) * (ix.n + 3), cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaMemcpyAsync(ix.tgt.get<int32_t>(ix.m + 3), tgt, sizeof(int32_t) * (ix.m + 3), cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaMemcpyAsync(ix.RLP.get<uint32_t>(ix.n), RLP, sizeof(uint32_t) * ix.n, cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaMemcpyAsync(ix.L_tar.get<uint8_t>(ix.m), L_tar, ix.m, cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaMemcpyAsync(ix.R_tar.get<uint8_t>(ix.m), R_tar, ix.m, cudaMemcpyHostToDevice, c->stream));
+        build_index_device(c);
+    });
+}
+
+extern "C" int cgx_sa_build_dev(cgx_ctx_t *c, const int32_t *str_dev, int64_t n, int32_t max_token, int32_t *sa_dev, int32_t *rounds_out,
+                                float *ms_out) {
+    CGX_TRY(c, {
+        CGX_REQUIRE(c && str_dev && sa_dev && n >= 2, "bad argument");
+        CUDA_CHECK(cudaSetDevice(c->device));
+        cudaEvent_t e0, e1;
+        CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+        SaStats st;
+        CUDA_CHECK(cudaEventRecord(e0, c->stream));
+        build_suffix_array(str_dev, (size_t)n, max_token, sa_dev, c->ws, c->stream, &st);
+        CUDA_CHECK(cudaEventRecord(e1, c->stream));
+        CUDA_CHECK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        if (rounds_out) *rounds_out = st.rounds;
+        if (ms_out) *ms_out = ms;
+        c->ix.sa_stats = st;
+        c->ix.sa_stats.ms = ms;
+    });
+}
+
+__global__ void lex_keys_kernel(const int32_t *__restrict__ f, const int32_t *__restrict__ e, size_t n, uint64_t *__restrict__ keys, uint32_t *__restrict__ idx) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keys[i] = ((uint64_t)(uint32_t)(f[i] + 1) << 32) | (uint64_t)(uint32_t)(e[i] + 1);
+    idx[i] = (uint32_t)i;
+}
+__global__ void lex_gather_kernel(const uint32_t *__restrict__ idx, const float *__restrict__ v1, const float *__restrict__ v2, size_t n,
+                                  float *__restrict__ o1, float *__restrict__ o2) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    o1[i] = v1[idx[i]];
+    o2[i] = v2[idx[i]];
+}
+
+extern "C" int cgx_lex_load(cgx_ctx_t *c, const int32_t *f, const int32_t *e, const float *v1, const float *v2, int64_t count) {
+    CGX_TRY(c, {
+        CGX_REQUIRE(c && (count == 0 || (f && e && v1 && v2)), "null argument");
+        CUDA_CHECK(cudaSetDevice(c->device));
+        Index &ix = c->ix;
+        size_t n = (size_t)count;
+        ix.lex_count = n;
+        uint64_t *keys = ix.lex_key.get<uint64_t>(n + 1);
+        float *o1 = ix.lex_v1.get<float>(n + 1), *o2 = ix.lex_v2.get<float>(n + 1);
+        if (n == 0) return 0;
+        DevBuf df, de, d1, d2, kt, ix0, ix1, ksrc;
+        RadixTemp rt;
+        int32_t *pf = df.get<int32_t>(n), *pe = de.get<int32_t>(n);
+        float *p1 = d1.get<float>(n), *p2 = d2.get<float>(n);
+        CUDA_CHECK(cudaMemcpyAsync(pf, f, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaMemcpyAsync(pe, e, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaMemcpyAsync(p1, v1, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaMemcpyAsync(p2, v2, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+        uint64_t *k0 = ksrc.get<uint64_t>(n), *k1 = kt.get<uint64_t>(n);
+        uint32_t *i0 = ix0.get<uint32_t>(n), *i1 = ix1.get<uint32_t>(n);
+        lex_keys_kernel<<<cgx_div_up(n, 256), 256, 0, c->stream>>>(pf, pe, n, k0, i0);
+        uint64_t *ks;
+        uint32_t *is;
+        radix_sort<uint64_t>(k0, k1, i0, i1, n, 0, 64, c->stream, rt, &ks, &is);
+        CUDA_CHECK(cudaMemcpyAsync(keys, ks, sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice, c->stream));
+        lex_gather_kernel<<<cgx_div_up(n, 256), 256, 0, c->stream>>>(is, p1, p2, n, o1, o2);
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        DevBuf *tmp[] = {&df, &de, &d1, &d2, &kt, &ix0, &ix1, &ksrc, &rt.hist, &rt.status, &rt.counters};
+        for (auto *t : tmp) t->release();
+    });
+}
+
+extern "C" int cgx_index_info(const cgx_ctx_t *c, cgx_index_info_t *out) {
+    if (!c || !out) return 1;
+    const Index &ix = c->ix;
+    out->n = (int64_t)ix.n; out->m = (int64_t)ix.m;
+    out->sa_rounds = ix.sa_stats.rounds; out->sa_key_bits = ix.sa_stats.key_bits; out->sa_launches = ix.sa_stats.launches;
+    out->sa_build_ms = ix.sa_stats.ms; out->aux_build_ms = c->aux_ms;
+    out->index_bytes = (int64_t)(ix.str.cap + ix.sa.cap + ix.inv[0].cap + ix.inv[1].cap + ix.inv[2].cap + ix.tok_start.cap + ix.RLP.cap + ix.L_tar.cap +
+                                 ix.R_tar.cap + ix.tgt.cap + ix.freq_flag.cap + ix.lex_key.cap + ix.lex_v1.cap + ix.lex_v2.cap);
+    return 0;
+}
+
+extern "C" int cgx_index_export(cgx_ctx_t *c, cgx_index_arrays_t *o) {
+    CGX_TRY(c, {
+        CGX_REQUIRE(c && o && c->ix.built, "index not built");
+        Index &ix = c->ix;
+        o->n = (int64_t)ix.n; o->m = (int64_t)ix.m; o->lex_count = (int64_t)ix.lex_count; o->max_token = ix.maxtok;
+        memcpy(o->freq_list, ix.freq_list, sizeof(ix.freq_list));
+        o->str = ix.str.p; o->sa = ix.sa.p; o->inv1 = ix.inv[0].p; o->inv2 = ix.inv[1].p; o->inv3 = ix.inv[2].p; o->tok_start = ix.tok_start.p;
+        o->RLP = ix.RLP.p; o->L_tar = ix.L_tar.p; o->R_tar = ix.R_tar.p; o->tgt = ix.tgt.p; o->freq_flag = ix.freq_flag.p;
+        o->lex_key = ix.lex_key.p; o->lex_v1 = ix.lex_v1.p; o->lex_v2 = ix.lex_v2.p;
+    });
+}
+
+extern "C" int cgx_index_alloc(cgx_ctx_t *c, const cgx_index_arrays_t *s, cgx_index_arrays_t *o) {
+    CGX_TRY(c, {
+        CGX_REQUIRE(c && s && o, "null argument");
+        CUDA_CHECK(cudaSetDevice(c->device));
+        Index &ix = c->ix;
+        ix.n = (size_t)s->n; ix.m = (size_t)s->m; ix.lex_count = (size_t)s->lex_count; ix.maxtok = s->max_token;
+        memcpy(ix.freq_list, s->freq_list, sizeof(ix.freq_list));
+        size_t nt = (size_t)ix.maxtok + 2;
+        ix.str.get<int32_t>(ix.n + 3); ix.sa.get<int32_t>(ix.n);
+        for (int k = 0; k < 3; k++) ix.inv[k].get<int32_t>(ix.n);
+        ix.tok_start.get<int32_t>(nt); ix.RLP.get<uint32_t>(ix.n); ix.L_tar.get<uint8_t>(ix.m); ix.R_tar.get<uint8_t>(ix.m);
+        ix.tgt.get<int32_t>(ix.m + 3); ix.freq_flag.get<uint8_t>(nt);
+        ix.lex_key.get<uint64_t>(ix.lex_count + 1); ix.lex_v1.get<float>(ix.lex_count + 1); ix.lex_v2.get<float>(ix.lex_count + 1);
+        ix.built = false;
+        *o = *s;
+        o->str = ix.str.p; o->sa = ix.sa.p; o->inv1 = ix.inv[0].p; o->inv2 = ix.inv[1].p; o->inv3 = ix.inv[2].p; o->tok_start = ix.tok_start.p;
+        o->RLP = ix.RLP.p; o->L_tar = ix.L_tar.p; o->R_tar = ix.R_tar.p; o->tgt = ix.tgt.p; o->freq_flag = ix.freq_flag.p;
+        o->lex_key = ix.lex_key.p; o->lex_v1 = ix.lex_v1.p; o->lex_v2 = ix.lex_v2.p;
+    });
+}
+
+extern "C" int cgx_index_commit(cgx_ctx_t *c) {
+    if (!c) return 1;
+    c->ix.built = true;
+    return 0;
+}
+
+extern "C" int cgx_index_copy_sa(cgx_ctx_t *c, int32_t *out) {
+    CGX_TRY(c, {
+        CGX_REQUIRE(c && out && c->ix.n, "no index");
+        CUDA_CHECK(cudaSetDevice(c->device));
+        CUDA_CHECK(cudaMemcpy(out, c->ix.sa.p, sizeof(int32_t) * c->ix.n, cudaMemcpyDeviceToHost));
+    });
+}
+extern "C" int cgx_index_copy_inv(cgx_ctx_t *c, int which, int32_t *out) {
+    CGX_TRY(c, {
+        CGX_REQUIRE(c && out && c->ix.built && which >= 1 && which <= 3, "bad argument");
+        CUDA_CHECK(cudaSetDevice(c->device));
+        CUDA_CHECK(cudaMemcpy(out, c->ix.inv[which - 1].p, sizeof(int32_t) * c->ix.n, cudaMemcpyDeviceToHost));
+    });
+}
+extern "C" int cgx_index_copy_frequent(cgx_ctx_t *c, int32_t *out) {
+    if (!c || !out || !c->ix.built) return 1;
+    memcpy(out, c->ix.freq_list, sizeof(int32_t) * CGX_PRECOMP);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// query batch
+// ------------------------------------------------------------------------------------------------
+extern "C" int cgx_extract(cgx_ctx_t *c, const int32_t *qry_tok, const int32_t *qry_off, int32_t Q) {
+    CGX_TRY(c, {
+        CGX_REQUIRE(c && qry_off && Q >= 0, "bad argument");
+        CGX_REQUIRE(c->ix.built, "index not built");
+        CUDA_CHECK(cudaSetDevice(c->device));
+        Batch &b = c->batch;
+        const Index &ix = c->ix;
+        cudaStream_t s = c->stream;
+        const int32_t T = qry_off[Q];
+        CGX_REQUIRE(T == 0 || qry_tok, "null query tokens");
+        b.Q = Q; b.T = T; b.launches = 0;
+        memset(&b.info, 0, sizeof(b.info));
+        // stage the inputs through pinned memory: [tok T][off Q+1][tok2q T]
+        size_t need = (size_t)T * 2 + (size_t)Q + 1;
+        if (need > b.h_pinned_cap) {
+            if (b.h_pinned) CUDA_CHECK(cudaFreeHost(b.h_pinned));
+            CUDA_CHECK(cudaMallocHost((void **)&b.h_pinned, sizeof(int32_t) * (need + need / 4 + 64)));
+            b.h_pinned_cap = need + need / 4 + 64;
+        }
+        int32_t *hp = b.h_pinned;
+        if (T) memcpy(hp, qry_tok, sizeof(int32_t) * (size_t)T);
+        memcpy(hp + T, qry_off, sizeof(int32_t) * ((size_t)Q + 1));
+        int32_t *t2q = hp + T + Q + 1;
+        for (int32_t q = 0; q < Q; q++) {
+            CGX_REQUIRE(qry_off[q + 1] >= qry_off[q], "query offsets must be non-decreasing");
+            for (int32_t t = qry_off[q]; t < qry_off[q + 1]; t++) t2q[t] = q;
+        }
+        CUDA_CHECK(cudaEventRecord(b.ev[0], s));
+        int32_t *d_tok = b.q_tok.get<int32_t>((size_t)T + 8);
+        int32_t *d_off = b.q_off.get<int32_t>((size_t)Q + 1);
+        int32_t *d_t2q = b.tok2q.get<int32_t>((size_t)T + 1);
+        if (T) CUDA_CHECK(cudaMemcpyAsync(d_tok, hp, sizeof(int32_t) * (size_t)T, cudaMemcpyHostToDevice, s));
+        CUDA_CHECK(cudaMemcpyAsync(d_off, hp + T, sizeof(int32_t) * ((size_t)Q + 1), cudaMemcpyHostToDevice, s));
+        if (T) CUDA_CHECK(cudaMemcpyAsync(d_t2q, t2q, sizeof(int32_t) * (size_t)T, cudaMemcpyHostToDevice, s));
+        stage_lookup(ix, b, s);
+        CUDA_CHECK(cudaEventRecord(b.ev[1], s));
+        stage_phrases(ix, b, s);
+        stage_onegap_enumerate(ix, b, s);
+        CUDA_CHECK(cudaEventRecord(b.ev[2], s));
+        stage_onegap_join(ix, b, s);
+        CUDA_CHECK(cudaEventRecord(b.ev[3], s));
+        stage_twogap_enumerate(ix, b, s);
+        CUDA_CHECK(cudaEventRecord(b.ev[4], s));
+        stage_twogap_join(ix, b, s);
+        CUDA_CHECK(cudaEventRecord(b.ev[5], s));
+        stage_extract(ix, b, s);
+        CUDA_CHECK(cudaEventRecord(b.ev[6], s));
+        stage_aggregate(ix, b, s);
+        // pattern tables and phrase ids to the host
+        b.h_phrase_id.resize((size_t)T * CGX_LONGEST_SRC);
+        b.h_phrases.resize((size_t)b.G * 4);
+        b.h_pat1.resize((size_t)b.D1 * 8);
+        b.h_pat2.resize((size_t)b.D2 * 4);
+        if (T) CUDA_CHECK(cudaMemcpyAsync(b.h_phrase_id.data(), b.phrase_id.p, sizeof(int32_t) * b.h_phrase_id.size(), cudaMemcpyDeviceToHost, s));
+        if (b.G) CUDA_CHECK(cudaMemcpyAsync(b.h_phrases.data(), b.phrases.p, sizeof(int32_t) * b.h_phrases.size(), cudaMemcpyDeviceToHost, s));
+        if (b.D1) CUDA_CHECK(cudaMemcpyAsync(b.h_pat1.data(), b.pat1.p, sizeof(int32_t) * b.h_pat1.size(), cudaMemcpyDeviceToHost, s));
+        if (b.D2) CUDA_CHECK(cudaMemcpyAsync(b.h_pat2.data(), b.pat2.p, sizeof(int32_t) * b.h_pat2.size(), cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaEventRecord(b.ev[7], s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        cgx_batch_info_t &in = b.info;
+        in.Q = Q; in.T = T; in.G = b.G; in.enu1 = b.enu1; in.D1 = b.D1; in.hits1 = b.hits1; in.enu2 = b.enu2; in.D2 = b.D2; in.hits2 = b.hits2;
+        in.samples = b.samples; in.n_ab = b.n_rec[0]; in.n_1gap = b.n_rec[1]; in.n_2gap = b.n_rec[2];
+        for (int k = 0; k < 3; k++) in.rules[k] = b.n_rules[k];
+        in.launches = b.launches;
+        float t1, t2, t3, t4;
+        CUDA_CHECK(cudaEventElapsedTime(&in.ms_total, b.ev[0], b.ev[7]));
+        CUDA_CHECK(cudaEventElapsedTime(&in.ms_lookup, b.ev[0], b.ev[1]));
+        CUDA_CHECK(cudaEventElapsedTime(&t1, b.ev[1], b.ev[2]));
+        CUDA_CHECK(cudaEventElapsedTime(&t2, b.ev[3], b.ev[4]));
+        in.ms_enum = t1 + t2;
+        CUDA_CHECK(cudaEventElapsedTime(&t3, b.ev[2], b.ev[3]));
+        CUDA_CHECK(cudaEventElapsedTime(&t4, b.ev[4], b.ev[5]));
+        in.ms_join = t3 + t4;
+        CUDA_CHECK(cudaEventElapsedTime(&in.ms_extract, b.ev[5], b.ev[6]));
+        CUDA_CHECK(cudaEventElapsedTime(&in.ms_aggregate, b.ev[6], b.ev[7]));
+    });
+}
+
+extern "C" int cgx_batch_info(const cgx_ctx_t *c, cgx_batch_info_t *out) {
+    if (!c || !out) return 1;
+    *out = c->batch.info;
+    return 0;
+}
+
+extern "C" int cgx_result(cgx_ctx_t *c, cgx_result_t *o) {
+    if (!c || !o) return 1;
+    Batch &b = c->batch;
+    o->Q = b.Q; o->T = b.T; o->G = b.G; o->D1 = b.D1; o->D2 = b.D2;
+    o->phrase_id = b.h_phrase_id.data(); o->phrases = b.h_phrases.data(); o->pat1 = b.h_pat1.data(); o->pat2 = b.h_pat2.data();
+    o->q1_off = b.h_q1_off.data(); o->q1_ids = b.h_q1_ids.data(); o->q2_off = b.h_q2_off.data(); o->q2_ids = b.h_q2_ids.data();
+    for (int k = 0; k < 3; k++) {
+        o->rules[k] = b.h_rules[k].data(); o->n_rules[k] = b.n_rules[k];
+        o->updown[k] = b.h_updown[k].data(); o->n_ids[k] = b.n_ids[k];
+    }
+    return 0;
+}
+
+extern "C" int64_t cgx_debug_fetch(cgx_ctx_t *c, const char *what, int32_t *out, int64_t cap) {
+    if (!c || !what || !out) return -1;
+    try {
+        CUDA_CHECK(cudaSetDevice(c->device));
+        Batch &b = c->batch;
+        std::string w(what);
+        auto copy_i32 = [&](const void *dev, size_t count) -> int64_t {
+            if ((int64_t)count > cap) return -2;
+            if (count) CUDA_CHECK(cudaMemcpy(out, dev, sizeof(int32_t) * count, cudaMemcpyDeviceToHost));
+            return (int64_t)count;
+        };
+        if (w == "longest") return copy_i32(b.longest.p, (size_t)b.T);
+        if (w == "intervals") return copy_i32(b.iv.p, (size_t)b.T * CGX_LONGEST_SRC * 2);
+        if (w == "hits1" || w == "hits2") {
+            bool two = w == "hits2";
+            size_t H = (size_t)(two ? b.hits2 : b.hits1);
+            int cols = two ? 4 : 3;
+            if ((int64_t)(H * cols) > cap) return -2;
+            std::vector<uint64_t> h(H);
+            if (H) CUDA_CHECK(cudaMemcpy(h.data(), two ? b.hits2_sorted.p : b.hits1_sorted.p, sizeof(uint64_t) * H, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < H; i++) {
+                if (two) { out[4 * i] = (int32_t)(h[i] >> 38); out[4 * i + 1] = (int32_t)((h[i] >> 8) & 0x3fffffffu); out[4 * i + 2] = (int32_t)((h[i] >> 4) & 15); out[4 * i + 3] = (int32_t)(h[i] & 15); }
+                else { out[3 * i] = (int32_t)(h[i] >> 34); out[3 * i + 1] = (int32_t)((h[i] >> 4) & 0x3fffffffu); out[3 * i + 2] = (int32_t)(h[i] & 15); }
+            }
+            return (int64_t)(H * cols);
+        }
+        if (w == "rec_ab" || w == "rec_1" || w == "rec_2") {
+            int k = w == "rec_ab" ? 0 : w == "rec_1" ? 1 : 2;
+            size_t N = (size_t)b.n_rec[k];
+            if ((int64_t)(N * 7) > cap) return -2;
+            std::vector<RuleRec> r(N);
+            if (N) CUDA_CHECK(cudaMemcpy(r.data(), b.rec[k].p, sizeof(RuleRec) * N, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < N; i++) {
+                out[7 * i] = r[i].id; out[7 * i + 1] = r[i].tgt_start; out[7 * i + 2] = r[i].end;
+                out[7 * i + 3] = r[i].gap1 == 255 ? -1 : r[i].gap1; out[7 * i + 4] = r[i].gap1 == 255 ? -1 : r[i].gap1_1;
+                out[7 * i + 5] = r[i].gap2 == 255 ? -1 : r[i].gap2; out[7 * i + 6] = r[i].gap2 == 255 ? -1 : r[i].gap2_1;
+            }
+            return (int64_t)(N * 7);
+        }
+        c->err = "unknown debug array";
+        return -3;
+    } catch (const CgxError &e) {
+        c->err = e.msg;
+        return -4;
+    }
+}

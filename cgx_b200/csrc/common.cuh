@@ -1,0 +1,100 @@
+// cgx-b200: shared device/host helpers (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#define CGX_MAX_RULE_SPAN 15       // ComTypes.h:42-43
+#define CGX_MAX_RULE_SYMBOLS 5     // ComTypes.h:44
+#define CGX_MAXSCORE 99.0f         // ComTypes.h:51
+#define CGX_PRECOMP 100            // ComTypes.h:55
+#define CGX_SAMPLER 300            // ComTypes.h:63
+#define CGX_SAMPLER_ONEGAP 65      // ComTypes.h:64
+#define CGX_SAMPLER_TWOGAP 70      // ComTypes.h:65
+#define CGX_LONGEST_SRC 5          // ExtractPair.cu:16
+
+#define CGX_NUM_SMS 148
+
+struct CgxError {
+    std::string msg;
+};
+
+#define CUDA_CHECK(expr)                                                                              \
+    do {                                                                                              \
+        cudaError_t e_ = (expr);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            char b_[512];                                                                             \
+            snprintf(b_, sizeof b_, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); \
+            throw CgxError{b_};                                                                       \
+        }                                                                                             \
+    } while (0)
+
+#define CGX_REQUIRE(cond, ...)                                                    \
+    do {                                                                          \
+        if (!(cond)) {                                                            \
+            char b_[512];                                                         \
+            snprintf(b_, sizeof b_, __VA_ARGS__);                                 \
+            throw CgxError{std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": " + b_}; \
+        }                                                                         \
+    } while (0)
+
+// Grow-only device buffer: allocations are reused across query batches so that the steady-state hot
+// path performs no cudaMalloc.
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    bool owned = true;
+    template <typename T>
+    T *get(size_t count) {
+        size_t bytes = count * sizeof(T);
+        if (bytes > cap) {
+            if (p && owned) CUDA_CHECK(cudaFree(p));
+            size_t want = bytes + bytes / 4 + 256;
+            CUDA_CHECK(cudaMalloc(&p, want));
+            cap = want;
+            owned = true;
+        }
+        return reinterpret_cast<T *>(p);
+    }
+    template <typename T>
+    T *ptr() const { return reinterpret_cast<T *>(p); }
+    void release() {
+        if (p && owned) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    // adopt caller-owned device memory (multi-GPU import path)
+    void adopt(void *q, size_t bytes) {
+        release();
+        p = q;
+        cap = bytes;
+        owned = false;
+    }
+};
+
+static inline unsigned cgx_div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+static inline int cgx_bits_for(uint64_t v) {   // number of bits needed to represent values in [0, v]
+    int b = 0;
+    while (v) { b++; v >>= 1; }
+    return b ? b : 1;
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+// streaming (read-once) 128-bit load that does not pollute L1
+__device__ __forceinline__ int4 ld_nc_int4(const int4 *p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+#endif

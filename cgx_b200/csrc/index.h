@@ -1,0 +1,55 @@
+// cgx-b200: the resident corpus index (one per GPU) and the per-batch query workspace.
+#pragma once
+#include "common.cuh"
+#include "radix_sort.cuh"
+#include "scan.cuh"
+
+namespace cgx {
+
+struct SaStats {
+    int rounds = 0;
+    int launches = 0;
+    int key_bits = 0;
+    float ms = 0.f;
+};
+
+struct SaWorkspace {
+    DevBuf keys, keys_tmp, vals, vals_tmp, rank, flags, total;
+    RadixTemp radix;
+    ScanTemp scan;
+    void release() {
+        keys.release(); keys_tmp.release(); vals.release(); vals_tmp.release(); rank.release(); flags.release(); total.release();
+        radix.hist.release(); radix.status.release(); radix.counters.release();
+        for (auto &l : scan.level) l.release();
+    }
+};
+
+void build_suffix_array(const int32_t *d_str, size_t n, int32_t maxtok, int32_t *d_sa_out, SaWorkspace &ws, cudaStream_t stream,
+                        SaStats *stats);
+
+// HBM layout of the index (all arrays dense, 16-byte aligned by cudaMalloc):
+//   str     int32 [n+3]   source text ids (Start.cu:240-380 layout: EOS=1, trailer, 3 zeros)
+//   sa      int32 [n]     suffix array
+//   inv[m]  int32 [n]     m = 1..3: positions sorted by (first m tokens, position).  The bucket of an
+//                         m-gram occupies the same index range as its SA interval, so inv[m][up..down]
+//                         is the *position-sorted* occurrence list of that m-gram (drives the band joins)
+//   tok_start int32 [maxtok+2]  SA bucket start of every token id (1-gram intervals in O(1))
+//   RLP     uint32 [n]    (L<<24)|(R<<16)|(P<<8) per source token; target sentence offset at EOS
+//   L_tar/R_tar uint8 [m] min/max aligned source index per target token (255 = unaligned)
+//   tgt     int32 [m+3]   target text ids
+//   freq_flag uint8 [maxtok+2]  1 for the PRECOMPUTECOUNT most frequent source tokens
+//   lex_key uint64 [L] / lex_v1, lex_v2 float [L]  lexical table sorted by (f+1)<<32 | (e+1)
+struct Index {
+    size_t n = 0, m = 0;
+    int32_t maxtok = 0;
+    DevBuf str, sa, inv[3], tok_start, RLP, L_tar, R_tar, tgt, freq_flag;
+    DevBuf lex_key, lex_v1, lex_v2;
+    size_t lex_count = 0;
+    int32_t freq_list[CGX_PRECOMP];
+    bool built = false;
+    SaStats sa_stats;
+};
+
+void build_index_aux(Index &ix, SaWorkspace &ws, cudaStream_t stream, int *launches);
+
+}  // namespace cgx

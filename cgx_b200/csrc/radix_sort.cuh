@@ -1,0 +1,267 @@
+// cgx-b200: hand-written onesweep LSD radix sort for sm_100a (no Thrust / CUB).
+//
+// One upfront kernel builds the digit histograms of every pass in a single read of the keys; each
+// pass is then ONE kernel ("onesweep", Adinets & Merrill 2022): a tile of keys is ranked with
+// warp-level match/ballot multisplit, the tile's per-digit counts are published, the global prefix of
+// every digit is obtained by decoupled look-back over the preceding tiles' published counts, and the
+// keys (and optional 32-bit payloads) are staged through shared memory so that the scatter to HBM is
+// written in digit-contiguous, coalesced runs.  Per pass the traffic is therefore one read and one
+// write of the data: (sizeof(K)+payload) * 2 bytes per element -- HBM-bound.
+//
+// The sort is stable.  Keys are uint32_t or uint64_t; only bits [begin_bit, end_bit) are sorted on
+// (callers know their key widths: packed (rank,rank) pairs, (pattern,position) pairs ...), split
+// into digits of at most 8 bits.
+#pragma once
+#include "common.cuh"
+
+namespace cgx {
+
+constexpr int RS_BLOCK = 256;                 // threads per CTA
+constexpr int RS_WARPS = RS_BLOCK / 32;
+constexpr int RS_ITEMS = 16;                  // keys per thread
+constexpr int RS_TILE = RS_BLOCK * RS_ITEMS;  // 4096 keys per tile
+constexpr int RS_BINS = 256;
+constexpr int RS_MAX_PASSES = 8;
+
+constexpr uint32_t RS_FLAG_PARTIAL = 1u << 30;
+constexpr uint32_t RS_FLAG_INCLUSIVE = 2u << 30;
+constexpr uint32_t RS_VALUE_MASK = (1u << 30) - 1;
+
+struct RadixPlan {
+    int num_passes;
+    int shift[RS_MAX_PASSES];
+    int bits[RS_MAX_PASSES];
+};
+
+static inline RadixPlan make_radix_plan(int begin_bit, int end_bit) {
+    RadixPlan p;
+    int total = end_bit - begin_bit;
+    if (total < 1) total = 1;
+    p.num_passes = (total + 7) / 8;
+    int base = total / p.num_passes, extra = total % p.num_passes, s = begin_bit;
+    for (int i = 0; i < p.num_passes; i++) {
+        p.bits[i] = base + (i < extra ? 1 : 0);
+        p.shift[i] = s;
+        s += p.bits[i];
+    }
+    return p;
+}
+
+struct RadixTemp {
+    DevBuf hist;      // [passes][256] uint32: digit histograms, then exclusive offsets
+    DevBuf status;    // [tiles][256] uint32 look-back words
+    DevBuf counters;  // [passes] dynamic tile counters
+};
+
+#ifdef __CUDACC__
+
+template <typename K>
+__global__ void __launch_bounds__(RS_BLOCK) rs_histogram_kernel(const K *__restrict__ keys, size_t n, RadixPlan plan,
+                                                                uint32_t *__restrict__ hist) {
+    __shared__ uint32_t sh[RS_MAX_PASSES * RS_BINS];
+    for (int i = threadIdx.x; i < plan.num_passes * RS_BINS; i += RS_BLOCK) sh[i] = 0;
+    __syncthreads();
+    size_t stride = (size_t)gridDim.x * RS_BLOCK;
+    for (size_t i = (size_t)blockIdx.x * RS_BLOCK + threadIdx.x; i < n; i += stride) {
+        K k = keys[i];
+#pragma unroll
+        for (int p = 0; p < RS_MAX_PASSES; p++) {
+            if (p < plan.num_passes) {
+                uint32_t d = (uint32_t)(k >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u);
+                atomicAdd(&sh[p * RS_BINS + d], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < plan.num_passes * RS_BINS; i += RS_BLOCK)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+// exclusive scan of each pass's 256-bin histogram (one CTA of 256 threads per pass)
+static __global__ void __launch_bounds__(RS_BINS) rs_scan_hist_kernel(uint32_t *hist) {
+    __shared__ uint32_t sh[RS_BINS];
+    uint32_t *h = hist + blockIdx.x * RS_BINS;
+    uint32_t v = h[threadIdx.x];
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = 1; off < RS_BINS; off <<= 1) {
+        uint32_t t = threadIdx.x >= off ? sh[threadIdx.x - off] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += t;
+        __syncthreads();
+    }
+    h[threadIdx.x] = sh[threadIdx.x] - v;
+}
+
+template <typename K, bool HAS_VALUES>
+__global__ void __launch_bounds__(RS_BLOCK) rs_onesweep_kernel(const K *__restrict__ keys_in, K *__restrict__ keys_out,
+                                                               const uint32_t *__restrict__ vals_in, uint32_t *__restrict__ vals_out,
+                                                               size_t n, int shift, int bits, const uint32_t *__restrict__ digit_offset,
+                                                               uint32_t *status, uint32_t *tile_counter) {
+    __shared__ K s_keys[RS_TILE];                       // reused for the payload exchange
+    __shared__ uint32_t s_warp_hist[RS_WARPS][RS_BINS];
+    __shared__ uint32_t s_bin_start[RS_BINS];
+    __shared__ uint32_t s_global_base[RS_BINS];
+    __shared__ uint32_t s_tile;
+
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t mask = (1u << bits) - 1u;
+    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+    for (int i = tid; i < RS_WARPS * RS_BINS; i += RS_BLOCK) (&s_warp_hist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const size_t tile_base = (size_t)tile * RS_TILE;
+    const size_t warp_base = tile_base + (size_t)warp * (32 * RS_ITEMS);
+
+    K key[RS_ITEMS];
+    uint32_t rank[RS_ITEMS];
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; i++) {
+        size_t idx = warp_base + (size_t)i * 32 + lane;
+        key[i] = idx < n ? keys_in[idx] : (K)~(K)0;
+    }
+    // ---- warp-level multisplit: stable rank of every key among the warp's keys with the same digit
+    const unsigned lt = lanemask_lt();
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; i++) {
+        uint32_t d = (uint32_t)(key[i] >> shift) & mask;
+        unsigned peers = __match_any_sync(0xffffffffu, d);
+        int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if ((int)lane == leader) {
+            base = s_warp_hist[warp][d];
+            s_warp_hist[warp][d] = base + __popc(peers);
+        }
+        base = __shfl_sync(0xffffffffu, base, leader);
+        rank[i] = base + __popc(peers & lt);
+        __syncwarp();
+    }
+    __syncthreads();
+    // ---- per-digit: exclusive offsets across warps, tile count, look-back
+    uint32_t tile_count = 0;
+    {
+        const unsigned d = tid;   // RS_BLOCK == RS_BINS
+        uint32_t sum = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) {
+            uint32_t t = s_warp_hist[w][d];
+            s_warp_hist[w][d] = sum;
+            sum += t;
+        }
+        tile_count = sum;
+        volatile uint32_t *st = status + (size_t)tile * RS_BINS + d;
+        if (tile == 0) *st = sum | RS_FLAG_INCLUSIVE; else *st = sum | RS_FLAG_PARTIAL;
+        s_bin_start[d] = sum;
+    }
+    __syncthreads();
+    // exclusive scan of the 256 tile counts (Hillis-Steele in shared memory)
+    {
+        uint32_t v = s_bin_start[tid];
+        for (int off = 1; off < RS_BINS; off <<= 1) {
+            uint32_t t = tid >= (unsigned)off ? s_bin_start[tid - off] : 0;
+            __syncthreads();
+            s_bin_start[tid] += t;
+            __syncthreads();
+        }
+        uint32_t incl = s_bin_start[tid];
+        __syncthreads();
+        s_bin_start[tid] = incl - v;
+    }
+    {
+        const unsigned d = tid;
+        uint32_t excl = 0;
+        if (tile > 0) {
+            int t = (int)tile - 1;
+            while (true) {
+                volatile uint32_t *pst = status + (size_t)t * RS_BINS + d;
+                uint32_t v = *pst;
+                while ((v & (RS_FLAG_PARTIAL | RS_FLAG_INCLUSIVE)) == 0) { __nanosleep(20); v = *pst; }
+                excl += v & RS_VALUE_MASK;
+                if (v & RS_FLAG_INCLUSIVE) break;
+                t--;
+            }
+            volatile uint32_t *st = status + (size_t)tile * RS_BINS + d;
+            *st = (excl + tile_count) | RS_FLAG_INCLUSIVE;
+        }
+        __syncthreads();   // s_bin_start final
+        s_global_base[d] = digit_offset[d] + excl - s_bin_start[d];
+    }
+    __syncthreads();
+    // ---- exchange through shared memory, then coalesced digit-contiguous stores
+    uint32_t pos[RS_ITEMS];
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; i++) {
+        uint32_t d = (uint32_t)(key[i] >> shift) & mask;
+        pos[i] = s_bin_start[d] + s_warp_hist[warp][d] + rank[i];
+        s_keys[pos[i]] = key[i];
+    }
+    __syncthreads();
+    size_t outp[RS_ITEMS];
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; i++) {
+        unsigned j = tid + i * RS_BLOCK;
+        K k = s_keys[j];
+        uint32_t d = (uint32_t)(k >> shift) & mask;
+        outp[i] = (size_t)s_global_base[d] + j;
+        if (outp[i] < n) keys_out[outp[i]] = k;
+    }
+    if (HAS_VALUES) {
+        __syncthreads();
+        uint32_t *s_vals = reinterpret_cast<uint32_t *>(s_keys);
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; i++) {
+            size_t idx = warp_base + (size_t)i * 32 + lane;
+            uint32_t v = idx < n ? vals_in[idx] : 0u;
+            s_vals[pos[i]] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; i++) {
+            unsigned j = tid + i * RS_BLOCK;
+            if (outp[i] < n) vals_out[outp[i]] = s_vals[j];
+        }
+    }
+}
+
+// Sorts n keys (and optional payloads) on bits [begin_bit, end_bit).  keys/vals and the *_tmp buffers
+// ping-pong; the sorted data ends in *keys_sorted / *vals_sorted (one of the two buffers).
+template <typename K>
+void radix_sort(K *keys, K *keys_tmp, uint32_t *vals, uint32_t *vals_tmp, size_t n, int begin_bit, int end_bit,
+                cudaStream_t stream, RadixTemp &tmp, K **keys_sorted, uint32_t **vals_sorted, int *launches = nullptr) {
+    *keys_sorted = keys;
+    if (vals_sorted) *vals_sorted = vals;
+    if (n <= 1) return;
+    CGX_REQUIRE(n < (size_t)RS_VALUE_MASK, "radix_sort: n=%zu too large for 30-bit look-back counters", n);
+    RadixPlan plan = make_radix_plan(begin_bit, end_bit);
+    size_t tiles = (n + RS_TILE - 1) / RS_TILE;
+    uint32_t *hist = tmp.hist.get<uint32_t>(RS_MAX_PASSES * RS_BINS);
+    uint32_t *status = tmp.status.get<uint32_t>(tiles * RS_BINS);
+    uint32_t *counters = tmp.counters.get<uint32_t>(RS_MAX_PASSES);
+    CUDA_CHECK(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * RS_MAX_PASSES * RS_BINS, stream));
+    CUDA_CHECK(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * RS_MAX_PASSES, stream));
+    unsigned hgrid = (unsigned)std::min<size_t>((n + RS_BLOCK * 8 - 1) / (RS_BLOCK * 8), (size_t)CGX_NUM_SMS * 8);
+    rs_histogram_kernel<K><<<hgrid, RS_BLOCK, 0, stream>>>(keys, n, plan, hist);
+    rs_scan_hist_kernel<<<plan.num_passes, RS_BINS, 0, stream>>>(hist);
+    if (launches) *launches += 2;
+    K *kin = keys, *kout = keys_tmp;
+    uint32_t *vin = vals, *vout = vals_tmp;
+    for (int p = 0; p < plan.num_passes; p++) {
+        CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(uint32_t) * tiles * RS_BINS, stream));
+        if (vals)
+            rs_onesweep_kernel<K, true><<<(unsigned)tiles, RS_BLOCK, 0, stream>>>(kin, kout, vin, vout, n, plan.shift[p], plan.bits[p],
+                                                                                 hist + p * RS_BINS, status, counters + p);
+        else
+            rs_onesweep_kernel<K, false><<<(unsigned)tiles, RS_BLOCK, 0, stream>>>(kin, kout, nullptr, nullptr, n, plan.shift[p], plan.bits[p],
+                                                                                  hist + p * RS_BINS, status, counters + p);
+        if (launches) *launches += 1;
+        std::swap(kin, kout);
+        std::swap(vin, vout);
+    }
+    CUDA_CHECK(cudaGetLastError());
+    *keys_sorted = kin;
+    if (vals_sorted) *vals_sorted = vin;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace cgx

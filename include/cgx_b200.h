@@ -1,0 +1,148 @@
+/* cgx_b200.h -- C ABI of the B200-native hierarchical grammar extractor (libcgx_b200.so).
+ *
+ * The reference (hohoCode/cgx) has no plugin / FFI surface: its only stable interface is the
+ * `strmatchcuda` executable (Main.c:28-61) and, internally, the C-to-CUDA call sequence of
+ * start() (Start.cu:488-629).  This header is that internal boundary re-drawn as a thin C ABI:
+ * plain pointers and sizes, opaque handle, no C++ / torch types.  Each entry point names the
+ * reference function(s) it replaces.
+ *
+ * Conventions: every function returns 0 on success, non-zero on failure (cgx_last_error() has the
+ * text).  Host pointers unless a name ends in _dev.  One context per GPU; a context is not
+ * thread-safe, different contexts are independent.  There is NO CPU fallback: every entry point
+ * fails if the CUDA device is unavailable.
+ */
+#ifndef CGX_B200_H
+#define CGX_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cgx_ctx cgx_ctx_t;
+
+/* ---- context --------------------------------------------------------------------------------- */
+/* replaces suffixArraySearchInit (SuffixArray.cu:769) / cudaSetDevice */
+int cgx_create(int device, cgx_ctx_t **out);
+void cgx_destroy(cgx_ctx_t *ctx);                     /* suffixArraySearchFinalize (:807), extractPairFinalize (ExtractPair.cu:2434) */
+const char *cgx_last_error(const cgx_ctx_t *ctx);
+int cgx_version(void);
+
+/* ---- index (one-time per corpus) ------------------------------------------------------------- */
+/* Replaces suffixArrayConstruct (SuffixArray.c:196, CPU DC3 + LCP tables), the H2D copies of
+ * suffixArraySearch (SuffixArray.cu:1396-1412) and preComputation (:1132-1340).
+ *   src   : n+3 ints, layout of initRefSet (Start.cu:240-380): ids >= 2, EOS = 1, trailer "1, V+2", 0 0 0
+ *   tgt   : m+3 ints, layout of initRefTargetSet (Start.cu:142-238)
+ *   RLP, L_tar, R_tar : layout of initAlignment (ExtractPair.cu:2639-2739)
+ * Builds the suffix array on the GPU (prefix doubling + onesweep radix sort) and the auxiliary
+ * position-sorted n-gram occurrence lists. */
+int cgx_index_build(cgx_ctx_t *ctx, const int32_t *src, int64_t n, const int32_t *tgt, int64_t m,
+                    const uint32_t *RLP, const uint8_t *L_tar, const uint8_t *R_tar);
+
+/* Replaces initWordPossibilityIntKey (ExtractPair.cu:2442-2554): f/e ids (-1 = NULL word), v1 feeds
+ * MaxLexEgivenF, v2 feeds MaxLexFgivenE.  Sorted on the GPU by (f, e). */
+int cgx_lex_load(cgx_ctx_t *ctx, const int32_t *f, const int32_t *e, const float *v1, const float *v2, int64_t count);
+
+typedef struct {
+    int64_t n, m;
+    int32_t sa_rounds;        /* prefix-doubling rounds executed */
+    int32_t sa_key_bits;      /* sorted key width */
+    int32_t sa_launches;
+    float sa_build_ms;        /* tokens on device -> sa[] on device (CUDA events) */
+    float aux_build_ms;       /* occurrence lists, token buckets, frequent tokens */
+    int64_t index_bytes;      /* resident HBM bytes of the index */
+} cgx_index_info_t;
+int cgx_index_info(const cgx_ctx_t *ctx, cgx_index_info_t *out);
+
+/* Suffix array only, device pointers in/out (bench: SA-build metric with inputs resident in HBM).
+ * str_dev: n+3 ints; sa_dev: n ints. */
+int cgx_sa_build_dev(cgx_ctx_t *ctx, const int32_t *str_dev, int64_t n, int32_t max_token, int32_t *sa_dev,
+                     int32_t *rounds_out, float *ms_out);
+
+/* Device-resident index arrays, for broadcasting a built index to peer GPUs (NCCL) and adopting it there. */
+typedef struct {
+    int64_t n, m, lex_count;
+    int32_t max_token;
+    int32_t freq_list[100];
+    void *str, *sa, *inv1, *inv2, *inv3, *tok_start, *RLP, *L_tar, *R_tar, *tgt, *freq_flag, *lex_key, *lex_v1, *lex_v2;
+} cgx_index_arrays_t;
+int cgx_index_export(cgx_ctx_t *ctx, cgx_index_arrays_t *out);            /* pointers stay owned by ctx */
+int cgx_index_alloc(cgx_ctx_t *ctx, const cgx_index_arrays_t *shape, cgx_index_arrays_t *out);  /* allocate empty arrays of that shape on this ctx */
+int cgx_index_commit(cgx_ctx_t *ctx);                                      /* mark the (filled) arrays as a built index */
+
+/* parity helpers: copy index arrays to the host */
+int cgx_index_copy_sa(cgx_ctx_t *ctx, int32_t *sa_out);                    /* n ints */
+int cgx_index_copy_inv(cgx_ctx_t *ctx, int which, int32_t *out);           /* which = 1..3, n ints */
+int cgx_index_copy_frequent(cgx_ctx_t *ctx, int32_t *out100);
+
+/* ---- one query batch: match + extract + score ------------------------------------------------- */
+/* Replaces suffixArraySearch (SuffixArray.cu:1342-2269) + ExtractPairs_Large_Data_Gappy
+ * (ExtractPair.cu:3215-4001) incl. the host aggregation createLexicon*Fast (ExtractPair.c:515-1276)
+ * and lexicalTaskMaxEF (ExtractPair.cu:2144).
+ *   qry_tok : T ids in the source vocabulary, -1 = OOV (constructQryIndex, Start.cu:50-132)
+ *   qry_off : Q+1 offsets into qry_tok
+ * Results stay in the context until the next cgx_extract / cgx_destroy. */
+int cgx_extract(cgx_ctx_t *ctx, const int32_t *qry_tok, const int32_t *qry_off, int32_t Q);
+
+typedef struct {
+    int32_t Q, T;
+    int32_t G;          /* distinct contiguous phrases (GenerateBlocks, ExtractPair.cu:2742) */
+    int32_t enu1, D1;   /* one-gap enumeration count / distinct patterns */
+    int64_t hits1;      /* one-gap corpus occurrences (oneGapLookUpSA) */
+    int32_t enu2, D2;
+    int64_t hits2;
+    int64_t samples;    /* sampled occurrences extracted */
+    int64_t n_ab, n_1gap, n_2gap;      /* rule records per array */
+    int32_t rules[3];   /* distinct rules: [0] ab, [1] Xab|abX|aXb, [2] XabX|aXbXc|XaXb|aXbX */
+    int32_t launches;   /* kernels launched for this batch */
+    float ms_total, ms_lookup, ms_enum, ms_join, ms_extract, ms_aggregate;   /* CUDA-event stage times */
+} cgx_batch_info_t;
+int cgx_batch_info(const cgx_ctx_t *ctx, cgx_batch_info_t *out);
+
+/* A distinct scored rule (red_dup_t, ComTypes.h:244-255).  `id` is the converted id of
+ * ExtractPair.c:723-729 / :999-1006 within its array (kind). */
+typedef struct {
+    int32_t id;
+    int32_t tgt_start;     /* representative target span: start in the target text ... */
+    uint8_t end;           /* ... and inclusive length-1 */
+    uint8_t gap1, gap1_1;  /* target gap 1 as offsets from tgt_start (255 = none) */
+    uint8_t gap2, gap2_1;
+    uint8_t pad[3];
+    int32_t f;             /* extracted pairs with this source id   -> IsSingletonF  */
+    int32_t fs;            /* all_suffix_fsample (capped at 300)     -> SampleCountF  */
+    int32_t pc;            /* paircount                              -> CountEF, EgivenFCoherent, IsSingletonFE */
+    float max_lex_f_given_e, max_lex_e_given_f;
+} cgx_rule_t;
+
+/* Host views of the batch results (valid until the next cgx_extract):
+ *   phrase_id : T*5 ints, id of the contiguous phrase q[t..t+len) for len = 1..5, -1 when absent
+ *   phrases   : G x {sa_up, sa_down, len, corpus_pos}      (saind_t, ComTypes.h:342)
+ *   pat1      : D1 x {a_pos, ls, b_pos, le, hit_start, hit_count, marker_pair(-1|0..9999), fs_extra}
+ *   pat2      : D2 x {pat1_id, c_token, hit_start, hit_count}
+ *   q1_off/q1_ids, q2_off/q2_ids : per-query lists of one-gap / two-gap pattern ids (ascending id)
+ *   rules[k], n_rules[k], and per converted id the [first,last] rule range (updown, -1 when empty) */
+typedef struct {
+    int32_t Q, T, G, D1, D2;
+    const int32_t *phrase_id;
+    const int32_t *phrases;
+    const int32_t *pat1;
+    const int32_t *pat2;
+    const int32_t *q1_off, *q1_ids, *q2_off, *q2_ids;
+    const cgx_rule_t *rules[3];
+    int32_t n_rules[3];
+    const int32_t *updown[3];
+    int32_t n_ids[3];
+} cgx_result_t;
+int cgx_result(cgx_ctx_t *ctx, cgx_result_t *out);
+
+/* parity helpers (tests): intermediate arrays of the last batch, copied to the host.
+ *   what = "longest" (T ints, capped at 5), "intervals" (T*5*2 ints), "hits1" (hits1 x 3: id,pos,len),
+ *          "hits2" (hits2 x 4), "rec_ab"/"rec_1"/"rec_2" (7 ints per record, converted ids)
+ * Returns the number of int32 written (<= cap) or a negative error. */
+int64_t cgx_debug_fetch(cgx_ctx_t *ctx, const char *what, int32_t *out, int64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
