@@ -1,0 +1,124 @@
+/* cgx-b200 host: the driver behind strmatchcuda -- load, index, match + extract per query batch, write.
+ * Replaces start() (Start.cu:488-629).  Queries are independent, so they are cut
+ * into batches and, with n_gpus > 1, the batches are dealt round-robin to the GPUs of the box; the index
+ * is built once on GPU 0 and broadcast to the peers over NVLink (cgx_index_broadcast, NCCL). */
+#define _GNU_SOURCE
+#include "cgx_host.h"
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+static double now_s(void) {
+    struct timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
+}
+
+typedef struct {
+    cgx_ctx_t *ctx;
+    const cgxh_options_t *opt;
+    const cgxh_queries_t *qry;
+    const cgxh_side_t *src, *tgt;
+    int gpu, n_gpus, batch;
+    double t_gpu, t_write;
+    int64_t rules, launches;
+    int rc;
+} worker_t;
+
+static void *worker_main(void *arg) {
+    worker_t *w = (worker_t *)arg;
+    const cgxh_queries_t *q = w->qry;
+    int32_t n_batches = (q->Q + w->batch - 1) / w->batch;
+    for (int32_t bi = w->gpu; bi < n_batches; bi += w->n_gpus) {
+        int32_t q0 = bi * w->batch, q1 = q0 + w->batch > q->Q ? q->Q : q0 + w->batch;
+        int32_t nq = q1 - q0, base = q->off[q0];
+        int32_t *off = (int32_t *)malloc(sizeof(int32_t) * ((size_t)nq + 1));
+        for (int32_t i = 0; i <= nq; i++) off[i] = q->off[q0 + i] - base;
+        double t0 = now_s();
+        if (cgx_extract(w->ctx, q->tok + base, off, nq)) { fprintf(stderr, "cgx_extract: %s\n", cgx_last_error(w->ctx)); w->rc = 1; free(off); return NULL; }
+        cgx_result_t res;
+        cgx_result(w->ctx, &res);
+        cgx_batch_info_t bi_info;
+        cgx_batch_info(w->ctx, &bi_info);
+        double t1 = now_s();
+        if (cgxh_write_grammars(w->opt->destinationDirectory, &res, off, q0, w->src, w->tgt, w->opt->writer_threads)) { w->rc = 1; free(off); return NULL; }
+        double t2 = now_s();
+        w->t_gpu += t1 - t0; w->t_write += t2 - t1;
+        w->rules += (int64_t)res.n_rules[0] + res.n_rules[1] + res.n_rules[2];
+        w->launches += bi_info.launches;
+        if (!w->opt->quiet)
+            fprintf(stderr, "[gpu %d] queries %d..%d: phrases %d, aXb patterns %d (%lld hits), aXbXc patterns %d (%lld hits), rules %d/%d/%d, device %.3f ms\n",
+                    w->gpu, q0, q1 - 1, bi_info.G, bi_info.D1, (long long)bi_info.hits1, bi_info.D2, (long long)bi_info.hits2, bi_info.rules[0],
+                    bi_info.rules[1], bi_info.rules[2], bi_info.ms_total);
+        free(off);
+    }
+    return NULL;
+}
+
+int cgxh_run(const cgxh_options_t *opt) {
+    cgxh_side_t src, tgt;
+    cgxh_align_t al;
+    cgxh_lex_t lex;
+    cgxh_queries_t qry;
+    double t0 = now_s();
+    fprintf(stderr, "\nLoading the reference\n");
+    if (cgxh_corpus_load(opt->reffile, 1, &src)) return 1;
+    fprintf(stderr, "Reference toklen number is %lld HASH_COUNT %d\n", (long long)src.n, cgxh_vocab_size(src.vocab) - 2);
+    if (cgxh_corpus_load(opt->reftargetfile, 0, &tgt)) return 1;
+    fprintf(stderr, "Target Reference toklen number is %lld HASH_COUNT TARGET %d\n", (long long)tgt.n, cgxh_vocab_size(tgt.vocab) - 2);
+    if (cgxh_lex_load(opt->wordscdec, &src, &tgt, &lex)) return 1;
+    fprintf(stderr, "Lex File Word Possibility COUNTER: %lld\n", (long long)lex.count);
+    if (cgxh_queries_load(opt->qryfile, &src, &qry)) return 1;
+    fprintf(stderr, "\nMax length of queries is %d\n", qry.max_len);
+    if (cgxh_alignment_load(opt->align, &src, &tgt, &al)) return 1;
+    double t1 = now_s();
+
+    int n_gpus = opt->n_gpus > 0 ? opt->n_gpus : 1;
+    cgx_ctx_t **ctx = (cgx_ctx_t **)calloc((size_t)n_gpus, sizeof(cgx_ctx_t *));
+    for (int g = 0; g < n_gpus; g++)
+        if (cgx_create(g, &ctx[g])) { fprintf(stderr, "cgx_create(%d): %s\n", g, cgx_last_error(NULL)); return 1; }
+    if (cgx_index_build(ctx[0], src.tok, src.n, tgt.tok, tgt.n, al.RLP, al.L_tar, al.R_tar)) { fprintf(stderr, "cgx_index_build: %s\n", cgx_last_error(ctx[0])); return 1; }
+    if (cgx_lex_load(ctx[0], lex.f, lex.e, lex.v1, lex.v2, lex.count)) { fprintf(stderr, "cgx_lex_load: %s\n", cgx_last_error(ctx[0])); return 1; }
+    cgx_index_info_t ii;
+    cgx_index_info(ctx[0], &ii);
+    fprintf(stderr, "SA Construction %.4f sec (GPU prefix doubling, %d rounds, %d-bit keys); auxiliary index %.4f sec; %.1f MB resident\n",
+            ii.sa_build_ms / 1e3, ii.sa_rounds, ii.sa_key_bits, ii.aux_build_ms / 1e3, (double)ii.index_bytes / 1048576.0);
+    if (n_gpus > 1 && cgx_index_broadcast(ctx, n_gpus)) { fprintf(stderr, "cgx_index_broadcast: %s\n", cgx_last_error(ctx[0])); return 1; }
+    double t2 = now_s();
+
+    fprintf(stderr, "Start Extract Pair\n");
+    int batch = opt->batch_queries > 0 ? opt->batch_queries : (qry.Q > 0 ? (qry.Q + n_gpus - 1) / n_gpus : 1);
+    worker_t *w = (worker_t *)calloc((size_t)n_gpus, sizeof(worker_t));
+    pthread_t *th = (pthread_t *)calloc((size_t)n_gpus, sizeof(pthread_t));
+    for (int g = 0; g < n_gpus; g++) {
+        w[g].ctx = ctx[g]; w[g].opt = opt; w[g].qry = &qry; w[g].src = &src; w[g].tgt = &tgt; w[g].gpu = g; w[g].n_gpus = n_gpus; w[g].batch = batch;
+        if (n_gpus == 1) worker_main(&w[g]); else pthread_create(&th[g], NULL, worker_main, &w[g]);
+    }
+    int rc = 0;
+    double t_gpu = 0, t_write = 0;
+    int64_t rules = 0;
+    for (int g = 0; g < n_gpus; g++) {
+        if (n_gpus > 1) pthread_join(th[g], NULL);
+        rc |= w[g].rc;
+        if (w[g].t_gpu > t_gpu) t_gpu = w[g].t_gpu;
+        if (w[g].t_write > t_write) t_write = w[g].t_write;
+        rules += w[g].rules;
+    }
+    double t3 = now_s();
+    fprintf(stderr, "Start Printing Gappy Phrases...\n");   /* the reference's completion marker (README.md:76-79) */
+    fprintf(stderr, "loading %.3f s, index %.3f s, match+extract %.3f s (max over %d GPU%s), grammar writing %.3f s, total %.3f s; %lld rules; %.1f query sentences/s\n",
+            t1 - t0, t2 - t1, t_gpu, n_gpus, n_gpus > 1 ? "s" : "", t_write, t3 - t0, (long long)rules, qry.Q / (t3 - t2 > 0 ? t3 - t2 : 1e-9));
+    if (opt->timefile) {
+        FILE *fh = fopen(opt->timefile, "a");
+        if (fh) {
+            fprintf(fh, "total: %f , load: %f , index: %f , extract: %f , write: %f , gpus: %d , queries: %d\n", t3 - t0, t1 - t0, t2 - t1, t_gpu, t_write, n_gpus, qry.Q);
+            fclose(fh);
+        }
+    }
+    for (int g = 0; g < n_gpus; g++) cgx_destroy(ctx[g]);
+    free(ctx); free(w); free(th);
+    cgxh_side_free(&src); cgxh_side_free(&tgt); cgxh_align_free(&al); cgxh_lex_free(&lex); cgxh_queries_free(&qry);
+    return rc;
+}

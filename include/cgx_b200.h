@@ -71,6 +71,13 @@ int cgx_index_export(cgx_ctx_t *ctx, cgx_index_arrays_t *out);            /* poi
 int cgx_index_alloc(cgx_ctx_t *ctx, const cgx_index_arrays_t *shape, cgx_index_arrays_t *out);  /* allocate empty arrays of that shape on this ctx */
 int cgx_index_commit(cgx_ctx_t *ctx);                                      /* mark the (filled) arrays as a built index */
 
+/* Single-process multi-GPU: broadcast the index built on ctxs[0] to ctxs[1..n-1] with ncclBroadcast over
+ * NVLink / NVSwitch (one communicator per device, ncclCommInitAll).  New relative to the reference, which
+ * is single-GPU; queries are then sharded across the contexts by the caller (no steady-state collective).
+ * NCCL is dlopen()ed at call time.  Multi-process callers (torchrun) broadcast the exported arrays with
+ * their own communicator instead (cgx_index_export / cgx_index_alloc / cgx_index_commit). */
+int cgx_index_broadcast(cgx_ctx_t **ctxs, int n);
+
 /* parity helpers: copy index arrays to the host */
 int cgx_index_copy_sa(cgx_ctx_t *ctx, int32_t *sa_out);                    /* n ints */
 int cgx_index_copy_inv(cgx_ctx_t *ctx, int which, int32_t *out);           /* which = 1..3, n ints */
