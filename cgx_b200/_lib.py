@@ -20,11 +20,11 @@ class IndexInfo(C.Structure):
 
 class IndexArrays(C.Structure):
     _fields_ = [("n", C.c_int64), ("m", C.c_int64), ("lex_count", C.c_int64), ("max_token", C.c_int32), ("freq_list", C.c_int32 * 100)] + \
-               [(k, C.c_void_p) for k in ("str", "sa", "inv1", "inv2", "inv3", "tok_start", "RLP", "L_tar", "R_tar", "tgt", "freq_flag",
+               [(k, C.c_void_p) for k in ("str", "sa", "inv1", "inv2", "inv3", "tok_start", "RLP", "L_tar", "R_tar", "tgt", "freq_flag", "gapw",
                                          "lex_key", "lex_v1", "lex_v2")]
 
     ARRAYS = (("str", 4, "n3"), ("sa", 4, "n"), ("inv1", 4, "n"), ("inv2", 4, "n"), ("inv3", 4, "n"), ("tok_start", 4, "nt"), ("RLP", 4, "n"),
-              ("L_tar", 1, "m"), ("R_tar", 1, "m"), ("tgt", 4, "m3"), ("freq_flag", 1, "nt"), ("lex_key", 8, "lex1"), ("lex_v1", 4, "lex1"),
+              ("L_tar", 1, "m"), ("R_tar", 1, "m"), ("tgt", 4, "m3"), ("freq_flag", 1, "nt"), ("gapw", 4, "n"), ("lex_key", 8, "lex1"), ("lex_v1", 4, "lex1"),
               ("lex_v2", 4, "lex1"))
 
     def nbytes(self, name):
@@ -91,6 +91,11 @@ def load():
     L.cgx_index_copy_inv.argtypes = [vp, C.c_int, i32p]
     L.cgx_index_copy_frequent.argtypes = [vp, i32p]
     L.cgx_extract.argtypes = [vp, i32p, i32p, C.c_int32]
+    L.cgx_extract_dev.argtypes = [vp, vp, vp, vp, C.c_int32, C.c_int32]
+    L.cgx_profile_enable.argtypes = [vp, C.c_int]
+    L.cgx_profile_report.argtypes = [vp]
+    L.cgx_profile_report.restype = C.c_char_p
+    L.cgx_index_broadcast.argtypes = [C.POINTER(vp), C.c_int]
     L.cgx_batch_info.argtypes = [vp, C.POINTER(BatchInfo)]
     L.cgx_result.argtypes = [vp, C.POINTER(Result)]
     L.cgx_debug_fetch.argtypes = [vp, C.c_char_p, i32p, C.c_int64]
@@ -101,4 +106,5 @@ def load():
 
 EXPORTED_SYMBOLS = ("cgx_version", "cgx_create", "cgx_destroy", "cgx_last_error", "cgx_index_build", "cgx_lex_load", "cgx_index_info",
                     "cgx_sa_build_dev", "cgx_index_export", "cgx_index_alloc", "cgx_index_commit", "cgx_index_copy_sa", "cgx_index_copy_inv",
-                    "cgx_index_copy_frequent", "cgx_extract", "cgx_batch_info", "cgx_result", "cgx_debug_fetch")
+                    "cgx_index_copy_frequent", "cgx_extract", "cgx_extract_dev", "cgx_profile_enable", "cgx_profile_report",
+                    "cgx_index_broadcast", "cgx_batch_info", "cgx_result", "cgx_debug_fetch")

@@ -19,6 +19,7 @@ using namespace cgx;
     }
 
 static thread_local std::string g_create_err;
+namespace cgx { thread_local Prof *g_prof = nullptr; }
 
 extern "C" int cgx_version(void) { return 100; }
 
@@ -52,7 +53,7 @@ extern "C" void cgx_destroy(cgx_ctx_t *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     Index &ix = c->ix;
-    DevBuf *ib[] = {&ix.str, &ix.sa, &ix.inv[0], &ix.inv[1], &ix.inv[2], &ix.tok_start, &ix.RLP, &ix.L_tar, &ix.R_tar, &ix.tgt, &ix.freq_flag,
+    DevBuf *ib[] = {&ix.str, &ix.sa, &ix.inv[0], &ix.inv[1], &ix.inv[2], &ix.tok_start, &ix.RLP, &ix.L_tar, &ix.R_tar, &ix.tgt, &ix.freq_flag, &ix.gapw,
                     &ix.lex_key, &ix.lex_v1, &ix.lex_v2};
     for (auto *b : ib) b->release();
     c->ws.release();
@@ -67,6 +68,10 @@ extern "C" void cgx_destroy(cgx_ctx_t *c) {
     for (int k = 0; k < 3; k++) { b.slot_off[k].release(); b.rec[k].release(); b.rec_sorted[k].release(); b.rules[k].release(); b.updown[k].release(); b.id_count[k].release(); }
     for (auto &l : b.scan.level) l.release();
     if (b.h_pinned) cudaFreeHost(b.h_pinned);
+    PinnedBuf *pb[] = {&b.h_phrase_id, &b.h_phrases, &b.h_pat1, &b.h_pat2, &b.h_q1_off, &b.h_q1_ids, &b.h_q2_off, &b.h_q2_ids};
+    for (auto *x : pb) x->release();
+    for (int k = 0; k < 3; k++) { b.h_rules[k].release(); b.h_updown[k].release(); }
+    c->prof.destroy();
     for (auto &ev : b.ev) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -87,6 +92,8 @@ static void build_index_device(cgx_ctx *c) {
     Index &ix = c->ix;
     cudaEvent_t e0, e1, e2;
     CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1)); CUDA_CHECK(cudaEventCreate(&e2));
+    c->prof.stream = c->stream;
+    g_prof = &c->prof;
     CUDA_CHECK(cudaEventRecord(e0, c->stream));
     build_suffix_array(ix.str.ptr<int32_t>(), ix.n, ix.maxtok, ix.sa.get<int32_t>(ix.n), c->ws, c->stream, &ix.sa_stats);
     CUDA_CHECK(cudaEventRecord(e1, c->stream));
@@ -94,6 +101,8 @@ static void build_index_device(cgx_ctx *c) {
     build_index_aux(ix, c->ws, c->stream, &launches);
     CUDA_CHECK(cudaEventRecord(e2, c->stream));
     CUDA_CHECK(cudaEventSynchronize(e2));
+    c->prof.resolve();
+    g_prof = nullptr;
     CUDA_CHECK(cudaEventElapsedTime(&ix.sa_stats.ms, e0, e1));
     CUDA_CHECK(cudaEventElapsedTime(&c->aux_ms, e1, e2));
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
@@ -195,7 +204,7 @@ extern "C" int cgx_index_info(const cgx_ctx_t *c, cgx_index_info_t *out) {
     out->sa_rounds = ix.sa_stats.rounds; out->sa_key_bits = ix.sa_stats.key_bits; out->sa_launches = ix.sa_stats.launches;
     out->sa_build_ms = ix.sa_stats.ms; out->aux_build_ms = c->aux_ms;
     out->index_bytes = (int64_t)(ix.str.cap + ix.sa.cap + ix.inv[0].cap + ix.inv[1].cap + ix.inv[2].cap + ix.tok_start.cap + ix.RLP.cap + ix.L_tar.cap +
-                                 ix.R_tar.cap + ix.tgt.cap + ix.freq_flag.cap + ix.lex_key.cap + ix.lex_v1.cap + ix.lex_v2.cap);
+                                 ix.R_tar.cap + ix.tgt.cap + ix.freq_flag.cap + ix.gapw.cap + ix.lex_key.cap + ix.lex_v1.cap + ix.lex_v2.cap);
     return 0;
 }
 
@@ -206,7 +215,7 @@ extern "C" int cgx_index_export(cgx_ctx_t *c, cgx_index_arrays_t *o) {
         o->n = (int64_t)ix.n; o->m = (int64_t)ix.m; o->lex_count = (int64_t)ix.lex_count; o->max_token = ix.maxtok;
         memcpy(o->freq_list, ix.freq_list, sizeof(ix.freq_list));
         o->str = ix.str.p; o->sa = ix.sa.p; o->inv1 = ix.inv[0].p; o->inv2 = ix.inv[1].p; o->inv3 = ix.inv[2].p; o->tok_start = ix.tok_start.p;
-        o->RLP = ix.RLP.p; o->L_tar = ix.L_tar.p; o->R_tar = ix.R_tar.p; o->tgt = ix.tgt.p; o->freq_flag = ix.freq_flag.p;
+        o->RLP = ix.RLP.p; o->L_tar = ix.L_tar.p; o->R_tar = ix.R_tar.p; o->tgt = ix.tgt.p; o->freq_flag = ix.freq_flag.p; o->gapw = ix.gapw.p;
         o->lex_key = ix.lex_key.p; o->lex_v1 = ix.lex_v1.p; o->lex_v2 = ix.lex_v2.p;
     });
 }
@@ -222,12 +231,12 @@ extern "C" int cgx_index_alloc(cgx_ctx_t *c, const cgx_index_arrays_t *s, cgx_in
         ix.str.get<int32_t>(ix.n + 3); ix.sa.get<int32_t>(ix.n);
         for (int k = 0; k < 3; k++) ix.inv[k].get<int32_t>(ix.n);
         ix.tok_start.get<int32_t>(nt); ix.RLP.get<uint32_t>(ix.n); ix.L_tar.get<uint8_t>(ix.m); ix.R_tar.get<uint8_t>(ix.m);
-        ix.tgt.get<int32_t>(ix.m + 3); ix.freq_flag.get<uint8_t>(nt);
+        ix.tgt.get<int32_t>(ix.m + 3); ix.freq_flag.get<uint8_t>(nt); ix.gapw.get<uint32_t>(ix.n);
         ix.lex_key.get<uint64_t>(ix.lex_count + 1); ix.lex_v1.get<float>(ix.lex_count + 1); ix.lex_v2.get<float>(ix.lex_count + 1);
         ix.built = false;
         *o = *s;
         o->str = ix.str.p; o->sa = ix.sa.p; o->inv1 = ix.inv[0].p; o->inv2 = ix.inv[1].p; o->inv3 = ix.inv[2].p; o->tok_start = ix.tok_start.p;
-        o->RLP = ix.RLP.p; o->L_tar = ix.L_tar.p; o->R_tar = ix.R_tar.p; o->tgt = ix.tgt.p; o->freq_flag = ix.freq_flag.p;
+        o->RLP = ix.RLP.p; o->L_tar = ix.L_tar.p; o->R_tar = ix.R_tar.p; o->tgt = ix.tgt.p; o->freq_flag = ix.freq_flag.p; o->gapw = ix.gapw.p;
         o->lex_key = ix.lex_key.p; o->lex_v1 = ix.lex_v1.p; o->lex_v2 = ix.lex_v2.p;
     });
 }
@@ -261,13 +270,67 @@ extern "C" int cgx_index_copy_frequent(cgx_ctx_t *c, int32_t *out) {
 // ------------------------------------------------------------------------------------------------
 // query batch
 // ------------------------------------------------------------------------------------------------
+
+// Runs the stages on queries already resident in b.q_tok / b.q_off / b.tok2q.
+static void run_batch(cgx_ctx *c, int32_t Q, int32_t T, bool fetch) {
+    Batch &b = c->batch;
+    const Index &ix = c->ix;
+    cudaStream_t s = c->stream;
+    b.fetch_results = fetch;
+    c->prof.stream = s;
+    g_prof = &c->prof;
+    stage_lookup(ix, b, s);
+    CUDA_CHECK(cudaEventRecord(b.ev[1], s));
+    stage_phrases(ix, b, s);
+    stage_onegap_enumerate(ix, b, s);
+    CUDA_CHECK(cudaEventRecord(b.ev[2], s));
+    stage_onegap_join(ix, b, s);
+    CUDA_CHECK(cudaEventRecord(b.ev[3], s));
+    stage_twogap_enumerate(ix, b, s);
+    CUDA_CHECK(cudaEventRecord(b.ev[4], s));
+    stage_twogap_join(ix, b, s);
+    CUDA_CHECK(cudaEventRecord(b.ev[5], s));
+    stage_extract(ix, b, s);
+    CUDA_CHECK(cudaEventRecord(b.ev[6], s));
+    stage_aggregate(ix, b, s);
+    if (fetch) {   // pattern tables and phrase ids to the (pinned) host mirrors
+        int32_t *hp = b.h_phrase_id.get<int32_t>((size_t)T * CGX_LONGEST_SRC + 1);
+        int32_t *hph = b.h_phrases.get<int32_t>((size_t)b.G * 4 + 1);
+        int32_t *h1 = b.h_pat1.get<int32_t>((size_t)b.D1 * 8 + 1);
+        int32_t *h2 = b.h_pat2.get<int32_t>((size_t)b.D2 * 4 + 1);
+        if (T) CUDA_CHECK(cudaMemcpyAsync(hp, b.phrase_id.p, sizeof(int32_t) * (size_t)T * CGX_LONGEST_SRC, cudaMemcpyDeviceToHost, s));
+        if (b.G) CUDA_CHECK(cudaMemcpyAsync(hph, b.phrases.p, sizeof(int32_t) * (size_t)b.G * 4, cudaMemcpyDeviceToHost, s));
+        if (b.D1) CUDA_CHECK(cudaMemcpyAsync(h1, b.pat1.p, sizeof(int32_t) * (size_t)b.D1 * 8, cudaMemcpyDeviceToHost, s));
+        if (b.D2) CUDA_CHECK(cudaMemcpyAsync(h2, b.pat2.p, sizeof(int32_t) * (size_t)b.D2 * 4, cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_CHECK(cudaEventRecord(b.ev[7], s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    c->prof.resolve();
+    g_prof = nullptr;
+    cgx_batch_info_t &in = b.info;
+    in.Q = Q; in.T = T; in.G = b.G; in.enu1 = b.enu1; in.D1 = b.D1; in.hits1 = b.hits1; in.enu2 = b.enu2; in.D2 = b.D2; in.hits2 = b.hits2;
+    in.samples = b.samples; in.n_ab = b.n_rec[0]; in.n_1gap = b.n_rec[1]; in.n_2gap = b.n_rec[2];
+    for (int k = 0; k < 3; k++) in.rules[k] = b.n_rules[k];
+    in.launches = b.launches;
+    float t1, t2, t3, t4;
+    CUDA_CHECK(cudaEventElapsedTime(&in.ms_total, b.ev[0], b.ev[7]));
+    CUDA_CHECK(cudaEventElapsedTime(&in.ms_lookup, b.ev[0], b.ev[1]));
+    CUDA_CHECK(cudaEventElapsedTime(&t1, b.ev[1], b.ev[2]));
+    CUDA_CHECK(cudaEventElapsedTime(&t2, b.ev[3], b.ev[4]));
+    in.ms_enum = t1 + t2;
+    CUDA_CHECK(cudaEventElapsedTime(&t3, b.ev[2], b.ev[3]));
+    CUDA_CHECK(cudaEventElapsedTime(&t4, b.ev[4], b.ev[5]));
+    in.ms_join = t3 + t4;
+    CUDA_CHECK(cudaEventElapsedTime(&in.ms_extract, b.ev[5], b.ev[6]));
+    CUDA_CHECK(cudaEventElapsedTime(&in.ms_aggregate, b.ev[6], b.ev[7]));
+}
+
 extern "C" int cgx_extract(cgx_ctx_t *c, const int32_t *qry_tok, const int32_t *qry_off, int32_t Q) {
     CGX_TRY(c, {
         CGX_REQUIRE(c && qry_off && Q >= 0, "bad argument");
         CGX_REQUIRE(c->ix.built, "index not built");
         CUDA_CHECK(cudaSetDevice(c->device));
         Batch &b = c->batch;
-        const Index &ix = c->ix;
         cudaStream_t s = c->stream;
         const int32_t T = qry_off[Q];
         CGX_REQUIRE(T == 0 || qry_tok, "null query tokens");
@@ -295,48 +358,51 @@ extern "C" int cgx_extract(cgx_ctx_t *c, const int32_t *qry_tok, const int32_t *
         if (T) CUDA_CHECK(cudaMemcpyAsync(d_tok, hp, sizeof(int32_t) * (size_t)T, cudaMemcpyHostToDevice, s));
         CUDA_CHECK(cudaMemcpyAsync(d_off, hp + T, sizeof(int32_t) * ((size_t)Q + 1), cudaMemcpyHostToDevice, s));
         if (T) CUDA_CHECK(cudaMemcpyAsync(d_t2q, t2q, sizeof(int32_t) * (size_t)T, cudaMemcpyHostToDevice, s));
-        stage_lookup(ix, b, s);
-        CUDA_CHECK(cudaEventRecord(b.ev[1], s));
-        stage_phrases(ix, b, s);
-        stage_onegap_enumerate(ix, b, s);
-        CUDA_CHECK(cudaEventRecord(b.ev[2], s));
-        stage_onegap_join(ix, b, s);
-        CUDA_CHECK(cudaEventRecord(b.ev[3], s));
-        stage_twogap_enumerate(ix, b, s);
-        CUDA_CHECK(cudaEventRecord(b.ev[4], s));
-        stage_twogap_join(ix, b, s);
-        CUDA_CHECK(cudaEventRecord(b.ev[5], s));
-        stage_extract(ix, b, s);
-        CUDA_CHECK(cudaEventRecord(b.ev[6], s));
-        stage_aggregate(ix, b, s);
-        // pattern tables and phrase ids to the host
-        b.h_phrase_id.resize((size_t)T * CGX_LONGEST_SRC);
-        b.h_phrases.resize((size_t)b.G * 4);
-        b.h_pat1.resize((size_t)b.D1 * 8);
-        b.h_pat2.resize((size_t)b.D2 * 4);
-        if (T) CUDA_CHECK(cudaMemcpyAsync(b.h_phrase_id.data(), b.phrase_id.p, sizeof(int32_t) * b.h_phrase_id.size(), cudaMemcpyDeviceToHost, s));
-        if (b.G) CUDA_CHECK(cudaMemcpyAsync(b.h_phrases.data(), b.phrases.p, sizeof(int32_t) * b.h_phrases.size(), cudaMemcpyDeviceToHost, s));
-        if (b.D1) CUDA_CHECK(cudaMemcpyAsync(b.h_pat1.data(), b.pat1.p, sizeof(int32_t) * b.h_pat1.size(), cudaMemcpyDeviceToHost, s));
-        if (b.D2) CUDA_CHECK(cudaMemcpyAsync(b.h_pat2.data(), b.pat2.p, sizeof(int32_t) * b.h_pat2.size(), cudaMemcpyDeviceToHost, s));
-        CUDA_CHECK(cudaEventRecord(b.ev[7], s));
-        CUDA_CHECK(cudaStreamSynchronize(s));
-        cgx_batch_info_t &in = b.info;
-        in.Q = Q; in.T = T; in.G = b.G; in.enu1 = b.enu1; in.D1 = b.D1; in.hits1 = b.hits1; in.enu2 = b.enu2; in.D2 = b.D2; in.hits2 = b.hits2;
-        in.samples = b.samples; in.n_ab = b.n_rec[0]; in.n_1gap = b.n_rec[1]; in.n_2gap = b.n_rec[2];
-        for (int k = 0; k < 3; k++) in.rules[k] = b.n_rules[k];
-        in.launches = b.launches;
-        float t1, t2, t3, t4;
-        CUDA_CHECK(cudaEventElapsedTime(&in.ms_total, b.ev[0], b.ev[7]));
-        CUDA_CHECK(cudaEventElapsedTime(&in.ms_lookup, b.ev[0], b.ev[1]));
-        CUDA_CHECK(cudaEventElapsedTime(&t1, b.ev[1], b.ev[2]));
-        CUDA_CHECK(cudaEventElapsedTime(&t2, b.ev[3], b.ev[4]));
-        in.ms_enum = t1 + t2;
-        CUDA_CHECK(cudaEventElapsedTime(&t3, b.ev[2], b.ev[3]));
-        CUDA_CHECK(cudaEventElapsedTime(&t4, b.ev[4], b.ev[5]));
-        in.ms_join = t3 + t4;
-        CUDA_CHECK(cudaEventElapsedTime(&in.ms_extract, b.ev[5], b.ev[6]));
-        CUDA_CHECK(cudaEventElapsedTime(&in.ms_aggregate, b.ev[6], b.ev[7]));
+        run_batch(c, Q, T, true);
     });
+}
+
+extern "C" int cgx_extract_dev(cgx_ctx_t *c, const int32_t *qry_tok_dev, const int32_t *qry_off_dev, const int32_t *tok2q_dev, int32_t Q, int32_t T) {
+    CGX_TRY(c, {
+        CGX_REQUIRE(c && qry_off_dev && Q >= 0 && T >= 0 && (T == 0 || (qry_tok_dev && tok2q_dev)), "bad argument");
+        CGX_REQUIRE(c->ix.built, "index not built");
+        CUDA_CHECK(cudaSetDevice(c->device));
+        Batch &b = c->batch;
+        cudaStream_t s = c->stream;
+        b.Q = Q; b.T = T; b.launches = 0;
+        memset(&b.info, 0, sizeof(b.info));
+        int32_t *d_tok = b.q_tok.get<int32_t>((size_t)T + 8);
+        int32_t *d_off = b.q_off.get<int32_t>((size_t)Q + 1);
+        int32_t *d_t2q = b.tok2q.get<int32_t>((size_t)T + 1);
+        CUDA_CHECK(cudaEventRecord(b.ev[0], s));
+        if (T) CUDA_CHECK(cudaMemcpyAsync(d_tok, qry_tok_dev, sizeof(int32_t) * (size_t)T, cudaMemcpyDeviceToDevice, s));
+        CUDA_CHECK(cudaMemcpyAsync(d_off, qry_off_dev, sizeof(int32_t) * ((size_t)Q + 1), cudaMemcpyDeviceToDevice, s));
+        if (T) CUDA_CHECK(cudaMemcpyAsync(d_t2q, tok2q_dev, sizeof(int32_t) * (size_t)T, cudaMemcpyDeviceToDevice, s));
+        run_batch(c, Q, T, false);
+    });
+}
+
+extern "C" int cgx_profile_enable(cgx_ctx_t *c, int on) {
+    if (!c) return 1;
+    c->prof.enabled = on != 0;
+    c->prof.reset();
+    return 0;
+}
+
+extern "C" const char *cgx_profile_report(cgx_ctx_t *c) {
+    if (!c) return "";
+    std::string j = "{";
+    bool first = true;
+    for (auto &kv : c->prof.table) {
+        char buf[512];
+        snprintf(buf, sizeof buf, "%s\"%s\": {\"launches\": %ld, \"ms\": %.6f, \"bytes\": %.0f}", first ? "" : ", ", kv.first.c_str(), kv.second.launches,
+                 kv.second.ms, kv.second.bytes);
+        j += buf;
+        first = false;
+    }
+    j += "}";
+    c->prof_json = j;
+    return c->prof_json.c_str();
 }
 
 extern "C" int cgx_batch_info(const cgx_ctx_t *c, cgx_batch_info_t *out) {
@@ -349,11 +415,12 @@ extern "C" int cgx_result(cgx_ctx_t *c, cgx_result_t *o) {
     if (!c || !o) return 1;
     Batch &b = c->batch;
     o->Q = b.Q; o->T = b.T; o->G = b.G; o->D1 = b.D1; o->D2 = b.D2;
-    o->phrase_id = b.h_phrase_id.data(); o->phrases = b.h_phrases.data(); o->pat1 = b.h_pat1.data(); o->pat2 = b.h_pat2.data();
-    o->q1_off = b.h_q1_off.data(); o->q1_ids = b.h_q1_ids.data(); o->q2_off = b.h_q2_off.data(); o->q2_ids = b.h_q2_ids.data();
+    if (!b.fetch_results) { c->err = "the last batch kept its results on the device (cgx_extract_dev)"; return 1; }
+    o->phrase_id = b.h_phrase_id.ptr<int32_t>(); o->phrases = b.h_phrases.ptr<int32_t>(); o->pat1 = b.h_pat1.ptr<int32_t>(); o->pat2 = b.h_pat2.ptr<int32_t>();
+    o->q1_off = b.h_q1_off.ptr<int32_t>(); o->q1_ids = b.h_q1_ids.ptr<int32_t>(); o->q2_off = b.h_q2_off.ptr<int32_t>(); o->q2_ids = b.h_q2_ids.ptr<int32_t>();
     for (int k = 0; k < 3; k++) {
-        o->rules[k] = b.h_rules[k].data(); o->n_rules[k] = b.n_rules[k];
-        o->updown[k] = b.h_updown[k].data(); o->n_ids[k] = b.n_ids[k];
+        o->rules[k] = b.h_rules[k].ptr<cgx_rule_t>(); o->n_rules[k] = b.n_rules[k];
+        o->updown[k] = b.h_updown[k].ptr<int32_t>(); o->n_ids[k] = b.n_ids[k];
     }
     return 0;
 }

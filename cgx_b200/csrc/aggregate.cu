@@ -15,6 +15,7 @@
 // Lexical weights: one thread per distinct rule, binary search in the (f,e)-sorted lexical table
 // (L2-resident: 16 B/entry), -log10 through the same lg2.approx path the reference's -use_fast_math build takes.
 #include "batch.h"
+#include "prof.h"
 
 namespace cgx {
 
@@ -209,8 +210,9 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
         const size_t N = (size_t)b.n_rec[kind];
         b.n_ids[kind] = nids[kind];
         b.n_rules[kind] = 0;
-        b.h_rules[kind].clear();
-        b.h_updown[kind].assign((size_t)2 * nids[kind], -1);
+        int32_t *h_ud = b.h_updown[kind].get<int32_t>((size_t)2 * nids[kind] + 2);
+        memset(h_ud, 0xff, sizeof(int32_t) * 2 * (size_t)nids[kind]);
+        b.h_rules[kind].get<cgx_rule_t>(1);
         if (N == 0 || nids[kind] == 0) continue;
         const RuleRec *rec = b.rec[kind].ptr<RuleRec>();
         uint64_t *hk = b.rec_keys.get<uint64_t>(N), *hk_tmp = b.rec_keys_tmp.get<uint64_t>(N);
@@ -223,7 +225,7 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
         uint64_t seed = 0x243f6a8885a308d3ULL;
         uint32_t R = 0;
         for (int attempt = 0; attempt < 8; attempt++, seed = seed * 6364136223846793005ULL + 1442695040888963407ULL) {
-            agg_hash_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(rec, N, ix.tgt.ptr<int32_t>(), seed, hk, idx);
+            PROF("agg_hash", (double)N * 28, (agg_hash_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(rec, N, ix.tgt.ptr<int32_t>(), seed, hk, idx)));
             CUDA_CHECK(cudaMemcpyAsync(hash_by_rec, hk, sizeof(uint64_t) * N, cudaMemcpyDeviceToDevice, stream));
             uint64_t *ks;
             uint32_t *is;
@@ -234,7 +236,7 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
             radix_sort<uint32_t>(idk, idk_tmp, is, other, N, 0, cgx_bits_for((uint64_t)nids[kind]), stream, b.radix, &ids_sorted, &is2, &b.launches);
             CUDA_CHECK(cudaMemsetAsync(id_count, 0, sizeof(uint32_t) * (size_t)nids[kind], stream));
             CUDA_CHECK(cudaMemsetAsync(collision, 0, sizeof(int), stream));
-            agg_flags_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(rec, is2, hash_by_rec, N, ix.tgt.ptr<int32_t>(), flags, id_count, collision);
+            PROF("agg_flags", (double)N * 48, (agg_flags_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(rec, is2, hash_by_rec, N, ix.tgt.ptr<int32_t>(), flags, id_count, collision)));
             exclusive_scan_u32(flags, flags, N, tot, stream, b.scan, 0, &b.launches);
             b.launches += 3;
             uint32_t hostv[16];
@@ -243,8 +245,8 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
             if (hostv[14] == 0) {
                 R = hostv[0];
                 cgx_rule_t *rules = b.rules[kind].get<cgx_rule_t>(R);
-                agg_rules_kernel<<<cgx_div_up(R, 128), 128, 0, stream>>>(a, kind, rec, is2, flags, N, R, id_count, ix.lex_key.ptr<uint64_t>(),
-                                                                       ix.lex_v1.ptr<float>(), ix.lex_v2.ptr<float>(), (int)ix.lex_count, rules);
+                PROF("agg_rules", (double)R * 36 + (double)N * 20, (agg_rules_kernel<<<cgx_div_up(R, 128), 128, 0, stream>>>(a, kind, rec, is2, flags, N, R, id_count, ix.lex_key.ptr<uint64_t>(),
+                                                                       ix.lex_v1.ptr<float>(), ix.lex_v2.ptr<float>(), (int)ix.lex_count, rules)));
                 CUDA_CHECK(cudaMemsetAsync(updown, 0xff, sizeof(int32_t) * 2 * (size_t)nids[kind], stream));
                 agg_updown_kernel<<<cgx_div_up(R, 256), 256, 0, stream>>>(rules, R, updown);
                 b.launches += 2;
@@ -253,10 +255,11 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
             CGX_REQUIRE(attempt < 7, "aggregation: hash collisions persisted over 8 seeds");
         }
         b.n_rules[kind] = (int32_t)R;
-        b.h_rules[kind].resize(R);
-        if (R) CUDA_CHECK(cudaMemcpyAsync(b.h_rules[kind].data(), b.rules[kind].ptr<cgx_rule_t>(), sizeof(cgx_rule_t) * R, cudaMemcpyDeviceToHost, stream));
-        CUDA_CHECK(cudaMemcpyAsync(b.h_updown[kind].data(), updown, sizeof(int32_t) * 2 * (size_t)nids[kind], cudaMemcpyDeviceToHost, stream));
-        CUDA_CHECK(cudaStreamSynchronize(stream));
+        if (b.fetch_results) {
+            cgx_rule_t *h_r = b.h_rules[kind].get<cgx_rule_t>((size_t)R + 1);
+            if (R) CUDA_CHECK(cudaMemcpyAsync(h_r, b.rules[kind].ptr<cgx_rule_t>(), sizeof(cgx_rule_t) * R, cudaMemcpyDeviceToHost, stream));
+            CUDA_CHECK(cudaMemcpyAsync(h_ud, updown, sizeof(int32_t) * 2 * (size_t)nids[kind], cudaMemcpyDeviceToHost, stream));
+        }
     }
     (void)read_u32;
 }

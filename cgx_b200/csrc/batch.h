@@ -68,9 +68,9 @@ struct Batch {
     int32_t *h_pinned = nullptr;
     size_t h_pinned_cap = 0;
     // host mirrors
-    std::vector<int32_t> h_phrase_id, h_phrases, h_pat1, h_pat2, h_q1_off, h_q1_ids, h_q2_off, h_q2_ids;
-    std::vector<cgx_rule_t> h_rules[3];
-    std::vector<int32_t> h_updown[3];
+    PinnedBuf h_phrase_id, h_phrases, h_pat1, h_pat2, h_q1_off, h_q1_ids, h_q2_off, h_q2_ids;
+    PinnedBuf h_rules[3], h_updown[3];
+    bool fetch_results = true;       // false: results stay on the device (device-resident throughput measurement)
     cgx_batch_info_t info;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int launches = 0;

@@ -62,7 +62,7 @@ extern "C" int cgx_index_broadcast(cgx_ctx_t **ctxs, int n) {
             {offsetof(cgx_index_arrays_t, inv3), (size_t)shape.n * 4}, {offsetof(cgx_index_arrays_t, tok_start), nt * 4},
             {offsetof(cgx_index_arrays_t, RLP), (size_t)shape.n * 4}, {offsetof(cgx_index_arrays_t, L_tar), (size_t)shape.m},
             {offsetof(cgx_index_arrays_t, R_tar), (size_t)shape.m}, {offsetof(cgx_index_arrays_t, tgt), (size_t)(shape.m + 3) * 4},
-            {offsetof(cgx_index_arrays_t, freq_flag), nt}, {offsetof(cgx_index_arrays_t, lex_key), (size_t)(shape.lex_count + 1) * 8},
+            {offsetof(cgx_index_arrays_t, freq_flag), nt}, {offsetof(cgx_index_arrays_t, gapw), (size_t)shape.n * 4}, {offsetof(cgx_index_arrays_t, lex_key), (size_t)(shape.lex_count + 1) * 8},
             {offsetof(cgx_index_arrays_t, lex_v1), (size_t)(shape.lex_count + 1) * 4}, {offsetof(cgx_index_arrays_t, lex_v2), (size_t)(shape.lex_count + 1) * 4}};
         for (const Item &it : items) {
             NCCL_CHECK(api, api.GroupStart());

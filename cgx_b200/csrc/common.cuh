@@ -76,6 +76,30 @@ struct DevBuf {
     }
 };
 
+// Grow-only pinned host buffer (result staging: D2H at full PCIe rate, reused across batches).
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    template <typename T>
+    T *get(size_t count) {
+        size_t bytes = count * sizeof(T);
+        if (bytes > cap) {
+            if (p) CUDA_CHECK(cudaFreeHost(p));
+            size_t want = bytes + bytes / 4 + 4096;
+            CUDA_CHECK(cudaMallocHost(&p, want));
+            cap = want;
+        }
+        return reinterpret_cast<T *>(p);
+    }
+    template <typename T>
+    T *ptr() const { return reinterpret_cast<T *>(p); }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
 static inline unsigned cgx_div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
 static inline int cgx_bits_for(uint64_t v) {   // number of bits needed to represent values in [0, v]

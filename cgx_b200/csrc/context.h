@@ -3,6 +3,7 @@
 #include "../../include/cgx_b200.h"
 #include "index.h"
 #include "batch.h"
+#include "prof.h"
 
 struct cgx_ctx {
     int device = 0;
@@ -12,4 +13,6 @@ struct cgx_ctx {
     cgx::SaWorkspace ws;
     cgx::Batch batch;
     float aux_ms = 0.f;
+    cgx::Prof prof;
+    std::string prof_json;
 };

@@ -16,6 +16,7 @@
 // are exact upper bounds (each occurrence emits at most one record of each rule shape), so there is no
 // overflow path.
 #include "batch.h"
+#include "prof.h"
 
 namespace cgx {
 
@@ -459,9 +460,9 @@ void stage_extract(const Index &ix, Batch &b, cudaStream_t stream) {
     // exact upper bounds: every sampled occurrence emits at most one record of each shape
     size_t cap0 = ns[0], cap1 = (size_t)2 * ns[0] + ns[1], cap2 = (size_t)ns[0] + ns[2] + (size_t)2 * ns[1];
     RuleRec *r0 = b.rec[0].get<RuleRec>(cap0 + 1), *r1 = b.rec[1].get<RuleRec>(cap1 + 1), *r2 = b.rec[2].get<RuleRec>(cap2 + 1);
-    if (ns[0]) extract_contig_kernel<<<cgx_div_up(ns[0], 128), 128, 0, stream>>>(x, b.phrases.ptr<int32_t>(), G, so0, ns[0], r0, r1, r2, ctr);
-    if (ns[2]) extract_twogap_kernel<<<cgx_div_up(ns[2], 128), 128, 0, stream>>>(x, b.pat2.ptr<Pat2>(), b.pat1.ptr<Pat1>(), D2, b.hits2_sorted.ptr<uint64_t>(), so2, ns[2], G, r2, ctr);
-    if (ns[1]) extract_onegap_kernel<<<cgx_div_up(ns[1], 128), 128, 0, stream>>>(x, b.pat1.ptr<Pat1>(), D1, b.hits1_sorted.ptr<uint64_t>(), so1, ns[1], G, D2, r1, r2, ctr);
+    if (ns[0]) PROF("extract_contig", 0.0, (extract_contig_kernel<<<cgx_div_up(ns[0], 128), 128, 0, stream>>>(x, b.phrases.ptr<int32_t>(), G, so0, ns[0], r0, r1, r2, ctr)));
+    if (ns[2]) PROF("extract_twogap", 0.0, (extract_twogap_kernel<<<cgx_div_up(ns[2], 128), 128, 0, stream>>>(x, b.pat2.ptr<Pat2>(), b.pat1.ptr<Pat1>(), D2, b.hits2_sorted.ptr<uint64_t>(), so2, ns[2], G, r2, ctr)));
+    if (ns[1]) PROF("extract_onegap", 0.0, (extract_onegap_kernel<<<cgx_div_up(ns[1], 128), 128, 0, stream>>>(x, b.pat1.ptr<Pat1>(), D1, b.hits1_sorted.ptr<uint64_t>(), so1, ns[1], G, D2, r1, r2, ctr)));
     b.launches += 3;
     unsigned long long nrec[3];
     CUDA_CHECK(cudaMemcpyAsync(nrec, ctr, sizeof(nrec), cudaMemcpyDeviceToHost, stream));

@@ -21,6 +21,48 @@ __global__ void ix_ngram_keys_kernel(const int32_t *__restrict__ str, size_t n, 
     vals[p] = (uint32_t)p;
 }
 
+// Gap-consistency words.  For a span [i, i+g-1] of source tokens (a gap of a hierarchical phrase):
+// GappyLook.cu:43-126 checkBoundaryGap = first and last token aligned; target span [min L, max R] of the
+// aligned tokens narrower than 15; and, over that target span, min L_tar / max R_tar map back exactly onto the
+// source span.  The source-side min/max is maintained incrementally while g grows.
+__global__ void ix_gap_words_kernel(const int32_t *__restrict__ str, const uint32_t *__restrict__ RLP, const uint8_t *__restrict__ L_tar,
+                                    const uint8_t *__restrict__ R_tar, size_t n, uint32_t *__restrict__ gapw) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t word = 0;
+    if (str[i] >= 2) {
+        int run = 1;
+        while (run < 15 && str[i + run] >= 2) run++;
+        word = (uint32_t)run << 16;
+        const uint32_t w0 = RLP[i];
+        const unsigned L0 = (w0 >> 24) & 0xFF, R0 = (w0 >> 16) & 0xFF;
+        if (L0 != 255 && R0 != 255) {
+            const int eos_prev = (int)i - (int)((w0 >> 8) & 0xFF) - 1;
+            const int tgt_base = eos_prev < 0 ? 0 : (int)RLP[eos_prev];
+            const int src_base = eos_prev + 1;
+            unsigned mn = L0, mx = R0;
+            const int gmax = run < 13 ? run : 13;
+            for (int g = 1; g <= gmax; g++) {
+                if (g > 1) {
+                    const uint32_t w = RLP[i + g - 1];
+                    const unsigned L = (w >> 24) & 0xFF, R = (w >> 16) & 0xFF;
+                    if (L == 255 || R == 255) continue;          // last token unaligned: this g fails, larger g may pass
+                    mn = min(mn, L); mx = max(mx, R);
+                }
+                if (mx - mn >= CGX_MAX_RULE_SPAN) break;           // the span only grows with g
+                unsigned tmn = 255, tmx = 0;
+                for (int k = tgt_base + (int)mn; k <= tgt_base + (int)mx; k++) {
+                    const unsigned L = L_tar[k], R = R_tar[k];
+                    if (L == 255 || R == 255) continue;
+                    tmn = min(tmn, L); tmx = max(tmx, R);
+                }
+                if (src_base + (int)tmn == (int)i && src_base + (int)tmx == (int)i + g - 1) word |= 1u << (g - 1);
+            }
+        }
+    }
+    gapw[i] = word;
+}
+
 // SuffixArray.cu:1148-1198: the PRECOMPUTECOUNT most frequent tokens (frequency descending, ties by
 // ascending id -- the intended order of compareUserTotal1 under a stable sort), stored ascending by id.
 static void pick_frequent(const std::vector<uint32_t> &counts, int32_t maxtok, int32_t *freq_list, std::vector<uint8_t> &flag) {
@@ -50,6 +92,9 @@ void build_index_aux(Index &ix, SaWorkspace &ws, cudaStream_t stream, int *launc
     pick_frequent(counts, ix.maxtok, ix.freq_list, flag);
     CUDA_CHECK(cudaMemcpyAsync(ix.freq_flag.get<uint8_t>(nt), flag.data(), nt, cudaMemcpyHostToDevice, stream));
     exclusive_scan_u32(ts, ts, nt, nullptr, stream, ws.scan, 0, launches);
+    ix_gap_words_kernel<<<cgx_div_up(n, 128), 128, 0, stream>>>(str, ix.RLP.ptr<uint32_t>(), ix.L_tar.ptr<uint8_t>(), ix.R_tar.ptr<uint8_t>(), n,
+                                                              ix.gapw.get<uint32_t>(n));
+    if (launches) *launches += 1;
     // position-sorted occurrence lists of every 1-, 2- and 3-gram
     const int tokbits = cgx_bits_for((uint64_t)ix.maxtok);
     uint64_t *keys = ws.keys.get<uint64_t>(n), *keys_tmp = ws.keys_tmp.get<uint64_t>(n);

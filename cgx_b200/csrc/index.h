@@ -37,12 +37,16 @@ void build_suffix_array(const int32_t *d_str, size_t n, int32_t maxtok, int32_t 
 //   RLP     uint32 [n]    (L<<24)|(R<<16)|(P<<8) per source token; target sentence offset at EOS
 //   L_tar/R_tar uint8 [m] min/max aligned source index per target token (255 = unaligned)
 //   tgt     int32 [m+3]   target text ids
-//   freq_flag uint8 [maxtok+2]  1 for the PRECOMPUTECOUNT most frequent source tokens
+//   gapw    uint32 [n]    gap-consistency word of every source position i (built once, on the GPU):
+//                         bit g-1 (g = 1..13) = checkBoundaryGap(i, i+g-1) holds (GappyLook.cu:43-126) and every
+//                         token of the span is >= 2; bits 16..19 = number of consecutive tokens >= 2 from i
+//                         (capped at 15).  Turns the per-candidate gap test of the joins into one word load.
+//   freq_flag uint8 [maxtok+2]  rank+1 among the PRECOMPUTECOUNT most frequent source tokens, else 0
 //   lex_key uint64 [L] / lex_v1, lex_v2 float [L]  lexical table sorted by (f+1)<<32 | (e+1)
 struct Index {
     size_t n = 0, m = 0;
     int32_t maxtok = 0;
-    DevBuf str, sa, inv[3], tok_start, RLP, L_tar, R_tar, tgt, freq_flag;
+    DevBuf str, sa, inv[3], tok_start, RLP, L_tar, R_tar, tgt, freq_flag, gapw;
     DevBuf lex_key, lex_v1, lex_v2;
     size_t lex_count = 0;
     int32_t freq_list[CGX_PRECOMP];

@@ -21,6 +21,7 @@
 // two frequent tokens, ExtractPair.c:900-908) is reproduced by counting, in the same join, the
 // candidates that fail only the alignment check.
 #include "batch.h"
+#include "prof.h"
 
 namespace cgx {
 
@@ -35,40 +36,14 @@ __device__ __forceinline__ int lower_bound_i32(const int32_t *__restrict__ a, in
 }
 
 // GappyLook.cu:43-126 checkBoundaryGap, preceded by the "every gap token >= 2" scan of the callers
-// (:341-351, :403-418).  Returns 0 = a token < 2 in the gap, 1 = alignment check failed, 2 = ok.
-__device__ __forceinline__ int gap_check(const int32_t *__restrict__ str, const uint32_t *__restrict__ RLP, const uint8_t *__restrict__ L_tar,
-                                         const uint8_t *__restrict__ R_tar, int start, int ender) {
-    unsigned min_L = 255, max_R = 0;
-    int sen_target_begin = -1, tempind = 0;
-    bool edge_unaligned = false;
-    for (int k = start; k <= ender; k++) {
-        if (__ldg(&str[k]) < 2) return 0;
-        uint32_t w = __ldg(&RLP[k]);
-        unsigned L = (w >> 24) & 0xFF, R = (w >> 16) & 0xFF;
-        bool un = (L == 255 || R == 255);
-        if (un) { if (k == start || k == ender) edge_unaligned = true; }
-        else {
-            if (k == start) {
-                tempind = k - (int)((w >> 8) & 0xFF) - 1;
-                sen_target_begin = tempind == -1 ? 0 : (int)__ldg(&RLP[tempind]);
-            }
-            min_L = min(min_L, L);
-            max_R = max(max_R, R);
-        }
-    }
-    if (edge_unaligned) return 1;
-    if (!(min_L <= max_R && max_R - min_L < CGX_MAX_RULE_SPAN)) return 1;
-    tempind++;
-    int ts = (int)min_L + sen_target_begin, te = (int)max_R + sen_target_begin;
-    unsigned mn = 255, mx = 0;
-    for (int k = ts; k <= te; k++) {
-        unsigned L = __ldg(&L_tar[k]), R = __ldg(&R_tar[k]);
-        if (L == 255 || R == 255) continue;
-        mn = min(mn, L);
-        mx = max(mx, R);
-    }
-    if (tempind + (int)mn != start || tempind + (int)mx != ender) return 1;
-    return 2;
+// (:341-351, :403-418), answered from the precomputed gap-consistency word of the span's first position
+// (index.cu ix_gap_words_kernel): one 4-byte load per candidate instead of a walk over the gap's RLP words and
+// its target window.  Returns 0 = a token < 2 in the gap, 1 = alignment check failed, 2 = ok.
+__device__ __forceinline__ int gap_check(const uint32_t *__restrict__ gapw, int start, int ender) {
+    const uint32_t w = __ldg(&gapw[start]);
+    const int g = ender - start + 1;
+    if ((int)((w >> 16) & 15u) < g) return 0;
+    return ((w >> (g - 1)) & 1u) ? 2 : 1;
 }
 
 __device__ __forceinline__ void append_hit(uint64_t key, unsigned long long *counter, uint64_t *out, size_t cap) {
@@ -102,8 +77,7 @@ __device__ __forceinline__ int find_owner(const uint32_t *__restrict__ off, int 
 __global__ void __launch_bounds__(JN_TILE) j1_join_kernel(const Pat1 *__restrict__ pat, const Pat1Dev *__restrict__ patd, int D1,
                                                           const uint32_t *__restrict__ tile_off, const int32_t *__restrict__ inv1,
                                                           const int32_t *__restrict__ inv2, const int32_t *__restrict__ inv3,
-                                                          const int32_t *__restrict__ str, const uint32_t *__restrict__ RLP,
-                                                          const uint8_t *__restrict__ L_tar, const uint8_t *__restrict__ R_tar,
+                                                          const uint32_t *__restrict__ gapw,
                                                           unsigned long long *__restrict__ counter, uint64_t *__restrict__ hits, size_t cap,
                                                           int32_t *__restrict__ missing) {
     __shared__ int s_d, s_olo, s_ohi, s_missing;
@@ -142,7 +116,7 @@ __global__ void __launch_bounds__(JN_TILE) j1_join_kernel(const Pat1 *__restrict
             int y = __ldg(&oth[j]);
             if (y > x + hi_off) break;
             int a_p = driveA ? x : y, b_p = driveA ? y : x;
-            int r = gap_check(str, RLP, L_tar, R_tar, a_p + ls, b_p - 1);
+            int r = gap_check(gapw, a_p + ls, b_p - 1);
             if (r == 2) {
                 uint64_t key = ((uint64_t)(uint32_t)d << 34) | ((uint64_t)(uint32_t)a_p << 4) | (uint64_t)(b_p + le - 1 - a_p);
                 append_hit(key, counter, hits, cap);
@@ -207,9 +181,8 @@ void stage_onegap_join(const Index &ix, Batch &b, cudaStream_t stream) {
         CUDA_CHECK(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), stream));
         CUDA_CHECK(cudaMemsetAsync(missing, 0, sizeof(int32_t) * (size_t)D1, stream));
         if (n_tiles)
-            j1_join_kernel<<<n_tiles, JN_TILE, 0, stream>>>(b.pat1.ptr<Pat1>(), b.pat1_dev.ptr<Pat1Dev>(), D1, tiles, ix.inv[0].ptr<int32_t>(),
-                                                           ix.inv[1].ptr<int32_t>(), ix.inv[2].ptr<int32_t>(), ix.str.ptr<int32_t>(), ix.RLP.ptr<uint32_t>(),
-                                                           ix.L_tar.ptr<uint8_t>(), ix.R_tar.ptr<uint8_t>(), ctr, hits, b.hit_cap, missing);
+            PROF("join_onegap", 0.0, (j1_join_kernel<<<n_tiles, JN_TILE, 0, stream>>>(b.pat1.ptr<Pat1>(), b.pat1_dev.ptr<Pat1Dev>(), D1, tiles, ix.inv[0].ptr<int32_t>(),
+                                                           ix.inv[1].ptr<int32_t>(), ix.inv[2].ptr<int32_t>(), ix.gapw.ptr<uint32_t>(), ctr, hits, b.hit_cap, missing)));
         b.launches += 2;
         unsigned long long H = read_u64(ctr, stream);
         if (H <= b.hit_cap) { b.hits1 = (int64_t)H; break; }
@@ -257,8 +230,7 @@ __device__ __forceinline__ int lower_bound_hitpos(const uint64_t *__restrict__ h
 __global__ void __launch_bounds__(JN_TILE) j2_join_kernel(const Pat2 *__restrict__ pat2, const Pat1 *__restrict__ pat1, int D2,
                                                           const uint32_t *__restrict__ tile_off, const uint64_t *__restrict__ hits1,
                                                           const int32_t *__restrict__ inv1, const int32_t *__restrict__ tok_start,
-                                                          const int32_t *__restrict__ str, const uint32_t *__restrict__ RLP,
-                                                          const uint8_t *__restrict__ L_tar, const uint8_t *__restrict__ R_tar,
+                                                          const uint32_t *__restrict__ gapw,
                                                           unsigned long long *__restrict__ counter, uint64_t *__restrict__ hits, size_t cap) {
     __shared__ int s_d, s_olo, s_ohi;
     if (threadIdx.x == 0) s_d = find_owner(tile_off, D2, blockIdx.x);
@@ -294,7 +266,7 @@ __global__ void __launch_bounds__(JN_TILE) j2_join_kernel(const Pat2 *__restrict
         for (; j < s_ohi; j++) {
             int c = __ldg(&C[j]);
             if (c > p + CGX_MAX_RULE_SPAN - 1) break;
-            if (gap_check(str, RLP, L_tar, R_tar, p + L + 1, c - 1) == 2)
+            if (gap_check(gapw, p + L + 1, c - 1) == 2)
                 append_hit(((uint64_t)(uint32_t)d << 38) | ((uint64_t)(uint32_t)p << 8) | ((uint64_t)L << 4) | (uint64_t)(c - p), counter, hits, cap);
         }
     } else {
@@ -305,7 +277,7 @@ __global__ void __launch_bounds__(JN_TILE) j2_join_kernel(const Pat2 *__restrict
             int p = (int)((hk >> 4) & 0x3fffffffu), L = (int)(hk & 15);
             if (p > c - 4) break;
             if (c < p + L + 2) continue;
-            if (gap_check(str, RLP, L_tar, R_tar, p + L + 1, c - 1) == 2)
+            if (gap_check(gapw, p + L + 1, c - 1) == 2)
                 append_hit(((uint64_t)(uint32_t)d << 38) | ((uint64_t)(uint32_t)p << 8) | ((uint64_t)L << 4) | (uint64_t)(c - p), counter, hits, cap);
         }
     }
@@ -328,9 +300,8 @@ void stage_twogap_join(const Index &ix, Batch &b, cudaStream_t stream) {
         uint64_t *hits = b.hit_keys.get<uint64_t>(b.hit_cap);
         CUDA_CHECK(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), stream));
         if (n_tiles)
-            j2_join_kernel<<<n_tiles, JN_TILE, 0, stream>>>(b.pat2.ptr<Pat2>(), b.pat1.ptr<Pat1>(), D2, tiles, b.hits1_sorted.ptr<uint64_t>(),
-                                                           ix.inv[0].ptr<int32_t>(), ix.tok_start.ptr<int32_t>(), ix.str.ptr<int32_t>(),
-                                                           ix.RLP.ptr<uint32_t>(), ix.L_tar.ptr<uint8_t>(), ix.R_tar.ptr<uint8_t>(), ctr, hits, b.hit_cap);
+            PROF("join_twogap", 0.0, (j2_join_kernel<<<n_tiles, JN_TILE, 0, stream>>>(b.pat2.ptr<Pat2>(), b.pat1.ptr<Pat1>(), D2, tiles, b.hits1_sorted.ptr<uint64_t>(),
+                                                           ix.inv[0].ptr<int32_t>(), ix.tok_start.ptr<int32_t>(), ix.gapw.ptr<uint32_t>(), ctr, hits, b.hit_cap)));
         b.launches += 2;
         unsigned long long H = read_u64(ctr, stream);
         if (H <= b.hit_cap) { b.hits2 = (int64_t)H; break; }

@@ -16,6 +16,7 @@
 // gathers), and a ballot picks the sub-range -- log33(range) dependent rounds instead of log2(range).
 // The first rounds of every warp hit the same top-of-tree probes, which therefore stay L1/L2 resident.
 #include "batch.h"
+#include "prof.h"
 
 namespace cgx {
 
@@ -88,9 +89,9 @@ void stage_lookup(const Index &ix, Batch &b, cudaStream_t stream) {
     int32_t *longest = b.longest.get<int32_t>((size_t)T + 1);
     int32_t *iv = b.iv.get<int32_t>((size_t)T * CGX_LONGEST_SRC * 2 + 2);
     if (T == 0) return;
-    lookup_kernel<<<cgx_div_up(T, LK_WARPS), LK_WARPS * 32, 0, stream>>>(ix.sa.ptr<int32_t>(), ix.str.ptr<int32_t>(), ix.tok_start.ptr<int32_t>(),
+    PROF("lookup", (double)T * 8.0 * 64, (lookup_kernel<<<cgx_div_up(T, LK_WARPS), LK_WARPS * 32, 0, stream>>>(ix.sa.ptr<int32_t>(), ix.str.ptr<int32_t>(), ix.tok_start.ptr<int32_t>(),
                                                                         ix.maxtok, b.q_tok.ptr<int32_t>(), b.q_off.ptr<int32_t>(),
-                                                                        b.tok2q.ptr<int32_t>(), T, longest, iv);
+                                                                        b.tok2q.ptr<int32_t>(), T, longest, iv)));
     b.launches++;
 }
 

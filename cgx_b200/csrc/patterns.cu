@@ -14,6 +14,7 @@
 // Every enumeration is count -> prefix sum -> fill (deterministic slots, no atomics), sorted with the
 // onesweep radix sort, then flag / scan / compact.
 #include "batch.h"
+#include "prof.h"
 
 namespace cgx {
 
@@ -206,10 +207,11 @@ __global__ void qlist_compact_kernel(const int32_t *__restrict__ pid, const int3
 
 // builds per-query sorted id lists from (pid,qid) of the pattern-sorted instances
 static void build_query_lists(Batch &b, const int32_t *pid, const int32_t *qid, int n, int idbits, DevBuf &off_buf, DevBuf &ids_buf,
-                              std::vector<int32_t> &h_off, std::vector<int32_t> &h_ids, cudaStream_t stream) {
+                              PinnedBuf &h_off, PinnedBuf &h_ids, cudaStream_t stream) {
     const int Q = b.Q;
-    h_off.assign((size_t)Q + 1, 0);
-    h_ids.clear();
+    int32_t *ho = h_off.get<int32_t>((size_t)Q + 1);
+    memset(ho, 0, sizeof(int32_t) * ((size_t)Q + 1));
+    h_ids.get<int32_t>(1);
     if (n == 0) return;
     uint32_t *flags = b.scratch.get<uint32_t>((size_t)n + 2);
     uint32_t *tot = b.counters.get<uint32_t>(16);
@@ -226,16 +228,17 @@ static void build_query_lists(Batch &b, const int32_t *pid, const int32_t *qid, 
     query_offsets_kernel<<<cgx_div_up(Q + 1, 256), 256, 0, stream>>>(ks, (int)M, Q, off);
     low32_kernel<<<cgx_div_up(M, 256), 256, 0, stream>>>(ks, (int)M, ids);
     b.launches += 4;
-    h_ids.resize(M);
-    CUDA_CHECK(cudaMemcpyAsync(h_off.data(), off, sizeof(int32_t) * ((size_t)Q + 1), cudaMemcpyDeviceToHost, stream));
-    CUDA_CHECK(cudaMemcpyAsync(h_ids.data(), ids, sizeof(int32_t) * (size_t)M, cudaMemcpyDeviceToHost, stream));
+    if (!b.fetch_results) return;
+    int32_t *hi = h_ids.get<int32_t>((size_t)M + 1);
+    CUDA_CHECK(cudaMemcpyAsync(ho, off, sizeof(int32_t) * ((size_t)Q + 1), cudaMemcpyDeviceToHost, stream));
+    CUDA_CHECK(cudaMemcpyAsync(hi, ids, sizeof(int32_t) * (size_t)M, cudaMemcpyDeviceToHost, stream));
 }
 
 void stage_onegap_enumerate(const Index &ix, Batch &b, cudaStream_t stream) {
     const int T = b.T;
     b.enu1 = 0; b.D1 = 0;
-    b.h_q1_off.assign((size_t)b.Q + 1, 0);
-    b.h_q1_ids.clear();
+    memset(b.h_q1_off.get<int32_t>((size_t)b.Q + 1), 0, sizeof(int32_t) * ((size_t)b.Q + 1));
+    b.h_q1_ids.get<int32_t>(1);
     if (T == 0) return;
     uint32_t *cnt = b.e1_count.get<uint32_t>((size_t)T + 2);
     uint32_t *tot = b.counters.get<uint32_t>(16);
@@ -251,7 +254,7 @@ void stage_onegap_enumerate(const Index &ix, Batch &b, cudaStream_t stream) {
     uint32_t *inst_info = (uint32_t *)(inst_t + E);
     uint64_t *keys = b.e1_keys.get<uint64_t>(E), *keys_tmp = b.e1_keys_tmp.get<uint64_t>(E);
     uint32_t *vals = b.e1_vals.get<uint32_t>(E), *vals_tmp = b.e1_vals_tmp.get<uint32_t>(E);
-    e1_enum_kernel<true><<<cgx_div_up(T, 128), 128, 0, stream>>>(q_tok, q_off, tok2q, T, longest, iv, nullptr, cnt, inst_t, inst_info, keys, vals);
+    PROF("enum_onegap", (double)E * 24, (e1_enum_kernel<true><<<cgx_div_up(T, 128), 128, 0, stream>>>(q_tok, q_off, tok2q, T, longest, iv, nullptr, cnt, inst_t, inst_info, keys, vals)));
     b.launches++;
     uint64_t *ks;
     uint32_t *vs;
@@ -329,8 +332,8 @@ __global__ void e2_patterns_kernel(const uint64_t *__restrict__ keys, const uint
 
 void stage_twogap_enumerate(const Index &ix, Batch &b, cudaStream_t stream) {
     b.enu2 = 0; b.D2 = 0;
-    b.h_q2_off.assign((size_t)b.Q + 1, 0);
-    b.h_q2_ids.clear();
+    memset(b.h_q2_off.get<int32_t>((size_t)b.Q + 1), 0, sizeof(int32_t) * ((size_t)b.Q + 1));
+    b.h_q2_ids.get<int32_t>(1);
     const int E = b.enu1;
     if (E == 0 || b.D1 == 0) return;
     uint32_t *cnt = b.e2_count.get<uint32_t>((size_t)E + 2);
@@ -348,8 +351,8 @@ void stage_twogap_enumerate(const Index &ix, Batch &b, cudaStream_t stream) {
     if (E2 == 0) return;
     uint64_t *keys = b.e2_keys.get<uint64_t>(E2), *keys_tmp = b.e2_keys_tmp.get<uint64_t>(E2);
     uint32_t *vals = b.e2_vals.get<uint32_t>(E2), *vals_tmp = b.e2_vals_tmp.get<uint32_t>(E2);
-    e2_enum_kernel<true><<<cgx_div_up(E, 256), 256, 0, stream>>>(pid, sorted_inst, E, b.pat1.ptr<Pat1>(), inst_t, inst_info, b.q_tok.ptr<int32_t>(),
-                                                                b.q_off.ptr<int32_t>(), b.tok2q.ptr<int32_t>(), b.longest.ptr<int32_t>(), nullptr, cnt, keys, vals);
+    PROF("enum_twogap", (double)E2 * 12, (e2_enum_kernel<true><<<cgx_div_up(E, 256), 256, 0, stream>>>(pid, sorted_inst, E, b.pat1.ptr<Pat1>(), inst_t, inst_info, b.q_tok.ptr<int32_t>(),
+                                                                b.q_off.ptr<int32_t>(), b.tok2q.ptr<int32_t>(), b.longest.ptr<int32_t>(), nullptr, cnt, keys, vals)));
     b.launches++;
     uint64_t *ks;
     uint32_t *vs;

@@ -13,6 +13,8 @@
 // into digits of at most 8 bits.
 #pragma once
 #include "common.cuh"
+#include "prof.h"
+#include <algorithm>
 
 namespace cgx {
 
@@ -240,7 +242,7 @@ void radix_sort(K *keys, K *keys_tmp, uint32_t *vals, uint32_t *vals_tmp, size_t
     CUDA_CHECK(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * RS_MAX_PASSES * RS_BINS, stream));
     CUDA_CHECK(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * RS_MAX_PASSES, stream));
     unsigned hgrid = (unsigned)std::min<size_t>((n + RS_BLOCK * 8 - 1) / (RS_BLOCK * 8), (size_t)CGX_NUM_SMS * 8);
-    rs_histogram_kernel<K><<<hgrid, RS_BLOCK, 0, stream>>>(keys, n, plan, hist);
+    PROF("radix_histogram", (double)n * sizeof(K), rs_histogram_kernel<K><<<hgrid, RS_BLOCK, 0, stream>>>(keys, n, plan, hist));
     rs_scan_hist_kernel<<<plan.num_passes, RS_BINS, 0, stream>>>(hist);
     if (launches) *launches += 2;
     K *kin = keys, *kout = keys_tmp;
@@ -248,11 +250,11 @@ void radix_sort(K *keys, K *keys_tmp, uint32_t *vals, uint32_t *vals_tmp, size_t
     for (int p = 0; p < plan.num_passes; p++) {
         CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(uint32_t) * tiles * RS_BINS, stream));
         if (vals)
-            rs_onesweep_kernel<K, true><<<(unsigned)tiles, RS_BLOCK, 0, stream>>>(kin, kout, vin, vout, n, plan.shift[p], plan.bits[p],
-                                                                                 hist + p * RS_BINS, status, counters + p);
+            PROF("radix_onesweep", (double)n * 2.0 * (sizeof(K) + 4), (rs_onesweep_kernel<K, true><<<(unsigned)tiles, RS_BLOCK, 0, stream>>>(
+                     kin, kout, vin, vout, n, plan.shift[p], plan.bits[p], hist + p * RS_BINS, status, counters + p)));
         else
-            rs_onesweep_kernel<K, false><<<(unsigned)tiles, RS_BLOCK, 0, stream>>>(kin, kout, nullptr, nullptr, n, plan.shift[p], plan.bits[p],
-                                                                                  hist + p * RS_BINS, status, counters + p);
+            PROF("radix_onesweep", (double)n * 2.0 * sizeof(K), (rs_onesweep_kernel<K, false><<<(unsigned)tiles, RS_BLOCK, 0, stream>>>(
+                     kin, kout, nullptr, nullptr, n, plan.shift[p], plan.bits[p], hist + p * RS_BINS, status, counters + p)));
         if (launches) *launches += 1;
         std::swap(kin, kout);
         std::swap(vin, vout);

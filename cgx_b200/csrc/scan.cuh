@@ -3,6 +3,7 @@
 // is read twice and the output written once (12 B/element for uint32) -- HBM-bound.
 #pragma once
 #include "common.cuh"
+#include "prof.h"
 #include <algorithm>
 
 namespace cgx {
@@ -89,16 +90,16 @@ static void exclusive_scan_u32(const uint32_t *in, uint32_t *out, size_t n, uint
     }
     size_t tiles = (n + SC_TILE - 1) / SC_TILE;
     if (tiles == 1) {
-        sc_scan_kernel<<<1, SC_BLOCK, 0, stream>>>(in, out, n, nullptr, total_out);
+        PROF("scan", (double)n * 8, sc_scan_kernel<<<1, SC_BLOCK, 0, stream>>>(in, out, n, nullptr, total_out));
         if (launches) *launches += 1;
         return;
     }
     CGX_REQUIRE(level < 4, "scan: too many levels");
     uint32_t *sums = tmp.level[level].get<uint32_t>(tiles);
-    sc_reduce_kernel<<<(unsigned)tiles, SC_BLOCK, 0, stream>>>(in, n, sums);
+    PROF("scan", (double)n * 4, sc_reduce_kernel<<<(unsigned)tiles, SC_BLOCK, 0, stream>>>(in, n, sums));
     if (launches) *launches += 1;
     exclusive_scan_u32(sums, sums, tiles, nullptr, stream, tmp, level + 1, launches);
-    sc_scan_kernel<<<(unsigned)tiles, SC_BLOCK, 0, stream>>>(in, out, n, sums, total_out);
+    PROF("scan", (double)n * 8, sc_scan_kernel<<<(unsigned)tiles, SC_BLOCK, 0, stream>>>(in, out, n, sums, total_out));
     if (launches) *launches += 1;
 }
 

@@ -253,6 +253,20 @@ class GrammarExtractor:
         self.L.cgx_result(self.h, C.byref(r))
         return BatchResult(r, info, qry_tok, qry_off)
 
+    def extract_dev(self, tok_ptr: int, off_ptr: int, t2q_ptr: int, Q: int, T: int):
+        """Queries resident in HBM, results left in HBM (device-resident throughput)."""
+        self._check(self.L.cgx_extract_dev(self.h, C.c_void_p(tok_ptr), C.c_void_p(off_ptr), C.c_void_p(t2q_ptr), Q, T), "cgx_extract_dev")
+        info = BatchInfo()
+        self.L.cgx_batch_info(self.h, C.byref(info))
+        return info.as_dict()
+
+    def profile(self, on=True):
+        self.L.cgx_profile_enable(self.h, 1 if on else 0)
+
+    def profile_report(self):
+        import json
+        return json.loads((self.L.cgx_profile_report(self.h) or b"{}").decode())
+
     def debug_fetch(self, what, cap, cols=None):
         out = np.empty(max(1, cap), dtype=np.int32)
         n = self.L.cgx_debug_fetch(self.h, what.encode(), _p(out, C.c_int32), cap)

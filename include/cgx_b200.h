@@ -65,7 +65,7 @@ typedef struct {
     int64_t n, m, lex_count;
     int32_t max_token;
     int32_t freq_list[100];
-    void *str, *sa, *inv1, *inv2, *inv3, *tok_start, *RLP, *L_tar, *R_tar, *tgt, *freq_flag, *lex_key, *lex_v1, *lex_v2;
+    void *str, *sa, *inv1, *inv2, *inv3, *tok_start, *RLP, *L_tar, *R_tar, *tgt, *freq_flag, *gapw, *lex_key, *lex_v1, *lex_v2;
 } cgx_index_arrays_t;
 int cgx_index_export(cgx_ctx_t *ctx, cgx_index_arrays_t *out);            /* pointers stay owned by ctx */
 int cgx_index_alloc(cgx_ctx_t *ctx, const cgx_index_arrays_t *shape, cgx_index_arrays_t *out);  /* allocate empty arrays of that shape on this ctx */
@@ -91,6 +91,17 @@ int cgx_index_copy_frequent(cgx_ctx_t *ctx, int32_t *out100);
  *   qry_off : Q+1 offsets into qry_tok
  * Results stay in the context until the next cgx_extract / cgx_destroy. */
 int cgx_extract(cgx_ctx_t *ctx, const int32_t *qry_tok, const int32_t *qry_off, int32_t Q);
+
+/* Same pipeline with the queries already resident in HBM and the results left there (device pointers:
+ * qry_tok_dev T ints, qry_off_dev Q+1 ints, tok2q_dev T ints = query index of every token).  Used to
+ * measure the device-resident throughput; cgx_result() is not available after this call. */
+int cgx_extract_dev(cgx_ctx_t *ctx, const int32_t *qry_tok_dev, const int32_t *qry_off_dev, const int32_t *tok2q_dev, int32_t Q, int32_t T);
+
+/* Per-kernel CUDA-event timing on the launching stream (off by default).  cgx_profile_report returns a JSON
+ * object {kernel: {launches, ms, bytes}} accumulated since cgx_profile_enable(ctx, 1); `bytes` are the
+ * algorithmic bytes of DESIGN.md. */
+int cgx_profile_enable(cgx_ctx_t *ctx, int on);
+const char *cgx_profile_report(cgx_ctx_t *ctx);
 
 typedef struct {
     int32_t Q, T;
