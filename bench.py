@@ -1,0 +1,443 @@
+#!/usr/bin/env python
+"""bench.py -- query sentences/s of the grammar-extraction hot path (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (default `c2` = BASELINE.json configs[1]): synthetic 1 M sentence-pair Zipfian parallel corpus
+(V = 50 k, word alignments with 10 % dropped links), 10 k query sentences per GPU, max phrase length 5, rule
+shapes of the reference (one- and two-gap), sample sizes 300/65/70.  One *step* = one pass of the hot path
+(contiguous lookup -> pattern enumeration -> gappy band joins -> extraction -> aggregation + lexical
+scoring) over the rank's query batch against the resident index.
+
+  value  : whole-job query sentences/s, queries resident in HBM, results left in HBM (cgx_extract_dev),
+           CUDA-event time of the K steps, max over ranks.
+  e2e    : the same through the C ABI with HOST buffers (cgx_extract + cgx_result): H2D of the queries and D2H
+           of every rule / pattern table inside the timed region, wall clock with a device synchronise on
+           both sides, max over ranks.
+  roofline : the dominant kernel of the step (per-kernel CUDA events on the launching stream,
+           cgx_profile_*), algorithmic bytes as defined in DESIGN.md, peak from MEASURED_PEAKS.json.
+  cpu_baseline : the CPU oracle port (oracle/cgx_oracle.c, single thread) on a bounded sample of the same
+           queries against the same corpus, SA from the reference's own SuffixArray.c (oracle/_ref/libref_sa.so).
+  --impl reference : the CPU implementation of the path on all host cores (the reference has no CPU
+           matcher/extractor -- SURVEY.md section 0 -- so this is the oracle port, one process per core over a
+           bounded query sample; its suffix array is built by the reference's SuffixArray.c).
+
+Multi-GPU (weak scaling): the index is built once on rank 0 and broadcast over NVLink with NCCL; every rank
+then processes its own 10 k-query batch; there is no data-path collective.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (sentence pairs, queries per GPU, vocabulary, description)
+    "c2": (1_000_000, 10_000, 50_000, "synthetic 1M sentence-pair Zipfian corpus (V=50k), 10k queries, max phrase len 5 (BASELINE.json configs[1])"),
+    "c1": (10_000, 100, 2_000, "synthetic toy-scale corpus: 10k sentence pairs (V=2k), 100 queries (stand-in for the unshipped toy/ corpus, configs[0])"),
+    "mid": (200_000, 2_000, 30_000, "synthetic 200k sentence-pair corpus (V=30k), 2k queries (development size)"),
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def make_inputs(workload: str, rank: int):
+    from cgx_b200 import synth
+    ns, nq, v, _ = WORKLOADS[workload]
+    t0 = time.time()
+    c = synth.generate(ns, nq, v_src=v, v_tgt=v, seed=1234, qry_seed=4321 + rank)
+    lay = synth.text_layout(c)
+    log("[rank %d] synthetic corpus: n=%d source tokens, m=%d target tokens, Q=%d queries (T=%d tokens), lex=%d entries, %.1f s"
+        % (rank, lay["n"], lay["m"], len(lay["qry_off"]) - 1, len(lay["qry_tok"]), len(lay["lex_f"]), time.time() - t0))
+    return lay
+
+
+# ----------------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md "clocks DURING the timed region")
+# ----------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t_begin, t_end):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], None, set(), []
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ts, line in self.rows:
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                mhz, mx = float(p[0]), float(p[1])
+            except ValueError:
+                continue
+            smax = mx
+            if t_begin - 0.05 <= ts <= t_end + 0.05:
+                sm.append(mhz)
+                try:
+                    power.append(float(p[2]))
+                except ValueError:
+                    pass
+                for nm, val in zip(names, p[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(power) if power else None}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (test infrastructure) timed as the reported baseline
+# ----------------------------------------------------------------------------------------------------------
+def cpu_suffix_array(lay):
+    """Suffix array on the CPU by the reference's own SuffixArray.c (oracle/_ref/libref_sa.so); falls back to the
+    oracle's prefix-doubling port when that library was not built.  Returns (sa, seconds, kind)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _oracle import REF_SA_PATH
+    s = np.ascontiguousarray(lay["str"], dtype=np.int32)
+    n = int(lay["n"])
+    if os.path.exists(REF_SA_PATH):
+        L = C.CDLL(REF_SA_PATH)
+        L.ref_sa_build.restype = C.c_double
+        L.ref_sa_build.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        sa = np.empty(n, dtype=np.int32)
+        devnull = os.open(os.devnull, os.O_WRONLY)      # SuffixArray.c prints progress on stderr/stdout
+        so, se = os.dup(1), os.dup(2)
+        os.dup2(devnull, 1), os.dup2(devnull, 2)
+        try:
+            sec = L.ref_sa_build(s.ctypes.data, n, int(s[n - 1]), sa.ctypes.data, None)
+        finally:
+            os.dup2(so, 1), os.dup2(se, 2)
+            os.close(devnull), os.close(so), os.close(se)
+        return sa, float(sec), "reference"
+    return None, None, "port"
+
+
+def make_oracle(lay, sa):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _oracle import Oracle
+    o = Oracle.from_layout(lay)
+    t0 = time.time()
+    if sa is not None:
+        o.set_sa(sa)
+        sa_s = None
+    else:
+        o.build_sa()
+        sa_s = time.time() - t0
+    # one-time index-side work of the oracle (frequent-pair precomputation, SuffixArray.cu:1132-1340): untimed
+    o.run(lay["qry_tok"][:1], np.array([0, 1], dtype=np.int32))
+    return o, sa_s
+
+
+def oracle_time_queries(o, lay, q0, q1):
+    off, tok = lay["qry_off"], lay["qry_tok"]
+    t0 = time.perf_counter()
+    o.run(tok[off[q0]:off[q1]], (off[q0:q1 + 1] - off[q0]).astype(np.int32))
+    return time.perf_counter() - t0
+
+
+def cpu_baseline_single(lay, budget_s=25.0):
+    """Single-thread oracle on the first queries of the batch, growing the sample until ~budget_s is spent."""
+    sa, sa_sec, sa_kind = cpu_suffix_array(lay)
+    o, port_sa_s = make_oracle(lay, sa)
+    Q = len(lay["qry_off"]) - 1
+    nq, spent, done_q, done_t = 1, 0.0, 0, 0.0
+    while spent < budget_s and nq <= Q:
+        dt = oracle_time_queries(o, lay, 0, nq)
+        spent += dt
+        done_q, done_t = nq, dt
+        if dt * 2.2 + spent > budget_s * 1.6:
+            break
+        nq *= 2
+    o.close()
+    return {"value": done_q / done_t, "unit": "query sentences/s", "cores": 1, "kind": "port",
+            "sample": "first %d of %d queries as one batch, %.1f s of single-thread oracle work (oracle/cgx_oracle.c); per-query CPU cost "
+                      "falls with batch size because patterns are de-duplicated across queries" % (done_q, Q, done_t),
+            "sa_build_s": sa_sec if sa_sec is not None else port_sa_s, "sa_build_kind": sa_kind}
+
+
+def reference_arm(args):
+    """bench.py --impl reference: the CPU implementation of the path on all host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    lay = make_inputs(args.workload, 0)
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 64))
+    per_worker = args.cpu_queries_per_core
+    sa, sa_sec, sa_kind = cpu_suffix_array(lay)
+    log("CPU suffix array (%s): %s s" % (sa_kind, "%.2f" % sa_sec if sa_sec else "n/a"))
+    o, port_sa_s = make_oracle(lay, sa)
+    Q = len(lay["qry_off"]) - 1
+    workers = min(workers, max(1, Q // per_worker))
+    sample_q = workers * per_worker
+
+    def one_step():
+        """fork one process per core; each runs the oracle on its own slice of the sample (index shared copy-on-write)."""
+        t0 = time.perf_counter()
+        pids = []
+        for w in range(workers):
+            pid = os.fork()
+            if pid == 0:
+                try:
+                    oracle_time_queries(o, lay, w * per_worker, (w + 1) * per_worker)
+                    os._exit(0)
+                except BaseException:
+                    os._exit(1)
+            pids.append(pid)
+        ok = True
+        for pid in pids:
+            _, st = os.waitpid(pid, 0)
+            ok &= (st == 0)
+        if not ok:
+            raise RuntimeError("an oracle worker failed")
+        return time.perf_counter() - t0
+
+    for _ in range(args.warmup):
+        one_step()
+    times = [one_step() for _ in range(args.steps)]
+    total = sum(times)
+    value = sample_q * args.steps / total
+    desc = WORKLOADS[args.workload][3]
+    sample = ("%d queries per step (%d processes x %d), each process one oracle batch against the full corpus index; "
+              "the reference has no CPU matcher/extractor, so the path is the oracle port; suffix array by the reference's SuffixArray.c"
+              % (sample_q, workers, per_worker))
+    print(json.dumps({
+        "impl": "reference", "metric": "query sentences/sec (grammar extraction)", "value": value, "unit": "query sentences/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": desc, "queries_per_step": sample_q, "source_tokens": int(lay["n"])},
+        "cpu_baseline": {"value": value, "unit": "query sentences/s", "cores": workers, "kind": "port", "sample": sample,
+                         "sa_build_s": sa_sec if sa_sec is not None else port_sa_s, "sa_build_kind": sa_kind},
+        "e2e": {"value": value, "unit": "query sentences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def result_bytes(ex):
+    """D2H bytes of one cgx_extract batch (every array cgx_result exposes)."""
+    from cgx_b200._lib import Result
+    r = Result()
+    ex.L.cgx_result(ex.h, C.byref(r))
+    q1 = int(np.ctypeslib.as_array(r.q1_off, shape=(r.Q + 1,))[-1]) if r.Q else 0
+    q2 = int(np.ctypeslib.as_array(r.q2_off, shape=(r.Q + 1,))[-1]) if r.Q else 0
+    b = 4 * (r.T * 5 + r.G * 4 + r.D1 * 8 + r.D2 * 4 + 2 * (r.Q + 1) + q1 + q2)
+    for k in range(3):
+        b += 36 * r.n_rules[k] + 8 * r.n_ids[k]
+    return int(b)
+
+
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from cgx_b200 import dist as cdist
+    from cgx_b200.extractor import GrammarExtractor
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch --gpus %d through torch.distributed.run (one rank per GPU)" % args.gpus)
+        args.gpus = world
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    lay = make_inputs(args.workload, rank)
+    Q, T = len(lay["qry_off"]) - 1, len(lay["qry_tok"])
+    ex = GrammarExtractor(local)             # raises when the CUDA library / device is missing: there is no fallback
+    bcast_ms, bcast_bytes = 0.0, 0
+    if rank == 0:
+        t0 = time.time()
+        info = ex.build_index(lay)
+        log("index: SA %.1f ms (%d doubling rounds, %d-bit keys), auxiliary %.1f ms, %.2f GB resident, wall %.2f s"
+            % (info["sa_build_ms"], info["sa_rounds"], info["sa_key_bits"], info["aux_build_ms"], info["index_bytes"] / 1e9, time.time() - t0))
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        bcast_bytes = cdist.broadcast_index(ex, src=0)
+        torch.cuda.synchronize()
+        dist.barrier()
+        bcast_ms = 1e3 * (time.perf_counter() - t0)
+        info = ex.index_info()
+        log("[rank %d] index broadcast over NCCL: %.1f MB in %.1f ms" % (rank, bcast_bytes / 1e6, bcast_ms))
+
+    # device-resident query batch (value) and pinned host copies (e2e)
+    qt_h = torch.from_numpy(np.ascontiguousarray(lay["qry_tok"], dtype=np.int32)).pin_memory()
+    qo_h = torch.from_numpy(np.ascontiguousarray(lay["qry_off"], dtype=np.int32)).pin_memory()
+    t2q = np.repeat(np.arange(Q, dtype=np.int32), np.diff(lay["qry_off"]))
+    qt_d, qo_d, t2q_d = qt_h.to(dev), qo_h.to(dev), torch.from_numpy(t2q).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    qt_np, qo_np = qt_h.numpy(), qo_h.numpy()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_dev():
+        flush.zero_()                                    # evict L2 between steps (outside the timed events)
+        torch.cuda.synchronize()
+        return ex.extract_dev(qt_d.data_ptr(), qo_d.data_ptr(), t2q_d.data_ptr(), Q, T)
+
+    def step_e2e():
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        binfo = ex.extract(qt_np, qo_np, fetch=False)    # cgx_extract: returns after every result array is on the host
+        return time.perf_counter() - t0, binfo
+
+    for _ in range(args.warmup):
+        step_dev()
+    for _ in range(args.warmup):
+        step_e2e()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    # ---- timed: device-resident -------------------------------------------------------------------
+    ex.profile(True)
+    barrier()
+    t_begin = time.time()
+    w0 = time.perf_counter()
+    dev_ms, binfo = 0.0, None
+    for _ in range(args.steps):
+        binfo = step_dev()
+        dev_ms += binfo["ms_total"]
+    barrier()
+    wall_dev = time.perf_counter() - w0
+    prof = ex.profile_report()
+    ex.profile(False)
+    # ---- timed: end to end through the C ABI with host buffers ------------------------------------------
+    barrier()
+    e2e_s = 0.0
+    for _ in range(args.steps):
+        dt, einfo = step_e2e()
+        e2e_s += dt
+    barrier()
+    t_end = time.time()
+    d2h = result_bytes(ex)
+    clocks = sampler.stop(t_begin, t_end) if sampler else None
+
+    tv = torch.tensor([dev_ms, e2e_s, wall_dev], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_s_max, wall_dev_max = (float(x) for x in tv.cpu())
+
+    if rank == 0:
+        hbm_peak, peak_src = peaks()
+        kern = {}
+        for name, v in prof.items():
+            per = v["ms"] / args.steps
+            kern[name] = {"ms_per_step": round(per, 4), "launches_per_step": v["launches"] / args.steps,
+                          "alg_bytes_per_step": v["bytes"] / args.steps,
+                          "gbs": (v["bytes"] / 1e9) / (v["ms"] / 1e3) if v["ms"] > 0 else None}
+        top = max(prof.items(), key=lambda kv: kv[1]["ms"])
+        tn, tvv = top
+        ach = (tvv["bytes"] / 1e9) / (tvv["ms"] / 1e3) if tvv["ms"] > 0 else 0.0
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")       # per-launch DRAM bytes from the committed ncu --set full capture
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(tn, {}).get("dram_bytes_per_launch")
+        roofline = {"bound": "hbm", "kernel": tn, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
+                    "peak_source": peak_src, "share_of_step": tvv["ms"] / max(1e-9, sum(v["ms"] for v in prof.values())),
+                    "avg_launch_ms": tvv["ms"] / max(1, tvv["launches"]), "alg_bytes_per_launch": tvv["bytes"] / max(1, tvv["launches"])}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                cpu = cpu_baseline_single(lay, args.cpu_budget)
+            except Exception as e:  # the baseline is reported, never required
+                cpu = {"value": None, "unit": "query sentences/s", "cores": 1, "kind": "port", "sample": "failed: %r" % (e,)}
+        ns, nq, v, desc = WORKLOADS[args.workload]
+        out = {
+            "metric": "query sentences/sec (grammar extraction)", "value": world * Q * args.steps / (dev_ms_max / 1e3), "unit": "query sentences/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": desc, "sentence_pairs": ns, "source_tokens": int(lay["n"]), "queries_per_gpu": Q, "query_tokens_per_gpu": T,
+                       "rule_shapes": "ab, Xab, abX, XabX, aXb, XaXb, aXbX, aXbXc (the reference's full set; superset of the quoted 1-gap)",
+                       "samples": [300, 65, 70], "parallelism": "query-sharded x%d, index broadcast once" % world,
+                       "l2": "explicit 256 MB flush between steps; index working set %.2f GB >> 126 MB L2" % (info["index_bytes"] / 1e9)},
+            "clocks": clocks,
+            "e2e": {"value": world * Q * args.steps / e2e_s_max, "unit": "query sentences/s", "h2d_bytes_per_step": 4 * (2 * T + Q + 1),
+                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s_max / args.steps},
+            "gpu_launches": int(binfo["launches"]) * args.steps,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "sa_build": {"gpu_ms": info["sa_build_ms"], "rounds": info["sa_rounds"], "key_bits": info["sa_key_bits"],
+                         "alg_bytes": 16.0 * info["n"] * info["sa_rounds"],
+                         "gbs": 16.0 * info["n"] * info["sa_rounds"] / 1e9 / (info["sa_build_ms"] / 1e3) if info["sa_build_ms"] else None,
+                         "aux_index_ms": info["aux_build_ms"], "cpu_reference_s": cpu.get("sa_build_s") if cpu else None},
+            "index_broadcast": {"ms": bcast_ms, "bytes": bcast_bytes} if world > 1 else None,
+            "batch": {k: binfo[k] for k in ("G", "D1", "hits1", "D2", "hits2", "samples", "n_ab", "n_1gap", "n_2gap", "rules", "launches", "ms_lookup",
+                                           "ms_enum", "ms_join", "ms_extract", "ms_aggregate")},
+            "kernels": kern,
+            "wall_ms_per_step_incl_flush": 1e3 * wall_dev_max / args.steps,
+        }
+        print(json.dumps(out), flush=True)
+    ex.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cgx_b200", choices=["cgx_b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of single-thread CPU oracle work for cpu_baseline")
+    ap.add_argument("--cpu-queries-per-core", type=int, default=1, help="--impl reference: queries per process and step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "cgx_b200" else max(args.warmup, 0)
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -26,7 +26,7 @@ __global__ void ix_ngram_keys_kernel(const int32_t *__restrict__ str, size_t n, 
 // aligned tokens narrower than 15; and, over that target span, min L_tar / max R_tar map back exactly onto the
 // source span.  The source-side min/max is maintained incrementally while g grows.
 __global__ void ix_gap_words_kernel(const int32_t *__restrict__ str, const uint32_t *__restrict__ RLP, const uint8_t *__restrict__ L_tar,
-                                    const uint8_t *__restrict__ R_tar, size_t n, uint32_t *__restrict__ gapw) {
+                                    const uint8_t *__restrict__ R_tar, size_t n, size_t m, uint32_t *__restrict__ gapw) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t word = 0;
@@ -36,7 +36,8 @@ __global__ void ix_gap_words_kernel(const int32_t *__restrict__ str, const uint3
         word = (uint32_t)run << 16;
         const uint32_t w0 = RLP[i];
         const unsigned L0 = (w0 >> 24) & 0xFF, R0 = (w0 >> 16) & 0xFF;
-        if (L0 != 255 && R0 != 255) {
+        // the unique final symbol at n-1 (Start.cu:324-326) has no alignment record and is never matched by a query
+        if (L0 != 255 && R0 != 255 && i + 1 < n) {
             const int eos_prev = (int)i - (int)((w0 >> 8) & 0xFF) - 1;
             const int tgt_base = eos_prev < 0 ? 0 : (int)RLP[eos_prev];
             const int src_base = eos_prev + 1;
@@ -50,6 +51,7 @@ __global__ void ix_gap_words_kernel(const int32_t *__restrict__ str, const uint3
                     mn = min(mn, L); mx = max(mx, R);
                 }
                 if (mx - mn >= CGX_MAX_RULE_SPAN) break;           // the span only grows with g
+                if (tgt_base < 0 || (size_t)tgt_base + mx >= m) break;   // malformed alignment record: never consistent
                 unsigned tmn = 255, tmx = 0;
                 for (int k = tgt_base + (int)mn; k <= tgt_base + (int)mx; k++) {
                     const unsigned L = L_tar[k], R = R_tar[k];
@@ -92,7 +94,7 @@ void build_index_aux(Index &ix, SaWorkspace &ws, cudaStream_t stream, int *launc
     pick_frequent(counts, ix.maxtok, ix.freq_list, flag);
     CUDA_CHECK(cudaMemcpyAsync(ix.freq_flag.get<uint8_t>(nt), flag.data(), nt, cudaMemcpyHostToDevice, stream));
     exclusive_scan_u32(ts, ts, nt, nullptr, stream, ws.scan, 0, launches);
-    ix_gap_words_kernel<<<cgx_div_up(n, 128), 128, 0, stream>>>(str, ix.RLP.ptr<uint32_t>(), ix.L_tar.ptr<uint8_t>(), ix.R_tar.ptr<uint8_t>(), n,
+    ix_gap_words_kernel<<<cgx_div_up(n, 128), 128, 0, stream>>>(str, ix.RLP.ptr<uint32_t>(), ix.L_tar.ptr<uint8_t>(), ix.R_tar.ptr<uint8_t>(), n, ix.m,
                                                               ix.gapw.get<uint32_t>(n));
     if (launches) *launches += 1;
     // position-sorted occurrence lists of every 1-, 2- and 3-gram
