@@ -20,10 +20,10 @@ class IndexInfo(C.Structure):
 
 class IndexArrays(C.Structure):
     _fields_ = [("n", C.c_int64), ("m", C.c_int64), ("lex_count", C.c_int64), ("max_token", C.c_int32), ("freq_list", C.c_int32 * 100)] + \
-               [(k, C.c_void_p) for k in ("str", "sa", "inv1", "inv2", "inv3", "tok_start", "RLP", "L_tar", "R_tar", "tgt", "freq_flag", "gapw",
+               [(k, C.c_void_p) for k in ("str", "sa", "inv1", "inv2", "inv3", "bkt1", "bkt2", "bkt3", "tok_start", "RLP", "L_tar", "R_tar", "tgt", "freq_flag", "gapw",
                                          "lex_key", "lex_v1", "lex_v2")]
 
-    ARRAYS = (("str", 4, "n3"), ("sa", 4, "n"), ("inv1", 4, "n"), ("inv2", 4, "n"), ("inv3", 4, "n"), ("tok_start", 4, "nt"), ("RLP", 4, "n"),
+    ARRAYS = (("str", 4, "n3"), ("sa", 4, "n"), ("inv1", 4, "n"), ("inv2", 4, "n"), ("inv3", 4, "n"), ("bkt1", 4, "n"), ("bkt2", 4, "n"), ("bkt3", 4, "n"), ("tok_start", 4, "nt"), ("RLP", 4, "n"),
               ("L_tar", 1, "m"), ("R_tar", 1, "m"), ("tgt", 4, "m3"), ("freq_flag", 1, "nt"), ("gapw", 4, "n"), ("lex_key", 8, "lex1"), ("lex_v1", 4, "lex1"),
               ("lex_v2", 4, "lex1"))
 

@@ -53,14 +53,14 @@ extern "C" void cgx_destroy(cgx_ctx_t *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     Index &ix = c->ix;
-    DevBuf *ib[] = {&ix.str, &ix.sa, &ix.inv[0], &ix.inv[1], &ix.inv[2], &ix.tok_start, &ix.RLP, &ix.L_tar, &ix.R_tar, &ix.tgt, &ix.freq_flag, &ix.gapw,
+    DevBuf *ib[] = {&ix.str, &ix.sa, &ix.inv[0], &ix.inv[1], &ix.inv[2], &ix.bkt[0], &ix.bkt[1], &ix.bkt[2], &ix.tok_start, &ix.RLP, &ix.L_tar, &ix.R_tar, &ix.tgt, &ix.freq_flag, &ix.gapw,
                     &ix.lex_key, &ix.lex_v1, &ix.lex_v2};
     for (auto *b : ib) b->release();
     c->ws.release();
     Batch &b = c->batch;
     DevBuf *bb[] = {&b.q_tok, &b.q_off, &b.tok2q, &b.longest, &b.iv, &b.ph_keys, &b.ph_keys_tmp, &b.ph_vals, &b.ph_vals_tmp, &b.ph_flags, &b.phrase_id,
                     &b.phrases, &b.e1_count, &b.e1_inst, &b.e1_keys, &b.e1_keys_tmp, &b.e1_vals, &b.e1_vals_tmp, &b.e1_flags, &b.e1_pid, &b.pat1,
-                    &b.pat1_dev, &b.pat1_pos, &b.ql_keys, &b.ql_keys_tmp, &b.q1_off, &b.q1_ids, &b.q2_off, &b.q2_ids, &b.j_tiles, &b.hit_keys,
+                    &b.pat1_dev, &b.pat1_pos, &b.ql_keys, &b.ql_keys_tmp, &b.q1_off, &b.q1_ids, &b.q2_off, &b.q2_ids, &b.j_tiles, &b.j_bitmaps, &b.j_aflag, &b.j_hash, &b.pat1_ga, &b.hit_keys,
                     &b.hit_keys_tmp, &b.counters, &b.missing, &b.hits1_sorted, &b.hits2_sorted, &b.e2_count, &b.e2_keys, &b.e2_keys_tmp, &b.e2_vals,
                     &b.e2_vals_tmp, &b.e2_flags, &b.pat2, &b.rec_hash, &b.rec_idx, &b.rec_idx_tmp, &b.rec_keys, &b.rec_keys_tmp, &b.rec_flags,
                     &b.scratch, &b.scratch2, &b.radix.hist, &b.radix.status, &b.radix.counters};
@@ -203,7 +203,7 @@ extern "C" int cgx_index_info(const cgx_ctx_t *c, cgx_index_info_t *out) {
     out->n = (int64_t)ix.n; out->m = (int64_t)ix.m;
     out->sa_rounds = ix.sa_stats.rounds; out->sa_key_bits = ix.sa_stats.key_bits; out->sa_launches = ix.sa_stats.launches;
     out->sa_build_ms = ix.sa_stats.ms; out->aux_build_ms = c->aux_ms;
-    out->index_bytes = (int64_t)(ix.str.cap + ix.sa.cap + ix.inv[0].cap + ix.inv[1].cap + ix.inv[2].cap + ix.tok_start.cap + ix.RLP.cap + ix.L_tar.cap +
+    out->index_bytes = (int64_t)(ix.str.cap + ix.sa.cap + ix.inv[0].cap + ix.inv[1].cap + ix.inv[2].cap + ix.bkt[0].cap + ix.bkt[1].cap + ix.bkt[2].cap + ix.tok_start.cap + ix.RLP.cap + ix.L_tar.cap +
                                  ix.R_tar.cap + ix.tgt.cap + ix.freq_flag.cap + ix.gapw.cap + ix.lex_key.cap + ix.lex_v1.cap + ix.lex_v2.cap);
     return 0;
 }
@@ -214,7 +214,7 @@ extern "C" int cgx_index_export(cgx_ctx_t *c, cgx_index_arrays_t *o) {
         Index &ix = c->ix;
         o->n = (int64_t)ix.n; o->m = (int64_t)ix.m; o->lex_count = (int64_t)ix.lex_count; o->max_token = ix.maxtok;
         memcpy(o->freq_list, ix.freq_list, sizeof(ix.freq_list));
-        o->str = ix.str.p; o->sa = ix.sa.p; o->inv1 = ix.inv[0].p; o->inv2 = ix.inv[1].p; o->inv3 = ix.inv[2].p; o->tok_start = ix.tok_start.p;
+        o->str = ix.str.p; o->sa = ix.sa.p; o->inv1 = ix.inv[0].p; o->inv2 = ix.inv[1].p; o->inv3 = ix.inv[2].p; o->bkt1 = ix.bkt[0].p; o->bkt2 = ix.bkt[1].p; o->bkt3 = ix.bkt[2].p; o->tok_start = ix.tok_start.p;
         o->RLP = ix.RLP.p; o->L_tar = ix.L_tar.p; o->R_tar = ix.R_tar.p; o->tgt = ix.tgt.p; o->freq_flag = ix.freq_flag.p; o->gapw = ix.gapw.p;
         o->lex_key = ix.lex_key.p; o->lex_v1 = ix.lex_v1.p; o->lex_v2 = ix.lex_v2.p;
     });
@@ -229,13 +229,13 @@ extern "C" int cgx_index_alloc(cgx_ctx_t *c, const cgx_index_arrays_t *s, cgx_in
         memcpy(ix.freq_list, s->freq_list, sizeof(ix.freq_list));
         size_t nt = (size_t)ix.maxtok + 2;
         ix.str.get<int32_t>(ix.n + 3); ix.sa.get<int32_t>(ix.n);
-        for (int k = 0; k < 3; k++) ix.inv[k].get<int32_t>(ix.n);
+        for (int k = 0; k < 3; k++) { ix.inv[k].get<int32_t>(ix.n); ix.bkt[k].get<int32_t>(ix.n); }
         ix.tok_start.get<int32_t>(nt); ix.RLP.get<uint32_t>(ix.n); ix.L_tar.get<uint8_t>(ix.m); ix.R_tar.get<uint8_t>(ix.m);
         ix.tgt.get<int32_t>(ix.m + 3); ix.freq_flag.get<uint8_t>(nt); ix.gapw.get<uint32_t>(ix.n);
         ix.lex_key.get<uint64_t>(ix.lex_count + 1); ix.lex_v1.get<float>(ix.lex_count + 1); ix.lex_v2.get<float>(ix.lex_count + 1);
         ix.built = false;
         *o = *s;
-        o->str = ix.str.p; o->sa = ix.sa.p; o->inv1 = ix.inv[0].p; o->inv2 = ix.inv[1].p; o->inv3 = ix.inv[2].p; o->tok_start = ix.tok_start.p;
+        o->str = ix.str.p; o->sa = ix.sa.p; o->inv1 = ix.inv[0].p; o->inv2 = ix.inv[1].p; o->inv3 = ix.inv[2].p; o->bkt1 = ix.bkt[0].p; o->bkt2 = ix.bkt[1].p; o->bkt3 = ix.bkt[2].p; o->tok_start = ix.tok_start.p;
         o->RLP = ix.RLP.p; o->L_tar = ix.L_tar.p; o->R_tar = ix.R_tar.p; o->tgt = ix.tgt.p; o->freq_flag = ix.freq_flag.p; o->gapw = ix.gapw.p;
         o->lex_key = ix.lex_key.p; o->lex_v1 = ix.lex_v1.p; o->lex_v2 = ix.lex_v2.p;
     });
@@ -438,6 +438,7 @@ extern "C" int64_t cgx_debug_fetch(cgx_ctx_t *c, const char *what, int32_t *out,
         };
         if (w == "longest") return copy_i32(b.longest.p, (size_t)b.T);
         if (w == "intervals") return copy_i32(b.iv.p, (size_t)b.T * CGX_LONGEST_SRC * 2);
+        if (w == "pat1_dev") return copy_i32(b.pat1_dev.p, (size_t)b.D1 * 4);
         if (w == "hits1" || w == "hits2") {
             bool two = w == "hits2";
             size_t H = (size_t)(two ? b.hits2 : b.hits1);
@@ -446,8 +447,9 @@ extern "C" int64_t cgx_debug_fetch(cgx_ctx_t *c, const char *what, int32_t *out,
             std::vector<uint64_t> h(H);
             if (H) CUDA_CHECK(cudaMemcpy(h.data(), two ? b.hits2_sorted.p : b.hits1_sorted.p, sizeof(uint64_t) * H, cudaMemcpyDeviceToHost));
             for (size_t i = 0; i < H; i++) {
-                if (two) { out[4 * i] = (int32_t)(h[i] >> 38); out[4 * i + 1] = (int32_t)((h[i] >> 8) & 0x3fffffffu); out[4 * i + 2] = (int32_t)((h[i] >> 4) & 15); out[4 * i + 3] = (int32_t)(h[i] & 15); }
-                else { out[3 * i] = (int32_t)(h[i] >> 34); out[3 * i + 1] = (int32_t)((h[i] >> 4) & 0x3fffffffu); out[3 * i + 2] = (int32_t)(h[i] & 15); }
+                const uint64_t pm = (1ull << b.pbits) - 1;
+                if (two) { out[4 * i] = (int32_t)(h[i] >> (b.pbits + 8)); out[4 * i + 1] = (int32_t)((h[i] >> 8) & pm); out[4 * i + 2] = (int32_t)((h[i] >> 4) & 15); out[4 * i + 3] = (int32_t)(h[i] & 15); }
+                else { out[3 * i] = (int32_t)(h[i] >> (b.pbits + 4)); out[3 * i + 1] = (int32_t)((h[i] >> 4) & pm); out[3 * i + 2] = (int32_t)(h[i] & 15); }
             }
             return (int64_t)(H * cols);
         }

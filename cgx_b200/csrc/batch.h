@@ -44,10 +44,11 @@ struct Batch {
     DevBuf ql_keys, ql_keys_tmp, q1_off, q1_ids, q2_off, q2_ids;
     int32_t enu1 = 0, D1 = 0;
     // joins
-    DevBuf j_tiles, hit_keys, hit_keys_tmp, counters, missing;
-    int64_t hits1 = 0, hits2 = 0;
+    DevBuf j_tiles, j_bitmaps, j_aflag, j_hash, pat1_ga, hit_keys, hit_keys_tmp, counters, missing;
+    int64_t hits1 = 0, hits2 = 0, j1_elems = 0;
+    int pbits = 30;                        // position field width of the packed hit keys (bits needed for n)
     size_t hit_cap = 0;
-    DevBuf hits1_sorted, hits2_sorted;     // uint64 keys
+    DevBuf hits1_sorted, hits2_sorted;     // uint64 keys: pattern << (pbits+4) | pos << 4 | len-1  /  pattern << (pbits+8) | pos << 8 | L << 4 | c-pos
     // two-gap enumeration
     DevBuf e2_count, e2_keys, e2_keys_tmp, e2_vals, e2_vals_tmp, e2_flags, pat2;
     int32_t enu2 = 0, D2 = 0;

@@ -305,7 +305,7 @@ __global__ void slots_pat1_kernel(const Pat1 *__restrict__ pat, int D1, uint32_t
 }
 
 __global__ void __launch_bounds__(128) extract_onegap_kernel(ExtractIdx x, const Pat1 *__restrict__ pat, int D1, const uint64_t *__restrict__ hits1,
-                                                             const uint32_t *__restrict__ slot_off, uint32_t n_slots, int G, int D2,
+                                                             const uint32_t *__restrict__ slot_off, uint32_t n_slots, int G, int D2, int pbits,
                                                              RuleRec *__restrict__ rec_1, RuleRec *__restrict__ rec_2,
                                                              unsigned long long *__restrict__ counters) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(128) extract_onegap_kernel(ExtractIdx x, const
     const int occ = sample_index((int)(slot - slot_off[d]), p.hit_count, CGX_SAMPLER_ONEGAP, 1.0f / (float)CGX_SAMPLER_ONEGAP);
     if (occ < 0) return;
     const uint64_t hk = hits1[(size_t)p.hit_start + occ];
-    const int current_str = (int)((hk >> 4) & 0x3fffffffu), firstEnd = (int)(hk & 15);
+    const int current_str = (int)((hk >> 4) & ((1ull << pbits) - 1)), firstEnd = (int)(hk & 15);
     const int startLen = p.ls, endLen = p.le;
     const int SPAN = CGX_MAX_RULE_SPAN;
     const int ender = current_str + firstEnd;
@@ -399,7 +399,7 @@ __global__ void slots_pat2_kernel(const Pat2 *__restrict__ pat, int D2, uint32_t
 
 __global__ void __launch_bounds__(128) extract_twogap_kernel(ExtractIdx x, const Pat2 *__restrict__ pat2, const Pat1 *__restrict__ pat1, int D2,
                                                              const uint64_t *__restrict__ hits2, const uint32_t *__restrict__ slot_off, uint32_t n_slots,
-                                                             int G, RuleRec *__restrict__ rec_2, unsigned long long *__restrict__ counters) {
+                                                             int G, int pbits, RuleRec *__restrict__ rec_2, unsigned long long *__restrict__ counters) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= n_slots) return;
     const int d = find_owner_u32(slot_off, D2, slot);
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(128) extract_twogap_kernel(ExtractIdx x, const
     const int occ = sample_index((int)(slot - slot_off[d]), p2.hit_count, CGX_SAMPLER_TWOGAP, 1.0f / (float)CGX_SAMPLER_TWOGAP);
     if (occ < 0) return;
     const uint64_t hk = hits2[(size_t)p2.hit_start + occ];
-    const int current_str = (int)((hk >> 8) & 0x3fffffffu), firstEnd = (int)((hk >> 4) & 15), secondEnd = (int)(hk & 15);
+    const int current_str = (int)((hk >> 8) & ((1ull << pbits) - 1)), firstEnd = (int)((hk >> 4) & 15), secondEnd = (int)(hk & 15);
     const Pat1 p1 = pat1[p2.pat1];
     unsigned mnL, mxR;
     int stb, ti;
@@ -461,8 +461,8 @@ void stage_extract(const Index &ix, Batch &b, cudaStream_t stream) {
     size_t cap0 = ns[0], cap1 = (size_t)2 * ns[0] + ns[1], cap2 = (size_t)ns[0] + ns[2] + (size_t)2 * ns[1];
     RuleRec *r0 = b.rec[0].get<RuleRec>(cap0 + 1), *r1 = b.rec[1].get<RuleRec>(cap1 + 1), *r2 = b.rec[2].get<RuleRec>(cap2 + 1);
     if (ns[0]) PROF("extract_contig", 0.0, (extract_contig_kernel<<<cgx_div_up(ns[0], 128), 128, 0, stream>>>(x, b.phrases.ptr<int32_t>(), G, so0, ns[0], r0, r1, r2, ctr)));
-    if (ns[2]) PROF("extract_twogap", 0.0, (extract_twogap_kernel<<<cgx_div_up(ns[2], 128), 128, 0, stream>>>(x, b.pat2.ptr<Pat2>(), b.pat1.ptr<Pat1>(), D2, b.hits2_sorted.ptr<uint64_t>(), so2, ns[2], G, r2, ctr)));
-    if (ns[1]) PROF("extract_onegap", 0.0, (extract_onegap_kernel<<<cgx_div_up(ns[1], 128), 128, 0, stream>>>(x, b.pat1.ptr<Pat1>(), D1, b.hits1_sorted.ptr<uint64_t>(), so1, ns[1], G, D2, r1, r2, ctr)));
+    if (ns[2]) PROF("extract_twogap", 0.0, (extract_twogap_kernel<<<cgx_div_up(ns[2], 128), 128, 0, stream>>>(x, b.pat2.ptr<Pat2>(), b.pat1.ptr<Pat1>(), D2, b.hits2_sorted.ptr<uint64_t>(), so2, ns[2], G, b.pbits, r2, ctr)));
+    if (ns[1]) PROF("extract_onegap", 0.0, (extract_onegap_kernel<<<cgx_div_up(ns[1], 128), 128, 0, stream>>>(x, b.pat1.ptr<Pat1>(), D1, b.hits1_sorted.ptr<uint64_t>(), so1, ns[1], G, D2, b.pbits, r1, r2, ctr)));
     b.launches += 3;
     unsigned long long nrec[3];
     CUDA_CHECK(cudaMemcpyAsync(nrec, ctr, sizeof(nrec), cudaMemcpyDeviceToHost, stream));

@@ -21,6 +21,23 @@ __global__ void ix_ngram_keys_kernel(const int32_t *__restrict__ str, size_t n, 
     vals[p] = (uint32_t)p;
 }
 
+// bucket start of every m-gram: heads of the sorted key array mark the bucket starts; gid = dense bucket number
+__global__ void ix_bucket_heads_kernel(const uint64_t *__restrict__ keys, size_t n, uint32_t *__restrict__ flags) {
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) flags[k] = (k == 0 || keys[k] != keys[k - 1]) ? 1u : 0u;
+}
+__global__ void ix_bucket_starts_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ excl, size_t n, uint32_t *__restrict__ start_of) {
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n && (k == 0 || keys[k] != keys[k - 1])) start_of[excl[k]] = (uint32_t)k;
+}
+__global__ void ix_bucket_scatter_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pos, const uint32_t *__restrict__ excl,
+                                         const uint32_t *__restrict__ start_of, size_t n, int32_t *__restrict__ bkt) {
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t head = (k == 0 || keys[k] != keys[k - 1]) ? 1u : 0u;
+    bkt[pos[k]] = (int32_t)start_of[excl[k] + head - 1];
+}
+
 // Gap-consistency words.  For a span [i, i+g-1] of source tokens (a gap of a hierarchical phrase):
 // GappyLook.cu:43-126 checkBoundaryGap = first and last token aligned; target span [min L, max R] of the
 // aligned tokens narrower than 15; and, over that target span, min L_tar / max R_tar map back exactly onto the
@@ -108,6 +125,12 @@ void build_index_aux(Index &ix, SaWorkspace &ws, cudaStream_t stream, int *launc
         uint32_t *vs;
         radix_sort<uint64_t>(keys, keys_tmp, vals, vals_tmp, n, 0, mlen * tokbits, stream, ws.radix, &ks, &vs, launches);
         CUDA_CHECK(cudaMemcpyAsync(ix.inv[mlen - 1].get<int32_t>(n), vs, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, stream));
+        uint32_t *flags = ws.flags.get<uint32_t>(n), *start_of = ws.rank.get<uint32_t>(n);
+        ix_bucket_heads_kernel<<<cgx_div_up(n, 256), 256, 0, stream>>>(ks, n, flags);
+        exclusive_scan_u32(flags, flags, n, nullptr, stream, ws.scan, 0, launches);
+        ix_bucket_starts_kernel<<<cgx_div_up(n, 256), 256, 0, stream>>>(ks, flags, n, start_of);
+        ix_bucket_scatter_kernel<<<cgx_div_up(n, 256), 256, 0, stream>>>(ks, vs, flags, start_of, n, ix.bkt[mlen - 1].get<int32_t>(n));
+        if (launches) *launches += 3;
     }
     CUDA_CHECK(cudaStreamSynchronize(stream));
 }

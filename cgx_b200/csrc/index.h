@@ -33,6 +33,9 @@ void build_suffix_array(const int32_t *d_str, size_t n, int32_t maxtok, int32_t 
 //   inv[m]  int32 [n]     m = 1..3: positions sorted by (first m tokens, position).  The bucket of an
 //                         m-gram occupies the same index range as its SA interval, so inv[m][up..down]
 //                         is the *position-sorted* occurrence list of that m-gram (drives the band joins)
+//   bkt[m]  int32 [n]     m = 1..3: start of the SA interval (= inv[m] bucket) of the m-gram at every corpus position --
+//                         the canonical id of that m-gram; lets the gappy join recognise "b starts at q" with one
+//                         coalesced load instead of a search in b's occurrence list
 //   tok_start int32 [maxtok+2]  SA bucket start of every token id (1-gram intervals in O(1))
 //   RLP     uint32 [n]    (L<<24)|(R<<16)|(P<<8) per source token; target sentence offset at EOS
 //   L_tar/R_tar uint8 [m] min/max aligned source index per target token (255 = unaligned)
@@ -46,7 +49,7 @@ void build_suffix_array(const int32_t *d_str, size_t n, int32_t maxtok, int32_t 
 struct Index {
     size_t n = 0, m = 0;
     int32_t maxtok = 0;
-    DevBuf str, sa, inv[3], tok_start, RLP, L_tar, R_tar, tgt, freq_flag, gapw;
+    DevBuf str, sa, inv[3], bkt[3], tok_start, RLP, L_tar, R_tar, tgt, freq_flag, gapw;
     DevBuf lex_key, lex_v1, lex_v2;
     size_t lex_count = 0;
     int32_t freq_list[CGX_PRECOMP];

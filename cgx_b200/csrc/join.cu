@@ -1,4 +1,4 @@
-// cgx-b200: gappy-phrase matching as sorted-occurrence band joins.
+// cgx-b200: gappy-phrase matching as a window scan over the occurrences of the patterns' first phrases.
 //
 // Replaces oneGapLookUpSA (GappyLook.cu:128-474), twoGapLookUpSA (:476-737), the frequent-pair
 // precomputation they lean on (precomp, :740-870; preComputation, SuffixArray.cu:1132-1340), the
@@ -9,41 +9,71 @@
 // from b, walk of the precomputed pair list -- see oracle/cgx_oracle.c onegap_lookup):
 //   { (p, L) : a at p, b at p+ls+g, g >= 1, ls+g+le <= 15, every token of the gap >= 2,
 //              checkBoundaryGap(p+ls, p+ls+g-1) },   L = ls+g+le-1
-// Both occurrence lists are POSITION-SORTED slices of the index (inv[len-1][up..down]), so the join is
-// a band merge: the shorter list drives, cut into tiles of JN_TILE elements (a load-balanced tile list
-// over all patterns, found by binary search on the scanned tile counts -- merge-path style
-// partitioning); per tile two binary searches bracket the slice of the other list that can fall into
-// the band of the tile, and every lane then only searches that bracket.  Hits are appended with
-// warp-aggregated atomics as packed 64-bit keys (pattern | position | length) and put in
-// (pattern, position, length) order by one onesweep radix sort; a boundary kernel derives the
-// per-pattern ranges.  The reference's 100x100 frequent-pair cache is not needed for speed; the one
-// place where it leaks into results (featureMissingCount is added to SampleCountF for patterns made of
-// two frequent tokens, ExtractPair.c:900-908) is reproduced by counting, in the same join, the
-// candidates that fail only the alignment check.
+//
+// The reference (and round 1a of this file) joins the two occurrence lists of EVERY pattern: work
+// sum_d min(|occ a|, |occ b|) = 6.8e9 list elements at C2 for 2.4e8 hits.  Here the loop is turned inside out:
+//   * every distinct first phrase `a` of the batch is walked ONCE over its position-sorted occurrence list
+//     inv[ls][up_a..down_a] (a flat, load-balanced element list: sum_a |occ a| <= 3n, 5e7 at C2);
+//   * one half-warp takes one occurrence p: lane g-1 owns gap width g.  One load of the gap-consistency word
+//     gapw[p+ls] (index.cu) answers "gap tokens >= 2" and checkBoundaryGap for all 13 widths at once; the lanes
+//     whose width passes read the canonical m-gram ids bkt[le][p+ls+g] (coalesced: 13 consecutive words per
+//     half-warp and le) -- "which phrase starts at q" without searching anything;
+//   * (a, le, id of the le-gram at q) is looked up in a per-batch open-addressing hash table of the batch's
+//     patterns (16-byte slots: key + pattern id in one sector), after a 1-bit-per-bucket filter ("is this m-gram
+//     the second phrase of any pattern", n/8 bytes per le: L2-resident) has rejected most candidates.
+// Hits are appended with warp-aggregated atomics as packed 64-bit keys (pattern | position | length) and put
+// in (pattern, position, length) order by one onesweep radix sort; a boundary kernel derives the per-pattern
+// ranges.  The reference's 100x100 frequent-pair cache is not needed; the one place where it leaks into
+// results (featureMissingCount is added to SampleCountF for patterns made of two frequent tokens,
+// ExtractPair.c:900-908) is reproduced by counting, in the same scan, the candidates that fail only the
+// alignment check.
+//
+// aXbXc (a, b, c single tokens; GappyLook.cu:595-655): one thread per parent hit (p, L) of aXb whose pattern has
+// children; the second gap's word gapw[p+L+1] yields the admissible widths g2 <= 13-L, and for each the token
+// c = str[p+L+1+g2] is looked up as (parent pattern, c) in a second hash table.
 #include "batch.h"
 #include "prof.h"
 
 namespace cgx {
 
-constexpr int JN_TILE = 128;
+// ------------------------------------------------------------------------------------------------
+// per-batch hash table: 64-bit key -> 32-bit value, linear probing, 16-byte slots
+// ------------------------------------------------------------------------------------------------
+constexpr uint64_t HT_EMPTY = ~0ull;
 
-__device__ __forceinline__ int lower_bound_i32(const int32_t *__restrict__ a, int lo, int hi, int x) {   // first idx in [lo,hi) with a[idx] >= x
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (__ldg(&a[mid]) < x) lo = mid + 1; else hi = mid;
-    }
-    return lo;
+__device__ __forceinline__ uint64_t ht_mix(uint64_t z) {
+    z ^= z >> 33; z *= 0xff51afd7ed558ccdULL; z ^= z >> 33; z *= 0xc4ceb9fe1a85ec53ULL; z ^= z >> 33;
+    return z;
 }
 
-// GappyLook.cu:43-126 checkBoundaryGap, preceded by the "every gap token >= 2" scan of the callers
-// (:341-351, :403-418), answered from the precomputed gap-consistency word of the span's first position
-// (index.cu ix_gap_words_kernel): one 4-byte load per candidate instead of a walk over the gap's RLP words and
-// its target window.  Returns 0 = a token < 2 in the gap, 1 = alignment check failed, 2 = ok.
-__device__ __forceinline__ int gap_check(const uint32_t *__restrict__ gapw, int start, int ender) {
-    const uint32_t w = __ldg(&gapw[start]);
-    const int g = ender - start + 1;
-    if ((int)((w >> 16) & 15u) < g) return 0;
-    return ((w >> (g - 1)) & 1u) ? 2 : 1;
+__device__ __forceinline__ void ht_insert(ulonglong2 *__restrict__ slots, uint32_t mask, uint64_t key, uint32_t val) {
+    uint32_t s = (uint32_t)ht_mix(key) & mask;
+    while (true) {
+        unsigned long long prev = atomicCAS(&slots[s].x, (unsigned long long)HT_EMPTY, (unsigned long long)key);
+        if (prev == HT_EMPTY || prev == key) { slots[s].y = val; return; }
+        s = (s + 1) & mask;
+    }
+}
+
+// returns the value or 0xFFFFFFFF
+__device__ __forceinline__ uint32_t ht_find(const ulonglong2 *__restrict__ slots, uint32_t mask, uint64_t key) {
+    uint32_t s = (uint32_t)ht_mix(key) & mask;
+    while (true) {
+        const ulonglong2 v = __ldg(&slots[s]);
+        if (v.x == key) return (uint32_t)v.y;
+        if (v.x == HT_EMPTY) return 0xFFFFFFFFu;
+        s = (s + 1) & mask;
+    }
+}
+
+static uint32_t ht_slots_for(size_t entries) {      // power of two, load factor <= 0.5
+    uint32_t s = 1024;
+    while ((size_t)s < 2 * entries) s <<= 1;
+    return s;
+}
+
+__device__ __forceinline__ uint64_t key1_of(uint32_t phrase_a, int le, uint32_t bucket_b) {
+    return ((uint64_t)phrase_a << 32) | ((uint64_t)le << 30) | (uint64_t)bucket_b;
 }
 
 __device__ __forceinline__ void append_hit(uint64_t key, unsigned long long *counter, uint64_t *out, size_t cap) {
@@ -56,91 +86,128 @@ __device__ __forceinline__ void append_hit(uint64_t key, unsigned long long *cou
     if (slot < cap) out[slot] = key;
 }
 
+__device__ __forceinline__ bool bit_test(const uint32_t *__restrict__ bm, uint32_t i) { return (__ldg(&bm[i >> 5]) >> (i & 31)) & 1u; }
+
 // ------------------------------------------------------------------------------------------------
-__global__ void j1_tiles_kernel(const Pat1Dev *__restrict__ patd, int D1, uint32_t *__restrict__ tiles) {
+// one-gap: per-batch tables
+// ------------------------------------------------------------------------------------------------
+// aflag[g]: bit 0 = phrase g is the first phrase of some pattern; bit 1 = it is a single top-100 token (only then
+// can a pattern be a "marker pair" of the reference's frequent-pair table)
+__global__ void j1_setup_kernel(const Pat1 *__restrict__ pat, const Pat1Dev *__restrict__ patd, const int32_t *__restrict__ pat_ga, int D1,
+                                const int32_t *__restrict__ str, const uint8_t *__restrict__ freq_rank, ulonglong2 *__restrict__ slots, uint32_t mask,
+                                uint32_t *__restrict__ bm1, uint32_t *__restrict__ bm2, uint32_t *__restrict__ bm3, uint32_t *__restrict__ bm_marker,
+                                uint32_t *__restrict__ aflag) {
     int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= D1) return;
-    Pat1Dev p = patd[d];
-    int nA = p.down_a - p.up_a + 1, nB = p.down_b - p.up_b + 1;
-    tiles[d] = (uint32_t)((min(nA, nB) + JN_TILE - 1) / JN_TILE);
+    const Pat1 p = pat[d];
+    const uint32_t ub = (uint32_t)patd[d].up_b;
+    const uint32_t ga = (uint32_t)pat_ga[d];
+    ht_insert(slots, mask, key1_of(ga, p.le, ub), (uint32_t)d | (p.marker_pair >= 0 ? 0x80000000u : 0u));
+    uint32_t *bm = p.le == 1 ? bm1 : p.le == 2 ? bm2 : bm3;
+    atomicOr(&bm[ub >> 5], 1u << (ub & 31));
+    if (p.marker_pair >= 0) atomicOr(&bm_marker[ub >> 5], 1u << (ub & 31));
+    const uint32_t f = 1u | ((p.ls == 1 && freq_rank[str[p.a_pos]]) ? 2u : 0u);
+    if (aflag[ga] != f) aflag[ga] = f;          // every writer of one slot writes the same value
 }
 
-__device__ __forceinline__ int find_owner(const uint32_t *__restrict__ off, int n, uint32_t tile) {   // largest d with off[d] <= tile
+// elements per phrase: its occurrence count when it is the first phrase of some pattern, else 0
+__global__ void j1_counts_kernel(const int32_t *__restrict__ phrases, const uint32_t *__restrict__ aflag, int G, uint32_t *__restrict__ cnt) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < G) cnt[g] = (aflag[g] & 1u) ? (uint32_t)(phrases[g * 4 + 1] - phrases[g * 4] + 1) : 0u;
+}
+
+__device__ __forceinline__ int find_owner(const uint32_t *__restrict__ off, int n, uint32_t e) {   // largest g with off[g] <= e
     int lo = 0, hi = n;
     while (hi - lo > 1) {
         int mid = (lo + hi) >> 1;
-        if (__ldg(&off[mid]) <= tile) lo = mid; else hi = mid;
+        if (__ldg(&off[mid]) <= e) lo = mid; else hi = mid;
     }
     return lo;
 }
 
-__global__ void __launch_bounds__(JN_TILE) j1_join_kernel(const Pat1 *__restrict__ pat, const Pat1Dev *__restrict__ patd, int D1,
-                                                          const uint32_t *__restrict__ tile_off, const int32_t *__restrict__ inv1,
-                                                          const int32_t *__restrict__ inv2, const int32_t *__restrict__ inv3,
-                                                          const uint32_t *__restrict__ gapw,
-                                                          unsigned long long *__restrict__ counter, uint64_t *__restrict__ hits, size_t cap,
-                                                          int32_t *__restrict__ missing) {
-    __shared__ int s_d, s_olo, s_ohi, s_missing;
-    if (threadIdx.x == 0) {
-        s_d = find_owner(tile_off, D1, blockIdx.x);
-        s_missing = 0;
+constexpr int J1_BLOCK = 256;
+
+struct J1Args {
+    const int32_t *phrases;
+    const uint32_t *aflag, *elem_off;
+    int G;
+    uint32_t n_elems;
+    const int32_t *inv[3];
+    const int32_t *bkt[3];
+    const uint32_t *gapw;
+    const uint32_t *bm[3];
+    const uint32_t *bm_marker;
+    const ulonglong2 *slots;
+    uint32_t mask;
+    int pshift;                      // hit key = pattern << pshift | position << 4 | (length-1)
+    uint32_t n;
+    unsigned long long *counter;     // [0] hits, [1] bucket words read (algorithmic-byte account)
+    uint64_t *hits;
+    size_t cap;
+    int32_t *missing;
+};
+
+__global__ void __launch_bounds__(J1_BLOCK) j1_scan_kernel(const J1Args a) {
+    const unsigned lane = threadIdx.x & 31;
+    const uint32_t e = (blockIdx.x * (uint32_t)J1_BLOCK + threadIdx.x);      // one element per lane, then 2 elements per warp step
+    // ---- lane-parallel: owner phrase and corpus position of 32 consecutive elements
+    int my_g = -1, my_len = 0, my_p = 0, my_f = 0;
+    if (e < a.n_elems) {
+        my_g = find_owner(a.elem_off, a.G, e);
+        const int up = a.phrases[my_g * 4];
+        my_len = a.phrases[my_g * 4 + 2];
+        my_p = __ldg(&a.inv[my_len - 1][up + (int)(e - a.elem_off[my_g])]);
+        my_f = (int)((a.aflag[my_g] >> 1) & 1u);
     }
-    __syncthreads();
-    const int d = s_d;
-    const Pat1 p = pat[d];
-    const Pat1Dev pd = patd[d];
-    const int ls = p.ls, le = p.le;
-    const int nA = pd.down_a - pd.up_a + 1, nB = pd.down_b - pd.up_b + 1;
-    const bool driveA = nA <= nB;                                // GappyLook.cu:241 (dis <= dis2 -> forward)
-    const int32_t *invA = (ls == 1 ? inv1 : ls == 2 ? inv2 : inv3) + pd.up_a;
-    const int32_t *invB = (le == 1 ? inv1 : le == 2 ? inv2 : inv3) + pd.up_b;
-    const int32_t *drv = driveA ? invA : invB;
-    const int32_t *oth = driveA ? invB : invA;
-    const int ndrv = driveA ? nA : nB, noth = driveA ? nB : nA;
-    const int e0 = (int)(blockIdx.x - tile_off[d]) * JN_TILE;
-    const int e1 = min(e0 + JN_TILE, ndrv);
-    // band of the other list relative to a driver position x:  [x+lo_off, x+hi_off]
-    const int lo_off = driveA ? ls + 1 : -(CGX_MAX_RULE_SPAN - le);
-    const int hi_off = driveA ? CGX_MAX_RULE_SPAN - le : -(ls + 1);
-    if (threadIdx.x == 0) {
-        int xf = drv[e0], xl = drv[e1 - 1];
-        s_olo = lower_bound_i32(oth, 0, noth, xf + lo_off);
-        s_ohi = lower_bound_i32(oth, s_olo, noth, xl + hi_off + 1);
-    }
-    __syncthreads();
-    const int e = e0 + threadIdx.x;
-    if (e < e1 && s_ohi > s_olo) {
-        const int x = drv[e];
-        int j = lower_bound_i32(oth, s_olo, s_ohi, x + lo_off);
-        for (; j < s_ohi; j++) {
-            int y = __ldg(&oth[j]);
-            if (y > x + hi_off) break;
-            int a_p = driveA ? x : y, b_p = driveA ? y : x;
-            int r = gap_check(gapw, a_p + ls, b_p - 1);
-            if (r == 2) {
-                uint64_t key = ((uint64_t)(uint32_t)d << 34) | ((uint64_t)(uint32_t)a_p << 4) | (uint64_t)(b_p + le - 1 - a_p);
-                append_hit(key, counter, hits, cap);
-            } else if (r == 1 && p.marker_pair >= 0) {
-                atomicAdd(&s_missing, 1);
+    const unsigned half = lane >> 4, h = lane & 15;
+    const int g = (int)h + 1;                                              // gap width of this lane
+    unsigned probes = 0;
+#pragma unroll 1
+    for (int it = 0; it < 16; it++) {
+        const int src = it * 2 + (int)half;
+        const int ga = __shfl_sync(0xffffffffu, my_g, src);
+        const int ls = __shfl_sync(0xffffffffu, my_len, src);
+        const int p = __shfl_sync(0xffffffffu, my_p, src);
+        const int fa = __shfl_sync(0xffffffffu, my_f, src);
+        if (ga < 0) continue;
+        const uint32_t w = __ldg(&a.gapw[p + ls]);
+        const int run = (int)((w >> 16) & 15u);
+        if (g > run || g > CGX_MAX_RULE_SPAN - 1 - ls) continue;           // a token < 2 inside the gap, or no room for b
+        const bool ok = (w >> (g - 1)) & 1u;
+        if (!ok && !fa) continue;
+        const uint32_t q = (uint32_t)(p + ls + g);
+        const int le_max = min(min(3, CGX_MAX_RULE_SYMBOLS - 1 - ls), CGX_MAX_RULE_SPAN - ls - g);
+        if (ok) {
+            for (int le = 1; le <= le_max; le++) {
+                if (q + (uint32_t)le > a.n) break;
+                const uint32_t ub = (uint32_t)__ldg(&a.bkt[le - 1][q]);
+                probes++;
+                if (!bit_test(a.bm[le - 1], ub)) continue;
+                const uint32_t v = ht_find(a.slots, a.mask, key1_of((uint32_t)ga, le, ub));
+                if (v == 0xFFFFFFFFu) continue;
+                const uint64_t key = ((uint64_t)(v & 0x7fffffffu) << a.pshift) | ((uint64_t)(uint32_t)p << 4) | (uint64_t)(ls + g + le - 1);
+                append_hit(key, &a.counter[0], a.hits, a.cap);
+            }
+        } else if (q < a.n) {                                              // frequent single token a: count what the pair table would miss
+            const uint32_t ub = (uint32_t)__ldg(&a.bkt[0][q]);
+            probes++;
+            if (bit_test(a.bm_marker, ub)) {
+                const uint32_t v = ht_find(a.slots, a.mask, key1_of((uint32_t)ga, 1, ub));
+                if (v != 0xFFFFFFFFu && (v & 0x80000000u)) atomicAdd(&a.missing[v & 0x7fffffffu], 1);
             }
         }
     }
-    __syncthreads();
-    if (threadIdx.x == 0 && s_missing) atomicAdd(&missing[d], s_missing);
+    for (int o = 16; o; o >>= 1) probes += __shfl_xor_sync(0xffffffffu, probes, o);
+    if (lane == 0 && probes) atomicAdd(&a.counter[1], (unsigned long long)probes);
 }
 
 // per-pattern [start,count] in the sorted hit list
-template <int SHIFT>
-__global__ void hit_ranges_kernel(const uint64_t *__restrict__ hits, size_t n, int32_t *__restrict__ start_count, int stride_ints) {
+__global__ void hit_ranges_kernel(const uint64_t *__restrict__ hits, size_t n, int shift, int32_t *__restrict__ start_count, int stride_ints) {
     size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    uint32_t d = (uint32_t)(hits[k] >> SHIFT);
-    if (k == 0 || (uint32_t)(hits[k - 1] >> SHIFT) != d) start_count[(size_t)d * stride_ints + 0] = (int32_t)k;
-    if (k == n - 1 || (uint32_t)(hits[k + 1] >> SHIFT) != d) {
-        // count = k - start + 1 ; start may be written by another thread -> derive it by searching backwards is costly;
-        // store end in the count slot and fix up in a second kernel
-        start_count[(size_t)d * stride_ints + 1] = (int32_t)k;
-    }
+    uint32_t d = (uint32_t)(hits[k] >> shift);
+    if (k == 0 || (uint32_t)(hits[k - 1] >> shift) != d) start_count[(size_t)d * stride_ints + 0] = (int32_t)k;
+    if (k == n - 1 || (uint32_t)(hits[k + 1] >> shift) != d) start_count[(size_t)d * stride_ints + 1] = (int32_t)k;   // end; fixed up below
 }
 __global__ void hit_ranges_fix_kernel(int32_t *__restrict__ start_count, int n_pat, int stride_ints) {
     int d = blockIdx.x * blockDim.x + threadIdx.x;
@@ -154,40 +221,62 @@ __global__ void j1_missing_kernel(Pat1 *__restrict__ pat, const int32_t *__restr
     if (d < D1) pat[d].fs_extra = missing[d];
 }
 
-static unsigned long long read_u64(const unsigned long long *d, cudaStream_t stream) {
-    unsigned long long v = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&v, d, sizeof(v), cudaMemcpyDeviceToHost, stream));
+static void read_u64s(unsigned long long *dst, const unsigned long long *d, int count, cudaStream_t stream) {
+    CUDA_CHECK(cudaMemcpyAsync(dst, d, sizeof(unsigned long long) * count, cudaMemcpyDeviceToHost, stream));
     CUDA_CHECK(cudaStreamSynchronize(stream));
-    return v;
+}
+
+static void prof_add_bytes(const char *name, double bytes) {
+    if (g_prof && g_prof->enabled) g_prof->table[name].bytes += bytes;
 }
 
 void stage_onegap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     b.hits1 = 0;
-    const int D1 = b.D1;
+    const int D1 = b.D1, G = b.G;
+    b.pbits = cgx_bits_for((uint64_t)ix.n);
     if (D1 == 0) return;
-    CGX_REQUIRE(D1 < (1 << 30) && ix.n < (1ull << 30), "one-gap join: pattern or corpus size exceeds the 30-bit key fields");
-    uint32_t *tiles = b.j_tiles.get<uint32_t>((size_t)D1 + 2);
-    uint32_t *tot = b.counters.get<uint32_t>(16);
-    unsigned long long *ctr = (unsigned long long *)(tot + 4);
-    j1_tiles_kernel<<<cgx_div_up(D1, 256), 256, 0, stream>>>(b.pat1_dev.ptr<Pat1Dev>(), D1, tiles);
-    exclusive_scan_u32(tiles, tiles, (size_t)D1, tot, stream, b.scan, 0, &b.launches);
-    uint32_t n_tiles = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&n_tiles, tot, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    CGX_REQUIRE(cgx_bits_for((uint64_t)D1) + b.pbits + 4 <= 64 && ix.n < (1ull << 30) && D1 < (1 << 30), "one-gap join: pattern/corpus size exceeds the hit-key fields");
+    const size_t bm_words = (ix.n + 31) / 32 + 1;
+    uint32_t *bm = b.j_bitmaps.get<uint32_t>(4 * bm_words);
+    uint32_t *aflag = b.j_aflag.get<uint32_t>((size_t)G + 1);
+    uint32_t *eoff = b.j_tiles.get<uint32_t>((size_t)G + 2);
+    const uint32_t slots_n = ht_slots_for((size_t)D1);
+    ulonglong2 *slots = b.j_hash.get<ulonglong2>(slots_n);
+    uint32_t *tot = b.counters.get<uint32_t>(32);
+    unsigned long long *ctr = (unsigned long long *)(tot + 4);         // [0] hits [1] bucket words read
+    CUDA_CHECK(cudaMemsetAsync(bm, 0, sizeof(uint32_t) * 4 * bm_words, stream));
+    CUDA_CHECK(cudaMemsetAsync(aflag, 0, sizeof(uint32_t) * ((size_t)G + 1), stream));
+    CUDA_CHECK(cudaMemsetAsync(slots, 0xff, sizeof(ulonglong2) * (size_t)slots_n, stream));
+        PROF("join_setup", (double)D1 * (32 + 16 + 4 + 16), (j1_setup_kernel<<<cgx_div_up(D1, 256), 256, 0, stream>>>(b.pat1.ptr<Pat1>(), b.pat1_dev.ptr<Pat1Dev>(), b.pat1_ga.ptr<int32_t>(), D1, ix.str.ptr<int32_t>(),
+                                                                ix.freq_flag.ptr<uint8_t>(), slots, slots_n - 1, bm, bm + bm_words, bm + 2 * bm_words, bm + 3 * bm_words, aflag)));
+    j1_counts_kernel<<<cgx_div_up(G, 256), 256, 0, stream>>>(b.phrases.ptr<int32_t>(), aflag, G, eoff);
+    exclusive_scan_u32(eoff, eoff, (size_t)G, tot, stream, b.scan, 0, &b.launches);
+    b.launches += 2;
+    uint32_t n_elems = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&n_elems, tot, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     CUDA_CHECK(cudaStreamSynchronize(stream));
     int32_t *missing = b.missing.get<int32_t>((size_t)D1);
     if (b.hit_cap == 0) b.hit_cap = 1u << 22;
+    J1Args a;
+    a.phrases = b.phrases.ptr<int32_t>(); a.aflag = aflag; a.elem_off = eoff; a.G = G; a.n_elems = n_elems;
+    for (int k = 0; k < 3; k++) { a.inv[k] = ix.inv[k].ptr<int32_t>(); a.bkt[k] = ix.bkt[k].ptr<int32_t>(); a.bm[k] = bm + (size_t)k * bm_words; }
+    a.gapw = ix.gapw.ptr<uint32_t>(); a.bm_marker = bm + 3 * bm_words; a.slots = slots; a.mask = slots_n - 1;
+    a.pshift = b.pbits + 4; a.n = (uint32_t)ix.n; a.counter = ctr; a.missing = missing;
+    unsigned long long host_ctr[2] = {0, 0};
     while (true) {
-        uint64_t *hits = b.hit_keys.get<uint64_t>(b.hit_cap);
-        CUDA_CHECK(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), stream));
+        a.hits = b.hit_keys.get<uint64_t>(b.hit_cap);
+        a.cap = b.hit_cap;
+        CUDA_CHECK(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long) * 2, stream));
         CUDA_CHECK(cudaMemsetAsync(missing, 0, sizeof(int32_t) * (size_t)D1, stream));
-        if (n_tiles)
-            PROF("join_onegap", 0.0, (j1_join_kernel<<<n_tiles, JN_TILE, 0, stream>>>(b.pat1.ptr<Pat1>(), b.pat1_dev.ptr<Pat1Dev>(), D1, tiles, ix.inv[0].ptr<int32_t>(),
-                                                           ix.inv[1].ptr<int32_t>(), ix.inv[2].ptr<int32_t>(), ix.gapw.ptr<uint32_t>(), ctr, hits, b.hit_cap, missing)));
-        b.launches += 2;
-        unsigned long long H = read_u64(ctr, stream);
-        if (H <= b.hit_cap) { b.hits1 = (int64_t)H; break; }
-        b.hit_cap = (size_t)H + (size_t)H / 8 + 1024;        // grow once to the exact need and redo the join
+        if (n_elems) PROF("join_onegap", 0.0, (j1_scan_kernel<<<cgx_div_up(n_elems, J1_BLOCK), J1_BLOCK, 0, stream>>>(a)));
+        b.launches += 1;
+        read_u64s(host_ctr, ctr, 2, stream);
+        if (host_ctr[0] <= b.hit_cap) { b.hits1 = (int64_t)host_ctr[0]; break; }
+        b.hit_cap = (size_t)host_ctr[0] + (size_t)host_ctr[0] / 8 + 1024;        // grow once to the exact need and redo the scan
     }
+    // algorithmic bytes: per element its position + gap word, every bucket word read, every hit written
+    prof_add_bytes("join_onegap", 8.0 * (double)n_elems + 4.0 * (double)host_ctr[1] + 8.0 * (double)host_ctr[0]);
+    b.j1_elems = (int64_t)n_elems;
     j1_missing_kernel<<<cgx_div_up(D1, 256), 256, 0, stream>>>(b.pat1.ptr<Pat1>(), missing, D1);
     b.launches++;
     if (b.hits1 == 0) return;
@@ -195,128 +284,98 @@ void stage_onegap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     uint64_t *hits = b.hit_keys.ptr<uint64_t>();
     uint64_t *tmp = b.hit_keys_tmp.get<uint64_t>(H);
     uint64_t *hs;
-    radix_sort<uint64_t>(hits, tmp, nullptr, nullptr, H, 0, 34 + cgx_bits_for((uint64_t)D1), stream, b.radix, &hs, nullptr, &b.launches);
+    radix_sort<uint64_t>(hits, tmp, nullptr, nullptr, H, 0, b.pbits + 4 + cgx_bits_for((uint64_t)D1), stream, b.radix, &hs, nullptr, &b.launches);
     uint64_t *dst = b.hits1_sorted.get<uint64_t>(H);
     CUDA_CHECK(cudaMemcpyAsync(dst, hs, sizeof(uint64_t) * H, cudaMemcpyDeviceToDevice, stream));
     static_assert(sizeof(Pat1) == 32, "Pat1 layout");
-    hit_ranges_kernel<34><<<cgx_div_up(H, 256), 256, 0, stream>>>(dst, H, &b.pat1.ptr<int32_t>()[4], 8);
+    hit_ranges_kernel<<<cgx_div_up(H, 256), 256, 0, stream>>>(dst, H, b.pbits + 4, &b.pat1.ptr<int32_t>()[4], 8);
     hit_ranges_fix_kernel<<<cgx_div_up(D1, 256), 256, 0, stream>>>(&b.pat1.ptr<int32_t>()[4], D1, 8);
     b.launches += 2;
 }
 
 // ------------------------------------------------------------------------------------------------
-// two-gap: parent hits (p, L) of aXb joined with the occurrences of the single token c
-//   c at p+L+1+g2, g2 >= 1, (L+1)+g2+1 <= 15  ->  c_pos in [p+L+2, p+14]        (GappyLook.cu:595-655)
+// two-gap: parent hits (p, L) of aXb extended by the single token c
+//   c at p+L+1+g2, g2 >= 1, (L+1)+g2+1 <= 15  ->  g2 <= 13-L                      (GappyLook.cu:595-655)
 // ------------------------------------------------------------------------------------------------
-__global__ void j2_tiles_kernel(const Pat2 *__restrict__ pat2, const Pat1 *__restrict__ pat1, const int32_t *__restrict__ tok_start, int D2,
-                                uint32_t *__restrict__ tiles) {
+__global__ void j2_setup_kernel(const Pat2 *__restrict__ pat2, int D2, ulonglong2 *__restrict__ slots, uint32_t mask, uint8_t *__restrict__ has_child) {
     int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= D2) return;
-    Pat2 p = pat2[d];
-    int nH = pat1[p.pat1].hit_count;
-    int nC = tok_start[p.ctok + 1] - tok_start[p.ctok];
-    tiles[d] = nH > 0 ? (uint32_t)((min(nH, nC) + JN_TILE - 1) / JN_TILE) : 0u;
+    const Pat2 p = pat2[d];
+    ht_insert(slots, mask, ((uint64_t)(uint32_t)p.pat1 << 32) | (uint64_t)(uint32_t)p.ctok, (uint32_t)d);
+    if (!has_child[p.pat1]) has_child[p.pat1] = 1;
 }
 
-__device__ __forceinline__ int lower_bound_hitpos(const uint64_t *__restrict__ h, int lo, int hi, int x) {   // first idx with pos >= x
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        int pos = (int)((h[mid] >> 4) & 0x3fffffffu);
-        if (pos < x) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
-__global__ void __launch_bounds__(JN_TILE) j2_join_kernel(const Pat2 *__restrict__ pat2, const Pat1 *__restrict__ pat1, int D2,
-                                                          const uint32_t *__restrict__ tile_off, const uint64_t *__restrict__ hits1,
-                                                          const int32_t *__restrict__ inv1, const int32_t *__restrict__ tok_start,
-                                                          const uint32_t *__restrict__ gapw,
-                                                          unsigned long long *__restrict__ counter, uint64_t *__restrict__ hits, size_t cap) {
-    __shared__ int s_d, s_olo, s_ohi;
-    if (threadIdx.x == 0) s_d = find_owner(tile_off, D2, blockIdx.x);
-    __syncthreads();
-    const int d = s_d;
-    const Pat2 p2 = pat2[d];
-    const Pat1 p1 = pat1[p2.pat1];
-    const uint64_t *H = hits1 + p1.hit_start;
-    const int nH = p1.hit_count;
-    const int32_t *C = inv1 + tok_start[p2.ctok];
-    const int nC = tok_start[p2.ctok + 1] - tok_start[p2.ctok];
-    const bool driveH = nH <= nC;
-    const int e0 = (int)(blockIdx.x - tile_off[d]) * JN_TILE;
-    const int e1 = min(e0 + JN_TILE, driveH ? nH : nC);
-    if (threadIdx.x == 0) {
-        if (driveH) {
-            int pf = (int)((H[e0] >> 4) & 0x3fffffffu), pl = (int)((H[e1 - 1] >> 4) & 0x3fffffffu);
-            s_olo = lower_bound_i32(C, 0, nC, pf + 4);                          // L >= 2 -> c_pos >= p+4
-            s_ohi = lower_bound_i32(C, s_olo, nC, pl + CGX_MAX_RULE_SPAN);      // c_pos <= p+14
-        } else {
-            int cf = C[e0], cl = C[e1 - 1];
-            s_olo = lower_bound_hitpos(H, 0, nH, cf - (CGX_MAX_RULE_SPAN - 1));
-            s_ohi = lower_bound_hitpos(H, s_olo, nH, cl - 4 + 1);
+__global__ void __launch_bounds__(256) j2_scan_kernel(const uint64_t *__restrict__ hits1, size_t H1, int pbits, const uint8_t *__restrict__ has_child,
+                                                      const int32_t *__restrict__ str, const uint32_t *__restrict__ gapw,
+                                                      const ulonglong2 *__restrict__ slots, uint32_t mask,
+                                                      unsigned long long *__restrict__ counter, uint64_t *__restrict__ hits, size_t cap) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned active = 0, probes = 0;
+    if (k < H1) {
+        const uint64_t hk = hits1[k];
+        const uint32_t d1 = (uint32_t)(hk >> (pbits + 4));
+        if (has_child[d1]) {
+            const int p = (int)((hk >> 4) & ((1ull << pbits) - 1)), L = (int)(hk & 15);
+            const uint32_t w = __ldg(&gapw[p + L + 1]);
+            const int run = (int)((w >> 16) & 15u);
+            const int gmax = min(run, CGX_MAX_RULE_SPAN - 2 - L);
+            uint32_t bits = gmax > 0 ? (w & ((1u << gmax) - 1u)) : 0u;
+            active = 1;
+            while (bits) {
+                const int g2 = __ffs(bits);
+                bits &= bits - 1;
+                const int r = p + L + 1 + g2;
+                const uint32_t c = (uint32_t)__ldg(&str[r]);
+                probes++;
+                const uint32_t d2 = ht_find(slots, mask, ((uint64_t)d1 << 32) | (uint64_t)c);
+                if (d2 != 0xFFFFFFFFu)
+                    append_hit(((uint64_t)d2 << (pbits + 8)) | ((uint64_t)(uint32_t)p << 8) | ((uint64_t)L << 4) | (uint64_t)(r - p), &counter[0], hits, cap);
+            }
         }
     }
-    __syncthreads();
-    const int e = e0 + threadIdx.x;
-    if (e >= e1 || s_ohi <= s_olo) return;
-    if (driveH) {
-        uint64_t hk = H[e];
-        int p = (int)((hk >> 4) & 0x3fffffffu), L = (int)(hk & 15);
-        int j = lower_bound_i32(C, s_olo, s_ohi, p + L + 2);
-        for (; j < s_ohi; j++) {
-            int c = __ldg(&C[j]);
-            if (c > p + CGX_MAX_RULE_SPAN - 1) break;
-            if (gap_check(gapw, p + L + 1, c - 1) == 2)
-                append_hit(((uint64_t)(uint32_t)d << 38) | ((uint64_t)(uint32_t)p << 8) | ((uint64_t)L << 4) | (uint64_t)(c - p), counter, hits, cap);
-        }
-    } else {
-        int c = C[e];
-        int j = lower_bound_hitpos(H, s_olo, s_ohi, c - (CGX_MAX_RULE_SPAN - 1));
-        for (; j < s_ohi; j++) {
-            uint64_t hk = H[j];
-            int p = (int)((hk >> 4) & 0x3fffffffu), L = (int)(hk & 15);
-            if (p > c - 4) break;
-            if (c < p + L + 2) continue;
-            if (gap_check(gapw, p + L + 1, c - 1) == 2)
-                append_hit(((uint64_t)(uint32_t)d << 38) | ((uint64_t)(uint32_t)p << 8) | ((uint64_t)L << 4) | (uint64_t)(c - p), counter, hits, cap);
-        }
-    }
+    const unsigned lane = threadIdx.x & 31;
+    for (int o = 16; o; o >>= 1) { active += __shfl_xor_sync(0xffffffffu, active, o); probes += __shfl_xor_sync(0xffffffffu, probes, o); }
+    if (lane == 0 && active) { atomicAdd(&counter[1], (unsigned long long)probes); atomicAdd(&counter[2], (unsigned long long)active); }
 }
 
 void stage_twogap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     b.hits2 = 0;
     const int D2 = b.D2;
     if (D2 == 0 || b.hits1 == 0) return;
-    CGX_REQUIRE(D2 < (1 << 26), "two-gap join: %d distinct patterns exceed the 26-bit key field", D2);
-    uint32_t *tiles = b.j_tiles.get<uint32_t>((size_t)D2 + 2);
-    uint32_t *tot = b.counters.get<uint32_t>(16);
+    CGX_REQUIRE(cgx_bits_for((uint64_t)D2) + b.pbits + 8 <= 64, "two-gap join: %d distinct patterns exceed the hit-key field", D2);
+    const uint32_t slots_n = ht_slots_for((size_t)D2);
+    ulonglong2 *slots = b.j_hash.get<ulonglong2>(slots_n);
+    uint8_t *has_child = b.j_aflag.get<uint8_t>((size_t)b.D1 + 4);
+    uint32_t *tot = b.counters.get<uint32_t>(32);
     unsigned long long *ctr = (unsigned long long *)(tot + 4);
-    j2_tiles_kernel<<<cgx_div_up(D2, 256), 256, 0, stream>>>(b.pat2.ptr<Pat2>(), b.pat1.ptr<Pat1>(), ix.tok_start.ptr<int32_t>(), D2, tiles);
-    exclusive_scan_u32(tiles, tiles, (size_t)D2, tot, stream, b.scan, 0, &b.launches);
-    uint32_t n_tiles = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&n_tiles, tot, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    CUDA_CHECK(cudaStreamSynchronize(stream));
+    CUDA_CHECK(cudaMemsetAsync(slots, 0xff, sizeof(ulonglong2) * (size_t)slots_n, stream));
+    CUDA_CHECK(cudaMemsetAsync(has_child, 0, (size_t)b.D1, stream));
+    PROF("join_setup", (double)D2 * (16 + 16), (j2_setup_kernel<<<cgx_div_up(D2, 256), 256, 0, stream>>>(b.pat2.ptr<Pat2>(), D2, slots, slots_n - 1, has_child)));
+    b.launches++;
+    const size_t H1 = (size_t)b.hits1;
+    unsigned long long host_ctr[3] = {0, 0, 0};
     while (true) {
         uint64_t *hits = b.hit_keys.get<uint64_t>(b.hit_cap);
-        CUDA_CHECK(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), stream));
-        if (n_tiles)
-            PROF("join_twogap", 0.0, (j2_join_kernel<<<n_tiles, JN_TILE, 0, stream>>>(b.pat2.ptr<Pat2>(), b.pat1.ptr<Pat1>(), D2, tiles, b.hits1_sorted.ptr<uint64_t>(),
-                                                           ix.inv[0].ptr<int32_t>(), ix.tok_start.ptr<int32_t>(), ix.gapw.ptr<uint32_t>(), ctr, hits, b.hit_cap)));
-        b.launches += 2;
-        unsigned long long H = read_u64(ctr, stream);
-        if (H <= b.hit_cap) { b.hits2 = (int64_t)H; break; }
-        b.hit_cap = (size_t)H + (size_t)H / 8 + 1024;
+        CUDA_CHECK(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long) * 3, stream));
+        PROF("join_twogap", 0.0, (j2_scan_kernel<<<cgx_div_up(H1, 256), 256, 0, stream>>>(b.hits1_sorted.ptr<uint64_t>(), H1, b.pbits, has_child, ix.str.ptr<int32_t>(),
+                                                           ix.gapw.ptr<uint32_t>(), slots, slots_n - 1, ctr, hits, b.hit_cap)));
+        b.launches += 1;
+        read_u64s(host_ctr, ctr, 3, stream);
+        if (host_ctr[0] <= b.hit_cap) { b.hits2 = (int64_t)host_ctr[0]; break; }
+        b.hit_cap = (size_t)host_ctr[0] + (size_t)host_ctr[0] / 8 + 1024;
     }
+    // algorithmic bytes: every parent hit read, gap word of the active ones, each candidate token, each hit written
+    prof_add_bytes("join_twogap", 8.0 * (double)H1 + 4.0 * (double)host_ctr[2] + 4.0 * (double)host_ctr[1] + 8.0 * (double)host_ctr[0]);
     if (b.hits2 == 0) return;
     const size_t H = (size_t)b.hits2;
     uint64_t *hits = b.hit_keys.ptr<uint64_t>();
     uint64_t *tmp = b.hit_keys_tmp.get<uint64_t>(H);
     uint64_t *hs;
-    radix_sort<uint64_t>(hits, tmp, nullptr, nullptr, H, 0, 38 + cgx_bits_for((uint64_t)D2), stream, b.radix, &hs, nullptr, &b.launches);
+    radix_sort<uint64_t>(hits, tmp, nullptr, nullptr, H, 0, b.pbits + 8 + cgx_bits_for((uint64_t)D2), stream, b.radix, &hs, nullptr, &b.launches);
     uint64_t *dst = b.hits2_sorted.get<uint64_t>(H);
     CUDA_CHECK(cudaMemcpyAsync(dst, hs, sizeof(uint64_t) * H, cudaMemcpyDeviceToDevice, stream));
     static_assert(sizeof(Pat2) == 16, "Pat2 layout");
-    hit_ranges_kernel<38><<<cgx_div_up(H, 256), 256, 0, stream>>>(dst, H, &b.pat2.ptr<int32_t>()[2], 4);
+    hit_ranges_kernel<<<cgx_div_up(H, 256), 256, 0, stream>>>(dst, H, b.pbits + 8, &b.pat2.ptr<int32_t>()[2], 4);
     hit_ranges_fix_kernel<<<cgx_div_up(D2, 256), 256, 0, stream>>>(&b.pat2.ptr<int32_t>()[2], D2, 4);
     b.launches += 2;
 }

@@ -156,7 +156,8 @@ __global__ void e1_enum_kernel(const int32_t *__restrict__ q_tok, const int32_t 
 __global__ void e1_patterns_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, const uint32_t *__restrict__ excl, int n,
                                    const int32_t *__restrict__ inst_t, const uint32_t *__restrict__ inst_info, const int32_t *__restrict__ iv,
                                    const int32_t *__restrict__ sa, const int32_t *__restrict__ str, const uint8_t *__restrict__ freq_rank,
-                                   int32_t *__restrict__ pid, Pat1 *__restrict__ pat, Pat1Dev *__restrict__ patd, int32_t *__restrict__ pat_pos) {
+                                   const int32_t *__restrict__ phrase_id, int32_t *__restrict__ pid, Pat1 *__restrict__ pat, Pat1Dev *__restrict__ patd,
+                                   int32_t *__restrict__ pat_pos, int32_t *__restrict__ pat_ga) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     bool head = (k == 0 || keys[k] != keys[k - 1]);
@@ -183,6 +184,7 @@ __global__ void e1_patterns_kernel(const uint64_t *__restrict__ keys, const uint
     }
     pat[d] = p;
     pat_pos[d] = k;
+    pat_ga[d] = phrase_id[(size_t)t * CGX_LONGEST_SRC + (ls - 1)];      // distinct-phrase id of a (drives the join scan)
 }
 
 // (query, pattern) pairs without duplicates: instances of one pattern are sorted by instance index,
@@ -269,10 +271,11 @@ void stage_onegap_enumerate(const Index &ix, Batch &b, cudaStream_t stream) {
     Pat1 *pat = b.pat1.get<Pat1>((size_t)b.D1);
     Pat1Dev *patd = b.pat1_dev.get<Pat1Dev>((size_t)b.D1);
     int32_t *pat_pos = b.pat1_pos.get<int32_t>((size_t)b.D1 + 1);
+    int32_t *pat_ga = b.pat1_ga.get<int32_t>((size_t)b.D1 + 1);
     int32_t *pid = b.e1_pid.get<int32_t>((size_t)E * 2);
     int32_t *qid = pid + E;
     e1_patterns_kernel<<<cgx_div_up(E, 256), 256, 0, stream>>>(ks, vals, flags, (int)E, inst_t, inst_info, iv, ix.sa.ptr<int32_t>(), ix.str.ptr<int32_t>(),
-                                                             ix.freq_flag.ptr<uint8_t>(), pid, pat, patd, pat_pos);
+                                                             ix.freq_flag.ptr<uint8_t>(), b.phrase_id.ptr<int32_t>(), pid, pat, patd, pat_pos, pat_ga);
     int32_t e_i = (int32_t)E;
     CUDA_CHECK(cudaMemcpyAsync(pat_pos + b.D1, &e_i, sizeof(int32_t), cudaMemcpyHostToDevice, stream));
     e1_sorted_qid_kernel<<<cgx_div_up(E, 256), 256, 0, stream>>>(vals, inst_t, tok2q, (int)E, qid);

@@ -65,7 +65,7 @@ typedef struct {
     int64_t n, m, lex_count;
     int32_t max_token;
     int32_t freq_list[100];
-    void *str, *sa, *inv1, *inv2, *inv3, *tok_start, *RLP, *L_tar, *R_tar, *tgt, *freq_flag, *gapw, *lex_key, *lex_v1, *lex_v2;
+    void *str, *sa, *inv1, *inv2, *inv3, *bkt1, *bkt2, *bkt3, *tok_start, *RLP, *L_tar, *R_tar, *tgt, *freq_flag, *gapw, *lex_key, *lex_v1, *lex_v2;
 } cgx_index_arrays_t;
 int cgx_index_export(cgx_ctx_t *ctx, cgx_index_arrays_t *out);            /* pointers stay owned by ctx */
 int cgx_index_alloc(cgx_ctx_t *ctx, const cgx_index_arrays_t *shape, cgx_index_arrays_t *out);  /* allocate empty arrays of that shape on this ctx */
