@@ -54,7 +54,7 @@ extern "C" void cgx_destroy(cgx_ctx_t *c) {
     cudaStreamSynchronize(c->stream);
     Index &ix = c->ix;
     DevBuf *ib[] = {&ix.str, &ix.sa, &ix.inv[0], &ix.inv[1], &ix.inv[2], &ix.bkt[0], &ix.bkt[1], &ix.bkt[2], &ix.tok_start, &ix.RLP, &ix.L_tar, &ix.R_tar, &ix.tgt, &ix.freq_flag, &ix.gapw,
-                    &ix.lex_key, &ix.lex_v1, &ix.lex_v2};
+                    &ix.lex_key, &ix.lex_v1, &ix.lex_v2, &ix.lex_hash};
     for (auto *b : ib) b->release();
     c->ws.release();
     Batch &b = c->batch;
@@ -63,7 +63,7 @@ extern "C" void cgx_destroy(cgx_ctx_t *c) {
                     &b.pat1_dev, &b.pat1_pos, &b.ql_keys, &b.ql_keys_tmp, &b.q1_off, &b.q1_ids, &b.q2_off, &b.q2_ids, &b.j_tiles, &b.j_bitmaps, &b.j_aflag, &b.j_hash, &b.pat1_ga, &b.hit_keys,
                     &b.hit_keys_tmp, &b.counters, &b.missing, &b.hits1_sorted, &b.hits2_sorted, &b.e2_count, &b.e2_keys, &b.e2_keys_tmp, &b.e2_vals,
                     &b.e2_vals_tmp, &b.e2_flags, &b.pat2, &b.rec_hash, &b.rec_idx, &b.rec_idx_tmp, &b.rec_keys, &b.rec_keys_tmp, &b.rec_flags,
-                    &b.scratch, &b.scratch2, &b.radix.hist, &b.radix.status, &b.radix.counters};
+                    &b.scratch, &b.scratch2, &b.rule_head, &b.radix.hist, &b.radix.status, &b.radix.counters};
     for (auto *x : bb) x->release();
     for (int k = 0; k < 3; k++) { b.slot_off[k].release(); b.rec[k].release(); b.rec_sorted[k].release(); b.rules[k].release(); b.updown[k].release(); b.id_count[k].release(); }
     for (auto &l : b.scan.level) l.release();
@@ -174,7 +174,7 @@ extern "C" int cgx_lex_load(cgx_ctx_t *c, const int32_t *f, const int32_t *e, co
         ix.lex_count = n;
         uint64_t *keys = ix.lex_key.get<uint64_t>(n + 1);
         float *o1 = ix.lex_v1.get<float>(n + 1), *o2 = ix.lex_v2.get<float>(n + 1);
-        if (n == 0) return 0;
+        if (n == 0) { build_lex_hash(ix, c->stream); return 0; }
         DevBuf df, de, d1, d2, kt, ix0, ix1, ksrc;
         RadixTemp rt;
         int32_t *pf = df.get<int32_t>(n), *pe = de.get<int32_t>(n);
@@ -192,6 +192,7 @@ extern "C" int cgx_lex_load(cgx_ctx_t *c, const int32_t *f, const int32_t *e, co
         CUDA_CHECK(cudaMemcpyAsync(keys, ks, sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice, c->stream));
         lex_gather_kernel<<<cgx_div_up(n, 256), 256, 0, c->stream>>>(is, p1, p2, n, o1, o2);
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        build_lex_hash(ix, c->stream);
         DevBuf *tmp[] = {&df, &de, &d1, &d2, &kt, &ix0, &ix1, &ksrc, &rt.hist, &rt.status, &rt.counters};
         for (auto *t : tmp) t->release();
     });
@@ -204,7 +205,7 @@ extern "C" int cgx_index_info(const cgx_ctx_t *c, cgx_index_info_t *out) {
     out->sa_rounds = ix.sa_stats.rounds; out->sa_key_bits = ix.sa_stats.key_bits; out->sa_launches = ix.sa_stats.launches;
     out->sa_build_ms = ix.sa_stats.ms; out->aux_build_ms = c->aux_ms;
     out->index_bytes = (int64_t)(ix.str.cap + ix.sa.cap + ix.inv[0].cap + ix.inv[1].cap + ix.inv[2].cap + ix.bkt[0].cap + ix.bkt[1].cap + ix.bkt[2].cap + ix.tok_start.cap + ix.RLP.cap + ix.L_tar.cap +
-                                 ix.R_tar.cap + ix.tgt.cap + ix.freq_flag.cap + ix.gapw.cap + ix.lex_key.cap + ix.lex_v1.cap + ix.lex_v2.cap);
+                                 ix.R_tar.cap + ix.tgt.cap + ix.freq_flag.cap + ix.gapw.cap + ix.lex_key.cap + ix.lex_v1.cap + ix.lex_v2.cap + ix.lex_hash.cap);
     return 0;
 }
 
@@ -242,9 +243,12 @@ extern "C" int cgx_index_alloc(cgx_ctx_t *c, const cgx_index_arrays_t *s, cgx_in
 }
 
 extern "C" int cgx_index_commit(cgx_ctx_t *c) {
-    if (!c) return 1;
-    c->ix.built = true;
-    return 0;
+    CGX_TRY(c, {
+        CGX_REQUIRE(c, "null context");
+        CUDA_CHECK(cudaSetDevice(c->device));
+        build_lex_hash(c->ix, c->stream);          // derived from the (broadcast) sorted lexical arrays
+        c->ix.built = true;
+    });
 }
 
 extern "C" int cgx_index_copy_sa(cgx_ctx_t *c, int32_t *out) {
@@ -277,6 +281,7 @@ static void run_batch(cgx_ctx *c, int32_t Q, int32_t T, bool fetch) {
     const Index &ix = c->ix;
     cudaStream_t s = c->stream;
     b.fetch_results = fetch;
+    if (!ix.lex_hash.p) build_lex_hash(c->ix, s);      // no lexical table loaded: an empty one (every weight = MAXSCORE)
     c->prof.stream = s;
     g_prof = &c->prof;
     stage_lookup(ix, b, s);

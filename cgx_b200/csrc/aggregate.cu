@@ -12,9 +12,11 @@
 // id, all_suffix_fsample from the pattern tables.  Exactness does not rest on the hash: every record is
 // compared symbol-by-symbol with its predecessor in the run, and a mismatch raises a flag on which the
 // host re-runs the aggregation with another hash seed.
-// Lexical weights: one thread per distinct rule, binary search in the (f,e)-sorted lexical table
-// (L2-resident: 16 B/entry), -log10 through the same lg2.approx path the reference's -use_fast_math build takes.
+// Lexical weights: one thread per distinct rule; every (f,e) pair is ONE probe of the lexical hash table (16-byte
+// slots holding both directions' values; 2^21 slots = 32 MB at C2, L2-resident) instead of a 20-step binary search;
+// -log10 through the same lg2.approx path the reference's -use_fast_math build takes.
 #include "batch.h"
+#include "hash.cuh"
 #include "prof.h"
 
 namespace cgx {
@@ -110,40 +112,36 @@ __device__ __forceinline__ int source_terminals(const AggIdx &a, int kind, int i
     return n;
 }
 
-// ExtractPair.cu:2108-2142 searchLexFile: value of (f,e) or 0 when absent
-__device__ __forceinline__ float lex_get(const uint64_t *__restrict__ keys, const float *__restrict__ vals, int count, int f, int e) {
-    uint64_t k = ((uint64_t)(uint32_t)(f + 1) << 32) | (uint64_t)(uint32_t)(e + 1);
-    int lo = 0, hi = count;
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        uint64_t v = __ldg(&keys[mid]);
-        if (v < k) lo = mid + 1; else hi = mid;
-    }
-    if (lo < count && __ldg(&keys[lo]) == k) return __ldg(&vals[lo]);
-    return 0.0f;
+// ExtractPair.cu:2108-2142 searchLexFile: both values of (f,e) in one probe of the lexical hash table; absent -> 0
+__device__ __forceinline__ void lex_get(const ulonglong2 *__restrict__ slots, uint32_t mask, int f, int e, float *v1, float *v2) {
+    const uint64_t k = ((uint64_t)(uint32_t)(f + 1) << 32) | (uint64_t)(uint32_t)(e + 1);
+    uint64_t pay;
+    if (ht_find(slots, mask, k, &pay)) { *v1 = __uint_as_float((uint32_t)pay); *v2 = __uint_as_float((uint32_t)(pay >> 32)); }
+    else { *v1 = 0.f; *v2 = 0.f; }
+}
+
+// head_pos[r] = sorted index of the first record of rule r (excl = exclusive scan of the head flags); head_pos[R] = n
+__global__ void agg_head_pos_kernel(const uint32_t *__restrict__ excl, size_t n, uint32_t n_rules, uint32_t *__restrict__ head_pos) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t e = excl[i];
+    const uint32_t nxt = (i + 1 < n) ? excl[i + 1] : n_rules;
+    if (nxt != e) head_pos[e] = (uint32_t)i;
+    if (i == 0) head_pos[n_rules] = (uint32_t)n;
 }
 
 // One thread per distinct rule: paircount, f, fs, representative record, lexical weights.
 __global__ void __launch_bounds__(128) agg_rules_kernel(AggIdx a, int kind, const RuleRec *__restrict__ rec, const uint32_t *__restrict__ idx,
-                                                        const uint32_t *__restrict__ excl, size_t n, uint32_t n_rules,
-                                                        const uint32_t *__restrict__ id_count, const uint64_t *__restrict__ lex_key,
-                                                        const float *__restrict__ lex_v1, const float *__restrict__ lex_v2, int lex_count,
+                                                        const uint32_t *__restrict__ head_pos, uint32_t n_rules,
+                                                        const uint32_t *__restrict__ id_count, const ulonglong2 *__restrict__ lex, uint32_t lex_mask,
                                                         cgx_rule_t *__restrict__ rules) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rules) return;
-    // excl = exclusive scan of the head flags: the head of rule r has excl == r, the other members of its
-    // run (and the head of rule r+1) have excl == r+1.  Hence head(r) = last index with excl <= r.
-    size_t lo = 0, hi = n;
-    while (lo < hi) { size_t mid = (lo + hi) >> 1; if (excl[mid] <= r) lo = mid + 1; else hi = mid; }
-    const size_t head = lo - 1;                    // last index with excl <= r  == the head of rule r
-    size_t lo2 = head + 1, hi2 = n;                // end of run: last index with excl <= r+1
-    while (lo2 < hi2) { size_t mid = (lo2 + hi2) >> 1; if (excl[mid] <= r + 1) lo2 = mid + 1; else hi2 = mid; }
-    const size_t run_end = lo2 - 1;                // head of the next rule (or n-1 when none)
-    const size_t next_head = (r + 1 < n_rules) ? run_end : n;
+    const uint32_t head = head_pos[r], next_head = head_pos[r + 1];
     const int pc = (int)(next_head - head);
-    // deterministic representative: smallest (tgt_start, packed span) of the run
+    // deterministic representative: smallest tgt_start of the run
     RuleRec best = rec[idx[head]];
-    for (size_t i = head + 1; i < next_head; i++) {
+    for (uint32_t i = head + 1; i < next_head; i++) {
         RuleRec c = rec[idx[i]];
         if (c.tgt_start < best.tgt_start) best = c;
     }
@@ -155,30 +153,42 @@ __global__ void __launch_bounds__(128) agg_rules_kernel(AggIdx a, int kind, cons
     out.f = (int)id_count[best.id];
     int fs = fsample_of(a, kind, best.id);
     out.fs = fs > CGX_SAMPLER ? CGX_SAMPLER : fs;                          // ExtractPair.c:638,910,1249
-    // ---- lexicalTaskMaxEF (ExtractPair.cu:2144-2432)
+    // ---- lexicalTaskMaxEF (ExtractPair.cu:2144-2432): for every source terminal the best MaxLexFgivenE over the target
+    // terminals (and NULL), for every target terminal the best MaxLexEgivenF over the source terminals (and NULL).  One
+    // table probe serves both directions of a (f, e) pair.
     int32_t F[8];
     const int nf = source_terminals(a, kind, best.id, F);
-    float fgivene = 0.f, egivenf = 0.f;
+    float mxf[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) mxf[j] = 0.f;
+    float egivenf = 0.f, v1, v2;
+    bool any_e = false;
     const int ts = best.tgt_start;
-    for (int j = 0; j < nf; j++) {
-        float mx = 0.f;
-        bool first = true;
-        for (int jj = 0; jj <= (int)best.end; jj++) {
-            if (best.gap1 != 255 && jj >= (int)best.gap1 && jj <= (int)best.gap1_1) continue;
-            if (best.gap2 != 255 && jj >= (int)best.gap2 && jj <= (int)best.gap2_1) continue;
-            if (first) { mx = fmaxf(mx, lex_get(lex_key, lex_v2, lex_count, F[j], -1)); first = false; }
-            mx = fmaxf(mx, lex_get(lex_key, lex_v2, lex_count, F[j], __ldg(&a.tgt[ts + jj])));
-        }
-        fgivene += mx > 0.f ? -__log10f(mx) : CGX_MAXSCORE;
-    }
     for (int jj = 0; jj <= (int)best.end; jj++) {
         if (best.gap1 != 255 && jj >= (int)best.gap1 && jj <= (int)best.gap1_1) continue;
         if (best.gap2 != 255 && jj >= (int)best.gap2 && jj <= (int)best.gap2_1) continue;
+        any_e = true;
         const int e = __ldg(&a.tgt[ts + jj]);
         float mx = 0.f;
-        if (nf > 0) mx = fmaxf(mx, lex_get(lex_key, lex_v1, lex_count, -1, e));
-        for (int j = 0; j < nf; j++) mx = fmaxf(mx, lex_get(lex_key, lex_v1, lex_count, F[j], e));
+        if (nf > 0) { lex_get(lex, lex_mask, -1, e, &v1, &v2); mx = fmaxf(mx, v1); }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (j < nf) {
+                lex_get(lex, lex_mask, F[j], e, &v1, &v2);
+                mx = fmaxf(mx, v1);
+                mxf[j] = fmaxf(mxf[j], v2);
+            }
+        }
         egivenf += mx > 0.f ? -__log10f(mx) : CGX_MAXSCORE;
+    }
+    float fgivene = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        if (j < nf) {
+            float mx = mxf[j];
+            if (any_e) { lex_get(lex, lex_mask, F[j], -1, &v1, &v2); mx = fmaxf(mx, v2); }
+            fgivene += mx > 0.f ? -__log10f(mx) : CGX_MAXSCORE;
+        }
     }
     out.max_lex_f_given_e = fgivene;
     out.max_lex_e_given_f = egivenf;
@@ -245,8 +255,11 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
             if (hostv[14] == 0) {
                 R = hostv[0];
                 cgx_rule_t *rules = b.rules[kind].get<cgx_rule_t>(R);
-                PROF("agg_rules", (double)R * 36 + (double)N * 20, (agg_rules_kernel<<<cgx_div_up(R, 128), 128, 0, stream>>>(a, kind, rec, is2, flags, N, R, id_count, ix.lex_key.ptr<uint64_t>(),
-                                                                       ix.lex_v1.ptr<float>(), ix.lex_v2.ptr<float>(), (int)ix.lex_count, rules)));
+                uint32_t *head_pos = b.rule_head.get<uint32_t>((size_t)R + 2);
+                agg_head_pos_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(flags, N, R, head_pos);
+                PROF("agg_rules", (double)R * 36 + (double)N * 20, (agg_rules_kernel<<<cgx_div_up(R, 128), 128, 0, stream>>>(a, kind, rec, is2, head_pos, R, id_count,
+                                                                       ix.lex_hash.ptr<ulonglong2>(), ix.lex_hash_mask, rules)));
+                b.launches++;
                 CUDA_CHECK(cudaMemsetAsync(updown, 0xff, sizeof(int32_t) * 2 * (size_t)nids[kind], stream));
                 agg_updown_kernel<<<cgx_div_up(R, 256), 256, 0, stream>>>(rules, R, updown);
                 b.launches += 2;

@@ -58,7 +58,7 @@ struct Batch {
     int64_t n_rec[3] = {0, 0, 0};
     int64_t samples = 0;
     // rules
-    DevBuf rules[3], updown[3], id_count[3];
+    DevBuf rules[3], updown[3], id_count[3], rule_head;
     int32_t n_rules[3] = {0, 0, 0};
     int32_t n_ids[3] = {0, 0, 0};
     // temp

@@ -1,5 +1,6 @@
 // cgx-b200: auxiliary index arrays built once per corpus, on the GPU, after the suffix array.
 #include "index.h"
+#include "hash.cuh"
 #include <algorithm>
 #include <vector>
 
@@ -80,6 +81,25 @@ __global__ void ix_gap_words_kernel(const int32_t *__restrict__ str, const uint3
         }
     }
     gapw[i] = word;
+}
+
+// lexical table -> hash.  Duplicate (f,e) rows: the first of the (stably) sorted run wins, like the binary search it replaces.
+__global__ void ix_lex_hash_kernel(const uint64_t *__restrict__ keys, const float *__restrict__ v1, const float *__restrict__ v2, size_t n,
+                                   ulonglong2 *__restrict__ slots, uint32_t mask) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || (i > 0 && keys[i] == keys[i - 1])) return;
+    ht_insert(slots, mask, keys[i], (uint64_t)__float_as_uint(v1[i]) | ((uint64_t)__float_as_uint(v2[i]) << 32));
+}
+
+void build_lex_hash(Index &ix, cudaStream_t stream) {
+    const uint32_t slots_n = ht_slots_for(ix.lex_count);
+    ulonglong2 *slots = ix.lex_hash.get<ulonglong2>(slots_n);
+    ix.lex_hash_mask = slots_n - 1;
+    CUDA_CHECK(cudaMemsetAsync(slots, 0xff, sizeof(ulonglong2) * (size_t)slots_n, stream));
+    if (ix.lex_count)
+        ix_lex_hash_kernel<<<cgx_div_up(ix.lex_count, 256), 256, 0, stream>>>(ix.lex_key.ptr<uint64_t>(), ix.lex_v1.ptr<float>(), ix.lex_v2.ptr<float>(), ix.lex_count, slots,
+                                                                            ix.lex_hash_mask);
+    CUDA_CHECK(cudaStreamSynchronize(stream));
 }
 
 // SuffixArray.cu:1148-1198: the PRECOMPUTECOUNT most frequent tokens (frequency descending, ties by

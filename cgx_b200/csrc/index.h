@@ -46,17 +46,21 @@ void build_suffix_array(const int32_t *d_str, size_t n, int32_t maxtok, int32_t 
 //                         (capped at 15).  Turns the per-candidate gap test of the joins into one word load.
 //   freq_flag uint8 [maxtok+2]  rank+1 among the PRECOMPUTECOUNT most frequent source tokens, else 0
 //   lex_key uint64 [L] / lex_v1, lex_v2 float [L]  lexical table sorted by (f+1)<<32 | (e+1)
+//   lex_hash 16 B x 2^k    the same table as an open-addressing hash (key -> v1 | v2 << 32): one probe per lookup
+//                         instead of log2(L) dependent loads (rebuilt locally from the sorted arrays after a broadcast)
 struct Index {
     size_t n = 0, m = 0;
     int32_t maxtok = 0;
     DevBuf str, sa, inv[3], bkt[3], tok_start, RLP, L_tar, R_tar, tgt, freq_flag, gapw;
-    DevBuf lex_key, lex_v1, lex_v2;
+    DevBuf lex_key, lex_v1, lex_v2, lex_hash;
     size_t lex_count = 0;
+    uint32_t lex_hash_mask = 0;
     int32_t freq_list[CGX_PRECOMP];
     bool built = false;
     SaStats sa_stats;
 };
 
 void build_index_aux(Index &ix, SaWorkspace &ws, cudaStream_t stream, int *launches);
+void build_lex_hash(Index &ix, cudaStream_t stream);
 
 }  // namespace cgx

@@ -32,45 +32,10 @@
 // children; the second gap's word gapw[p+L+1] yields the admissible widths g2 <= 13-L, and for each the token
 // c = str[p+L+1+g2] is looked up as (parent pattern, c) in a second hash table.
 #include "batch.h"
+#include "hash.cuh"
 #include "prof.h"
 
 namespace cgx {
-
-// ------------------------------------------------------------------------------------------------
-// per-batch hash table: 64-bit key -> 32-bit value, linear probing, 16-byte slots
-// ------------------------------------------------------------------------------------------------
-constexpr uint64_t HT_EMPTY = ~0ull;
-
-__device__ __forceinline__ uint64_t ht_mix(uint64_t z) {
-    z ^= z >> 33; z *= 0xff51afd7ed558ccdULL; z ^= z >> 33; z *= 0xc4ceb9fe1a85ec53ULL; z ^= z >> 33;
-    return z;
-}
-
-__device__ __forceinline__ void ht_insert(ulonglong2 *__restrict__ slots, uint32_t mask, uint64_t key, uint32_t val) {
-    uint32_t s = (uint32_t)ht_mix(key) & mask;
-    while (true) {
-        unsigned long long prev = atomicCAS(&slots[s].x, (unsigned long long)HT_EMPTY, (unsigned long long)key);
-        if (prev == HT_EMPTY || prev == key) { slots[s].y = val; return; }
-        s = (s + 1) & mask;
-    }
-}
-
-// returns the value or 0xFFFFFFFF
-__device__ __forceinline__ uint32_t ht_find(const ulonglong2 *__restrict__ slots, uint32_t mask, uint64_t key) {
-    uint32_t s = (uint32_t)ht_mix(key) & mask;
-    while (true) {
-        const ulonglong2 v = __ldg(&slots[s]);
-        if (v.x == key) return (uint32_t)v.y;
-        if (v.x == HT_EMPTY) return 0xFFFFFFFFu;
-        s = (s + 1) & mask;
-    }
-}
-
-static uint32_t ht_slots_for(size_t entries) {      // power of two, load factor <= 0.5
-    uint32_t s = 1024;
-    while ((size_t)s < 2 * entries) s <<= 1;
-    return s;
-}
 
 __device__ __forceinline__ uint64_t key1_of(uint32_t phrase_a, int le, uint32_t bucket_b) {
     return ((uint64_t)phrase_a << 32) | ((uint64_t)le << 30) | (uint64_t)bucket_b;
@@ -183,8 +148,8 @@ __global__ void __launch_bounds__(J1_BLOCK) j1_scan_kernel(const J1Args a) {
                 const uint32_t ub = (uint32_t)__ldg(&a.bkt[le - 1][q]);
                 probes++;
                 if (!bit_test(a.bm[le - 1], ub)) continue;
-                const uint32_t v = ht_find(a.slots, a.mask, key1_of((uint32_t)ga, le, ub));
-                if (v == 0xFFFFFFFFu) continue;
+                uint64_t v;
+                if (!ht_find(a.slots, a.mask, key1_of((uint32_t)ga, le, ub), &v)) continue;
                 const uint64_t key = ((uint64_t)(v & 0x7fffffffu) << a.pshift) | ((uint64_t)(uint32_t)p << 4) | (uint64_t)(ls + g + le - 1);
                 append_hit(key, &a.counter[0], a.hits, a.cap);
             }
@@ -192,8 +157,8 @@ __global__ void __launch_bounds__(J1_BLOCK) j1_scan_kernel(const J1Args a) {
             const uint32_t ub = (uint32_t)__ldg(&a.bkt[0][q]);
             probes++;
             if (bit_test(a.bm_marker, ub)) {
-                const uint32_t v = ht_find(a.slots, a.mask, key1_of((uint32_t)ga, 1, ub));
-                if (v != 0xFFFFFFFFu && (v & 0x80000000u)) atomicAdd(&a.missing[v & 0x7fffffffu], 1);
+                uint64_t v;
+                if (ht_find(a.slots, a.mask, key1_of((uint32_t)ga, 1, ub), &v) && (v & 0x80000000u)) atomicAdd(&a.missing[v & 0x7fffffffu], 1);
             }
         }
     }
@@ -327,8 +292,8 @@ __global__ void __launch_bounds__(256) j2_scan_kernel(const uint64_t *__restrict
                 const int r = p + L + 1 + g2;
                 const uint32_t c = (uint32_t)__ldg(&str[r]);
                 probes++;
-                const uint32_t d2 = ht_find(slots, mask, ((uint64_t)d1 << 32) | (uint64_t)c);
-                if (d2 != 0xFFFFFFFFu)
+                uint64_t d2;
+                if (ht_find(slots, mask, ((uint64_t)d1 << 32) | (uint64_t)c, &d2))
                     append_hit(((uint64_t)d2 << (pbits + 8)) | ((uint64_t)(uint32_t)p << 8) | ((uint64_t)L << 4) | (uint64_t)(r - p), &counter[0], hits, cap);
             }
         }
