@@ -41,14 +41,28 @@ __device__ __forceinline__ uint64_t key1_of(uint32_t phrase_a, int le, uint32_t 
     return ((uint64_t)phrase_a << 32) | ((uint64_t)le << 30) | (uint64_t)bucket_b;
 }
 
-__device__ __forceinline__ void append_hit(uint64_t key, unsigned long long *counter, uint64_t *out, size_t cap) {
-    unsigned m = __activemask();
-    int leader = __ffs(m) - 1;
+// Hits are staged per warp in shared memory and flushed with ONE global atomic per ~200 hits (a single counter
+// hit by one atomic per few hits serialises the whole grid: 56 % of the stall samples of round 1b's kernel).
+constexpr int ST_CAP = 256;                    // staged keys per warp
+
+__device__ __forceinline__ void stage_push(bool found, uint64_t key, uint64_t *__restrict__ buf, int &count) {   // all 32 lanes call
+    const unsigned m = __ballot_sync(0xffffffffu, found);
+    if (found) buf[count + __popc(m & lanemask_lt())] = key;
+    count += __popc(m);
+}
+
+__device__ __forceinline__ void stage_flush(uint64_t *__restrict__ buf, int &count, unsigned long long *__restrict__ counter, uint64_t *__restrict__ out,
+                                            size_t cap) {                                                    // all 32 lanes call
+    if (count == 0) return;
+    __syncwarp();
+    const unsigned lane = threadIdx.x & 31;
     unsigned long long base = 0;
-    if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
-    base = __shfl_sync(m, base, leader);
-    size_t slot = (size_t)base + __popc(m & lanemask_lt());
-    if (slot < cap) out[slot] = key;
+    if (lane == 0) base = atomicAdd(counter, (unsigned long long)count);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (int i = (int)lane; i < count; i += 32)
+        if ((size_t)base + i < cap) out[(size_t)base + i] = buf[i];
+    __syncwarp();
+    count = 0;
 }
 
 __device__ __forceinline__ bool bit_test(const uint32_t *__restrict__ bm, uint32_t i) { return (__ldg(&bm[i >> 5]) >> (i & 31)) & 1u; }
@@ -113,55 +127,64 @@ struct J1Args {
 };
 
 __global__ void __launch_bounds__(J1_BLOCK) j1_scan_kernel(const J1Args a) {
+    __shared__ uint64_t s_stage[J1_BLOCK / 32][ST_CAP];
+    uint64_t *stage = s_stage[threadIdx.x >> 5];
+    int staged = 0;
     const unsigned lane = threadIdx.x & 31;
     const uint32_t e = (blockIdx.x * (uint32_t)J1_BLOCK + threadIdx.x);      // one element per lane, then 2 elements per warp step
-    // ---- lane-parallel: owner phrase and corpus position of 32 consecutive elements
-    int my_g = -1, my_len = 0, my_p = 0, my_f = 0;
+    // ---- lane-parallel: owner phrase, corpus position and gap word of 32 consecutive elements
+    int my_g = -1, my_len = 0, my_p = 0;
+    uint32_t my_w = 0;
     if (e < a.n_elems) {
         my_g = find_owner(a.elem_off, a.G, e);
         const int up = a.phrases[my_g * 4];
         my_len = a.phrases[my_g * 4 + 2];
         my_p = __ldg(&a.inv[my_len - 1][up + (int)(e - a.elem_off[my_g])]);
-        my_f = (int)((a.aflag[my_g] >> 1) & 1u);
+        my_w = __ldg(&a.gapw[my_p + my_len]) | (((a.aflag[my_g] >> 1) & 1u) << 31);      // bit 31: a is a frequent single token
     }
     const unsigned half = lane >> 4, h = lane & 15;
     const int g = (int)h + 1;                                              // gap width of this lane
     unsigned probes = 0;
-#pragma unroll 1
+#pragma unroll 2
     for (int it = 0; it < 16; it++) {
         const int src = it * 2 + (int)half;
         const int ga = __shfl_sync(0xffffffffu, my_g, src);
         const int ls = __shfl_sync(0xffffffffu, my_len, src);
         const int p = __shfl_sync(0xffffffffu, my_p, src);
-        const int fa = __shfl_sync(0xffffffffu, my_f, src);
-        if (ga < 0) continue;
-        const uint32_t w = __ldg(&a.gapw[p + ls]);
+        const uint32_t w = __shfl_sync(0xffffffffu, my_w, src);
         const int run = (int)((w >> 16) & 15u);
-        if (g > run || g > CGX_MAX_RULE_SPAN - 1 - ls) continue;           // a token < 2 inside the gap, or no room for b
-        const bool ok = (w >> (g - 1)) & 1u;
-        if (!ok && !fa) continue;
+        // lane is live when its width leaves every gap token >= 2 and room for b
+        const bool live = ga >= 0 && g <= run && g <= CGX_MAX_RULE_SPAN - 1 - ls;
+        const bool ok = live && ((w >> (g - 1)) & 1u);
+        const bool miss = live && !ok && (w >> 31);                       // frequent single token a: count what the pair table would miss
         const uint32_t q = (uint32_t)(p + ls + g);
         const int le_max = min(min(3, CGX_MAX_RULE_SYMBOLS - 1 - ls), CGX_MAX_RULE_SPAN - ls - g);
-        if (ok) {
-            for (int le = 1; le <= le_max; le++) {
-                if (q + (uint32_t)le > a.n) break;
-                const uint32_t ub = (uint32_t)__ldg(&a.bkt[le - 1][q]);
-                probes++;
-                if (!bit_test(a.bm[le - 1], ub)) continue;
-                uint64_t v;
-                if (!ht_find(a.slots, a.mask, key1_of((uint32_t)ga, le, ub), &v)) continue;
-                const uint64_t key = ((uint64_t)(v & 0x7fffffffu) << a.pshift) | ((uint64_t)(uint32_t)p << 4) | (uint64_t)(ls + g + le - 1);
-                append_hit(key, &a.counter[0], a.hits, a.cap);
-            }
-        } else if (q < a.n) {                                              // frequent single token a: count what the pair table would miss
-            const uint32_t ub = (uint32_t)__ldg(&a.bkt[0][q]);
-            probes++;
-            if (bit_test(a.bm_marker, ub)) {
-                uint64_t v;
-                if (ht_find(a.slots, a.mask, key1_of((uint32_t)ga, 1, ub), &v) && (v & 0x80000000u)) atomicAdd(&a.missing[v & 0x7fffffffu], 1);
-            }
+        // independent loads first: the canonical ids of the 1-, 2-, 3-grams at q, then their filter bits
+        uint32_t ub[3];
+        bool cand[3];
+#pragma unroll
+        for (int le = 1; le <= 3; le++) {
+            cand[le - 1] = (ok && le <= le_max && q + (uint32_t)le <= a.n) || (miss && le == 1 && q < a.n);
+            ub[le - 1] = cand[le - 1] ? (uint32_t)__ldg(&a.bkt[le - 1][q]) : 0u;
+            probes += cand[le - 1] ? 1u : 0u;
         }
+#pragma unroll
+        for (int le = 1; le <= 3; le++)
+            if (cand[le - 1]) cand[le - 1] = bit_test((le == 1 && miss) ? a.bm_marker : a.bm[le - 1], ub[le - 1]);
+#pragma unroll
+        for (int le = 1; le <= 3; le++) {
+            uint64_t v = 0;
+            bool found = cand[le - 1] && ht_find(a.slots, a.mask, key1_of((uint32_t)ga, le, ub[le - 1]), &v);
+            if (found && miss) {                                           // only le == 1 reaches here with miss set
+                if (v & 0x80000000u) atomicAdd(&a.missing[v & 0x7fffffffu], 1);
+                found = false;
+            }
+            const uint64_t key = ((uint64_t)(v & 0x7fffffffu) << a.pshift) | ((uint64_t)(uint32_t)p << 4) | (uint64_t)(ls + g + le - 1);
+            stage_push(found, key, stage, staged);
+        }
+        if (staged > ST_CAP - 96) stage_flush(stage, staged, &a.counter[0], a.hits, a.cap);
     }
+    stage_flush(stage, staged, &a.counter[0], a.hits, a.cap);
     for (int o = 16; o; o >>= 1) probes += __shfl_xor_sync(0xffffffffu, probes, o);
     if (lane == 0 && probes) atomicAdd(&a.counter[1], (unsigned long long)probes);
 }
@@ -274,33 +297,46 @@ __global__ void __launch_bounds__(256) j2_scan_kernel(const uint64_t *__restrict
                                                       const int32_t *__restrict__ str, const uint32_t *__restrict__ gapw,
                                                       const ulonglong2 *__restrict__ slots, uint32_t mask,
                                                       unsigned long long *__restrict__ counter, uint64_t *__restrict__ hits, size_t cap) {
+    __shared__ uint64_t s_stage[256 / 32][ST_CAP];
+    uint64_t *stage = s_stage[threadIdx.x >> 5];
+    int staged = 0;
     const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned active = 0, probes = 0;
+    uint32_t bits = 0, d1 = 0;
+    int p = 0, L = 0;
     if (k < H1) {
         const uint64_t hk = hits1[k];
-        const uint32_t d1 = (uint32_t)(hk >> (pbits + 4));
+        d1 = (uint32_t)(hk >> (pbits + 4));
         if (has_child[d1]) {
-            const int p = (int)((hk >> 4) & ((1ull << pbits) - 1)), L = (int)(hk & 15);
+            p = (int)((hk >> 4) & ((1ull << pbits) - 1)); L = (int)(hk & 15);
             const uint32_t w = __ldg(&gapw[p + L + 1]);
             const int run = (int)((w >> 16) & 15u);
             const int gmax = min(run, CGX_MAX_RULE_SPAN - 2 - L);
-            uint32_t bits = gmax > 0 ? (w & ((1u << gmax) - 1u)) : 0u;
+            bits = gmax > 0 ? (w & ((1u << gmax) - 1u)) : 0u;
             active = 1;
-            while (bits) {
-                const int g2 = __ffs(bits);
-                bits &= bits - 1;
-                const int r = p + L + 1 + g2;
-                const uint32_t c = (uint32_t)__ldg(&str[r]);
-                probes++;
-                uint64_t d2;
-                if (ht_find(slots, mask, ((uint64_t)d1 << 32) | (uint64_t)c, &d2))
-                    append_hit(((uint64_t)d2 << (pbits + 8)) | ((uint64_t)(uint32_t)p << 8) | ((uint64_t)L << 4) | (uint64_t)(r - p), &counter[0], hits, cap);
-            }
         }
     }
-    const unsigned lane = threadIdx.x & 31;
+    while (__any_sync(0xffffffffu, bits != 0)) {                       // every round each lane tries its next admissible width
+        bool found = false;
+        uint64_t key = 0;
+        if (bits) {
+            const int g2 = __ffs(bits);
+            bits &= bits - 1;
+            const int r = p + L + 1 + g2;
+            const uint32_t c = (uint32_t)__ldg(&str[r]);
+            probes++;
+            uint64_t d2;
+            if (ht_find(slots, mask, ((uint64_t)d1 << 32) | (uint64_t)c, &d2)) {
+                found = true;
+                key = (d2 << (pbits + 8)) | ((uint64_t)(uint32_t)p << 8) | ((uint64_t)L << 4) | (uint64_t)(r - p);
+            }
+        }
+        stage_push(found, key, stage, staged);
+        if (staged > ST_CAP - 32) stage_flush(stage, staged, &counter[0], hits, cap);
+    }
+    stage_flush(stage, staged, &counter[0], hits, cap);
     for (int o = 16; o; o >>= 1) { active += __shfl_xor_sync(0xffffffffu, active, o); probes += __shfl_xor_sync(0xffffffffu, probes, o); }
-    if (lane == 0 && active) { atomicAdd(&counter[1], (unsigned long long)probes); atomicAdd(&counter[2], (unsigned long long)active); }
+    if ((threadIdx.x & 31) == 0 && active) { atomicAdd(&counter[1], (unsigned long long)probes); atomicAdd(&counter[2], (unsigned long long)active); }
 }
 
 void stage_twogap_join(const Index &ix, Batch &b, cudaStream_t stream) {
