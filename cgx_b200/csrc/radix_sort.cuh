@@ -18,9 +18,9 @@
 
 namespace cgx {
 
-constexpr int RS_BLOCK = 256;                 // threads per CTA
+constexpr int RS_BLOCK = 512;                 // threads per CTA
 constexpr int RS_WARPS = RS_BLOCK / 32;
-constexpr int RS_ITEMS = 16;                  // keys per thread
+constexpr int RS_ITEMS = 8;                   // keys per thread
 constexpr int RS_TILE = RS_BLOCK * RS_ITEMS;  // 4096 keys per tile
 constexpr int RS_BINS = 256;
 constexpr int RS_MAX_PASSES = 8;
@@ -95,135 +95,142 @@ static __global__ void __launch_bounds__(RS_BINS) rs_scan_hist_kernel(uint32_t *
     h[threadIdx.x] = sh[threadIdx.x] - v;
 }
 
+// One onesweep pass.  512 threads x 8 keys = one 4096-key tile; the tile's keys (and payloads) are exchanged through a
+// shared-memory buffer that aliases the per-warp digit counters of the ranking phase, so a CTA needs 32 KB (+16 KB
+// with payloads) and <= 64 registers per thread: two CTAs (1024 threads) per SM.  (Round 1a kept 16 keys, their
+// ranks, staging positions and 64-bit output offsets in registers: 157 registers with payloads = one 256-thread CTA
+// per SM, 12 % occupancy, 1.3 TB/s.)
 template <typename K, bool HAS_VALUES>
-__global__ void __launch_bounds__(RS_BLOCK) rs_onesweep_kernel(const K *__restrict__ keys_in, K *__restrict__ keys_out,
-                                                               const uint32_t *__restrict__ vals_in, uint32_t *__restrict__ vals_out,
-                                                               size_t n, int shift, int bits, const uint32_t *__restrict__ digit_offset,
-                                                               uint32_t *status, uint32_t *tile_counter) {
-    __shared__ K s_keys[RS_TILE];                       // reused for the payload exchange
-    __shared__ uint32_t s_warp_hist[RS_WARPS][RS_BINS];
+__global__ void __launch_bounds__(RS_BLOCK, 2) rs_onesweep_kernel(const K *__restrict__ keys_in, K *__restrict__ keys_out,
+                                                                  const uint32_t *__restrict__ vals_in, uint32_t *__restrict__ vals_out,
+                                                                  size_t n, int shift, int bits, const uint32_t *__restrict__ digit_offset,
+                                                                  uint32_t *status, uint32_t *tile_counter) {
+    extern __shared__ __align__(16) unsigned char s_raw[];      // RS_TILE keys (+ RS_TILE payloads): rs_smem_bytes<K>(HAS_VALUES)
     __shared__ uint32_t s_bin_start[RS_BINS];
     __shared__ uint32_t s_global_base[RS_BINS];
+    __shared__ uint32_t s_scan_tot[RS_BINS / 32];
     __shared__ uint32_t s_tile;
+    uint16_t(*s_warp_hist)[RS_BINS] = reinterpret_cast<uint16_t(*)[RS_BINS]>(s_raw);      // [RS_WARPS][RS_BINS], phase 1-3 only
+    K *s_keys = reinterpret_cast<K *>(s_raw);
+    uint32_t *s_vals = reinterpret_cast<uint32_t *>(s_raw + RS_TILE * sizeof(K));
+    static_assert(RS_WARPS * RS_BINS * sizeof(uint16_t) <= RS_TILE * sizeof(uint32_t), "digit counters must fit the exchange buffer");
 
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t mask = (1u << bits) - 1u;
     if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
-    for (int i = tid; i < RS_WARPS * RS_BINS; i += RS_BLOCK) (&s_warp_hist[0][0])[i] = 0;
+    for (int i = tid; i < RS_WARPS * RS_BINS / 2; i += RS_BLOCK) reinterpret_cast<uint32_t *>(s_raw)[i] = 0;
     __syncthreads();
     const uint32_t tile = s_tile;
-    const size_t tile_base = (size_t)tile * RS_TILE;
-    const size_t warp_base = tile_base + (size_t)warp * (32 * RS_ITEMS);
+    const size_t warp_base = (size_t)tile * RS_TILE + (size_t)warp * (32 * RS_ITEMS);
 
     K key[RS_ITEMS];
+    uint32_t val[HAS_VALUES ? RS_ITEMS : 1];
     uint32_t rank[RS_ITEMS];
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; i++) {
-        size_t idx = warp_base + (size_t)i * 32 + lane;
+        const size_t idx = warp_base + (size_t)i * 32 + lane;
         key[i] = idx < n ? keys_in[idx] : (K)~(K)0;
+        if (HAS_VALUES) val[i] = idx < n ? vals_in[idx] : 0u;
     }
-    // ---- warp-level multisplit: stable rank of every key among the warp's keys with the same digit
+    // ---- warp-level multisplit: stable rank of every key among the warp's keys with the same digit.  The peer mask is
+    // built from one ballot per digit bit: MATCH.ANY occupies the XU pipe for ~200 cycles per warp instruction on
+    // sm_100 (ncu, round 1b: pipe_xu 73 % busy, the limiter of the whole pass), eight VOTEs do not.
     const unsigned lt = lanemask_lt();
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; i++) {
-        uint32_t d = (uint32_t)(key[i] >> shift) & mask;
-        unsigned peers = __match_any_sync(0xffffffffu, d);
-        int leader = __ffs(peers) - 1;
-        uint32_t base = 0;
-        if ((int)lane == leader) {
-            base = s_warp_hist[warp][d];
-            s_warp_hist[warp][d] = base + __popc(peers);
+        const uint32_t d = (uint32_t)(key[i] >> shift) & mask;
+        unsigned peers = 0xffffffffu;
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            if (b < bits) {
+                const bool p = (d >> b) & 1u;
+                const unsigned m = __ballot_sync(0xffffffffu, p);
+                peers &= p ? m : ~m;
+            }
         }
-        base = __shfl_sync(0xffffffffu, base, leader);
+        const uint32_t base = s_warp_hist[warp][d];            // every peer reads the same counter (broadcast)
+        __syncwarp();
+        if ((peers & lt) == 0) s_warp_hist[warp][d] = (uint16_t)(base + __popc(peers));   // lowest peer lane updates it
         rank[i] = base + __popc(peers & lt);
         __syncwarp();
     }
     __syncthreads();
-    // ---- per-digit: exclusive offsets across warps, tile count, look-back
-    uint32_t tile_count = 0;
-    {
-        const unsigned d = tid;   // RS_BLOCK == RS_BINS
+    // ---- per digit (threads 0..255): exclusive offsets across warps, tile count published for the look-back
+    uint32_t tile_count = 0, incl = 0;
+    if (tid < RS_BINS) {
         uint32_t sum = 0;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; w++) {
-            uint32_t t = s_warp_hist[w][d];
-            s_warp_hist[w][d] = sum;
+            const uint32_t t = s_warp_hist[w][tid];
+            s_warp_hist[w][tid] = (uint16_t)sum;
             sum += t;
         }
         tile_count = sum;
-        volatile uint32_t *st = status + (size_t)tile * RS_BINS + d;
-        if (tile == 0) *st = sum | RS_FLAG_INCLUSIVE; else *st = sum | RS_FLAG_PARTIAL;
-        s_bin_start[d] = sum;
+        volatile uint32_t *st = status + (size_t)tile * RS_BINS + tid;
+        *st = sum | (tile == 0 ? RS_FLAG_INCLUSIVE : RS_FLAG_PARTIAL);
+        // block-wide exclusive scan of the 256 tile counts: shuffle scan per warp, then the 8 warp totals
+        incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += t;
+        }
+        if (lane == 31) s_scan_tot[warp] = incl;
     }
     __syncthreads();
-    // exclusive scan of the 256 tile counts (Hillis-Steele in shared memory)
-    {
-        uint32_t v = s_bin_start[tid];
-        for (int off = 1; off < RS_BINS; off <<= 1) {
-            uint32_t t = tid >= (unsigned)off ? s_bin_start[tid - off] : 0;
-            __syncthreads();
-            s_bin_start[tid] += t;
-            __syncthreads();
-        }
-        uint32_t incl = s_bin_start[tid];
-        __syncthreads();
-        s_bin_start[tid] = incl - v;
-    }
-    {
-        const unsigned d = tid;
+    if (tid < RS_BINS) {
+        uint32_t pre = 0;
+#pragma unroll
+        for (int w = 0; w < RS_BINS / 32; w++) pre += (w < (int)warp) ? s_scan_tot[w] : 0u;
+        const uint32_t bin_start = pre + incl - tile_count;
+        s_bin_start[tid] = bin_start;
+        // decoupled look-back over the preceding tiles' published counts
         uint32_t excl = 0;
         if (tile > 0) {
             int t = (int)tile - 1;
             while (true) {
-                volatile uint32_t *pst = status + (size_t)t * RS_BINS + d;
+                volatile uint32_t *pst = status + (size_t)t * RS_BINS + tid;
                 uint32_t v = *pst;
                 while ((v & (RS_FLAG_PARTIAL | RS_FLAG_INCLUSIVE)) == 0) { __nanosleep(20); v = *pst; }
                 excl += v & RS_VALUE_MASK;
                 if (v & RS_FLAG_INCLUSIVE) break;
                 t--;
             }
-            volatile uint32_t *st = status + (size_t)tile * RS_BINS + d;
+            volatile uint32_t *st = status + (size_t)tile * RS_BINS + tid;
             *st = (excl + tile_count) | RS_FLAG_INCLUSIVE;
         }
-        __syncthreads();   // s_bin_start final
-        s_global_base[d] = digit_offset[d] + excl - s_bin_start[d];
+        s_global_base[tid] = digit_offset[tid] + excl - bin_start;
     }
     __syncthreads();
-    // ---- exchange through shared memory, then coalesced digit-contiguous stores
-    uint32_t pos[RS_ITEMS];
+    // ---- staging position of every key (last use of the digit counters), then exchange through shared memory
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; i++) {
-        uint32_t d = (uint32_t)(key[i] >> shift) & mask;
-        pos[i] = s_bin_start[d] + s_warp_hist[warp][d] + rank[i];
-        s_keys[pos[i]] = key[i];
+        const uint32_t d = (uint32_t)(key[i] >> shift) & mask;
+        rank[i] += s_bin_start[d] + s_warp_hist[warp][d];
     }
     __syncthreads();
-    size_t outp[RS_ITEMS];
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; i++) {
-        unsigned j = tid + i * RS_BLOCK;
-        K k = s_keys[j];
-        uint32_t d = (uint32_t)(k >> shift) & mask;
-        outp[i] = (size_t)s_global_base[d] + j;
-        if (outp[i] < n) keys_out[outp[i]] = k;
+        s_keys[rank[i]] = key[i];
+        if (HAS_VALUES) s_vals[rank[i]] = val[i];
     }
-    if (HAS_VALUES) {
-        __syncthreads();
-        uint32_t *s_vals = reinterpret_cast<uint32_t *>(s_keys);
+    __syncthreads();
+    // ---- digit-contiguous, coalesced stores
 #pragma unroll
-        for (int i = 0; i < RS_ITEMS; i++) {
-            size_t idx = warp_base + (size_t)i * 32 + lane;
-            uint32_t v = idx < n ? vals_in[idx] : 0u;
-            s_vals[pos[i]] = v;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < RS_ITEMS; i++) {
-            unsigned j = tid + i * RS_BLOCK;
-            if (outp[i] < n) vals_out[outp[i]] = s_vals[j];
+    for (int i = 0; i < RS_ITEMS; i++) {
+        const unsigned j = tid + i * RS_BLOCK;
+        const K k = s_keys[j];
+        const uint32_t d = (uint32_t)(k >> shift) & mask;
+        const size_t o = (size_t)s_global_base[d] + j;
+        if (o < n) {
+            keys_out[o] = k;
+            if (HAS_VALUES) vals_out[o] = s_vals[j];
         }
     }
 }
+
+template <typename K>
+static inline size_t rs_smem_bytes(bool has_values) { return RS_TILE * sizeof(K) + (has_values ? RS_TILE * sizeof(uint32_t) : 0); }
 
 // Sorts n keys (and optional payloads) on bits [begin_bit, end_bit).  keys/vals and the *_tmp buffers
 // ping-pong; the sorted data ends in *keys_sorted / *vals_sorted (one of the two buffers).
@@ -247,13 +254,16 @@ void radix_sort(K *keys, K *keys_tmp, uint32_t *vals, uint32_t *vals_tmp, size_t
     if (launches) *launches += 2;
     K *kin = keys, *kout = keys_tmp;
     uint32_t *vin = vals, *vout = vals_tmp;
+    const size_t smem = rs_smem_bytes<K>(vals != nullptr);
+    if (vals) CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int p = 0; p < plan.num_passes; p++) {
         CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(uint32_t) * tiles * RS_BINS, stream));
         if (vals)
-            PROF("radix_onesweep", (double)n * 2.0 * (sizeof(K) + 4), (rs_onesweep_kernel<K, true><<<(unsigned)tiles, RS_BLOCK, 0, stream>>>(
+            PROF("radix_onesweep", (double)n * 2.0 * (sizeof(K) + 4), (rs_onesweep_kernel<K, true><<<(unsigned)tiles, RS_BLOCK, smem, stream>>>(
                      kin, kout, vin, vout, n, plan.shift[p], plan.bits[p], hist + p * RS_BINS, status, counters + p)));
         else
-            PROF("radix_onesweep", (double)n * 2.0 * sizeof(K), (rs_onesweep_kernel<K, false><<<(unsigned)tiles, RS_BLOCK, 0, stream>>>(
+            PROF("radix_onesweep", (double)n * 2.0 * sizeof(K), (rs_onesweep_kernel<K, false><<<(unsigned)tiles, RS_BLOCK, smem, stream>>>(
                      kin, kout, nullptr, nullptr, n, plan.shift[p], plan.bits[p], hist + p * RS_BINS, status, counters + p)));
         if (launches) *launches += 1;
         std::swap(kin, kout);
