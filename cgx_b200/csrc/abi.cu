@@ -430,6 +430,32 @@ extern "C" int cgx_result(cgx_ctx_t *c, cgx_result_t *o) {
     return 0;
 }
 
+extern "C" int cgx_debug_sort_u64(cgx_ctx_t *c, uint64_t *keys_dev, uint32_t *vals_dev, int64_t n, int begin_bit, int end_bit, float *ms_out, int *passes_out) {
+    CGX_TRY(c, {
+        CGX_REQUIRE(c && keys_dev && n >= 0 && begin_bit >= 0 && end_bit <= 64 && begin_bit < end_bit, "bad argument");
+        CUDA_CHECK(cudaSetDevice(c->device));
+        Batch &b = c->batch;
+        uint64_t *tmp = b.hit_keys_tmp.get<uint64_t>((size_t)n + 1);
+        uint32_t *vtmp = vals_dev ? b.scratch.get<uint32_t>((size_t)n + 1) : nullptr;
+        cudaEvent_t e0, e1;
+        CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+        uint64_t *ks;
+        uint32_t *vs;
+        int launches = 0;
+        CUDA_CHECK(cudaEventRecord(e0, c->stream));
+        radix_sort<uint64_t>(keys_dev, tmp, vals_dev, vtmp, (size_t)n, begin_bit, end_bit, c->stream, b.radix, &ks, &vs, &launches);
+        CUDA_CHECK(cudaEventRecord(e1, c->stream));
+        if (ks != keys_dev) CUDA_CHECK(cudaMemcpyAsync(keys_dev, ks, sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
+        if (vals_dev && vs != vals_dev) CUDA_CHECK(cudaMemcpyAsync(vals_dev, vs, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        float ms = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        if (ms_out) *ms_out = ms;
+        if (passes_out) *passes_out = launches - 2;
+    });
+}
+
 extern "C" int64_t cgx_debug_fetch(cgx_ctx_t *c, const char *what, int32_t *out, int64_t cap) {
     if (!c || !what || !out) return -1;
     try {

@@ -18,9 +18,17 @@
 
 namespace cgx {
 
-constexpr int RS_BLOCK = 512;                 // threads per CTA
+// tile shape, measured on B200 with tools/sort_bench.py (2^27 keys; 52-bit keys only / 64-bit keys + payload, ms per sort):
+//   512x8 (2 CTAs/SM) 8.19 / 10.9    256x8 (4) 9.84 / 12.3    256x16 (3) 7.31 / 9.42    256x16 (4) 6.68 / 10.15    256x24 (2) 7.44 / 9.77
+#ifndef CGX_RS_BLOCK
+#define CGX_RS_BLOCK 256
+#endif
+#ifndef CGX_RS_ITEMS
+#define CGX_RS_ITEMS 16
+#endif
+constexpr int RS_BLOCK = CGX_RS_BLOCK;        // threads per CTA (>= 256: one thread per digit in the look-back)
 constexpr int RS_WARPS = RS_BLOCK / 32;
-constexpr int RS_ITEMS = 8;                   // keys per thread
+constexpr int RS_ITEMS = CGX_RS_ITEMS;        // keys per thread
 constexpr int RS_TILE = RS_BLOCK * RS_ITEMS;  // 4096 keys per tile
 constexpr int RS_BINS = 256;
 constexpr int RS_MAX_PASSES = 8;
@@ -56,6 +64,29 @@ struct RadixTemp {
 };
 
 #ifdef __CUDACC__
+
+// peers of this lane's digit: one ballot per digit bit (cf. the MatchAny of CUB's radix rank).  MATCH.ANY occupies the XU
+// pipe for ~200 cycles per warp instruction on sm_100 (ncu, round 1b: pipe_xu 73 % busy, the limiter of the whole pass).
+__device__ __forceinline__ unsigned rs_match_digit(uint32_t d, int bits) {
+    unsigned peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        if (b < bits) {
+            const bool p = (d >> b) & 1u;
+            const unsigned m = __ballot_sync(0xffffffffu, p);
+            peers &= p ? m : ~m;
+        }
+    }
+    return peers;
+}
+__device__ __forceinline__ uint32_t rs_ld_status(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void rs_st_status(uint32_t *p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 template <typename K>
 __global__ void __launch_bounds__(RS_BLOCK) rs_histogram_kernel(const K *__restrict__ keys, size_t n, RadixPlan plan,
@@ -95,13 +126,13 @@ static __global__ void __launch_bounds__(RS_BINS) rs_scan_hist_kernel(uint32_t *
     h[threadIdx.x] = sh[threadIdx.x] - v;
 }
 
-// One onesweep pass.  512 threads x 8 keys = one 4096-key tile; the tile's keys (and payloads) are exchanged through a
+// One onesweep pass.  256 threads x 16 keys = one 4096-key tile; the tile's keys (and payloads) are exchanged through a
 // shared-memory buffer that aliases the per-warp digit counters of the ranking phase, so a CTA needs 32 KB (+16 KB
-// with payloads) and <= 64 registers per thread: two CTAs (1024 threads) per SM.  (Round 1a kept 16 keys, their
-// ranks, staging positions and 64-bit output offsets in registers: 157 registers with payloads = one 256-thread CTA
-// per SM, 12 % occupancy, 1.3 TB/s.)
+// with payloads) and 64-80 registers per thread: four (three with payloads) CTAs per SM.  (Round 1a kept the keys, their
+// ranks, staging positions and 64-bit output offsets in registers: 157 registers with payloads = one CTA per SM,
+// 12 % occupancy, 1.3 TB/s.)
 template <typename K, bool HAS_VALUES>
-__global__ void __launch_bounds__(RS_BLOCK, 2) rs_onesweep_kernel(const K *__restrict__ keys_in, K *__restrict__ keys_out,
+__global__ void __launch_bounds__(RS_BLOCK, HAS_VALUES ? 3 : 4) rs_onesweep_kernel(const K *__restrict__ keys_in, K *__restrict__ keys_out,
                                                                   const uint32_t *__restrict__ vals_in, uint32_t *__restrict__ vals_out,
                                                                   size_t n, int shift, int bits, const uint32_t *__restrict__ digit_offset,
                                                                   uint32_t *status, uint32_t *tile_counter) {
@@ -126,28 +157,30 @@ __global__ void __launch_bounds__(RS_BLOCK, 2) rs_onesweep_kernel(const K *__res
     K key[RS_ITEMS];
     uint32_t val[HAS_VALUES ? RS_ITEMS : 1];
     uint32_t rank[RS_ITEMS];
+    const bool full = ((size_t)tile + 1) * RS_TILE <= n;         // all tiles but the last: no bounds checks
+    if (full) {
+        const K *kp = keys_in + warp_base + lane;
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; i++) {
-        const size_t idx = warp_base + (size_t)i * 32 + lane;
-        key[i] = idx < n ? keys_in[idx] : (K)~(K)0;
-        if (HAS_VALUES) val[i] = idx < n ? vals_in[idx] : 0u;
+        for (int i = 0; i < RS_ITEMS; i++) key[i] = kp[i * 32];
+        if (HAS_VALUES) {
+            const uint32_t *vp = vals_in + warp_base + lane;
+#pragma unroll
+            for (int i = 0; i < RS_ITEMS; i++) val[i] = vp[i * 32];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; i++) {
+            const size_t idx = warp_base + (size_t)i * 32 + lane;
+            key[i] = idx < n ? keys_in[idx] : (K)~(K)0;
+            if (HAS_VALUES) val[i] = idx < n ? vals_in[idx] : 0u;
+        }
     }
-    // ---- warp-level multisplit: stable rank of every key among the warp's keys with the same digit.  The peer mask is
-    // built from one ballot per digit bit: MATCH.ANY occupies the XU pipe for ~200 cycles per warp instruction on
-    // sm_100 (ncu, round 1b: pipe_xu 73 % busy, the limiter of the whole pass), eight VOTEs do not.
+    // ---- warp-level multisplit: stable rank of every key among the warp's keys with the same digit
     const unsigned lt = lanemask_lt();
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; i++) {
         const uint32_t d = (uint32_t)(key[i] >> shift) & mask;
-        unsigned peers = 0xffffffffu;
-#pragma unroll
-        for (int b = 0; b < 8; b++) {
-            if (b < bits) {
-                const bool p = (d >> b) & 1u;
-                const unsigned m = __ballot_sync(0xffffffffu, p);
-                peers &= p ? m : ~m;
-            }
-        }
+        const unsigned peers = rs_match_digit(d, bits);
         const uint32_t base = s_warp_hist[warp][d];            // every peer reads the same counter (broadcast)
         __syncwarp();
         if ((peers & lt) == 0) s_warp_hist[warp][d] = (uint16_t)(base + __popc(peers));   // lowest peer lane updates it
@@ -166,8 +199,7 @@ __global__ void __launch_bounds__(RS_BLOCK, 2) rs_onesweep_kernel(const K *__res
             sum += t;
         }
         tile_count = sum;
-        volatile uint32_t *st = status + (size_t)tile * RS_BINS + tid;
-        *st = sum | (tile == 0 ? RS_FLAG_INCLUSIVE : RS_FLAG_PARTIAL);
+        rs_st_status(status + (size_t)tile * RS_BINS + tid, sum | (tile == 0 ? RS_FLAG_INCLUSIVE : RS_FLAG_PARTIAL));
         // block-wide exclusive scan of the 256 tile counts: shuffle scan per warp, then the 8 warp totals
         incl = sum;
 #pragma unroll
@@ -189,15 +221,14 @@ __global__ void __launch_bounds__(RS_BLOCK, 2) rs_onesweep_kernel(const K *__res
         if (tile > 0) {
             int t = (int)tile - 1;
             while (true) {
-                volatile uint32_t *pst = status + (size_t)t * RS_BINS + tid;
-                uint32_t v = *pst;
-                while ((v & (RS_FLAG_PARTIAL | RS_FLAG_INCLUSIVE)) == 0) { __nanosleep(20); v = *pst; }
+                const uint32_t *pst = status + (size_t)t * RS_BINS + tid;
+                uint32_t v = rs_ld_status(pst);
+                while ((v & (RS_FLAG_PARTIAL | RS_FLAG_INCLUSIVE)) == 0) { __nanosleep(20); v = rs_ld_status(pst); }
                 excl += v & RS_VALUE_MASK;
                 if (v & RS_FLAG_INCLUSIVE) break;
                 t--;
             }
-            volatile uint32_t *st = status + (size_t)tile * RS_BINS + tid;
-            *st = (excl + tile_count) | RS_FLAG_INCLUSIVE;
+            rs_st_status(status + (size_t)tile * RS_BINS + tid, (excl + tile_count) | RS_FLAG_INCLUSIVE);
         }
         s_global_base[tid] = digit_offset[tid] + excl - bin_start;
     }
@@ -222,7 +253,7 @@ __global__ void __launch_bounds__(RS_BLOCK, 2) rs_onesweep_kernel(const K *__res
         const K k = s_keys[j];
         const uint32_t d = (uint32_t)(k >> shift) & mask;
         const size_t o = (size_t)s_global_base[d] + j;
-        if (o < n) {
+        if (full || o < n) {
             keys_out[o] = k;
             if (HAS_VALUES) vals_out[o] = s_vals[j];
         }

@@ -160,6 +160,11 @@ int cgx_result(cgx_ctx_t *ctx, cgx_result_t *out);
  * Returns the number of int32 written (<= cap) or a negative error. */
 int64_t cgx_debug_fetch(cgx_ctx_t *ctx, const char *what, int32_t *out, int64_t cap);
 
+/* The onesweep radix sort on its own (tests / tools/sort_bench.py): sorts n device-resident 64-bit keys on bits
+ * [begin_bit, end_bit), optionally carrying 32-bit payloads (vals_dev may be NULL).  keys_dev/vals_dev hold the sorted
+ * data on return; ms_out = CUDA-event time of the sort, passes_out = onesweep passes executed. */
+int cgx_debug_sort_u64(cgx_ctx_t *ctx, uint64_t *keys_dev, uint32_t *vals_dev, int64_t n, int begin_bit, int end_bit, float *ms_out, int *passes_out);
+
 #ifdef __cplusplus
 }
 #endif

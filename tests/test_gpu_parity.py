@@ -274,3 +274,33 @@ def test_medium_scale_properties():
     assert sorted(a.grammar_lines(149, lay)) == sorted(full.grammar_lines(149, lay))
     assert sorted(b.grammar_lines(0, lay)) == sorted(full.grammar_lines(150, lay))
     assert tot_full > 0
+
+
+@pytest.mark.parametrize("n,bits,with_vals", [(1, 8, 0), (4097, 17, 1), (300_000, 52, 0), (1_000_003, 64, 1), (2_500_000, 23, 1)])
+def test_radix_sort_matches_stable_reference(n, bits, with_vals):
+    """The hand-written onesweep radix sort (every stage of the path sorts with it) against numpy's stable sort:
+    keys bit-exact and payloads equal to the stable permutation, ragged sizes and partial key widths included."""
+    import ctypes as C
+    import torch
+    from cgx_b200 import _lib
+    L = _lib.load()
+    h = C.c_void_p()
+    assert L.cgx_create(0, C.byref(h)) == 0
+    try:
+        rng = np.random.default_rng(n)
+        src = rng.integers(0, 1 << 63, size=n, dtype=np.uint64)
+        if n > 1000:
+            src[: n // 3] &= np.uint64(0xFFFF)            # heavy duplicates: stability matters
+        if bits < 64:
+            src &= np.uint64((1 << bits) - 1)
+        keys = torch.from_numpy(src.view(np.int64).copy()).cuda()
+        vals = torch.arange(n, dtype=torch.int32).cuda() if with_vals else None
+        ms, passes = C.c_float(), C.c_int()
+        rc = L.cgx_debug_sort_u64(h, keys.data_ptr(), vals.data_ptr() if with_vals else None, n, 0, bits, C.byref(ms), C.byref(passes))
+        assert rc == 0, L.cgx_last_error(h)
+        perm = np.argsort(src, kind="stable")
+        assert np.array_equal(keys.cpu().numpy().view(np.uint64), src[perm])
+        if with_vals:
+            assert np.array_equal(vals.cpu().numpy().astype(np.int64), perm)
+    finally:
+        L.cgx_destroy(h)
