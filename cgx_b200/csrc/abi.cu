@@ -62,10 +62,10 @@ extern "C" void cgx_destroy(cgx_ctx_t *c) {
                     &b.phrases, &b.e1_count, &b.e1_inst, &b.e1_keys, &b.e1_keys_tmp, &b.e1_vals, &b.e1_vals_tmp, &b.e1_flags, &b.e1_pid, &b.pat1,
                     &b.pat1_dev, &b.pat1_pos, &b.ql_keys, &b.ql_keys_tmp, &b.q1_off, &b.q1_ids, &b.q2_off, &b.q2_ids, &b.j_tiles, &b.j_bitmaps, &b.j_aflag, &b.j_hash, &b.pat1_ga, &b.hit_keys,
                     &b.hit_keys_tmp, &b.counters, &b.missing, &b.hits1_sorted, &b.hits2_sorted, &b.e2_count, &b.e2_keys, &b.e2_keys_tmp, &b.e2_vals,
-                    &b.e2_vals_tmp, &b.e2_flags, &b.pat2, &b.rec_hash, &b.rec_idx, &b.rec_idx_tmp, &b.rec_keys, &b.rec_keys_tmp, &b.rec_flags,
+                    &b.e2_vals_tmp, &b.e2_flags, &b.pat2, &b.rec_hash, &b.rec_flags, &b.rec_meta,
                     &b.scratch, &b.scratch2, &b.rule_head, &b.radix.hist, &b.radix.status, &b.radix.counters};
     for (auto *x : bb) x->release();
-    for (int k = 0; k < 3; k++) { b.slot_off[k].release(); b.rec[k].release(); b.rec_sorted[k].release(); b.rules[k].release(); b.updown[k].release(); b.id_count[k].release(); }
+    for (int k = 0; k < 3; k++) { b.slot_off[k].release(); b.rec[k].release(); b.rules[k].release(); b.updown[k].release(); b.id_count[k].release(); }
     for (auto &l : b.scan.level) l.release();
     if (b.h_pinned) cudaFreeHost(b.h_pinned);
     PinnedBuf *pb[] = {&b.h_phrase_id, &b.h_phrases, &b.h_pat1, &b.h_pat2, &b.h_q1_off, &b.h_q1_ids, &b.h_q2_off, &b.h_q2_ids};
@@ -486,10 +486,11 @@ extern "C" int64_t cgx_debug_fetch(cgx_ctx_t *c, const char *what, int32_t *out,
         }
         if (w == "rec_ab" || w == "rec_1" || w == "rec_2") {
             int k = w == "rec_ab" ? 0 : w == "rec_1" ? 1 : 2;
-            size_t N = (size_t)b.n_rec[k];
+            size_t cells = b.rec_cells[k], N = 0;                // slot-indexed cells: keep the non-empty ones
+            std::vector<RuleRec> r(cells);
+            if (cells) CUDA_CHECK(cudaMemcpy(r.data(), b.rec[k].p, sizeof(RuleRec) * cells, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < cells; i++) if (r[i].id >= 0) r[N++] = r[i];
             if ((int64_t)(N * 7) > cap) return -2;
-            std::vector<RuleRec> r(N);
-            if (N) CUDA_CHECK(cudaMemcpy(r.data(), b.rec[k].p, sizeof(RuleRec) * N, cudaMemcpyDeviceToHost));
             for (size_t i = 0; i < N; i++) {
                 out[7 * i] = r[i].id; out[7 * i + 1] = r[i].tgt_start; out[7 * i + 2] = r[i].end;
                 out[7 * i + 3] = r[i].gap1 == 255 ? -1 : r[i].gap1; out[7 * i + 4] = r[i].gap1 == 255 ? -1 : r[i].gap1_1;

@@ -6,12 +6,16 @@
 // and lexicalTaskMaxEF + searchLexFile (:2108-2432).
 //
 // Rule identity = (converted source id, target symbol sequence with each gap collapsed to one marker)
-// (ExtractPair.c:813-848, :1141-1173).  Every record gets a 64-bit hash of its target symbol sequence;
-// records are ordered by (id, hash) with two stable onesweep radix sorts of (key, record index) pairs;
-// run heads are flagged, prefix-summed and compacted into rules: paircount = run length, f = records per
-// id, all_suffix_fsample from the pattern tables.  Exactness does not rest on the hash: every record is
-// compared symbol-by-symbol with its predecessor in the run, and a mismatch raises a flag on which the
-// host re-runs the aggregation with another hash seed.
+// (ExtractPair.c:813-848, :1141-1173).  The extraction kernels leave their records in slot-indexed cells that are
+// already grouped by source id (extract.cu): all records of one id sit in the <= 300 (65 / 70 for gappy seeds)
+// consecutive cells of its pattern.  So no global sort is needed (round 1a-1c: a 64-bit hash sort + an id sort of
+// 1.2e8 records = 30 GB of radix passes per batch): every record gets a 64-bit hash of its target symbol sequence,
+// and one thread per cell compares its hash with the other cells of its segment (broadcast loads, the segment is
+// shared by the neighbouring threads): paircount = equal cells, rule head = first equal cell, f = non-empty cells,
+// representative = equal cell with the smallest target start.  Heads are flagged, prefix-summed and compacted
+// into rules in (id, first cell) order -- deterministic.  Exactness does not rest on the hash: every non-head
+// record is compared symbol-by-symbol with its head, and a mismatch raises a flag on which the host re-runs the
+// aggregation with another hash seed.
 // Lexical weights: one thread per distinct rule; every (f,e) pair is ONE probe of the lexical hash table (16-byte
 // slots holding both directions' values; 2^21 slots = 32 MB at C2, L2-resident) instead of a 20-step binary search;
 // -log10 through the same lg2.approx path the reference's -use_fast_math build takes.
@@ -45,42 +49,79 @@ __device__ __forceinline__ int target_symbols(const int32_t *__restrict__ tgt, c
     return n;
 }
 
-__global__ void agg_hash_kernel(const RuleRec *__restrict__ rec, size_t n, const int32_t *__restrict__ tgt, uint64_t seed, uint64_t *__restrict__ keys,
-                                uint32_t *__restrict__ idx) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    RuleRec r = rec[i];
-    uint32_t sym[16];
-    int ns = target_symbols(tgt, r, sym);
-    uint64_t h = seed ^ (uint64_t)ns;
-    for (int k = 0; k < ns; k++) h = mix64(h ^ (uint64_t)sym[k]) + 0x9e3779b97f4a7c15ULL;
-    keys[i] = h;
-    idx[i] = (uint32_t)i;
+// cells of one kind: up to 4 slot-indexed regions in ascending id order (extract.cu)
+struct AggRegion {
+    uint32_t base;                 // first cell
+    int32_t id_base;               // converted id of pattern 0 of the region
+    const uint32_t *slot_off;      // pattern -> first slot (n_patterns + 1 entries)
+};
+struct AggLayout {
+    AggRegion r[4];
+    int n_regions;
+    uint32_t cells;
+};
+
+// hash[i] = 0 for an empty cell, else the (odd) hash of the record's target symbol sequence
+__global__ void agg_hash_kernel(const RuleRec *__restrict__ rec, uint32_t cells, const int32_t *__restrict__ tgt, uint64_t seed, uint64_t *__restrict__ hash,
+                                unsigned long long *__restrict__ n_records) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = false;
+    if (i < cells) {
+        const RuleRec r = rec[i];
+        uint64_t h = 0;
+        if (r.id >= 0) {
+            live = true;
+            uint32_t sym[16];
+            const int ns = target_symbols(tgt, r, sym);
+            h = seed ^ (uint64_t)ns;
+            for (int k = 0; k < ns; k++) h = mix64(h ^ (uint64_t)sym[k]) + 0x9e3779b97f4a7c15ULL;
+            h |= 1ull;
+        }
+        hash[i] = h;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, live);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_records, (unsigned long long)__popc(m));
 }
 
-__global__ void agg_id_keys_kernel(const RuleRec *__restrict__ rec, const uint32_t *__restrict__ idx, size_t n, uint32_t *__restrict__ keys) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) keys[i] = (uint32_t)rec[idx[i]].id;
-}
-
-// flags[i] = 1 when record i (in sorted order) starts a new rule; also verifies equal-hash neighbours
-__global__ void agg_flags_kernel(const RuleRec *__restrict__ rec, const uint32_t *__restrict__ idx, const uint64_t *__restrict__ hash, size_t n,
-                                 const int32_t *__restrict__ tgt, uint32_t *__restrict__ flags, uint32_t *__restrict__ id_count, int *__restrict__ collision) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    RuleRec r = rec[idx[i]];
-    atomicAdd(&id_count[r.id], 1u);
-    if (i == 0) { flags[i] = 1; return; }
-    RuleRec q = rec[idx[i - 1]];
-    bool head = (q.id != r.id) || (hash[idx[i]] != hash[idx[i - 1]]);
-    if (!head) {
+// One thread per cell: group the records of its segment (= the cells of its source id) by target sequence.
+//   flags[i] = 1 when cell i is the first cell of its rule; meta[i] = {representative cell, paircount | f << 16} for heads.
+__global__ void __launch_bounds__(256) agg_group_kernel(AggLayout lay, const RuleRec *__restrict__ rec, const uint64_t *__restrict__ hash,
+                                                        const int32_t *__restrict__ tgt, uint32_t *__restrict__ flags, uint2 *__restrict__ meta,
+                                                        int *__restrict__ collision) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= lay.cells) return;
+    const uint64_t h = hash[i];
+    if (h == 0) { flags[i] = 0; return; }
+    const RuleRec r = rec[i];
+    int reg = 0;
+#pragma unroll
+    for (int k = 1; k < 4; k++) if (k < lay.n_regions && i >= lay.r[k].base) reg = k;
+    const uint32_t pat = (uint32_t)(r.id - lay.r[reg].id_base);
+    const uint32_t s0 = lay.r[reg].base + __ldg(&lay.r[reg].slot_off[pat]), s1 = lay.r[reg].base + __ldg(&lay.r[reg].slot_off[pat + 1]);
+    uint32_t first = i, best = i, cnt = 0, f = 0;
+    int best_ts = r.tgt_start;
+    for (uint32_t j = s0; j < s1; j++) {
+        const uint64_t hj = __ldg(&hash[j]);
+        f += hj != 0;
+        if (hj == h) {
+            cnt++;
+            if (j < first) first = j;
+            const int tsj = __ldg(&rec[j].tgt_start);
+            if (tsj < best_ts || (tsj == best_ts && j < best)) { best = j; best_ts = tsj; }
+        }
+    }
+    if (first == i) {
+        flags[i] = 1;
+        meta[i] = make_uint2(best, cnt | (f << 16));
+    } else {
+        flags[i] = 0;
+        const RuleRec q = rec[first];
         uint32_t a[16], c[16];
-        int na = target_symbols(tgt, r, a), nc = target_symbols(tgt, q, c);
+        const int na = target_symbols(tgt, r, a), nc = target_symbols(tgt, q, c);
         bool same = na == nc;
         for (int k = 0; same && k < na; k++) same = a[k] == c[k];
         if (!same) atomicExch(collision, 1);
     }
-    flags[i] = head ? 1u : 0u;
 }
 
 // all_suffix_fsample before the cap (ExtractPair.c:637, :891-908, :1211-1247)
@@ -120,37 +161,30 @@ __device__ __forceinline__ void lex_get(const ulonglong2 *__restrict__ slots, ui
     else { *v1 = 0.f; *v2 = 0.f; }
 }
 
-// head_pos[r] = sorted index of the first record of rule r (excl = exclusive scan of the head flags); head_pos[R] = n
-__global__ void agg_head_pos_kernel(const uint32_t *__restrict__ excl, size_t n, uint32_t n_rules, uint32_t *__restrict__ head_pos) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+// head_cell[r] = cell of the first record of rule r (excl = exclusive scan of the head flags)
+__global__ void agg_head_cell_kernel(const uint32_t *__restrict__ excl, uint32_t cells, uint32_t n_rules, uint32_t *__restrict__ head_cell) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cells) return;
     const uint32_t e = excl[i];
-    const uint32_t nxt = (i + 1 < n) ? excl[i + 1] : n_rules;
-    if (nxt != e) head_pos[e] = (uint32_t)i;
-    if (i == 0) head_pos[n_rules] = (uint32_t)n;
+    const uint32_t nxt = (i + 1 < cells) ? excl[i + 1] : n_rules;
+    if (nxt != e) head_cell[e] = i;
 }
 
 // One thread per distinct rule: paircount, f, fs, representative record, lexical weights.
-__global__ void __launch_bounds__(128) agg_rules_kernel(AggIdx a, int kind, const RuleRec *__restrict__ rec, const uint32_t *__restrict__ idx,
-                                                        const uint32_t *__restrict__ head_pos, uint32_t n_rules,
-                                                        const uint32_t *__restrict__ id_count, const ulonglong2 *__restrict__ lex, uint32_t lex_mask,
-                                                        cgx_rule_t *__restrict__ rules) {
+__global__ void __launch_bounds__(128) agg_rules_kernel(AggIdx a, int kind, const RuleRec *__restrict__ rec, const uint32_t *__restrict__ head_cell,
+                                                        const uint2 *__restrict__ meta, uint32_t n_rules, const ulonglong2 *__restrict__ lex,
+                                                        uint32_t lex_mask, cgx_rule_t *__restrict__ rules) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rules) return;
-    const uint32_t head = head_pos[r], next_head = head_pos[r + 1];
-    const int pc = (int)(next_head - head);
-    // deterministic representative: smallest tgt_start of the run
-    RuleRec best = rec[idx[head]];
-    for (uint32_t i = head + 1; i < next_head; i++) {
-        RuleRec c = rec[idx[i]];
-        if (c.tgt_start < best.tgt_start) best = c;
-    }
+    const uint2 mt = meta[head_cell[r]];
+    const RuleRec best = rec[mt.x];
+    const int pc = (int)(mt.y & 0xffffu);
     cgx_rule_t out;
     out.id = best.id; out.tgt_start = best.tgt_start; out.end = best.end;
     out.gap1 = best.gap1; out.gap1_1 = best.gap1_1; out.gap2 = best.gap2; out.gap2_1 = best.gap2_1;
     out.pad[0] = out.pad[1] = out.pad[2] = 0;
     out.pc = pc;
-    out.f = (int)id_count[best.id];
+    out.f = (int)(mt.y >> 16);
     int fs = fsample_of(a, kind, best.id);
     out.fs = fs > CGX_SAMPLER ? CGX_SAMPLER : fs;                          // ExtractPair.c:638,910,1249
     // ---- lexicalTaskMaxEF (ExtractPair.cu:2144-2432): for every source terminal the best MaxLexFgivenE over the target
@@ -204,20 +238,23 @@ __global__ void agg_updown_kernel(const cgx_rule_t *__restrict__ rules, uint32_t
     if (r == n_rules - 1 || rules[r + 1].id != id) updown[2 * id + 1] = (int32_t)r;
 }
 
-static uint32_t read_u32(const uint32_t *d, cudaStream_t stream) {
-    uint32_t v = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&v, d, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    CUDA_CHECK(cudaStreamSynchronize(stream));
-    return v;
-}
-
 void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
     AggIdx a{ix.str.ptr<int32_t>(), ix.tgt.ptr<int32_t>(), b.phrases.ptr<int32_t>(), b.pat1.ptr<Pat1>(), b.pat2.ptr<Pat2>(), b.G, b.D1, b.D2};
-    const int nids[3] = {b.G, 2 * b.G + b.D1, b.G + b.D2 + 2 * b.D1};
-    uint32_t *tot = b.counters.get<uint32_t>(16);
+    const int G = b.G, D1 = b.D1, D2 = b.D2;
+    const int nids[3] = {G, 2 * G + D1, G + D2 + 2 * D1};
+    const uint32_t ns0 = (uint32_t)b.n_slots[0], ns1 = (uint32_t)b.n_slots[1], ns2 = (uint32_t)b.n_slots[2];
+    const uint32_t *so0 = b.slot_off[0].ptr<uint32_t>(), *so1 = b.slot_off[1].ptr<uint32_t>(), *so2 = b.slot_off[2].ptr<uint32_t>();
+    AggLayout lay[3];
+    lay[0].n_regions = 1; lay[0].r[0] = {0u, 0, so0};
+    lay[1].n_regions = 3; lay[1].r[0] = {0u, 0, so0}; lay[1].r[1] = {ns0, G, so0}; lay[1].r[2] = {2 * ns0, 2 * G, so1};
+    lay[2].n_regions = 4; lay[2].r[0] = {0u, 0, so0}; lay[2].r[1] = {ns0, G, so2}; lay[2].r[2] = {ns0 + ns2, G + D2, so1}; lay[2].r[3] = {ns0 + ns2 + ns1, G + D2 + D1, so1};
+    uint32_t *tot = b.counters.get<uint32_t>(32);
     int *collision = (int *)(tot + 14);
+    unsigned long long *n_records = (unsigned long long *)(tot + 16);
     for (int kind = 0; kind < 3; kind++) {
-        const size_t N = (size_t)b.n_rec[kind];
+        const uint32_t N = (uint32_t)b.rec_cells[kind];
+        lay[kind].cells = N;
+        for (int k = lay[kind].n_regions; k < 4; k++) lay[kind].r[k] = lay[kind].r[0];
         b.n_ids[kind] = nids[kind];
         b.n_rules[kind] = 0;
         int32_t *h_ud = b.h_updown[kind].get<int32_t>((size_t)2 * nids[kind] + 2);
@@ -225,44 +262,40 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
         b.h_rules[kind].get<cgx_rule_t>(1);
         if (N == 0 || nids[kind] == 0) continue;
         const RuleRec *rec = b.rec[kind].ptr<RuleRec>();
-        uint64_t *hk = b.rec_keys.get<uint64_t>(N), *hk_tmp = b.rec_keys_tmp.get<uint64_t>(N);
-        uint32_t *idx = b.rec_idx.get<uint32_t>(N), *idx_tmp = b.rec_idx_tmp.get<uint32_t>(N);
-        uint64_t *hash_by_rec = b.rec_hash.get<uint64_t>(N);
-        uint32_t *idk = b.scratch.get<uint32_t>(2 * N + 2), *idk_tmp = idk + N;
-        uint32_t *flags = b.rec_flags.get<uint32_t>(N + 2);
-        uint32_t *id_count = b.id_count[kind].get<uint32_t>((size_t)nids[kind]);
+        uint64_t *hash = b.rec_hash.get<uint64_t>((size_t)N);
+        uint32_t *flags = b.rec_flags.get<uint32_t>((size_t)N + 2);
+        uint2 *meta = b.rec_meta.get<uint2>((size_t)N);
         int32_t *updown = b.updown[kind].get<int32_t>((size_t)2 * nids[kind]);
         uint64_t seed = 0x243f6a8885a308d3ULL;
         uint32_t R = 0;
         for (int attempt = 0; attempt < 8; attempt++, seed = seed * 6364136223846793005ULL + 1442695040888963407ULL) {
-            PROF("agg_hash", (double)N * 28, (agg_hash_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(rec, N, ix.tgt.ptr<int32_t>(), seed, hk, idx)));
-            CUDA_CHECK(cudaMemcpyAsync(hash_by_rec, hk, sizeof(uint64_t) * N, cudaMemcpyDeviceToDevice, stream));
-            uint64_t *ks;
-            uint32_t *is;
-            radix_sort<uint64_t>(hk, hk_tmp, idx, idx_tmp, N, 0, 64, stream, b.radix, &ks, &is, &b.launches);
-            agg_id_keys_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(rec, is, N, idk);
-            uint32_t *ids_sorted, *is2;
-            uint32_t *other = (is == idx) ? idx_tmp : idx;
-            radix_sort<uint32_t>(idk, idk_tmp, is, other, N, 0, cgx_bits_for((uint64_t)nids[kind]), stream, b.radix, &ids_sorted, &is2, &b.launches);
-            CUDA_CHECK(cudaMemsetAsync(id_count, 0, sizeof(uint32_t) * (size_t)nids[kind], stream));
             CUDA_CHECK(cudaMemsetAsync(collision, 0, sizeof(int), stream));
-            PROF("agg_flags", (double)N * 48, (agg_flags_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(rec, is2, hash_by_rec, N, ix.tgt.ptr<int32_t>(), flags, id_count, collision)));
+            CUDA_CHECK(cudaMemsetAsync(n_records, 0, sizeof(unsigned long long), stream));
+            PROF("agg_hash", (double)N * 24, (agg_hash_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(rec, N, ix.tgt.ptr<int32_t>(), seed, hash, n_records)));
+            PROF("agg_group", (double)N * (8 + 4), (agg_group_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(lay[kind], rec, hash, ix.tgt.ptr<int32_t>(), flags, meta, collision)));
             exclusive_scan_u32(flags, flags, N, tot, stream, b.scan, 0, &b.launches);
-            b.launches += 3;
-            uint32_t hostv[16];
+            b.launches += 2;
+            uint32_t hostv[20];
             CUDA_CHECK(cudaMemcpyAsync(hostv, tot, sizeof(hostv), cudaMemcpyDeviceToHost, stream));
             CUDA_CHECK(cudaStreamSynchronize(stream));
             if (hostv[14] == 0) {
                 R = hostv[0];
+                unsigned long long nr;
+                memcpy(&nr, &hostv[16], sizeof(nr));
+                b.n_rec[kind] = (int64_t)nr;
+                if (g_prof && g_prof->enabled) {          // records actually grouped: 16 B record + 8 B meta per head, 20 B per record compared
+                    g_prof->table["agg_group"].bytes += (double)nr * 16 + (double)R * 8;
+                    g_prof->table["agg_hash"].bytes += (double)nr * 12;
+                }
+                if (R == 0) break;
                 cgx_rule_t *rules = b.rules[kind].get<cgx_rule_t>(R);
-                uint32_t *head_pos = b.rule_head.get<uint32_t>((size_t)R + 2);
-                agg_head_pos_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(flags, N, R, head_pos);
-                PROF("agg_rules", (double)R * 36 + (double)N * 20, (agg_rules_kernel<<<cgx_div_up(R, 128), 128, 0, stream>>>(a, kind, rec, is2, head_pos, R, id_count,
+                uint32_t *head_cell = b.rule_head.get<uint32_t>((size_t)R + 2);
+                agg_head_cell_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(flags, N, R, head_cell);
+                PROF("agg_rules", (double)R * (4 + 8 + 16 + 36) + (double)R * 13 * 16, (agg_rules_kernel<<<cgx_div_up(R, 128), 128, 0, stream>>>(a, kind, rec, head_cell, meta, R,
                                                                        ix.lex_hash.ptr<ulonglong2>(), ix.lex_hash_mask, rules)));
-                b.launches++;
                 CUDA_CHECK(cudaMemsetAsync(updown, 0xff, sizeof(int32_t) * 2 * (size_t)nids[kind], stream));
                 agg_updown_kernel<<<cgx_div_up(R, 256), 256, 0, stream>>>(rules, R, updown);
-                b.launches += 2;
+                b.launches += 3;
                 break;
             }
             CGX_REQUIRE(attempt < 7, "aggregation: hash collisions persisted over 8 seeds");
@@ -271,10 +304,9 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
         if (b.fetch_results) {
             cgx_rule_t *h_r = b.h_rules[kind].get<cgx_rule_t>((size_t)R + 1);
             if (R) CUDA_CHECK(cudaMemcpyAsync(h_r, b.rules[kind].ptr<cgx_rule_t>(), sizeof(cgx_rule_t) * R, cudaMemcpyDeviceToHost, stream));
-            CUDA_CHECK(cudaMemcpyAsync(h_ud, updown, sizeof(int32_t) * 2 * (size_t)nids[kind], cudaMemcpyDeviceToHost, stream));
+            if (R) CUDA_CHECK(cudaMemcpyAsync(h_ud, updown, sizeof(int32_t) * 2 * (size_t)nids[kind], cudaMemcpyDeviceToHost, stream));
         }
     }
-    (void)read_u32;
 }
 
 }  // namespace cgx

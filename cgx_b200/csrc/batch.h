@@ -53,9 +53,10 @@ struct Batch {
     DevBuf e2_count, e2_keys, e2_keys_tmp, e2_vals, e2_vals_tmp, e2_flags, pat2;
     int32_t enu2 = 0, D2 = 0;
     // extraction
-    DevBuf slot_off[3], rec[3], rec_sorted[3], rec_hash, rec_idx, rec_idx_tmp, rec_keys, rec_keys_tmp, rec_flags;
-    size_t rec_cap[3] = {0, 0, 0};
-    int64_t n_rec[3] = {0, 0, 0};
+    DevBuf slot_off[3], rec[3], rec_hash, rec_flags, rec_meta;   // rec[k]: slot-indexed cells (extract.cu), empty cells have id = -1
+    size_t rec_cells[3] = {0, 0, 0};       // cells per kind
+    int64_t n_slots[3] = {0, 0, 0};        // sampled-occurrence slots: contiguous / one-gap / two-gap
+    int64_t n_rec[3] = {0, 0, 0};          // non-empty cells per kind
     int64_t samples = 0;
     // rules
     DevBuf rules[3], updown[3], id_count[3], rule_head;

@@ -12,9 +12,13 @@
 // occurrence (int)((double)((float)j * ((float)n * (1.0f/S))) + 0.5), the exact arithmetic of the
 // reference under -use_fast_math (single FMUL by the rounded reciprocal, verified in its sm_100 SASS) --
 // and ONE thread is launched per sampled occurrence over a flat, load-balanced slot list (prefix sum of
-// min(n, S) per pattern).  Records are 16-byte words appended with warp-aggregated atomics; buffer sizes
-// are exact upper bounds (each occurrence emits at most one record of each rule shape), so there is no
-// overflow path.
+// min(n, S) per pattern).  Every occurrence emits at most one record of each rule shape, so each (shape, slot) has its
+// OWN 16-byte cell: record arrays are slot-indexed regions laid out in ascending converted-id order (no atomics, no
+// counters, deterministic, and already grouped by source id for the aggregation -- aggregate.cu); cells that stay
+// empty keep id = -1 from the memset that precedes the kernels.
+//   kind 0 (ab)   : [ab: ns0]
+//   kind 1        : [Xab: ns0][abX: ns0][aXb: ns1]
+//   kind 2        : [XabX: ns0][aXbXc: ns2][XaXb: ns1][aXbX: ns1]          (ns0/1/2 = contiguous / one-gap / two-gap slots)
 #include "batch.h"
 #include "prof.h"
 
@@ -41,20 +45,13 @@ __device__ __forceinline__ bool consistent(const ExtractIdx &x, int start, int e
     return !(startpos_source + (int)mn != start_chk || startpos_source + (int)mx != end_chk);
 }
 
-__device__ __forceinline__ void emit(RuleRec *__restrict__ out, unsigned long long *__restrict__ counter, int id, unsigned ts, unsigned te, int g1s,
-                                     int g1e, int g2s, int g2e) {
-    unsigned m = __activemask();
-    int leader = __ffs(m) - 1;
-    unsigned long long base = 0;
-    if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
-    base = __shfl_sync(m, base, leader);
-    size_t slot = (size_t)base + __popc(m & lanemask_lt());
+__device__ __forceinline__ void emit(RuleRec *__restrict__ out, size_t cell, int id, unsigned ts, unsigned te, int g1s, int g1e, int g2s, int g2e) {
     RuleRec r;
     r.id = id; r.tgt_start = (int32_t)ts; r.end = (uint8_t)(te - ts);
     r.gap1 = g1s < 0 ? 255 : (uint8_t)(g1s - (int)ts); r.gap1_1 = g1s < 0 ? 255 : (uint8_t)(g1e - (int)ts);
     r.gap2 = g2s < 0 ? 255 : (uint8_t)(g2s - (int)ts); r.gap2_1 = g2s < 0 ? 255 : (uint8_t)(g2e - (int)ts);
     r.pad[0] = r.pad[1] = r.pad[2] = 0;
-    *reinterpret_cast<uint4 *>(&out[slot]) = *reinterpret_cast<const uint4 *>(&r);
+    *reinterpret_cast<uint4 *>(&out[cell]) = *reinterpret_cast<const uint4 *>(&r);
 }
 
 // ExtractPair.cu:1133-1160 / :445-471 / :946-972 sampling.  Returns the occurrence index of slot j, or -1.
@@ -84,8 +81,8 @@ __global__ void slots_contig_kernel(const int32_t *__restrict__ phrases, int G, 
 }
 
 __global__ void __launch_bounds__(128) extract_contig_kernel(ExtractIdx x, const int32_t *__restrict__ phrases, int G, const uint32_t *__restrict__ slot_off,
-                                                             uint32_t n_slots, RuleRec *__restrict__ rec_ab, RuleRec *__restrict__ rec_1,
-                                                             RuleRec *__restrict__ rec_2, unsigned long long *__restrict__ counters) {
+                                                             uint32_t n_slots, RuleRec *__restrict__ rec_ab, RuleRec *__restrict__ rec_Xab,
+                                                             RuleRec *__restrict__ rec_abX, RuleRec *__restrict__ rec_XabX) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= n_slots) return;
     const int bnum = find_owner_u32(slot_off, G, slot);
@@ -121,7 +118,7 @@ __global__ void __launch_bounds__(128) extract_contig_kernel(ExtractIdx x, const
     tempind++;
     const int ender = current_str + longestmatch - 1;
     if (ab && consistent(x, (int)min_L + sen_target_begin, (int)max_R + sen_target_begin, current_str, ender, tempind))
-        emit(rec_ab, &counters[0], bnum, min_L + sen_target_begin, max_R + sen_target_begin, -1, -1, -1, -1);
+        emit(rec_ab, slot, bnum, min_L + sen_target_begin, max_R + sen_target_begin, -1, -1, -1, -1);
     if (longestmatch + 1 > CGX_MAX_RULE_SYMBOLS) { abX = false; Xab = false; }
     if (longestmatch + 2 > CGX_MAX_RULE_SYMBOLS) XabX = false;
 
@@ -147,7 +144,7 @@ __global__ void __launch_bounds__(128) extract_contig_kernel(ExtractIdx x, const
                 if (next) next = consistent(x, (int)target_start, (int)target_end, current_str - i, ender, tempind);
             }
             if (XabNoSuccess && next) {
-                emit(rec_1, &counters[1], bnum, target_start, target_end, (int)gap1_start, (int)gap1_end, -1, -1);
+                emit(rec_Xab, slot, bnum, target_start, target_end, (int)gap1_start, (int)gap1_end, -1, -1);
                 XabNoSuccess = false;
             }
         } else Xab = false;
@@ -172,7 +169,7 @@ __global__ void __launch_bounds__(128) extract_contig_kernel(ExtractIdx x, const
                 if (next) next = consistent(x, (int)target_start, (int)target_end, current_str, ender + i, tempind);
             }
             if (abXNoSuccess && next) {
-                emit(rec_1, &counters[1], globalc + bnum, target_start, target_end, (int)gap1_start, (int)gap1_end, -1, -1);
+                emit(rec_abX, slot, globalc + bnum, target_start, target_end, (int)gap1_start, (int)gap1_end, -1, -1);
                 abXNoSuccess = false;
             }
         } else abX = false;
@@ -201,7 +198,7 @@ __global__ void __launch_bounds__(128) extract_contig_kernel(ExtractIdx x, const
                         if (next) next = consistent(x, (int)target_start, (int)target_end, current_str - XabCount, ender + icount, tempind);
                         if (next) {
                             gap1_start = sen_target_begin + min_L_Xab; gap1_end = sen_target_begin + max_R_Xab;
-                            emit(rec_2, &counters[2], bnum, target_start, target_end, (int)gap1_start, (int)gap1_end, (int)gap2_start, (int)gap2_end);
+                            emit(rec_XabX, slot, bnum, target_start, target_end, (int)gap1_start, (int)gap1_end, (int)gap2_start, (int)gap2_end);
                             XabX = false;
                         }
                     }
@@ -230,7 +227,7 @@ __global__ void __launch_bounds__(128) extract_contig_kernel(ExtractIdx x, const
                         if (next) next = consistent(x, (int)target_start, (int)target_end, current_str - icount, ender + abXCount, tempind);
                         if (next) {
                             gap2_start = sen_target_begin + min_L_abX; gap2_end = sen_target_begin + max_R_abX;
-                            emit(rec_2, &counters[2], bnum, target_start, target_end, (int)gap1_start, (int)gap1_end, (int)gap2_start, (int)gap2_end);
+                            emit(rec_XabX, slot, bnum, target_start, target_end, (int)gap1_start, (int)gap1_end, (int)gap2_start, (int)gap2_end);
                             XabX = false;
                         }
                     }
@@ -306,8 +303,8 @@ __global__ void slots_pat1_kernel(const Pat1 *__restrict__ pat, int D1, uint32_t
 
 __global__ void __launch_bounds__(128) extract_onegap_kernel(ExtractIdx x, const Pat1 *__restrict__ pat, int D1, const uint64_t *__restrict__ hits1,
                                                              const uint32_t *__restrict__ slot_off, uint32_t n_slots, int G, int D2, int pbits,
-                                                             RuleRec *__restrict__ rec_1, RuleRec *__restrict__ rec_2,
-                                                             unsigned long long *__restrict__ counters) {
+                                                             RuleRec *__restrict__ rec_aXb, RuleRec *__restrict__ rec_XaXb,
+                                                             RuleRec *__restrict__ rec_aXbX) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= n_slots) return;
     const int d = find_owner_u32(slot_off, D1, slot);
@@ -333,7 +330,7 @@ __global__ void __launch_bounds__(128) extract_onegap_kernel(ExtractIdx x, const
     else if (re == 3) { next = false; left = false; }
     else if (re == 4) { next = false; left = false; right = false; }
     if ((target_start == 0 && target_end == 0) || min_L > max_R || gap1_start < target_start || gap1_end > target_end) return;   // :591-595
-    if (next) emit(rec_1, &counters[1], 2 * G + d, target_start, target_end, (int)gap1_start, (int)gap1_end, -1, -1);
+    if (next) emit(rec_aXb, slot, 2 * G + d, target_start, target_end, (int)gap1_start, (int)gap1_end, -1, -1);
     if (startLen + endLen + 2 > CGX_MAX_RULE_SYMBOLS) return;
     const unsigned originalGapStart = gap1_start, originalGapEnd = gap1_end;
     unsigned min_XaXb = 255, max_XaXb = 0, min_aXbX = 255, max_aXbX = 0, L, R, temp;
@@ -358,7 +355,7 @@ __global__ void __launch_bounds__(128) extract_onegap_kernel(ExtractIdx x, const
                 if (next) next = consistent(x, (int)target_start, (int)target_end, current_str - i, ender, tempind);
             }
             if (next) {
-                emit(rec_2, &counters[2], G + D2 + d, target_start, target_end, (int)g_s, (int)g_e, (int)originalGapStart, (int)originalGapEnd);
+                emit(rec_XaXb, slot, G + D2 + d, target_start, target_end, (int)g_s, (int)g_e, (int)originalGapStart, (int)originalGapEnd);
                 left = false;
             }
         } else left = false;
@@ -382,7 +379,7 @@ __global__ void __launch_bounds__(128) extract_onegap_kernel(ExtractIdx x, const
                 if (next) next = consistent(x, (int)target_start, (int)target_end, current_str, ender + i, tempind);
             }
             if (next) {
-                emit(rec_2, &counters[2], G + D2 + D1 + d, target_start, target_end, (int)originalGapStart, (int)originalGapEnd, (int)g_s, (int)g_e);
+                emit(rec_aXbX, slot, G + D2 + D1 + d, target_start, target_end, (int)originalGapStart, (int)originalGapEnd, (int)g_s, (int)g_e);
                 right = false;
             }
         } else right = false;
@@ -399,7 +396,7 @@ __global__ void slots_pat2_kernel(const Pat2 *__restrict__ pat, int D2, uint32_t
 
 __global__ void __launch_bounds__(128) extract_twogap_kernel(ExtractIdx x, const Pat2 *__restrict__ pat2, const Pat1 *__restrict__ pat1, int D2,
                                                              const uint64_t *__restrict__ hits2, const uint32_t *__restrict__ slot_off, uint32_t n_slots,
-                                                             int G, int pbits, RuleRec *__restrict__ rec_2, unsigned long long *__restrict__ counters) {
+                                                             int G, int pbits, RuleRec *__restrict__ rec_aXbXc) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= n_slots) return;
     const int d = find_owner_u32(slot_off, D2, slot);
@@ -418,37 +415,33 @@ __global__ void __launch_bounds__(128) extract_twogap_kernel(ExtractIdx x, const
     unsigned g2s = mnL + stb, g2e = mxR + stb;
     unsigned ts, te;
     if (check_boundary(x, current_str, current_str + secondEnd, &ts, &te) == 1)
-        emit(rec_2, &counters[2], G + d, ts, te, (int)g1s, (int)g1e, (int)g2s, (int)g2e);
-}
-
-// ------------------------------------------------------------------------------------------------
-static uint32_t read_u32(const uint32_t *d, cudaStream_t stream) {
-    uint32_t v = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&v, d, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    CUDA_CHECK(cudaStreamSynchronize(stream));
-    return v;
+        emit(rec_aXbXc, slot, G + d, ts, te, (int)g1s, (int)g1e, (int)g2s, (int)g2e);
 }
 
 void stage_extract(const Index &ix, Batch &b, cudaStream_t stream) {
     const int G = b.G, D1 = b.D1, D2 = b.D2;
     b.n_rec[0] = b.n_rec[1] = b.n_rec[2] = 0;
+    b.rec_cells[0] = b.rec_cells[1] = b.rec_cells[2] = 0;
+    b.n_slots[0] = b.n_slots[1] = b.n_slots[2] = 0;
     b.samples = 0;
     if (G == 0) return;
     ExtractIdx x{ix.sa.ptr<int32_t>(), ix.str.ptr<int32_t>(), ix.RLP.ptr<uint32_t>(), ix.L_tar.ptr<uint8_t>(), ix.R_tar.ptr<uint8_t>(), (int)ix.n};
-    uint32_t *tot = b.counters.get<uint32_t>(16);
-    unsigned long long *ctr = (unsigned long long *)(tot + 8);      // 3 record counters
-    CUDA_CHECK(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long) * 3, stream));
+    uint32_t *tot = b.counters.get<uint32_t>(32);
+    // slot offsets: G+1 / D1+1 / D2+1 entries (the last one = total), also read by the aggregation
     uint32_t *so0 = b.slot_off[0].get<uint32_t>((size_t)G + 2);
     slots_contig_kernel<<<cgx_div_up(G, 256), 256, 0, stream>>>(b.phrases.ptr<int32_t>(), G, so0);
     exclusive_scan_u32(so0, so0, (size_t)G, tot, stream, b.scan, 0, &b.launches);
+    CUDA_CHECK(cudaMemcpyAsync(so0 + G, tot, sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
     uint32_t *so1 = b.slot_off[1].get<uint32_t>((size_t)D1 + 2), *so2 = b.slot_off[2].get<uint32_t>((size_t)D2 + 2);
     if (D1) {
         slots_pat1_kernel<<<cgx_div_up(D1, 256), 256, 0, stream>>>(b.pat1.ptr<Pat1>(), D1, so1);
         exclusive_scan_u32(so1, so1, (size_t)D1, tot + 1, stream, b.scan, 0, &b.launches);
+        CUDA_CHECK(cudaMemcpyAsync(so1 + D1, tot + 1, sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
     }
     if (D2) {
         slots_pat2_kernel<<<cgx_div_up(D2, 256), 256, 0, stream>>>(b.pat2.ptr<Pat2>(), D2, so2);
         exclusive_scan_u32(so2, so2, (size_t)D2, tot + 2, stream, b.scan, 0, &b.launches);
+        CUDA_CHECK(cudaMemcpyAsync(so2 + D2, tot + 2, sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
     }
     uint32_t ns[3] = {0, 0, 0};
     CUDA_CHECK(cudaMemcpyAsync(ns, tot, sizeof(uint32_t) * 3, cudaMemcpyDeviceToHost, stream));
@@ -457,18 +450,22 @@ void stage_extract(const Index &ix, Batch &b, cudaStream_t stream) {
     if (!D2) ns[2] = 0;
     b.launches += 3;
     b.samples = (int64_t)ns[0] + ns[1] + ns[2];
-    // exact upper bounds: every sampled occurrence emits at most one record of each shape
-    size_t cap0 = ns[0], cap1 = (size_t)2 * ns[0] + ns[1], cap2 = (size_t)ns[0] + ns[2] + (size_t)2 * ns[1];
-    RuleRec *r0 = b.rec[0].get<RuleRec>(cap0 + 1), *r1 = b.rec[1].get<RuleRec>(cap1 + 1), *r2 = b.rec[2].get<RuleRec>(cap2 + 1);
-    if (ns[0]) PROF("extract_contig", 0.0, (extract_contig_kernel<<<cgx_div_up(ns[0], 128), 128, 0, stream>>>(x, b.phrases.ptr<int32_t>(), G, so0, ns[0], r0, r1, r2, ctr)));
-    if (ns[2]) PROF("extract_twogap", 0.0, (extract_twogap_kernel<<<cgx_div_up(ns[2], 128), 128, 0, stream>>>(x, b.pat2.ptr<Pat2>(), b.pat1.ptr<Pat1>(), D2, b.hits2_sorted.ptr<uint64_t>(), so2, ns[2], G, b.pbits, r2, ctr)));
-    if (ns[1]) PROF("extract_onegap", 0.0, (extract_onegap_kernel<<<cgx_div_up(ns[1], 128), 128, 0, stream>>>(x, b.pat1.ptr<Pat1>(), D1, b.hits1_sorted.ptr<uint64_t>(), so1, ns[1], G, D2, b.pbits, r1, r2, ctr)));
+    for (int k = 0; k < 3; k++) b.n_slots[k] = ns[k];
+    // one cell per (shape, slot)
+    const size_t c0 = ns[0], c1 = (size_t)2 * ns[0] + ns[1], c2 = (size_t)ns[0] + ns[2] + (size_t)2 * ns[1];
+    CGX_REQUIRE(c2 < (1ull << 32), "extraction: %zu record cells exceed the 32-bit cell index", c2);
+    b.rec_cells[0] = c0; b.rec_cells[1] = c1; b.rec_cells[2] = c2;
+    RuleRec *r0 = b.rec[0].get<RuleRec>(c0 + 1), *r1 = b.rec[1].get<RuleRec>(c1 + 1), *r2 = b.rec[2].get<RuleRec>(c2 + 1);
+    CUDA_CHECK(cudaMemsetAsync(r0, 0xff, sizeof(RuleRec) * c0, stream));
+    CUDA_CHECK(cudaMemsetAsync(r1, 0xff, sizeof(RuleRec) * c1, stream));
+    CUDA_CHECK(cudaMemsetAsync(r2, 0xff, sizeof(RuleRec) * c2, stream));
+    // algorithmic bytes (SURVEY 8d B_ext, lower bound): per sampled occurrence its SA / hit entry and slot owner (8 B), the
+    // RLP + text words of the smallest source window it must inspect (phrase + one extension token per side: 8 B x 5)
+    // and the L/R bytes of a 4-token target window (2 x 4) = 56 B; emitted cells are not counted
+    if (ns[0]) PROF("extract_contig", (double)ns[0] * 56, (extract_contig_kernel<<<cgx_div_up(ns[0], 128), 128, 0, stream>>>(x, b.phrases.ptr<int32_t>(), G, so0, ns[0], r0, r1, r1 + ns[0], r2)));
+    if (ns[2]) PROF("extract_twogap", (double)ns[2] * 56, (extract_twogap_kernel<<<cgx_div_up(ns[2], 128), 128, 0, stream>>>(x, b.pat2.ptr<Pat2>(), b.pat1.ptr<Pat1>(), D2, b.hits2_sorted.ptr<uint64_t>(), so2, ns[2], G, b.pbits, r2 + ns[0])));
+    if (ns[1]) PROF("extract_onegap", (double)ns[1] * 56, (extract_onegap_kernel<<<cgx_div_up(ns[1], 128), 128, 0, stream>>>(x, b.pat1.ptr<Pat1>(), D1, b.hits1_sorted.ptr<uint64_t>(), so1, ns[1], G, D2, b.pbits, r1 + (size_t)2 * ns[0], r2 + (size_t)ns[0] + ns[2], r2 + (size_t)ns[0] + ns[2] + ns[1])));
     b.launches += 3;
-    unsigned long long nrec[3];
-    CUDA_CHECK(cudaMemcpyAsync(nrec, ctr, sizeof(nrec), cudaMemcpyDeviceToHost, stream));
-    CUDA_CHECK(cudaStreamSynchronize(stream));
-    for (int k = 0; k < 3; k++) b.n_rec[k] = (int64_t)nrec[k];
-    (void)read_u32;
 }
 
 }  // namespace cgx
