@@ -305,6 +305,17 @@ def gpu_arm(args):
         info = ex.index_info()
         log("[rank %d] index broadcast over NCCL: %.1f MB in %.1f ms" % (rank, bcast_bytes / 1e6, bcast_ms))
 
+    # ---- SA build ms (second headline metric): tokens resident in HBM -> sa[] in HBM, warm (1 untimed + 3 timed builds)
+    sa_ms = None
+    if rank == 0:
+        str_d = torch.from_numpy(np.ascontiguousarray(lay["str"], dtype=np.int32)).to(dev)
+        sa_d = torch.empty(int(lay["n"]), dtype=torch.int32, device=dev)
+        ex.sa_build_dev(str_d.data_ptr(), int(lay["n"]), int(lay["str"][: lay["n"]].max()), sa_d.data_ptr())
+        runs = [ex.sa_build_dev(str_d.data_ptr(), int(lay["n"]), int(lay["str"][: lay["n"]].max()), sa_d.data_ptr())[1] for _ in range(3)]
+        sa_ms = float(np.mean(runs))
+        log("SA build (warm, tokens in HBM): %.2f ms mean of %s" % (sa_ms, ["%.2f" % r for r in runs]))
+        del str_d, sa_d
+
     # device-resident query batch (value) and pinned host copies (e2e)
     qt_h = torch.from_numpy(np.ascontiguousarray(lay["qry_tok"], dtype=np.int32)).pin_memory()
     qo_h = torch.from_numpy(np.ascontiguousarray(lay["qry_off"], dtype=np.int32)).pin_memory()
@@ -405,9 +416,9 @@ def gpu_arm(args):
             "gpu_launches": int(binfo["launches"]) * args.steps,
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "sa_build": {"gpu_ms": info["sa_build_ms"], "rounds": info["sa_rounds"], "key_bits": info["sa_key_bits"],
+            "sa_build": {"gpu_ms": sa_ms, "gpu_ms_first_call": info["sa_build_ms"], "rounds": info["sa_rounds"], "key_bits": info["sa_key_bits"],
                          "alg_bytes": 16.0 * info["n"] * info["sa_rounds"],
-                         "gbs": 16.0 * info["n"] * info["sa_rounds"] / 1e9 / (info["sa_build_ms"] / 1e3) if info["sa_build_ms"] else None,
+                         "gbs": 16.0 * info["n"] * info["sa_rounds"] / 1e9 / (sa_ms / 1e3) if sa_ms else None,
                          "aux_index_ms": info["aux_build_ms"], "cpu_reference_s": cpu.get("sa_build_s") if cpu else None},
             "index_broadcast": {"ms": bcast_ms, "bytes": bcast_bytes} if world > 1 else None,
             "batch": {k: binfo[k] for k in ("G", "D1", "hits1", "D2", "hits2", "samples", "n_ab", "n_1gap", "n_2gap", "rules", "launches", "ms_lookup",

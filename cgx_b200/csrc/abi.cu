@@ -38,6 +38,8 @@ extern "C" int cgx_create(int device, cgx_ctx_t **out) {
         c->device = device;
         CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         for (auto &ev : c->batch.ev) CUDA_CHECK(cudaEventCreate(&ev));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&c->batch.copy_stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&c->batch.copy_ev, cudaEventDisableTiming));
         memset(&c->batch.info, 0, sizeof(c->batch.info));
         *out = c;
         return 0;
@@ -62,7 +64,7 @@ extern "C" void cgx_destroy(cgx_ctx_t *c) {
                     &b.phrases, &b.e1_count, &b.e1_inst, &b.e1_keys, &b.e1_keys_tmp, &b.e1_vals, &b.e1_vals_tmp, &b.e1_flags, &b.e1_pid, &b.pat1,
                     &b.pat1_dev, &b.pat1_pos, &b.ql_keys, &b.ql_keys_tmp, &b.q1_off, &b.q1_ids, &b.q2_off, &b.q2_ids, &b.j_tiles, &b.j_bitmaps, &b.j_aflag, &b.j_hash, &b.pat1_ga, &b.hit_keys,
                     &b.hit_keys_tmp, &b.counters, &b.missing, &b.hits1_sorted, &b.hits2_sorted, &b.e2_count, &b.e2_keys, &b.e2_keys_tmp, &b.e2_vals,
-                    &b.e2_vals_tmp, &b.e2_flags, &b.pat2, &b.rec_hash, &b.rec_flags, &b.rec_meta,
+                    &b.e2_vals_tmp, &b.e2_flags, &b.pat2, &b.rec_hash, &b.rec_tag, &b.rec_flags, &b.rec_meta,
                     &b.scratch, &b.scratch2, &b.rule_head, &b.radix.hist, &b.radix.status, &b.radix.counters};
     for (auto *x : bb) x->release();
     for (int k = 0; k < 3; k++) { b.slot_off[k].release(); b.rec[k].release(); b.rules[k].release(); b.updown[k].release(); b.id_count[k].release(); }
@@ -73,6 +75,8 @@ extern "C" void cgx_destroy(cgx_ctx_t *c) {
     for (int k = 0; k < 3; k++) { b.h_rules[k].release(); b.h_updown[k].release(); }
     c->prof.destroy();
     for (auto &ev : b.ev) if (ev) cudaEventDestroy(ev);
+    if (b.copy_ev) cudaEventDestroy(b.copy_ev);
+    if (b.copy_stream) cudaStreamDestroy(b.copy_stream);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -295,18 +299,22 @@ static void run_batch(cgx_ctx *c, int32_t Q, int32_t T, bool fetch) {
     CUDA_CHECK(cudaEventRecord(b.ev[4], s));
     stage_twogap_join(ix, b, s);
     CUDA_CHECK(cudaEventRecord(b.ev[5], s));
-    stage_extract(ix, b, s);
-    CUDA_CHECK(cudaEventRecord(b.ev[6], s));
-    stage_aggregate(ix, b, s);
-    if (fetch) {   // pattern tables and phrase ids to the (pinned) host mirrors
+    if (fetch) {   // the pattern tables and phrase ids are final here: they travel while extraction and aggregation run
         int32_t *hp = b.h_phrase_id.get<int32_t>((size_t)T * CGX_LONGEST_SRC + 1);
         int32_t *hph = b.h_phrases.get<int32_t>((size_t)b.G * 4 + 1);
         int32_t *h1 = b.h_pat1.get<int32_t>((size_t)b.D1 * 8 + 1);
         int32_t *h2 = b.h_pat2.get<int32_t>((size_t)b.D2 * 4 + 1);
-        if (T) CUDA_CHECK(cudaMemcpyAsync(hp, b.phrase_id.p, sizeof(int32_t) * (size_t)T * CGX_LONGEST_SRC, cudaMemcpyDeviceToHost, s));
-        if (b.G) CUDA_CHECK(cudaMemcpyAsync(hph, b.phrases.p, sizeof(int32_t) * (size_t)b.G * 4, cudaMemcpyDeviceToHost, s));
-        if (b.D1) CUDA_CHECK(cudaMemcpyAsync(h1, b.pat1.p, sizeof(int32_t) * (size_t)b.D1 * 8, cudaMemcpyDeviceToHost, s));
-        if (b.D2) CUDA_CHECK(cudaMemcpyAsync(h2, b.pat2.p, sizeof(int32_t) * (size_t)b.D2 * 4, cudaMemcpyDeviceToHost, s));
+        fetch_async(b, hp, b.phrase_id.p, sizeof(int32_t) * (size_t)T * CGX_LONGEST_SRC, s);
+        fetch_async(b, hph, b.phrases.p, sizeof(int32_t) * (size_t)b.G * 4, s);
+        fetch_async(b, h1, b.pat1.p, sizeof(int32_t) * (size_t)b.D1 * 8, s);
+        fetch_async(b, h2, b.pat2.p, sizeof(int32_t) * (size_t)b.D2 * 4, s);
+    }
+    stage_extract(ix, b, s);
+    CUDA_CHECK(cudaEventRecord(b.ev[6], s));
+    stage_aggregate(ix, b, s);
+    if (fetch) {   // the batch ends when the last result byte is on the host
+        CUDA_CHECK(cudaEventRecord(b.copy_ev, b.copy_stream));
+        CUDA_CHECK(cudaStreamWaitEvent(s, b.copy_ev, 0));
     }
     CUDA_CHECK(cudaEventRecord(b.ev[7], s));
     CUDA_CHECK(cudaStreamSynchronize(s));

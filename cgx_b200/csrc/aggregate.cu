@@ -11,7 +11,7 @@
 // consecutive cells of its pattern.  So no global sort is needed (round 1a-1c: a 64-bit hash sort + an id sort of
 // 1.2e8 records = 30 GB of radix passes per batch): every record gets a 64-bit hash of its target symbol sequence,
 // and one thread per cell compares its hash with the other cells of its segment (broadcast loads, the segment is
-// shared by the neighbouring threads): paircount = equal cells, rule head = first equal cell, f = non-empty cells,
+// shared by the neighbouring threads): paircount = equal cells, rule head = first equal cell, f = records of the id,
 // representative = equal cell with the smallest target start.  Heads are flagged, prefix-summed and compacted
 // into rules in (id, first cell) order -- deterministic.  Exactness does not rest on the hash: every non-head
 // record is compared symbol-by-symbol with its head, and a mismatch raises a flag on which the host re-runs the
@@ -61,9 +61,10 @@ struct AggLayout {
     uint32_t cells;
 };
 
-// hash[i] = 0 for an empty cell, else the (odd) hash of the record's target symbol sequence
+// hash[i] = 0 for an empty cell, else the (odd) hash of the record's target symbol sequence; tag[i] = its low word (the
+// 4-byte filter the grouping loop scans); id_count[id] = records of the id (-> f)
 __global__ void agg_hash_kernel(const RuleRec *__restrict__ rec, uint32_t cells, const int32_t *__restrict__ tgt, uint64_t seed, uint64_t *__restrict__ hash,
-                                unsigned long long *__restrict__ n_records) {
+                                uint32_t *__restrict__ tag, uint32_t *__restrict__ id_count, unsigned long long *__restrict__ n_records) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool live = false;
     if (i < cells) {
@@ -76,43 +77,50 @@ __global__ void agg_hash_kernel(const RuleRec *__restrict__ rec, uint32_t cells,
             h = seed ^ (uint64_t)ns;
             for (int k = 0; k < ns; k++) h = mix64(h ^ (uint64_t)sym[k]) + 0x9e3779b97f4a7c15ULL;
             h |= 1ull;
+            atomicAdd(&id_count[r.id], 1u);
         }
         hash[i] = h;
+        tag[i] = (uint32_t)h;
     }
     const unsigned m = __ballot_sync(0xffffffffu, live);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_records, (unsigned long long)__popc(m));
 }
 
 // One thread per cell: group the records of its segment (= the cells of its source id) by target sequence.
-//   flags[i] = 1 when cell i is the first cell of its rule; meta[i] = {representative cell, paircount | f << 16} for heads.
+//   flags[i] = 1 when cell i is the first cell of its rule; meta[i] = {representative cell, paircount} for heads.
+// A record that finds an equal cell before itself is not a head and stops there; heads scan the rest of the segment
+// for their paircount.  The loops read the 4-byte tags (the segment is shared by the neighbouring threads: L1 broadcast).
 __global__ void __launch_bounds__(256) agg_group_kernel(AggLayout lay, const RuleRec *__restrict__ rec, const uint64_t *__restrict__ hash,
-                                                        const int32_t *__restrict__ tgt, uint32_t *__restrict__ flags, uint2 *__restrict__ meta,
-                                                        int *__restrict__ collision) {
+                                                        const uint32_t *__restrict__ tag, const int32_t *__restrict__ tgt, uint32_t *__restrict__ flags,
+                                                        uint2 *__restrict__ meta, int *__restrict__ collision) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= lay.cells) return;
     const uint64_t h = hash[i];
     if (h == 0) { flags[i] = 0; return; }
+    const uint32_t t = (uint32_t)h;
     const RuleRec r = rec[i];
     int reg = 0;
 #pragma unroll
     for (int k = 1; k < 4; k++) if (k < lay.n_regions && i >= lay.r[k].base) reg = k;
     const uint32_t pat = (uint32_t)(r.id - lay.r[reg].id_base);
     const uint32_t s0 = lay.r[reg].base + __ldg(&lay.r[reg].slot_off[pat]), s1 = lay.r[reg].base + __ldg(&lay.r[reg].slot_off[pat + 1]);
-    uint32_t first = i, best = i, cnt = 0, f = 0;
-    int best_ts = r.tgt_start;
-    for (uint32_t j = s0; j < s1; j++) {
-        const uint64_t hj = __ldg(&hash[j]);
-        f += hj != 0;
-        if (hj == h) {
-            cnt++;
-            if (j < first) first = j;
-            const int tsj = __ldg(&rec[j].tgt_start);
-            if (tsj < best_ts || (tsj == best_ts && j < best)) { best = j; best_ts = tsj; }
-        }
-    }
+    uint32_t first = i;
+#pragma unroll 4
+    for (uint32_t j = s0; j < i; j++)
+        if (__ldg(&tag[j]) == t && __ldg(&hash[j]) == h) { first = j; break; }
     if (first == i) {
+        uint32_t best = i, cnt = 1;
+        int best_ts = r.tgt_start;
+#pragma unroll 4
+        for (uint32_t j = i + 1; j < s1; j++) {
+            if (__ldg(&tag[j]) == t && __ldg(&hash[j]) == h) {
+                cnt++;
+                const int tsj = __ldg(&rec[j].tgt_start);
+                if (tsj < best_ts) { best = j; best_ts = tsj; }
+            }
+        }
         flags[i] = 1;
-        meta[i] = make_uint2(best, cnt | (f << 16));
+        meta[i] = make_uint2(best, cnt);
     } else {
         flags[i] = 0;
         const RuleRec q = rec[first];
@@ -172,19 +180,19 @@ __global__ void agg_head_cell_kernel(const uint32_t *__restrict__ excl, uint32_t
 
 // One thread per distinct rule: paircount, f, fs, representative record, lexical weights.
 __global__ void __launch_bounds__(128) agg_rules_kernel(AggIdx a, int kind, const RuleRec *__restrict__ rec, const uint32_t *__restrict__ head_cell,
-                                                        const uint2 *__restrict__ meta, uint32_t n_rules, const ulonglong2 *__restrict__ lex,
-                                                        uint32_t lex_mask, cgx_rule_t *__restrict__ rules) {
+                                                        const uint2 *__restrict__ meta, uint32_t n_rules, const uint32_t *__restrict__ id_count,
+                                                        const ulonglong2 *__restrict__ lex, uint32_t lex_mask, cgx_rule_t *__restrict__ rules) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rules) return;
     const uint2 mt = meta[head_cell[r]];
     const RuleRec best = rec[mt.x];
-    const int pc = (int)(mt.y & 0xffffu);
+    const int pc = (int)mt.y;
     cgx_rule_t out;
     out.id = best.id; out.tgt_start = best.tgt_start; out.end = best.end;
     out.gap1 = best.gap1; out.gap1_1 = best.gap1_1; out.gap2 = best.gap2; out.gap2_1 = best.gap2_1;
     out.pad[0] = out.pad[1] = out.pad[2] = 0;
     out.pc = pc;
-    out.f = (int)(mt.y >> 16);
+    out.f = (int)id_count[best.id];
     int fs = fsample_of(a, kind, best.id);
     out.fs = fs > CGX_SAMPLER ? CGX_SAMPLER : fs;                          // ExtractPair.c:638,910,1249
     // ---- lexicalTaskMaxEF (ExtractPair.cu:2144-2432): for every source terminal the best MaxLexFgivenE over the target
@@ -206,23 +214,21 @@ __global__ void __launch_bounds__(128) agg_rules_kernel(AggIdx a, int kind, cons
         float mx = 0.f;
         if (nf > 0) { lex_get(lex, lex_mask, -1, e, &v1, &v2); mx = fmaxf(mx, v1); }
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            if (j < nf) {
-                lex_get(lex, lex_mask, F[j], e, &v1, &v2);
-                mx = fmaxf(mx, v1);
-                mxf[j] = fmaxf(mxf[j], v2);
-            }
+        for (int j = 0; j < 5; j++) {                                       // nf <= 5 (CGX_LONGEST_SRC / MAX_rule_symbols)
+            if (j >= nf) break;
+            lex_get(lex, lex_mask, F[j], e, &v1, &v2);
+            mx = fmaxf(mx, v1);
+            mxf[j] = fmaxf(mxf[j], v2);
         }
         egivenf += mx > 0.f ? -__log10f(mx) : CGX_MAXSCORE;
     }
     float fgivene = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-        if (j < nf) {
-            float mx = mxf[j];
-            if (any_e) { lex_get(lex, lex_mask, F[j], -1, &v1, &v2); mx = fmaxf(mx, v2); }
-            fgivene += mx > 0.f ? -__log10f(mx) : CGX_MAXSCORE;
-        }
+    for (int j = 0; j < 5; j++) {
+        if (j >= nf) break;
+        float mx = mxf[j];
+        if (any_e) { lex_get(lex, lex_mask, F[j], -1, &v1, &v2); mx = fmaxf(mx, v2); }
+        fgivene += mx > 0.f ? -__log10f(mx) : CGX_MAXSCORE;
     }
     out.max_lex_f_given_e = fgivene;
     out.max_lex_e_given_f = egivenf;
@@ -251,7 +257,8 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
     uint32_t *tot = b.counters.get<uint32_t>(32);
     int *collision = (int *)(tot + 14);
     unsigned long long *n_records = (unsigned long long *)(tot + 16);
-    for (int kind = 0; kind < 3; kind++) {
+    for (int kk = 0; kk < 3; kk++) {
+        const int kind = 2 - kk;                           // largest result first: its D2H overlaps the other kinds' kernels
         const uint32_t N = (uint32_t)b.rec_cells[kind];
         lay[kind].cells = N;
         for (int k = lay[kind].n_regions; k < 4; k++) lay[kind].r[k] = lay[kind].r[0];
@@ -265,14 +272,17 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
         uint64_t *hash = b.rec_hash.get<uint64_t>((size_t)N);
         uint32_t *flags = b.rec_flags.get<uint32_t>((size_t)N + 2);
         uint2 *meta = b.rec_meta.get<uint2>((size_t)N);
+        uint32_t *tag = b.rec_tag.get<uint32_t>((size_t)N);
+        uint32_t *id_count = b.id_count[kind].get<uint32_t>((size_t)nids[kind]);
         int32_t *updown = b.updown[kind].get<int32_t>((size_t)2 * nids[kind]);
         uint64_t seed = 0x243f6a8885a308d3ULL;
         uint32_t R = 0;
         for (int attempt = 0; attempt < 8; attempt++, seed = seed * 6364136223846793005ULL + 1442695040888963407ULL) {
             CUDA_CHECK(cudaMemsetAsync(collision, 0, sizeof(int), stream));
             CUDA_CHECK(cudaMemsetAsync(n_records, 0, sizeof(unsigned long long), stream));
-            PROF("agg_hash", (double)N * 24, (agg_hash_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(rec, N, ix.tgt.ptr<int32_t>(), seed, hash, n_records)));
-            PROF("agg_group", (double)N * (8 + 4), (agg_group_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(lay[kind], rec, hash, ix.tgt.ptr<int32_t>(), flags, meta, collision)));
+            CUDA_CHECK(cudaMemsetAsync(id_count, 0, sizeof(uint32_t) * (size_t)nids[kind], stream));
+            PROF("agg_hash", (double)N * 28, (agg_hash_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(rec, N, ix.tgt.ptr<int32_t>(), seed, hash, tag, id_count, n_records)));
+            PROF("agg_group", (double)N * (8 + 4), (agg_group_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(lay[kind], rec, hash, tag, ix.tgt.ptr<int32_t>(), flags, meta, collision)));
             exclusive_scan_u32(flags, flags, N, tot, stream, b.scan, 0, &b.launches);
             b.launches += 2;
             uint32_t hostv[20];
@@ -291,7 +301,7 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
                 cgx_rule_t *rules = b.rules[kind].get<cgx_rule_t>(R);
                 uint32_t *head_cell = b.rule_head.get<uint32_t>((size_t)R + 2);
                 agg_head_cell_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(flags, N, R, head_cell);
-                PROF("agg_rules", (double)R * (4 + 8 + 16 + 36) + (double)R * 13 * 16, (agg_rules_kernel<<<cgx_div_up(R, 128), 128, 0, stream>>>(a, kind, rec, head_cell, meta, R,
+                PROF("agg_rules", (double)R * (4 + 8 + 16 + 36) + (double)R * 13 * 16, (agg_rules_kernel<<<cgx_div_up(R, 128), 128, 0, stream>>>(a, kind, rec, head_cell, meta, R, id_count,
                                                                        ix.lex_hash.ptr<ulonglong2>(), ix.lex_hash_mask, rules)));
                 CUDA_CHECK(cudaMemsetAsync(updown, 0xff, sizeof(int32_t) * 2 * (size_t)nids[kind], stream));
                 agg_updown_kernel<<<cgx_div_up(R, 256), 256, 0, stream>>>(rules, R, updown);
@@ -303,8 +313,8 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
         b.n_rules[kind] = (int32_t)R;
         if (b.fetch_results) {
             cgx_rule_t *h_r = b.h_rules[kind].get<cgx_rule_t>((size_t)R + 1);
-            if (R) CUDA_CHECK(cudaMemcpyAsync(h_r, b.rules[kind].ptr<cgx_rule_t>(), sizeof(cgx_rule_t) * R, cudaMemcpyDeviceToHost, stream));
-            if (R) CUDA_CHECK(cudaMemcpyAsync(h_ud, updown, sizeof(int32_t) * 2 * (size_t)nids[kind], cudaMemcpyDeviceToHost, stream));
+            if (R) fetch_async(b, h_r, b.rules[kind].ptr<cgx_rule_t>(), sizeof(cgx_rule_t) * R, stream);
+            if (R) fetch_async(b, h_ud, updown, sizeof(int32_t) * 2 * (size_t)nids[kind], stream);
         }
     }
 }

@@ -53,7 +53,7 @@ struct Batch {
     DevBuf e2_count, e2_keys, e2_keys_tmp, e2_vals, e2_vals_tmp, e2_flags, pat2;
     int32_t enu2 = 0, D2 = 0;
     // extraction
-    DevBuf slot_off[3], rec[3], rec_hash, rec_flags, rec_meta;   // rec[k]: slot-indexed cells (extract.cu), empty cells have id = -1
+    DevBuf slot_off[3], rec[3], rec_hash, rec_tag, rec_flags, rec_meta;   // rec[k]: slot-indexed cells (extract.cu), empty cells have id = -1
     size_t rec_cells[3] = {0, 0, 0};       // cells per kind
     int64_t n_slots[3] = {0, 0, 0};        // sampled-occurrence slots: contiguous / one-gap / two-gap
     int64_t n_rec[3] = {0, 0, 0};          // non-empty cells per kind
@@ -75,8 +75,19 @@ struct Batch {
     bool fetch_results = true;       // false: results stay on the device (device-resident throughput measurement)
     cgx_batch_info_t info;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // results travel to the (pinned) host mirrors on their own stream, overlapping the kernels that follow their producer
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_ev = nullptr;
     int launches = 0;
 };
+
+// D2H of a finished result array: ordered after everything enqueued so far on `stream`, runs on the copy stream
+static inline void fetch_async(Batch &b, void *dst, const void *src, size_t bytes, cudaStream_t stream) {
+    if (!bytes) return;
+    CUDA_CHECK(cudaEventRecord(b.copy_ev, stream));
+    CUDA_CHECK(cudaStreamWaitEvent(b.copy_stream, b.copy_ev, 0));
+    CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, b.copy_stream));
+}
 
 // stages (each enqueues on `stream`; those that need a count on the host synchronise once)
 void stage_lookup(const Index &ix, Batch &b, cudaStream_t stream);

@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(J1_BLOCK) j1_scan_kernel(const J1Args a) {
             if (cand[le - 1]) cand[le - 1] = bit_test((le == 1 && miss) ? a.bm_marker : a.bm[le - 1], ub[le - 1]);
 #pragma unroll
         for (int le = 1; le <= 3; le++) {
+            if (!__any_sync(0xffffffffu, cand[le - 1])) continue;          // warp-uniform
             uint64_t v = 0;
             bool found = cand[le - 1] && ht_find(a.slots, a.mask, key1_of((uint32_t)ga, le, ub[le - 1]), &v);
             if (found && miss) {                                           // only le == 1 reaches here with miss set

@@ -232,8 +232,8 @@ static void build_query_lists(Batch &b, const int32_t *pid, const int32_t *qid, 
     b.launches += 4;
     if (!b.fetch_results) return;
     int32_t *hi = h_ids.get<int32_t>((size_t)M + 1);
-    CUDA_CHECK(cudaMemcpyAsync(ho, off, sizeof(int32_t) * ((size_t)Q + 1), cudaMemcpyDeviceToHost, stream));
-    CUDA_CHECK(cudaMemcpyAsync(hi, ids, sizeof(int32_t) * (size_t)M, cudaMemcpyDeviceToHost, stream));
+    fetch_async(b, ho, off, sizeof(int32_t) * ((size_t)Q + 1), stream);
+    fetch_async(b, hi, ids, sizeof(int32_t) * (size_t)M, stream);
 }
 
 void stage_onegap_enumerate(const Index &ix, Batch &b, cudaStream_t stream) {
