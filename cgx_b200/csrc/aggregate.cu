@@ -72,11 +72,23 @@ __global__ void agg_hash_kernel(const RuleRec *__restrict__ rec, uint32_t cells,
         uint64_t h = 0;
         if (r.id >= 0) {
             live = true;
-            uint32_t sym[16];
-            const int ns = target_symbols(tgt, r, sym);
-            h = seed ^ (uint64_t)ns;
-            for (int k = 0; k < ns; k++) h = mix64(h ^ (uint64_t)sym[k]) + 0x9e3779b97f4a7c15ULL;
-            h |= 1ull;
+            uint32_t tok[15];                                     // the span is <= 15 tokens: issue every load before using any
+#pragma unroll
+            for (int j = 0; j < 15; j++) tok[j] = j <= (int)r.end ? (uint32_t)__ldg(&tgt[r.tgt_start + j]) : 0u;
+            int ns = 0, skip_to = -1;                             // same walk as target_symbols()
+            uint64_t hh = 0;
+#pragma unroll
+            for (int j = 0; j < 15; j++) {
+                if (j > (int)r.end) break;
+                if (j <= skip_to) continue;
+                uint32_t sym;
+                if (r.gap1 != 255 && j >= (int)r.gap1 && j <= (int)r.gap1_1) { sym = 0xFFFFFFFFu; skip_to = r.gap1_1; }
+                else if (r.gap2 != 255 && j >= (int)r.gap2 && j <= (int)r.gap2_1) { sym = 0xFFFFFFFEu; skip_to = r.gap2_1; }
+                else sym = tok[j];
+                hh = mix64(hh ^ (uint64_t)sym) + 0x9e3779b97f4a7c15ULL;
+                ns++;
+            }
+            h = (mix64(hh ^ seed ^ (uint64_t)ns)) | 1ull;
             atomicAdd(&id_count[r.id], 1u);
         }
         hash[i] = h;

@@ -33,6 +33,21 @@ __device__ __forceinline__ void ht_insert(ulonglong2 *__restrict__ slots, uint32
     }
 }
 
+// Two-step lookup for memory-level parallelism: the caller loads the first slot of several keys back to back
+// (ht_first), then resolves each (ht_resolve continues along the probe sequence only on a collision).
+__device__ __forceinline__ ulonglong2 ht_first(const ulonglong2 *__restrict__ slots, uint32_t mask, uint64_t key, uint32_t *slot) {
+    *slot = ht_mix(key) & mask;
+    return __ldg(&slots[*slot]);
+}
+__device__ __forceinline__ bool ht_resolve(const ulonglong2 *__restrict__ slots, uint32_t mask, uint64_t key, uint32_t s, ulonglong2 v, uint64_t *payload) {
+    while (true) {
+        if (v.x == key) { *payload = v.y; return true; }
+        if (v.x == HT_EMPTY) return false;
+        s = (s + 1) & mask;
+        v = __ldg(&slots[s]);
+    }
+}
+
 __device__ __forceinline__ bool ht_find(const ulonglong2 *__restrict__ slots, uint32_t mask, uint64_t key, uint64_t *payload) {
     uint32_t s = ht_mix(key) & mask;
     while (true) {

@@ -83,6 +83,18 @@ __global__ void ix_gap_words_kernel(const int32_t *__restrict__ str, const uint3
     gapw[i] = word;
 }
 
+__global__ void ix_jwin_kernel(const int32_t *__restrict__ b1, const int32_t *__restrict__ b2, const int32_t *__restrict__ b3,
+                               const uint32_t *__restrict__ gapw, size_t n, int4 *__restrict__ jwin) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) jwin[p] = make_int4(b1[p], b2[p], b3[p], (int)gapw[p]);
+}
+
+void build_jwin(Index &ix, cudaStream_t stream) {
+    ix_jwin_kernel<<<cgx_div_up(ix.n, 256), 256, 0, stream>>>(ix.bkt[0].ptr<int32_t>(), ix.bkt[1].ptr<int32_t>(), ix.bkt[2].ptr<int32_t>(),
+                                                            ix.gapw.ptr<uint32_t>(), ix.n, ix.jwin.get<int4>(ix.n));
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+
 // lexical table -> hash.  Duplicate (f,e) rows: the first of the (stably) sorted run wins, like the binary search it replaces.
 __global__ void ix_lex_hash_kernel(const uint64_t *__restrict__ keys, const float *__restrict__ v1, const float *__restrict__ v2, size_t n,
                                    ulonglong2 *__restrict__ slots, uint32_t mask) {
@@ -152,7 +164,8 @@ void build_index_aux(Index &ix, SaWorkspace &ws, cudaStream_t stream, int *launc
         ix_bucket_scatter_kernel<<<cgx_div_up(n, 256), 256, 0, stream>>>(ks, vs, flags, start_of, n, ix.bkt[mlen - 1].get<int32_t>(n));
         if (launches) *launches += 3;
     }
-    CUDA_CHECK(cudaStreamSynchronize(stream));
+    build_jwin(ix, stream);
+    if (launches) *launches += 1;
 }
 
 }  // namespace cgx

@@ -75,7 +75,7 @@ __device__ __forceinline__ bool bit_test(const uint32_t *__restrict__ bm, uint32
 __global__ void j1_setup_kernel(const Pat1 *__restrict__ pat, const Pat1Dev *__restrict__ patd, const int32_t *__restrict__ pat_ga, int D1,
                                 const int32_t *__restrict__ str, const uint8_t *__restrict__ freq_rank, ulonglong2 *__restrict__ slots, uint32_t mask,
                                 uint32_t *__restrict__ bm1, uint32_t *__restrict__ bm2, uint32_t *__restrict__ bm3, uint32_t *__restrict__ bm_marker,
-                                uint32_t *__restrict__ aflag) {
+                                uint32_t *__restrict__ aflag, uint32_t *__restrict__ bma, size_t bm_words, uint32_t *__restrict__ aid, size_t n) {
     int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= D1) return;
     const Pat1 p = pat[d];
@@ -87,6 +87,14 @@ __global__ void j1_setup_kernel(const Pat1 *__restrict__ pat, const Pat1Dev *__r
     if (p.marker_pair >= 0) atomicOr(&bm_marker[ub >> 5], 1u << (ub & 31));
     const uint32_t f = 1u | ((p.ls == 1 && freq_rank[str[p.a_pos]]) ? 2u : 0u);
     if (aflag[ga] != f) aflag[ga] = f;          // every writer of one slot writes the same value
+    // position-major scan: "an ls-gram with bucket up_a is a first phrase" (bitmap) and its phrase id (valid where the bit is set;
+    // entries of earlier batches are never read because the bitmap is cleared per batch)
+    const uint32_t ua = (uint32_t)patd[d].up_a;
+    uint32_t *ba = bma + (size_t)(p.ls - 1) * bm_words;
+    if (!((ba[ua >> 5] >> (ua & 31)) & 1u)) atomicOr(&ba[ua >> 5], 1u << (ua & 31));
+    const uint32_t av = ga | ((f & 2u) << 30);
+    uint32_t *ai = aid + (size_t)(p.ls - 1) * n;
+    if (ai[ua] != av) ai[ua] = av;
 }
 
 // elements per phrase: its occurrence count when it is the first phrase of some pattern, else 0
@@ -171,11 +179,16 @@ __global__ void __launch_bounds__(J1_BLOCK) j1_scan_kernel(const J1Args a) {
 #pragma unroll
         for (int le = 1; le <= 3; le++)
             if (cand[le - 1]) cand[le - 1] = bit_test((le == 1 && miss) ? a.bm_marker : a.bm[le - 1], ub[le - 1]);
+        ulonglong2 sv[3];
+        uint32_t ss[3];
+#pragma unroll
+        for (int le = 1; le <= 3; le++)
+            if (cand[le - 1]) sv[le - 1] = ht_first(a.slots, a.mask, key1_of((uint32_t)ga, le, ub[le - 1]), &ss[le - 1]);
 #pragma unroll
         for (int le = 1; le <= 3; le++) {
             if (!__any_sync(0xffffffffu, cand[le - 1])) continue;          // warp-uniform
             uint64_t v = 0;
-            bool found = cand[le - 1] && ht_find(a.slots, a.mask, key1_of((uint32_t)ga, le, ub[le - 1]), &v);
+            bool found = cand[le - 1] && ht_resolve(a.slots, a.mask, key1_of((uint32_t)ga, le, ub[le - 1]), ss[le - 1], sv[le - 1], &v);
             if (found && miss) {                                           // only le == 1 reaches here with miss set
                 if (v & 0x80000000u) atomicAdd(&a.missing[v & 0x7fffffffu], 1);
                 found = false;
@@ -188,6 +201,120 @@ __global__ void __launch_bounds__(J1_BLOCK) j1_scan_kernel(const J1Args a) {
     stage_flush(stage, staged, &a.counter[0], a.hits, a.cap);
     for (int o = 16; o; o >>= 1) probes += __shfl_xor_sync(0xffffffffu, probes, o);
     if (lane == 0 && probes) atomicAdd(&a.counter[1], (unsigned long long)probes);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Position-major variant (large batches).  The phrase-major scan above fetches the 15-token window of every occurrence
+// of every first phrase separately -- random 32-byte sectors, and B200 sustains only ~47 G random sectors/s
+// (tools/gather_bench.cu: 1.5 TB/s against 6.5 TB/s streaming).  When most corpus positions start a first phrase anyway,
+// it is cheaper to STREAM the interleaved window array jwin = {bkt1, bkt2, bkt3, gapw} once through shared memory: a CTA
+// stages 256+17 consecutive positions, each half-warp takes 16 of them; lane h tests "is the m-gram at position P+h a first
+// phrase" for m = 1..3 (three L2-resident bitmaps), and every (position, m) that is one runs the same 13-lane window
+// logic as above on shared memory.  HBM traffic: 16 B per corpus position + the pattern-table probes.
+// ------------------------------------------------------------------------------------------------
+constexpr int JP_TILE = 256;         // positions per CTA
+constexpr int JP_HALO = 17;          // q <= p + 3 + 13
+
+struct JPArgs {
+    const int4 *jwin;
+    uint32_t n;
+    const uint32_t *bma[3];          // first-phrase bitmaps by length
+    const uint32_t *aid[3];          // bucket -> phrase id | frequent-single-token flag << 31
+    const uint32_t *bm[3];
+    const uint32_t *bm_marker;
+    const ulonglong2 *slots;
+    uint32_t mask;
+    int pshift;
+    unsigned long long *counter;     // [0] hits, [1] table lookups, [2] elements
+    uint64_t *hits;
+    size_t cap;
+    int32_t *missing;
+};
+
+__global__ void __launch_bounds__(JP_TILE) j1_pos_kernel(const JPArgs a) {
+    __shared__ int4 s_win[JP_TILE + JP_HALO];
+    __shared__ uint64_t s_stage[JP_TILE / 32][ST_CAP];
+    uint64_t *stage = s_stage[threadIdx.x >> 5];
+    int staged = 0;
+    const unsigned lane = threadIdx.x & 31, half = lane >> 4, h = lane & 15;
+    const uint32_t P0 = blockIdx.x * (uint32_t)JP_TILE;
+    for (int i = threadIdx.x; i < JP_TILE + JP_HALO; i += JP_TILE) {
+        const uint32_t p = P0 + i;
+        s_win[i] = p < a.n ? __ldg(&a.jwin[p]) : make_int4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    // this half-warp's 16 positions: lane h owns position hp + h while the first-phrase tests run
+    const int hw = (int)(threadIdx.x >> 4);                     // 0..15
+    const int my = hw * 16 + (int)h;                            // tile-relative position of this lane
+    const int4 mine = s_win[my];
+    uint32_t my_aid[3];
+    unsigned my_mask = 0;
+    const bool inside = P0 + my < a.n;
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+        const uint32_t ub = (uint32_t)(m == 0 ? mine.x : m == 1 ? mine.y : mine.z);
+        my_aid[m] = 0;
+        if (inside && bit_test(a.bma[m], ub)) { my_mask |= 1u << m; my_aid[m] = __ldg(&a.aid[m][ub]); }
+    }
+    const int g = (int)h + 1;
+    unsigned lookups = 0, elems = 0;
+    // walk the 16 positions of both half-warps in lock step (warp-uniform trip count)
+    for (int k = 0; k < 16; k++) {
+        const int src = (int)(half * 16) + k;
+        const unsigned pm = __shfl_sync(0xffffffffu, my_mask, src);
+        const uint32_t a0 = __shfl_sync(0xffffffffu, my_aid[0], src), a1 = __shfl_sync(0xffffffffu, my_aid[1], src), a2 = __shfl_sync(0xffffffffu, my_aid[2], src);
+        if (!__any_sync(0xffffffffu, pm != 0)) continue;
+        const int rel = hw * 16 + k;                              // tile-relative position p
+        const int p = (int)P0 + rel;
+#pragma unroll
+        for (int ls = 1; ls <= 3; ls++) {
+            const bool on = (pm >> (ls - 1)) & 1u;
+            if (!__any_sync(0xffffffffu, on)) continue;
+            const uint32_t av = ls == 1 ? a0 : ls == 2 ? a1 : a2;
+            const uint32_t ga = av & 0x7fffffffu;
+            const uint32_t w = on ? (uint32_t)s_win[rel + ls].w : 0u;
+            const int run = (int)((w >> 16) & 15u);
+            const bool live = on && g <= run && g <= CGX_MAX_RULE_SPAN - 1 - ls;
+            const bool ok = live && ((w >> (g - 1)) & 1u);
+            const bool miss = live && !ok && (av >> 31);
+            const int qrel = rel + ls + g;
+            const uint32_t q = (uint32_t)(p + ls + g);
+            const int le_max = min(min(3, CGX_MAX_RULE_SYMBOLS - 1 - ls), CGX_MAX_RULE_SPAN - ls - g);
+            if (h == 0 && on) elems++;
+            uint32_t ub[3];
+            bool cand[3];
+            const int4 wq = (ok || miss) ? s_win[qrel] : make_int4(0, 0, 0, 0);
+#pragma unroll
+            for (int le = 1; le <= 3; le++) {
+                cand[le - 1] = (ok && le <= le_max && q + (uint32_t)le <= a.n) || (miss && le == 1 && q < a.n);
+                ub[le - 1] = (uint32_t)(le == 1 ? wq.x : le == 2 ? wq.y : wq.z);
+            }
+#pragma unroll
+            for (int le = 1; le <= 3; le++)
+                if (cand[le - 1]) cand[le - 1] = bit_test((le == 1 && miss) ? a.bm_marker : a.bm[le - 1], ub[le - 1]);
+            ulonglong2 sv[3];
+            uint32_t ss[3];
+#pragma unroll
+            for (int le = 1; le <= 3; le++)
+                if (cand[le - 1]) { sv[le - 1] = ht_first(a.slots, a.mask, key1_of(ga, le, ub[le - 1]), &ss[le - 1]); lookups++; }
+#pragma unroll
+            for (int le = 1; le <= 3; le++) {
+                if (!__any_sync(0xffffffffu, cand[le - 1])) continue;
+                uint64_t v = 0;
+                bool found = cand[le - 1] && ht_resolve(a.slots, a.mask, key1_of(ga, le, ub[le - 1]), ss[le - 1], sv[le - 1], &v);
+                if (found && miss) {
+                    if (v & 0x80000000u) atomicAdd(&a.missing[v & 0x7fffffffu], 1);
+                    found = false;
+                }
+                const uint64_t key = ((uint64_t)(v & 0x7fffffffu) << a.pshift) | ((uint64_t)(uint32_t)p << 4) | (uint64_t)(ls + g + le - 1);
+                stage_push(found, key, stage, staged);
+            }
+            if (staged > ST_CAP - 96) stage_flush(stage, staged, &a.counter[0], a.hits, a.cap);
+        }
+    }
+    stage_flush(stage, staged, &a.counter[0], a.hits, a.cap);
+    for (int o = 16; o; o >>= 1) { lookups += __shfl_xor_sync(0xffffffffu, lookups, o); elems += __shfl_xor_sync(0xffffffffu, elems, o); }
+    if (lane == 0 && (lookups | elems)) { atomicAdd(&a.counter[1], (unsigned long long)lookups); atomicAdd(&a.counter[2], (unsigned long long)elems); }
 }
 
 // per-pattern [start,count] in the sorted hit list
@@ -226,18 +353,20 @@ void stage_onegap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     if (D1 == 0) return;
     CGX_REQUIRE(cgx_bits_for((uint64_t)D1) + b.pbits + 4 <= 64 && ix.n < (1ull << 30) && D1 < (1 << 30), "one-gap join: pattern/corpus size exceeds the hit-key fields");
     const size_t bm_words = (ix.n + 31) / 32 + 1;
-    uint32_t *bm = b.j_bitmaps.get<uint32_t>(4 * bm_words);
+    uint32_t *bm = b.j_bitmaps.get<uint32_t>(7 * bm_words);            // [0..2] second phrases by length, [3] marker, [4..6] first phrases
+    uint32_t *aid = b.j_aid.get<uint32_t>(3 * ix.n);                   // bucket -> first-phrase id, valid where the first-phrase bit is set
     uint32_t *aflag = b.j_aflag.get<uint32_t>((size_t)G + 1);
     uint32_t *eoff = b.j_tiles.get<uint32_t>((size_t)G + 2);
     const uint32_t slots_n = ht_slots_for((size_t)D1);
     ulonglong2 *slots = b.j_hash.get<ulonglong2>(slots_n);
     uint32_t *tot = b.counters.get<uint32_t>(32);
     unsigned long long *ctr = (unsigned long long *)(tot + 4);         // [0] hits [1] bucket words read
-    CUDA_CHECK(cudaMemsetAsync(bm, 0, sizeof(uint32_t) * 4 * bm_words, stream));
+    CUDA_CHECK(cudaMemsetAsync(bm, 0, sizeof(uint32_t) * 7 * bm_words, stream));
     CUDA_CHECK(cudaMemsetAsync(aflag, 0, sizeof(uint32_t) * ((size_t)G + 1), stream));
     CUDA_CHECK(cudaMemsetAsync(slots, 0xff, sizeof(ulonglong2) * (size_t)slots_n, stream));
         PROF("join_setup", (double)D1 * (32 + 16 + 4 + 16), (j1_setup_kernel<<<cgx_div_up(D1, 256), 256, 0, stream>>>(b.pat1.ptr<Pat1>(), b.pat1_dev.ptr<Pat1Dev>(), b.pat1_ga.ptr<int32_t>(), D1, ix.str.ptr<int32_t>(),
-                                                                ix.freq_flag.ptr<uint8_t>(), slots, slots_n - 1, bm, bm + bm_words, bm + 2 * bm_words, bm + 3 * bm_words, aflag)));
+                                                                ix.freq_flag.ptr<uint8_t>(), slots, slots_n - 1, bm, bm + bm_words, bm + 2 * bm_words, bm + 3 * bm_words, aflag,
+                                                                bm + 4 * bm_words, bm_words, aid, ix.n)));
     j1_counts_kernel<<<cgx_div_up(G, 256), 256, 0, stream>>>(b.phrases.ptr<int32_t>(), aflag, G, eoff);
     exclusive_scan_u32(eoff, eoff, (size_t)G, tot, stream, b.scan, 0, &b.launches);
     b.launches += 2;
@@ -251,20 +380,31 @@ void stage_onegap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     for (int k = 0; k < 3; k++) { a.inv[k] = ix.inv[k].ptr<int32_t>(); a.bkt[k] = ix.bkt[k].ptr<int32_t>(); a.bm[k] = bm + (size_t)k * bm_words; }
     a.gapw = ix.gapw.ptr<uint32_t>(); a.bm_marker = bm + 3 * bm_words; a.slots = slots; a.mask = slots_n - 1;
     a.pshift = b.pbits + 4; a.n = (uint32_t)ix.n; a.counter = ctr; a.missing = missing;
-    unsigned long long host_ctr[2] = {0, 0};
+    // variant: stream the whole corpus once (position-major) when the first phrases cover a good part of it, else walk
+    // the occurrence lists (phrase-major).  CGX_JOIN_MODE=phrase|position forces one (tests exercise both).
+    bool position_major = (size_t)n_elems * 4 >= ix.n;
+    if (const char *e = getenv("CGX_JOIN_MODE")) { if (!strcmp(e, "phrase")) position_major = false; else if (!strcmp(e, "position")) position_major = true; }
+    JPArgs ap;
+    ap.jwin = ix.jwin.ptr<int4>(); ap.n = (uint32_t)ix.n;
+    for (int k = 0; k < 3; k++) { ap.bma[k] = bm + (size_t)(4 + k) * bm_words; ap.aid[k] = aid + (size_t)k * ix.n; ap.bm[k] = bm + (size_t)k * bm_words; }
+    ap.bm_marker = bm + 3 * bm_words; ap.slots = slots; ap.mask = slots_n - 1; ap.pshift = b.pbits + 4; ap.counter = ctr; ap.missing = missing;
+    unsigned long long host_ctr[3] = {0, 0, 0};
     while (true) {
-        a.hits = b.hit_keys.get<uint64_t>(b.hit_cap);
-        a.cap = b.hit_cap;
-        CUDA_CHECK(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long) * 2, stream));
+        a.hits = ap.hits = b.hit_keys.get<uint64_t>(b.hit_cap);
+        a.cap = ap.cap = b.hit_cap;
+        CUDA_CHECK(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long) * 3, stream));
         CUDA_CHECK(cudaMemsetAsync(missing, 0, sizeof(int32_t) * (size_t)D1, stream));
-        if (n_elems) PROF("join_onegap", 0.0, (j1_scan_kernel<<<cgx_div_up(n_elems, J1_BLOCK), J1_BLOCK, 0, stream>>>(a)));
+        if (n_elems && position_major) PROF("join_onegap", 0.0, (j1_pos_kernel<<<cgx_div_up(ix.n, JP_TILE), JP_TILE, 0, stream>>>(ap)));
+        else if (n_elems) PROF("join_onegap", 0.0, (j1_scan_kernel<<<cgx_div_up(n_elems, J1_BLOCK), J1_BLOCK, 0, stream>>>(a)));
         b.launches += 1;
-        read_u64s(host_ctr, ctr, 2, stream);
+        read_u64s(host_ctr, ctr, 3, stream);
         if (host_ctr[0] <= b.hit_cap) { b.hits1 = (int64_t)host_ctr[0]; break; }
         b.hit_cap = (size_t)host_ctr[0] + (size_t)host_ctr[0] / 8 + 1024;        // grow once to the exact need and redo the scan
     }
-    // algorithmic bytes: per element its position + gap word, every bucket word read, every hit written
-    prof_add_bytes("join_onegap", 8.0 * (double)n_elems + 4.0 * (double)host_ctr[1] + 8.0 * (double)host_ctr[0]);
+    // algorithmic bytes.  phrase-major: per element its position + gap word, every bucket word read, every hit
+    // written; position-major: the window array streamed once, the phrase id per element, one 16-byte slot per table lookup, hits
+    if (position_major) prof_add_bytes("join_onegap", 16.0 * (double)ix.n + 4.0 * (double)host_ctr[2] + 16.0 * (double)host_ctr[1] + 8.0 * (double)host_ctr[0]);
+    else prof_add_bytes("join_onegap", 8.0 * (double)n_elems + 4.0 * (double)host_ctr[1] + 8.0 * (double)host_ctr[0]);
     b.j1_elems = (int64_t)n_elems;
     j1_missing_kernel<<<cgx_div_up(D1, 256), 256, 0, stream>>>(b.pat1.ptr<Pat1>(), missing, D1);
     b.launches++;
@@ -273,7 +413,9 @@ void stage_onegap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     uint64_t *hits = b.hit_keys.ptr<uint64_t>();
     uint64_t *tmp = b.hit_keys_tmp.get<uint64_t>(H);
     uint64_t *hs;
-    radix_sort<uint64_t>(hits, tmp, nullptr, nullptr, H, 0, b.pbits + 4 + cgx_bits_for((uint64_t)D1), stream, b.radix, &hs, nullptr, &b.launches);
+    // The sort is stable and hits of one (pattern, position) leave the scan in ascending length (one stage_push, lane = gap
+    // width), so sorting on (pattern, position) alone yields (pattern, position, length) order: the 4 length bits are skipped.
+    radix_sort<uint64_t>(hits, tmp, nullptr, nullptr, H, 4, b.pbits + 4 + cgx_bits_for((uint64_t)D1), stream, b.radix, &hs, nullptr, &b.launches);
     uint64_t *dst = b.hits1_sorted.get<uint64_t>(H);
     CUDA_CHECK(cudaMemcpyAsync(dst, hs, sizeof(uint64_t) * H, cudaMemcpyDeviceToDevice, stream));
     static_assert(sizeof(Pat1) == 32, "Pat1 layout");
@@ -317,23 +459,28 @@ __global__ void __launch_bounds__(256) j2_scan_kernel(const uint64_t *__restrict
             active = 1;
         }
     }
-    while (__any_sync(0xffffffffu, bits != 0)) {                       // every round each lane tries its next admissible width
-        bool found = false;
-        uint64_t key = 0;
-        if (bits) {
-            const int g2 = __ffs(bits);
-            bits &= bits - 1;
-            const int r = p + L + 1 + g2;
-            const uint32_t c = (uint32_t)__ldg(&str[r]);
-            probes++;
-            uint64_t d2;
-            if (ht_find(slots, mask, ((uint64_t)d1 << 32) | (uint64_t)c, &d2)) {
-                found = true;
-                key = (d2 << (pbits + 8)) | ((uint64_t)(uint32_t)p << 8) | ((uint64_t)L << 4) | (uint64_t)(r - p);
-            }
+    while (__any_sync(0xffffffffu, bits != 0)) {       // every round each lane tries its next (up to) four admissible widths:
+        int rr[4];                                     // tokens, then first table probes, issued together
+        uint32_t cc[4], ss[4];
+        ulonglong2 sv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            rr[u] = 0;
+            if (bits) { rr[u] = p + L + 1 + __ffs(bits); bits &= bits - 1; probes++; }
         }
-        stage_push(found, key, stage, staged);
-        if (staged > ST_CAP - 32) stage_flush(stage, staged, &counter[0], hits, cap);
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (rr[u]) cc[u] = (uint32_t)__ldg(&str[rr[u]]);
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (rr[u]) sv[u] = ht_first(slots, mask, ((uint64_t)d1 << 32) | (uint64_t)cc[u], &ss[u]);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (!__any_sync(0xffffffffu, rr[u] != 0)) continue;
+            uint64_t d2 = 0;
+            const bool found = rr[u] && ht_resolve(slots, mask, ((uint64_t)d1 << 32) | (uint64_t)cc[u], ss[u], sv[u], &d2);
+            const uint64_t key = (d2 << (pbits + 8)) | ((uint64_t)(uint32_t)p << 8) | ((uint64_t)L << 4) | (uint64_t)(rr[u] - p);
+            stage_push(found, key, stage, staged);
+        }
+        if (staged > ST_CAP - 128) stage_flush(stage, staged, &counter[0], hits, cap);
     }
     stage_flush(stage, staged, &counter[0], hits, cap);
     for (int o = 16; o; o >>= 1) { active += __shfl_xor_sync(0xffffffffu, active, o); probes += __shfl_xor_sync(0xffffffffu, probes, o); }

@@ -304,3 +304,27 @@ def test_radix_sort_matches_stable_reference(n, bits, with_vals):
             assert np.array_equal(vals.cpu().numpy().astype(np.int64), perm)
     finally:
         L.cgx_destroy(h)
+
+
+@pytest.mark.parametrize("mode", ["phrase", "position"])
+def test_join_variants_agree_with_oracle(mode, micro, micro_oracle, monkeypatch):
+    """Both one-gap join variants (walk of the first phrases' occurrence lists / one streamed pass over the corpus) must give
+    the oracle's hit list, two-gap hits and missing counts bit for bit."""
+    from cgx_b200.extractor import GrammarExtractor
+    monkeypatch.setenv("CGX_JOIN_MODE", mode)
+    _, lay = micro
+    ex = GrammarExtractor(0)
+    try:
+        ex.build_index(lay)
+        res = ex.extract(lay["qry_tok"], lay["qry_off"])
+        o = micro_oracle
+        assert np.array_equal(ex.debug_fetch("hits1", int(res.info["hits1"]) * 3, 3), expand_marker_hits(o))
+        assert np.array_equal(ex.debug_fetch("hits2", int(res.info["hits2"]) * 4, 4), o.twogap_hits())
+        miss = o.feature_missing()
+        for d in range(res.D1):
+            if res.pat1[d, 6] >= 0 and res.pat1[d, 5] > 0:
+                assert int(res.pat1[d, 7]) == int(miss[res.pat1[d, 6]])
+        for k in range(3):
+            assert len(res.rules[k]) == len(o.rules(k))
+    finally:
+        ex.close()
