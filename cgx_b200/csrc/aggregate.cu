@@ -62,9 +62,9 @@ struct AggLayout {
 };
 
 // hash[i] = 0 for an empty cell, else the (odd) hash of the record's target symbol sequence; tag[i] = its low word (the
-// 4-byte filter the grouping loop scans); id_count[id] = records of the id (-> f)
+// 4-byte filter the grouping loop scans)
 __global__ void agg_hash_kernel(const RuleRec *__restrict__ rec, uint32_t cells, const int32_t *__restrict__ tgt, uint64_t seed, uint64_t *__restrict__ hash,
-                                uint32_t *__restrict__ tag, uint32_t *__restrict__ id_count, unsigned long long *__restrict__ n_records) {
+                                uint32_t *__restrict__ tag, unsigned long long *__restrict__ n_records) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool live = false;
     if (i < cells) {
@@ -89,7 +89,6 @@ __global__ void agg_hash_kernel(const RuleRec *__restrict__ rec, uint32_t cells,
                 ns++;
             }
             h = (mix64(hh ^ seed ^ (uint64_t)ns)) | 1ull;
-            atomicAdd(&id_count[r.id], 1u);
         }
         hash[i] = h;
         tag[i] = (uint32_t)h;
@@ -99,7 +98,8 @@ __global__ void agg_hash_kernel(const RuleRec *__restrict__ rec, uint32_t cells,
 }
 
 // One thread per cell: group the records of its segment (= the cells of its source id) by target sequence.
-//   flags[i] = 1 when cell i is the first cell of its rule; meta[i] = {representative cell, paircount} for heads.
+//   flags[i] = 1 when cell i is the first cell of its rule; meta[i] = {representative cell, paircount | f << 16} for heads
+//   (f = records of the id = non-empty cells of the segment).
 // A record that finds an equal cell before itself is not a head and stops there; heads scan the rest of the segment
 // for their paircount.  The loops read the 4-byte tags (the segment is shared by the neighbouring threads: L1 broadcast).
 __global__ void __launch_bounds__(256) agg_group_kernel(AggLayout lay, const RuleRec *__restrict__ rec, const uint64_t *__restrict__ hash,
@@ -116,23 +116,28 @@ __global__ void __launch_bounds__(256) agg_group_kernel(AggLayout lay, const Rul
     for (int k = 1; k < 4; k++) if (k < lay.n_regions && i >= lay.r[k].base) reg = k;
     const uint32_t pat = (uint32_t)(r.id - lay.r[reg].id_base);
     const uint32_t s0 = lay.r[reg].base + __ldg(&lay.r[reg].slot_off[pat]), s1 = lay.r[reg].base + __ldg(&lay.r[reg].slot_off[pat + 1]);
-    uint32_t first = i;
+    uint32_t first = i, f = 1;
 #pragma unroll 4
-    for (uint32_t j = s0; j < i; j++)
-        if (__ldg(&tag[j]) == t && __ldg(&hash[j]) == h) { first = j; break; }
+    for (uint32_t j = s0; j < i; j++) {
+        const uint32_t tj = __ldg(&tag[j]);
+        if (tj == t && __ldg(&hash[j]) == h) { first = j; break; }
+        f += tj != 0;
+    }
     if (first == i) {
         uint32_t best = i, cnt = 1;
         int best_ts = r.tgt_start;
 #pragma unroll 4
         for (uint32_t j = i + 1; j < s1; j++) {
-            if (__ldg(&tag[j]) == t && __ldg(&hash[j]) == h) {
+            const uint32_t tj = __ldg(&tag[j]);
+            f += tj != 0;
+            if (tj == t && __ldg(&hash[j]) == h) {
                 cnt++;
                 const int tsj = __ldg(&rec[j].tgt_start);
                 if (tsj < best_ts) { best = j; best_ts = tsj; }
             }
         }
         flags[i] = 1;
-        meta[i] = make_uint2(best, cnt);
+        meta[i] = make_uint2(best, cnt | (f << 16));
     } else {
         flags[i] = 0;
         const RuleRec q = rec[first];
@@ -190,21 +195,22 @@ __global__ void agg_head_cell_kernel(const uint32_t *__restrict__ excl, uint32_t
     if (nxt != e) head_cell[e] = i;
 }
 
-// One thread per distinct rule: paircount, f, fs, representative record, lexical weights.
+// One thread per distinct rule: paircount, f, fs, representative record, lexical weights.  (One thread per CELL with the
+// heads writing their rule keeps the reads streaming but leaves 73 % of the lanes idle in the probe-heavy part: 2x slower.)
 __global__ void __launch_bounds__(128) agg_rules_kernel(AggIdx a, int kind, const RuleRec *__restrict__ rec, const uint32_t *__restrict__ head_cell,
-                                                        const uint2 *__restrict__ meta, uint32_t n_rules, const uint32_t *__restrict__ id_count,
+                                                        const uint2 *__restrict__ meta, uint32_t n_rules,
                                                         const ulonglong2 *__restrict__ lex, uint32_t lex_mask, cgx_rule_t *__restrict__ rules) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rules) return;
     const uint2 mt = meta[head_cell[r]];
     const RuleRec best = rec[mt.x];
-    const int pc = (int)mt.y;
+    const int pc = (int)(mt.y & 0xffffu);
     cgx_rule_t out;
     out.id = best.id; out.tgt_start = best.tgt_start; out.end = best.end;
     out.gap1 = best.gap1; out.gap1_1 = best.gap1_1; out.gap2 = best.gap2; out.gap2_1 = best.gap2_1;
     out.pad[0] = out.pad[1] = out.pad[2] = 0;
     out.pc = pc;
-    out.f = (int)id_count[best.id];
+    out.f = (int)(mt.y >> 16);
     int fs = fsample_of(a, kind, best.id);
     out.fs = fs > CGX_SAMPLER ? CGX_SAMPLER : fs;                          // ExtractPair.c:638,910,1249
     // ---- lexicalTaskMaxEF (ExtractPair.cu:2144-2432): for every source terminal the best MaxLexFgivenE over the target
@@ -285,15 +291,13 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
         uint32_t *flags = b.rec_flags.get<uint32_t>((size_t)N + 2);
         uint2 *meta = b.rec_meta.get<uint2>((size_t)N);
         uint32_t *tag = b.rec_tag.get<uint32_t>((size_t)N);
-        uint32_t *id_count = b.id_count[kind].get<uint32_t>((size_t)nids[kind]);
         int32_t *updown = b.updown[kind].get<int32_t>((size_t)2 * nids[kind]);
         uint64_t seed = 0x243f6a8885a308d3ULL;
         uint32_t R = 0;
         for (int attempt = 0; attempt < 8; attempt++, seed = seed * 6364136223846793005ULL + 1442695040888963407ULL) {
             CUDA_CHECK(cudaMemsetAsync(collision, 0, sizeof(int), stream));
             CUDA_CHECK(cudaMemsetAsync(n_records, 0, sizeof(unsigned long long), stream));
-            CUDA_CHECK(cudaMemsetAsync(id_count, 0, sizeof(uint32_t) * (size_t)nids[kind], stream));
-            PROF("agg_hash", (double)N * 28, (agg_hash_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(rec, N, ix.tgt.ptr<int32_t>(), seed, hash, tag, id_count, n_records)));
+            PROF("agg_hash", (double)N * 28, (agg_hash_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(rec, N, ix.tgt.ptr<int32_t>(), seed, hash, tag, n_records)));
             PROF("agg_group", (double)N * (8 + 4), (agg_group_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(lay[kind], rec, hash, tag, ix.tgt.ptr<int32_t>(), flags, meta, collision)));
             exclusive_scan_u32(flags, flags, N, tot, stream, b.scan, 0, &b.launches);
             b.launches += 2;
@@ -313,7 +317,7 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
                 cgx_rule_t *rules = b.rules[kind].get<cgx_rule_t>(R);
                 uint32_t *head_cell = b.rule_head.get<uint32_t>((size_t)R + 2);
                 agg_head_cell_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(flags, N, R, head_cell);
-                PROF("agg_rules", (double)R * (4 + 8 + 16 + 36) + (double)R * 13 * 16, (agg_rules_kernel<<<cgx_div_up(R, 128), 128, 0, stream>>>(a, kind, rec, head_cell, meta, R, id_count,
+                PROF("agg_rules", (double)R * (4 + 8 + 16 + 36) + (double)R * 13 * 16, (agg_rules_kernel<<<cgx_div_up(R, 128), 128, 0, stream>>>(a, kind, rec, head_cell, meta, R,
                                                                        ix.lex_hash.ptr<ulonglong2>(), ix.lex_hash_mask, rules)));
                 CUDA_CHECK(cudaMemsetAsync(updown, 0xff, sizeof(int32_t) * 2 * (size_t)nids[kind], stream));
                 agg_updown_kernel<<<cgx_div_up(R, 256), 256, 0, stream>>>(rules, R, updown);
