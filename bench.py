@@ -262,7 +262,7 @@ def result_bytes(ex):
     q2 = int(np.ctypeslib.as_array(r.q2_off, shape=(r.Q + 1,))[-1]) if r.Q else 0
     b = 4 * (r.T * 5 + r.G * 4 + r.D1 * 8 + r.D2 * 4 + 2 * (r.Q + 1) + q1 + q2)
     for k in range(3):
-        b += 36 * r.n_rules[k] + 8 * r.n_ids[k]
+        b += 28 * r.n_rules[k] + 8 * r.n_ids[k]
     return int(b)
 
 

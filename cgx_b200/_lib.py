@@ -50,8 +50,8 @@ class BatchInfo(C.Structure):
 
 
 RULE_DTYPE = np.dtype([("id", "<i4"), ("tgt_start", "<i4"), ("end", "u1"), ("gap1", "u1"), ("gap1_1", "u1"), ("gap2", "u1"), ("gap2_1", "u1"),
-                       ("pad", "u1", (3,)), ("f", "<i4"), ("fs", "<i4"), ("pc", "<i4"), ("mlfe", "<f4"), ("mlef", "<f4")])
-assert RULE_DTYPE.itemsize == 36
+                       ("pad", "u1"), ("f", "<u2"), ("fs", "<u2"), ("pc", "<u2"), ("mlfe", "<f4"), ("mlef", "<f4")])
+assert RULE_DTYPE.itemsize == 28
 
 
 class Result(C.Structure):

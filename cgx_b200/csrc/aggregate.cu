@@ -208,11 +208,11 @@ __global__ void __launch_bounds__(128) agg_rules_kernel(AggIdx a, int kind, cons
     cgx_rule_t out;
     out.id = best.id; out.tgt_start = best.tgt_start; out.end = best.end;
     out.gap1 = best.gap1; out.gap1_1 = best.gap1_1; out.gap2 = best.gap2; out.gap2_1 = best.gap2_1;
-    out.pad[0] = out.pad[1] = out.pad[2] = 0;
-    out.pc = pc;
-    out.f = (int)(mt.y >> 16);
+    out.pad = 0;
+    out.pc = (uint16_t)pc;
+    out.f = (uint16_t)(mt.y >> 16);
     int fs = fsample_of(a, kind, best.id);
-    out.fs = fs > CGX_SAMPLER ? CGX_SAMPLER : fs;                          // ExtractPair.c:638,910,1249
+    out.fs = (uint16_t)(fs > CGX_SAMPLER ? CGX_SAMPLER : fs);                          // ExtractPair.c:638,910,1249
     // ---- lexicalTaskMaxEF (ExtractPair.cu:2144-2432): for every source terminal the best MaxLexFgivenE over the target
     // terminals (and NULL), for every target terminal the best MaxLexEgivenF over the source terminals (and NULL).  One
     // table probe serves both directions of a (f, e) pair.
@@ -317,7 +317,7 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
                 cgx_rule_t *rules = b.rules[kind].get<cgx_rule_t>(R);
                 uint32_t *head_cell = b.rule_head.get<uint32_t>((size_t)R + 2);
                 agg_head_cell_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(flags, N, R, head_cell);
-                PROF("agg_rules", (double)R * (4 + 8 + 16 + 36) + (double)R * 13 * 16, (agg_rules_kernel<<<cgx_div_up(R, 128), 128, 0, stream>>>(a, kind, rec, head_cell, meta, R,
+                PROF("agg_rules", (double)R * (4 + 8 + 16 + 28) + (double)R * 13 * 16, (agg_rules_kernel<<<cgx_div_up(R, 128), 128, 0, stream>>>(a, kind, rec, head_cell, meta, R,
                                                                        ix.lex_hash.ptr<ulonglong2>(), ix.lex_hash_mask, rules)));
                 CUDA_CHECK(cudaMemsetAsync(updown, 0xff, sizeof(int32_t) * 2 * (size_t)nids[kind], stream));
                 agg_updown_kernel<<<cgx_div_up(R, 256), 256, 0, stream>>>(rules, R, updown);

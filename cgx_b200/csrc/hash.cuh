@@ -57,6 +57,43 @@ __device__ __forceinline__ bool ht_find(const ulonglong2 *__restrict__ slots, ui
         s = (s + 1) & mask;
     }
 }
+// ---- packed 8-byte table: slot = key << vbits | value (key << vbits | value < 2^63, so no slot equals HT_EMPTY), linear
+// probing at load factor <= 0.71.  Used where key and value fit 63 bits (two-gap patterns: parent id, token -> id): half the
+// bytes of the 16-byte form, 44 MB for the 5.5e6 two-gap patterns of a C2 batch -> L2-resident.  (Measured for the one-gap
+// table too: its key needs a second dependent lookup to fit, and the longer latency chain made that kernel 2x slower.)
+struct PackTab {
+    unsigned long long *slots;
+    uint32_t mask;
+    int vbits;
+};
+
+__device__ __forceinline__ void pt_insert(const PackTab t, uint64_t key, uint64_t val) {
+    const unsigned long long w = (key << t.vbits) | val;
+    uint32_t s = ht_mix(key) & t.mask;
+    while (true) {
+        const unsigned long long prev = atomicCAS(&t.slots[s], (unsigned long long)HT_EMPTY, w);
+        if (prev == HT_EMPTY || (prev >> t.vbits) == key) return;
+        s = (s + 1) & t.mask;
+    }
+}
+__device__ __forceinline__ unsigned long long pt_first(const PackTab t, uint64_t key, uint32_t *slot) {
+    *slot = ht_mix(key) & t.mask;
+    return __ldg(&t.slots[*slot]);
+}
+__device__ __forceinline__ bool pt_resolve(const PackTab t, uint64_t key, uint32_t s, unsigned long long w, uint64_t *val) {
+    while (true) {
+        if ((w >> t.vbits) == key) { *val = w & ((1ull << t.vbits) - 1ull); return true; }
+        if (w == HT_EMPTY) return false;
+        s = (s + 1) & t.mask;
+        w = __ldg(&t.slots[s]);
+    }
+}
 #endif
+
+static inline uint32_t pt_slots_for(size_t entries) {       // power of two, load factor <= 0.71
+    uint32_t s = 1024;
+    while ((double)s * 0.71 < (double)entries) s <<= 1;
+    return s;
+}
 
 }  // namespace cgx

@@ -428,17 +428,17 @@ void stage_onegap_join(const Index &ix, Batch &b, cudaStream_t stream) {
 // two-gap: parent hits (p, L) of aXb extended by the single token c
 //   c at p+L+1+g2, g2 >= 1, (L+1)+g2+1 <= 15  ->  g2 <= 13-L                      (GappyLook.cu:595-655)
 // ------------------------------------------------------------------------------------------------
-__global__ void j2_setup_kernel(const Pat2 *__restrict__ pat2, int D2, ulonglong2 *__restrict__ slots, uint32_t mask, uint8_t *__restrict__ has_child) {
+__global__ void j2_setup_kernel(const Pat2 *__restrict__ pat2, int D2, PackTab tab, int cbits, uint8_t *__restrict__ has_child) {
     int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= D2) return;
     const Pat2 p = pat2[d];
-    ht_insert(slots, mask, ((uint64_t)(uint32_t)p.pat1 << 32) | (uint64_t)(uint32_t)p.ctok, (uint32_t)d);
+    pt_insert(tab, ((uint64_t)(uint32_t)p.pat1 << cbits) | (uint64_t)(uint32_t)p.ctok, (uint64_t)d);
     if (!has_child[p.pat1]) has_child[p.pat1] = 1;
 }
 
 __global__ void __launch_bounds__(256) j2_scan_kernel(const uint64_t *__restrict__ hits1, size_t H1, int pbits, const uint8_t *__restrict__ has_child,
                                                       const int32_t *__restrict__ str, const uint32_t *__restrict__ gapw,
-                                                      const ulonglong2 *__restrict__ slots, uint32_t mask,
+                                                      const PackTab tab, int cbits,
                                                       unsigned long long *__restrict__ counter, uint64_t *__restrict__ hits, size_t cap) {
     __shared__ uint64_t s_stage[256 / 32][ST_CAP];
     uint64_t *stage = s_stage[threadIdx.x >> 5];
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(256) j2_scan_kernel(const uint64_t *__restrict
     while (__any_sync(0xffffffffu, bits != 0)) {       // every round each lane tries its next (up to) four admissible widths:
         int rr[4];                                     // tokens, then first table probes, issued together
         uint32_t cc[4], ss[4];
-        ulonglong2 sv[4];
+        unsigned long long sv[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             rr[u] = 0;
@@ -471,12 +471,12 @@ __global__ void __launch_bounds__(256) j2_scan_kernel(const uint64_t *__restrict
 #pragma unroll
         for (int u = 0; u < 4; u++) if (rr[u]) cc[u] = (uint32_t)__ldg(&str[rr[u]]);
 #pragma unroll
-        for (int u = 0; u < 4; u++) if (rr[u]) sv[u] = ht_first(slots, mask, ((uint64_t)d1 << 32) | (uint64_t)cc[u], &ss[u]);
+        for (int u = 0; u < 4; u++) if (rr[u]) sv[u] = pt_first(tab, ((uint64_t)d1 << cbits) | (uint64_t)cc[u], &ss[u]);
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             if (!__any_sync(0xffffffffu, rr[u] != 0)) continue;
             uint64_t d2 = 0;
-            const bool found = rr[u] && ht_resolve(slots, mask, ((uint64_t)d1 << 32) | (uint64_t)cc[u], ss[u], sv[u], &d2);
+            const bool found = rr[u] && pt_resolve(tab, ((uint64_t)d1 << cbits) | (uint64_t)cc[u], ss[u], sv[u], &d2);
             const uint64_t key = (d2 << (pbits + 8)) | ((uint64_t)(uint32_t)p << 8) | ((uint64_t)L << 4) | (uint64_t)(rr[u] - p);
             stage_push(found, key, stage, staged);
         }
@@ -492,14 +492,17 @@ void stage_twogap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     const int D2 = b.D2;
     if (D2 == 0 || b.hits1 == 0) return;
     CGX_REQUIRE(cgx_bits_for((uint64_t)D2) + b.pbits + 8 <= 64, "two-gap join: %d distinct patterns exceed the hit-key field", D2);
-    const uint32_t slots_n = ht_slots_for((size_t)D2);
-    ulonglong2 *slots = b.j_hash.get<ulonglong2>(slots_n);
+    // corpus tokens never exceed maxtok, so (parent id, token) fits dbits1 + cbits
+    const int cbits = cgx_bits_for((uint64_t)ix.maxtok), d2bits = cgx_bits_for((uint64_t)D2);
+    CGX_REQUIRE(cgx_bits_for((uint64_t)b.D1) + cbits + d2bits <= 63, "two-gap join: %d x %d patterns do not fit the packed pattern table; use smaller query batches", b.D1, D2);
+    const uint32_t slots_n = pt_slots_for((size_t)D2);
+    PackTab tab{b.j_hash.get<unsigned long long>(slots_n), slots_n - 1, d2bits};
     uint8_t *has_child = b.j_aflag.get<uint8_t>((size_t)b.D1 + 4);
     uint32_t *tot = b.counters.get<uint32_t>(32);
     unsigned long long *ctr = (unsigned long long *)(tot + 4);
-    CUDA_CHECK(cudaMemsetAsync(slots, 0xff, sizeof(ulonglong2) * (size_t)slots_n, stream));
+    CUDA_CHECK(cudaMemsetAsync(tab.slots, 0xff, sizeof(unsigned long long) * (size_t)slots_n, stream));
     CUDA_CHECK(cudaMemsetAsync(has_child, 0, (size_t)b.D1, stream));
-    PROF("join_setup", (double)D2 * (16 + 16), (j2_setup_kernel<<<cgx_div_up(D2, 256), 256, 0, stream>>>(b.pat2.ptr<Pat2>(), D2, slots, slots_n - 1, has_child)));
+    PROF("join_setup", (double)D2 * (16 + 8), (j2_setup_kernel<<<cgx_div_up(D2, 256), 256, 0, stream>>>(b.pat2.ptr<Pat2>(), D2, tab, cbits, has_child)));
     b.launches++;
     const size_t H1 = (size_t)b.hits1;
     unsigned long long host_ctr[3] = {0, 0, 0};
@@ -507,7 +510,7 @@ void stage_twogap_join(const Index &ix, Batch &b, cudaStream_t stream) {
         uint64_t *hits = b.hit_keys.get<uint64_t>(b.hit_cap);
         CUDA_CHECK(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long) * 3, stream));
         PROF("join_twogap", 0.0, (j2_scan_kernel<<<cgx_div_up(H1, 256), 256, 0, stream>>>(b.hits1_sorted.ptr<uint64_t>(), H1, b.pbits, has_child, ix.str.ptr<int32_t>(),
-                                                           ix.gapw.ptr<uint32_t>(), slots, slots_n - 1, ctr, hits, b.hit_cap)));
+                                                           ix.gapw.ptr<uint32_t>(), tab, cbits, ctr, hits, b.hit_cap)));
         b.launches += 1;
         read_u64s(host_ctr, ctr, 3, stream);
         if (host_ctr[0] <= b.hit_cap) { b.hits2 = (int64_t)host_ctr[0]; break; }

@@ -119,17 +119,18 @@ typedef struct {
 int cgx_batch_info(const cgx_ctx_t *ctx, cgx_batch_info_t *out);
 
 /* A distinct scored rule (red_dup_t, ComTypes.h:244-255).  `id` is the converted id of
- * ExtractPair.c:723-729 / :999-1006 within its array (kind). */
+ * ExtractPair.c:723-729 / :999-1006 within its array (kind).  28 bytes: a C2 batch returns 7e7 of them, and the
+ * device-to-host copy of the rules is the tail of every batch; the three counts are bounded by the sample size (300). */
 typedef struct {
     int32_t id;
     int32_t tgt_start;     /* representative target span: start in the target text ... */
     uint8_t end;           /* ... and inclusive length-1 */
     uint8_t gap1, gap1_1;  /* target gap 1 as offsets from tgt_start (255 = none) */
     uint8_t gap2, gap2_1;
-    uint8_t pad[3];
-    int32_t f;             /* extracted pairs with this source id   -> IsSingletonF  */
-    int32_t fs;            /* all_suffix_fsample (capped at 300)     -> SampleCountF  */
-    int32_t pc;            /* paircount                              -> CountEF, EgivenFCoherent, IsSingletonFE */
+    uint8_t pad;
+    uint16_t f;            /* extracted pairs with this source id   -> IsSingletonF  */
+    uint16_t fs;           /* all_suffix_fsample (capped at 300)     -> SampleCountF  */
+    uint16_t pc;           /* paircount                              -> CountEF, EgivenFCoherent, IsSingletonFE */
     float max_lex_f_given_e, max_lex_e_given_f;
 } cgx_rule_t;
 
