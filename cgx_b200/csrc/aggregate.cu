@@ -62,16 +62,15 @@ struct AggLayout {
 };
 
 // hash[i] = 0 for an empty cell, else the (odd) hash of the record's target symbol sequence; tag[i] = its low word (the
-// 4-byte filter the grouping loop scans)
+// 4-byte filter the grouping loop scans); live[i] = 1 for a record (its exclusive scan gives the records per segment = f)
 __global__ void agg_hash_kernel(const RuleRec *__restrict__ rec, uint32_t cells, const int32_t *__restrict__ tgt, uint64_t seed, uint64_t *__restrict__ hash,
-                                uint32_t *__restrict__ tag, unsigned long long *__restrict__ n_records) {
+                                uint32_t *__restrict__ tag, uint32_t *__restrict__ live) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool live = false;
     if (i < cells) {
         const RuleRec r = rec[i];
         uint64_t h = 0;
-        if (r.id >= 0) {
-            live = true;
+        const bool is_live = r.id >= 0;
+        if (is_live) {
             uint32_t tok[15];                                     // the span is <= 15 tokens: issue every load before using any
 #pragma unroll
             for (int j = 0; j < 15; j++) tok[j] = j <= (int)r.end ? (uint32_t)__ldg(&tgt[r.tgt_start + j]) : 0u;
@@ -92,9 +91,8 @@ __global__ void agg_hash_kernel(const RuleRec *__restrict__ rec, uint32_t cells,
         }
         hash[i] = h;
         tag[i] = (uint32_t)h;
+        live[i] = is_live ? 1u : 0u;
     }
-    const unsigned m = __ballot_sync(0xffffffffu, live);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_records, (unsigned long long)__popc(m));
 }
 
 // One thread per cell: group the records of its segment (= the cells of its source id) by target sequence.
@@ -103,8 +101,9 @@ __global__ void agg_hash_kernel(const RuleRec *__restrict__ rec, uint32_t cells,
 // A record that finds an equal cell before itself is not a head and stops there; heads scan the rest of the segment
 // for their paircount.  The loops read the 4-byte tags (the segment is shared by the neighbouring threads: L1 broadcast).
 __global__ void __launch_bounds__(256) agg_group_kernel(AggLayout lay, const RuleRec *__restrict__ rec, const uint64_t *__restrict__ hash,
-                                                        const uint32_t *__restrict__ tag, const int32_t *__restrict__ tgt, uint32_t *__restrict__ flags,
-                                                        uint2 *__restrict__ meta, int *__restrict__ collision) {
+                                                        const uint32_t *__restrict__ tag, const uint32_t *__restrict__ live_before,
+                                                        const int32_t *__restrict__ tgt, uint32_t *__restrict__ flags, uint2 *__restrict__ meta,
+                                                        int *__restrict__ collision) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= lay.cells) return;
     const uint64_t h = hash[i];
@@ -116,26 +115,34 @@ __global__ void __launch_bounds__(256) agg_group_kernel(AggLayout lay, const Rul
     for (int k = 1; k < 4; k++) if (k < lay.n_regions && i >= lay.r[k].base) reg = k;
     const uint32_t pat = (uint32_t)(r.id - lay.r[reg].id_base);
     const uint32_t s0 = lay.r[reg].base + __ldg(&lay.r[reg].slot_off[pat]), s1 = lay.r[reg].base + __ldg(&lay.r[reg].slot_off[pat + 1]);
-    uint32_t first = i, f = 1;
-#pragma unroll 4
-    for (uint32_t j = s0; j < i; j++) {
-        const uint32_t tj = __ldg(&tag[j]);
-        if (tj == t && __ldg(&hash[j]) == h) { first = j; break; }
-        f += tj != 0;
+    // the tags are scanned four at a time (aligned 16-byte loads; cells outside [lo, hi) are masked by position)
+    uint32_t first = i;
+    for (uint32_t base = s0 & ~3u; base < i && first == i; base += 4) {
+        const uint4 t4 = __ldg(reinterpret_cast<const uint4 *>(tag + base));
+        const uint32_t tt[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t j = base + k;
+            if (tt[k] == t && j >= s0 && j < i && first == i && __ldg(&hash[j]) == h) first = j;
+        }
     }
     if (first == i) {
         uint32_t best = i, cnt = 1;
         int best_ts = r.tgt_start;
-#pragma unroll 4
-        for (uint32_t j = i + 1; j < s1; j++) {
-            const uint32_t tj = __ldg(&tag[j]);
-            f += tj != 0;
-            if (tj == t && __ldg(&hash[j]) == h) {
-                cnt++;
-                const int tsj = __ldg(&rec[j].tgt_start);
-                if (tsj < best_ts) { best = j; best_ts = tsj; }
+        for (uint32_t base = (i + 1) & ~3u; base < s1; base += 4) {
+            const uint4 t4 = __ldg(reinterpret_cast<const uint4 *>(tag + base));
+            const uint32_t tt[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t j = base + k;
+                if (tt[k] == t && j > i && j < s1 && __ldg(&hash[j]) == h) {
+                    cnt++;
+                    const int tsj = __ldg(&rec[j].tgt_start);
+                    if (tsj < best_ts) { best = j; best_ts = tsj; }
+                }
             }
         }
+        const uint32_t f = __ldg(&live_before[s1]) - __ldg(&live_before[s0]);      // records of the id = non-empty cells of the segment
         flags[i] = 1;
         meta[i] = make_uint2(best, cnt | (f << 16));
     } else {
@@ -274,7 +281,6 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
     lay[2].n_regions = 4; lay[2].r[0] = {0u, 0, so0}; lay[2].r[1] = {ns0, G, so2}; lay[2].r[2] = {ns0 + ns2, G + D2, so1}; lay[2].r[3] = {ns0 + ns2 + ns1, G + D2 + D1, so1};
     uint32_t *tot = b.counters.get<uint32_t>(32);
     int *collision = (int *)(tot + 14);
-    unsigned long long *n_records = (unsigned long long *)(tot + 16);
     for (int kk = 0; kk < 3; kk++) {
         const int kind = 2 - kk;                           // largest result first: its D2H overlaps the other kinds' kernels
         const uint32_t N = (uint32_t)b.rec_cells[kind];
@@ -290,15 +296,17 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
         uint64_t *hash = b.rec_hash.get<uint64_t>((size_t)N);
         uint32_t *flags = b.rec_flags.get<uint32_t>((size_t)N + 2);
         uint2 *meta = b.rec_meta.get<uint2>((size_t)N);
-        uint32_t *tag = b.rec_tag.get<uint32_t>((size_t)N);
+        uint32_t *tag = b.rec_tag.get<uint32_t>((size_t)N + 8);
+        uint32_t *live = b.rec_live.get<uint32_t>((size_t)N + 2);
         int32_t *updown = b.updown[kind].get<int32_t>((size_t)2 * nids[kind]);
         uint64_t seed = 0x243f6a8885a308d3ULL;
         uint32_t R = 0;
         for (int attempt = 0; attempt < 8; attempt++, seed = seed * 6364136223846793005ULL + 1442695040888963407ULL) {
             CUDA_CHECK(cudaMemsetAsync(collision, 0, sizeof(int), stream));
-            CUDA_CHECK(cudaMemsetAsync(n_records, 0, sizeof(unsigned long long), stream));
-            PROF("agg_hash", (double)N * 28, (agg_hash_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(rec, N, ix.tgt.ptr<int32_t>(), seed, hash, tag, n_records)));
-            PROF("agg_group", (double)N * (8 + 4), (agg_group_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(lay[kind], rec, hash, tag, ix.tgt.ptr<int32_t>(), flags, meta, collision)));
+            PROF("agg_hash", (double)N * 32, (agg_hash_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(rec, N, ix.tgt.ptr<int32_t>(), seed, hash, tag, live)));
+            exclusive_scan_u32(live, live, N, tot + 16, stream, b.scan, 0, &b.launches);          // live[N] = total below
+            CUDA_CHECK(cudaMemcpyAsync(live + N, tot + 16, sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
+            PROF("agg_group", (double)N * (8 + 4), (agg_group_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(lay[kind], rec, hash, tag, live, ix.tgt.ptr<int32_t>(), flags, meta, collision)));
             exclusive_scan_u32(flags, flags, N, tot, stream, b.scan, 0, &b.launches);
             b.launches += 2;
             uint32_t hostv[20];
@@ -306,8 +314,7 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
             CUDA_CHECK(cudaStreamSynchronize(stream));
             if (hostv[14] == 0) {
                 R = hostv[0];
-                unsigned long long nr;
-                memcpy(&nr, &hostv[16], sizeof(nr));
+                const unsigned long long nr = hostv[16];
                 b.n_rec[kind] = (int64_t)nr;
                 if (g_prof && g_prof->enabled) {          // records actually grouped: 16 B record + 8 B meta per head, 20 B per record compared
                     g_prof->table["agg_group"].bytes += (double)nr * 16 + (double)R * 8;
