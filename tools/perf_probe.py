@@ -9,13 +9,20 @@ from cgx_b200.extractor import GrammarExtractor
 ns, nq = int(sys.argv[1]), int(sys.argv[2])
 v = int(sys.argv[3]) if len(sys.argv) > 3 else 50000
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
+bq = int(sys.argv[5]) if len(sys.argv) > 5 else nq          # queries per cgx_extract batch
 t0 = time.time(); c = synth.generate(ns, nq, v_src=v, v_tgt=v); t1 = time.time(); lay = synth.text_layout(c); t2 = time.time()
 print("gen %.1fs layout %.1fs n=%d m=%d T=%d lex=%d" % (t1 - t0, t2 - t1, lay["n"], lay["m"], len(lay["qry_tok"]), len(lay["lex_f"])), flush=True)
 ex = GrammarExtractor(0)
 t0 = time.time(); info = ex.build_index(lay); print("index build wall %.2fs" % (time.time() - t0), info, flush=True)
 ex.profile(True)
+qo = np.asarray(lay["qry_off"]); qt = np.asarray(lay["qry_tok"]); Q = len(qo) - 1
 for r in range(reps):
-    t0 = time.time(); res = ex.extract(lay["qry_tok"], lay["qry_off"], fetch=False); dt = time.time() - t0
+    t0 = time.time()
+    for q0 in range(0, Q, bq):
+        q1 = min(Q, q0 + bq)
+        res = ex.extract(qt[qo[q0]:qo[q1]], qo[q0:q1 + 1] - qo[q0], fetch=False)
+        if bq < Q: print("  batch %d..%d" % (q0, q1), json.dumps(res), flush=True)
+    dt = time.time() - t0
     print("rep %d wall %.3fs -> %.0f q/s" % (r, dt, nq / dt), json.dumps(res), flush=True)
 rep = ex.profile_report()
 tot = sum(v["ms"] for v in rep.values())
