@@ -91,6 +91,8 @@ def load():
     L.cgx_index_copy_inv.argtypes = [vp, C.c_int, i32p]
     L.cgx_index_copy_frequent.argtypes = [vp, i32p]
     L.cgx_extract.argtypes = [vp, i32p, i32p, C.c_int32]
+    L.cgx_extract_begin.argtypes = [vp, i32p, i32p, C.c_int32]
+    L.cgx_result_at.argtypes = [vp, C.c_int, C.POINTER(Result)]
     L.cgx_extract_dev.argtypes = [vp, vp, vp, vp, C.c_int32, C.c_int32]
     L.cgx_profile_enable.argtypes = [vp, C.c_int]
     L.cgx_profile_report.argtypes = [vp]
@@ -107,5 +109,5 @@ def load():
 
 EXPORTED_SYMBOLS = ("cgx_version", "cgx_create", "cgx_destroy", "cgx_last_error", "cgx_index_build", "cgx_lex_load", "cgx_index_info",
                     "cgx_sa_build_dev", "cgx_index_export", "cgx_index_alloc", "cgx_index_commit", "cgx_index_copy_sa", "cgx_index_copy_inv",
-                    "cgx_index_copy_frequent", "cgx_extract", "cgx_extract_dev", "cgx_profile_enable", "cgx_profile_report",
+                    "cgx_index_copy_frequent", "cgx_extract", "cgx_extract_begin", "cgx_result_at", "cgx_extract_dev", "cgx_profile_enable", "cgx_profile_report",
                     "cgx_index_broadcast", "cgx_batch_info", "cgx_result", "cgx_debug_fetch", "cgx_debug_sort_u64")

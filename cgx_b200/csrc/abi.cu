@@ -40,6 +40,8 @@ extern "C" int cgx_create(int device, cgx_ctx_t **out) {
         for (auto &ev : c->batch.ev) CUDA_CHECK(cudaEventCreate(&ev));
         CUDA_CHECK(cudaStreamCreateWithFlags(&c->batch.copy_stream, cudaStreamNonBlocking));
         CUDA_CHECK(cudaEventCreateWithFlags(&c->batch.copy_ev, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&c->batch.done_ev, cudaEventDisableTiming));
+        for (auto &r : c->batch.parked) CUDA_CHECK(cudaEventCreateWithFlags(&r.done, cudaEventDisableTiming));
         memset(&c->batch.info, 0, sizeof(c->batch.info));
         *out = c;
         return 0;
@@ -76,6 +78,8 @@ extern "C" void cgx_destroy(cgx_ctx_t *c) {
     c->prof.destroy();
     for (auto &ev : b.ev) if (ev) cudaEventDestroy(ev);
     if (b.copy_ev) cudaEventDestroy(b.copy_ev);
+    if (b.done_ev) cudaEventDestroy(b.done_ev);
+    for (auto &r : b.parked) r.release();
     if (b.copy_stream) cudaStreamDestroy(b.copy_stream);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -281,7 +285,8 @@ extern "C" int cgx_index_copy_frequent(cgx_ctx_t *c, int32_t *out) {
 // ------------------------------------------------------------------------------------------------
 
 // Runs the stages on queries already resident in b.q_tok / b.q_off / b.tok2q.
-static void run_batch(cgx_ctx *c, int32_t Q, int32_t T, bool fetch) {
+// wait_copies = false (cgx_extract_begin): returns when the kernels are done; the tail of the D2H is still travelling.
+static void run_batch(cgx_ctx *c, int32_t Q, int32_t T, bool fetch, bool wait_copies = true) {
     Batch &b = c->batch;
     const Index &ix = c->ix;
     cudaStream_t s = c->stream;
@@ -314,9 +319,10 @@ static void run_batch(cgx_ctx *c, int32_t Q, int32_t T, bool fetch) {
     CUDA_CHECK(cudaEventRecord(b.ev[6], s));
     stage_aggregate(ix, b, s);
     if (fetch) {   // the batch ends when the last result byte is on the host
-        CUDA_CHECK(cudaEventRecord(b.copy_ev, b.copy_stream));
-        CUDA_CHECK(cudaStreamWaitEvent(s, b.copy_ev, 0));
+        CUDA_CHECK(cudaEventRecord(b.done_ev, b.copy_stream));
+        if (wait_copies) CUDA_CHECK(cudaStreamWaitEvent(s, b.done_ev, 0));
     }
+    b.valid = true;
     CUDA_CHECK(cudaEventRecord(b.ev[7], s));
     CUDA_CHECK(cudaStreamSynchronize(s));
     c->prof.resolve();
@@ -339,41 +345,49 @@ static void run_batch(cgx_ctx *c, int32_t Q, int32_t T, bool fetch) {
     CUDA_CHECK(cudaEventElapsedTime(&in.ms_aggregate, b.ev[6], b.ev[7]));
 }
 
+static void extract_host(cgx_ctx *c, const int32_t *qry_tok, const int32_t *qry_off, int32_t Q, bool pipelined) {
+    CGX_REQUIRE(c && qry_off && Q >= 0, "bad argument");
+    CGX_REQUIRE(c->ix.built, "index not built");
+    CUDA_CHECK(cudaSetDevice(c->device));
+    Batch &b = c->batch;
+    cudaStream_t s = c->stream;
+    const int32_t T = qry_off[Q];
+    CGX_REQUIRE(T == 0 || qry_tok, "null query tokens");
+    if (pipelined) rotate_results(b);
+    b.valid = false;
+    b.Q = Q; b.T = T; b.launches = 0;
+    memset(&b.info, 0, sizeof(b.info));
+    // stage the inputs through pinned memory: [tok T][off Q+1][tok2q T]
+    size_t need = (size_t)T * 2 + (size_t)Q + 1;
+    if (need > b.h_pinned_cap) {
+        if (b.h_pinned) CUDA_CHECK(cudaFreeHost(b.h_pinned));
+        CUDA_CHECK(cudaMallocHost((void **)&b.h_pinned, sizeof(int32_t) * (need + need / 4 + 64)));
+        b.h_pinned_cap = need + need / 4 + 64;
+    }
+    int32_t *hp = b.h_pinned;
+    if (T) memcpy(hp, qry_tok, sizeof(int32_t) * (size_t)T);
+    memcpy(hp + T, qry_off, sizeof(int32_t) * ((size_t)Q + 1));
+    int32_t *t2q = hp + T + Q + 1;
+    for (int32_t q = 0; q < Q; q++) {
+        CGX_REQUIRE(qry_off[q + 1] >= qry_off[q], "query offsets must be non-decreasing");
+        for (int32_t t = qry_off[q]; t < qry_off[q + 1]; t++) t2q[t] = q;
+    }
+    CUDA_CHECK(cudaEventRecord(b.ev[0], s));
+    int32_t *d_tok = b.q_tok.get<int32_t>((size_t)T + 8);
+    int32_t *d_off = b.q_off.get<int32_t>((size_t)Q + 1);
+    int32_t *d_t2q = b.tok2q.get<int32_t>((size_t)T + 1);
+    if (T) CUDA_CHECK(cudaMemcpyAsync(d_tok, hp, sizeof(int32_t) * (size_t)T, cudaMemcpyHostToDevice, s));
+    CUDA_CHECK(cudaMemcpyAsync(d_off, hp + T, sizeof(int32_t) * ((size_t)Q + 1), cudaMemcpyHostToDevice, s));
+    if (T) CUDA_CHECK(cudaMemcpyAsync(d_t2q, t2q, sizeof(int32_t) * (size_t)T, cudaMemcpyHostToDevice, s));
+    run_batch(c, Q, T, true, !pipelined);
+}
+
 extern "C" int cgx_extract(cgx_ctx_t *c, const int32_t *qry_tok, const int32_t *qry_off, int32_t Q) {
-    CGX_TRY(c, {
-        CGX_REQUIRE(c && qry_off && Q >= 0, "bad argument");
-        CGX_REQUIRE(c->ix.built, "index not built");
-        CUDA_CHECK(cudaSetDevice(c->device));
-        Batch &b = c->batch;
-        cudaStream_t s = c->stream;
-        const int32_t T = qry_off[Q];
-        CGX_REQUIRE(T == 0 || qry_tok, "null query tokens");
-        b.Q = Q; b.T = T; b.launches = 0;
-        memset(&b.info, 0, sizeof(b.info));
-        // stage the inputs through pinned memory: [tok T][off Q+1][tok2q T]
-        size_t need = (size_t)T * 2 + (size_t)Q + 1;
-        if (need > b.h_pinned_cap) {
-            if (b.h_pinned) CUDA_CHECK(cudaFreeHost(b.h_pinned));
-            CUDA_CHECK(cudaMallocHost((void **)&b.h_pinned, sizeof(int32_t) * (need + need / 4 + 64)));
-            b.h_pinned_cap = need + need / 4 + 64;
-        }
-        int32_t *hp = b.h_pinned;
-        if (T) memcpy(hp, qry_tok, sizeof(int32_t) * (size_t)T);
-        memcpy(hp + T, qry_off, sizeof(int32_t) * ((size_t)Q + 1));
-        int32_t *t2q = hp + T + Q + 1;
-        for (int32_t q = 0; q < Q; q++) {
-            CGX_REQUIRE(qry_off[q + 1] >= qry_off[q], "query offsets must be non-decreasing");
-            for (int32_t t = qry_off[q]; t < qry_off[q + 1]; t++) t2q[t] = q;
-        }
-        CUDA_CHECK(cudaEventRecord(b.ev[0], s));
-        int32_t *d_tok = b.q_tok.get<int32_t>((size_t)T + 8);
-        int32_t *d_off = b.q_off.get<int32_t>((size_t)Q + 1);
-        int32_t *d_t2q = b.tok2q.get<int32_t>((size_t)T + 1);
-        if (T) CUDA_CHECK(cudaMemcpyAsync(d_tok, hp, sizeof(int32_t) * (size_t)T, cudaMemcpyHostToDevice, s));
-        CUDA_CHECK(cudaMemcpyAsync(d_off, hp + T, sizeof(int32_t) * ((size_t)Q + 1), cudaMemcpyHostToDevice, s));
-        if (T) CUDA_CHECK(cudaMemcpyAsync(d_t2q, t2q, sizeof(int32_t) * (size_t)T, cudaMemcpyHostToDevice, s));
-        run_batch(c, Q, T, true);
-    });
+    CGX_TRY(c, extract_host(c, qry_tok, qry_off, Q, false));
+}
+
+extern "C" int cgx_extract_begin(cgx_ctx_t *c, const int32_t *qry_tok, const int32_t *qry_off, int32_t Q) {
+    CGX_TRY(c, extract_host(c, qry_tok, qry_off, Q, true));
 }
 
 extern "C" int cgx_extract_dev(cgx_ctx_t *c, const int32_t *qry_tok_dev, const int32_t *qry_off_dev, const int32_t *tok2q_dev, int32_t Q, int32_t T) {
@@ -383,6 +397,7 @@ extern "C" int cgx_extract_dev(cgx_ctx_t *c, const int32_t *qry_tok_dev, const i
         CUDA_CHECK(cudaSetDevice(c->device));
         Batch &b = c->batch;
         cudaStream_t s = c->stream;
+        b.valid = false;
         b.Q = Q; b.T = T; b.launches = 0;
         memset(&b.info, 0, sizeof(b.info));
         int32_t *d_tok = b.q_tok.get<int32_t>((size_t)T + 8);
@@ -425,19 +440,38 @@ extern "C" int cgx_batch_info(const cgx_ctx_t *c, cgx_batch_info_t *out) {
     return 0;
 }
 
-extern "C" int cgx_result(cgx_ctx_t *c, cgx_result_t *o) {
-    if (!c || !o) return 1;
-    Batch &b = c->batch;
-    o->Q = b.Q; o->T = b.T; o->G = b.G; o->D1 = b.D1; o->D2 = b.D2;
-    if (!b.fetch_results) { c->err = "the last batch kept its results on the device (cgx_extract_dev)"; return 1; }
-    o->phrase_id = b.h_phrase_id.ptr<int32_t>(); o->phrases = b.h_phrases.ptr<int32_t>(); o->pat1 = b.h_pat1.ptr<int32_t>(); o->pat2 = b.h_pat2.ptr<int32_t>();
-    o->q1_off = b.h_q1_off.ptr<int32_t>(); o->q1_ids = b.h_q1_ids.ptr<int32_t>(); o->q2_off = b.h_q2_off.ptr<int32_t>(); o->q2_ids = b.h_q2_ids.ptr<int32_t>();
-    for (int k = 0; k < 3; k++) {
-        o->rules[k] = b.h_rules[k].ptr<cgx_rule_t>(); o->n_rules[k] = b.n_rules[k];
-        o->updown[k] = b.h_updown[k].ptr<int32_t>(); o->n_ids[k] = b.n_ids[k];
-    }
-    return 0;
+extern "C" int cgx_result_at(cgx_ctx_t *c, int age, cgx_result_t *o) {
+    CGX_TRY(c, {
+        CGX_REQUIRE(c && o && age >= 0 && age < CGX_RESULT_SETS, "bad argument (age must be 0..%d)", CGX_RESULT_SETS - 1);
+        Batch &b = c->batch;
+        CUDA_CHECK(cudaSetDevice(c->device));
+        if (age == 0) {
+            CGX_REQUIRE(b.valid, "no finished batch");
+            CGX_REQUIRE(b.fetch_results, "the last batch kept its results on the device (cgx_extract_dev)");
+            CUDA_CHECK(cudaEventSynchronize(b.done_ev));
+            o->Q = b.Q; o->T = b.T; o->G = b.G; o->D1 = b.D1; o->D2 = b.D2;
+            o->phrase_id = b.h_phrase_id.ptr<int32_t>(); o->phrases = b.h_phrases.ptr<int32_t>(); o->pat1 = b.h_pat1.ptr<int32_t>(); o->pat2 = b.h_pat2.ptr<int32_t>();
+            o->q1_off = b.h_q1_off.ptr<int32_t>(); o->q1_ids = b.h_q1_ids.ptr<int32_t>(); o->q2_off = b.h_q2_off.ptr<int32_t>(); o->q2_ids = b.h_q2_ids.ptr<int32_t>();
+            for (int k = 0; k < 3; k++) {
+                o->rules[k] = b.h_rules[k].ptr<cgx_rule_t>(); o->n_rules[k] = b.n_rules[k];
+                o->updown[k] = b.h_updown[k].ptr<int32_t>(); o->n_ids[k] = b.n_ids[k];
+            }
+        } else {
+            ResultSet &r = b.parked[age - 1];
+            CGX_REQUIRE(r.valid && r.fetched, "no batch of that age (cgx_extract_begin keeps the last %d)", CGX_RESULT_SETS);
+            CUDA_CHECK(cudaEventSynchronize(r.done));
+            o->Q = r.Q; o->T = r.T; o->G = r.G; o->D1 = r.D1; o->D2 = r.D2;
+            o->phrase_id = r.h_phrase_id.ptr<int32_t>(); o->phrases = r.h_phrases.ptr<int32_t>(); o->pat1 = r.h_pat1.ptr<int32_t>(); o->pat2 = r.h_pat2.ptr<int32_t>();
+            o->q1_off = r.h_q1_off.ptr<int32_t>(); o->q1_ids = r.h_q1_ids.ptr<int32_t>(); o->q2_off = r.h_q2_off.ptr<int32_t>(); o->q2_ids = r.h_q2_ids.ptr<int32_t>();
+            for (int k = 0; k < 3; k++) {
+                o->rules[k] = r.h_rules[k].ptr<cgx_rule_t>(); o->n_rules[k] = r.n_rules[k];
+                o->updown[k] = r.h_updown[k].ptr<int32_t>(); o->n_ids[k] = r.n_ids[k];
+            }
+        }
+    });
 }
+
+extern "C" int cgx_result(cgx_ctx_t *c, cgx_result_t *o) { return cgx_result_at(c, 0, o); }
 
 extern "C" int cgx_debug_sort_u64(cgx_ctx_t *c, uint64_t *keys_dev, uint32_t *vals_dev, int64_t n, int begin_bit, int end_bit, float *ms_out, int *passes_out) {
     CGX_TRY(c, {

@@ -289,9 +289,8 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
         b.n_ids[kind] = nids[kind];
         b.n_rules[kind] = 0;
         int32_t *h_ud = b.h_updown[kind].get<int32_t>((size_t)2 * nids[kind] + 2);
-        memset(h_ud, 0xff, sizeof(int32_t) * 2 * (size_t)nids[kind]);
         b.h_rules[kind].get<cgx_rule_t>(1);
-        if (N == 0 || nids[kind] == 0) continue;
+        if (N == 0 || nids[kind] == 0) { memset(h_ud, 0xff, sizeof(int32_t) * 2 * (size_t)nids[kind]); continue; }
         const RuleRec *rec = b.rec[kind].ptr<RuleRec>();
         uint64_t *hash = b.rec_hash.get<uint64_t>((size_t)N);
         uint32_t *flags = b.rec_flags.get<uint32_t>((size_t)N + 2);
@@ -338,6 +337,7 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
             cgx_rule_t *h_r = b.h_rules[kind].get<cgx_rule_t>((size_t)R + 1);
             if (R) fetch_async(b, h_r, b.rules[kind].ptr<cgx_rule_t>(), sizeof(cgx_rule_t) * R, stream);
             if (R) fetch_async(b, h_ud, updown, sizeof(int32_t) * 2 * (size_t)nids[kind], stream);
+            else memset(h_ud, 0xff, sizeof(int32_t) * 2 * (size_t)nids[kind]);      // no rule at all: every range empty
         }
     }
 }

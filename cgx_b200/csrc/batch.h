@@ -2,6 +2,7 @@
 #pragma once
 #include "../../include/cgx_b200.h"
 #include "index.h"
+#include <utility>
 
 namespace cgx {
 
@@ -28,6 +29,30 @@ struct Pat1Dev {                         // device-only companion
 };
 struct Pat2 {
     int32_t pat1, ctok, hit_start, hit_count;
+};
+
+// Everything cgx_result() exposes for one batch -- device arrays, their pinned host mirrors and the counts -- so that
+// a finished batch can be parked while the next one runs: its D2H then overlaps the next batch's kernels and the host
+// may still be writing the batch before it (cgx_extract_begin / cgx_result_at; three sets = one computing, one
+// travelling, one being consumed).
+constexpr int CGX_RESULT_SETS = 3;
+struct ResultSet {
+    DevBuf phrase_id, phrases, pat1, pat2, q1_off, q1_ids, q2_off, q2_ids, rules[3], updown[3];
+    PinnedBuf h_phrase_id, h_phrases, h_pat1, h_pat2, h_q1_off, h_q1_ids, h_q2_off, h_q2_ids, h_rules[3], h_updown[3];
+    int32_t Q = 0, T = 0, G = 0, D1 = 0, D2 = 0;
+    int32_t n_rules[3] = {0, 0, 0}, n_ids[3] = {0, 0, 0};
+    cgx_batch_info_t info;
+    cudaEvent_t done = nullptr;      // recorded on the copy stream behind the batch's last D2H
+    bool fetched = false;            // the batch copied its results to the host mirrors
+    bool valid = false;
+    void release() {
+        DevBuf *d[] = {&phrase_id, &phrases, &pat1, &pat2, &q1_off, &q1_ids, &q2_off, &q2_ids, &rules[0], &rules[1], &rules[2], &updown[0], &updown[1], &updown[2]};
+        for (auto *x : d) x->release();
+        PinnedBuf *h[] = {&h_phrase_id, &h_phrases, &h_pat1, &h_pat2, &h_q1_off, &h_q1_ids, &h_q2_off, &h_q2_ids, &h_rules[0], &h_rules[1], &h_rules[2], &h_updown[0], &h_updown[1], &h_updown[2]};
+        for (auto *x : h) x->release();
+        if (done) cudaEventDestroy(done);
+        done = nullptr;
+    }
 };
 
 struct Batch {
@@ -74,6 +99,10 @@ struct Batch {
     PinnedBuf h_rules[3], h_updown[3];
     bool fetch_results = true;       // false: results stay on the device (device-resident throughput measurement)
     cgx_batch_info_t info;
+    // the two batches before this one (parked[0] = previous); the current batch's arrays are the named members above
+    ResultSet parked[CGX_RESULT_SETS - 1];
+    cudaEvent_t done_ev = nullptr;   // current batch: behind its last D2H on the copy stream
+    bool valid = false;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // results travel to the (pinned) host mirrors on their own stream, overlapping the kernels that follow their producer
     cudaStream_t copy_stream = nullptr;
@@ -87,6 +116,27 @@ static inline void fetch_async(Batch &b, void *dst, const void *src, size_t byte
     CUDA_CHECK(cudaEventRecord(b.copy_ev, stream));
     CUDA_CHECK(cudaStreamWaitEvent(b.copy_stream, b.copy_ev, 0));
     CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, b.copy_stream));
+}
+
+// current result arrays <-> a parked set (pointer swaps only)
+static inline void swap_results(Batch &b, ResultSet &r) {
+    std::swap(b.phrase_id, r.phrase_id); std::swap(b.phrases, r.phrases); std::swap(b.pat1, r.pat1); std::swap(b.pat2, r.pat2);
+    std::swap(b.q1_off, r.q1_off); std::swap(b.q1_ids, r.q1_ids); std::swap(b.q2_off, r.q2_off); std::swap(b.q2_ids, r.q2_ids);
+    std::swap(b.h_phrase_id, r.h_phrase_id); std::swap(b.h_phrases, r.h_phrases); std::swap(b.h_pat1, r.h_pat1); std::swap(b.h_pat2, r.h_pat2);
+    std::swap(b.h_q1_off, r.h_q1_off); std::swap(b.h_q1_ids, r.h_q1_ids); std::swap(b.h_q2_off, r.h_q2_off); std::swap(b.h_q2_ids, r.h_q2_ids);
+    for (int k = 0; k < 3; k++) {
+        std::swap(b.rules[k], r.rules[k]); std::swap(b.updown[k], r.updown[k]); std::swap(b.h_rules[k], r.h_rules[k]); std::swap(b.h_updown[k], r.h_updown[k]);
+        std::swap(b.n_rules[k], r.n_rules[k]); std::swap(b.n_ids[k], r.n_ids[k]);
+    }
+    std::swap(b.Q, r.Q); std::swap(b.T, r.T); std::swap(b.G, r.G); std::swap(b.D1, r.D1); std::swap(b.D2, r.D2);
+    std::swap(b.info, r.info); std::swap(b.done_ev, r.done); std::swap(b.fetch_results, r.fetched); std::swap(b.valid, r.valid);
+}
+// A new batch begins: current -> parked[0] -> parked[1] -> current.  The set that becomes current held the batch three
+// begins ago; its copies have long finished (waited for all the same before its arrays are overwritten).
+static inline void rotate_results(Batch &b) {
+    swap_results(b, b.parked[0]);          // current = old parked[0], parked[0] = the batch that just finished
+    swap_results(b, b.parked[1]);          // current = old parked[1], parked[1] = old parked[0]
+    if (b.done_ev) CUDA_CHECK(cudaEventSynchronize(b.done_ev));
 }
 
 // stages (each enqueues on `stream`; those that need a count on the host synchronise once)

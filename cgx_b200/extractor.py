@@ -253,6 +253,27 @@ class GrammarExtractor:
         self.L.cgx_result(self.h, C.byref(r))
         return BatchResult(r, info, qry_tok, qry_off)
 
+    def extract_begin(self, qry_tok, qry_off):
+        """Pipelined batch (cgx_extract_begin): returns when the kernels are done, the result copy still travelling; it
+        overlaps the next extract_begin.  Collect with result_at(age, ...)."""
+        qt = np.ascontiguousarray(qry_tok, dtype=np.int32)
+        qo = np.ascontiguousarray(qry_off, dtype=np.int32)
+        if len(qt) == 0:
+            qt = np.zeros(1, dtype=np.int32)
+        self._check(self.L.cgx_extract_begin(self.h, _p(qt, C.c_int32), _p(qo, C.c_int32), len(qo) - 1), "cgx_extract_begin")
+        info = BatchInfo()
+        self.L.cgx_batch_info(self.h, C.byref(info))
+        return info
+
+    def result_at(self, age, qry_tok=None, qry_off=None, info=None, raw=False):
+        """Results of the batch `age` begins ago (0 = latest), complete on the host when this returns.  raw=True
+        returns the ctypes views (no copy), else a BatchResult (needs that batch's qry_tok / qry_off)."""
+        r = Result()
+        self._check(self.L.cgx_result_at(self.h, age, C.byref(r)), "cgx_result_at")
+        if raw:
+            return r
+        return BatchResult(r, info if info is not None else BatchInfo(), qry_tok, qry_off)
+
     def extract_dev(self, tok_ptr: int, off_ptr: int, t2q_ptr: int, Q: int, T: int):
         """Queries resident in HBM, results left in HBM (device-resident throughput)."""
         self._check(self.L.cgx_extract_dev(self.h, C.c_void_p(tok_ptr), C.c_void_p(off_ptr), C.c_void_p(t2q_ptr), Q, T), "cgx_extract_dev")

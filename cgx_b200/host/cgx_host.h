@@ -66,12 +66,13 @@ void cgxh_queries_free(cgxh_queries_t *q);
 int cgxh_write_grammars(const char *outdir, const cgx_result_t *res, const int32_t *qry_off, int32_t qid_base, const cgxh_side_t *src,
                         const cgxh_side_t *tgt, int n_threads);
 
+#define CGXH_DEFAULT_BATCH 10000
 typedef struct {
     const char *reffile, *qryfile, *reftargetfile, *align, *wordscdec, *destinationDirectory;   /* options_t, ComTypes.h:67-78 */
     const char *timefile;
     int minmatchlen, fingerlen;
     int n_gpus;          /* extension: queries sharded over this many GPUs of the box (default 1) */
-    int batch_queries;   /* extension: queries per GPU batch (0 = all at once like the reference) */
+    int batch_queries;   /* extension: queries per GPU batch (0 = even split over the GPUs, at most CGXH_DEFAULT_BATCH) */
     int writer_threads;
     int quiet;
 } cgxh_options_t;

@@ -27,33 +27,79 @@ typedef struct {
     int rc;
 } worker_t;
 
+/* one finished batch handed to the writer thread: host views of its results (valid for two more cgx_extract_begin) */
+typedef struct {
+    pthread_t th;
+    int active, rc;
+    cgx_result_t res;
+    int32_t *off, q0;
+    const worker_t *w;
+    double t_write;
+} wtask_t;
+
+static void *writer_main(void *arg) {
+    wtask_t *t = (wtask_t *)arg;
+    double t0 = now_s();
+    t->rc = cgxh_write_grammars(t->w->opt->destinationDirectory, &t->res, t->off, t->q0, t->w->src, t->w->tgt, t->w->opt->writer_threads);
+    t->t_write = now_s() - t0;
+    return NULL;
+}
+
+static int writer_join(wtask_t *t, worker_t *w) {
+    if (!t->active) return 0;
+    pthread_join(t->th, NULL);
+    t->active = 0;
+    free(t->off); t->off = NULL;
+    w->t_write += t->t_write;
+    return t->rc;
+}
+
+/* Batches of this GPU run as a three-deep pipeline (cgx_extract_begin): while batch k computes, the results of batch
+ * k-1 are still travelling over PCIe and the grammars of batch k-2 are being written (the reference's "IO step",
+ * README.md:76-79, PrintResults.c:434-574, off the critical path). */
 static void *worker_main(void *arg) {
     worker_t *w = (worker_t *)arg;
     const cgxh_queries_t *q = w->qry;
     int32_t n_batches = (q->Q + w->batch - 1) / w->batch;
+    wtask_t wt;
+    memset(&wt, 0, sizeof wt);
+    wt.w = w;
+    int32_t *prev_off = NULL, prev_q0 = 0;
+    int have_prev = 0;
     for (int32_t bi = w->gpu; bi < n_batches; bi += w->n_gpus) {
         int32_t q0 = bi * w->batch, q1 = q0 + w->batch > q->Q ? q->Q : q0 + w->batch;
         int32_t nq = q1 - q0, base = q->off[q0];
         int32_t *off = (int32_t *)malloc(sizeof(int32_t) * ((size_t)nq + 1));
         for (int32_t i = 0; i <= nq; i++) off[i] = q->off[q0 + i] - base;
         double t0 = now_s();
-        if (cgx_extract(w->ctx, q->tok + base, off, nq)) { fprintf(stderr, "cgx_extract: %s\n", cgx_last_error(w->ctx)); w->rc = 1; free(off); return NULL; }
-        cgx_result_t res;
-        cgx_result(w->ctx, &res);
+        if (cgx_extract_begin(w->ctx, q->tok + base, off, nq)) { fprintf(stderr, "cgx_extract_begin: %s\n", cgx_last_error(w->ctx)); w->rc = 1; free(off); break; }
         cgx_batch_info_t bi_info;
         cgx_batch_info(w->ctx, &bi_info);
-        double t1 = now_s();
-        if (cgxh_write_grammars(w->opt->destinationDirectory, &res, off, q0, w->src, w->tgt, w->opt->writer_threads)) { w->rc = 1; free(off); return NULL; }
-        double t2 = now_s();
-        w->t_gpu += t1 - t0; w->t_write += t2 - t1;
-        w->rules += (int64_t)res.n_rules[0] + res.n_rules[1] + res.n_rules[2];
+        w->t_gpu += now_s() - t0;
+        w->rules += (int64_t)bi_info.rules[0] + bi_info.rules[1] + bi_info.rules[2];
         w->launches += bi_info.launches;
         if (!w->opt->quiet)
             fprintf(stderr, "[gpu %d] queries %d..%d: phrases %d, aXb patterns %d (%lld hits), aXbXc patterns %d (%lld hits), rules %d/%d/%d, device %.3f ms\n",
                     w->gpu, q0, q1 - 1, bi_info.G, bi_info.D1, (long long)bi_info.hits1, bi_info.D2, (long long)bi_info.hits2, bi_info.rules[0],
                     bi_info.rules[1], bi_info.rules[2], bi_info.ms_total);
-        free(off);
+        if (writer_join(&wt, w)) { w->rc = 1; free(off); break; }        /* batch k-2 written (it ran beside this batch's kernels) */
+        if (have_prev) {                                                  /* batch k-1 is on the host by now: hand it to the writer */
+            if (cgx_result_at(w->ctx, 1, &wt.res)) { fprintf(stderr, "cgx_result_at: %s\n", cgx_last_error(w->ctx)); w->rc = 1; free(off); break; }
+            wt.off = prev_off; wt.q0 = prev_q0; wt.active = 1; prev_off = NULL;
+            pthread_create(&wt.th, NULL, writer_main, &wt);
+        }
+        prev_off = off; prev_q0 = q0; have_prev = 1;
     }
+    if (writer_join(&wt, w)) w->rc = 1;
+    if (have_prev && prev_off && !w->rc) {                                /* the last batch */
+        double t0 = now_s();
+        if (cgx_result_at(w->ctx, 0, &wt.res)) { fprintf(stderr, "cgx_result_at: %s\n", cgx_last_error(w->ctx)); w->rc = 1; }
+        w->t_gpu += now_s() - t0;
+        t0 = now_s();
+        if (!w->rc && cgxh_write_grammars(w->opt->destinationDirectory, &wt.res, prev_off, prev_q0, w->src, w->tgt, w->opt->writer_threads)) w->rc = 1;
+        w->t_write += now_s() - t0;
+    }
+    free(prev_off);
     return NULL;
 }
 
@@ -89,7 +135,10 @@ int cgxh_run(const cgxh_options_t *opt) {
     double t2 = now_s();
 
     fprintf(stderr, "Start Extract Pair\n");
+    /* queries per batch: -b, else an even split over the GPUs capped at CGXH_DEFAULT_BATCH (the per-batch hit lists grow
+     * with corpus size x batch size; the reference needs <= ~5 k queries per process at its preallocation sizes) */
     int batch = opt->batch_queries > 0 ? opt->batch_queries : (qry.Q > 0 ? (qry.Q + n_gpus - 1) / n_gpus : 1);
+    if (opt->batch_queries <= 0 && batch > CGXH_DEFAULT_BATCH) batch = CGXH_DEFAULT_BATCH;
     worker_t *w = (worker_t *)calloc((size_t)n_gpus, sizeof(worker_t));
     pthread_t *th = (pthread_t *)calloc((size_t)n_gpus, sizeof(pthread_t));
     for (int g = 0; g < n_gpus; g++) {

@@ -92,6 +92,16 @@ int cgx_index_copy_frequent(cgx_ctx_t *ctx, int32_t *out100);
  * Results stay in the context until the next cgx_extract / cgx_destroy. */
 int cgx_extract(cgx_ctx_t *ctx, const int32_t *qry_tok, const int32_t *qry_off, int32_t Q);
 
+/* Pipelined form of cgx_extract for a stream of batches (new relative to the reference, which runs one query file per
+ * process, Start.cu:558): returns as soon as the batch's kernels have finished, while the tail of its result copy is
+ * still travelling to the host; that copy then overlaps the kernels of the next cgx_extract_begin.  The context keeps
+ * the results of the last three batches (device arrays and pinned host mirrors rotate), so the caller can still be
+ * writing batch i-2 while batch i-1 travels and batch i computes:
+ *     cgx_extract_begin(ctx, batch[i]);  cgx_result_at(ctx, 1, &res) -> batch[i-1] complete on the host
+ * cgx_result_at(ctx, age, ..) blocks until that batch's copies are done; age 0 = the most recent batch (= cgx_result),
+ * 1 = the one before, 2 = two before.  Views of a batch stay valid until the third cgx_extract_begin after its own. */
+int cgx_extract_begin(cgx_ctx_t *ctx, const int32_t *qry_tok, const int32_t *qry_off, int32_t Q);
+
 /* Same pipeline with the queries already resident in HBM and the results left there (device pointers:
  * qry_tok_dev T ints, qry_off_dev Q+1 ints, tok2q_dev T ints = query index of every token).  Used to
  * measure the device-resident throughput; cgx_result() is not available after this call. */
@@ -134,7 +144,7 @@ typedef struct {
     float max_lex_f_given_e, max_lex_e_given_f;
 } cgx_rule_t;
 
-/* Host views of the batch results (valid until the next cgx_extract):
+/* Host views of the batch results (valid until the next cgx_extract; see cgx_extract_begin for the pipelined form):
  *   phrase_id : T*5 ints, id of the contiguous phrase q[t..t+len) for len = 1..5, -1 when absent
  *   phrases   : G x {sa_up, sa_down, len, corpus_pos}      (saind_t, ComTypes.h:342)
  *   pat1      : D1 x {a_pos, ls, b_pos, le, hit_start, hit_count, marker_pair(-1|0..9999), fs_extra}
@@ -154,6 +164,7 @@ typedef struct {
     int32_t n_ids[3];
 } cgx_result_t;
 int cgx_result(cgx_ctx_t *ctx, cgx_result_t *out);
+int cgx_result_at(cgx_ctx_t *ctx, int age, cgx_result_t *out);      /* see cgx_extract_begin */
 
 /* parity helpers (tests): intermediate arrays of the last batch, copied to the host.
  *   what = "longest" (T ints, capped at 5), "intervals" (T*5*2 ints), "hits1" (hits1 x 3: id,pos,len),

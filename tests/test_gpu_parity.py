@@ -239,6 +239,55 @@ def test_batching_is_transparent(micro):
     assert la + lb == lines_full
 
 
+def test_pipelined_batches_equal_synchronous(micro):
+    """cgx_extract_begin / cgx_result_at: five batches through the three-set pipeline; every batch read back at age 1 (or
+    2, or 0 for the last) equals the same batch through the synchronous cgx_extract, array by array."""
+    from cgx_b200.extractor import GrammarExtractor
+    _, lay = micro
+    ex = GrammarExtractor(0)
+    ex.build_index(lay)
+    off, tok = lay["qry_off"], lay["qry_tok"]
+    Q = len(off) - 1
+    cuts = [0, Q // 7, Q // 3, Q // 3, Q // 2, Q]          # ragged batches, one of them empty
+    parts = [(tok[off[a]:off[b]], off[a:b + 1] - off[a]) for a, b in zip(cuts[:-1], cuts[1:])]
+    want = [ex.extract(t, o) for t, o in parts]
+
+    def same(x, y):
+        assert (x.Q, x.T, x.G, x.D1, x.D2) == (y.Q, y.T, y.G, y.D1, y.D2)
+        for name in ("phrase_id", "phrases", "pat1", "pat2", "q1_off", "q1_ids", "q2_off", "q2_ids"):
+            assert np.array_equal(getattr(x, name), getattr(y, name)), name
+        for k in range(3):
+            assert x.rules[k].tobytes() == y.rules[k].tobytes(), k
+            assert np.array_equal(x.updown[k], y.updown[k]), k
+
+    got = [None] * len(parts)
+    for i, (t, o) in enumerate(parts):
+        ex.extract_begin(t, o)
+        if i >= 2:                                           # the batch two begins ago is still there
+            same(ex.result_at(2, *parts[i - 2]), want[i - 2])
+        if i >= 1:
+            got[i - 1] = ex.result_at(1, *parts[i - 1])
+    got[-1] = ex.result_at(0, *parts[-1])
+    for g, w in zip(got, want):
+        same(g, w)
+    with pytest.raises(RuntimeError):
+        ex.result_at(3)
+
+
+def test_cli_pipelined_batches_write_the_same_grammars(micro, micro_files, tmp_path):
+    """bin/strmatchcuda -b: many small batches through the begin / writer-thread pipeline == one batch, file by file."""
+    outs = []
+    for name, extra in (("one", []), ("many", ["-b", "7", "-w", "2"])):
+        out = tmp_path / name
+        out.mkdir()
+        r = subprocess.run([os.path.join(ROOT, "bin", "strmatchcuda"), "-q"] + extra + [micro_files["f"], micro_files["q"], micro_files["e"], micro_files["a"],
+                            micro_files["lex"], str(out)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(out)
+    c = gc.compare_dirs(str(outs[0]), str(outs[1]), rtol=0, atol=0)
+    assert c["files"] == micro[0].n_qry and c["only_a"] == 0 and c["only_b"] == 0 and c["float_mismatch"] == 0, c
+
+
 def test_medium_scale_properties():
     """A corpus the oracle would need minutes for: size-independent properties only.
     SA is a permutation whose adjacent suffixes are in order; occurrence lists are position-sorted inside every
