@@ -12,7 +12,7 @@ using namespace cgx;
         return 0;                                           \
     } catch (const CgxError &e) {                           \
         if (ctx) (ctx)->err = e.msg;                        \
-        return 1;                                           \
+        return e.code;                                      \
     } catch (const std::exception &e) {                     \
         if (ctx) (ctx)->err = e.what();                     \
         return 2;                                           \
@@ -345,15 +345,27 @@ static void run_batch(cgx_ctx *c, int32_t Q, int32_t T, bool fetch, bool wait_co
     CUDA_CHECK(cudaEventElapsedTime(&in.ms_aggregate, b.ev[6], b.ev[7]));
 }
 
+static void extract_host_run(cgx_ctx *c, const int32_t *qry_tok, const int32_t *qry_off, int32_t Q, int32_t T, bool pipelined);
+
 static void extract_host(cgx_ctx *c, const int32_t *qry_tok, const int32_t *qry_off, int32_t Q, bool pipelined) {
     CGX_REQUIRE(c && qry_off && Q >= 0, "bad argument");
     CGX_REQUIRE(c->ix.built, "index not built");
     CUDA_CHECK(cudaSetDevice(c->device));
     Batch &b = c->batch;
-    cudaStream_t s = c->stream;
     const int32_t T = qry_off[Q];
     CGX_REQUIRE(T == 0 || qry_tok, "null query tokens");
     if (pipelined) rotate_results(b);
+    try {
+        extract_host_run(c, qry_tok, qry_off, Q, T, pipelined);
+    } catch (...) {
+        if (pipelined) { swap_results(b, b.parked[1]); swap_results(b, b.parked[0]); }      // a failed batch leaves the pipeline as it was
+        throw;
+    }
+}
+
+static void extract_host_run(cgx_ctx *c, const int32_t *qry_tok, const int32_t *qry_off, int32_t Q, int32_t T, bool pipelined) {
+    Batch &b = c->batch;
+    cudaStream_t s = c->stream;
     b.valid = false;
     b.Q = Q; b.T = T; b.launches = 0;
     memset(&b.info, 0, sizeof(b.info));

@@ -21,6 +21,7 @@
 
 struct CgxError {
     std::string msg;
+    int code = 1;        // return value of the C ABI entry point (CGX_E_* in include/cgx_b200.h)
 };
 
 #define CUDA_CHECK(expr)                                                                              \
@@ -39,6 +40,16 @@ struct CgxError {
             char b_[512];                                                         \
             snprintf(b_, sizeof b_, __VA_ARGS__);                                 \
             throw CgxError{std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": " + b_}; \
+        }                                                                         \
+    } while (0)
+
+// the batch does not fit the 31-bit hit / 32-bit cell indices: the caller splits it (CGX_E_BATCH_TOO_LARGE)
+#define CGX_REQUIRE_BATCH(cond, ...)                                              \
+    do {                                                                          \
+        if (!(cond)) {                                                            \
+            char b_[512];                                                         \
+            snprintf(b_, sizeof b_, __VA_ARGS__);                                 \
+            throw CgxError{std::string("batch too large: ") + b_, 3};             \
         }                                                                         \
     } while (0)
 

@@ -337,6 +337,14 @@ __global__ void j1_missing_kernel(Pat1 *__restrict__ pat, const int32_t *__restr
     if (d < D1) pat[d].fs_extra = missing[d];
 }
 
+// hits per batch and kind: hit_start / hit_count of the pattern tables are int32.  CGX_HIT_LIMIT lowers it (tests of the
+// caller's batch splitting).
+static unsigned long long hit_limit() {
+    unsigned long long lim = (1ull << 31) - 1;
+    if (const char *e = getenv("CGX_HIT_LIMIT")) { unsigned long long v = strtoull(e, nullptr, 10); if (v && v < lim) lim = v; }
+    return lim;
+}
+
 static void read_u64s(unsigned long long *dst, const unsigned long long *d, int count, cudaStream_t stream) {
     CUDA_CHECK(cudaMemcpyAsync(dst, d, sizeof(unsigned long long) * count, cudaMemcpyDeviceToHost, stream));
     CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -398,6 +406,7 @@ void stage_onegap_join(const Index &ix, Batch &b, cudaStream_t stream) {
         else if (n_elems) PROF("join_onegap", 0.0, (j1_scan_kernel<<<cgx_div_up(n_elems, J1_BLOCK), J1_BLOCK, 0, stream>>>(a)));
         b.launches += 1;
         read_u64s(host_ctr, ctr, 3, stream);
+        CGX_REQUIRE_BATCH(host_ctr[0] < hit_limit(), "%llu one-gap hits", host_ctr[0]);
         if (host_ctr[0] <= b.hit_cap) { b.hits1 = (int64_t)host_ctr[0]; break; }
         b.hit_cap = (size_t)host_ctr[0] + (size_t)host_ctr[0] / 8 + 1024;        // grow once to the exact need and redo the scan
     }
@@ -494,7 +503,7 @@ void stage_twogap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     CGX_REQUIRE(cgx_bits_for((uint64_t)D2) + b.pbits + 8 <= 64, "two-gap join: %d distinct patterns exceed the hit-key field", D2);
     // corpus tokens never exceed maxtok, so (parent id, token) fits dbits1 + cbits
     const int cbits = cgx_bits_for((uint64_t)ix.maxtok), d2bits = cgx_bits_for((uint64_t)D2);
-    CGX_REQUIRE(cgx_bits_for((uint64_t)b.D1) + cbits + d2bits <= 63, "two-gap join: %d x %d patterns do not fit the packed pattern table; use smaller query batches", b.D1, D2);
+    CGX_REQUIRE_BATCH(cgx_bits_for((uint64_t)b.D1) + cbits + d2bits <= 63, "%d x %d patterns do not fit the packed two-gap pattern table", b.D1, D2);
     const uint32_t slots_n = pt_slots_for((size_t)D2);
     PackTab tab{b.j_hash.get<unsigned long long>(slots_n), slots_n - 1, d2bits};
     uint8_t *has_child = b.j_aflag.get<uint8_t>((size_t)b.D1 + 4);
@@ -513,6 +522,7 @@ void stage_twogap_join(const Index &ix, Batch &b, cudaStream_t stream) {
                                                            ix.gapw.ptr<uint32_t>(), tab, cbits, ctr, hits, b.hit_cap)));
         b.launches += 1;
         read_u64s(host_ctr, ctr, 3, stream);
+        CGX_REQUIRE_BATCH(host_ctr[0] < hit_limit(), "%llu two-gap hits", host_ctr[0]);
         if (host_ctr[0] <= b.hit_cap) { b.hits2 = (int64_t)host_ctr[0]; break; }
         b.hit_cap = (size_t)host_ctr[0] + (size_t)host_ctr[0] / 8 + 1024;
     }

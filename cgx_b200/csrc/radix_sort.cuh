@@ -33,9 +33,14 @@ constexpr int RS_TILE = RS_BLOCK * RS_ITEMS;  // 4096 keys per tile
 constexpr int RS_BINS = 256;
 constexpr int RS_MAX_PASSES = 8;
 
-constexpr uint32_t RS_FLAG_PARTIAL = 1u << 30;
-constexpr uint32_t RS_FLAG_INCLUSIVE = 2u << 30;
-constexpr uint32_t RS_VALUE_MASK = (1u << 30) - 1;
+// look-back status word: two flag bits above the count.  32-bit words (30-bit counts) up to 2^30 keys, 64-bit words beyond
+template <typename S> struct RsStatus;
+template <> struct RsStatus<uint32_t> {
+    static constexpr uint32_t PARTIAL = 1u << 30, INCLUSIVE = 2u << 30, VALUE_MASK = (1u << 30) - 1;
+};
+template <> struct RsStatus<uint64_t> {
+    static constexpr uint64_t PARTIAL = 1ull << 62, INCLUSIVE = 2ull << 62, VALUE_MASK = (1ull << 62) - 1;
+};
 
 struct RadixPlan {
     int num_passes;
@@ -59,7 +64,7 @@ static inline RadixPlan make_radix_plan(int begin_bit, int end_bit) {
 
 struct RadixTemp {
     DevBuf hist;      // [passes][256] uint32: digit histograms, then exclusive offsets
-    DevBuf status;    // [tiles][256] uint32 look-back words
+    DevBuf status;    // [tiles][256] look-back words (uint32, uint64 from 2^30 keys on)
     DevBuf counters;  // [passes] dynamic tile counters
 };
 
@@ -86,6 +91,14 @@ __device__ __forceinline__ uint32_t rs_ld_status(const uint32_t *p) {
 }
 __device__ __forceinline__ void rs_st_status(uint32_t *p, uint32_t v) {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t rs_ld_status(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void rs_st_status(uint64_t *p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 template <typename K>
@@ -131,11 +144,12 @@ static __global__ void __launch_bounds__(RS_BINS) rs_scan_hist_kernel(uint32_t *
 // with payloads) and 64-80 registers per thread: four (three with payloads) CTAs per SM.  (Round 1a kept the keys, their
 // ranks, staging positions and 64-bit output offsets in registers: 157 registers with payloads = one CTA per SM,
 // 12 % occupancy, 1.3 TB/s.)
-template <typename K, bool HAS_VALUES>
+template <typename K, bool HAS_VALUES, typename S = uint32_t>
 __global__ void __launch_bounds__(RS_BLOCK, HAS_VALUES ? 3 : 4) rs_onesweep_kernel(const K *__restrict__ keys_in, K *__restrict__ keys_out,
                                                                   const uint32_t *__restrict__ vals_in, uint32_t *__restrict__ vals_out,
                                                                   size_t n, int shift, int bits, const uint32_t *__restrict__ digit_offset,
-                                                                  uint32_t *status, uint32_t *tile_counter) {
+                                                                  S *status, uint32_t *tile_counter) {
+    using ST = RsStatus<S>;
     extern __shared__ __align__(16) unsigned char s_raw[];      // RS_TILE keys (+ RS_TILE payloads): rs_smem_bytes<K>(HAS_VALUES)
     __shared__ uint32_t s_bin_start[RS_BINS];
     __shared__ uint32_t s_global_base[RS_BINS];
@@ -199,7 +213,7 @@ __global__ void __launch_bounds__(RS_BLOCK, HAS_VALUES ? 3 : 4) rs_onesweep_kern
             sum += t;
         }
         tile_count = sum;
-        rs_st_status(status + (size_t)tile * RS_BINS + tid, sum | (tile == 0 ? RS_FLAG_INCLUSIVE : RS_FLAG_PARTIAL));
+        rs_st_status(status + (size_t)tile * RS_BINS + tid, (S)sum | (tile == 0 ? ST::INCLUSIVE : ST::PARTIAL));
         // block-wide exclusive scan of the 256 tile counts: shuffle scan per warp, then the 8 warp totals
         incl = sum;
 #pragma unroll
@@ -221,14 +235,14 @@ __global__ void __launch_bounds__(RS_BLOCK, HAS_VALUES ? 3 : 4) rs_onesweep_kern
         if (tile > 0) {
             int t = (int)tile - 1;
             while (true) {
-                const uint32_t *pst = status + (size_t)t * RS_BINS + tid;
-                uint32_t v = rs_ld_status(pst);
-                while ((v & (RS_FLAG_PARTIAL | RS_FLAG_INCLUSIVE)) == 0) { __nanosleep(20); v = rs_ld_status(pst); }
-                excl += v & RS_VALUE_MASK;
-                if (v & RS_FLAG_INCLUSIVE) break;
+                const S *pst = status + (size_t)t * RS_BINS + tid;
+                S v = rs_ld_status(pst);
+                while ((v & (ST::PARTIAL | ST::INCLUSIVE)) == 0) { __nanosleep(20); v = rs_ld_status(pst); }
+                excl += (uint32_t)(v & ST::VALUE_MASK);          // counts stay below 2^32 (n < 2^32)
+                if (v & ST::INCLUSIVE) break;
                 t--;
             }
-            rs_st_status(status + (size_t)tile * RS_BINS + tid, (excl + tile_count) | RS_FLAG_INCLUSIVE);
+            rs_st_status(status + (size_t)tile * RS_BINS + tid, (S)(excl + tile_count) | ST::INCLUSIVE);
         }
         s_global_base[tid] = digit_offset[tid] + excl - bin_start;
     }
@@ -271,11 +285,13 @@ void radix_sort(K *keys, K *keys_tmp, uint32_t *vals, uint32_t *vals_tmp, size_t
     *keys_sorted = keys;
     if (vals_sorted) *vals_sorted = vals;
     if (n <= 1) return;
-    CGX_REQUIRE(n < (size_t)RS_VALUE_MASK, "radix_sort: n=%zu too large for 30-bit look-back counters", n);
+    CGX_REQUIRE(n < (1ull << 32) - RS_TILE, "radix_sort: n=%zu does not fit the 32-bit digit offsets", n);
+    const bool wide = n >= (size_t)RsStatus<uint32_t>::VALUE_MASK;      // 64-bit look-back words from 2^30 keys on
     RadixPlan plan = make_radix_plan(begin_bit, end_bit);
     size_t tiles = (n + RS_TILE - 1) / RS_TILE;
     uint32_t *hist = tmp.hist.get<uint32_t>(RS_MAX_PASSES * RS_BINS);
-    uint32_t *status = tmp.status.get<uint32_t>(tiles * RS_BINS);
+    const size_t status_bytes = tiles * RS_BINS * (wide ? sizeof(uint64_t) : sizeof(uint32_t));
+    void *status = tmp.status.get<unsigned char>(status_bytes);
     uint32_t *counters = tmp.counters.get<uint32_t>(RS_MAX_PASSES);
     CUDA_CHECK(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * RS_MAX_PASSES * RS_BINS, stream));
     CUDA_CHECK(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * RS_MAX_PASSES, stream));
@@ -286,16 +302,22 @@ void radix_sort(K *keys, K *keys_tmp, uint32_t *vals, uint32_t *vals_tmp, size_t
     K *kin = keys, *kout = keys_tmp;
     uint32_t *vin = vals, *vout = vals_tmp;
     const size_t smem = rs_smem_bytes<K>(vals != nullptr);
-    if (vals) CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, true, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<K>(true)));
+    CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, false, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<K>(false)));
+    CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, true, uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<K>(true)));
+    CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, false, uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<K>(false)));
     for (int p = 0; p < plan.num_passes; p++) {
-        CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(uint32_t) * tiles * RS_BINS, stream));
-        if (vals)
-            PROF("radix_onesweep", (double)n * 2.0 * (sizeof(K) + 4), (rs_onesweep_kernel<K, true><<<(unsigned)tiles, RS_BLOCK, smem, stream>>>(
-                     kin, kout, vin, vout, n, plan.shift[p], plan.bits[p], hist + p * RS_BINS, status, counters + p)));
+        CUDA_CHECK(cudaMemsetAsync(status, 0, status_bytes, stream));
+        const double bytes = (double)n * 2.0 * (sizeof(K) + (vals ? 4 : 0));
+        const uint32_t *off = hist + p * RS_BINS;
+        if (vals && !wide)
+            PROF("radix_onesweep", bytes, (rs_onesweep_kernel<K, true, uint32_t><<<(unsigned)tiles, RS_BLOCK, smem, stream>>>(kin, kout, vin, vout, n, plan.shift[p], plan.bits[p], off, (uint32_t *)status, counters + p)));
+        else if (!vals && !wide)
+            PROF("radix_onesweep", bytes, (rs_onesweep_kernel<K, false, uint32_t><<<(unsigned)tiles, RS_BLOCK, smem, stream>>>(kin, kout, nullptr, nullptr, n, plan.shift[p], plan.bits[p], off, (uint32_t *)status, counters + p)));
+        else if (vals)
+            PROF("radix_onesweep", bytes, (rs_onesweep_kernel<K, true, uint64_t><<<(unsigned)tiles, RS_BLOCK, smem, stream>>>(kin, kout, vin, vout, n, plan.shift[p], plan.bits[p], off, (uint64_t *)status, counters + p)));
         else
-            PROF("radix_onesweep", (double)n * 2.0 * sizeof(K), (rs_onesweep_kernel<K, false><<<(unsigned)tiles, RS_BLOCK, smem, stream>>>(
-                     kin, kout, nullptr, nullptr, n, plan.shift[p], plan.bits[p], hist + p * RS_BINS, status, counters + p)));
+            PROF("radix_onesweep", bytes, (rs_onesweep_kernel<K, false, uint64_t><<<(unsigned)tiles, RS_BLOCK, smem, stream>>>(kin, kout, nullptr, nullptr, n, plan.shift[p], plan.bits[p], off, (uint64_t *)status, counters + p)));
         if (launches) *launches += 1;
         std::swap(kin, kout);
         std::swap(vin, vout);

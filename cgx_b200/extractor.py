@@ -274,6 +274,39 @@ class GrammarExtractor:
             return r
         return BatchResult(r, info if info is not None else BatchInfo(), qry_tok, qry_off)
 
+    def extract_stream(self, qry_tok, qry_off, batch_queries=10000, on_batch=None):
+        """A stream of query batches through the pipelined API, the way bin/strmatchcuda drives it: batches of
+        `batch_queries`, a batch refused as too large (CGX_E_BATCH_TOO_LARGE) is cut in two.  on_batch(q0, q1, raw
+        cgx_result_t views) is called for every finished batch, in order; returns the list of batch infos."""
+        qt = np.ascontiguousarray(qry_tok, dtype=np.int32)
+        qo = np.ascontiguousarray(qry_off, dtype=np.int32)
+        Q = len(qo) - 1
+        todo = [(a, min(Q, a + batch_queries)) for a in range(0, Q, batch_queries)][::-1]
+        infos, prev = [], None
+        while todo:
+            q0, q1 = todo.pop()
+            t = qt[qo[q0]:qo[q1]] if qo[q1] > qo[q0] else np.zeros(1, dtype=np.int32)
+            o = np.ascontiguousarray(qo[q0:q1 + 1] - qo[q0])
+            rc = self.L.cgx_extract_begin(self.h, _p(np.ascontiguousarray(t), C.c_int32), _p(o, C.c_int32), q1 - q0)
+            if rc == 3 and q1 - q0 > 1:
+                mid = (q0 + q1) // 2
+                todo += [(mid, q1), (q0, mid)]
+                continue
+            self._check(rc, "cgx_extract_begin")
+            info = BatchInfo()
+            self.L.cgx_batch_info(self.h, C.byref(info))
+            d = info.as_dict()
+            d["q0"], d["q1"] = q0, q1
+            infos.append(d)
+            if prev is not None and on_batch is not None:
+                on_batch(prev[0], prev[1], self.result_at(1, raw=True))
+            prev = (q0, q1)
+        if prev is not None:
+            r = self.result_at(0, raw=True)
+            if on_batch is not None:
+                on_batch(prev[0], prev[1], r)
+        return infos
+
     def extract_dev(self, tok_ptr: int, off_ptr: int, t2q_ptr: int, Q: int, T: int):
         """Queries resident in HBM, results left in HBM (device-resident throughput)."""
         self._check(self.L.cgx_extract_dev(self.h, C.c_void_p(tok_ptr), C.c_void_p(off_ptr), C.c_void_p(t2q_ptr), Q, T), "cgx_extract_dev")

@@ -56,7 +56,8 @@ static int writer_join(wtask_t *t, worker_t *w) {
 
 /* Batches of this GPU run as a three-deep pipeline (cgx_extract_begin): while batch k computes, the results of batch
  * k-1 are still travelling over PCIe and the grammars of batch k-2 are being written (the reference's "IO step",
- * README.md:76-79, PrintResults.c:434-574, off the critical path). */
+ * README.md:76-79, PrintResults.c:434-574, off the critical path).  A batch the library refuses as too large
+ * (CGX_E_BATCH_TOO_LARGE: hit lists grow with corpus size x batch size) is cut in two and both halves queued again. */
 static void *worker_main(void *arg) {
     worker_t *w = (worker_t *)arg;
     const cgxh_queries_t *q = w->qry;
@@ -66,30 +67,51 @@ static void *worker_main(void *arg) {
     wt.w = w;
     int32_t *prev_off = NULL, prev_q0 = 0;
     int have_prev = 0;
+    /* work list of [q0,q1) ranges, processed in ascending order (a refused range is replaced by its halves) */
+    int32_t cap = 64, top = 0;
+    int32_t (*stack)[2] = (int32_t (*)[2])malloc(sizeof(int32_t[2]) * (size_t)cap);
     for (int32_t bi = w->gpu; bi < n_batches; bi += w->n_gpus) {
         int32_t q0 = bi * w->batch, q1 = q0 + w->batch > q->Q ? q->Q : q0 + w->batch;
-        int32_t nq = q1 - q0, base = q->off[q0];
-        int32_t *off = (int32_t *)malloc(sizeof(int32_t) * ((size_t)nq + 1));
-        for (int32_t i = 0; i <= nq; i++) off[i] = q->off[q0 + i] - base;
-        double t0 = now_s();
-        if (cgx_extract_begin(w->ctx, q->tok + base, off, nq)) { fprintf(stderr, "cgx_extract_begin: %s\n", cgx_last_error(w->ctx)); w->rc = 1; free(off); break; }
-        cgx_batch_info_t bi_info;
-        cgx_batch_info(w->ctx, &bi_info);
-        w->t_gpu += now_s() - t0;
-        w->rules += (int64_t)bi_info.rules[0] + bi_info.rules[1] + bi_info.rules[2];
-        w->launches += bi_info.launches;
-        if (!w->opt->quiet)
-            fprintf(stderr, "[gpu %d] queries %d..%d: phrases %d, aXb patterns %d (%lld hits), aXbXc patterns %d (%lld hits), rules %d/%d/%d, device %.3f ms\n",
-                    w->gpu, q0, q1 - 1, bi_info.G, bi_info.D1, (long long)bi_info.hits1, bi_info.D2, (long long)bi_info.hits2, bi_info.rules[0],
-                    bi_info.rules[1], bi_info.rules[2], bi_info.ms_total);
-        if (writer_join(&wt, w)) { w->rc = 1; free(off); break; }        /* batch k-2 written (it ran beside this batch's kernels) */
-        if (have_prev) {                                                  /* batch k-1 is on the host by now: hand it to the writer */
-            if (cgx_result_at(w->ctx, 1, &wt.res)) { fprintf(stderr, "cgx_result_at: %s\n", cgx_last_error(w->ctx)); w->rc = 1; free(off); break; }
-            wt.off = prev_off; wt.q0 = prev_q0; wt.active = 1; prev_off = NULL;
-            pthread_create(&wt.th, NULL, writer_main, &wt);
+        stack[0][0] = q0; stack[0][1] = q1; top = 1;
+        while (top > 0 && !w->rc) {
+            top--;
+            q0 = stack[top][0]; q1 = stack[top][1];
+            int32_t nq = q1 - q0, base = q->off[q0];
+            int32_t *off = (int32_t *)malloc(sizeof(int32_t) * ((size_t)nq + 1));
+            for (int32_t i = 0; i <= nq; i++) off[i] = q->off[q0 + i] - base;
+            double t0 = now_s();
+            int rc = cgx_extract_begin(w->ctx, q->tok + base, off, nq);
+            if (rc == CGX_E_BATCH_TOO_LARGE && nq > 1) {
+                if (!w->opt->quiet) fprintf(stderr, "[gpu %d] queries %d..%d: %s -- splitting\n", w->gpu, q0, q1 - 1, cgx_last_error(w->ctx));
+                free(off);
+                if (top + 2 > cap) { cap *= 2; stack = (int32_t (*)[2])realloc(stack, sizeof(int32_t[2]) * (size_t)cap); }
+                int32_t mid = q0 + nq / 2;
+                stack[top][0] = mid; stack[top][1] = q1; top++;          /* second half below the first: ascending order */
+                stack[top][0] = q0; stack[top][1] = mid; top++;
+                w->t_gpu += now_s() - t0;
+                continue;
+            }
+            if (rc) { fprintf(stderr, "cgx_extract_begin: %s\n", cgx_last_error(w->ctx)); w->rc = 1; free(off); break; }
+            cgx_batch_info_t bi_info;
+            cgx_batch_info(w->ctx, &bi_info);
+            w->t_gpu += now_s() - t0;
+            w->rules += (int64_t)bi_info.rules[0] + bi_info.rules[1] + bi_info.rules[2];
+            w->launches += bi_info.launches;
+            if (!w->opt->quiet)
+                fprintf(stderr, "[gpu %d] queries %d..%d: phrases %d, aXb patterns %d (%lld hits), aXbXc patterns %d (%lld hits), rules %d/%d/%d, device %.3f ms\n",
+                        w->gpu, q0, q1 - 1, bi_info.G, bi_info.D1, (long long)bi_info.hits1, bi_info.D2, (long long)bi_info.hits2, bi_info.rules[0],
+                        bi_info.rules[1], bi_info.rules[2], bi_info.ms_total);
+            if (writer_join(&wt, w)) { w->rc = 1; free(off); break; }        /* batch k-2 written (it ran beside this batch's kernels) */
+            if (have_prev) {                                                  /* batch k-1 is on the host by now: hand it to the writer */
+                if (cgx_result_at(w->ctx, 1, &wt.res)) { fprintf(stderr, "cgx_result_at: %s\n", cgx_last_error(w->ctx)); w->rc = 1; free(off); break; }
+                wt.off = prev_off; wt.q0 = prev_q0; wt.active = 1; prev_off = NULL;
+                pthread_create(&wt.th, NULL, writer_main, &wt);
+            }
+            prev_off = off; prev_q0 = q0; have_prev = 1;
         }
-        prev_off = off; prev_q0 = q0; have_prev = 1;
+        if (w->rc) break;
     }
+    free(stack);
     if (writer_join(&wt, w)) w->rc = 1;
     if (have_prev && prev_off && !w->rc) {                                /* the last batch */
         double t0 = now_s();

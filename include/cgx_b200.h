@@ -22,6 +22,15 @@ extern "C" {
 
 typedef struct cgx_ctx cgx_ctx_t;
 
+/* return codes */
+#define CGX_OK 0
+#define CGX_E_FAILED 1            /* cgx_last_error() has the text */
+#define CGX_E_EXCEPTION 2
+#define CGX_E_BATCH_TOO_LARGE 3   /* cgx_extract*: the batch's hit lists / record cells exceed the 31-bit indices of the result
+                                     tables (hits grow with corpus size x batch size): split the batch and call again.  The
+                                     reference has the same limit without the check (ONEGAP_PREALLOCATION 60 M hits,
+                                     ComTypes.h:56; SURVEY.md 8c "operating envelope"). */
+
 /* ---- context --------------------------------------------------------------------------------- */
 /* replaces suffixArraySearchInit (SuffixArray.cu:769) / cudaSetDevice */
 int cgx_create(int device, cgx_ctx_t **out);

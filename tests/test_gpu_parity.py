@@ -3,6 +3,7 @@
 committed reference fixtures, against the reference binary run live next to it, and -- at larger sizes --
 through size-independent properties."""
 import collections
+import ctypes as C
 import os
 import subprocess
 
@@ -283,6 +284,47 @@ def test_cli_pipelined_batches_write_the_same_grammars(micro, micro_files, tmp_p
         r = subprocess.run([os.path.join(ROOT, "bin", "strmatchcuda"), "-q"] + extra + [micro_files["f"], micro_files["q"], micro_files["e"], micro_files["a"],
                             micro_files["lex"], str(out)], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(out)
+    c = gc.compare_dirs(str(outs[0]), str(outs[1]), rtol=0, atol=0)
+    assert c["files"] == micro[0].n_qry and c["only_a"] == 0 and c["only_b"] == 0 and c["float_mismatch"] == 0, c
+
+
+def test_oversized_batches_are_split(micro, micro_files, tmp_path, monkeypatch):
+    """A batch whose hit lists exceed the index width of the result tables is refused with CGX_E_BATCH_TOO_LARGE (the
+    limit is lowered here through CGX_HIT_LIMIT); the callers -- extract_stream and bin/strmatchcuda -- cut it in two,
+    the pipeline state survives the refusal, and the grammars equal those of the unsplit run."""
+    from cgx_b200.extractor import GrammarExtractor
+    _, lay = micro
+    ex = GrammarExtractor(0)
+    ex.build_index(lay)
+    off, tok = lay["qry_off"], lay["qry_tok"]
+    full = ex.extract(tok, off)
+    want = [sorted(full.grammar_lines(q, lay)) for q in range(full.Q)]
+    limit = max(int(full.info["hits1"]), int(full.info["hits2"])) // 3
+    monkeypatch.setenv("CGX_HIT_LIMIT", str(limit))
+    assert ex.L.cgx_extract(ex.h, tok.ctypes.data_as(C.POINTER(C.c_int32)), np.ascontiguousarray(off, dtype=np.int32).ctypes.data_as(C.POINTER(C.c_int32)), full.Q) == 3
+    got = {}
+
+    def on_batch(q0, q1, r):
+        from cgx_b200.extractor import BatchResult
+        from cgx_b200._lib import BatchInfo
+        br = BatchResult(r, BatchInfo(), tok[off[q0]:off[q1]], off[q0:q1 + 1] - off[q0])
+        for q in range(q0, q1):
+            got[q] = sorted(br.grammar_lines(q - q0, lay))
+
+    infos = ex.extract_stream(tok, off, batch_queries=full.Q, on_batch=on_batch)
+    assert len(infos) >= 3 and [got[q] for q in range(full.Q)] == want
+    outs = []
+    for name in ("plain", "split"):
+        out = tmp_path / name
+        out.mkdir()
+        env = dict(os.environ)
+        if name == "plain":
+            env.pop("CGX_HIT_LIMIT", None)
+        r = subprocess.run([os.path.join(ROOT, "bin", "strmatchcuda"), micro_files["f"], micro_files["q"], micro_files["e"], micro_files["a"],
+                            micro_files["lex"], str(out)], capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert ("splitting" in r.stderr) == (name == "split")
         outs.append(out)
     c = gc.compare_dirs(str(outs[0]), str(outs[1]), rtol=0, atol=0)
     assert c["files"] == micro[0].n_qry and c["only_a"] == 0 and c["only_b"] == 0 and c["float_mismatch"] == 0, c

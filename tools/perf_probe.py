@@ -15,15 +15,13 @@ print("gen %.1fs layout %.1fs n=%d m=%d T=%d lex=%d" % (t1 - t0, t2 - t1, lay["n
 ex = GrammarExtractor(0)
 t0 = time.time(); info = ex.build_index(lay); print("index build wall %.2fs" % (time.time() - t0), info, flush=True)
 ex.profile(True)
-qo = np.asarray(lay["qry_off"]); qt = np.asarray(lay["qry_tok"]); Q = len(qo) - 1
 for r in range(reps):
     t0 = time.time()
-    for q0 in range(0, Q, bq):
-        q1 = min(Q, q0 + bq)
-        res = ex.extract(qt[qo[q0]:qo[q1]], qo[q0:q1 + 1] - qo[q0], fetch=False)
-        if bq < Q: print("  batch %d..%d" % (q0, q1), json.dumps(res), flush=True)
+    infos = ex.extract_stream(lay["qry_tok"], lay["qry_off"], bq)
     dt = time.time() - t0
-    print("rep %d wall %.3fs -> %.0f q/s" % (r, dt, nq / dt), json.dumps(res), flush=True)
+    if len(infos) > 1:
+        for i in infos: print("  batch", json.dumps(i), flush=True)
+    print("rep %d wall %.3fs -> %.0f q/s (%d batches, device ms %.1f)" % (r, dt, nq / dt, len(infos), sum(i["ms_total"] for i in infos)), json.dumps(infos[-1]), flush=True)
 rep = ex.profile_report()
 tot = sum(v["ms"] for v in rep.values())
 print("profiled kernels: %.1f ms over %d reps" % (tot, reps))
