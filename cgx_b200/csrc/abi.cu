@@ -57,7 +57,7 @@ extern "C" void cgx_destroy(cgx_ctx_t *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     Index &ix = c->ix;
-    DevBuf *ib[] = {&ix.str, &ix.sa, &ix.inv[0], &ix.inv[1], &ix.inv[2], &ix.bkt[0], &ix.bkt[1], &ix.bkt[2], &ix.jwin, &ix.tok_start, &ix.RLP, &ix.L_tar, &ix.R_tar, &ix.tgt, &ix.freq_flag, &ix.gapw,
+    DevBuf *ib[] = {&ix.str, &ix.sa, &ix.inv[0], &ix.inv[1], &ix.inv[2], &ix.bkt[0], &ix.bkt[1], &ix.bkt[2], &ix.jwin, &ix.xw, &ix.lr, &ix.tok_start, &ix.RLP, &ix.L_tar, &ix.R_tar, &ix.tgt, &ix.freq_flag, &ix.gapw,
                     &ix.lex_key, &ix.lex_v1, &ix.lex_v2, &ix.lex_hash};
     for (auto *b : ib) b->release();
     c->ws.release();
@@ -212,7 +212,7 @@ extern "C" int cgx_index_info(const cgx_ctx_t *c, cgx_index_info_t *out) {
     out->n = (int64_t)ix.n; out->m = (int64_t)ix.m;
     out->sa_rounds = ix.sa_stats.rounds; out->sa_key_bits = ix.sa_stats.key_bits; out->sa_launches = ix.sa_stats.launches;
     out->sa_build_ms = ix.sa_stats.ms; out->aux_build_ms = c->aux_ms;
-    out->index_bytes = (int64_t)(ix.str.cap + ix.sa.cap + ix.inv[0].cap + ix.inv[1].cap + ix.inv[2].cap + ix.bkt[0].cap + ix.bkt[1].cap + ix.bkt[2].cap + ix.jwin.cap + ix.tok_start.cap + ix.RLP.cap + ix.L_tar.cap +
+    out->index_bytes = (int64_t)(ix.str.cap + ix.sa.cap + ix.inv[0].cap + ix.inv[1].cap + ix.inv[2].cap + ix.bkt[0].cap + ix.bkt[1].cap + ix.bkt[2].cap + ix.jwin.cap + ix.xw.cap + ix.lr.cap + ix.tok_start.cap + ix.RLP.cap + ix.L_tar.cap +
                                  ix.R_tar.cap + ix.tgt.cap + ix.freq_flag.cap + ix.gapw.cap + ix.lex_key.cap + ix.lex_v1.cap + ix.lex_v2.cap + ix.lex_hash.cap);
     return 0;
 }
@@ -255,7 +255,7 @@ extern "C" int cgx_index_commit(cgx_ctx_t *c) {
         CGX_REQUIRE(c, "null context");
         CUDA_CHECK(cudaSetDevice(c->device));
         build_lex_hash(c->ix, c->stream);          // derived from the (broadcast) sorted lexical arrays
-        build_jwin(c->ix, c->stream);              // derived from the (broadcast) bucket arrays and gap words
+        build_jwin(c->ix, c->stream);              // derived from the (broadcast) bucket arrays, gap words, text and alignment arrays
         c->ix.built = true;
     });
 }

@@ -115,7 +115,11 @@ static inline void fetch_async(Batch &b, void *dst, const void *src, size_t byte
     if (!bytes) return;
     CUDA_CHECK(cudaEventRecord(b.copy_ev, stream));
     CUDA_CHECK(cudaStreamWaitEvent(b.copy_stream, b.copy_ev, 0));
-    CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, b.copy_stream));
+    // In pieces: the D2H engine serves one copy at a time, and the 4-byte count read-backs of the NEXT batch (pipelined
+    // callers) would otherwise queue behind a 1.3 GB rule array and stall its kernels for the whole copy.
+    static const size_t piece = [] { const char *e = getenv("CGX_D2H_PIECE"); size_t v = e ? strtoull(e, nullptr, 10) : 0; return v ? v : (size_t)4 << 20; }();
+    for (size_t o = 0; o < bytes; o += piece)
+        CUDA_CHECK(cudaMemcpyAsync((char *)dst + o, (const char *)src + o, bytes - o < piece ? bytes - o : piece, cudaMemcpyDeviceToHost, b.copy_stream));
 }
 
 // current result arrays <-> a parked set (pointer swaps only)

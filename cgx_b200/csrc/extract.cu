@@ -24,20 +24,22 @@
 
 namespace cgx {
 
+// xw[k] = RLP[k] | 1 for a word (token >= 2), 0 at EOS / padding: the extension loops test "is a word" and read its aligned
+// span with ONE load (the reference reads str[k], then RLP[k]: two dependent random sectors); lr[j] = {L_tar[j], R_tar[j]}.
+// RLP itself is only read for the target offset stored at the previous EOS.
 struct ExtractIdx {
-    const int32_t *sa, *str;
-    const uint32_t *RLP;
-    const uint8_t *L_tar, *R_tar;
+    const int32_t *sa;
+    const uint32_t *xw, *RLP;
+    const uchar2 *lr;
     int n;
 };
-
-__device__ __forceinline__ unsigned rl(const ExtractIdx &x, int k) { return (__ldg(&x.RLP[k]) >> 24) & 0xFF; }
 
 // ExtractPair.cu:103-133 consistent
 __device__ __forceinline__ bool consistent(const ExtractIdx &x, int start, int end, int start_chk, int end_chk, int startpos_source) {
     unsigned mn = 255, mx = 0;
     for (int k = start; k <= end; k++) {
-        unsigned L = __ldg(&x.L_tar[k]), R = __ldg(&x.R_tar[k]);
+        const uchar2 v = __ldg(&x.lr[k]);
+        const unsigned L = v.x, R = v.y;
         if (L == 255 || R == 255) continue;
         mn = min(mn, L);
         mx = max(mx, R);
@@ -102,7 +104,7 @@ __global__ void __launch_bounds__(128) extract_contig_kernel(ExtractIdx x, const
     unsigned min_L_Xab = 255, max_R_Xab = 0, min_L_abX = 255, max_R_abX = 0, min_L_XabX = 255, max_R_XabX = 0;
 
     for (int k = current_str; k < current_str + longestmatch; k++) {
-        temp = __ldg(&x.RLP[k]);
+        temp = __ldg(&x.xw[k]);
         L = (temp >> 24) & 0xFF; R = (temp >> 16) & 0xFF;
         if (k == current_str) {
             tempind = k - (int)((temp >> 8) & 0xFF) - 1;
@@ -124,9 +126,9 @@ __global__ void __launch_bounds__(128) extract_contig_kernel(ExtractIdx x, const
 
     for (int i = 1; longestmatch + i <= SPAN && (abXNoSuccess || XabNoSuccess || XabX); i++) {
         // ---- X on the left: tokens current_str-i .. current_str-1 ----
-        if (Xab && current_str - i >= 0 && __ldg(&x.str[current_str - i]) >= 2) {
+        temp = (Xab && current_str - i >= 0) ? __ldg(&x.xw[current_str - i]) : 0u;
+        if (temp & 1u) {
             next = true;
-            temp = __ldg(&x.RLP[current_str - i]);
             L = (temp >> 24) & 0xFF; R = (temp >> 16) & 0xFF;
             if (L == 255 || R == 255) { next = false; if (i == 1) { Xab = false; XabX = false; } }
             else { min_L_Xab = min(min_L_Xab, L); max_R_Xab = max(max_R_Xab, R); }
@@ -149,9 +151,9 @@ __global__ void __launch_bounds__(128) extract_contig_kernel(ExtractIdx x, const
             }
         } else Xab = false;
         // ---- X on the right: tokens ender+1 .. ender+i ----
-        if (abX && __ldg(&x.str[ender + i]) >= 2) {
+        temp = abX ? __ldg(&x.xw[ender + i]) : 0u;
+        if (temp & 1u) {
             next = true;
-            temp = __ldg(&x.RLP[ender + i]);
             L = (temp >> 24) & 0xFF; R = (temp >> 16) & 0xFF;
             if (L == 255 || R == 255) { next = false; if (i == 1) { abX = false; XabX = false; } }
             else { min_L_abX = min(min_L_abX, L); max_R_abX = max(max_R_abX, R); }
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(128) extract_contig_kernel(ExtractIdx x, const
                 for (int icount = 1; XabX && icount <= abXCount; icount++) {
                     next = true;
                     if (icount + XabCount + longestmatch <= SPAN) {
-                        temp = __ldg(&x.RLP[ender + icount]);
+                        temp = __ldg(&x.xw[ender + icount]);
                         L = (temp >> 24) & 0xFF; R = (temp >> 16) & 0xFF;
                         if (L == 255 || R == 255) { next = false; if (i == 1) return; }
                         else { min_L_XabX = min(min_L_XabX, L); max_R_XabX = max(max_R_XabX, R); }
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(128) extract_contig_kernel(ExtractIdx x, const
                 for (int icount = 1; XabX && icount <= XabCount; icount++) {
                     next = true;
                     if (icount + abXCount + longestmatch <= SPAN) {
-                        temp = __ldg(&x.RLP[current_str - icount]);
+                        temp = __ldg(&x.xw[current_str - icount]);
                         L = (temp >> 24) & 0xFF; R = (temp >> 16) & 0xFF;
                         if (L == 255 || R == 255) { next = false; if (i == 1) return; }
                         else { min_L_XabX = min(min_L_XabX, L); max_R_XabX = max(max_R_XabX, R); }
@@ -250,7 +252,7 @@ __device__ __forceinline__ bool boundary_fast(const ExtractIdx &x, int start, in
     unsigned min_L = 255, max_R = 0;
     *sen_target_begin = -1; *tempind = 0;
     for (int k = start; k <= ender; k++) {
-        uint32_t w = __ldg(&x.RLP[k]);
+        uint32_t w = __ldg(&x.xw[k]);
         unsigned L = (w >> 24) & 0xFF, R = (w >> 16) & 0xFF;
         if ((L == 255 || R == 255) && (k == start || k == ender)) return false;
         if (L == 255 || R == 255) continue;
@@ -270,7 +272,7 @@ __device__ __forceinline__ int check_boundary(const ExtractIdx &x, int start, in
     unsigned min_L = 255, max_R = 0;
     int sen_target_begin = -1, tempind = 0, wrong = 0;
     for (int k = start; k <= ender; k++) {
-        uint32_t w = __ldg(&x.RLP[k]);
+        uint32_t w = __ldg(&x.xw[k]);
         unsigned L = (w >> 24) & 0xFF, R = (w >> 16) & 0xFF;
         bool un = (L == 255 || R == 255);
         if (k == start) {
@@ -335,9 +337,9 @@ __global__ void __launch_bounds__(128) extract_onegap_kernel(ExtractIdx x, const
     const unsigned originalGapStart = gap1_start, originalGapEnd = gap1_end;
     unsigned min_XaXb = 255, max_XaXb = 0, min_aXbX = 255, max_aXbX = 0, L, R, temp;
     for (int i = 1; firstEnd + 1 + i <= SPAN && (left || right); i++) {
-        if (left && current_str - i >= 0 && __ldg(&x.str[current_str - i]) >= 2) {
+        temp = (left && current_str - i >= 0) ? __ldg(&x.xw[current_str - i]) : 0u;
+        if (temp & 1u) {
             next = true;
-            temp = __ldg(&x.RLP[current_str - i]);
             L = (temp >> 24) & 0xFF; R = (temp >> 16) & 0xFF;
             if (L == 255 || R == 255) { next = false; if (i == 1) left = false; }
             else { min_XaXb = min(min_XaXb, L); max_XaXb = max(max_XaXb, R); }
@@ -359,9 +361,9 @@ __global__ void __launch_bounds__(128) extract_onegap_kernel(ExtractIdx x, const
                 left = false;
             }
         } else left = false;
-        if (right && __ldg(&x.str[ender + i]) >= 2) {
+        temp = right ? __ldg(&x.xw[ender + i]) : 0u;
+        if (temp & 1u) {
             next = true;
-            temp = __ldg(&x.RLP[ender + i]);
             L = (temp >> 24) & 0xFF; R = (temp >> 16) & 0xFF;
             if (L == 255 || R == 255) { next = false; if (i == 1) right = false; }
             else { min_aXbX = min(min_aXbX, L); max_aXbX = max(max_aXbX, R); }
@@ -425,7 +427,7 @@ void stage_extract(const Index &ix, Batch &b, cudaStream_t stream) {
     b.n_slots[0] = b.n_slots[1] = b.n_slots[2] = 0;
     b.samples = 0;
     if (G == 0) return;
-    ExtractIdx x{ix.sa.ptr<int32_t>(), ix.str.ptr<int32_t>(), ix.RLP.ptr<uint32_t>(), ix.L_tar.ptr<uint8_t>(), ix.R_tar.ptr<uint8_t>(), (int)ix.n};
+    ExtractIdx x{ix.sa.ptr<int32_t>(), ix.xw.ptr<uint32_t>(), ix.RLP.ptr<uint32_t>(), ix.lr.ptr<uchar2>(), (int)ix.n};
     uint32_t *tot = b.counters.get<uint32_t>(32);
     // slot offsets: G+1 / D1+1 / D2+1 entries (the last one = total), also read by the aggregation
     uint32_t *so0 = b.slot_off[0].get<uint32_t>((size_t)G + 2);

@@ -89,9 +89,21 @@ __global__ void ix_jwin_kernel(const int32_t *__restrict__ b1, const int32_t *__
     if (p < n) jwin[p] = make_int4(b1[p], b2[p], b3[p], (int)gapw[p]);
 }
 
+// extraction views: xw[k] = RLP[k] | 1 where the source token is a word (>= 2), else 0 (EOS, padding; n+3 entries like str);
+// lr[j] = {L_tar[j], R_tar[j]}.  The window loops of extract.cu then touch one array per side instead of two.
+__global__ void ix_extract_views_kernel(const int32_t *__restrict__ str, const uint32_t *__restrict__ RLP, size_t n, const uint8_t *__restrict__ L_tar,
+                                        const uint8_t *__restrict__ R_tar, size_t m, uint32_t *__restrict__ xw, uchar2 *__restrict__ lr) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n + 3) xw[i] = (i < n && str[i] >= 2) ? (RLP[i] | 1u) : 0u;
+    if (i < m) lr[i] = make_uchar2(L_tar[i], R_tar[i]);
+}
+
 void build_jwin(Index &ix, cudaStream_t stream) {
     ix_jwin_kernel<<<cgx_div_up(ix.n, 256), 256, 0, stream>>>(ix.bkt[0].ptr<int32_t>(), ix.bkt[1].ptr<int32_t>(), ix.bkt[2].ptr<int32_t>(),
                                                             ix.gapw.ptr<uint32_t>(), ix.n, ix.jwin.get<int4>(ix.n));
+    const size_t cnt = ix.n + 3 > ix.m ? ix.n + 3 : ix.m;
+    ix_extract_views_kernel<<<cgx_div_up(cnt, 256), 256, 0, stream>>>(ix.str.ptr<int32_t>(), ix.RLP.ptr<uint32_t>(), ix.n, ix.L_tar.ptr<uint8_t>(),
+                                                                     ix.R_tar.ptr<uint8_t>(), ix.m, ix.xw.get<uint32_t>(ix.n + 3), ix.lr.get<uchar2>(ix.m));
     CUDA_CHECK(cudaStreamSynchronize(stream));
 }
 

@@ -34,6 +34,7 @@
 #include "batch.h"
 #include "hash.cuh"
 #include "prof.h"
+#include <utility>
 
 namespace cgx {
 
@@ -425,8 +426,9 @@ void stage_onegap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     // The sort is stable and hits of one (pattern, position) leave the scan in ascending length (one stage_push, lane = gap
     // width), so sorting on (pattern, position) alone yields (pattern, position, length) order: the 4 length bits are skipped.
     radix_sort<uint64_t>(hits, tmp, nullptr, nullptr, H, 4, b.pbits + 4 + cgx_bits_for((uint64_t)D1), stream, b.radix, &hs, nullptr, &b.launches);
-    uint64_t *dst = b.hits1_sorted.get<uint64_t>(H);
-    CUDA_CHECK(cudaMemcpyAsync(dst, hs, sizeof(uint64_t) * H, cudaMemcpyDeviceToDevice, stream));
+    // the buffer the sort ended in becomes hits1_sorted (buffers rotate instead of a 16 B/hit copy)
+    std::swap(b.hits1_sorted, hs == hits ? b.hit_keys : b.hit_keys_tmp);
+    uint64_t *dst = b.hits1_sorted.ptr<uint64_t>();
     static_assert(sizeof(Pat1) == 32, "Pat1 layout");
     hit_ranges_kernel<<<cgx_div_up(H, 256), 256, 0, stream>>>(dst, H, b.pbits + 4, &b.pat1.ptr<int32_t>()[4], 8);
     hit_ranges_fix_kernel<<<cgx_div_up(D1, 256), 256, 0, stream>>>(&b.pat1.ptr<int32_t>()[4], D1, 8);
@@ -534,8 +536,8 @@ void stage_twogap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     uint64_t *tmp = b.hit_keys_tmp.get<uint64_t>(H);
     uint64_t *hs;
     radix_sort<uint64_t>(hits, tmp, nullptr, nullptr, H, 0, b.pbits + 8 + cgx_bits_for((uint64_t)D2), stream, b.radix, &hs, nullptr, &b.launches);
-    uint64_t *dst = b.hits2_sorted.get<uint64_t>(H);
-    CUDA_CHECK(cudaMemcpyAsync(dst, hs, sizeof(uint64_t) * H, cudaMemcpyDeviceToDevice, stream));
+    std::swap(b.hits2_sorted, hs == hits ? b.hit_keys : b.hit_keys_tmp);
+    uint64_t *dst = b.hits2_sorted.ptr<uint64_t>();
     static_assert(sizeof(Pat2) == 16, "Pat2 layout");
     hit_ranges_kernel<<<cgx_div_up(H, 256), 256, 0, stream>>>(dst, H, b.pbits + 8, &b.pat2.ptr<int32_t>()[2], 4);
     hit_ranges_fix_kernel<<<cgx_div_up(D2, 256), 256, 0, stream>>>(&b.pat2.ptr<int32_t>()[2], D2, 4);

@@ -300,7 +300,13 @@ def test_oversized_batches_are_split(micro, micro_files, tmp_path, monkeypatch):
     off, tok = lay["qry_off"], lay["qry_tok"]
     full = ex.extract(tok, off)
     want = [sorted(full.grammar_lines(q, lay)) for q in range(full.Q)]
-    limit = max(int(full.info["hits1"]), int(full.info["hits2"])) // 3
+    single = 0                                               # the largest single query must still fit
+    for q in range(full.Q):
+        i = ex.extract(tok[off[q]:off[q + 1]], off[q:q + 2] - off[q], fetch=False)
+        single = max(single, int(i["hits1"]), int(i["hits2"]))
+    total = max(int(full.info["hits1"]), int(full.info["hits2"]))
+    limit = max(single + 1, total // 3)
+    assert limit < total
     monkeypatch.setenv("CGX_HIT_LIMIT", str(limit))
     assert ex.L.cgx_extract(ex.h, tok.ctypes.data_as(C.POINTER(C.c_int32)), np.ascontiguousarray(off, dtype=np.int32).ctypes.data_as(C.POINTER(C.c_int32)), full.Q) == 3
     got = {}
