@@ -309,8 +309,7 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
             exclusive_scan_u32(flags, flags, N, tot, stream, b.scan, 0, &b.launches);
             b.launches += 2;
             uint32_t hostv[20];
-            CUDA_CHECK(cudaMemcpyAsync(hostv, tot, sizeof(hostv), cudaMemcpyDeviceToHost, stream));
-            CUDA_CHECK(cudaStreamSynchronize(stream));
+            cgx_read_back(hostv, tot, sizeof(hostv), stream);
             if (hostv[14] == 0) {
                 R = hostv[0];
                 const unsigned long long nr = hostv[16];

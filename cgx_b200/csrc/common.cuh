@@ -126,6 +126,24 @@ __device__ __forceinline__ unsigned lanemask_lt() {
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
     return m;
 }
+// Small device -> host read-back (counts the host needs to size the next stage) that stays off the copy engines: one warp
+// stores the words into mapped pinned memory, the stream is synchronised, the host reads them.  A cudaMemcpyAsync D2H
+// would queue in the D2H engine behind whatever result array of the previous batch is still travelling (FIFO per
+// engine, 1.3 GB = 25-50 ms) and stall a pipelined batch at every count (cgx_extract_begin).
+static __global__ void cgx_mailbox_kernel(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, int words) {
+    const int i = threadIdx.x;
+    if (i < words) dst[i] = src[i];
+}
+static inline void cgx_read_back(void *host_dst, const void *dev_src, size_t bytes, cudaStream_t stream) {
+    thread_local uint32_t *box = nullptr;                 // one mailbox per host thread (one thread drives one GPU)
+    constexpr int WORDS = 64;
+    if (!box) CUDA_CHECK(cudaHostAlloc((void **)&box, WORDS * sizeof(uint32_t), cudaHostAllocPortable | cudaHostAllocMapped));
+    if (bytes % 4 != 0 || bytes > WORDS * sizeof(uint32_t)) throw CgxError{"cgx_read_back: unsupported size"};
+    cgx_mailbox_kernel<<<1, WORDS, 0, stream>>>(box, (const uint32_t *)dev_src, (int)(bytes / 4));
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    memcpy(host_dst, box, bytes);
+}
+
 // streaming (read-once) 128-bit load that does not pollute L1
 __device__ __forceinline__ int4 ld_nc_int4(const int4 *p) {
     int4 r;

@@ -446,8 +446,7 @@ void stage_extract(const Index &ix, Batch &b, cudaStream_t stream) {
         CUDA_CHECK(cudaMemcpyAsync(so2 + D2, tot + 2, sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
     }
     uint32_t ns[3] = {0, 0, 0};
-    CUDA_CHECK(cudaMemcpyAsync(ns, tot, sizeof(uint32_t) * 3, cudaMemcpyDeviceToHost, stream));
-    CUDA_CHECK(cudaStreamSynchronize(stream));
+    cgx_read_back(ns, tot, sizeof(uint32_t) * 3, stream);
     if (!D1) ns[1] = 0;
     if (!D2) ns[2] = 0;
     b.launches += 3;

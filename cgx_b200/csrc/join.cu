@@ -347,8 +347,7 @@ static unsigned long long hit_limit() {
 }
 
 static void read_u64s(unsigned long long *dst, const unsigned long long *d, int count, cudaStream_t stream) {
-    CUDA_CHECK(cudaMemcpyAsync(dst, d, sizeof(unsigned long long) * count, cudaMemcpyDeviceToHost, stream));
-    CUDA_CHECK(cudaStreamSynchronize(stream));
+    cgx_read_back(dst, d, sizeof(unsigned long long) * count, stream);
 }
 
 static void prof_add_bytes(const char *name, double bytes) {
@@ -380,8 +379,7 @@ void stage_onegap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     exclusive_scan_u32(eoff, eoff, (size_t)G, tot, stream, b.scan, 0, &b.launches);
     b.launches += 2;
     uint32_t n_elems = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&n_elems, tot, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    CUDA_CHECK(cudaStreamSynchronize(stream));
+    cgx_read_back(&n_elems, tot, sizeof(uint32_t), stream);
     int32_t *missing = b.missing.get<int32_t>((size_t)D1);
     if (b.hit_cap == 0) b.hit_cap = 1u << 22;
     J1Args a;

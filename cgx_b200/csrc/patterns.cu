@@ -29,8 +29,7 @@ __global__ void head_flags_u64_kernel(const uint64_t *__restrict__ keys, size_t 
 
 static uint32_t read_u32(const uint32_t *d, cudaStream_t stream) {
     uint32_t v = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&v, d, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    CUDA_CHECK(cudaStreamSynchronize(stream));
+    cgx_read_back(&v, d, sizeof(uint32_t), stream);
     return v;
 }
 

@@ -72,8 +72,7 @@ void build_suffix_array(const int32_t *d_str, size_t n, int32_t maxtok, int32_t 
         sa_head_flags_kernel<<<grid, 256, 0, stream>>>(ks, n, flags);
         exclusive_scan_u32(flags, flags, n, d_total, stream, ws.scan, 0, &launches);
         uint32_t distinct = 0;
-        CUDA_CHECK(cudaMemcpyAsync(&distinct, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-        CUDA_CHECK(cudaStreamSynchronize(stream));
+        cgx_read_back(&distinct, d_total, sizeof(uint32_t), stream);
         launches += 1;
         if ((size_t)distinct == n) break;
         CGX_REQUIRE(h < 2 * n, "suffix array: did not converge (text without a unique final symbol?)");
