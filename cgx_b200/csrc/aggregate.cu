@@ -95,14 +95,38 @@ __global__ void agg_hash_kernel(const RuleRec *__restrict__ rec, uint32_t cells,
     }
 }
 
+// next target symbol of a record from span offset j on (tokens outside the gaps, gap1 -> 0xFFFFFFFF, gap2 -> 0xFFFFFFFE);
+// returns false past the end.  Same walk as target_symbols(), without the symbol array.
+__device__ __forceinline__ bool next_symbol(const int32_t *__restrict__ tgt, const RuleRec &r, int &j, uint32_t &sym) {
+    if (j > (int)r.end) return false;
+    if (r.gap1 != 255 && j >= (int)r.gap1 && j <= (int)r.gap1_1) { sym = 0xFFFFFFFFu; j = (int)r.gap1_1 + 1; }
+    else if (r.gap2 != 255 && j >= (int)r.gap2 && j <= (int)r.gap2_1) { sym = 0xFFFFFFFEu; j = (int)r.gap2_1 + 1; }
+    else { sym = (uint32_t)__ldg(&tgt[r.tgt_start + j]); j++; }
+    return true;
+}
+__device__ __forceinline__ bool same_target(const int32_t *__restrict__ tgt, const RuleRec &x, const RuleRec &y) {
+    int jx = 0, jy = 0;
+    while (true) {
+        uint32_t sx = 0, sy = 0;
+        const bool hx = next_symbol(tgt, x, jx, sx), hy = next_symbol(tgt, y, jy, sy);
+        if (hx != hy) return false;
+        if (!hx) return true;
+        if (sx != sy) return false;
+    }
+}
+
 // One thread per cell: group the records of its segment (= the cells of its source id) by target sequence.
-//   flags[i] = 1 when cell i is the first cell of its rule; meta[i] = {representative cell, paircount | f << 16} for heads
-//   (f = records of the id = non-empty cells of the segment).
-// A record that finds an equal cell before itself is not a head and stops there; heads scan the rest of the segment
-// for their paircount.  The loops read the 4-byte tags (the segment is shared by the neighbouring threads: L1 broadcast).
+//   flags[i] = 1 when cell i is the first cell of its rule (no equal cell before it in the segment).
+//   Every record then reports to its rule head h (itself for a head) with two commutative atomics:
+//     acc_cnt[h]  += 1 per non-head member  (+ f << 16 by the head: f = records of the id = non-empty cells of the segment)
+//     acc_best[h]  = min(tgt_start << 32 | cell)   -> the representative = member with the smallest target start
+//   so heads need no forward scan of the segment for their paircount (round 1b: heads, 60 % of the records, scanned the
+//   whole segment twice; 8 of 32 lanes active on average).  The backward scan reads the 4-byte tags (shared with the
+//   neighbouring threads: L1 broadcast) four at a time and stops at the first equal cell.
 __global__ void __launch_bounds__(256) agg_group_kernel(AggLayout lay, const RuleRec *__restrict__ rec, const uint64_t *__restrict__ hash,
                                                         const uint32_t *__restrict__ tag, const uint32_t *__restrict__ live_before,
-                                                        const int32_t *__restrict__ tgt, uint32_t *__restrict__ flags, uint2 *__restrict__ meta,
+                                                        const int32_t *__restrict__ tgt, uint32_t *__restrict__ flags,
+                                                        unsigned long long *__restrict__ acc_best, uint32_t *__restrict__ acc_cnt,
                                                         int *__restrict__ collision) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= lay.cells) return;
@@ -114,8 +138,8 @@ __global__ void __launch_bounds__(256) agg_group_kernel(AggLayout lay, const Rul
 #pragma unroll
     for (int k = 1; k < 4; k++) if (k < lay.n_regions && i >= lay.r[k].base) reg = k;
     const uint32_t pat = (uint32_t)(r.id - lay.r[reg].id_base);
-    const uint32_t s0 = lay.r[reg].base + __ldg(&lay.r[reg].slot_off[pat]), s1 = lay.r[reg].base + __ldg(&lay.r[reg].slot_off[pat + 1]);
-    // the tags are scanned four at a time (aligned 16-byte loads; cells outside [lo, hi) are masked by position)
+    const uint32_t s0 = lay.r[reg].base + __ldg(&lay.r[reg].slot_off[pat]);
+    // the tags are scanned four at a time (aligned 16-byte loads; cells outside [s0, i) are masked by position)
     uint32_t first = i;
     for (uint32_t base = s0 & ~3u; base < i && first == i; base += 4) {
         const uint4 t4 = __ldg(reinterpret_cast<const uint4 *>(tag + base));
@@ -126,33 +150,18 @@ __global__ void __launch_bounds__(256) agg_group_kernel(AggLayout lay, const Rul
             if (tt[k] == t && j >= s0 && j < i && first == i && __ldg(&hash[j]) == h) first = j;
         }
     }
+    const unsigned long long key = ((unsigned long long)(uint32_t)r.tgt_start << 32) | (unsigned long long)i;
+    atomicMin(&acc_best[first], key);
     if (first == i) {
-        uint32_t best = i, cnt = 1;
-        int best_ts = r.tgt_start;
-        for (uint32_t base = (i + 1) & ~3u; base < s1; base += 4) {
-            const uint4 t4 = __ldg(reinterpret_cast<const uint4 *>(tag + base));
-            const uint32_t tt[4] = {t4.x, t4.y, t4.z, t4.w};
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uint32_t j = base + k;
-                if (tt[k] == t && j > i && j < s1 && __ldg(&hash[j]) == h) {
-                    cnt++;
-                    const int tsj = __ldg(&rec[j].tgt_start);
-                    if (tsj < best_ts) { best = j; best_ts = tsj; }
-                }
-            }
-        }
+        const uint32_t s1 = lay.r[reg].base + __ldg(&lay.r[reg].slot_off[pat + 1]);
         const uint32_t f = __ldg(&live_before[s1]) - __ldg(&live_before[s0]);      // records of the id = non-empty cells of the segment
         flags[i] = 1;
-        meta[i] = make_uint2(best, cnt | (f << 16));
+        atomicAdd(&acc_cnt[i], f << 16);
     } else {
         flags[i] = 0;
+        atomicAdd(&acc_cnt[first], 1u);
         const RuleRec q = rec[first];
-        uint32_t a[16], c[16];
-        const int na = target_symbols(tgt, r, a), nc = target_symbols(tgt, q, c);
-        bool same = na == nc;
-        for (int k = 0; same && k < na; k++) same = a[k] == c[k];
-        if (!same) atomicExch(collision, 1);
+        if (!same_target(tgt, r, q)) atomicExch(collision, 1);
     }
 }
 
@@ -204,20 +213,22 @@ __global__ void agg_head_cell_kernel(const uint32_t *__restrict__ excl, uint32_t
 
 // One thread per distinct rule: paircount, f, fs, representative record, lexical weights.  (One thread per CELL with the
 // heads writing their rule keeps the reads streaming but leaves 73 % of the lanes idle in the probe-heavy part: 2x slower.)
-__global__ void __launch_bounds__(128) agg_rules_kernel(AggIdx a, int kind, const RuleRec *__restrict__ rec, const uint32_t *__restrict__ head_cell,
-                                                        const uint2 *__restrict__ meta, uint32_t n_rules,
+template <bool PRELOAD>
+__global__ void __launch_bounds__(128, PRELOAD ? 5 : 6) agg_rules_kernel(AggIdx a, int kind, const RuleRec *__restrict__ rec, const uint32_t *__restrict__ head_cell,
+                                                        const unsigned long long *__restrict__ acc_best, const uint32_t *__restrict__ acc_cnt, uint32_t n_rules,
                                                         const ulonglong2 *__restrict__ lex, uint32_t lex_mask, cgx_rule_t *__restrict__ rules) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rules) return;
-    const uint2 mt = meta[head_cell[r]];
-    const RuleRec best = rec[mt.x];
-    const int pc = (int)(mt.y & 0xffffu);
+    const uint32_t hc = head_cell[r];
+    const uint32_t cw = acc_cnt[hc];                                     // members - 1 | f << 16
+    const RuleRec best = rec[(uint32_t)acc_best[hc]];                    // low word of min(tgt_start << 32 | cell)
+    const int pc = (int)(cw & 0xffffu) + 1;
     cgx_rule_t out;
     out.id = best.id; out.tgt_start = best.tgt_start; out.end = best.end;
     out.gap1 = best.gap1; out.gap1_1 = best.gap1_1; out.gap2 = best.gap2; out.gap2_1 = best.gap2_1;
     out.pad = 0;
     out.pc = (uint16_t)pc;
-    out.f = (uint16_t)(mt.y >> 16);
+    out.f = (uint16_t)(cw >> 16);
     int fs = fsample_of(a, kind, best.id);
     out.fs = (uint16_t)(fs > CGX_SAMPLER ? CGX_SAMPLER : fs);                          // ExtractPair.c:638,910,1249
     // ---- lexicalTaskMaxEF (ExtractPair.cu:2144-2432): for every source terminal the best MaxLexFgivenE over the target
@@ -225,35 +236,64 @@ __global__ void __launch_bounds__(128) agg_rules_kernel(AggIdx a, int kind, cons
     // table probe serves both directions of a (f, e) pair.
     int32_t F[8];
     const int nf = source_terminals(a, kind, best.id, F);
-    float mxf[8];
+    float mxf[5];
 #pragma unroll
-    for (int j = 0; j < 8; j++) mxf[j] = 0.f;
-    float egivenf = 0.f, v1, v2;
+    for (int j = 0; j < 5; j++) mxf[j] = 0.f;
+    float egivenf = 0.f;
     bool any_e = false;
     const int ts = best.tgt_start;
-    for (int jj = 0; jj <= (int)best.end; jj++) {
+    uint32_t tok[PRELOAD ? 15 : 1];                     // PRELOAD: the span is <= 15 tokens, every load issued before any is used
+    if (PRELOAD) {
+#pragma unroll
+        for (int j = 0; j < 15; j++) tok[j] = j <= (int)best.end ? (uint32_t)__ldg(&a.tgt[ts + j]) : 0u;
+    }
+    uint32_t e_next = PRELOAD ? 0u : (uint32_t)__ldg(&a.tgt[ts]);
+    // keys of one target terminal: slot 0 = (NULL, e), slot 1+j = (F[j], e); the first table slots of all of them are
+    // loaded back to back (ht_first), then resolved -- one L2 round trip per target terminal instead of nf + 1
+    uint64_t fkey[6];
+    fkey[0] = 0;                                        // f = -1 -> (f + 1) = 0
+#pragma unroll
+    for (int j = 0; j < 5; j++) fkey[1 + j] = j < nf ? ((uint64_t)(uint32_t)(F[j] + 1) << 32) : 0ull;
+#pragma unroll(PRELOAD ? 15 : 1)
+    for (int jj = 0; jj < 15; jj++) {
+        if (jj > (int)best.end) break;
+        const uint32_t e_cur = PRELOAD ? tok[PRELOAD ? jj : 0] : e_next;
+        if (!PRELOAD && jj < (int)best.end) e_next = (uint32_t)__ldg(&a.tgt[ts + jj + 1]);      // the next token travels while this one is probed
         if (best.gap1 != 255 && jj >= (int)best.gap1 && jj <= (int)best.gap1_1) continue;
         if (best.gap2 != 255 && jj >= (int)best.gap2 && jj <= (int)best.gap2_1) continue;
         any_e = true;
-        const int e = __ldg(&a.tgt[ts + jj]);
-        float mx = 0.f;
-        if (nf > 0) { lex_get(lex, lex_mask, -1, e, &v1, &v2); mx = fmaxf(mx, v1); }
+        if (nf == 0) { egivenf += CGX_MAXSCORE; continue; }
+        const uint64_t ek = (uint64_t)(e_cur + 1u);
+        ulonglong2 sv[6];
+        uint32_t ss[6];
 #pragma unroll
-        for (int j = 0; j < 5; j++) {                                       // nf <= 5 (CGX_LONGEST_SRC / MAX_rule_symbols)
-            if (j >= nf) break;
-            lex_get(lex, lex_mask, F[j], e, &v1, &v2);
-            mx = fmaxf(mx, v1);
-            mxf[j] = fmaxf(mxf[j], v2);
+        for (int u = 0; u < 6; u++) if (u <= nf) sv[u] = ht_first(lex, lex_mask, fkey[u] | ek, &ss[u]);
+        float mx = 0.f;
+#pragma unroll
+        for (int u = 0; u < 6; u++) {
+            if (u > nf) break;
+            uint64_t pay;
+            if (ht_resolve(lex, lex_mask, fkey[u] | ek, ss[u], sv[u], &pay)) {
+                mx = fmaxf(mx, __uint_as_float((uint32_t)pay));                                   // v1 -> MaxLexEgivenF
+                if (u > 0) mxf[u - 1] = fmaxf(mxf[u - 1], __uint_as_float((uint32_t)(pay >> 32)));   // v2 -> MaxLexFgivenE
+            }
         }
         egivenf += mx > 0.f ? -__log10f(mx) : CGX_MAXSCORE;
     }
     float fgivene = 0.f;
+    {   // (F[j], NULL) for every source terminal, again issued together
+        ulonglong2 sv[5];
+        uint32_t ss[5];
 #pragma unroll
-    for (int j = 0; j < 5; j++) {
-        if (j >= nf) break;
-        float mx = mxf[j];
-        if (any_e) { lex_get(lex, lex_mask, F[j], -1, &v1, &v2); mx = fmaxf(mx, v2); }
-        fgivene += mx > 0.f ? -__log10f(mx) : CGX_MAXSCORE;
+        for (int j = 0; j < 5; j++) if (j < nf && any_e) sv[j] = ht_first(lex, lex_mask, fkey[1 + j], &ss[j]);      // e = -1 -> (e + 1) = 0
+#pragma unroll
+        for (int j = 0; j < 5; j++) {
+            if (j >= nf) break;
+            float mx = mxf[j];
+            uint64_t pay;
+            if (any_e && ht_resolve(lex, lex_mask, fkey[1 + j], ss[j], sv[j], &pay)) mx = fmaxf(mx, __uint_as_float((uint32_t)(pay >> 32)));
+            fgivene += mx > 0.f ? -__log10f(mx) : CGX_MAXSCORE;
+        }
     }
     out.max_lex_f_given_e = fgivene;
     out.max_lex_e_given_f = egivenf;
@@ -294,7 +334,8 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
         const RuleRec *rec = b.rec[kind].ptr<RuleRec>();
         uint64_t *hash = b.rec_hash.get<uint64_t>((size_t)N);
         uint32_t *flags = b.rec_flags.get<uint32_t>((size_t)N + 2);
-        uint2 *meta = b.rec_meta.get<uint2>((size_t)N);
+        unsigned long long *acc_best = b.rec_meta.get<unsigned long long>((size_t)N);
+        uint32_t *acc_cnt = b.rec_cnt.get<uint32_t>((size_t)N);
         uint32_t *tag = b.rec_tag.get<uint32_t>((size_t)N + 8);
         uint32_t *live = b.rec_live.get<uint32_t>((size_t)N + 2);
         int32_t *updown = b.updown[kind].get<int32_t>((size_t)2 * nids[kind]);
@@ -302,10 +343,12 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
         uint32_t R = 0;
         for (int attempt = 0; attempt < 8; attempt++, seed = seed * 6364136223846793005ULL + 1442695040888963407ULL) {
             CUDA_CHECK(cudaMemsetAsync(collision, 0, sizeof(int), stream));
+            CUDA_CHECK(cudaMemsetAsync(acc_best, 0xff, sizeof(unsigned long long) * (size_t)N, stream));
+            CUDA_CHECK(cudaMemsetAsync(acc_cnt, 0, sizeof(uint32_t) * (size_t)N, stream));
             PROF("agg_hash", (double)N * 32, (agg_hash_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(rec, N, ix.tgt.ptr<int32_t>(), seed, hash, tag, live)));
             exclusive_scan_u32(live, live, N, tot + 16, stream, b.scan, 0, &b.launches);          // live[N] = total below
             CUDA_CHECK(cudaMemcpyAsync(live + N, tot + 16, sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
-            PROF("agg_group", (double)N * (8 + 4), (agg_group_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(lay[kind], rec, hash, tag, live, ix.tgt.ptr<int32_t>(), flags, meta, collision)));
+            PROF("agg_group", (double)N * (8 + 4), (agg_group_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(lay[kind], rec, hash, tag, live, ix.tgt.ptr<int32_t>(), flags, acc_best, acc_cnt, collision)));
             exclusive_scan_u32(flags, flags, N, tot, stream, b.scan, 0, &b.launches);
             b.launches += 2;
             uint32_t hostv[20];
@@ -322,7 +365,12 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
                 cgx_rule_t *rules = b.rules[kind].get<cgx_rule_t>(R);
                 uint32_t *head_cell = b.rule_head.get<uint32_t>((size_t)R + 2);
                 agg_head_cell_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(flags, N, R, head_cell);
-                PROF("agg_rules", (double)R * (4 + 8 + 16 + 28) + (double)R * 13 * 16, (agg_rules_kernel<<<cgx_div_up(R, 128), 128, 0, stream>>>(a, kind, rec, head_cell, meta, R,
+                static const bool preload = [] { const char *e = getenv("CGX_AGG_PRELOAD"); return e && e[0] == '1'; }();
+                if (preload)
+                    PROF("agg_rules", (double)R * (4 + 8 + 16 + 28) + (double)R * 13 * 16, (agg_rules_kernel<true><<<cgx_div_up(R, 128), 128, 0, stream>>>(a, kind, rec, head_cell, acc_best, acc_cnt, R,
+                                                                       ix.lex_hash.ptr<ulonglong2>(), ix.lex_hash_mask, rules)));
+                else
+                    PROF("agg_rules", (double)R * (4 + 8 + 16 + 28) + (double)R * 13 * 16, (agg_rules_kernel<false><<<cgx_div_up(R, 128), 128, 0, stream>>>(a, kind, rec, head_cell, acc_best, acc_cnt, R,
                                                                        ix.lex_hash.ptr<ulonglong2>(), ix.lex_hash_mask, rules)));
                 CUDA_CHECK(cudaMemsetAsync(updown, 0xff, sizeof(int32_t) * 2 * (size_t)nids[kind], stream));
                 agg_updown_kernel<<<cgx_div_up(R, 256), 256, 0, stream>>>(rules, R, updown);
