@@ -95,16 +95,23 @@ __global__ void agg_hash_kernel(const RuleRec *__restrict__ rec, uint32_t cells,
     }
 }
 
-// next target symbol of a record from span offset j on (tokens outside the gaps, gap1 -> 0xFFFFFFFF, gap2 -> 0xFFFFFFFE);
-// returns false past the end.  Same walk as target_symbols(), without the symbol array.
-__device__ __forceinline__ bool next_symbol(const int32_t *__restrict__ tgt, const RuleRec &r, int &j, uint32_t &sym) {
-    if (j > (int)r.end) return false;
-    if (r.gap1 != 255 && j >= (int)r.gap1 && j <= (int)r.gap1_1) { sym = 0xFFFFFFFFu; j = (int)r.gap1_1 + 1; }
-    else if (r.gap2 != 255 && j >= (int)r.gap2 && j <= (int)r.gap2_1) { sym = 0xFFFFFFFEu; j = (int)r.gap2_1 + 1; }
-    else { sym = (uint32_t)__ldg(&tgt[r.tgt_start + j]); j++; }
+// target side of a record, unpacked to scalars (byte fields of a by-reference RuleRec end up in local memory)
+struct TgtSpan {
+    int ts, end, g1, g1e, g2, g2e;       // g1 / g2 = -1 when the gap is absent
+    __device__ __forceinline__ explicit TgtSpan(const RuleRec &r)
+        : ts(r.tgt_start), end(r.end), g1(r.gap1 == 255 ? -1 : (int)r.gap1), g1e(r.gap1_1), g2(r.gap2 == 255 ? -1 : (int)r.gap2), g2e(r.gap2_1) {}
+};
+// next target symbol from span offset j on (tokens outside the gaps, gap1 -> 0xFFFFFFFF, gap2 -> 0xFFFFFFFE); false past the end.
+// Same walk as target_symbols(), without the symbol array.
+__device__ __forceinline__ bool next_symbol(const int32_t *__restrict__ tgt, const TgtSpan &r, int &j, uint32_t &sym) {
+    if (j > r.end) return false;
+    if (r.g1 >= 0 && j >= r.g1 && j <= r.g1e) { sym = 0xFFFFFFFFu; j = r.g1e + 1; }
+    else if (r.g2 >= 0 && j >= r.g2 && j <= r.g2e) { sym = 0xFFFFFFFEu; j = r.g2e + 1; }
+    else { sym = (uint32_t)__ldg(&tgt[r.ts + j]); j++; }
     return true;
 }
-__device__ __forceinline__ bool same_target(const int32_t *__restrict__ tgt, const RuleRec &x, const RuleRec &y) {
+__device__ __forceinline__ bool same_target(const int32_t *__restrict__ tgt, const RuleRec &rx, const RuleRec &ry) {
+    const TgtSpan x(rx), y(ry);
     int jx = 0, jy = 0;
     while (true) {
         uint32_t sx = 0, sy = 0;
@@ -213,8 +220,7 @@ __global__ void agg_head_cell_kernel(const uint32_t *__restrict__ excl, uint32_t
 
 // One thread per distinct rule: paircount, f, fs, representative record, lexical weights.  (One thread per CELL with the
 // heads writing their rule keeps the reads streaming but leaves 73 % of the lanes idle in the probe-heavy part: 2x slower.)
-template <bool PRELOAD>
-__global__ void __launch_bounds__(128, PRELOAD ? 5 : 6) agg_rules_kernel(AggIdx a, int kind, const RuleRec *__restrict__ rec, const uint32_t *__restrict__ head_cell,
+__global__ void __launch_bounds__(128) agg_rules_kernel(AggIdx a, int kind, const RuleRec *__restrict__ rec, const uint32_t *__restrict__ head_cell,
                                                         const unsigned long long *__restrict__ acc_best, const uint32_t *__restrict__ acc_cnt, uint32_t n_rules,
                                                         const ulonglong2 *__restrict__ lex, uint32_t lex_mask, cgx_rule_t *__restrict__ rules) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -236,64 +242,35 @@ __global__ void __launch_bounds__(128, PRELOAD ? 5 : 6) agg_rules_kernel(AggIdx 
     // table probe serves both directions of a (f, e) pair.
     int32_t F[8];
     const int nf = source_terminals(a, kind, best.id, F);
-    float mxf[5];
+    float mxf[8];
 #pragma unroll
-    for (int j = 0; j < 5; j++) mxf[j] = 0.f;
-    float egivenf = 0.f;
+    for (int j = 0; j < 8; j++) mxf[j] = 0.f;
+    float egivenf = 0.f, v1, v2;
     bool any_e = false;
     const int ts = best.tgt_start;
-    uint32_t tok[PRELOAD ? 15 : 1];                     // PRELOAD: the span is <= 15 tokens, every load issued before any is used
-    if (PRELOAD) {
-#pragma unroll
-        for (int j = 0; j < 15; j++) tok[j] = j <= (int)best.end ? (uint32_t)__ldg(&a.tgt[ts + j]) : 0u;
-    }
-    uint32_t e_next = PRELOAD ? 0u : (uint32_t)__ldg(&a.tgt[ts]);
-    // keys of one target terminal: slot 0 = (NULL, e), slot 1+j = (F[j], e); the first table slots of all of them are
-    // loaded back to back (ht_first), then resolved -- one L2 round trip per target terminal instead of nf + 1
-    uint64_t fkey[6];
-    fkey[0] = 0;                                        // f = -1 -> (f + 1) = 0
-#pragma unroll
-    for (int j = 0; j < 5; j++) fkey[1 + j] = j < nf ? ((uint64_t)(uint32_t)(F[j] + 1) << 32) : 0ull;
-#pragma unroll(PRELOAD ? 15 : 1)
-    for (int jj = 0; jj < 15; jj++) {
-        if (jj > (int)best.end) break;
-        const uint32_t e_cur = PRELOAD ? tok[PRELOAD ? jj : 0] : e_next;
-        if (!PRELOAD && jj < (int)best.end) e_next = (uint32_t)__ldg(&a.tgt[ts + jj + 1]);      // the next token travels while this one is probed
+    for (int jj = 0; jj <= (int)best.end; jj++) {
         if (best.gap1 != 255 && jj >= (int)best.gap1 && jj <= (int)best.gap1_1) continue;
         if (best.gap2 != 255 && jj >= (int)best.gap2 && jj <= (int)best.gap2_1) continue;
         any_e = true;
-        if (nf == 0) { egivenf += CGX_MAXSCORE; continue; }
-        const uint64_t ek = (uint64_t)(e_cur + 1u);
-        ulonglong2 sv[6];
-        uint32_t ss[6];
-#pragma unroll
-        for (int u = 0; u < 6; u++) if (u <= nf) sv[u] = ht_first(lex, lex_mask, fkey[u] | ek, &ss[u]);
+        const int e = __ldg(&a.tgt[ts + jj]);
         float mx = 0.f;
+        if (nf > 0) { lex_get(lex, lex_mask, -1, e, &v1, &v2); mx = fmaxf(mx, v1); }
 #pragma unroll
-        for (int u = 0; u < 6; u++) {
-            if (u > nf) break;
-            uint64_t pay;
-            if (ht_resolve(lex, lex_mask, fkey[u] | ek, ss[u], sv[u], &pay)) {
-                mx = fmaxf(mx, __uint_as_float((uint32_t)pay));                                   // v1 -> MaxLexEgivenF
-                if (u > 0) mxf[u - 1] = fmaxf(mxf[u - 1], __uint_as_float((uint32_t)(pay >> 32)));   // v2 -> MaxLexFgivenE
-            }
+        for (int j = 0; j < 5; j++) {                                       // nf <= 5 (CGX_LONGEST_SRC / MAX_rule_symbols)
+            if (j >= nf) break;
+            lex_get(lex, lex_mask, F[j], e, &v1, &v2);
+            mx = fmaxf(mx, v1);
+            mxf[j] = fmaxf(mxf[j], v2);
         }
         egivenf += mx > 0.f ? -__log10f(mx) : CGX_MAXSCORE;
     }
     float fgivene = 0.f;
-    {   // (F[j], NULL) for every source terminal, again issued together
-        ulonglong2 sv[5];
-        uint32_t ss[5];
 #pragma unroll
-        for (int j = 0; j < 5; j++) if (j < nf && any_e) sv[j] = ht_first(lex, lex_mask, fkey[1 + j], &ss[j]);      // e = -1 -> (e + 1) = 0
-#pragma unroll
-        for (int j = 0; j < 5; j++) {
-            if (j >= nf) break;
-            float mx = mxf[j];
-            uint64_t pay;
-            if (any_e && ht_resolve(lex, lex_mask, fkey[1 + j], ss[j], sv[j], &pay)) mx = fmaxf(mx, __uint_as_float((uint32_t)(pay >> 32)));
-            fgivene += mx > 0.f ? -__log10f(mx) : CGX_MAXSCORE;
-        }
+    for (int j = 0; j < 5; j++) {
+        if (j >= nf) break;
+        float mx = mxf[j];
+        if (any_e) { lex_get(lex, lex_mask, F[j], -1, &v1, &v2); mx = fmaxf(mx, v2); }
+        fgivene += mx > 0.f ? -__log10f(mx) : CGX_MAXSCORE;
     }
     out.max_lex_f_given_e = fgivene;
     out.max_lex_e_given_f = egivenf;
@@ -365,12 +342,9 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
                 cgx_rule_t *rules = b.rules[kind].get<cgx_rule_t>(R);
                 uint32_t *head_cell = b.rule_head.get<uint32_t>((size_t)R + 2);
                 agg_head_cell_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(flags, N, R, head_cell);
-                static const bool preload = [] { const char *e = getenv("CGX_AGG_PRELOAD"); return e && e[0] == '1'; }();
-                if (preload)
-                    PROF("agg_rules", (double)R * (4 + 8 + 16 + 28) + (double)R * 13 * 16, (agg_rules_kernel<true><<<cgx_div_up(R, 128), 128, 0, stream>>>(a, kind, rec, head_cell, acc_best, acc_cnt, R,
-                                                                       ix.lex_hash.ptr<ulonglong2>(), ix.lex_hash_mask, rules)));
-                else
-                    PROF("agg_rules", (double)R * (4 + 8 + 16 + 28) + (double)R * 13 * 16, (agg_rules_kernel<false><<<cgx_div_up(R, 128), 128, 0, stream>>>(a, kind, rec, head_cell, acc_best, acc_cnt, R,
+                // (issuing the nf + 1 probes of a target terminal together was measured: 80-96 registers, 12.0 -> 14.9 ms; the table is
+                // L2-resident and the kernel is bound by instruction issue, not by the probe latency)
+                PROF("agg_rules", (double)R * (4 + 8 + 16 + 28) + (double)R * 13 * 16, (agg_rules_kernel<<<cgx_div_up(R, 128), 128, 0, stream>>>(a, kind, rec, head_cell, acc_best, acc_cnt, R,
                                                                        ix.lex_hash.ptr<ulonglong2>(), ix.lex_hash_mask, rules)));
                 CUDA_CHECK(cudaMemsetAsync(updown, 0xff, sizeof(int32_t) * 2 * (size_t)nids[kind], stream));
                 agg_updown_kernel<<<cgx_div_up(R, 256), 256, 0, stream>>>(rules, R, updown);

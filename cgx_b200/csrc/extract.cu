@@ -82,27 +82,30 @@ __global__ void slots_contig_kernel(const int32_t *__restrict__ phrases, int G, 
     if (g < G) cnt[g] = (uint32_t)min(phrases[g * 4 + 1] - phrases[g * 4] + 1, CGX_SAMPLER);
 }
 
-__global__ void __launch_bounds__(128) extract_contig_kernel(ExtractIdx x, const int32_t *__restrict__ phrases, int G, const uint32_t *__restrict__ slot_off,
-                                                             uint32_t n_slots, RuleRec *__restrict__ rec_ab, RuleRec *__restrict__ rec_Xab,
-                                                             RuleRec *__restrict__ rec_abX, RuleRec *__restrict__ rec_XabX) {
-    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= n_slots) return;
+// The kernels below run in two phases with a CTA-level compaction in between.  Phase 1 (every sampled occurrence: owner,
+// sample index, seed span, the seed's own rule) keeps all lanes busy; the extension loops of phase 2 (X to the left / right)
+// are entered by a third of the occurrences and leave at different trip counts -- run in place they executed with 6-8 of 32
+// lanes active (ncu, round 1c: extract_contig 5.9, extract_onegap 8.5 active threads per warp, SM pipes 75-80 % busy).  The
+// survivors therefore park their state in shared memory and the first `count` threads of the CTA pick one each.
+constexpr int EX_BLOCK = 128;
+
+struct ContigState {      // 24 bytes
+    int32_t slot, bnum, current_str, sen_target_begin, tempind;
+    uint32_t packed;      // longestmatch | min_L << 8 | max_R << 16 | flags << 24 (abX, Xab, XabX, XabNoSuccess, abXNoSuccess)
+};
+
+__device__ __forceinline__ void contig_phase1(const ExtractIdx &x, const int32_t *__restrict__ phrases, int G, const uint32_t *__restrict__ slot_off,
+                                              uint32_t slot, RuleRec *__restrict__ rec_ab, ContigState *s_state, int *s_count) {
     const int bnum = find_owner_u32(slot_off, G, slot);
     const int start = phrases[bnum * 4], end = phrases[bnum * 4 + 1], longestmatch = phrases[bnum * 4 + 2];
     const int occ = sample_index((int)(slot - slot_off[bnum]), end - start + 1, CGX_SAMPLER, 1.0f / (float)CGX_SAMPLER);
     if (occ < 0) return;
     const int current_str = __ldg(&x.sa[start + occ]);
-    const int globalc = G;
     const int SPAN = CGX_MAX_RULE_SPAN;
-
     unsigned L, R, temp;
     int sen_target_begin = -1, tempind = 0;
     unsigned min_L = 255, max_R = 0;
-    unsigned gap1_start = 0, gap1_end = 0, gap2_start = 0, gap2_end = 0, target_start = 0, target_end = 0;
-    bool next = true, abX = true, Xab = true, XabX = true, ab = true, XabNoSuccess = true, abXNoSuccess = true;
-    int XabCount = 0, abXCount = 0;
-    unsigned min_L_Xab = 255, max_R_Xab = 0, min_L_abX = 255, max_R_abX = 0, min_L_XabX = 255, max_R_XabX = 0;
-
+    bool abX = true, Xab = true, XabX = true, ab = true, XabNoSuccess = true, abXNoSuccess = true;
     for (int k = current_str; k < current_str + longestmatch; k++) {
         temp = __ldg(&x.xw[k]);
         L = (temp >> 24) & 0xFF; R = (temp >> 16) & 0xFF;
@@ -123,6 +126,47 @@ __global__ void __launch_bounds__(128) extract_contig_kernel(ExtractIdx x, const
         emit(rec_ab, slot, bnum, min_L + sen_target_begin, max_R + sen_target_begin, -1, -1, -1, -1);
     if (longestmatch + 1 > CGX_MAX_RULE_SYMBOLS) { abX = false; Xab = false; }
     if (longestmatch + 2 > CGX_MAX_RULE_SYMBOLS) XabX = false;
+    // the extension loop runs while (abXNoSuccess || XabNoSuccess || XabX); with Xab, abX and XabX all false its first
+    // iteration only clears those flags and emits nothing, so such occurrences do not enter phase 2
+    if (longestmatch + 1 <= SPAN && (abXNoSuccess || XabNoSuccess || XabX) && (Xab || abX || XabX)) {
+        const int k = atomicAdd(s_count, 1);
+        ContigState st;
+        st.slot = (int32_t)slot; st.bnum = bnum; st.current_str = current_str; st.sen_target_begin = sen_target_begin; st.tempind = tempind;
+        st.packed = (uint32_t)longestmatch | (min_L << 8) | (max_R << 16) |
+                    ((uint32_t)(abX ? 1 : 0) | (Xab ? 2u : 0u) | (XabX ? 4u : 0u) | (XabNoSuccess ? 8u : 0u) | (abXNoSuccess ? 16u : 0u)) << 24;
+        s_state[k] = st;
+    }
+}
+
+__global__ void __launch_bounds__(EX_BLOCK) extract_contig_kernel(ExtractIdx x, const int32_t *__restrict__ phrases, int G, const uint32_t *__restrict__ slot_off,
+                                                             uint32_t n_slots, RuleRec *__restrict__ rec_ab, RuleRec *__restrict__ rec_Xab,
+                                                             RuleRec *__restrict__ rec_abX, RuleRec *__restrict__ rec_XabX) {
+    __shared__ ContigState s_state[EX_BLOCK];
+    __shared__ int s_count;
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    {
+        const uint32_t slot1 = blockIdx.x * blockDim.x + threadIdx.x;
+        if (slot1 < n_slots) contig_phase1(x, phrases, G, slot_off, slot1, rec_ab, s_state, &s_count);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x >= s_count) return;
+    // ---- phase 2: one surviving occurrence per thread
+    const ContigState st = s_state[threadIdx.x];
+    const uint32_t slot = (uint32_t)st.slot;
+    const int bnum = st.bnum, current_str = st.current_str, sen_target_begin = st.sen_target_begin, tempind = st.tempind;
+    const int longestmatch = (int)(st.packed & 0xFF);
+    const unsigned min_L = (st.packed >> 8) & 0xFF, max_R = (st.packed >> 16) & 0xFF;
+    bool abX = (st.packed >> 24) & 1u, Xab = (st.packed >> 25) & 1u, XabX = (st.packed >> 26) & 1u, XabNoSuccess = (st.packed >> 27) & 1u,
+         abXNoSuccess = (st.packed >> 28) & 1u;
+    const int globalc = G;
+    const int SPAN = CGX_MAX_RULE_SPAN;
+    const int ender = current_str + longestmatch - 1;
+    unsigned L, R, temp;
+    unsigned gap1_start = 0, gap1_end = 0, gap2_start = 0, gap2_end = 0, target_start = 0, target_end = 0;
+    bool next = true;
+    int XabCount = 0, abXCount = 0;
+    unsigned min_L_Xab = 255, max_R_Xab = 0, min_L_abX = 255, max_R_abX = 0, min_L_XabX = 255, max_R_XabX = 0;
 
     for (int i = 1; longestmatch + i <= SPAN && (abXNoSuccess || XabNoSuccess || XabX); i++) {
         // ---- X on the left: tokens current_str-i .. current_str-1 ----
@@ -303,12 +347,16 @@ __global__ void slots_pat1_kernel(const Pat1 *__restrict__ pat, int D1, uint32_t
     if (d < D1) cnt[d] = (uint32_t)min(pat[d].hit_count, CGX_SAMPLER_ONEGAP);
 }
 
-__global__ void __launch_bounds__(128) extract_onegap_kernel(ExtractIdx x, const Pat1 *__restrict__ pat, int D1, const uint64_t *__restrict__ hits1,
-                                                             const uint32_t *__restrict__ slot_off, uint32_t n_slots, int G, int D2, int pbits,
-                                                             RuleRec *__restrict__ rec_aXb, RuleRec *__restrict__ rec_XaXb,
-                                                             RuleRec *__restrict__ rec_aXbX) {
-    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= n_slots) return;
+struct OneGapState {      // 32 bytes
+    int32_t slot, d, current_str, sen_target_begin, tempind;
+    uint32_t gap_start, gap_end;
+    uint32_t packed;      // firstEnd | min_L << 8 | max_R << 16 | left << 24 | right << 25
+};
+
+// phase 1: the seed aXb (ExtractPair.cu:458-600)
+__device__ __forceinline__ void onegap_phase1(const ExtractIdx &x, const Pat1 *__restrict__ pat, int D1, const uint64_t *__restrict__ hits1,
+                                              const uint32_t *__restrict__ slot_off, uint32_t slot, int G, int pbits, RuleRec *__restrict__ rec_aXb,
+                                              OneGapState *s_state, int *s_count) {
     const int d = find_owner_u32(slot_off, D1, slot);
     const Pat1 p = pat[d];
     const int occ = sample_index((int)(slot - slot_off[d]), p.hit_count, CGX_SAMPLER_ONEGAP, 1.0f / (float)CGX_SAMPLER_ONEGAP);
@@ -334,7 +382,41 @@ __global__ void __launch_bounds__(128) extract_onegap_kernel(ExtractIdx x, const
     if ((target_start == 0 && target_end == 0) || min_L > max_R || gap1_start < target_start || gap1_end > target_end) return;   // :591-595
     if (next) emit(rec_aXb, slot, 2 * G + d, target_start, target_end, (int)gap1_start, (int)gap1_end, -1, -1);
     if (startLen + endLen + 2 > CGX_MAX_RULE_SYMBOLS) return;
-    const unsigned originalGapStart = gap1_start, originalGapEnd = gap1_end;
+    if (firstEnd + 2 <= SPAN && (left || right)) {          // the extension loop would run at least once
+        const int k = atomicAdd(s_count, 1);
+        OneGapState st;
+        st.slot = (int32_t)slot; st.d = d; st.current_str = current_str; st.sen_target_begin = sen_target_begin; st.tempind = tempind;
+        st.gap_start = gap1_start; st.gap_end = gap1_end;
+        st.packed = (uint32_t)firstEnd | (min_L << 8) | (max_R << 16) | (left ? 1u << 24 : 0u) | (right ? 1u << 25 : 0u);
+        s_state[k] = st;
+    }
+}
+
+__global__ void __launch_bounds__(EX_BLOCK) extract_onegap_kernel(ExtractIdx x, const Pat1 *__restrict__ pat, int D1, const uint64_t *__restrict__ hits1,
+                                                             const uint32_t *__restrict__ slot_off, uint32_t n_slots, int G, int D2, int pbits,
+                                                             RuleRec *__restrict__ rec_aXb, RuleRec *__restrict__ rec_XaXb,
+                                                             RuleRec *__restrict__ rec_aXbX) {
+    __shared__ OneGapState s_state[EX_BLOCK];
+    __shared__ int s_count;
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    {
+        const uint32_t slot1 = blockIdx.x * blockDim.x + threadIdx.x;
+        if (slot1 < n_slots) onegap_phase1(x, pat, D1, hits1, slot_off, slot1, G, pbits, rec_aXb, s_state, &s_count);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x >= s_count) return;
+    // ---- phase 2: XaXb / aXbX of one surviving seed per thread (ExtractPair.cu:600-887)
+    const OneGapState st = s_state[threadIdx.x];
+    const uint32_t slot = (uint32_t)st.slot;
+    const int d = st.d, current_str = st.current_str, sen_target_begin = st.sen_target_begin, tempind = st.tempind;
+    const int firstEnd = (int)(st.packed & 0xFF);
+    const unsigned min_L = (st.packed >> 8) & 0xFF, max_R = (st.packed >> 16) & 0xFF;
+    bool left = (st.packed >> 24) & 1u, right = (st.packed >> 25) & 1u, next = true;
+    const int SPAN = CGX_MAX_RULE_SPAN;
+    const int ender = current_str + firstEnd;
+    unsigned target_start = 0, target_end = 0;
+    const unsigned originalGapStart = st.gap_start, originalGapEnd = st.gap_end;
     unsigned min_XaXb = 255, max_XaXb = 0, min_aXbX = 255, max_aXbX = 0, L, R, temp;
     for (int i = 1; firstEnd + 1 + i <= SPAN && (left || right); i++) {
         temp = (left && current_str - i >= 0) ? __ldg(&x.xw[current_str - i]) : 0u;
