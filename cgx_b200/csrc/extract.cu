@@ -74,6 +74,16 @@ __device__ __forceinline__ int find_owner_u32(const uint32_t *__restrict__ off, 
     return lo;
 }
 
+// owner[slot] = pattern of every sampled-occurrence slot: one warp per pattern writes its (<= 300) slots, so that the
+// extraction threads read their pattern instead of binary-searching slot_off (23 dependent L2 loads per thread at C2,
+// 12 % of the extraction kernels' stall samples in round 1c)
+__global__ void slot_owner_kernel(const uint32_t *__restrict__ slot_off, int n_pat, uint32_t *__restrict__ owner) {
+    const int d = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    if (d >= n_pat) return;
+    const uint32_t s0 = slot_off[d], s1 = slot_off[d + 1];
+    for (uint32_t j = s0 + (threadIdx.x & 31); j < s1; j += 32) owner[j] = (uint32_t)d;
+}
+
 // ------------------------------------------------------------------------------------------------
 // contiguous phrases: ab, Xab, abX, XabX      (ExtractPair.cu:1163-1792)
 // ------------------------------------------------------------------------------------------------
@@ -82,11 +92,14 @@ __global__ void slots_contig_kernel(const int32_t *__restrict__ phrases, int G, 
     if (g < G) cnt[g] = (uint32_t)min(phrases[g * 4 + 1] - phrases[g * 4] + 1, CGX_SAMPLER);
 }
 
-// The kernels below run in two phases with a CTA-level compaction in between.  Phase 1 (every sampled occurrence: owner,
-// sample index, seed span, the seed's own rule) keeps all lanes busy; the extension loops of phase 2 (X to the left / right)
-// are entered by a third of the occurrences and leave at different trip counts -- run in place they executed with 6-8 of 32
-// lanes active (ncu, round 1c: extract_contig 5.9, extract_onegap 8.5 active threads per warp, SM pipes 75-80 % busy).  The
-// survivors therefore park their state in shared memory and the first `count` threads of the CTA pick one each.
+// Contiguous and one-gap seeds run as two kernels.  Phase 1 (every sampled occurrence: owner, sample index, seed span, the
+// seed's own rule) keeps all lanes busy; the extension loops of phase 2 (X to the left / right) are entered by a third of the
+// occurrences and leave at different trip counts -- run in place they executed with 6-8 of 32 lanes active (ncu, round 1c:
+// extract_contig 5.9, extract_onegap 8.5 active threads per warp, SM pipes 75-80 % busy).  The survivors therefore write their
+// state (24 / 32 bytes) to a queue -- compacted per CTA in shared memory, one global cursor bump per CTA -- and a second
+// kernel runs the loops with full warps.  (Compacting inside the CTA only was measured: the threads that retire keep their
+// warp slots until the CTA ends, occupancy collapses, extract_onegap 9.8 -> 16.6 ms.)  Cells are slot-indexed, so the
+// nondeterministic queue order does not reach the results.
 constexpr int EX_BLOCK = 128;
 
 struct ContigState {      // 24 bytes
@@ -94,9 +107,9 @@ struct ContigState {      // 24 bytes
     uint32_t packed;      // longestmatch | min_L << 8 | max_R << 16 | flags << 24 (abX, Xab, XabX, XabNoSuccess, abXNoSuccess)
 };
 
-__device__ __forceinline__ void contig_phase1(const ExtractIdx &x, const int32_t *__restrict__ phrases, int G, const uint32_t *__restrict__ slot_off,
+__device__ __forceinline__ void contig_phase1(const ExtractIdx &x, const int32_t *__restrict__ phrases, const uint32_t *__restrict__ owner, const uint32_t *__restrict__ slot_off,
                                               uint32_t slot, RuleRec *__restrict__ rec_ab, ContigState *s_state, int *s_count) {
-    const int bnum = find_owner_u32(slot_off, G, slot);
+    const int bnum = (int)owner[slot];
     const int start = phrases[bnum * 4], end = phrases[bnum * 4 + 1], longestmatch = phrases[bnum * 4 + 2];
     const int occ = sample_index((int)(slot - slot_off[bnum]), end - start + 1, CGX_SAMPLER, 1.0f / (float)CGX_SAMPLER);
     if (occ < 0) return;
@@ -138,21 +151,33 @@ __device__ __forceinline__ void contig_phase1(const ExtractIdx &x, const int32_t
     }
 }
 
-__global__ void __launch_bounds__(EX_BLOCK) extract_contig_kernel(ExtractIdx x, const int32_t *__restrict__ phrases, int G, const uint32_t *__restrict__ slot_off,
-                                                             uint32_t n_slots, RuleRec *__restrict__ rec_ab, RuleRec *__restrict__ rec_Xab,
-                                                             RuleRec *__restrict__ rec_abX, RuleRec *__restrict__ rec_XabX) {
+// survivors of a CTA: one global cursor bump per CTA, states copied out of shared memory in order
+template <typename State>
+__device__ __forceinline__ void flush_survivors(const State *s_state, const int &s_count, uint32_t *s_base, uint32_t *__restrict__ q_count, State *__restrict__ queue) {
+    __syncthreads();
+    if (threadIdx.x == 0 && s_count) *s_base = atomicAdd(q_count, (uint32_t)s_count);
+    __syncthreads();
+    if ((int)threadIdx.x < s_count) queue[*s_base + threadIdx.x] = s_state[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(EX_BLOCK) extract_contig_kernel(ExtractIdx x, const int32_t *__restrict__ phrases, const uint32_t *__restrict__ owner, const uint32_t *__restrict__ slot_off,
+                                                             uint32_t n_slots, RuleRec *__restrict__ rec_ab, uint32_t *__restrict__ q_count, ContigState *__restrict__ queue) {
     __shared__ ContigState s_state[EX_BLOCK];
     __shared__ int s_count;
+    __shared__ uint32_t s_base;
     if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
-    {
-        const uint32_t slot1 = blockIdx.x * blockDim.x + threadIdx.x;
-        if (slot1 < n_slots) contig_phase1(x, phrases, G, slot_off, slot1, rec_ab, s_state, &s_count);
-    }
-    __syncthreads();
-    if ((int)threadIdx.x >= s_count) return;
-    // ---- phase 2: one surviving occurrence per thread
-    const ContigState st = s_state[threadIdx.x];
+    const uint32_t slot1 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot1 < n_slots) contig_phase1(x, phrases, owner, slot_off, slot1, rec_ab, s_state, &s_count);
+    flush_survivors(s_state, s_count, &s_base, q_count, queue);
+}
+
+// phase 2: one surviving occurrence per thread, full warps (ExtractPair.cu:1290-1792)
+__global__ void __launch_bounds__(EX_BLOCK) extract_contig_ext_kernel(ExtractIdx x, int G, const uint32_t *__restrict__ q_count, const ContigState *__restrict__ queue,
+                                                                 RuleRec *__restrict__ rec_Xab, RuleRec *__restrict__ rec_abX, RuleRec *__restrict__ rec_XabX) {
+    const uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= *q_count) return;
+    const ContigState st = queue[qi];
     const uint32_t slot = (uint32_t)st.slot;
     const int bnum = st.bnum, current_str = st.current_str, sen_target_begin = st.sen_target_begin, tempind = st.tempind;
     const int longestmatch = (int)(st.packed & 0xFF);
@@ -354,10 +379,10 @@ struct OneGapState {      // 32 bytes
 };
 
 // phase 1: the seed aXb (ExtractPair.cu:458-600)
-__device__ __forceinline__ void onegap_phase1(const ExtractIdx &x, const Pat1 *__restrict__ pat, int D1, const uint64_t *__restrict__ hits1,
+__device__ __forceinline__ void onegap_phase1(const ExtractIdx &x, const Pat1 *__restrict__ pat, const uint32_t *__restrict__ owner, const uint64_t *__restrict__ hits1,
                                               const uint32_t *__restrict__ slot_off, uint32_t slot, int G, int pbits, RuleRec *__restrict__ rec_aXb,
                                               OneGapState *s_state, int *s_count) {
-    const int d = find_owner_u32(slot_off, D1, slot);
+    const int d = (int)owner[slot];
     const Pat1 p = pat[d];
     const int occ = sample_index((int)(slot - slot_off[d]), p.hit_count, CGX_SAMPLER_ONEGAP, 1.0f / (float)CGX_SAMPLER_ONEGAP);
     if (occ < 0) return;
@@ -392,22 +417,25 @@ __device__ __forceinline__ void onegap_phase1(const ExtractIdx &x, const Pat1 *_
     }
 }
 
-__global__ void __launch_bounds__(EX_BLOCK) extract_onegap_kernel(ExtractIdx x, const Pat1 *__restrict__ pat, int D1, const uint64_t *__restrict__ hits1,
-                                                             const uint32_t *__restrict__ slot_off, uint32_t n_slots, int G, int D2, int pbits,
-                                                             RuleRec *__restrict__ rec_aXb, RuleRec *__restrict__ rec_XaXb,
-                                                             RuleRec *__restrict__ rec_aXbX) {
+__global__ void __launch_bounds__(EX_BLOCK) extract_onegap_kernel(ExtractIdx x, const Pat1 *__restrict__ pat, const uint32_t *__restrict__ owner, const uint64_t *__restrict__ hits1,
+                                                             const uint32_t *__restrict__ slot_off, uint32_t n_slots, int G, int pbits,
+                                                             RuleRec *__restrict__ rec_aXb, uint32_t *__restrict__ q_count, OneGapState *__restrict__ queue) {
     __shared__ OneGapState s_state[EX_BLOCK];
     __shared__ int s_count;
+    __shared__ uint32_t s_base;
     if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
-    {
-        const uint32_t slot1 = blockIdx.x * blockDim.x + threadIdx.x;
-        if (slot1 < n_slots) onegap_phase1(x, pat, D1, hits1, slot_off, slot1, G, pbits, rec_aXb, s_state, &s_count);
-    }
-    __syncthreads();
-    if ((int)threadIdx.x >= s_count) return;
-    // ---- phase 2: XaXb / aXbX of one surviving seed per thread (ExtractPair.cu:600-887)
-    const OneGapState st = s_state[threadIdx.x];
+    const uint32_t slot1 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot1 < n_slots) onegap_phase1(x, pat, owner, hits1, slot_off, slot1, G, pbits, rec_aXb, s_state, &s_count);
+    flush_survivors(s_state, s_count, &s_base, q_count, queue);
+}
+
+// phase 2: XaXb / aXbX of one surviving seed per thread, full warps (ExtractPair.cu:600-887)
+__global__ void __launch_bounds__(EX_BLOCK) extract_onegap_ext_kernel(ExtractIdx x, int G, int D1, int D2, const uint32_t *__restrict__ q_count, const OneGapState *__restrict__ queue,
+                                                                 RuleRec *__restrict__ rec_XaXb, RuleRec *__restrict__ rec_aXbX) {
+    const uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= *q_count) return;
+    const OneGapState st = queue[qi];
     const uint32_t slot = (uint32_t)st.slot;
     const int d = st.d, current_str = st.current_str, sen_target_begin = st.sen_target_begin, tempind = st.tempind;
     const int firstEnd = (int)(st.packed & 0xFF);
@@ -478,12 +506,12 @@ __global__ void slots_pat2_kernel(const Pat2 *__restrict__ pat, int D2, uint32_t
     if (d < D2) cnt[d] = (uint32_t)min(pat[d].hit_count, CGX_SAMPLER_TWOGAP);
 }
 
-__global__ void __launch_bounds__(128) extract_twogap_kernel(ExtractIdx x, const Pat2 *__restrict__ pat2, const Pat1 *__restrict__ pat1, int D2,
+__global__ void __launch_bounds__(128) extract_twogap_kernel(ExtractIdx x, const Pat2 *__restrict__ pat2, const Pat1 *__restrict__ pat1, const uint32_t *__restrict__ owner,
                                                              const uint64_t *__restrict__ hits2, const uint32_t *__restrict__ slot_off, uint32_t n_slots,
                                                              int G, int pbits, RuleRec *__restrict__ rec_aXbXc) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= n_slots) return;
-    const int d = find_owner_u32(slot_off, D2, slot);
+    const int d = (int)owner[slot];
     const Pat2 p2 = pat2[d];
     const int occ = sample_index((int)(slot - slot_off[d]), p2.hit_count, CGX_SAMPLER_TWOGAP, 1.0f / (float)CGX_SAMPLER_TWOGAP);
     if (occ < 0) return;
@@ -545,10 +573,26 @@ void stage_extract(const Index &ix, Batch &b, cudaStream_t stream) {
     // algorithmic bytes (SURVEY 8d B_ext, lower bound): per sampled occurrence its SA / hit entry and slot owner (8 B), the
     // RLP + text words of the smallest source window it must inspect (phrase + one extension token per side: 8 B x 5)
     // and the L/R bytes of a 4-token target window (2 x 4) = 56 B; emitted cells are not counted
-    if (ns[0]) PROF("extract_contig", (double)ns[0] * 56, (extract_contig_kernel<<<cgx_div_up(ns[0], 128), 128, 0, stream>>>(x, b.phrases.ptr<int32_t>(), G, so0, ns[0], r0, r1, r1 + ns[0], r2)));
-    if (ns[2]) PROF("extract_twogap", (double)ns[2] * 56, (extract_twogap_kernel<<<cgx_div_up(ns[2], 128), 128, 0, stream>>>(x, b.pat2.ptr<Pat2>(), b.pat1.ptr<Pat1>(), D2, b.hits2_sorted.ptr<uint64_t>(), so2, ns[2], G, b.pbits, r2 + ns[0])));
-    if (ns[1]) PROF("extract_onegap", (double)ns[1] * 56, (extract_onegap_kernel<<<cgx_div_up(ns[1], 128), 128, 0, stream>>>(x, b.pat1.ptr<Pat1>(), D1, b.hits1_sorted.ptr<uint64_t>(), so1, ns[1], G, D2, b.pbits, r1 + (size_t)2 * ns[0], r2 + (size_t)ns[0] + ns[2], r2 + (size_t)ns[0] + ns[2] + ns[1])));
-    b.launches += 3;
+    // slot -> pattern (4 B per slot, written by one warp per pattern)
+    uint32_t *own = b.slot_owner.get<uint32_t>((size_t)ns[0] + ns[1] + ns[2] + 1);
+    uint32_t *own0 = own, *own1 = own + ns[0], *own2 = own1 + ns[1];
+    if (ns[0]) PROF("extract_owner", (double)ns[0] * 4 + (double)G * 8, (slot_owner_kernel<<<cgx_div_up((size_t)G * 32, 256), 256, 0, stream>>>(so0, G, own0)));
+    if (ns[1]) PROF("extract_owner", (double)ns[1] * 4 + (double)D1 * 8, (slot_owner_kernel<<<cgx_div_up((size_t)D1 * 32, 256), 256, 0, stream>>>(so1, D1, own1)));
+    if (ns[2]) PROF("extract_owner", (double)ns[2] * 4 + (double)D2 * 8, (slot_owner_kernel<<<cgx_div_up((size_t)D2 * 32, 256), 256, 0, stream>>>(so2, D2, own2)));
+    uint32_t *qcnt = tot + 8;                                      // [0] contiguous, [1] one-gap survivors
+    CUDA_CHECK(cudaMemsetAsync(qcnt, 0, sizeof(uint32_t) * 2, stream));
+    ContigState *q0 = b.ex_queue0.get<ContigState>((size_t)ns[0] + 1);
+    OneGapState *q1 = b.ex_queue1.get<OneGapState>((size_t)ns[1] + 1);
+    if (ns[0]) {
+        PROF("extract_contig", (double)ns[0] * 56, (extract_contig_kernel<<<cgx_div_up(ns[0], EX_BLOCK), EX_BLOCK, 0, stream>>>(x, b.phrases.ptr<int32_t>(), own0, so0, ns[0], r0, qcnt, q0)));
+        PROF("extract_contig", 0.0, (extract_contig_ext_kernel<<<cgx_div_up(ns[0], EX_BLOCK), EX_BLOCK, 0, stream>>>(x, G, qcnt, q0, r1, r1 + ns[0], r2)));
+    }
+    if (ns[2]) PROF("extract_twogap", (double)ns[2] * 56, (extract_twogap_kernel<<<cgx_div_up(ns[2], 128), 128, 0, stream>>>(x, b.pat2.ptr<Pat2>(), b.pat1.ptr<Pat1>(), own2, b.hits2_sorted.ptr<uint64_t>(), so2, ns[2], G, b.pbits, r2 + ns[0])));
+    if (ns[1]) {
+        PROF("extract_onegap", (double)ns[1] * 56, (extract_onegap_kernel<<<cgx_div_up(ns[1], EX_BLOCK), EX_BLOCK, 0, stream>>>(x, b.pat1.ptr<Pat1>(), own1, b.hits1_sorted.ptr<uint64_t>(), so1, ns[1], G, b.pbits, r1 + (size_t)2 * ns[0], qcnt + 1, q1)));
+        PROF("extract_onegap", 0.0, (extract_onegap_ext_kernel<<<cgx_div_up(ns[1], EX_BLOCK), EX_BLOCK, 0, stream>>>(x, G, D1, D2, qcnt + 1, q1, r2 + (size_t)ns[0] + ns[2], r2 + (size_t)ns[0] + ns[2] + ns[1])));
+    }
+    b.launches += 8;
 }
 
 }  // namespace cgx
