@@ -87,6 +87,8 @@ def load():
     L.cgx_index_export.argtypes = [vp, C.POINTER(IndexArrays)]
     L.cgx_index_alloc.argtypes = [vp, C.POINTER(IndexArrays), C.POINTER(IndexArrays)]
     L.cgx_index_commit.argtypes = [vp]
+    L.cgx_index_save.argtypes = [vp, C.c_char_p]
+    L.cgx_index_load.argtypes = [vp, C.c_char_p]
     L.cgx_index_copy_sa.argtypes = [vp, i32p]
     L.cgx_index_copy_inv.argtypes = [vp, C.c_int, i32p]
     L.cgx_index_copy_frequent.argtypes = [vp, i32p]
@@ -108,6 +110,6 @@ def load():
 
 
 EXPORTED_SYMBOLS = ("cgx_version", "cgx_create", "cgx_destroy", "cgx_last_error", "cgx_index_build", "cgx_lex_load", "cgx_index_info",
-                    "cgx_sa_build_dev", "cgx_index_export", "cgx_index_alloc", "cgx_index_commit", "cgx_index_copy_sa", "cgx_index_copy_inv",
+                    "cgx_sa_build_dev", "cgx_index_export", "cgx_index_alloc", "cgx_index_commit", "cgx_index_save", "cgx_index_load", "cgx_index_copy_sa", "cgx_index_copy_inv",
                     "cgx_index_copy_frequent", "cgx_extract", "cgx_extract_begin", "cgx_result_at", "cgx_extract_dev", "cgx_profile_enable", "cgx_profile_report",
                     "cgx_index_broadcast", "cgx_batch_info", "cgx_result", "cgx_debug_fetch", "cgx_debug_sort_u64")

@@ -66,7 +66,7 @@ extern "C" void cgx_destroy(cgx_ctx_t *c) {
                     &b.phrases, &b.e1_count, &b.e1_inst, &b.e1_keys, &b.e1_keys_tmp, &b.e1_vals, &b.e1_vals_tmp, &b.e1_flags, &b.e1_pid, &b.pat1,
                     &b.pat1_dev, &b.pat1_pos, &b.ql_keys, &b.ql_keys_tmp, &b.q1_off, &b.q1_ids, &b.q2_off, &b.q2_ids, &b.j_tiles, &b.j_bitmaps, &b.j_aflag, &b.j_aid, &b.j_hash, &b.pat1_ga, &b.hit_keys,
                     &b.hit_keys_tmp, &b.counters, &b.missing, &b.hits1_sorted, &b.hits2_sorted, &b.e2_count, &b.e2_keys, &b.e2_keys_tmp, &b.e2_vals,
-                    &b.e2_vals_tmp, &b.e2_flags, &b.pat2, &b.rec_hash, &b.rec_tag, &b.rec_live, &b.rec_flags, &b.rec_meta, &b.rec_cnt, &b.slot_owner, &b.ex_queue0, &b.ex_queue1,
+                    &b.e2_vals_tmp, &b.e2_flags, &b.pat2, &b.rec_hash, &b.rec_tag, &b.rec_live, &b.rec_flags, &b.rec_meta, &b.rec_cnt,
                     &b.scratch, &b.scratch2, &b.rule_head, &b.radix.hist, &b.radix.status, &b.radix.counters};
     for (auto *x : bb) x->release();
     for (int k = 0; k < 3; k++) { b.slot_off[k].release(); b.rec[k].release(); b.rules[k].release(); b.updown[k].release(); b.id_count[k].release(); }
@@ -258,6 +258,102 @@ extern "C" int cgx_index_commit(cgx_ctx_t *c) {
         build_jwin(c->ix, c->stream);              // derived from the (broadcast) bucket arrays, gap words, text and alignment arrays
         c->ix.built = true;
     });
+}
+
+// ---- persisted index (the reference only has the dead sa_precomp.txt stub, SuffixArray.c:208-230) --------------
+struct IndexFileHeader {
+    char magic[8];                 // "CGXIDX01"
+    int64_t n, m, lex_count;
+    int32_t max_token, sa_rounds, sa_key_bits, reserved;
+    int32_t freq_list[CGX_PRECOMP];
+};
+struct IndexArrayRef { void *p; size_t bytes; };
+static int index_array_refs(const cgx_index_arrays_t &a, IndexArrayRef out[18]) {
+    const size_t n = (size_t)a.n, m = (size_t)a.m, nt = (size_t)a.max_token + 2, lx = (size_t)a.lex_count + 1;
+    const IndexArrayRef r[18] = {{a.str, 4 * (n + 3)}, {a.sa, 4 * n}, {a.inv1, 4 * n}, {a.inv2, 4 * n}, {a.inv3, 4 * n}, {a.bkt1, 4 * n}, {a.bkt2, 4 * n}, {a.bkt3, 4 * n},
+                                 {a.tok_start, 4 * nt}, {a.RLP, 4 * n}, {a.L_tar, m}, {a.R_tar, m}, {a.tgt, 4 * (m + 3)}, {a.freq_flag, nt}, {a.gapw, 4 * n},
+                                 {a.lex_key, 8 * lx}, {a.lex_v1, 4 * lx}, {a.lex_v2, 4 * lx}};
+    for (int i = 0; i < 18; i++) out[i] = r[i];
+    return 18;
+}
+
+extern "C" int cgx_index_save(cgx_ctx_t *c, const char *path) {
+    FILE *fh = nullptr;
+    void *stage = nullptr;
+    try {
+        CGX_REQUIRE(c && path && c->ix.built, "index not built");
+        CUDA_CHECK(cudaSetDevice(c->device));
+        cgx_index_arrays_t a;
+        CGX_REQUIRE(cgx_index_export(c, &a) == 0, "export failed");
+        fh = fopen(path, "wb");
+        CGX_REQUIRE(fh, "cannot open %s for writing", path);
+        IndexFileHeader h;
+        memset(&h, 0, sizeof h);
+        memcpy(h.magic, "CGXIDX01", 8);
+        h.n = a.n; h.m = a.m; h.lex_count = a.lex_count; h.max_token = a.max_token; h.sa_rounds = c->ix.sa_stats.rounds; h.sa_key_bits = c->ix.sa_stats.key_bits;
+        memcpy(h.freq_list, a.freq_list, sizeof h.freq_list);
+        CGX_REQUIRE(fwrite(&h, sizeof h, 1, fh) == 1, "write failed");
+        const size_t piece = (size_t)64 << 20;
+        CUDA_CHECK(cudaMallocHost(&stage, piece));
+        IndexArrayRef r[18];
+        const int k = index_array_refs(a, r);
+        for (int i = 0; i < k; i++)
+            for (size_t o = 0; o < r[i].bytes; o += piece) {
+                const size_t len = std::min(piece, r[i].bytes - o);
+                CUDA_CHECK(cudaMemcpy(stage, (const char *)r[i].p + o, len, cudaMemcpyDeviceToHost));
+                CGX_REQUIRE(fwrite(stage, 1, len, fh) == len, "write failed (disk full?)");
+            }
+        cudaFreeHost(stage);
+        CGX_REQUIRE(fclose(fh) == 0, "close failed");
+        return 0;
+    } catch (const CgxError &e) {
+        if (fh) fclose(fh);
+        if (stage) cudaFreeHost(stage);
+        if (c) c->err = e.msg;
+        return e.code;
+    }
+}
+
+extern "C" int cgx_index_load(cgx_ctx_t *c, const char *path) {
+    FILE *fh = nullptr;
+    void *stage = nullptr;
+    try {
+        CGX_REQUIRE(c && path, "null argument");
+        CUDA_CHECK(cudaSetDevice(c->device));
+        fh = fopen(path, "rb");
+        CGX_REQUIRE(fh, "cannot open %s", path);
+        IndexFileHeader h;
+        CGX_REQUIRE(fread(&h, sizeof h, 1, fh) == 1 && memcmp(h.magic, "CGXIDX01", 8) == 0, "%s is not a cgx-b200 index file", path);
+        CGX_REQUIRE(h.n >= 4 && h.m >= 1 && h.lex_count >= 0 && h.max_token >= 1, "%s: corrupt header", path);
+        cgx_index_arrays_t shape, a;
+        memset(&shape, 0, sizeof shape);
+        shape.n = h.n; shape.m = h.m; shape.lex_count = h.lex_count; shape.max_token = h.max_token;
+        memcpy(shape.freq_list, h.freq_list, sizeof h.freq_list);
+        CGX_REQUIRE(cgx_index_alloc(c, &shape, &a) == 0, "%s", c->err.c_str());
+        const size_t piece = (size_t)64 << 20;
+        CUDA_CHECK(cudaMallocHost(&stage, piece));
+        IndexArrayRef r[18];
+        const int k = index_array_refs(a, r);
+        for (int i = 0; i < k; i++)
+            for (size_t o = 0; o < r[i].bytes; o += piece) {
+                const size_t len = std::min(piece, r[i].bytes - o);
+                CGX_REQUIRE(fread(stage, 1, len, fh) == len, "%s: truncated", path);
+                CUDA_CHECK(cudaMemcpy((char *)r[i].p + o, stage, len, cudaMemcpyHostToDevice));
+            }
+        cudaFreeHost(stage);
+        stage = nullptr;
+        fclose(fh);
+        fh = nullptr;
+        c->ix.sa_stats.rounds = h.sa_rounds; c->ix.sa_stats.key_bits = h.sa_key_bits; c->ix.sa_stats.ms = 0.f; c->ix.sa_stats.launches = 0;
+        c->aux_ms = 0.f;
+        CGX_REQUIRE(cgx_index_commit(c) == 0, "%s", c->err.c_str());
+        return 0;
+    } catch (const CgxError &e) {
+        if (fh) fclose(fh);
+        if (stage) cudaFreeHost(stage);
+        if (c) c->err = e.msg;
+        return e.code;
+    }
 }
 
 extern "C" int cgx_index_copy_sa(cgx_ctx_t *c, int32_t *out) {

@@ -19,6 +19,13 @@
 //   kind 0 (ab)   : [ab: ns0]
 //   kind 1        : [Xab: ns0][abX: ns0][aXb: ns1]
 //   kind 2        : [XabX: ns0][aXbXc: ns2][XaXb: ns1][aXbX: ns1]          (ns0/1/2 = contiguous / one-gap / two-gap slots)
+//
+// Measured and dropped (round 1c, C2): the extension loops run with 6-8 of 32 lanes active (ncu: 5.9 / 8.5 active threads per
+// warp, SM pipes 75-80 % busy), so the survivors of the seed phase were compacted (a) inside the CTA through shared memory --
+// the retired threads keep their warp slots until the CTA ends, occupancy collapses: extract_onegap 9.8 -> 16.6 ms -- and
+// (b) through a global queue into a second kernel with full warps -- the extension phase then re-fetches the window sectors the
+// seed phase had just pulled into L1, and latency, not issue slots, is what it waits for: 9.8 -> 14.9 ms.  A slot -> pattern
+// array instead of the binary search costs 1.0 ms to fill and saves 0.2 ms.  The one-thread-per-occurrence form stays.
 #include "batch.h"
 #include "prof.h"
 
@@ -74,16 +81,6 @@ __device__ __forceinline__ int find_owner_u32(const uint32_t *__restrict__ off, 
     return lo;
 }
 
-// owner[slot] = pattern of every sampled-occurrence slot: one warp per pattern writes its (<= 300) slots, so that the
-// extraction threads read their pattern instead of binary-searching slot_off (23 dependent L2 loads per thread at C2,
-// 12 % of the extraction kernels' stall samples in round 1c)
-__global__ void slot_owner_kernel(const uint32_t *__restrict__ slot_off, int n_pat, uint32_t *__restrict__ owner) {
-    const int d = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
-    if (d >= n_pat) return;
-    const uint32_t s0 = slot_off[d], s1 = slot_off[d + 1];
-    for (uint32_t j = s0 + (threadIdx.x & 31); j < s1; j += 32) owner[j] = (uint32_t)d;
-}
-
 // ------------------------------------------------------------------------------------------------
 // contiguous phrases: ab, Xab, abX, XabX      (ExtractPair.cu:1163-1792)
 // ------------------------------------------------------------------------------------------------
@@ -92,33 +89,27 @@ __global__ void slots_contig_kernel(const int32_t *__restrict__ phrases, int G, 
     if (g < G) cnt[g] = (uint32_t)min(phrases[g * 4 + 1] - phrases[g * 4] + 1, CGX_SAMPLER);
 }
 
-// Contiguous and one-gap seeds run as two kernels.  Phase 1 (every sampled occurrence: owner, sample index, seed span, the
-// seed's own rule) keeps all lanes busy; the extension loops of phase 2 (X to the left / right) are entered by a third of the
-// occurrences and leave at different trip counts -- run in place they executed with 6-8 of 32 lanes active (ncu, round 1c:
-// extract_contig 5.9, extract_onegap 8.5 active threads per warp, SM pipes 75-80 % busy).  The survivors therefore write their
-// state (24 / 32 bytes) to a queue -- compacted per CTA in shared memory, one global cursor bump per CTA -- and a second
-// kernel runs the loops with full warps.  (Compacting inside the CTA only was measured: the threads that retire keep their
-// warp slots until the CTA ends, occupancy collapses, extract_onegap 9.8 -> 16.6 ms.)  Cells are slot-indexed, so the
-// nondeterministic queue order does not reach the results.
-constexpr int EX_BLOCK = 128;
-
-struct ContigState {      // 24 bytes
-    int32_t slot, bnum, current_str, sen_target_begin, tempind;
-    uint32_t packed;      // longestmatch | min_L << 8 | max_R << 16 | flags << 24 (abX, Xab, XabX, XabNoSuccess, abXNoSuccess)
-};
-
-__device__ __forceinline__ void contig_phase1(const ExtractIdx &x, const int32_t *__restrict__ phrases, const uint32_t *__restrict__ owner, const uint32_t *__restrict__ slot_off,
-                                              uint32_t slot, RuleRec *__restrict__ rec_ab, ContigState *s_state, int *s_count) {
-    const int bnum = (int)owner[slot];
+__global__ void __launch_bounds__(128) extract_contig_kernel(ExtractIdx x, const int32_t *__restrict__ phrases, int G, const uint32_t *__restrict__ slot_off,
+                                                             uint32_t n_slots, RuleRec *__restrict__ rec_ab, RuleRec *__restrict__ rec_Xab,
+                                                             RuleRec *__restrict__ rec_abX, RuleRec *__restrict__ rec_XabX) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_slots) return;
+    const int bnum = find_owner_u32(slot_off, G, slot);
     const int start = phrases[bnum * 4], end = phrases[bnum * 4 + 1], longestmatch = phrases[bnum * 4 + 2];
     const int occ = sample_index((int)(slot - slot_off[bnum]), end - start + 1, CGX_SAMPLER, 1.0f / (float)CGX_SAMPLER);
     if (occ < 0) return;
     const int current_str = __ldg(&x.sa[start + occ]);
+    const int globalc = G;
     const int SPAN = CGX_MAX_RULE_SPAN;
+
     unsigned L, R, temp;
     int sen_target_begin = -1, tempind = 0;
     unsigned min_L = 255, max_R = 0;
-    bool abX = true, Xab = true, XabX = true, ab = true, XabNoSuccess = true, abXNoSuccess = true;
+    unsigned gap1_start = 0, gap1_end = 0, gap2_start = 0, gap2_end = 0, target_start = 0, target_end = 0;
+    bool next = true, abX = true, Xab = true, XabX = true, ab = true, XabNoSuccess = true, abXNoSuccess = true;
+    int XabCount = 0, abXCount = 0;
+    unsigned min_L_Xab = 255, max_R_Xab = 0, min_L_abX = 255, max_R_abX = 0, min_L_XabX = 255, max_R_XabX = 0;
+
     for (int k = current_str; k < current_str + longestmatch; k++) {
         temp = __ldg(&x.xw[k]);
         L = (temp >> 24) & 0xFF; R = (temp >> 16) & 0xFF;
@@ -139,59 +130,6 @@ __device__ __forceinline__ void contig_phase1(const ExtractIdx &x, const int32_t
         emit(rec_ab, slot, bnum, min_L + sen_target_begin, max_R + sen_target_begin, -1, -1, -1, -1);
     if (longestmatch + 1 > CGX_MAX_RULE_SYMBOLS) { abX = false; Xab = false; }
     if (longestmatch + 2 > CGX_MAX_RULE_SYMBOLS) XabX = false;
-    // the extension loop runs while (abXNoSuccess || XabNoSuccess || XabX); with Xab, abX and XabX all false its first
-    // iteration only clears those flags and emits nothing, so such occurrences do not enter phase 2
-    if (longestmatch + 1 <= SPAN && (abXNoSuccess || XabNoSuccess || XabX) && (Xab || abX || XabX)) {
-        const int k = atomicAdd(s_count, 1);
-        ContigState st;
-        st.slot = (int32_t)slot; st.bnum = bnum; st.current_str = current_str; st.sen_target_begin = sen_target_begin; st.tempind = tempind;
-        st.packed = (uint32_t)longestmatch | (min_L << 8) | (max_R << 16) |
-                    ((uint32_t)(abX ? 1 : 0) | (Xab ? 2u : 0u) | (XabX ? 4u : 0u) | (XabNoSuccess ? 8u : 0u) | (abXNoSuccess ? 16u : 0u)) << 24;
-        s_state[k] = st;
-    }
-}
-
-// survivors of a CTA: one global cursor bump per CTA, states copied out of shared memory in order
-template <typename State>
-__device__ __forceinline__ void flush_survivors(const State *s_state, const int &s_count, uint32_t *s_base, uint32_t *__restrict__ q_count, State *__restrict__ queue) {
-    __syncthreads();
-    if (threadIdx.x == 0 && s_count) *s_base = atomicAdd(q_count, (uint32_t)s_count);
-    __syncthreads();
-    if ((int)threadIdx.x < s_count) queue[*s_base + threadIdx.x] = s_state[threadIdx.x];
-}
-
-__global__ void __launch_bounds__(EX_BLOCK) extract_contig_kernel(ExtractIdx x, const int32_t *__restrict__ phrases, const uint32_t *__restrict__ owner, const uint32_t *__restrict__ slot_off,
-                                                             uint32_t n_slots, RuleRec *__restrict__ rec_ab, uint32_t *__restrict__ q_count, ContigState *__restrict__ queue) {
-    __shared__ ContigState s_state[EX_BLOCK];
-    __shared__ int s_count;
-    __shared__ uint32_t s_base;
-    if (threadIdx.x == 0) s_count = 0;
-    __syncthreads();
-    const uint32_t slot1 = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot1 < n_slots) contig_phase1(x, phrases, owner, slot_off, slot1, rec_ab, s_state, &s_count);
-    flush_survivors(s_state, s_count, &s_base, q_count, queue);
-}
-
-// phase 2: one surviving occurrence per thread, full warps (ExtractPair.cu:1290-1792)
-__global__ void __launch_bounds__(EX_BLOCK) extract_contig_ext_kernel(ExtractIdx x, int G, const uint32_t *__restrict__ q_count, const ContigState *__restrict__ queue,
-                                                                 RuleRec *__restrict__ rec_Xab, RuleRec *__restrict__ rec_abX, RuleRec *__restrict__ rec_XabX) {
-    const uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (qi >= *q_count) return;
-    const ContigState st = queue[qi];
-    const uint32_t slot = (uint32_t)st.slot;
-    const int bnum = st.bnum, current_str = st.current_str, sen_target_begin = st.sen_target_begin, tempind = st.tempind;
-    const int longestmatch = (int)(st.packed & 0xFF);
-    const unsigned min_L = (st.packed >> 8) & 0xFF, max_R = (st.packed >> 16) & 0xFF;
-    bool abX = (st.packed >> 24) & 1u, Xab = (st.packed >> 25) & 1u, XabX = (st.packed >> 26) & 1u, XabNoSuccess = (st.packed >> 27) & 1u,
-         abXNoSuccess = (st.packed >> 28) & 1u;
-    const int globalc = G;
-    const int SPAN = CGX_MAX_RULE_SPAN;
-    const int ender = current_str + longestmatch - 1;
-    unsigned L, R, temp;
-    unsigned gap1_start = 0, gap1_end = 0, gap2_start = 0, gap2_end = 0, target_start = 0, target_end = 0;
-    bool next = true;
-    int XabCount = 0, abXCount = 0;
-    unsigned min_L_Xab = 255, max_R_Xab = 0, min_L_abX = 255, max_R_abX = 0, min_L_XabX = 255, max_R_XabX = 0;
 
     for (int i = 1; longestmatch + i <= SPAN && (abXNoSuccess || XabNoSuccess || XabX); i++) {
         // ---- X on the left: tokens current_str-i .. current_str-1 ----
@@ -372,17 +310,13 @@ __global__ void slots_pat1_kernel(const Pat1 *__restrict__ pat, int D1, uint32_t
     if (d < D1) cnt[d] = (uint32_t)min(pat[d].hit_count, CGX_SAMPLER_ONEGAP);
 }
 
-struct OneGapState {      // 32 bytes
-    int32_t slot, d, current_str, sen_target_begin, tempind;
-    uint32_t gap_start, gap_end;
-    uint32_t packed;      // firstEnd | min_L << 8 | max_R << 16 | left << 24 | right << 25
-};
-
-// phase 1: the seed aXb (ExtractPair.cu:458-600)
-__device__ __forceinline__ void onegap_phase1(const ExtractIdx &x, const Pat1 *__restrict__ pat, const uint32_t *__restrict__ owner, const uint64_t *__restrict__ hits1,
-                                              const uint32_t *__restrict__ slot_off, uint32_t slot, int G, int pbits, RuleRec *__restrict__ rec_aXb,
-                                              OneGapState *s_state, int *s_count) {
-    const int d = (int)owner[slot];
+__global__ void __launch_bounds__(128) extract_onegap_kernel(ExtractIdx x, const Pat1 *__restrict__ pat, int D1, const uint64_t *__restrict__ hits1,
+                                                             const uint32_t *__restrict__ slot_off, uint32_t n_slots, int G, int D2, int pbits,
+                                                             RuleRec *__restrict__ rec_aXb, RuleRec *__restrict__ rec_XaXb,
+                                                             RuleRec *__restrict__ rec_aXbX) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_slots) return;
+    const int d = find_owner_u32(slot_off, D1, slot);
     const Pat1 p = pat[d];
     const int occ = sample_index((int)(slot - slot_off[d]), p.hit_count, CGX_SAMPLER_ONEGAP, 1.0f / (float)CGX_SAMPLER_ONEGAP);
     if (occ < 0) return;
@@ -407,44 +341,7 @@ __device__ __forceinline__ void onegap_phase1(const ExtractIdx &x, const Pat1 *_
     if ((target_start == 0 && target_end == 0) || min_L > max_R || gap1_start < target_start || gap1_end > target_end) return;   // :591-595
     if (next) emit(rec_aXb, slot, 2 * G + d, target_start, target_end, (int)gap1_start, (int)gap1_end, -1, -1);
     if (startLen + endLen + 2 > CGX_MAX_RULE_SYMBOLS) return;
-    if (firstEnd + 2 <= SPAN && (left || right)) {          // the extension loop would run at least once
-        const int k = atomicAdd(s_count, 1);
-        OneGapState st;
-        st.slot = (int32_t)slot; st.d = d; st.current_str = current_str; st.sen_target_begin = sen_target_begin; st.tempind = tempind;
-        st.gap_start = gap1_start; st.gap_end = gap1_end;
-        st.packed = (uint32_t)firstEnd | (min_L << 8) | (max_R << 16) | (left ? 1u << 24 : 0u) | (right ? 1u << 25 : 0u);
-        s_state[k] = st;
-    }
-}
-
-__global__ void __launch_bounds__(EX_BLOCK) extract_onegap_kernel(ExtractIdx x, const Pat1 *__restrict__ pat, const uint32_t *__restrict__ owner, const uint64_t *__restrict__ hits1,
-                                                             const uint32_t *__restrict__ slot_off, uint32_t n_slots, int G, int pbits,
-                                                             RuleRec *__restrict__ rec_aXb, uint32_t *__restrict__ q_count, OneGapState *__restrict__ queue) {
-    __shared__ OneGapState s_state[EX_BLOCK];
-    __shared__ int s_count;
-    __shared__ uint32_t s_base;
-    if (threadIdx.x == 0) s_count = 0;
-    __syncthreads();
-    const uint32_t slot1 = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot1 < n_slots) onegap_phase1(x, pat, owner, hits1, slot_off, slot1, G, pbits, rec_aXb, s_state, &s_count);
-    flush_survivors(s_state, s_count, &s_base, q_count, queue);
-}
-
-// phase 2: XaXb / aXbX of one surviving seed per thread, full warps (ExtractPair.cu:600-887)
-__global__ void __launch_bounds__(EX_BLOCK) extract_onegap_ext_kernel(ExtractIdx x, int G, int D1, int D2, const uint32_t *__restrict__ q_count, const OneGapState *__restrict__ queue,
-                                                                 RuleRec *__restrict__ rec_XaXb, RuleRec *__restrict__ rec_aXbX) {
-    const uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (qi >= *q_count) return;
-    const OneGapState st = queue[qi];
-    const uint32_t slot = (uint32_t)st.slot;
-    const int d = st.d, current_str = st.current_str, sen_target_begin = st.sen_target_begin, tempind = st.tempind;
-    const int firstEnd = (int)(st.packed & 0xFF);
-    const unsigned min_L = (st.packed >> 8) & 0xFF, max_R = (st.packed >> 16) & 0xFF;
-    bool left = (st.packed >> 24) & 1u, right = (st.packed >> 25) & 1u, next = true;
-    const int SPAN = CGX_MAX_RULE_SPAN;
-    const int ender = current_str + firstEnd;
-    unsigned target_start = 0, target_end = 0;
-    const unsigned originalGapStart = st.gap_start, originalGapEnd = st.gap_end;
+    const unsigned originalGapStart = gap1_start, originalGapEnd = gap1_end;
     unsigned min_XaXb = 255, max_XaXb = 0, min_aXbX = 255, max_aXbX = 0, L, R, temp;
     for (int i = 1; firstEnd + 1 + i <= SPAN && (left || right); i++) {
         temp = (left && current_str - i >= 0) ? __ldg(&x.xw[current_str - i]) : 0u;
@@ -506,12 +403,12 @@ __global__ void slots_pat2_kernel(const Pat2 *__restrict__ pat, int D2, uint32_t
     if (d < D2) cnt[d] = (uint32_t)min(pat[d].hit_count, CGX_SAMPLER_TWOGAP);
 }
 
-__global__ void __launch_bounds__(128) extract_twogap_kernel(ExtractIdx x, const Pat2 *__restrict__ pat2, const Pat1 *__restrict__ pat1, const uint32_t *__restrict__ owner,
+__global__ void __launch_bounds__(128) extract_twogap_kernel(ExtractIdx x, const Pat2 *__restrict__ pat2, const Pat1 *__restrict__ pat1, int D2,
                                                              const uint64_t *__restrict__ hits2, const uint32_t *__restrict__ slot_off, uint32_t n_slots,
                                                              int G, int pbits, RuleRec *__restrict__ rec_aXbXc) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= n_slots) return;
-    const int d = (int)owner[slot];
+    const int d = find_owner_u32(slot_off, D2, slot);
     const Pat2 p2 = pat2[d];
     const int occ = sample_index((int)(slot - slot_off[d]), p2.hit_count, CGX_SAMPLER_TWOGAP, 1.0f / (float)CGX_SAMPLER_TWOGAP);
     if (occ < 0) return;
@@ -573,26 +470,10 @@ void stage_extract(const Index &ix, Batch &b, cudaStream_t stream) {
     // algorithmic bytes (SURVEY 8d B_ext, lower bound): per sampled occurrence its SA / hit entry and slot owner (8 B), the
     // RLP + text words of the smallest source window it must inspect (phrase + one extension token per side: 8 B x 5)
     // and the L/R bytes of a 4-token target window (2 x 4) = 56 B; emitted cells are not counted
-    // slot -> pattern (4 B per slot, written by one warp per pattern)
-    uint32_t *own = b.slot_owner.get<uint32_t>((size_t)ns[0] + ns[1] + ns[2] + 1);
-    uint32_t *own0 = own, *own1 = own + ns[0], *own2 = own1 + ns[1];
-    if (ns[0]) PROF("extract_owner", (double)ns[0] * 4 + (double)G * 8, (slot_owner_kernel<<<cgx_div_up((size_t)G * 32, 256), 256, 0, stream>>>(so0, G, own0)));
-    if (ns[1]) PROF("extract_owner", (double)ns[1] * 4 + (double)D1 * 8, (slot_owner_kernel<<<cgx_div_up((size_t)D1 * 32, 256), 256, 0, stream>>>(so1, D1, own1)));
-    if (ns[2]) PROF("extract_owner", (double)ns[2] * 4 + (double)D2 * 8, (slot_owner_kernel<<<cgx_div_up((size_t)D2 * 32, 256), 256, 0, stream>>>(so2, D2, own2)));
-    uint32_t *qcnt = tot + 8;                                      // [0] contiguous, [1] one-gap survivors
-    CUDA_CHECK(cudaMemsetAsync(qcnt, 0, sizeof(uint32_t) * 2, stream));
-    ContigState *q0 = b.ex_queue0.get<ContigState>((size_t)ns[0] + 1);
-    OneGapState *q1 = b.ex_queue1.get<OneGapState>((size_t)ns[1] + 1);
-    if (ns[0]) {
-        PROF("extract_contig", (double)ns[0] * 56, (extract_contig_kernel<<<cgx_div_up(ns[0], EX_BLOCK), EX_BLOCK, 0, stream>>>(x, b.phrases.ptr<int32_t>(), own0, so0, ns[0], r0, qcnt, q0)));
-        PROF("extract_contig", 0.0, (extract_contig_ext_kernel<<<cgx_div_up(ns[0], EX_BLOCK), EX_BLOCK, 0, stream>>>(x, G, qcnt, q0, r1, r1 + ns[0], r2)));
-    }
-    if (ns[2]) PROF("extract_twogap", (double)ns[2] * 56, (extract_twogap_kernel<<<cgx_div_up(ns[2], 128), 128, 0, stream>>>(x, b.pat2.ptr<Pat2>(), b.pat1.ptr<Pat1>(), own2, b.hits2_sorted.ptr<uint64_t>(), so2, ns[2], G, b.pbits, r2 + ns[0])));
-    if (ns[1]) {
-        PROF("extract_onegap", (double)ns[1] * 56, (extract_onegap_kernel<<<cgx_div_up(ns[1], EX_BLOCK), EX_BLOCK, 0, stream>>>(x, b.pat1.ptr<Pat1>(), own1, b.hits1_sorted.ptr<uint64_t>(), so1, ns[1], G, b.pbits, r1 + (size_t)2 * ns[0], qcnt + 1, q1)));
-        PROF("extract_onegap", 0.0, (extract_onegap_ext_kernel<<<cgx_div_up(ns[1], EX_BLOCK), EX_BLOCK, 0, stream>>>(x, G, D1, D2, qcnt + 1, q1, r2 + (size_t)ns[0] + ns[2], r2 + (size_t)ns[0] + ns[2] + ns[1])));
-    }
-    b.launches += 8;
+    if (ns[0]) PROF("extract_contig", (double)ns[0] * 56, (extract_contig_kernel<<<cgx_div_up(ns[0], 128), 128, 0, stream>>>(x, b.phrases.ptr<int32_t>(), G, so0, ns[0], r0, r1, r1 + ns[0], r2)));
+    if (ns[2]) PROF("extract_twogap", (double)ns[2] * 56, (extract_twogap_kernel<<<cgx_div_up(ns[2], 128), 128, 0, stream>>>(x, b.pat2.ptr<Pat2>(), b.pat1.ptr<Pat1>(), D2, b.hits2_sorted.ptr<uint64_t>(), so2, ns[2], G, b.pbits, r2 + ns[0])));
+    if (ns[1]) PROF("extract_onegap", (double)ns[1] * 56, (extract_onegap_kernel<<<cgx_div_up(ns[1], 128), 128, 0, stream>>>(x, b.pat1.ptr<Pat1>(), D1, b.hits1_sorted.ptr<uint64_t>(), so1, ns[1], G, D2, b.pbits, r1 + (size_t)2 * ns[0], r2 + (size_t)ns[0] + ns[2], r2 + (size_t)ns[0] + ns[2] + ns[1])));
+    b.launches += 3;
 }
 
 }  // namespace cgx

@@ -437,15 +437,20 @@ void stage_onegap_join(const Index &ix, Batch &b, cudaStream_t stream) {
 // two-gap: parent hits (p, L) of aXb extended by the single token c
 //   c at p+L+1+g2, g2 >= 1, (L+1)+g2+1 <= 15  ->  g2 <= 13-L                      (GappyLook.cu:595-655)
 // ------------------------------------------------------------------------------------------------
-__global__ void j2_setup_kernel(const Pat2 *__restrict__ pat2, int D2, PackTab tab, int cbits, uint8_t *__restrict__ has_child) {
+// child_sig[d1]: 64-bit signature of the tokens c for which aXbXc is a pattern of the batch (bit = 6-bit hash of c); 0 = the
+// parent has no child.  A parent has ~5 children on average, so the signature rejects ~90 % of the candidate tokens before
+// they cost a probe of the pattern table (round 1c: every admissible width of every parent hit probed the table).
+__device__ __forceinline__ unsigned sig_bit(uint32_t c) { return (c * 0x9E3779B1u) >> 26; }
+
+__global__ void j2_setup_kernel(const Pat2 *__restrict__ pat2, int D2, PackTab tab, int cbits, unsigned long long *__restrict__ child_sig) {
     int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= D2) return;
     const Pat2 p = pat2[d];
     pt_insert(tab, ((uint64_t)(uint32_t)p.pat1 << cbits) | (uint64_t)(uint32_t)p.ctok, (uint64_t)d);
-    if (!has_child[p.pat1]) has_child[p.pat1] = 1;
+    atomicOr(&child_sig[p.pat1], 1ull << sig_bit((uint32_t)p.ctok));
 }
 
-__global__ void __launch_bounds__(256) j2_scan_kernel(const uint64_t *__restrict__ hits1, size_t H1, int pbits, const uint8_t *__restrict__ has_child,
+__global__ void __launch_bounds__(256) j2_scan_kernel(const uint64_t *__restrict__ hits1, size_t H1, int pbits, const unsigned long long *__restrict__ child_sig,
                                                       const int32_t *__restrict__ str, const uint32_t *__restrict__ gapw,
                                                       const PackTab tab, int cbits,
                                                       unsigned long long *__restrict__ counter, uint64_t *__restrict__ hits, size_t cap) {
@@ -455,11 +460,13 @@ __global__ void __launch_bounds__(256) j2_scan_kernel(const uint64_t *__restrict
     const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned active = 0, probes = 0;
     uint32_t bits = 0, d1 = 0;
+    unsigned long long sig = 0;
     int p = 0, L = 0;
     if (k < H1) {
         const uint64_t hk = hits1[k];
         d1 = (uint32_t)(hk >> (pbits + 4));
-        if (has_child[d1]) {
+        sig = __ldg(&child_sig[d1]);
+        if (sig) {
             p = (int)((hk >> 4) & ((1ull << pbits) - 1)); L = (int)(hk & 15);
             const uint32_t w = __ldg(&gapw[p + L + 1]);
             const int run = (int)((w >> 16) & 15u);
@@ -479,6 +486,8 @@ __global__ void __launch_bounds__(256) j2_scan_kernel(const uint64_t *__restrict
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) if (rr[u]) cc[u] = (uint32_t)__ldg(&str[rr[u]]);
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (rr[u] && !((sig >> sig_bit(cc[u])) & 1ull)) rr[u] = 0;      // not a child token of this parent
 #pragma unroll
         for (int u = 0; u < 4; u++) if (rr[u]) sv[u] = pt_first(tab, ((uint64_t)d1 << cbits) | (uint64_t)cc[u], &ss[u]);
 #pragma unroll
@@ -506,19 +515,19 @@ void stage_twogap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     CGX_REQUIRE_BATCH(cgx_bits_for((uint64_t)b.D1) + cbits + d2bits <= 63, "%d x %d patterns do not fit the packed two-gap pattern table", b.D1, D2);
     const uint32_t slots_n = pt_slots_for((size_t)D2);
     PackTab tab{b.j_hash.get<unsigned long long>(slots_n), slots_n - 1, d2bits};
-    uint8_t *has_child = b.j_aflag.get<uint8_t>((size_t)b.D1 + 4);
+    unsigned long long *child_sig = b.j_aflag.get<unsigned long long>((size_t)b.D1 + 1);
     uint32_t *tot = b.counters.get<uint32_t>(32);
     unsigned long long *ctr = (unsigned long long *)(tot + 4);
     CUDA_CHECK(cudaMemsetAsync(tab.slots, 0xff, sizeof(unsigned long long) * (size_t)slots_n, stream));
-    CUDA_CHECK(cudaMemsetAsync(has_child, 0, (size_t)b.D1, stream));
-    PROF("join_setup", (double)D2 * (16 + 8), (j2_setup_kernel<<<cgx_div_up(D2, 256), 256, 0, stream>>>(b.pat2.ptr<Pat2>(), D2, tab, cbits, has_child)));
+    CUDA_CHECK(cudaMemsetAsync(child_sig, 0, sizeof(unsigned long long) * (size_t)b.D1, stream));
+    PROF("join_setup", (double)D2 * (16 + 8), (j2_setup_kernel<<<cgx_div_up(D2, 256), 256, 0, stream>>>(b.pat2.ptr<Pat2>(), D2, tab, cbits, child_sig)));
     b.launches++;
     const size_t H1 = (size_t)b.hits1;
     unsigned long long host_ctr[3] = {0, 0, 0};
     while (true) {
         uint64_t *hits = b.hit_keys.get<uint64_t>(b.hit_cap);
         CUDA_CHECK(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long) * 3, stream));
-        PROF("join_twogap", 0.0, (j2_scan_kernel<<<cgx_div_up(H1, 256), 256, 0, stream>>>(b.hits1_sorted.ptr<uint64_t>(), H1, b.pbits, has_child, ix.str.ptr<int32_t>(),
+        PROF("join_twogap", 0.0, (j2_scan_kernel<<<cgx_div_up(H1, 256), 256, 0, stream>>>(b.hits1_sorted.ptr<uint64_t>(), H1, b.pbits, child_sig, ix.str.ptr<int32_t>(),
                                                            ix.gapw.ptr<uint32_t>(), tab, cbits, ctr, hits, b.hit_cap)));
         b.launches += 1;
         read_u64s(host_ctr, ctr, 3, stream);

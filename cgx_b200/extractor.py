@@ -198,6 +198,13 @@ class GrammarExtractor:
         v2 = np.ascontiguousarray(v2, dtype=np.float32)
         self._check(self.L.cgx_lex_load(self.h, _p(f, C.c_int32), _p(e, C.c_int32), _p(v1, C.c_float), _p(v2, C.c_float), len(f)), "cgx_lex_load")
 
+    def save_index(self, path):
+        self._check(self.L.cgx_index_save(self.h, str(path).encode()), "cgx_index_save")
+
+    def load_index(self, path):
+        self._check(self.L.cgx_index_load(self.h, str(path).encode()), "cgx_index_load")
+        return self.index_info()
+
     def index_info(self):
         info = IndexInfo()
         self.L.cgx_index_info(self.h, C.byref(info))

@@ -75,6 +75,7 @@ typedef struct {
     int batch_queries;   /* extension: queries per GPU batch (0 = even split over the GPUs, at most CGXH_DEFAULT_BATCH) */
     int writer_threads;
     int quiet;
+    const char *index_file;   /* extension: persisted GPU index (cgx_index_load when it exists, else build + cgx_index_save) */
 } cgxh_options_t;
 int cgxh_run(const cgxh_options_t *opt);
 

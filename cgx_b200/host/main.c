@@ -1,7 +1,8 @@
 /* strmatchcuda -- drop-in command line of the reference (Main.c:28-86): same getopt string "hl:t:s:",
  * exactly six positionals (source, query, target, alignment, lex file, output directory), help + exit(0)
  * otherwise.  Extensions that do not disturb the contract: -g <gpus>, -b <queries per batch>,
- * -w <writer threads>, -q (quiet). */
+ * -w <writer threads>, -q (quiet), -i <index file> (persisted GPU index: loaded when the file exists -- alignment and
+ * lexical files are then not parsed and no suffix array is built -- else built and saved there). */
 #include "cgx_host.h"
 #include <stdio.h>
 #include <stdlib.h>
@@ -9,7 +10,7 @@
 
 static void print_help(void) {
     printf("\nGPU source codes for gappy extraction. Please check your input arguments.\n\n"
-           "usage: strmatchcuda [-l minmatchlen] [-t fingerlen] [-s timefile] [-g gpus] [-b batch] [-w threads] [-q]\n"
+           "usage: strmatchcuda [-l minmatchlen] [-t fingerlen] [-s timefile] [-g gpus] [-b batch] [-w threads] [-i index_file] [-q]\n"
            "       <source_corpus> <query_file> <target_corpus> <alignment_file> <lex_file> <output_dir>\n");
     exit(0);
 }
@@ -18,8 +19,8 @@ int main(int argc, char **argv) {
     cgxh_options_t o;
     int ch, errflg = 0;
     o.reffile = o.qryfile = o.reftargetfile = o.align = o.wordscdec = o.destinationDirectory = o.timefile = NULL;
-    o.minmatchlen = 1; o.fingerlen = 10; o.n_gpus = 1; o.batch_queries = 0; o.writer_threads = 1; o.quiet = 0;
-    while (!errflg && (ch = getopt(argc, argv, "hl:t:s:g:b:w:q")) != -1) {
+    o.minmatchlen = 1; o.fingerlen = 10; o.n_gpus = 1; o.batch_queries = 0; o.writer_threads = 1; o.quiet = 0; o.index_file = NULL;
+    while (!errflg && (ch = getopt(argc, argv, "hl:t:s:g:b:w:i:q")) != -1) {
         switch (ch) {
         case 'h': print_help(); break;
         case 'l': o.minmatchlen = atoi(optarg); break;
@@ -28,6 +29,7 @@ int main(int argc, char **argv) {
         case 'g': o.n_gpus = atoi(optarg); break;
         case 'b': o.batch_queries = atoi(optarg); break;
         case 'w': o.writer_threads = atoi(optarg); break;
+        case 'i': o.index_file = optarg; break;
         case 'q': o.quiet = 1; break;
         case '?': fprintf(stderr, "Unknown option %c\n", optopt); errflg = 1; break;
         default: errflg = 1; break;

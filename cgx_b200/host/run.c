@@ -136,21 +136,37 @@ int cgxh_run(const cgxh_options_t *opt) {
     fprintf(stderr, "Reference toklen number is %lld HASH_COUNT %d\n", (long long)src.n, cgxh_vocab_size(src.vocab) - 2);
     if (cgxh_corpus_load(opt->reftargetfile, 0, &tgt)) return 1;
     fprintf(stderr, "Target Reference toklen number is %lld HASH_COUNT TARGET %d\n", (long long)tgt.n, cgxh_vocab_size(tgt.vocab) - 2);
-    if (cgxh_lex_load(opt->wordscdec, &src, &tgt, &lex)) return 1;
-    fprintf(stderr, "Lex File Word Possibility COUNTER: %lld\n", (long long)lex.count);
+    int have_index = 0;
+    if (opt->index_file) { FILE *fh = fopen(opt->index_file, "rb"); if (fh) { have_index = 1; fclose(fh); } }
+    memset(&lex, 0, sizeof lex);
+    memset(&al, 0, sizeof al);
+    if (!have_index) {
+        if (cgxh_lex_load(opt->wordscdec, &src, &tgt, &lex)) return 1;
+        fprintf(stderr, "Lex File Word Possibility COUNTER: %lld\n", (long long)lex.count);
+    }
     if (cgxh_queries_load(opt->qryfile, &src, &qry)) return 1;
     fprintf(stderr, "\nMax length of queries is %d\n", qry.max_len);
-    if (cgxh_alignment_load(opt->align, &src, &tgt, &al)) return 1;
+    if (!have_index && cgxh_alignment_load(opt->align, &src, &tgt, &al)) return 1;
     double t1 = now_s();
 
     int n_gpus = opt->n_gpus > 0 ? opt->n_gpus : 1;
     cgx_ctx_t **ctx = (cgx_ctx_t **)calloc((size_t)n_gpus, sizeof(cgx_ctx_t *));
     for (int g = 0; g < n_gpus; g++)
         if (cgx_create(g, &ctx[g])) { fprintf(stderr, "cgx_create(%d): %s\n", g, cgx_last_error(NULL)); return 1; }
-    if (cgx_index_build(ctx[0], src.tok, src.n, tgt.tok, tgt.n, al.RLP, al.L_tar, al.R_tar)) { fprintf(stderr, "cgx_index_build: %s\n", cgx_last_error(ctx[0])); return 1; }
-    if (cgx_lex_load(ctx[0], lex.f, lex.e, lex.v1, lex.v2, lex.count)) { fprintf(stderr, "cgx_lex_load: %s\n", cgx_last_error(ctx[0])); return 1; }
+    if (have_index) {
+        if (cgx_index_load(ctx[0], opt->index_file)) { fprintf(stderr, "cgx_index_load: %s\n", cgx_last_error(ctx[0])); return 1; }
+        fprintf(stderr, "index loaded from %s\n", opt->index_file);
+    } else {
+        if (cgx_index_build(ctx[0], src.tok, src.n, tgt.tok, tgt.n, al.RLP, al.L_tar, al.R_tar)) { fprintf(stderr, "cgx_index_build: %s\n", cgx_last_error(ctx[0])); return 1; }
+        if (cgx_lex_load(ctx[0], lex.f, lex.e, lex.v1, lex.v2, lex.count)) { fprintf(stderr, "cgx_lex_load: %s\n", cgx_last_error(ctx[0])); return 1; }
+        if (opt->index_file) {
+            if (cgx_index_save(ctx[0], opt->index_file)) { fprintf(stderr, "cgx_index_save: %s\n", cgx_last_error(ctx[0])); return 1; }
+            fprintf(stderr, "index saved to %s\n", opt->index_file);
+        }
+    }
     cgx_index_info_t ii;
     cgx_index_info(ctx[0], &ii);
+    if (ii.n != src.n || ii.m != tgt.n) { fprintf(stderr, "index file %s was built from another corpus (%lld / %lld tokens, corpus has %lld / %lld)\n", opt->index_file ? opt->index_file : "?", (long long)ii.n, (long long)ii.m, (long long)src.n, (long long)tgt.n); return 1; }
     fprintf(stderr, "SA Construction %.4f sec (GPU prefix doubling, %d rounds, %d-bit keys); auxiliary index %.4f sec; %.1f MB resident\n",
             ii.sa_build_ms / 1e3, ii.sa_rounds, ii.sa_key_bits, ii.aux_build_ms / 1e3, (double)ii.index_bytes / 1048576.0);
     if (n_gpus > 1 && cgx_index_broadcast(ctx, n_gpus)) { fprintf(stderr, "cgx_index_broadcast: %s\n", cgx_last_error(ctx[0])); return 1; }

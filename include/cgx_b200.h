@@ -87,6 +87,13 @@ int cgx_index_commit(cgx_ctx_t *ctx);                                      /* ma
  * their own communicator instead (cgx_index_export / cgx_index_alloc / cgx_index_commit). */
 int cgx_index_broadcast(cgx_ctx_t **ctxs, int n);
 
+/* Persisted index: every resident index array (text, suffix array, occurrence lists, bucket ids, alignment arrays, gap
+ * words, sorted lexical table) written to / read from one file, so that later runs on the same corpus skip the loaders'
+ * GPU work and the SA build.  The reference only has a dead stub of this (SuffixArray.c:208-230 "sa_precomp.txt"; README.md:85
+ * promises separating the one-time costs).  cgx_index_load replaces cgx_index_build + cgx_lex_load. */
+int cgx_index_save(cgx_ctx_t *ctx, const char *path);
+int cgx_index_load(cgx_ctx_t *ctx, const char *path);
+
 /* parity helpers: copy index arrays to the host */
 int cgx_index_copy_sa(cgx_ctx_t *ctx, int32_t *sa_out);                    /* n ints */
 int cgx_index_copy_inv(cgx_ctx_t *ctx, int which, int32_t *out);           /* which = 1..3, n ints */

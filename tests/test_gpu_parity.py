@@ -336,6 +336,49 @@ def test_oversized_batches_are_split(micro, micro_files, tmp_path, monkeypatch):
     assert c["files"] == micro[0].n_qry and c["only_a"] == 0 and c["only_b"] == 0 and c["float_mismatch"] == 0, c
 
 
+def test_persisted_index_round_trip(micro, micro_files, tmp_path):
+    """cgx_index_save / cgx_index_load: a context that loads the file answers a batch exactly like the one that built the
+    index (suffix array and every result array bit-identical); garbage and truncated files are refused; bin/strmatchcuda -i
+    builds + saves on the first run, loads on the second, and writes the same grammars."""
+    from cgx_b200.extractor import GrammarExtractor
+    _, lay = micro
+    a = GrammarExtractor(0)
+    a.build_index(lay)
+    path = tmp_path / "micro.cgxidx"
+    a.save_index(path)
+    b = GrammarExtractor(0)
+    info = b.load_index(path)
+    assert (info["n"], info["m"]) == (int(lay["n"]), int(lay["m"]))
+    assert np.array_equal(a.suffix_array(), b.suffix_array())
+    ra, rb = a.extract(lay["qry_tok"], lay["qry_off"]), b.extract(lay["qry_tok"], lay["qry_off"])
+    assert (ra.G, ra.D1, ra.D2) == (rb.G, rb.D1, rb.D2)
+    for name in ("phrase_id", "phrases", "pat1", "pat2", "q1_ids", "q2_ids"):
+        assert np.array_equal(getattr(ra, name), getattr(rb, name)), name
+    for k in range(3):
+        assert ra.rules[k].tobytes() == rb.rules[k].tobytes(), k
+    bad = tmp_path / "bad.cgxidx"
+    bad.write_bytes(b"not an index")
+    c = GrammarExtractor(0)
+    with pytest.raises(RuntimeError):
+        c.load_index(bad)
+    trunc = tmp_path / "trunc.cgxidx"
+    trunc.write_bytes(path.read_bytes()[: path.stat().st_size // 2])
+    with pytest.raises(RuntimeError):
+        c.load_index(trunc)
+    outs = []
+    idx = tmp_path / "cli.cgxidx"
+    for name in ("first", "second"):
+        out = tmp_path / name
+        out.mkdir()
+        r = subprocess.run([os.path.join(ROOT, "bin", "strmatchcuda"), "-i", str(idx), micro_files["f"], micro_files["q"], micro_files["e"], micro_files["a"],
+                            micro_files["lex"], str(out)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert ("index saved to" in r.stderr) == (name == "first") and ("index loaded from" in r.stderr) == (name == "second"), r.stderr[-1500:]
+        outs.append(out)
+    cmp = gc.compare_dirs(str(outs[0]), str(outs[1]), rtol=0, atol=0)
+    assert cmp["files"] == micro[0].n_qry and cmp["only_a"] == 0 and cmp["only_b"] == 0 and cmp["float_mismatch"] == 0, cmp
+
+
 def test_medium_scale_properties():
     """A corpus the oracle would need minutes for: size-independent properties only.
     SA is a permutation whose adjacent suffixes are in order; occurrence lists are position-sorted inside every
