@@ -53,9 +53,11 @@ static inline RadixPlan make_radix_plan(int begin_bit, int end_bit) {
     int total = end_bit - begin_bit;
     if (total < 1) total = 1;
     p.num_passes = (total + 7) / 8;
-    int base = total / p.num_passes, extra = total % p.num_passes, s = begin_bit;
+    // full 8-bit digits (the kernel specialised at compile time: half the ranking instructions of the runtime-width form),
+    // the remainder in the most significant pass
+    int s = begin_bit;
     for (int i = 0; i < p.num_passes; i++) {
-        p.bits[i] = base + (i < extra ? 1 : 0);
+        p.bits[i] = total - 8 * i >= 8 ? 8 : total - 8 * i;
         p.shift[i] = s;
         s += p.bits[i];
     }
@@ -83,6 +85,38 @@ __device__ __forceinline__ unsigned rs_match_digit(uint32_t d, int bits) {
         }
     }
     return peers;
+}
+// the same with the digit width known at compile time: per bit one bit-field extract, one ballot, one three-input logic op
+// (the runtime-width form spends ~7 instructions per bit on predicate bookkeeping -- cuobjdump, round 1c)
+// peers = AND of the ballots of my set bits, minus OR of the ballots of my clear bits: per bit one ballot and two predicated
+// logic ops (ptxas moves the digit's bits into predicates with one R2P)
+template <int B>
+__device__ __forceinline__ void rs_match_bit(unsigned &pos, unsigned &neg, uint32_t d) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 t, m;\n\t"
+        "and.b32 t, %2, %3;\n\t"
+        "setp.ne.u32 p, t, 0;\n\t"
+        "vote.sync.ballot.b32 m, p, 0xffffffff;\n\t"
+        "@p and.b32 %0, %0, m;\n\t"
+        "@!p or.b32 %1, %1, m;\n\t"
+        "}"
+        : "+r"(pos), "+r"(neg)
+        : "r"(d), "n"(1u << B));
+}
+template <int BITS>
+__device__ __forceinline__ unsigned rs_match_digit_ct(uint32_t d) {
+    unsigned pos = 0xffffffffu, neg = 0u;
+    if (BITS > 0) rs_match_bit<0>(pos, neg, d);
+    if (BITS > 1) rs_match_bit<1>(pos, neg, d);
+    if (BITS > 2) rs_match_bit<2>(pos, neg, d);
+    if (BITS > 3) rs_match_bit<3>(pos, neg, d);
+    if (BITS > 4) rs_match_bit<4>(pos, neg, d);
+    if (BITS > 5) rs_match_bit<5>(pos, neg, d);
+    if (BITS > 6) rs_match_bit<6>(pos, neg, d);
+    if (BITS > 7) rs_match_bit<7>(pos, neg, d);
+    return pos & ~neg;
 }
 __device__ __forceinline__ uint32_t rs_ld_status(const uint32_t *p) {
     uint32_t v;
@@ -144,7 +178,8 @@ static __global__ void __launch_bounds__(RS_BINS) rs_scan_hist_kernel(uint32_t *
 // with payloads) and 64-80 registers per thread: four (three with payloads) CTAs per SM.  (Round 1a kept the keys, their
 // ranks, staging positions and 64-bit output offsets in registers: 157 registers with payloads = one CTA per SM,
 // 12 % occupancy, 1.3 TB/s.)
-template <typename K, bool HAS_VALUES, typename S = uint32_t>
+// CT_BITS = 8: digit width fixed at compile time (bits == 8); CT_BITS = 0: runtime width (the remainder pass, tiny keys)
+template <typename K, bool HAS_VALUES, typename S = uint32_t, int CT_BITS = 0>
 __global__ void __launch_bounds__(RS_BLOCK, HAS_VALUES ? 3 : 4) rs_onesweep_kernel(const K *__restrict__ keys_in, K *__restrict__ keys_out,
                                                                   const uint32_t *__restrict__ vals_in, uint32_t *__restrict__ vals_out,
                                                                   size_t n, int shift, int bits, const uint32_t *__restrict__ digit_offset,
@@ -161,7 +196,7 @@ __global__ void __launch_bounds__(RS_BLOCK, HAS_VALUES ? 3 : 4) rs_onesweep_kern
     static_assert(RS_WARPS * RS_BINS * sizeof(uint16_t) <= RS_TILE * sizeof(uint32_t), "digit counters must fit the exchange buffer");
 
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t mask = (1u << bits) - 1u;
+    const uint32_t mask = CT_BITS ? (1u << CT_BITS) - 1u : (1u << bits) - 1u;
     if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
     for (int i = tid; i < RS_WARPS * RS_BINS / 2; i += RS_BLOCK) reinterpret_cast<uint32_t *>(s_raw)[i] = 0;
     __syncthreads();
@@ -194,7 +229,7 @@ __global__ void __launch_bounds__(RS_BLOCK, HAS_VALUES ? 3 : 4) rs_onesweep_kern
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; i++) {
         const uint32_t d = (uint32_t)(key[i] >> shift) & mask;
-        const unsigned peers = rs_match_digit(d, bits);
+        const unsigned peers = CT_BITS ? rs_match_digit_ct<CT_BITS ? CT_BITS : 1>(d) : rs_match_digit(d, bits);
         const uint32_t base = s_warp_hist[warp][d];            // every peer reads the same counter (broadcast)
         __syncwarp();
         if ((peers & lt) == 0) s_warp_hist[warp][d] = (uint16_t)(base + __popc(peers));   // lowest peer lane updates it
@@ -302,22 +337,26 @@ void radix_sort(K *keys, K *keys_tmp, uint32_t *vals, uint32_t *vals_tmp, size_t
     K *kin = keys, *kout = keys_tmp;
     uint32_t *vin = vals, *vout = vals_tmp;
     const size_t smem = rs_smem_bytes<K>(vals != nullptr);
-    CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, true, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<K>(true)));
-    CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, false, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<K>(false)));
-    CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, true, uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<K>(true)));
-    CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, false, uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<K>(false)));
+    CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, true, uint32_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<K>(true)));
+    CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, false, uint32_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<K>(false)));
+    CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, true, uint32_t, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<K>(true)));
+    CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, false, uint32_t, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<K>(false)));
+    CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, true, uint64_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<K>(true)));
+    CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, false, uint64_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<K>(false)));
     for (int p = 0; p < plan.num_passes; p++) {
         CUDA_CHECK(cudaMemsetAsync(status, 0, status_bytes, stream));
         const double bytes = (double)n * 2.0 * (sizeof(K) + (vals ? 4 : 0));
         const uint32_t *off = hist + p * RS_BINS;
-        if (vals && !wide)
-            PROF("radix_onesweep", bytes, (rs_onesweep_kernel<K, true, uint32_t><<<(unsigned)tiles, RS_BLOCK, smem, stream>>>(kin, kout, vin, vout, n, plan.shift[p], plan.bits[p], off, (uint32_t *)status, counters + p)));
-        else if (!vals && !wide)
-            PROF("radix_onesweep", bytes, (rs_onesweep_kernel<K, false, uint32_t><<<(unsigned)tiles, RS_BLOCK, smem, stream>>>(kin, kout, nullptr, nullptr, n, plan.shift[p], plan.bits[p], off, (uint32_t *)status, counters + p)));
-        else if (vals)
-            PROF("radix_onesweep", bytes, (rs_onesweep_kernel<K, true, uint64_t><<<(unsigned)tiles, RS_BLOCK, smem, stream>>>(kin, kout, vin, vout, n, plan.shift[p], plan.bits[p], off, (uint64_t *)status, counters + p)));
-        else
-            PROF("radix_onesweep", bytes, (rs_onesweep_kernel<K, false, uint64_t><<<(unsigned)tiles, RS_BLOCK, smem, stream>>>(kin, kout, nullptr, nullptr, n, plan.shift[p], plan.bits[p], off, (uint64_t *)status, counters + p)));
+        const bool ct8 = plan.bits[p] == 8 && !wide;
+#define CGX_RS_LAUNCH(V, ST, CT, vi, vo) \
+        PROF("radix_onesweep", bytes, (rs_onesweep_kernel<K, V, ST, CT><<<(unsigned)tiles, RS_BLOCK, smem, stream>>>(kin, kout, vi, vo, n, plan.shift[p], plan.bits[p], off, (ST *)status, counters + p)))
+        if (vals && ct8) CGX_RS_LAUNCH(true, uint32_t, 8, vin, vout);
+        else if (!vals && ct8) CGX_RS_LAUNCH(false, uint32_t, 8, nullptr, nullptr);
+        else if (vals && !wide) CGX_RS_LAUNCH(true, uint32_t, 0, vin, vout);
+        else if (!vals && !wide) CGX_RS_LAUNCH(false, uint32_t, 0, nullptr, nullptr);
+        else if (vals) CGX_RS_LAUNCH(true, uint64_t, 0, vin, vout);
+        else CGX_RS_LAUNCH(false, uint64_t, 0, nullptr, nullptr);
+#undef CGX_RS_LAUNCH
         if (launches) *launches += 1;
         std::swap(kin, kout);
         std::swap(vin, vout);
