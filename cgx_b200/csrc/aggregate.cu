@@ -75,7 +75,10 @@ __global__ void agg_hash_kernel(const RuleRec *__restrict__ rec, uint32_t cells,
 #pragma unroll
             for (int j = 0; j < 15; j++) tok[j] = j <= (int)r.end ? (uint32_t)__ldg(&tgt[r.tgt_start + j]) : 0u;
             int ns = 0, skip_to = -1;                             // same walk as target_symbols()
-            uint64_t hh = 0;
+            // two independent 32-bit multiplicative lanes per symbol (4 instructions; a 64-bit murmur round per symbol was
+            // ~20 and made this kernel issue-bound), one 64-bit finaliser per record.  Equal hashes are verified symbol by
+            // symbol in agg_group, so the hash only has to make collisions inside a <= 300-cell segment rare.
+            uint32_t h1 = (uint32_t)seed, h2 = (uint32_t)(seed >> 32);
 #pragma unroll
             for (int j = 0; j < 15; j++) {
                 if (j > (int)r.end) break;
@@ -84,10 +87,11 @@ __global__ void agg_hash_kernel(const RuleRec *__restrict__ rec, uint32_t cells,
                 if (r.gap1 != 255 && j >= (int)r.gap1 && j <= (int)r.gap1_1) { sym = 0xFFFFFFFFu; skip_to = r.gap1_1; }
                 else if (r.gap2 != 255 && j >= (int)r.gap2 && j <= (int)r.gap2_1) { sym = 0xFFFFFFFEu; skip_to = r.gap2_1; }
                 else sym = tok[j];
-                hh = mix64(hh ^ (uint64_t)sym) + 0x9e3779b97f4a7c15ULL;
+                h1 = (h1 ^ sym) * 0x9E3779B1u;
+                h2 = (h2 + sym) * 0x85EBCA77u + 0x165667B1u;
                 ns++;
             }
-            h = (mix64(hh ^ seed ^ (uint64_t)ns)) | 1ull;
+            h = mix64((((uint64_t)h1 << 32) | (uint64_t)h2) ^ (uint64_t)ns) | 1ull;
         }
         hash[i] = h;
         tag[i] = (uint32_t)h;

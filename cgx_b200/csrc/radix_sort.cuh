@@ -295,29 +295,17 @@ __global__ void __launch_bounds__(RS_BLOCK, HAS_VALUES ? 3 : 4) rs_onesweep_kern
         if (HAS_VALUES) s_vals[rank[i]] = val[i];
     }
     __syncthreads();
-    // ---- digit-contiguous, coalesced stores
-    // (output positions fit 32 bits: n < 2^32.  Full tiles -- all but the last -- store without bounds checks.)
-    if (full) {
+    // ---- digit-contiguous, coalesced stores.  (A separate check-free loop for full tiles was measured: 1488 -> 1376 SASS
+    // instructions but 4.88 -> 5.12 ms per 2^27-key sort; the single predicated loop stays.)
 #pragma unroll
-        for (int i = 0; i < RS_ITEMS; i++) {
-            const unsigned j = tid + i * RS_BLOCK;
-            const K k = s_keys[j];
-            const uint32_t d = (uint32_t)(k >> shift) & mask;
-            const uint32_t o = s_global_base[d] + j;
+    for (int i = 0; i < RS_ITEMS; i++) {
+        const unsigned j = tid + i * RS_BLOCK;
+        const K k = s_keys[j];
+        const uint32_t d = (uint32_t)(k >> shift) & mask;
+        const size_t o = (size_t)s_global_base[d] + j;
+        if (full || o < n) {
             keys_out[o] = k;
             if (HAS_VALUES) vals_out[o] = s_vals[j];
-        }
-    } else {
-#pragma unroll 1
-        for (int i = 0; i < RS_ITEMS; i++) {
-            const unsigned j = tid + i * RS_BLOCK;
-            const K k = s_keys[j];
-            const uint32_t d = (uint32_t)(k >> shift) & mask;
-            const uint32_t o = s_global_base[d] + j;
-            if (o < n) {
-                keys_out[o] = k;
-                if (HAS_VALUES) vals_out[o] = s_vals[j];
-            }
         }
     }
 }
