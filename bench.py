@@ -423,7 +423,10 @@ def gpu_arm(args):
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")       # per-launch DRAM bytes from the committed ncu --set full capture
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(tn, {}).get("dram_bytes_per_launch")
+            tr = json.load(open(tpath)).get(tn, {})
+            traffic = tr.get("dram_bytes_per_launch")
+            if traffic and tr.get("alg_bytes_of_captured_launch"):     # scale the captured launch to this run's average launch
+                traffic = traffic * (tvv["bytes"] / max(1, tvv["launches"])) / tr["alg_bytes_of_captured_launch"]
         roofline = {"bound": "hbm", "kernel": tn, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
                     "peak_source": peak_src, "share_of_step": tvv["ms"] / max(1e-9, sum(v["ms"] for v in prof.values())),
                     "avg_launch_ms": tvv["ms"] / max(1, tvv["launches"]), "alg_bytes_per_launch": tvv["bytes"] / max(1, tvv["launches"])}

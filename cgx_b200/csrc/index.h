@@ -14,11 +14,12 @@ struct SaStats {
 };
 
 struct SaWorkspace {
-    DevBuf keys, keys_tmp, vals, vals_tmp, rank, flags, total;
+    DevBuf keys, keys_tmp, vals, vals_tmp, rank, flags, total, head, excl, headpos, apos;
     RadixTemp radix;
     ScanTemp scan;
     void release() {
         keys.release(); keys_tmp.release(); vals.release(); vals_tmp.release(); rank.release(); flags.release(); total.release();
+        head.release(); excl.release(); headpos.release(); apos.release();
         radix.hist.release(); radix.status.release(); radix.counters.release();
         for (auto &l : scan.level) l.release();
     }
