@@ -154,15 +154,26 @@ __global__ void __launch_bounds__(256) agg_group_kernel(AggLayout lay, const Rul
     for (int k = 1; k < 4; k++) if (k < lay.n_regions && i >= lay.r[k].base) reg = k;
     const uint32_t pat = (uint32_t)(r.id - lay.r[reg].id_base);
     const uint32_t s0 = lay.r[reg].base + __ldg(&lay.r[reg].slot_off[pat]);
-    // the tags are scanned four at a time (aligned 16-byte loads; cells outside [s0, i) are masked by position)
+    // the tags are scanned four at a time (aligned 16-byte loads).  Only the first and the last group of four can hold cells
+    // outside [s0, i): they are checked with position masks, the groups in between with four bare compares.
     uint32_t first = i;
-    for (uint32_t base = s0 & ~3u; base < i && first == i; base += 4) {
+    auto check4 = [&](uint32_t base, bool masked) {
         const uint4 t4 = __ldg(reinterpret_cast<const uint4 *>(tag + base));
+        if (t4.x != t && t4.y != t && t4.z != t && t4.w != t) return;
         const uint32_t tt[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const uint32_t j = base + k;
-            if (tt[k] == t && j >= s0 && j < i && first == i && __ldg(&hash[j]) == h) first = j;
+            if (tt[k] == t && (!masked || (j >= s0 && j < i)) && first == i && __ldg(&hash[j]) == h) first = j;
+        }
+    };
+    {
+        uint32_t base = s0 & ~3u;
+        const uint32_t last = (i - 1) & ~3u;            // group of cell i - 1 (i > s0 below)
+        if (i > s0) {
+            check4(base, true);
+            for (base += 4; base < last && first == i; base += 4) check4(base, false);
+            if (first == i && last > (s0 & ~3u)) check4(last, true);
         }
     }
     const unsigned long long key = ((unsigned long long)(uint32_t)r.tgt_start << 32) | (unsigned long long)i;
