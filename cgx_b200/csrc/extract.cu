@@ -19,6 +19,15 @@
 //   kind 0 (ab)   : [ab: ns0]
 //   kind 1        : [Xab: ns0][abX: ns0][aXb: ns1]
 //   kind 2        : [XabX: ns0][aXbXc: ns2][XaXb: ns1][aXbX: ns1]          (ns0/1/2 = contiguous / one-gap / two-gap slots)
+//
+// Measured and dropped (round 1c, C2): the extension loops run with 6-8 of 32 lanes active (ncu: 5.9 / 8.5 active threads per
+// warp, SM pipes 75-80 % busy), so the survivors of the seed phase were compacted (a) inside the CTA through shared memory --
+// the retired threads keep their warp slots until the CTA ends, occupancy collapses: extract_onegap 9.8 -> 16.6 ms -- and
+// (b) through a global queue into a second kernel with full warps -- the extension phase then re-fetches the window sectors the
+// seed phase had just pulled into L1, and latency, not issue slots, is what it waits for: 9.8 -> 14.9 ms.  A slot -> pattern
+// array instead of the binary search costs 1.0 ms to fill and saves 0.2 ms.  (c) Persistent warps that queue the survivors of 8 chunks
+// of 32 slots in shared memory and run the extension phase on 32 of them at a time: extract_onegap 9.8 -> 23.8 ms, extract_contig
+// 6.1 -> 6.8 ms (every full warp then waits for its longest extension chain).  The one-thread-per-occurrence form stays.
 #include "batch.h"
 #include "prof.h"
 
@@ -82,39 +91,27 @@ __global__ void slots_contig_kernel(const int32_t *__restrict__ phrases, int G, 
     if (g < G) cnt[g] = (uint32_t)min(phrases[g * 4 + 1] - phrases[g * 4] + 1, CGX_SAMPLER);
 }
 
-// Contiguous and one-gap seeds run in two phases inside PERSISTENT warps.  Phase 1 (every sampled occurrence: owner, sample
-// index, seed span, the seed's own rule) keeps all lanes busy; the extension loops of phase 2 (X to the left / right) are
-// entered by a third of the occurrences and leave at different trip counts -- run in place they executed with 6-8 of 32
-// lanes active (ncu, round 1c: extract_contig 5.9, extract_onegap 8.5 active threads per warp, SM pipes 75-80 % busy).
-// Each warp therefore walks EX_CHUNKS chunks of 32 slots: the survivors of phase 1 are appended to a per-warp queue in
-// shared memory (one ballot), and whenever 32 are queued the warp runs phase 2 on them with every lane busy.  The warp
-// stays resident and phase 2 follows phase 1 of the same occurrence within a few chunks on the same SM, so the window
-// sectors are still in L1.  (Measured and dropped before this form: compaction across the CTA -- the retired threads keep
-// their warp slots until the CTA ends, extract_onegap 9.8 -> 16.6 ms -- and a global queue with a second kernel -- the
-// extension phase re-fetches the sectors, 9.8 -> 14.9 ms.)  Cells are slot-indexed, so queue order does not reach the results.
-constexpr int EX_BLOCK = 128;
-constexpr int EX_WARPS = EX_BLOCK / 32;
-constexpr int EX_CHUNKS = 8;                 // 32-slot chunks per warp
-constexpr int EX_QUEUE = 64;                 // queued survivors per warp (< 32 before a chunk, + <= 32 from it)
-
-
-struct ContigState {      // 24 bytes
-    int32_t slot, bnum, current_str, sen_target_begin, tempind;
-    uint32_t packed;      // longestmatch | min_L << 8 | max_R << 16 | flags << 24 (abX, Xab, XabX, XabNoSuccess, abXNoSuccess)
-};
-
-__device__ __forceinline__ bool contig_phase1(const ExtractIdx &x, const int32_t *__restrict__ phrases, int G, const uint32_t *__restrict__ slot_off,
-                                              uint32_t slot, RuleRec *__restrict__ rec_ab, ContigState &st) {
+__global__ void __launch_bounds__(128) extract_contig_kernel(ExtractIdx x, const int32_t *__restrict__ phrases, int G, const uint32_t *__restrict__ slot_off,
+                                                             uint32_t n_slots, RuleRec *__restrict__ rec_ab, RuleRec *__restrict__ rec_Xab,
+                                                             RuleRec *__restrict__ rec_abX, RuleRec *__restrict__ rec_XabX) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_slots) return;
     const int bnum = find_owner_u32(slot_off, G, slot);
     const int start = phrases[bnum * 4], end = phrases[bnum * 4 + 1], longestmatch = phrases[bnum * 4 + 2];
     const int occ = sample_index((int)(slot - slot_off[bnum]), end - start + 1, CGX_SAMPLER, 1.0f / (float)CGX_SAMPLER);
-    if (occ < 0) return false;
+    if (occ < 0) return;
     const int current_str = __ldg(&x.sa[start + occ]);
+    const int globalc = G;
     const int SPAN = CGX_MAX_RULE_SPAN;
+
     unsigned L, R, temp;
     int sen_target_begin = -1, tempind = 0;
     unsigned min_L = 255, max_R = 0;
-    bool abX = true, Xab = true, XabX = true, ab = true, XabNoSuccess = true, abXNoSuccess = true;
+    unsigned gap1_start = 0, gap1_end = 0, gap2_start = 0, gap2_end = 0, target_start = 0, target_end = 0;
+    bool next = true, abX = true, Xab = true, XabX = true, ab = true, XabNoSuccess = true, abXNoSuccess = true;
+    int XabCount = 0, abXCount = 0;
+    unsigned min_L_Xab = 255, max_R_Xab = 0, min_L_abX = 255, max_R_abX = 0, min_L_XabX = 255, max_R_XabX = 0;
+
     for (int k = current_str; k < current_str + longestmatch; k++) {
         temp = __ldg(&x.xw[k]);
         L = (temp >> 24) & 0xFF; R = (temp >> 16) & 0xFF;
@@ -135,34 +132,6 @@ __device__ __forceinline__ bool contig_phase1(const ExtractIdx &x, const int32_t
         emit(rec_ab, slot, bnum, min_L + sen_target_begin, max_R + sen_target_begin, -1, -1, -1, -1);
     if (longestmatch + 1 > CGX_MAX_RULE_SYMBOLS) { abX = false; Xab = false; }
     if (longestmatch + 2 > CGX_MAX_RULE_SYMBOLS) XabX = false;
-    // the extension loop runs while (abXNoSuccess || XabNoSuccess || XabX); with Xab, abX and XabX all false its first
-    // iteration only clears those flags and emits nothing, so such occurrences do not enter phase 2
-    if (longestmatch + 1 <= SPAN && (abXNoSuccess || XabNoSuccess || XabX) && (Xab || abX || XabX)) {
-        st.slot = (int32_t)slot; st.bnum = bnum; st.current_str = current_str; st.sen_target_begin = sen_target_begin; st.tempind = tempind;
-        st.packed = (uint32_t)longestmatch | (min_L << 8) | (max_R << 16) |
-                    ((uint32_t)(abX ? 1 : 0) | (Xab ? 2u : 0u) | (XabX ? 4u : 0u) | (XabNoSuccess ? 8u : 0u) | (abXNoSuccess ? 16u : 0u)) << 24;
-        return true;
-    }
-    return false;
-}
-
-// phase 2: X to the left / right of one surviving occurrence (ExtractPair.cu:1290-1792)
-__device__ __forceinline__ void contig_phase2(const ExtractIdx &x, int G, const ContigState &st, RuleRec *__restrict__ rec_Xab,
-                                              RuleRec *__restrict__ rec_abX, RuleRec *__restrict__ rec_XabX) {
-    const uint32_t slot = (uint32_t)st.slot;
-    const int bnum = st.bnum, current_str = st.current_str, sen_target_begin = st.sen_target_begin, tempind = st.tempind;
-    const int longestmatch = (int)(st.packed & 0xFF);
-    const unsigned min_L = (st.packed >> 8) & 0xFF, max_R = (st.packed >> 16) & 0xFF;
-    bool abX = (st.packed >> 24) & 1u, Xab = (st.packed >> 25) & 1u, XabX = (st.packed >> 26) & 1u, XabNoSuccess = (st.packed >> 27) & 1u,
-         abXNoSuccess = (st.packed >> 28) & 1u;
-    const int globalc = G;
-    const int SPAN = CGX_MAX_RULE_SPAN;
-    const int ender = current_str + longestmatch - 1;
-    unsigned L, R, temp;
-    unsigned gap1_start = 0, gap1_end = 0, gap2_start = 0, gap2_end = 0, target_start = 0, target_end = 0;
-    bool next = true;
-    int XabCount = 0, abXCount = 0;
-    unsigned min_L_Xab = 255, max_R_Xab = 0, min_L_abX = 255, max_R_abX = 0, min_L_XabX = 255, max_R_XabX = 0;
 
     for (int i = 1; longestmatch + i <= SPAN && (abXNoSuccess || XabNoSuccess || XabX); i++) {
         // ---- X on the left: tokens current_str-i .. current_str-1 ----
@@ -283,45 +252,6 @@ __device__ __forceinline__ void contig_phase2(const ExtractIdx &x, int G, const 
     }
 }
 
-// persistent warps: see the note above ContigState
-template <typename State, typename P1, typename P2>
-__device__ __forceinline__ void run_two_phase(uint32_t n_slots, State (*s_queue)[EX_QUEUE], P1 phase1, P2 phase2) {
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    State *q = s_queue[warp];
-    int qn = 0;
-    const uint32_t first = (blockIdx.x * (uint32_t)EX_WARPS + warp) * (uint32_t)(EX_CHUNKS * 32);
-    for (int c = 0; c < EX_CHUNKS; c++) {
-        const uint32_t slot = first + (uint32_t)c * 32u + lane;
-        if (first + (uint32_t)c * 32u >= n_slots) break;                   // warp-uniform
-        State st;
-        const bool go = slot < n_slots && phase1(slot, st);
-        const unsigned m = __ballot_sync(0xffffffffu, go);
-        if (go) q[qn + __popc(m & lanemask_lt())] = st;
-        qn += __popc(m);
-        __syncwarp();
-        if (qn >= 32) {
-            const State s2 = q[qn - 32 + (int)lane];
-            qn -= 32;
-            __syncwarp();
-            phase2(s2);
-            __syncwarp();
-        }
-    }
-    if ((int)lane < qn) {
-        const State s2 = q[lane];
-        phase2(s2);
-    }
-}
-
-__global__ void __launch_bounds__(EX_BLOCK) extract_contig_kernel(ExtractIdx x, const int32_t *__restrict__ phrases, int G, const uint32_t *__restrict__ slot_off,
-                                                             uint32_t n_slots, RuleRec *__restrict__ rec_ab, RuleRec *__restrict__ rec_Xab,
-                                                             RuleRec *__restrict__ rec_abX, RuleRec *__restrict__ rec_XabX) {
-    __shared__ ContigState s_queue[EX_WARPS][EX_QUEUE];
-    run_two_phase<ContigState>(
-        n_slots, s_queue, [&](uint32_t slot, ContigState &st) { return contig_phase1(x, phrases, G, slot_off, slot, rec_ab, st); },
-        [&](const ContigState &st) { contig_phase2(x, G, st, rec_Xab, rec_abX, rec_XabX); });
-}
-
 // ------------------------------------------------------------------------------------------------
 // boundary helpers for the gappy seeds
 // ------------------------------------------------------------------------------------------------
@@ -382,20 +312,16 @@ __global__ void slots_pat1_kernel(const Pat1 *__restrict__ pat, int D1, uint32_t
     if (d < D1) cnt[d] = (uint32_t)min(pat[d].hit_count, CGX_SAMPLER_ONEGAP);
 }
 
-struct OneGapState {      // 32 bytes
-    int32_t slot, d, current_str, sen_target_begin, tempind;
-    uint32_t gap_start, gap_end;
-    uint32_t packed;      // firstEnd | min_L << 8 | max_R << 16 | left << 24 | right << 25
-};
-
-// phase 1: the seed aXb (ExtractPair.cu:458-600)
-__device__ __forceinline__ bool onegap_phase1(const ExtractIdx &x, const Pat1 *__restrict__ pat, int D1, const uint64_t *__restrict__ hits1,
-                                              const uint32_t *__restrict__ slot_off, uint32_t slot, int G, int pbits, RuleRec *__restrict__ rec_aXb,
-                                              OneGapState &st) {
+__global__ void __launch_bounds__(128) extract_onegap_kernel(ExtractIdx x, const Pat1 *__restrict__ pat, int D1, const uint64_t *__restrict__ hits1,
+                                                             const uint32_t *__restrict__ slot_off, uint32_t n_slots, int G, int D2, int pbits,
+                                                             RuleRec *__restrict__ rec_aXb, RuleRec *__restrict__ rec_XaXb,
+                                                             RuleRec *__restrict__ rec_aXbX) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_slots) return;
     const int d = find_owner_u32(slot_off, D1, slot);
     const Pat1 p = pat[d];
     const int occ = sample_index((int)(slot - slot_off[d]), p.hit_count, CGX_SAMPLER_ONEGAP, 1.0f / (float)CGX_SAMPLER_ONEGAP);
-    if (occ < 0) return false;
+    if (occ < 0) return;
     const uint64_t hk = hits1[(size_t)p.hit_start + occ];
     const int current_str = (int)((hk >> 4) & ((1ull << pbits) - 1)), firstEnd = (int)(hk & 15);
     const int startLen = p.ls, endLen = p.le;
@@ -403,7 +329,7 @@ __device__ __forceinline__ bool onegap_phase1(const ExtractIdx &x, const Pat1 *_
     const int ender = current_str + firstEnd;
     unsigned min_L, max_R;
     int sen_target_begin, tempind;
-    if (!boundary_fast(x, current_str + startLen, ender - endLen, &min_L, &max_R, &sen_target_begin, &tempind)) return false;
+    if (!boundary_fast(x, current_str + startLen, ender - endLen, &min_L, &max_R, &sen_target_begin, &tempind)) return;
     unsigned gap1_start = min_L + sen_target_begin, gap1_end = max_R + sen_target_begin;
     unsigned target_start = 0, target_end = 0;
     bool next = true, left = true, right = true;
@@ -414,30 +340,10 @@ __device__ __forceinline__ bool onegap_phase1(const ExtractIdx &x, const Pat1 *_
     else if (re == 2) { next = false; right = false; }
     else if (re == 3) { next = false; left = false; }
     else if (re == 4) { next = false; left = false; right = false; }
-    if ((target_start == 0 && target_end == 0) || min_L > max_R || gap1_start < target_start || gap1_end > target_end) return false;   // :591-595
+    if ((target_start == 0 && target_end == 0) || min_L > max_R || gap1_start < target_start || gap1_end > target_end) return;   // :591-595
     if (next) emit(rec_aXb, slot, 2 * G + d, target_start, target_end, (int)gap1_start, (int)gap1_end, -1, -1);
-    if (startLen + endLen + 2 > CGX_MAX_RULE_SYMBOLS) return false;
-    if (firstEnd + 2 <= SPAN && (left || right)) {          // the extension loop would run at least once
-        st.slot = (int32_t)slot; st.d = d; st.current_str = current_str; st.sen_target_begin = sen_target_begin; st.tempind = tempind;
-        st.gap_start = gap1_start; st.gap_end = gap1_end;
-        st.packed = (uint32_t)firstEnd | (min_L << 8) | (max_R << 16) | (left ? 1u << 24 : 0u) | (right ? 1u << 25 : 0u);
-        return true;
-    }
-    return false;
-}
-
-// phase 2: XaXb / aXbX of one surviving seed (ExtractPair.cu:600-887)
-__device__ __forceinline__ void onegap_phase2(const ExtractIdx &x, int G, int D1, int D2, const OneGapState &st, RuleRec *__restrict__ rec_XaXb,
-                                              RuleRec *__restrict__ rec_aXbX) {
-    const uint32_t slot = (uint32_t)st.slot;
-    const int d = st.d, current_str = st.current_str, sen_target_begin = st.sen_target_begin, tempind = st.tempind;
-    const int firstEnd = (int)(st.packed & 0xFF);
-    const unsigned min_L = (st.packed >> 8) & 0xFF, max_R = (st.packed >> 16) & 0xFF;
-    bool left = (st.packed >> 24) & 1u, right = (st.packed >> 25) & 1u, next = true;
-    const int SPAN = CGX_MAX_RULE_SPAN;
-    const int ender = current_str + firstEnd;
-    unsigned target_start = 0, target_end = 0;
-    const unsigned originalGapStart = st.gap_start, originalGapEnd = st.gap_end;
+    if (startLen + endLen + 2 > CGX_MAX_RULE_SYMBOLS) return;
+    const unsigned originalGapStart = gap1_start, originalGapEnd = gap1_end;
     unsigned min_XaXb = 255, max_XaXb = 0, min_aXbX = 255, max_aXbX = 0, L, R, temp;
     for (int i = 1; firstEnd + 1 + i <= SPAN && (left || right); i++) {
         temp = (left && current_str - i >= 0) ? __ldg(&x.xw[current_str - i]) : 0u;
@@ -489,16 +395,6 @@ __device__ __forceinline__ void onegap_phase2(const ExtractIdx &x, int G, int D1
             }
         } else right = false;
     }
-}
-
-__global__ void __launch_bounds__(EX_BLOCK) extract_onegap_kernel(ExtractIdx x, const Pat1 *__restrict__ pat, int D1, const uint64_t *__restrict__ hits1,
-                                                             const uint32_t *__restrict__ slot_off, uint32_t n_slots, int G, int D2, int pbits,
-                                                             RuleRec *__restrict__ rec_aXb, RuleRec *__restrict__ rec_XaXb,
-                                                             RuleRec *__restrict__ rec_aXbX) {
-    __shared__ OneGapState s_queue[EX_WARPS][EX_QUEUE];
-    run_two_phase<OneGapState>(
-        n_slots, s_queue, [&](uint32_t slot, OneGapState &st) { return onegap_phase1(x, pat, D1, hits1, slot_off, slot, G, pbits, rec_aXb, st); },
-        [&](const OneGapState &st) { onegap_phase2(x, G, D1, D2, st, rec_XaXb, rec_aXbX); });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -576,9 +472,9 @@ void stage_extract(const Index &ix, Batch &b, cudaStream_t stream) {
     // algorithmic bytes (SURVEY 8d B_ext, lower bound): per sampled occurrence its SA / hit entry and slot owner (8 B), the
     // RLP + text words of the smallest source window it must inspect (phrase + one extension token per side: 8 B x 5)
     // and the L/R bytes of a 4-token target window (2 x 4) = 56 B; emitted cells are not counted
-    if (ns[0]) PROF("extract_contig", (double)ns[0] * 56, (extract_contig_kernel<<<cgx_div_up(ns[0], EX_BLOCK * EX_CHUNKS), EX_BLOCK, 0, stream>>>(x, b.phrases.ptr<int32_t>(), G, so0, ns[0], r0, r1, r1 + ns[0], r2)));
+    if (ns[0]) PROF("extract_contig", (double)ns[0] * 56, (extract_contig_kernel<<<cgx_div_up(ns[0], 128), 128, 0, stream>>>(x, b.phrases.ptr<int32_t>(), G, so0, ns[0], r0, r1, r1 + ns[0], r2)));
     if (ns[2]) PROF("extract_twogap", (double)ns[2] * 56, (extract_twogap_kernel<<<cgx_div_up(ns[2], 128), 128, 0, stream>>>(x, b.pat2.ptr<Pat2>(), b.pat1.ptr<Pat1>(), D2, b.hits2_sorted.ptr<uint64_t>(), so2, ns[2], G, b.pbits, r2 + ns[0])));
-    if (ns[1]) PROF("extract_onegap", (double)ns[1] * 56, (extract_onegap_kernel<<<cgx_div_up(ns[1], EX_BLOCK * EX_CHUNKS), EX_BLOCK, 0, stream>>>(x, b.pat1.ptr<Pat1>(), D1, b.hits1_sorted.ptr<uint64_t>(), so1, ns[1], G, D2, b.pbits, r1 + (size_t)2 * ns[0], r2 + (size_t)ns[0] + ns[2], r2 + (size_t)ns[0] + ns[2] + ns[1])));
+    if (ns[1]) PROF("extract_onegap", (double)ns[1] * 56, (extract_onegap_kernel<<<cgx_div_up(ns[1], 128), 128, 0, stream>>>(x, b.pat1.ptr<Pat1>(), D1, b.hits1_sorted.ptr<uint64_t>(), so1, ns[1], G, D2, b.pbits, r1 + (size_t)2 * ns[0], r2 + (size_t)ns[0] + ns[2], r2 + (size_t)ns[0] + ns[2] + ns[1])));
     b.launches += 3;
 }
 
