@@ -213,6 +213,10 @@ __global__ void __launch_bounds__(J1_BLOCK) j1_scan_kernel(const J1Args a) {
 // phrase" for m = 1..3 (three L2-resident bitmaps), and every (position, m) that is one runs the same 13-lane window
 // logic as above on shared memory.  HBM traffic: 16 B per corpus position + the pattern-table probes.
 // ------------------------------------------------------------------------------------------------
+// (Measured and dropped, round 1d: candidates that pass the bitmap filters pushed to a per-warp FIFO in shared memory and probed 32
+// at a time -- the probe / resolve code runs with one or two active lanes in place -- 13.1 -> 17.2 ms: the in-place form issues
+// the three first-slot loads of a step together and overlaps them with the next step's window work, the drained form waits for
+// every probe.)
 constexpr int JP_TILE = 256;         // positions per CTA
 constexpr int JP_HALO = 17;          // q <= p + 3 + 13
 
@@ -232,58 +236,11 @@ struct JPArgs {
     int32_t *missing;
 };
 
-// Candidates that survive the bitmap filters are sparse (one or two lanes per (position, ls, le) step), so the table probe
-// and the hit staging do not run in place: every warp appends its candidates to a FIFO in shared memory (one ballot per
-// push) and probes 32 of them at a time with every lane busy (ncu, round 1d: the probe / resolve code ran with one active
-// lane).  FIFO order keeps the hits of one (pattern, position) in ascending length, which the hit sort relies on.
-constexpr int JQ_CAP = 128;          // candidates per warp: < 32 left over + <= 96 from one (position, ls) step
-struct JCand {
-    uint64_t key;                    // pattern-table key
-    uint32_t p;                      // corpus position of a
-    uint32_t meta;                   // length - 1 | miss << 8
-};
-
-__device__ __forceinline__ void jq_push(bool on, const JCand &c, JCand *__restrict__ q, int head, int &count) {     // all 32 lanes call
-    const unsigned m = __ballot_sync(0xffffffffu, on);
-    if (on) q[(head + count + __popc(m & lanemask_lt())) & (JQ_CAP - 1)] = c;
-    count += __popc(m);
-}
-
-// probe the first min(count, 32) queued candidates (all 32 lanes call)
-__device__ __forceinline__ void jq_drain(const JPArgs &a, JCand *__restrict__ q, int &head, int &count, uint64_t *__restrict__ stage, int &staged) {
-    __syncwarp();
-    const unsigned lane = threadIdx.x & 31;
-    const int take = min(count, 32);
-    const bool on = (int)lane < take;
-    JCand c;
-    c.key = 0; c.p = 0; c.meta = 0;
-    if (on) c = q[(head + (int)lane) & (JQ_CAP - 1)];
-    uint64_t v = 0;
-    bool found = false;
-    if (on) {
-        uint32_t ss;
-        const ulonglong2 sv = ht_first(a.slots, a.mask, c.key, &ss);
-        found = ht_resolve(a.slots, a.mask, c.key, ss, sv, &v);
-    }
-    if (found && (c.meta >> 8)) {                                  // only counted: what the frequent-pair table would miss
-        if (v & 0x80000000u) atomicAdd(&a.missing[v & 0x7fffffffu], 1);
-        found = false;
-    }
-    const uint64_t hit = ((uint64_t)(v & 0x7fffffffu) << a.pshift) | ((uint64_t)c.p << 4) | (uint64_t)(c.meta & 0xffu);
-    stage_push(found, hit, stage, staged);
-    if (staged > ST_CAP - 32) stage_flush(stage, staged, &a.counter[0], a.hits, a.cap);
-    head = (head + take) & (JQ_CAP - 1);
-    count -= take;
-    __syncwarp();
-}
-
 __global__ void __launch_bounds__(JP_TILE) j1_pos_kernel(const JPArgs a) {
     __shared__ int4 s_win[JP_TILE + JP_HALO];
     __shared__ uint64_t s_stage[JP_TILE / 32][ST_CAP];
-    __shared__ JCand s_queue[JP_TILE / 32][JQ_CAP];
     uint64_t *stage = s_stage[threadIdx.x >> 5];
-    JCand *queue = s_queue[threadIdx.x >> 5];
-    int staged = 0, q_head = 0, q_count = 0;
+    int staged = 0;
     const unsigned lane = threadIdx.x & 31, half = lane >> 4, h = lane & 15;
     const uint32_t P0 = blockIdx.x * (uint32_t)JP_TILE;
     for (int i = threadIdx.x; i < JP_TILE + JP_HALO; i += JP_TILE) {
@@ -340,20 +297,26 @@ __global__ void __launch_bounds__(JP_TILE) j1_pos_kernel(const JPArgs a) {
 #pragma unroll
             for (int le = 1; le <= 3; le++)
                 if (cand[le - 1]) cand[le - 1] = bit_test((le == 1 && miss) ? a.bm_marker : a.bm[le - 1], ub[le - 1]);
+            ulonglong2 sv[3];
+            uint32_t ss[3];
+#pragma unroll
+            for (int le = 1; le <= 3; le++)
+                if (cand[le - 1]) { sv[le - 1] = ht_first(a.slots, a.mask, key1_of(ga, le, ub[le - 1]), &ss[le - 1]); lookups++; }
 #pragma unroll
             for (int le = 1; le <= 3; le++) {
-                if (!__any_sync(0xffffffffu, cand[le - 1])) continue;          // warp-uniform
-                JCand c;
-                c.key = key1_of(ga, le, ub[le - 1]);
-                c.p = (uint32_t)p;
-                c.meta = (uint32_t)(ls + g + le - 1) | (miss ? 0x100u : 0u);
-                lookups += cand[le - 1] ? 1u : 0u;
-                jq_push(cand[le - 1], c, queue, q_head, q_count);
+                if (!__any_sync(0xffffffffu, cand[le - 1])) continue;
+                uint64_t v = 0;
+                bool found = cand[le - 1] && ht_resolve(a.slots, a.mask, key1_of(ga, le, ub[le - 1]), ss[le - 1], sv[le - 1], &v);
+                if (found && miss) {
+                    if (v & 0x80000000u) atomicAdd(&a.missing[v & 0x7fffffffu], 1);
+                    found = false;
+                }
+                const uint64_t key = ((uint64_t)(v & 0x7fffffffu) << a.pshift) | ((uint64_t)(uint32_t)p << 4) | (uint64_t)(ls + g + le - 1);
+                stage_push(found, key, stage, staged);
             }
-            while (q_count >= 32) jq_drain(a, queue, q_head, q_count, stage, staged);
+            if (staged > ST_CAP - 96) stage_flush(stage, staged, &a.counter[0], a.hits, a.cap);
         }
     }
-    while (q_count > 0) jq_drain(a, queue, q_head, q_count, stage, staged);
     stage_flush(stage, staged, &a.counter[0], a.hits, a.cap);
     for (int o = 16; o; o >>= 1) { lookups += __shfl_xor_sync(0xffffffffu, lookups, o); elems += __shfl_xor_sync(0xffffffffu, elems, o); }
     if (lane == 0 && (lookups | elems)) { atomicAdd(&a.counter[1], (unsigned long long)lookups); atomicAdd(&a.counter[2], (unsigned long long)elems); }
