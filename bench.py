@@ -270,6 +270,20 @@ def result_bytes(ex):
     return int(b)
 
 
+def bind_to_gpu_numa_node(local, rank):
+    """Pin this rank's host threads to the CPUs next to its GPU (NVML's ideal affinity) before anything is allocated: the
+    pinned result mirrors (2.6 GB per batch and set) then live on the GPU's own NUMA node.  With 8 unbound ranks the
+    result copies of a step crossed sockets and the end-to-end rate per GPU fell to a third of the single-GPU one."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+        cpus = sorted(os.sched_getaffinity(0))
+        log("[rank %d] bound to %d CPUs next to GPU %d (%d..%d)" % (rank, len(cpus), local, cpus[0], cpus[-1]))
+    except Exception as e:  # binding is an optimisation, never a requirement
+        log("[rank %d] CPU affinity not set: %r" % (rank, e))
+
+
 def gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -285,6 +299,7 @@ def gpu_arm(args):
         args.gpus = world
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    bind_to_gpu_numa_node(local, rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
