@@ -266,7 +266,7 @@ def result_bytes(ex):
     q2 = int(np.ctypeslib.as_array(r.q2_off, shape=(r.Q + 1,))[-1]) if r.Q else 0
     b = 4 * (r.T * 5 + r.G * 4 + r.D1 * 8 + r.D2 * 4 + 2 * (r.Q + 1) + q1 + q2)
     for k in range(3):
-        b += 28 * r.n_rules[k] + 8 * r.n_ids[k]
+        b += 16 * r.n_rules[k] + (8 + 4) * r.n_ids[k]
     return int(b)
 
 
@@ -368,7 +368,7 @@ def gpu_arm(args):
             n = int(r.n_rules[k])
             tot += n
             if n:
-                last = (C.c_char * 28).from_address(r.rules[k] + 28 * (n - 1))
+                last = (C.c_char * 16).from_address(r.rules[k] + 16 * (n - 1))
                 tot += last.raw[0] & 0
         return tot
 

@@ -67,14 +67,14 @@ extern "C" void cgx_destroy(cgx_ctx_t *c) {
                     &b.pat1_dev, &b.pat1_pos, &b.ql_keys, &b.ql_keys_tmp, &b.q1_off, &b.q1_ids, &b.q2_off, &b.q2_ids, &b.j_tiles, &b.j_bitmaps, &b.j_aflag, &b.j_aid, &b.j_hash, &b.pat1_ga, &b.hit_keys,
                     &b.hit_keys_tmp, &b.counters, &b.missing, &b.hits1_sorted, &b.hits2_sorted, &b.e2_count, &b.e2_keys, &b.e2_keys_tmp, &b.e2_vals,
                     &b.e2_vals_tmp, &b.e2_flags, &b.pat2, &b.rec_hash, &b.rec_tag, &b.rec_live, &b.rec_flags, &b.rec_meta, &b.rec_cnt,
-                    &b.scratch, &b.scratch2, &b.rule_head, &b.radix.hist, &b.radix.status, &b.radix.counters};
+                    &b.scratch, &b.scratch2, &b.rule_head, &b.rule_id, &b.radix.hist, &b.radix.status, &b.radix.counters};
     for (auto *x : bb) x->release();
-    for (int k = 0; k < 3; k++) { b.slot_off[k].release(); b.rec[k].release(); b.rules[k].release(); b.updown[k].release(); b.id_count[k].release(); }
+    for (int k = 0; k < 3; k++) { b.slot_off[k].release(); b.rec[k].release(); b.rules[k].release(); b.updown[k].release(); b.idinfo[k].release(); b.id_count[k].release(); }
     for (auto &l : b.scan.level) l.release();
     if (b.h_pinned) cudaFreeHost(b.h_pinned);
     PinnedBuf *pb[] = {&b.h_phrase_id, &b.h_phrases, &b.h_pat1, &b.h_pat2, &b.h_q1_off, &b.h_q1_ids, &b.h_q2_off, &b.h_q2_ids};
     for (auto *x : pb) x->release();
-    for (int k = 0; k < 3; k++) { b.h_rules[k].release(); b.h_updown[k].release(); }
+    for (int k = 0; k < 3; k++) { b.h_rules[k].release(); b.h_updown[k].release(); b.h_idinfo[k].release(); }
     c->prof.destroy();
     for (auto &ev : b.ev) if (ev) cudaEventDestroy(ev);
     if (b.copy_ev) cudaEventDestroy(b.copy_ev);
@@ -563,6 +563,7 @@ extern "C" int cgx_result_at(cgx_ctx_t *c, int age, cgx_result_t *o) {
             for (int k = 0; k < 3; k++) {
                 o->rules[k] = b.h_rules[k].ptr<cgx_rule_t>(); o->n_rules[k] = b.n_rules[k];
                 o->updown[k] = b.h_updown[k].ptr<int32_t>(); o->n_ids[k] = b.n_ids[k];
+                o->idinfo[k] = b.h_idinfo[k].ptr<uint32_t>();
             }
         } else {
             ResultSet &r = b.parked[age - 1];
@@ -574,6 +575,7 @@ extern "C" int cgx_result_at(cgx_ctx_t *c, int age, cgx_result_t *o) {
             for (int k = 0; k < 3; k++) {
                 o->rules[k] = r.h_rules[k].ptr<cgx_rule_t>(); o->n_rules[k] = r.n_rules[k];
                 o->updown[k] = r.h_updown[k].ptr<int32_t>(); o->n_ids[k] = r.n_ids[k];
+                o->idinfo[k] = r.h_idinfo[k].ptr<uint32_t>();
             }
         }
     });

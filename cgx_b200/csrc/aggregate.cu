@@ -241,7 +241,8 @@ __global__ void agg_head_cell_kernel(const uint32_t *__restrict__ excl, uint32_t
 // heads writing their rule keeps the reads streaming but leaves 73 % of the lanes idle in the probe-heavy part: 2x slower.)
 __global__ void __launch_bounds__(128) agg_rules_kernel(AggIdx a, int kind, const RuleRec *__restrict__ rec, const uint32_t *__restrict__ head_cell,
                                                         const unsigned long long *__restrict__ acc_best, const uint32_t *__restrict__ acc_cnt, uint32_t n_rules,
-                                                        const ulonglong2 *__restrict__ lex, uint32_t lex_mask, cgx_rule_t *__restrict__ rules) {
+                                                        const ulonglong2 *__restrict__ lex, uint32_t lex_mask, cgx_rule_t *__restrict__ rules,
+                                                        int32_t *__restrict__ rule_id, uint32_t *__restrict__ idinfo) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rules) return;
     const uint32_t hc = head_cell[r];
@@ -249,13 +250,14 @@ __global__ void __launch_bounds__(128) agg_rules_kernel(AggIdx a, int kind, cons
     const RuleRec best = rec[(uint32_t)acc_best[hc]];                    // low word of min(tgt_start << 32 | cell)
     const int pc = (int)(cw & 0xffffu) + 1;
     cgx_rule_t out;
-    out.id = best.id; out.tgt_start = best.tgt_start; out.end = best.end;
-    out.gap1 = best.gap1; out.gap1_1 = best.gap1_1; out.gap2 = best.gap2; out.gap2_1 = best.gap2_1;
-    out.pad = 0;
-    out.pc = (uint16_t)pc;
-    out.f = (uint16_t)(cw >> 16);
+    out.tgt_start = best.tgt_start;
+    const uint32_t g1 = best.gap1 == 255 ? 15u : (uint32_t)best.gap1, g1e = best.gap1 == 255 ? 15u : (uint32_t)best.gap1_1;
+    const uint32_t g2 = best.gap2 == 255 ? 15u : (uint32_t)best.gap2, g2e = best.gap2 == 255 ? 15u : (uint32_t)best.gap2_1;
+    out.span = (uint32_t)best.end | (g1 << 4) | (g1e << 8) | (g2 << 12) | (g2e << 16) | ((uint32_t)pc << 20);   // include/cgx_b200.h
     int fs = fsample_of(a, kind, best.id);
-    out.fs = (uint16_t)(fs > CGX_SAMPLER ? CGX_SAMPLER : fs);                          // ExtractPair.c:638,910,1249
+    fs = fs > CGX_SAMPLER ? CGX_SAMPLER : fs;                                           // ExtractPair.c:638,910,1249
+    rule_id[r] = best.id;
+    idinfo[best.id] = (cw >> 16) | ((uint32_t)fs << 16);       // f | fs << 16: every rule of the id writes the same word
     // ---- lexicalTaskMaxEF (ExtractPair.cu:2144-2432): for every source terminal the best MaxLexFgivenE over the target
     // terminals (and NULL), for every target terminal the best MaxLexEgivenF over the source terminals (and NULL).  One
     // table probe serves both directions of a (f, e) pair.
@@ -301,12 +303,12 @@ __global__ void __launch_bounds__(128) agg_rules_kernel(AggIdx a, int kind, cons
 }
 
 // per converted id: [first rule, last rule]  (globalOnPairsUpDown*, ExtractPair.cu:3745-3756, :3805-3816, :2082)
-__global__ void agg_updown_kernel(const cgx_rule_t *__restrict__ rules, uint32_t n_rules, int32_t *__restrict__ updown) {
+__global__ void agg_updown_kernel(const int32_t *__restrict__ rule_id, uint32_t n_rules, int32_t *__restrict__ updown) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rules) return;
-    int id = rules[r].id;
-    if (r == 0 || rules[r - 1].id != id) updown[2 * id] = (int32_t)r;
-    if (r == n_rules - 1 || rules[r + 1].id != id) updown[2 * id + 1] = (int32_t)r;
+    int id = rule_id[r];
+    if (r == 0 || rule_id[r - 1] != id) updown[2 * id] = (int32_t)r;
+    if (r == n_rules - 1 || rule_id[r + 1] != id) updown[2 * id + 1] = (int32_t)r;
 }
 
 void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
@@ -329,8 +331,13 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
         b.n_ids[kind] = nids[kind];
         b.n_rules[kind] = 0;
         int32_t *h_ud = b.h_updown[kind].get<int32_t>((size_t)2 * nids[kind] + 2);
+        uint32_t *h_ii = b.h_idinfo[kind].get<uint32_t>((size_t)nids[kind] + 1);
         b.h_rules[kind].get<cgx_rule_t>(1);
-        if (N == 0 || nids[kind] == 0) { memset(h_ud, 0xff, sizeof(int32_t) * 2 * (size_t)nids[kind]); continue; }
+        if (N == 0 || nids[kind] == 0) {
+            memset(h_ud, 0xff, sizeof(int32_t) * 2 * (size_t)nids[kind]);
+            memset(h_ii, 0, sizeof(uint32_t) * (size_t)nids[kind]);
+            continue;
+        }
         const RuleRec *rec = b.rec[kind].ptr<RuleRec>();
         uint64_t *hash = b.rec_hash.get<uint64_t>((size_t)N);
         uint32_t *flags = b.rec_flags.get<uint32_t>((size_t)N + 2);
@@ -339,6 +346,7 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
         uint32_t *tag = b.rec_tag.get<uint32_t>((size_t)N + 8);
         uint32_t *live = b.rec_live.get<uint32_t>((size_t)N + 2);
         int32_t *updown = b.updown[kind].get<int32_t>((size_t)2 * nids[kind]);
+        uint32_t *idinfo = b.idinfo[kind].get<uint32_t>((size_t)nids[kind] + 1);
         uint64_t seed = 0x243f6a8885a308d3ULL;
         uint32_t R = 0;
         for (int attempt = 0; attempt < 8; attempt++, seed = seed * 6364136223846793005ULL + 1442695040888963407ULL) {
@@ -361,14 +369,16 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
                 }
                 if (R == 0) break;
                 cgx_rule_t *rules = b.rules[kind].get<cgx_rule_t>(R);
+                int32_t *rule_id = b.rule_id.get<int32_t>((size_t)R + 1);
+                CUDA_CHECK(cudaMemsetAsync(idinfo, 0, sizeof(uint32_t) * (size_t)nids[kind], stream));
                 uint32_t *head_cell = b.rule_head.get<uint32_t>((size_t)R + 2);
                 agg_head_cell_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(flags, N, R, head_cell);
                 // (issuing the nf + 1 probes of a target terminal together was measured: 80-96 registers, 12.0 -> 14.9 ms; the table is
                 // L2-resident and the kernel is bound by instruction issue, not by the probe latency)
-                PROF("agg_rules", (double)R * (4 + 8 + 16 + 28) + (double)R * 13 * 16, (agg_rules_kernel<<<cgx_div_up(R, 128), 128, 0, stream>>>(a, kind, rec, head_cell, acc_best, acc_cnt, R,
-                                                                       ix.lex_hash.ptr<ulonglong2>(), ix.lex_hash_mask, rules)));
+                PROF("agg_rules", (double)R * (4 + 8 + 16 + 16 + 4) + (double)R * 13 * 16, (agg_rules_kernel<<<cgx_div_up(R, 128), 128, 0, stream>>>(a, kind, rec, head_cell, acc_best, acc_cnt, R,
+                                                                       ix.lex_hash.ptr<ulonglong2>(), ix.lex_hash_mask, rules, rule_id, idinfo)));
                 CUDA_CHECK(cudaMemsetAsync(updown, 0xff, sizeof(int32_t) * 2 * (size_t)nids[kind], stream));
-                agg_updown_kernel<<<cgx_div_up(R, 256), 256, 0, stream>>>(rules, R, updown);
+                agg_updown_kernel<<<cgx_div_up(R, 256), 256, 0, stream>>>(rule_id, R, updown);
                 b.launches += 3;
                 break;
             }
@@ -380,6 +390,8 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
             if (R) fetch_async(b, h_r, b.rules[kind].ptr<cgx_rule_t>(), sizeof(cgx_rule_t) * R, stream);
             if (R) fetch_async(b, h_ud, updown, sizeof(int32_t) * 2 * (size_t)nids[kind], stream);
             else memset(h_ud, 0xff, sizeof(int32_t) * 2 * (size_t)nids[kind]);      // no rule at all: every range empty
+            if (R) fetch_async(b, h_ii, idinfo, sizeof(uint32_t) * (size_t)nids[kind], stream);
+            else memset(h_ii, 0, sizeof(uint32_t) * (size_t)nids[kind]);
         }
     }
 }

@@ -37,8 +37,8 @@ struct Pat2 {
 // travelling, one being consumed).
 constexpr int CGX_RESULT_SETS = 3;
 struct ResultSet {
-    DevBuf phrase_id, phrases, pat1, pat2, q1_off, q1_ids, q2_off, q2_ids, rules[3], updown[3];
-    PinnedBuf h_phrase_id, h_phrases, h_pat1, h_pat2, h_q1_off, h_q1_ids, h_q2_off, h_q2_ids, h_rules[3], h_updown[3];
+    DevBuf phrase_id, phrases, pat1, pat2, q1_off, q1_ids, q2_off, q2_ids, rules[3], updown[3], idinfo[3];
+    PinnedBuf h_phrase_id, h_phrases, h_pat1, h_pat2, h_q1_off, h_q1_ids, h_q2_off, h_q2_ids, h_rules[3], h_updown[3], h_idinfo[3];
     int32_t Q = 0, T = 0, G = 0, D1 = 0, D2 = 0;
     int32_t n_rules[3] = {0, 0, 0}, n_ids[3] = {0, 0, 0};
     cgx_batch_info_t info;
@@ -46,9 +46,11 @@ struct ResultSet {
     bool fetched = false;            // the batch copied its results to the host mirrors
     bool valid = false;
     void release() {
-        DevBuf *d[] = {&phrase_id, &phrases, &pat1, &pat2, &q1_off, &q1_ids, &q2_off, &q2_ids, &rules[0], &rules[1], &rules[2], &updown[0], &updown[1], &updown[2]};
+        DevBuf *d[] = {&phrase_id, &phrases, &pat1, &pat2, &q1_off, &q1_ids, &q2_off, &q2_ids, &rules[0], &rules[1], &rules[2], &updown[0], &updown[1], &updown[2],
+                       &idinfo[0], &idinfo[1], &idinfo[2]};
         for (auto *x : d) x->release();
-        PinnedBuf *h[] = {&h_phrase_id, &h_phrases, &h_pat1, &h_pat2, &h_q1_off, &h_q1_ids, &h_q2_off, &h_q2_ids, &h_rules[0], &h_rules[1], &h_rules[2], &h_updown[0], &h_updown[1], &h_updown[2]};
+        PinnedBuf *h[] = {&h_phrase_id, &h_phrases, &h_pat1, &h_pat2, &h_q1_off, &h_q1_ids, &h_q2_off, &h_q2_ids, &h_rules[0], &h_rules[1], &h_rules[2], &h_updown[0], &h_updown[1], &h_updown[2],
+                          &h_idinfo[0], &h_idinfo[1], &h_idinfo[2]};
         for (auto *x : h) x->release();
         if (done) cudaEventDestroy(done);
         done = nullptr;
@@ -84,7 +86,7 @@ struct Batch {
     int64_t n_rec[3] = {0, 0, 0};          // non-empty cells per kind
     int64_t samples = 0;
     // rules
-    DevBuf rules[3], updown[3], id_count[3], rule_head;
+    DevBuf rules[3], updown[3], idinfo[3], id_count[3], rule_head, rule_id;
     int32_t n_rules[3] = {0, 0, 0};
     int32_t n_ids[3] = {0, 0, 0};
     // temp
@@ -96,7 +98,7 @@ struct Batch {
     size_t h_pinned_cap = 0;
     // host mirrors
     PinnedBuf h_phrase_id, h_phrases, h_pat1, h_pat2, h_q1_off, h_q1_ids, h_q2_off, h_q2_ids;
-    PinnedBuf h_rules[3], h_updown[3];
+    PinnedBuf h_rules[3], h_updown[3], h_idinfo[3];
     bool fetch_results = true;       // false: results stay on the device (device-resident throughput measurement)
     cgx_batch_info_t info;
     // the two batches before this one (parked[0] = previous); the current batch's arrays are the named members above
@@ -130,6 +132,7 @@ static inline void swap_results(Batch &b, ResultSet &r) {
     std::swap(b.h_q1_off, r.h_q1_off); std::swap(b.h_q1_ids, r.h_q1_ids); std::swap(b.h_q2_off, r.h_q2_off); std::swap(b.h_q2_ids, r.h_q2_ids);
     for (int k = 0; k < 3; k++) {
         std::swap(b.rules[k], r.rules[k]); std::swap(b.updown[k], r.updown[k]); std::swap(b.h_rules[k], r.h_rules[k]); std::swap(b.h_updown[k], r.h_updown[k]);
+        std::swap(b.idinfo[k], r.idinfo[k]); std::swap(b.h_idinfo[k], r.h_idinfo[k]);
         std::swap(b.n_rules[k], r.n_rules[k]); std::swap(b.n_ids[k], r.n_ids[k]);
     }
     std::swap(b.Q, r.Q); std::swap(b.T, r.T); std::swap(b.G, r.G); std::swap(b.D1, r.D1); std::swap(b.D2, r.D2);

@@ -16,7 +16,7 @@ import math
 import numpy as np
 
 from . import _lib
-from ._lib import BatchInfo, IndexArrays, IndexInfo, Result, RULE_DTYPE
+from ._lib import BatchInfo, IndexArrays, IndexInfo, Result, RULE_DTYPE, RULE_WIRE_DTYPE
 
 
 def _p(a, t):
@@ -45,15 +45,36 @@ class BatchResult:
         self.q1_ids = _np(r.q1_ids, int(self.q1_off[-1]) if self.Q else 0)
         self.q2_off = _np(r.q2_off, self.Q + 1)
         self.q2_ids = _np(r.q2_ids, int(self.q2_off[-1]) if self.Q else 0)
-        self.rules, self.updown = [], []
+        self.rules, self.updown, self.idinfo = [], [], []
         for k in range(3):
             n = r.n_rules[k]
+            ud = _np(r.updown[k], 2 * r.n_ids[k]).reshape(-1, 2)
+            ii = _np(r.idinfo[k], r.n_ids[k], dtype=np.uint32) if r.n_ids[k] else np.zeros(0, dtype=np.uint32)
+            self.updown.append(ud)
+            self.idinfo.append(ii)
+            out = np.zeros(n, dtype=RULE_DTYPE)
             if n:
-                buf = (C.c_char * (n * RULE_DTYPE.itemsize)).from_address(r.rules[k])
-                self.rules.append(np.frombuffer(buf, dtype=RULE_DTYPE).copy())
-            else:
-                self.rules.append(np.zeros(0, dtype=RULE_DTYPE))
-            self.updown.append(_np(r.updown[k], 2 * r.n_ids[k]).reshape(-1, 2))
+                buf = (C.c_char * (n * RULE_WIRE_DTYPE.itemsize)).from_address(r.rules[k])
+                w = np.frombuffer(buf, dtype=RULE_WIRE_DTYPE)
+                span = w["span"]
+                out["tgt_start"], out["mlfe"], out["mlef"] = w["tgt_start"], w["mlfe"], w["mlef"]
+                out["end"] = span & 15
+                for name, sh in (("gap1", 4), ("gap1_1", 8), ("gap2", 12), ("gap2_1", 16)):
+                    g = (span >> sh) & 15
+                    out[name] = np.where(g == 15, 255, g)
+                out["pc"] = (span >> 20) & 511
+                # the converted id of a rule is the updown range it sits in; f and fs travel once per id
+                ids = np.nonzero(ud[:, 0] >= 0)[0]                 # ids with rules, ascending = rule order
+                lo, hi = ud[ids, 0], ud[ids, 1]
+                starts = np.zeros(n, dtype=np.int64)
+                starts[lo] = 1
+                seg = np.cumsum(starts) - 1
+                assert np.array_equal(hi - lo + 1, np.bincount(seg, minlength=len(ids))), "updown ranges do not tile the rules"
+                rid = ids[seg].astype(np.int32)
+                out["id"] = rid
+                out["f"] = ii[rid] & 0xFFFF
+                out["fs"] = ii[rid] >> 16
+            self.rules.append(out)
 
     # ---- features exactly as the reference's host code computes them (ExtractPair.c:653-655, :641) ----
     @staticmethod

@@ -74,25 +74,29 @@ static void put_group(sbuf *b, const cgx_result_t *r, const cgxh_side_t *src, co
     sb_reserve(srcbuf, 1);
     srcbuf->p[srcbuf->n] = 0;
     char feat[256];
+    const uint32_t idw = r->idinfo[kind][cid];
+    const int f = CGX_ID_F(idw), fs = CGX_ID_FS(idw);
     for (int32_t i = lo; i <= hi; i++) {
         const cgx_rule_t *u = &r->rules[kind][i];
+        const int end = CGX_RULE_END(u), g1 = CGX_RULE_GAP1(u), g1e = CGX_RULE_GAP1_END(u), g2 = CGX_RULE_GAP2(u), g2e = CGX_RULE_GAP2_END(u);
+        const int pc = CGX_RULE_PC(u);
         sb_puts(b, "[X] ||| "); sb_puts(b, srcbuf->p); sb_puts(b, " ||| ");
         int first = 1;
-        for (int j = 0; j <= (int)u->end; j++) {
+        for (int j = 0; j <= end; j++) {
             const char *w;
-            if (u->gap1 != 255 && j >= (int)u->gap1 && j <= (int)u->gap1_1) { w = "[X,1]"; j = u->gap1_1; }
-            else if (u->gap2 != 255 && j >= (int)u->gap2 && j <= (int)u->gap2_1) { w = "[X,2]"; j = u->gap2_1; }
+            if (g1 != CGX_RULE_NOGAP && j >= g1 && j <= g1e) { w = "[X,1]"; j = g1e; }
+            else if (g2 != CGX_RULE_NOGAP && j >= g2 && j <= g2e) { w = "[X,2]"; j = g2e; }
             else w = cgxh_vocab_name(tgt->vocab, tgt->tok[u->tgt_start + j]);
             if (!first) sb_putc(b, ' ');
             first = 0;
             sb_puts(b, w);
         }
         /* ExtractPair.c:653-655, :641: float log10 of the ratio, double log10 of the counts */
-        float aa = -log10f((float)u->pc / (float)u->fs);
-        float score = (float)log10((double)(1 + u->fs));
-        float bb = (float)log10((double)(1 + u->pc));
+        float aa = -log10f((float)pc / (float)fs);
+        float score = (float)log10((double)(1 + fs));
+        float bb = (float)log10((double)(1 + pc));
         snprintf(feat, sizeof feat, " ||| EgivenFCoherent=%f SampleCountF=%f CountEF=%f MaxLexFgivenE=%f MaxLexEgivenF=%f IsSingletonF=%d IsSingletonFE=%d\n",
-                 aa, score, bb, u->max_lex_f_given_e, u->max_lex_e_given_f, u->f == 1, u->pc == 1);
+                 aa, score, bb, u->max_lex_f_given_e, u->max_lex_e_given_f, f == 1, pc == 1);
         sb_puts(b, feat);
     }
 }

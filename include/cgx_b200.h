@@ -144,21 +144,27 @@ typedef struct {
 } cgx_batch_info_t;
 int cgx_batch_info(const cgx_ctx_t *ctx, cgx_batch_info_t *out);
 
-/* A distinct scored rule (red_dup_t, ComTypes.h:244-255).  `id` is the converted id of
- * ExtractPair.c:723-729 / :999-1006 within its array (kind).  28 bytes: a C2 batch returns 7e7 of them, and the
- * device-to-host copy of the rules is the tail of every batch; the three counts are bounded by the sample size (300). */
+/* A distinct scored rule (red_dup_t, ComTypes.h:244-255), packed into 16 bytes: a C2 batch returns 7e7 of them and the
+ * device-to-host copy of the rules is most of what a batch sends back (8 ranks on one host share its ingest bandwidth).
+ * The converted id of a rule (ExtractPair.c:723-729 / :999-1006) is the `updown` range it sits in; the two per-id counts
+ * (f, all_suffix_fsample) travel once per id in `idinfo` instead of once per rule. */
 typedef struct {
-    int32_t id;
-    int32_t tgt_start;     /* representative target span: start in the target text ... */
-    uint8_t end;           /* ... and inclusive length-1 */
-    uint8_t gap1, gap1_1;  /* target gap 1 as offsets from tgt_start (255 = none) */
-    uint8_t gap2, gap2_1;
-    uint8_t pad;
-    uint16_t f;            /* extracted pairs with this source id   -> IsSingletonF  */
-    uint16_t fs;           /* all_suffix_fsample (capped at 300)     -> SampleCountF  */
-    uint16_t pc;           /* paircount                              -> CountEF, EgivenFCoherent, IsSingletonFE */
+    int32_t tgt_start;     /* representative target span: start in the target text */
+    uint32_t span;         /* bits 0-3 end (inclusive length-1); 4-7 gap1, 8-11 gap1_1, 12-15 gap2, 16-19 gap2_1: target gaps as offsets
+                              from tgt_start, 15 = no such gap; bits 20-28 paircount (<= 300) -> CountEF, EgivenFCoherent, IsSingletonFE */
     float max_lex_f_given_e, max_lex_e_given_f;
 } cgx_rule_t;
+#define CGX_RULE_NOGAP 15
+#define CGX_RULE_END(r) ((int)((r)->span & 15u))
+#define CGX_RULE_GAP1(r) ((int)(((r)->span >> 4) & 15u))
+#define CGX_RULE_GAP1_END(r) ((int)(((r)->span >> 8) & 15u))
+#define CGX_RULE_GAP2(r) ((int)(((r)->span >> 12) & 15u))
+#define CGX_RULE_GAP2_END(r) ((int)(((r)->span >> 16) & 15u))
+#define CGX_RULE_PC(r) ((int)(((r)->span >> 20) & 511u))
+/* idinfo word of a converted id: extracted pairs with this source id (-> IsSingletonF) and all_suffix_fsample capped at 300
+ * (-> SampleCountF); 0 for an id without rules */
+#define CGX_ID_F(w) ((int)((w) & 0xffffu))
+#define CGX_ID_FS(w) ((int)((w) >> 16))
 
 /* Host views of the batch results (valid until the next cgx_extract; see cgx_extract_begin for the pipelined form):
  *   phrase_id : T*5 ints, id of the contiguous phrase q[t..t+len) for len = 1..5, -1 when absent
@@ -166,7 +172,7 @@ typedef struct {
  *   pat1      : D1 x {a_pos, ls, b_pos, le, hit_start, hit_count, marker_pair(-1|0..9999), fs_extra}
  *   pat2      : D2 x {pat1_id, c_token, hit_start, hit_count}
  *   q1_off/q1_ids, q2_off/q2_ids : per-query lists of one-gap / two-gap pattern ids (ascending id)
- *   rules[k], n_rules[k], and per converted id the [first,last] rule range (updown, -1 when empty) */
+ *   rules[k], n_rules[k], and per converted id the [first,last] rule range (updown, -1 when empty) and its idinfo word */
 typedef struct {
     int32_t Q, T, G, D1, D2;
     const int32_t *phrase_id;
@@ -178,6 +184,7 @@ typedef struct {
     int32_t n_rules[3];
     const int32_t *updown[3];
     int32_t n_ids[3];
+    const uint32_t *idinfo[3];
 } cgx_result_t;
 int cgx_result(cgx_ctx_t *ctx, cgx_result_t *out);
 int cgx_result_at(cgx_ctx_t *ctx, int age, cgx_result_t *out);      /* see cgx_extract_begin */
