@@ -29,6 +29,33 @@ def _np(ptr, n, dtype=np.int32):
     return np.ctypeslib.as_array(ptr, shape=(n,)).copy()
 
 
+def decode_rules(wire, updown, idinfo):
+    """cgx_rule_t wire records (16 B, include/cgx_b200.h) -> RULE_DTYPE rows with the converted id, f and fs filled in:
+    the id of a rule is the updown range it sits in; f and fs travel once per id in idinfo."""
+    n = len(wire)
+    out = np.zeros(n, dtype=RULE_DTYPE)
+    if n == 0:
+        return out
+    span = wire["span"]
+    out["tgt_start"], out["mlfe"], out["mlef"] = wire["tgt_start"], wire["mlfe"], wire["mlef"]
+    out["end"] = span & 15
+    for name, sh in (("gap1", 4), ("gap1_1", 8), ("gap2", 12), ("gap2_1", 16)):
+        g = (span >> sh) & 15
+        out[name] = np.where(g == 15, 255, g)
+    out["pc"] = (span >> 20) & 511
+    ids = np.nonzero(updown[:, 0] >= 0)[0]                 # ids with rules, ascending = rule order
+    lo, hi = updown[ids, 0], updown[ids, 1]
+    starts = np.zeros(n, dtype=np.int64)
+    starts[lo] = 1
+    seg = np.cumsum(starts) - 1
+    assert np.array_equal(hi - lo + 1, np.bincount(seg, minlength=len(ids))), "updown ranges do not tile the rules"
+    rid = ids[seg].astype(np.int32)
+    out["id"] = rid
+    out["f"] = idinfo[rid] & 0xFFFF
+    out["fs"] = idinfo[rid] >> 16
+    return out
+
+
 class BatchResult:
     """Host copy of one batch's results (cgx_result_t)."""
 
@@ -52,29 +79,11 @@ class BatchResult:
             ii = _np(r.idinfo[k], r.n_ids[k], dtype=np.uint32) if r.n_ids[k] else np.zeros(0, dtype=np.uint32)
             self.updown.append(ud)
             self.idinfo.append(ii)
-            out = np.zeros(n, dtype=RULE_DTYPE)
             if n:
                 buf = (C.c_char * (n * RULE_WIRE_DTYPE.itemsize)).from_address(r.rules[k])
-                w = np.frombuffer(buf, dtype=RULE_WIRE_DTYPE)
-                span = w["span"]
-                out["tgt_start"], out["mlfe"], out["mlef"] = w["tgt_start"], w["mlfe"], w["mlef"]
-                out["end"] = span & 15
-                for name, sh in (("gap1", 4), ("gap1_1", 8), ("gap2", 12), ("gap2_1", 16)):
-                    g = (span >> sh) & 15
-                    out[name] = np.where(g == 15, 255, g)
-                out["pc"] = (span >> 20) & 511
-                # the converted id of a rule is the updown range it sits in; f and fs travel once per id
-                ids = np.nonzero(ud[:, 0] >= 0)[0]                 # ids with rules, ascending = rule order
-                lo, hi = ud[ids, 0], ud[ids, 1]
-                starts = np.zeros(n, dtype=np.int64)
-                starts[lo] = 1
-                seg = np.cumsum(starts) - 1
-                assert np.array_equal(hi - lo + 1, np.bincount(seg, minlength=len(ids))), "updown ranges do not tile the rules"
-                rid = ids[seg].astype(np.int32)
-                out["id"] = rid
-                out["f"] = ii[rid] & 0xFFFF
-                out["fs"] = ii[rid] >> 16
-            self.rules.append(out)
+                self.rules.append(decode_rules(np.frombuffer(buf, dtype=RULE_WIRE_DTYPE), ud, ii))
+            else:
+                self.rules.append(np.zeros(0, dtype=RULE_DTYPE))
 
     # ---- features exactly as the reference's host code computes them (ExtractPair.c:653-655, :641) ----
     @staticmethod

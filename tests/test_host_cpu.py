@@ -107,3 +107,65 @@ def test_synth_is_deterministic_and_within_reference_limits(micro):
     assert np.diff(c.src_off).max() < 255 and np.diff(c.tgt_off).max() < 255          # ExtractPair.cu:2683
     assert len(np.unique(c.src_words)) >= 100                                          # SuffixArray.cu:1175
     assert lay["str"][lay["n"] - 1] == lay["str"].max() and lay["str"][lay["n"]:].tolist() == [0, 0, 0]
+
+
+def test_rule_wire_format_macros_agree_with_python_decode(tmp_path):
+    """cgx_rule_t travels packed (16 B): the accessor macros of include/cgx_b200.h (what a C caller such as the grammar
+    writer uses) and cgx_b200.extractor.decode_rules (what the parity tests use) must read the same fields."""
+    from cgx_b200._lib import RULE_WIRE_DTYPE
+    from cgx_b200.extractor import decode_rules
+    rng = np.random.default_rng(5)
+    n_ids, rows = 40, []
+    updown = np.full((n_ids, 2), -1, dtype=np.int32)
+    idinfo = np.zeros(n_ids, dtype=np.uint32)
+    for cid in range(n_ids):
+        cnt = int(rng.integers(0, 4))
+        if cnt == 0:
+            continue
+        updown[cid] = (len(rows), len(rows) + cnt - 1)
+        idinfo[cid] = int(rng.integers(1, 301)) | (int(rng.integers(1, 301)) << 16)
+        for _ in range(cnt):
+            end = int(rng.integers(0, 15))
+            g = sorted(rng.integers(0, end + 1, size=4).tolist())
+            gaps = [15, 15, 15, 15]
+            kind = int(rng.integers(0, 3))
+            if kind >= 1:
+                gaps[0], gaps[1] = g[0], g[1]
+            if kind == 2:
+                gaps[2], gaps[3] = g[2], g[3]
+            pc = int(rng.integers(1, 301))
+            span = end | gaps[0] << 4 | gaps[1] << 8 | gaps[2] << 12 | gaps[3] << 16 | pc << 20
+            rows.append((int(rng.integers(0, 1 << 30)), span, float(rng.random()), float(rng.random())))
+    wire = np.array(rows, dtype=RULE_WIRE_DTYPE)
+    mine = decode_rules(wire, updown, idinfo)
+    src = tmp_path / "dump.c"
+    src.write_text(r"""
+#include <stdio.h>
+#include "cgx_b200.h"
+int main(int argc, char **argv) {
+    FILE *f = fopen(argv[1], "rb");
+    cgx_rule_t r;
+    _Static_assert(sizeof(cgx_rule_t) == 16, "cgx_rule_t is 16 bytes on the wire");
+    while (fread(&r, sizeof r, 1, f) == 1)
+        printf("%d %d %d %d %d %d %d\n", r.tgt_start, CGX_RULE_END(&r), CGX_RULE_GAP1(&r), CGX_RULE_GAP1_END(&r), CGX_RULE_GAP2(&r),
+               CGX_RULE_GAP2_END(&r), CGX_RULE_PC(&r));
+    unsigned w = 0x012c0007u;
+    printf("%d %d %d\n", CGX_ID_F(w), CGX_ID_FS(w), CGX_RULE_NOGAP);
+    return 0;
+}
+""")
+    exe, raw = tmp_path / "dump", tmp_path / "rules.bin"
+    raw.write_bytes(wire.tobytes())
+    subprocess.run(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe), str(raw)], capture_output=True, text=True, check=True).stdout.split("\n")
+    assert out[len(wire)].split() == ["7", "300", "15"]
+    for i, line in enumerate(out[:len(wire)]):
+        ts, end, g1, g1e, g2, g2e, pc = (int(x) for x in line.split())
+        m = mine[i]
+        none = lambda v: 255 if v == 15 else v
+        assert (ts, end, none(g1), none(g1e) if g1 != 15 else 255, none(g2), none(g2e) if g2 != 15 else 255, pc) == \
+               (int(m["tgt_start"]), int(m["end"]), int(m["gap1"]), int(m["gap1_1"]), int(m["gap2"]), int(m["gap2_1"]), int(m["pc"])), i
+    ids = np.repeat(np.arange(n_ids), np.where(updown[:, 0] >= 0, updown[:, 1] - updown[:, 0] + 1, 0))
+    assert np.array_equal(mine["id"], ids)
+    assert np.array_equal(mine["f"], idinfo[ids] & 0xFFFF) and np.array_equal(mine["fs"], idinfo[ids] >> 16)
+
