@@ -271,9 +271,10 @@ def result_bytes(ex):
 
 
 def bind_to_gpu_numa_node(local, rank):
-    """Pin this rank's host threads to the CPUs next to its GPU (NVML's ideal affinity) before anything is allocated: the
-    pinned result mirrors (2.6 GB per batch and set) then live on the GPU's own NUMA node.  With 8 unbound ranks the
-    result copies of a step crossed sockets and the end-to-end rate per GPU fell to a third of the single-GPU one."""
+    """Pin this rank's host threads to the CPUs next to its GPU (NVML's ideal affinity) before anything is allocated, so that
+    the pinned result mirrors (1.8 GB per batch and set) live on the GPU's own NUMA node.  On the single-socket 8-GPU VM
+    of this pool it changes nothing (one NUMA node: 8 ranks share ~90 GB/s of host ingest either way); it matters on
+    two-socket hosts."""
     try:
         import pynvml
         pynvml.nvmlInit()

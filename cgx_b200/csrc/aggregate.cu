@@ -38,17 +38,8 @@ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
     return z;
 }
 
-// target symbol sequence: tokens outside the gaps, gap1 -> 0xFFFFFFFF, gap2 -> 0xFFFFFFFE
-__device__ __forceinline__ int target_symbols(const int32_t *__restrict__ tgt, const RuleRec &r, uint32_t sym[16]) {
-    int n = 0;
-    for (int j = 0; j <= (int)r.end; j++) {
-        if (r.gap1 != 255 && j >= (int)r.gap1 && j <= (int)r.gap1_1) { sym[n++] = 0xFFFFFFFFu; j = r.gap1_1; }
-        else if (r.gap2 != 255 && j >= (int)r.gap2 && j <= (int)r.gap2_1) { sym[n++] = 0xFFFFFFFEu; j = r.gap2_1; }
-        else sym[n++] = (uint32_t)__ldg(&tgt[r.tgt_start + j]);
-    }
-    return n;
-}
-
+// target symbol sequence of a record: its target tokens outside the gaps, gap1 -> 0xFFFFFFFF, gap2 -> 0xFFFFFFFE (one symbol
+// per gap); walked by agg_hash_kernel (hash) and next_symbol() (verification)
 // cells of one kind: up to 4 slot-indexed regions in ascending id order (extract.cu)
 struct AggRegion {
     uint32_t base;                 // first cell
@@ -76,7 +67,7 @@ __global__ void agg_hash_kernel(const RuleRec *__restrict__ rec, uint32_t cells,
             uint32_t tok[15];                                     // the span is <= 15 tokens: issue every load before using any
 #pragma unroll
             for (int j = 0; j < 15; j++) tok[j] = j <= (int)r.end ? (uint32_t)__ldg(&tgt[r.tgt_start + j]) : 0u;
-            int ns = 0, skip_to = -1;                             // same walk as target_symbols()
+            int ns = 0, skip_to = -1;                             // the target symbol sequence (see above)
             // two independent 32-bit multiplicative lanes per symbol (4 instructions; a 64-bit murmur round per symbol was
             // ~20 and made this kernel issue-bound), one 64-bit finaliser per record.  Equal hashes are verified symbol by
             // symbol in agg_group, so the hash only has to make collisions inside a <= 300-cell segment rare.
@@ -110,7 +101,7 @@ struct TgtSpan {
         : ts(r.tgt_start), end(r.end), g1(r.gap1 == 255 ? -1 : (int)r.gap1), g1e(r.gap1_1), g2(r.gap2 == 255 ? -1 : (int)r.gap2), g2e(r.gap2_1) {}
 };
 // next target symbol from span offset j on (tokens outside the gaps, gap1 -> 0xFFFFFFFF, gap2 -> 0xFFFFFFFE); false past the end.
-// Same walk as target_symbols(), without the symbol array.
+// The same symbol sequence agg_hash_kernel hashes.
 __device__ __forceinline__ bool next_symbol(const int32_t *__restrict__ tgt, const TgtSpan &r, int &j, uint32_t &sym) {
     if (j > r.end) return false;
     if (r.g1 >= 0 && j >= r.g1 && j <= r.g1e) { sym = 0xFFFFFFFFu; j = r.g1e + 1; }
