@@ -9,13 +9,14 @@
 // (ExtractPair.c:813-848, :1141-1173).  The extraction kernels leave their records in slot-indexed cells that are
 // already grouped by source id (extract.cu): all records of one id sit in the <= 300 (65 / 70 for gappy seeds)
 // consecutive cells of its pattern.  So no global sort is needed (round 1a-1c: a 64-bit hash sort + an id sort of
-// 1.2e8 records = 30 GB of radix passes per batch): every record gets a 64-bit hash of its target symbol sequence,
-// and one thread per cell compares its hash with the other cells of its segment (broadcast loads, the segment is
-// shared by the neighbouring threads): paircount = equal cells, rule head = first equal cell, f = records of the id,
-// representative = equal cell with the smallest target start.  Heads are flagged, prefix-summed and compacted
-// into rules in (id, first cell) order -- deterministic.  Exactness does not rest on the hash: every non-head
-// record is compared symbol-by-symbol with its head, and a mismatch raises a flag on which the host re-runs the
-// aggregation with another hash seed.
+// 1.2e8 records = 30 GB of radix passes per batch): every record gets a 64-bit hash of its target symbol sequence
+// (agg_hash_kernel), and one thread per cell scans the 4-byte hash tags of the cells BEFORE it in its segment (broadcast
+// loads, the segment is shared by the neighbouring threads) for the first equal one = the head of its rule.  Every record
+// then reports to its head with two commutative atomics -- paircount += 1, representative = min(target start, cell) -- and
+// heads add f = records of the id (agg_group_kernel).  Heads are flagged, prefix-summed and compacted into rules in
+// (id, first cell) order -- deterministic, as are count and representative.  Exactness does not rest on the hash: every
+// non-head record is compared symbol-by-symbol with its head, and a mismatch raises a flag on which the host re-runs the
+// aggregation with another hash seed.  Rules leave the device packed (16 bytes + one word per id, include/cgx_b200.h).
 // Lexical weights: one thread per distinct rule; every (f,e) pair is ONE probe of the lexical hash table (16-byte
 // slots holding both directions' values; 2^21 slots = 32 MB at C2, L2-resident) instead of a 20-step binary search;
 // -log10 through the same lg2.approx path the reference's -use_fast_math build takes.

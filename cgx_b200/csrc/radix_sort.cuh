@@ -6,11 +6,13 @@
 // every digit is obtained by decoupled look-back over the preceding tiles' published counts, and the
 // keys (and optional 32-bit payloads) are staged through shared memory so that the scatter to HBM is
 // written in digit-contiguous, coalesced runs.  Per pass the traffic is therefore one read and one
-// write of the data: (sizeof(K)+payload) * 2 bytes per element -- HBM-bound.
+// write of the data: (sizeof(K)+payload) * 2 bytes per element (ncu: DRAM bytes = exactly that).  On B200 the pass is
+// bound by instruction issue, not by HBM: ~93 SASS instructions per key, 2.9 TB/s = 0.45 of the measured copy peak
+// (profiles/README.md r01e); the ranking (one ballot per digit bit) is half of them.
 //
 // The sort is stable.  Keys are uint32_t or uint64_t; only bits [begin_bit, end_bit) are sorted on
 // (callers know their key widths: packed (rank,rank) pairs, (pattern,position) pairs ...), split
-// into digits of at most 8 bits.
+// into 8-bit digits (compile-time width) plus one narrower remainder pass (runtime width).
 #pragma once
 #include "common.cuh"
 #include "prof.h"
