@@ -21,6 +21,15 @@ __global__ void ix_ngram_keys_kernel(const int32_t *__restrict__ str, size_t n, 
     keys[p] = k;
     vals[p] = (uint32_t)p;
 }
+// the same order from the bucket id of the (m-1)-gram at p and the m-th token: used when m tokens do not fit 64 bits
+// (vocabularies of 2^21 types and more: 3 * tokbits > 64)
+__global__ void ix_ngram_keys_from_bucket_kernel(const int32_t *__restrict__ str, const int32_t *__restrict__ bkt_prev, size_t n, int mlen, int tokbits,
+                                                 uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    keys[p] = ((uint64_t)(uint32_t)bkt_prev[p] << tokbits) | (uint64_t)(uint32_t)str[p + mlen - 1];
+    vals[p] = (uint32_t)p;
+}
 
 // bucket start of every m-gram: heads of the sorted key array mark the bucket starts; gid = dense bucket number
 __global__ void ix_bucket_heads_kernel(const uint64_t *__restrict__ keys, size_t n, uint32_t *__restrict__ flags) {
@@ -163,11 +172,19 @@ void build_index_aux(Index &ix, SaWorkspace &ws, cudaStream_t stream, int *launc
     uint64_t *keys = ws.keys.get<uint64_t>(n), *keys_tmp = ws.keys_tmp.get<uint64_t>(n);
     uint32_t *vals = ws.vals.get<uint32_t>(n), *vals_tmp = ws.vals_tmp.get<uint32_t>(n);
     for (int mlen = 1; mlen <= 3; mlen++) {
-        ix_ngram_keys_kernel<<<cgx_div_up(n, 256), 256, 0, stream>>>(str, n, mlen, tokbits, keys, vals);
+        // m packed token ids while they fit 64 bits, else (bucket of the (m-1)-gram, m-th token): same order, always <= 61 bits
+        int key_bits = mlen * tokbits;
+        static const bool force_bucket = getenv("CGX_FORCE_BUCKET_KEYS") != nullptr;      // tests: exercise the wide-vocabulary form
+        if (key_bits <= 64 && !(force_bucket && mlen > 1)) ix_ngram_keys_kernel<<<cgx_div_up(n, 256), 256, 0, stream>>>(str, n, mlen, tokbits, keys, vals);
+        else {
+            key_bits = cgx_bits_for((uint64_t)n) + tokbits;
+            CGX_REQUIRE(key_bits <= 64, "index: %d-gram keys need %d bits", mlen, key_bits);
+            ix_ngram_keys_from_bucket_kernel<<<cgx_div_up(n, 256), 256, 0, stream>>>(str, ix.bkt[mlen - 2].ptr<int32_t>(), n, mlen, tokbits, keys, vals);
+        }
         if (launches) *launches += 1;
         uint64_t *ks;
         uint32_t *vs;
-        radix_sort<uint64_t>(keys, keys_tmp, vals, vals_tmp, n, 0, mlen * tokbits, stream, ws.radix, &ks, &vs, launches);
+        radix_sort<uint64_t>(keys, keys_tmp, vals, vals_tmp, n, 0, key_bits, stream, ws.radix, &ks, &vs, launches);
         CUDA_CHECK(cudaMemcpyAsync(ix.inv[mlen - 1].get<int32_t>(n), vs, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, stream));
         uint32_t *flags = ws.flags.get<uint32_t>(n), *start_of = ws.rank.get<uint32_t>(n);
         ix_bucket_heads_kernel<<<cgx_div_up(n, 256), 256, 0, stream>>>(ks, n, flags);

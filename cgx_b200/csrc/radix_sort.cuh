@@ -325,6 +325,8 @@ void radix_sort(K *keys, K *keys_tmp, uint32_t *vals, uint32_t *vals_tmp, size_t
     if (n <= 1) return;
     CGX_REQUIRE(n < (1ull << 32) - RS_TILE, "radix_sort: n=%zu does not fit the 32-bit digit offsets", n);
     const bool wide = n >= (size_t)RsStatus<uint32_t>::VALUE_MASK;      // 64-bit look-back words from 2^30 keys on
+    CGX_REQUIRE(begin_bit >= 0 && end_bit <= (int)(8 * sizeof(K)) && (end_bit - begin_bit + 7) / 8 <= RS_MAX_PASSES,
+                "radix_sort: bits [%d, %d) do not fit a %zu-bit key / %d passes", begin_bit, end_bit, 8 * sizeof(K), RS_MAX_PASSES);
     RadixPlan plan = make_radix_plan(begin_bit, end_bit);
     size_t tiles = (n + RS_TILE - 1) / RS_TILE;
     uint32_t *hist = tmp.hist.get<uint32_t>(RS_MAX_PASSES * RS_BINS);
