@@ -174,7 +174,7 @@ void build_index_aux(Index &ix, SaWorkspace &ws, cudaStream_t stream, int *launc
     for (int mlen = 1; mlen <= 3; mlen++) {
         // m packed token ids while they fit 64 bits, else (bucket of the (m-1)-gram, m-th token): same order, always <= 61 bits
         int key_bits = mlen * tokbits;
-        static const bool force_bucket = getenv("CGX_FORCE_BUCKET_KEYS") != nullptr;      // tests: exercise the wide-vocabulary form
+        const bool force_bucket = getenv("CGX_FORCE_BUCKET_KEYS") != nullptr;      // tests: exercise the wide-vocabulary form
         if (key_bits <= 64 && !(force_bucket && mlen > 1)) ix_ngram_keys_kernel<<<cgx_div_up(n, 256), 256, 0, stream>>>(str, n, mlen, tokbits, keys, vals);
         else {
             key_bits = cgx_bits_for((uint64_t)n) + tokbits;

@@ -312,8 +312,219 @@ __global__ void __launch_bounds__(RS_BLOCK, HAS_VALUES ? 3 : 4) rs_onesweep_kern
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// sm_100a asynchronous-copy plumbing: 1-D bulk copies global -> shared (cp.async.bulk, SASS UBLKCP) that complete on an mbarrier
+// (SYNCS).  One elected thread arms the barrier with the byte count and issues the copy; every thread of the CTA waits on
+// the barrier's phase parity.  fence.proxy.async orders the CTA's earlier generic-proxy accesses to the buffer (the exchange of
+// the previous tile) before the async-proxy write that refills it.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t rs_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void rs_mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rs_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void rs_mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rs_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rs_mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(rs_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void rs_bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(rs_smem_u32(dst_smem)), "l"(src_gmem),
+                 "r"(bytes), "r"(rs_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void rs_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void rs_fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// One onesweep pass, Blackwell form: PERSISTENT CTAs (grid = resident CTAs) take tiles from the dynamic tile counter; the tile's
+// keys (and payloads) arrive in shared memory by cp.async.bulk into one of two stage buffers while the previous tile is still
+// being ranked and scattered, so no warp ever waits on a global load of keys (ncu of the one-tile-per-CTA form above: 6.1 of
+// 15.3 stall cycles per issued instruction were long-scoreboard waits on the 16 LDGs at the head of every CTA).  The stage
+// buffer a tile arrived in is also its exchange buffer (keys are in registers by then), the other one is being refilled.
+// Ranking, look-back and the digit-contiguous store are those of rs_onesweep_kernel.  Forward progress of the look-back: a
+// CTA holds at most its current and its prefetched next tile, both taken from the counter in ascending order, so the
+// smallest unfinished tile is always some running CTA's CURRENT tile and waits on nothing.
+template <typename K, bool HAS_VALUES, typename S = uint32_t, int CT_BITS = 0>
+__global__ void __launch_bounds__(RS_BLOCK, HAS_VALUES ? 2 : 3) rs_onesweep_bulk_kernel(const K *__restrict__ keys_in, K *__restrict__ keys_out,
+                                                                       const uint32_t *__restrict__ vals_in, uint32_t *__restrict__ vals_out,
+                                                                       size_t n, uint32_t num_tiles, int shift, int bits,
+                                                                       const uint32_t *__restrict__ digit_offset, S *status, uint32_t *tile_counter) {
+    using ST = RsStatus<S>;
+    constexpr unsigned KEY_BYTES = RS_TILE * sizeof(K), VAL_BYTES = HAS_VALUES ? RS_TILE * sizeof(uint32_t) : 0, STAGE_BYTES = KEY_BYTES + VAL_BYTES;
+    extern __shared__ __align__(128) unsigned char s_stages[];      // two stages: [keys | payloads] each
+    __shared__ uint16_t s_warp_hist[RS_WARPS][RS_BINS];
+    __shared__ uint32_t s_bin_start[RS_BINS];
+    __shared__ uint32_t s_global_base[RS_BINS];
+    __shared__ uint32_t s_scan_tot[RS_BINS / 32];
+    __shared__ uint32_t s_next;
+    __shared__ __align__(8) uint64_t s_bar[2];
+
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t mask = CT_BITS ? (1u << CT_BITS) - 1u : (1u << bits) - 1u;
+    const unsigned lt = lanemask_lt();
+    if (tid == 0) {
+        rs_mbar_init(&s_bar[0], 1);
+        rs_mbar_init(&s_bar[1], 1);
+        rs_fence_mbar_init();
+        s_next = atomicAdd(tile_counter, 1u);
+    }
+    __syncthreads();
+    uint32_t tile = s_next;
+    unsigned stage = 0, parity0 = 0, parity1 = 0;
+    auto issue = [&](uint32_t t, unsigned st) {                  // one thread: refill stage st with tile t (full tiles only)
+        unsigned char *dst = s_stages + (size_t)st * STAGE_BYTES;
+        rs_fence_proxy_async();
+        rs_mbar_expect_tx(&s_bar[st], STAGE_BYTES);
+        rs_bulk_g2s(dst, keys_in + (size_t)t * RS_TILE, KEY_BYTES, &s_bar[st]);
+        if (HAS_VALUES) rs_bulk_g2s(dst + KEY_BYTES, vals_in + (size_t)t * RS_TILE, VAL_BYTES, &s_bar[st]);
+    };
+    if (tid == 0 && tile < num_tiles && ((size_t)tile + 1) * RS_TILE <= n) issue(tile, 0);
+    __syncthreads();                                             // s_next read by everyone before thread 0 overwrites it
+
+    while (tile < num_tiles) {
+        if (tid == 0) s_next = atomicAdd(tile_counter, 1u);
+        for (int i = tid; i < RS_WARPS * RS_BINS / 2; i += RS_BLOCK) reinterpret_cast<uint32_t *>(&s_warp_hist[0][0])[i] = 0;
+        const bool full = ((size_t)tile + 1) * RS_TILE <= n;     // all tiles but the last
+        K *s_keys = reinterpret_cast<K *>(s_stages + (size_t)stage * STAGE_BYTES);
+        uint32_t *s_vals = reinterpret_cast<uint32_t *>(s_stages + (size_t)stage * STAGE_BYTES + KEY_BYTES);
+        const unsigned wbase = warp * (32 * RS_ITEMS) + lane;
+
+        K key[RS_ITEMS];
+        uint32_t val[HAS_VALUES ? RS_ITEMS : 1];
+        uint32_t rank[RS_ITEMS];
+        if (full) {
+            rs_mbar_wait(&s_bar[stage], stage ? parity1 : parity0);
+            if (stage) parity1 ^= 1u; else parity0 ^= 1u;
+#pragma unroll
+            for (int i = 0; i < RS_ITEMS; i++) key[i] = s_keys[wbase + i * 32];
+            if (HAS_VALUES) {
+#pragma unroll
+                for (int i = 0; i < RS_ITEMS; i++) val[i] = s_vals[wbase + i * 32];
+            }
+        } else {
+            const size_t gbase = (size_t)tile * RS_TILE + wbase;
+#pragma unroll
+            for (int i = 0; i < RS_ITEMS; i++) {
+                const size_t idx = gbase + (size_t)i * 32;
+                key[i] = idx < n ? keys_in[idx] : (K)~(K)0;
+                if (HAS_VALUES) val[i] = idx < n ? vals_in[idx] : 0u;
+            }
+        }
+        __syncthreads();                                         // keys are in registers: this stage is free for the exchange, the
+        const uint32_t next = s_next;                            // other one (last read before the barrier that ended the previous
+        if (tid == 0 && next < num_tiles && ((size_t)next + 1) * RS_TILE <= n) issue(next, stage ^ 1u);   // tile) for the refill
+        // ---- warp-level multisplit: stable rank of every key among the warp's keys with the same digit
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; i++) {
+            const uint32_t d = (uint32_t)(key[i] >> shift) & mask;
+            const unsigned peers = CT_BITS ? rs_match_digit_ct<CT_BITS ? CT_BITS : 1>(d) : rs_match_digit(d, bits);
+            const uint32_t base = s_warp_hist[warp][d];
+            __syncwarp();
+            if ((peers & lt) == 0) s_warp_hist[warp][d] = (uint16_t)(base + __popc(peers));
+            rank[i] = base + __popc(peers & lt);
+            __syncwarp();
+        }
+        __syncthreads();
+        // ---- per digit: exclusive offsets across warps, tile count published, decoupled look-back
+        uint32_t tile_count = 0, incl = 0;
+        if (tid < RS_BINS) {
+            uint32_t sum = 0;
+#pragma unroll
+            for (int w = 0; w < RS_WARPS; w++) {
+                const uint32_t t = s_warp_hist[w][tid];
+                s_warp_hist[w][tid] = (uint16_t)sum;
+                sum += t;
+            }
+            tile_count = sum;
+            rs_st_status(status + (size_t)tile * RS_BINS + tid, (S)sum | (tile == 0 ? ST::INCLUSIVE : ST::PARTIAL));
+            incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)lane >= o) incl += t;
+            }
+            if (lane == 31) s_scan_tot[warp] = incl;
+        }
+        __syncthreads();
+        if (tid < RS_BINS) {
+            uint32_t pre = 0;
+#pragma unroll
+            for (int w = 0; w < RS_BINS / 32; w++) pre += (w < (int)warp) ? s_scan_tot[w] : 0u;
+            const uint32_t bin_start = pre + incl - tile_count;
+            s_bin_start[tid] = bin_start;
+            uint32_t excl = 0;
+            if (tile > 0) {
+                int t = (int)tile - 1;
+                while (true) {
+                    const S *pst = status + (size_t)t * RS_BINS + tid;
+                    S v = rs_ld_status(pst);
+                    while ((v & (ST::PARTIAL | ST::INCLUSIVE)) == 0) { __nanosleep(20); v = rs_ld_status(pst); }
+                    excl += (uint32_t)(v & ST::VALUE_MASK);
+                    if (v & ST::INCLUSIVE) break;
+                    t--;
+                }
+                rs_st_status(status + (size_t)tile * RS_BINS + tid, (S)(excl + tile_count) | ST::INCLUSIVE);
+            }
+            s_global_base[tid] = __ldg(&digit_offset[tid]) + excl - bin_start;
+        }
+        __syncthreads();
+        // ---- staging position of every key, exchange through this tile's stage buffer
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; i++) {
+            const uint32_t d = (uint32_t)(key[i] >> shift) & mask;
+            const uint32_t r = rank[i] + s_bin_start[d] + s_warp_hist[warp][d];
+            s_keys[r] = key[i];
+            if (HAS_VALUES) s_vals[r] = val[i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; i++) {
+            const unsigned j = tid + i * RS_BLOCK;
+            const K k = s_keys[j];
+            const uint32_t d = (uint32_t)(k >> shift) & mask;
+            const size_t o = (size_t)s_global_base[d] + j;
+            if (full || o < n) {
+                keys_out[o] = k;
+                if (HAS_VALUES) vals_out[o] = s_vals[j];
+            }
+        }
+        __syncthreads();                                         // the stage, the digit tables and s_next are free again
+        tile = next;
+        stage ^= 1u;
+    }
+}
+
 template <typename K>
 static inline size_t rs_smem_bytes(bool has_values) { return RS_TILE * sizeof(K) + (has_values ? RS_TILE * sizeof(uint32_t) : 0); }
+
+// grid of the persistent form: every CTA resident at once (SMs x CTAs per SM for this instantiation and stage size), capped by
+// the tile count.  The occupancy query and the shared-memory opt-in happen once per instantiation and device.
+template <typename F>
+static inline unsigned rs_bulk_grid(F kernel, size_t dyn_smem, size_t tiles) {
+    static thread_local int cached_dev = -1, per_sm = 0, sms = 0;
+    static thread_local size_t cached_smem = 0;
+    int dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev != cached_dev || dyn_smem != cached_smem) {
+        CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, RS_BLOCK, dyn_smem));
+        CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        CGX_REQUIRE(per_sm >= 1, "onesweep: a %zu-byte stage pair does not fit one SM", dyn_smem);
+        cached_dev = dev;
+        cached_smem = dyn_smem;
+    }
+    const size_t resident = (size_t)per_sm * (size_t)sms;
+    return (unsigned)std::min(tiles, resident);
+}
 
 // Sorts n keys (and optional payloads) on bits [begin_bit, end_bit).  keys/vals and the *_tmp buffers
 // ping-pong; the sorted data ends in *keys_sorted / *vals_sorted (one of the two buffers).
@@ -342,19 +553,33 @@ void radix_sort(K *keys, K *keys_tmp, uint32_t *vals, uint32_t *vals_tmp, size_t
     K *kin = keys, *kout = keys_tmp;
     uint32_t *vin = vals, *vout = vals_tmp;
     const size_t smem = rs_smem_bytes<K>(vals != nullptr);
-    CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, true, uint32_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<K>(true)));
-    CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, false, uint32_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<K>(false)));
-    CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, true, uint32_t, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<K>(true)));
-    CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, false, uint32_t, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<K>(false)));
-    CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, true, uint64_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<K>(true)));
-    CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, false, uint64_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<K>(false)));
+    // persistent cp.async.bulk form (default) or the one-tile-per-CTA form (CGX_RS_V1=1; also when a buffer is not 16-byte
+    // aligned, which bulk copies require)
+    static const bool force_v1 = getenv("CGX_RS_V1") != nullptr;
+    const bool aligned = (((uintptr_t)keys | (uintptr_t)keys_tmp | (uintptr_t)vals | (uintptr_t)vals_tmp) & 15u) == 0;
+    const bool bulk = !force_v1 && aligned;
+    if (!bulk) {
+        CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, true, uint32_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<K>(true)));
+        CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, false, uint32_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<K>(false)));
+        CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, true, uint32_t, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<K>(true)));
+        CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, false, uint32_t, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<K>(false)));
+        CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, true, uint64_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<K>(true)));
+        CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, false, uint64_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<K>(false)));
+    }
     for (int p = 0; p < plan.num_passes; p++) {
         CUDA_CHECK(cudaMemsetAsync(status, 0, status_bytes, stream));
         const double bytes = (double)n * 2.0 * (sizeof(K) + (vals ? 4 : 0));
         const uint32_t *off = hist + p * RS_BINS;
         const bool ct8 = plan.bits[p] == 8 && !wide;
-#define CGX_RS_LAUNCH(V, ST, CT, vi, vo) \
-        PROF("radix_onesweep", bytes, (rs_onesweep_kernel<K, V, ST, CT><<<(unsigned)tiles, RS_BLOCK, smem, stream>>>(kin, kout, vi, vo, n, plan.shift[p], plan.bits[p], off, (ST *)status, counters + p)))
+#define CGX_RS_LAUNCH(V, ST, CT, vi, vo)                                                                                                                      \
+        do {                                                                                                                                              \
+            if (bulk) {                                                                                                                                   \
+                const unsigned g_ = rs_bulk_grid(rs_onesweep_bulk_kernel<K, V, ST, CT>, 2 * smem, tiles);                                                \
+                PROF("radix_onesweep", bytes, (rs_onesweep_bulk_kernel<K, V, ST, CT><<<g_, RS_BLOCK, 2 * smem, stream>>>(kin, kout, vi, vo, n, (uint32_t)tiles, plan.shift[p], plan.bits[p], off, (ST *)status, counters + p))); \
+            } else {                                                                                                                                      \
+                PROF("radix_onesweep", bytes, (rs_onesweep_kernel<K, V, ST, CT><<<(unsigned)tiles, RS_BLOCK, smem, stream>>>(kin, kout, vi, vo, n, plan.shift[p], plan.bits[p], off, (ST *)status, counters + p))); \
+            }                                                                                                                                             \
+        } while (0)
         if (vals && ct8) CGX_RS_LAUNCH(true, uint32_t, 8, vin, vout);
         else if (!vals && ct8) CGX_RS_LAUNCH(false, uint32_t, 8, nullptr, nullptr);
         else if (vals && !wide) CGX_RS_LAUNCH(true, uint32_t, 0, vin, vout);

@@ -42,6 +42,7 @@ def compare_files(path_a: str, path_b: str, rtol: float = 1e-5, atol: float = 2e
     """Returns dict(n_a, n_b, only_a, only_b, float_mismatch, examples)."""
     a, b = load(path_a), load(path_b)
     only_a = only_b = bad = 0
+    by_feature = dict.fromkeys(FLOAT_KEYS, 0)      # float mismatches by the first feature that differs
     ex = []
     for k in set(a) | set(b):
         va, vb = sorted(a.get(k, [])), sorted(b.get(k, []))
@@ -54,18 +55,20 @@ def compare_files(path_a: str, path_b: str, rtol: float = 1e-5, atol: float = 2e
             for i, (p, q) in enumerate(zip(x, y)):
                 if abs(p - q) > atol + rtol * max(abs(p), abs(q)):
                     bad += 1
+                    by_feature[FLOAT_KEYS[i]] += 1
                     if len(ex) < 10:
                         ex.append(("float", k, FLOAT_KEYS[i], p, q))
                     break
     na = sum(len(v) for v in a.values())
     nb = sum(len(v) for v in b.values())
-    return dict(n_a=na, n_b=nb, only_a=only_a, only_b=only_b, float_mismatch=bad, examples=ex)
+    return dict(n_a=na, n_b=nb, only_a=only_a, only_b=only_b, float_mismatch=bad, float_mismatch_by_feature=by_feature, examples=ex)
 
 
 def compare_dirs(dir_a: str, dir_b: str, rtol: float = 1e-5, atol: float = 2e-6):
     names = sorted(set(f for f in os.listdir(dir_a) if f.startswith("grammar.")) |
                    set(f for f in os.listdir(dir_b) if f.startswith("grammar.")))
-    tot = dict(files=0, n_a=0, n_b=0, only_a=0, only_b=0, float_mismatch=0, missing_files=0, examples=[])
+    tot = dict(files=0, n_a=0, n_b=0, only_a=0, only_b=0, float_mismatch=0, missing_files=0, examples=[],
+               float_mismatch_by_feature=dict.fromkeys(FLOAT_KEYS, 0))
     for n in names:
         pa, pb = os.path.join(dir_a, n), os.path.join(dir_b, n)
         if not (os.path.exists(pa) and os.path.exists(pb)):
@@ -75,6 +78,8 @@ def compare_dirs(dir_a: str, dir_b: str, rtol: float = 1e-5, atol: float = 2e-6)
         tot["files"] += 1
         for k in ("n_a", "n_b", "only_a", "only_b", "float_mismatch"):
             tot[k] += r[k]
+        for k, v in r["float_mismatch_by_feature"].items():
+            tot["float_mismatch_by_feature"][k] += v
         if len(tot["examples"]) < 10:
             tot["examples"] += [(n,) + e for e in r["examples"]][: 10 - len(tot["examples"])]
     matched = tot["n_b"] - tot["only_b"]

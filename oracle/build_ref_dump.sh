@@ -36,6 +36,20 @@ sed -i '1518a\
 sed -i '8a\
 #include "ref_dump_hooks.h"' "$W/SuffixArray.cu"
 # --- ExtractPair.cu ---------------------------------------------------------------------------
+# wall-clock brackets around the three host aggregation calls (createLexiconFast / GappyFast / TwoGapFast, ExtractPair.c:515,664,939 --
+# the "ExtractPair.c" CPU leg of SURVEY.md 8d): the reference times its kernels on stderr but not these loops
+sed -i '3868a\
+	cgx_toc("createLexiconFast", (long)prev_cout);' "$W/ExtractPair.cu"
+sed -i '3852a\
+	cgx_tic();' "$W/ExtractPair.cu"
+sed -i '3792a\
+	cgx_toc("createLexiconTwoGapFast", (long)count_two_gap);' "$W/ExtractPair.cu"
+sed -i '3765a\
+	cgx_tic();' "$W/ExtractPair.cu"
+sed -i '3734a\
+	cgx_toc("createLexiconGappyFast", (long)count_one_gap);' "$W/ExtractPair.cu"
+sed -i '3707a\
+	cgx_tic();' "$W/ExtractPair.cu"
 sed -i '3672a\
 	cgx_dump("out_res", out_res, (size_t)prev_cout*sizeof(res_phrase_t));\
 	cgx_dump("oneGapRule", oneGapRule, (size_t)count_one_gap*sizeof(rule_onegap));\
@@ -48,6 +62,9 @@ sed -i '3672a\
 	cgx_dump("tgt", ref_target->str, (size_t)ref_target->toklen*sizeof(int));' "$W/ExtractPair.cu"
 sed -i '5a\
 #include "ref_dump_hooks.h"' "$W/ExtractPair.cu"
+# the brackets must sit exactly around the calls (the reference snapshot is fixed; fail loudly if it ever is not)
+grep -A1 -n 'cgx_tic();' "$W/ExtractPair.cu" | grep -c 'createLexicon.*Fast(' | grep -qx 3 || { echo "build_ref_dump: timer hooks misplaced" >&2; exit 1; }
+grep -B1 -n 'cgx_toc(' "$W/ExtractPair.cu" | grep -c ');' | grep -qx 6 || { echo "build_ref_dump: timer hooks misplaced" >&2; exit 1; }
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}; CXX=${CXX:-g++}
 INC="-I$W -I$W/uthash -I/usr/local/cuda/include"
 mkdir -p "$W/obj" "$OUT"

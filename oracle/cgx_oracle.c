@@ -1468,8 +1468,16 @@ static void print_group(const orc_t *o, FILE *fp, int kind, int32_t cid) {
     }
 }
 
+/* contexts created from arrays carry no vocabulary strings: name every id "w<id>" (tests rename through their own tables) */
+static char **synthetic_vocab(int32_t count) {
+    char **v = (char **)calloc((size_t)count + 1, sizeof(char *));
+    for (int32_t i = 0; i < count; i++) { char b[32]; snprintf(b, sizeof b, "w%d", i); v[i] = strdup(b); }
+    return v;
+}
+
 int orc_write_grammars(orc_t *o, const char *outdir) {
-    if (!o->have_vocab) return 2;
+    if (!o->svocab) { o->sv = o->str[o->n - 1] + 1; o->svocab = synthetic_vocab(o->sv); }
+    if (!o->tvocab) { o->tv = o->tgt[o->m - 1] + 1; o->tvocab = synthetic_vocab(o->tv); }
     char fn[4096];
     for (int32_t qi = 0; qi < o->Q; qi++) {
         snprintf(fn, sizeof fn, "%s/grammar.%d.s", outdir, qi);

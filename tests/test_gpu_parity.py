@@ -16,8 +16,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def ms(a):
-    return collections.Counter(map(tuple, np.asarray(a).tolist()))
+from _parity import assert_full_parity, expand_marker_hits, ms, remap_ids  # noqa: E402,F401
 
 
 @pytest.fixture(scope="module")
@@ -28,20 +27,6 @@ def ex_micro(micro):
     ex.build_index(lay)
     res = ex.extract(lay["qry_tok"], lay["qry_off"])
     return ex, res
-
-
-def expand_marker_hits(o):
-    """The oracle keeps the reference's single marker record for frequent-pair patterns; expand it to the
-    precomputed pair list it stands for."""
-    oh, pidx, plist = o.onegap_hits(), o.precomp_index(), o.precomp_list()
-    rows = []
-    for h in oh:
-        if h[2] == 0:
-            a, b = pidx[h[1]]
-            rows += [(h[0], plist[k, 0], plist[k, 1]) for k in range(a, b + 1)]
-        else:
-            rows.append(tuple(h))
-    return np.array(sorted(rows), dtype=np.int32).reshape(-1, 3)
 
 
 def test_suffix_array_bit_exact(ex_micro, micro_oracle, golden):
@@ -98,26 +83,6 @@ def test_patterns_and_hits(ex_micro, micro_oracle, micro):
     for d in range(res.D1):
         if res.pat1[d, 6] >= 0 and res.pat1[d, 5] > 0:
             assert int(res.pat1[d, 7]) == int(miss[res.pat1[d, 6]])
-
-
-def remap_ids(rows, res, o, kind):
-    """Phrase ids differ (sorted (up,len) order here, first-appearance order in the reference): map the oracle's
-    converted ids into ours through (up, len)."""
-    ob = o.blocks()
-    mine = {(int(p[0]), int(p[2])): g for g, p in enumerate(res.phrases)}
-    g_map = np.array([mine[(int(b[0]), int(b[2]))] for b in ob], dtype=np.int64)
-    G = res.G
-    rows = rows.copy()
-    ids = rows[:, 0].astype(np.int64)
-    if kind == 0:
-        rows[:, 0] = g_map[ids]
-    elif kind == 1:
-        sel = ids < 2 * G
-        rows[sel, 0] = g_map[ids[sel] % G] + (ids[sel] // G) * G
-    else:
-        sel = ids < G
-        rows[sel, 0] = g_map[ids[sel]]
-    return rows
 
 
 def test_extraction_records_bit_exact(ex_micro, micro_oracle):
