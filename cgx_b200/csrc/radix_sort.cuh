@@ -508,22 +508,23 @@ static inline size_t rs_smem_bytes(bool has_values) { return RS_TILE * sizeof(K)
 
 // grid of the persistent form: every CTA resident at once (SMs x CTAs per SM for this instantiation and stage size), capped by
 // the tile count.  The occupancy query and the shared-memory opt-in happen once per instantiation and device.
+struct RsGridCache { const void *fn; int dev; size_t smem; size_t resident; };
 template <typename F>
 static inline unsigned rs_bulk_grid(F kernel, size_t dyn_smem, size_t tiles) {
-    static thread_local int cached_dev = -1, per_sm = 0, sms = 0;
-    static thread_local size_t cached_smem = 0;
+    // keyed by the kernel's ADDRESS: instantiations that differ only in non-type template arguments share one function type
+    static thread_local std::vector<RsGridCache> cache;
     int dev = 0;
     CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev != cached_dev || dyn_smem != cached_smem) {
-        CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, RS_BLOCK, dyn_smem));
-        CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        CGX_REQUIRE(per_sm >= 1, "onesweep: a %zu-byte stage pair does not fit one SM", dyn_smem);
-        cached_dev = dev;
-        cached_smem = dyn_smem;
-    }
-    const size_t resident = (size_t)per_sm * (size_t)sms;
-    return (unsigned)std::min(tiles, resident);
+    const void *fn = reinterpret_cast<const void *>(kernel);
+    for (const RsGridCache &c : cache)
+        if (c.fn == fn && c.dev == dev && c.smem == dyn_smem) return (unsigned)std::min(tiles, c.resident);
+    int per_sm = 0, sms = 0;
+    CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, RS_BLOCK, dyn_smem));
+    CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CGX_REQUIRE(per_sm >= 1, "onesweep: a %zu-byte stage pair does not fit one SM", dyn_smem);
+    cache.push_back({fn, dev, dyn_smem, (size_t)per_sm * (size_t)sms});
+    return (unsigned)std::min(tiles, cache.back().resident);
 }
 
 // Sorts n keys (and optional payloads) on bits [begin_bit, end_bit).  keys/vals and the *_tmp buffers

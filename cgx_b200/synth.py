@@ -22,7 +22,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-__all__ = ["SynthCorpus", "generate", "text_layout", "write_text", "first_appearance_ids"]
+__all__ = ["SynthCorpus", "generate", "generate_queries", "query_ids", "text_layout", "write_text", "first_appearance_ids"]
 
 
 @dataclass
@@ -108,17 +108,14 @@ def _sentences(rng, n_sent, inv, mean_len, sd_len, min_len, max_len, swap_p):
     order[idx] += 1
     order[idx + 1] -= 1
     # source offsets inside the sentence
-    sent_src_start = np.zeros(n_sent + 1, dtype=np.int64)
-    np.add.at(sent_src_start, sent_of + 1, slen)
-    sent_src_start = np.cumsum(sent_src_start)
+    sent_src_start = np.concatenate([[0], np.cumsum(np.bincount(sent_of, weights=slen, minlength=n_sent).astype(np.int64))])
     src_off_in = starts - starts[np.repeat(first_idx, counts)]
     # target offsets: sort phrases of each sentence by target order, cumulative tlen
     key = sent_of * (m + 1) + order
     perm = np.argsort(key, kind="stable")
     tl_sorted = tlen[perm]
     ctl = np.cumsum(tl_sorted) - tl_sorted
-    sent_tgt_len = np.zeros(n_sent, dtype=np.int64)
-    np.add.at(sent_tgt_len, sent_of, tlen)
+    sent_tgt_len = np.bincount(sent_of, weights=tlen, minlength=n_sent).astype(np.int64)
     sent_tgt_start = np.concatenate([[0], np.cumsum(sent_tgt_len)])
     tgt_off_in = np.empty(m, dtype=np.int64)
     tgt_off_in[perm] = ctl - sent_tgt_start[sent_of[perm]]
@@ -195,16 +192,50 @@ def generate(n_sent: int, n_qry: int, v_src: int = 50000, v_tgt: int = 50000, *,
                                  swap_p=swap_p, oov_p=oov_p))
 
 
+def generate_queries(n_sent: int, n_qry: int, v_src: int = 50000, v_tgt: int = 50000, *, seed: int = 1234, qry_seed: int = 4321,
+                     n_phrases: int | None = None, zipf_s: float = 1.0, mean_len: float = 25.0, sd_len: float = 8.0, min_len: int = 3,
+                     max_len: int = 80, oov_p: float = 0.0, qry_mean_len: float | None = None):
+    """Another query set for the corpus generate(n_sent, ..., seed=seed) makes, without re-generating the corpus: the phrase
+    inventory is the first thing drawn from `seed`, so it is rebuilt exactly; the queries come from `qry_seed` alone.
+    generate(..., qry_seed=s).qry_words == generate_queries(..., qry_seed=s)[0].  Returns (qry_words, qry_off)."""
+    rng = np.random.default_rng(seed)
+    if n_phrases is None:
+        n_phrases = max(2000, min(2_000_000, n_sent // 2))
+    inv = _inventory(rng, n_phrases, v_src, v_tgt, zipf_s)
+    qrng = np.random.default_rng(qry_seed)
+    inv["draw"] = _zipf_sampler(qrng, n_phrases, zipf_s)
+    q = _sentences(qrng, n_qry, inv, qry_mean_len or mean_len, sd_len, min_len, max_len, 0.0)
+    qw = q["src_words"].copy()
+    if oov_p > 0:
+        qw[qrng.random(len(qw)) < oov_p] = -1
+    return qw, q["src_off"]
+
+
+def query_ids(src_names: np.ndarray, qry_words: np.ndarray) -> np.ndarray:
+    """Query word names -> ids of the source vocabulary (id = 2 + first-appearance rank, Start.cu:288), -1 = OOV (Start.cu:97)."""
+    q_ids = np.full(len(qry_words), -1, dtype=np.int32)
+    srt = np.argsort(src_names, kind="stable")
+    sn_sorted = src_names[srt]
+    k = np.minimum(np.searchsorted(sn_sorted, qry_words), len(sn_sorted) - 1)
+    hit = (sn_sorted[k] == qry_words) & (qry_words >= 0)
+    q_ids[hit] = (srt[k[hit]] + 2).astype(np.int32)
+    return q_ids
+
+
 def first_appearance_ids(words: np.ndarray):
     """word-name -> id = 2 + first-appearance rank (Start.cu:182,288).  Returns (ids, names_by_id)."""
-    uniq, first = np.unique(words, return_index=True)
-    order = np.argsort(first, kind="stable")
+    words = np.asarray(words)
+    n, v = len(words), (int(words.max()) + 1 if len(words) else 0)
+    # first occurrence of every word name in O(N): scatter positions in reverse order, the last write (= smallest position) wins
+    first = np.full(v, n, dtype=np.int64)
+    first[words[::-1]] = np.arange(n - 1, -1, -1, dtype=np.int64)
+    uniq = np.nonzero(first < n)[0]
+    order = np.argsort(first[uniq], kind="stable")
     names_by_rank = uniq[order]
-    lut_keys = names_by_rank
-    rank_of = np.empty(len(uniq), dtype=np.int64)
-    rank_of[order] = np.arange(len(uniq))
-    ids = rank_of[np.searchsorted(uniq, words)] + 2
-    return ids.astype(np.int32), lut_keys.astype(np.int64)
+    rank_of = np.zeros(v, dtype=np.int32)
+    rank_of[names_by_rank] = np.arange(len(uniq), dtype=np.int32)
+    ids = rank_of[words] + 2
+    return ids.astype(np.int32), names_by_rank.astype(np.int64)
 
 
 def _layout_side(words, off, ids):
@@ -247,10 +278,8 @@ def text_layout(c: SynthCorpus) -> dict:
     R_tar = np.full(m, -1, dtype=np.int64)
     si = s_sent[c.link_sent] + c.link_s
     ti = t_sent[c.link_sent] + c.link_t
-    np.minimum.at(L_src, si, c.link_t)
-    np.maximum.at(R_src, si, c.link_t)
-    np.minimum.at(L_tar, ti, c.link_s)
-    np.maximum.at(R_tar, ti, c.link_s)
+    _min_max_by_key(si, c.link_t, L_src, R_src)
+    _min_max_by_key(ti, c.link_s, L_tar, R_tar)
     R_src[R_src < 0] = 255
     R_tar[R_tar < 0] = 255
     RLP = ((L_src.astype(np.uint32) << 24) | (R_src.astype(np.uint32) << 16) | (P.astype(np.uint32) << 8))
@@ -282,21 +311,27 @@ def text_layout(c: SynthCorpus) -> dict:
     # values are what a "%.6g" text round trip gives (so text and array paths agree bit-for-bit)
     lex_v1 = np.array([float("%.6g" % x) for x in lex_v1], dtype=np.float32) if len(lex_v1) < 200000 else _round6(lex_v1)
     lex_v2 = np.array([float("%.6g" % x) for x in lex_v2], dtype=np.float32) if len(lex_v2) < 200000 else _round6(lex_v2)
-    # queries -> source ids
-    lut = {}
-    q_ids = np.full(len(c.qry_words), -1, dtype=np.int32)
-    srt = np.argsort(s_names, kind="stable")
-    sn_sorted = s_names[srt]
-    k = np.searchsorted(sn_sorted, c.qry_words)
-    k = np.minimum(k, len(sn_sorted) - 1)
-    hit = (sn_sorted[k] == c.qry_words) & (c.qry_words >= 0)
-    q_ids[hit] = (srt[k[hit]] + 2).astype(np.int32)
-    del lut
+    q_ids = query_ids(s_names, c.qry_words)
     return dict(str=s_buf, n=n, tgt=t_buf, m=m, P=P, L_tar=L_tar.astype(np.uint8), R_tar=R_tar.astype(np.uint8),
                 RLP=RLP.astype(np.uint32), src_sentenceind=s_sent, tgt_sentenceind=t_sent,
                 src_names=s_names, tgt_names=t_names, src_last=int(s_buf[n - 1]), tgt_last=int(t_buf[m - 1]),
                 lex_f=lex_f, lex_e=lex_e, lex_v1=lex_v1, lex_v2=lex_v2,
                 qry_tok=q_ids, qry_off=c.qry_off.astype(np.int32))
+
+
+def _min_max_by_key(key, val, mn_out, mx_out):
+    """mn_out[k] = min(val[key == k]), mx_out[k] = max(...) for the keys that occur (np.minimum.at / np.maximum.at in one
+    sort instead of two scattered read-modify-write passes).  val < 256."""
+    if len(key) == 0:
+        return
+    packed = key.astype(np.int64) * 256 + val.astype(np.int64)
+    if np.any(packed[1:] < packed[:-1]):
+        packed = np.sort(packed)
+    k = packed >> 8
+    first = np.concatenate([[True], k[1:] != k[:-1]])
+    last = np.concatenate([first[1:], [True]])
+    mn_out[k[first]] = packed[first] & 255
+    mx_out[k[last]] = packed[last] & 255
 
 
 def _round6(x: np.ndarray) -> np.ndarray:
