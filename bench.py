@@ -27,8 +27,15 @@ scoring) over the rank's query batch against the resident index.
            matcher/extractor -- SURVEY.md section 0 -- so this is the oracle port, one process per core over a
            bounded query sample; its suffix array is built by the reference's SuffixArray.c).
 
-Multi-GPU (weak scaling): the index is built once on rank 0 and broadcast over NVLink with NCCL; every rank
-then processes its own 10 k-query batch; there is no data-path collective.
+  strong : a FIXED set of 80 k queries of the same corpus, cut into contiguous token-balanced shards (cgx_b200.dist.shard_queries),
+           every rank streaming its shard through cgx_extract_begin in 10 k-query batches; whole-set wall clock, max over ranks.
+           The weak-scaling `value` keeps 10 k queries per GPU; this block shows what a fixed job gains from N GPUs.
+  c3     : (N = 1 only) BASELINE.json configs[2] -- 10 M sentence pairs (~260 M tokens), 100 k queries -- as a second block: index
+           build, then all queries streamed in batches the way bin/strmatchcuda cuts them (a batch whose hit lists outgrow the
+           31-bit result indices is refused and halved); device-resident and end-to-end rates, per-kernel table.  --no-c3 skips it.
+
+Multi-GPU (weak scaling): the corpus and every rank's queries are generated once, on rank 0; the index is built once on rank 0
+and broadcast over NVLink with NCCL; every rank then processes its own 10 k-query batch; there is no data-path collective.
 """
 from __future__ import annotations
 
@@ -51,7 +58,11 @@ WORKLOADS = {
     "c2": (1_000_000, 10_000, 50_000, "synthetic 1M sentence-pair Zipfian corpus (V=50k), 10k queries, max phrase len 5 (BASELINE.json configs[1])"),
     "c1": (10_000, 100, 2_000, "synthetic toy-scale corpus: 10k sentence pairs (V=2k), 100 queries (stand-in for the unshipped toy/ corpus, configs[0])"),
     "mid": (200_000, 2_000, 30_000, "synthetic 200k sentence-pair corpus (V=30k), 2k queries (development size)"),
+    "c3": (10_000_000, 100_000, 50_000, "synthetic 10M sentence-pair corpus (~260M tokens, V=50k), 100k queries, one- and two-gap rules (BASELINE.json configs[2])"),
 }
+STRONG_QUERIES = 80_000          # fixed query set of the strong-scaling block (8 shards of one 10 k batch at N = 8)
+STRONG_SEED = 8765
+BATCH_QUERIES = 10_000           # queries per batch of a stream (run.c's CGXH_DEFAULT_BATCH)
 
 
 def log(*a):
@@ -67,6 +78,29 @@ def make_inputs(workload: str, rank: int):
     log("[rank %d] synthetic corpus: n=%d source tokens, m=%d target tokens, Q=%d queries (T=%d tokens), lex=%d entries, %.1f s"
         % (rank, lay["n"], lay["m"], len(lay["qry_off"]) - 1, len(lay["qry_tok"]), len(lay["lex_f"]), time.time() - t0))
     return lay
+
+
+def make_query_sets(workload: str, lay, world: int):
+    """Rank 0: the query batch of every rank (rank r: seed 4321 + r, as make_inputs(workload, r) would give it) and the fixed
+    strong-scaling set, as ids of the corpus vocabulary.  The corpus itself is not generated again."""
+    from cgx_b200 import synth
+    ns, nq, v, _ = WORKLOADS[workload]
+    weak = [(np.ascontiguousarray(lay["qry_tok"], dtype=np.int32), np.ascontiguousarray(lay["qry_off"], dtype=np.int32))]
+    for r in range(1, world):
+        w, off = synth.generate_queries(ns, nq, v_src=v, v_tgt=v, seed=1234, qry_seed=4321 + r)
+        weak.append((synth.query_ids(lay["src_names"], w), off.astype(np.int32)))
+    w, off = synth.generate_queries(ns, STRONG_QUERIES, v_src=v, v_tgt=v, seed=1234, qry_seed=STRONG_SEED)
+    strong = (synth.query_ids(lay["src_names"], w), off.astype(np.int32))
+    return {"weak": weak, "strong": strong, "n": int(lay["n"])}
+
+
+def config_of(workload: str, n_tokens: int, Q: int, T: int, world: int):
+    """`config` of the JSON line -- the same dictionary from both arms (the driver compares them)."""
+    ns, nq, v, desc = WORKLOADS[workload]
+    return {"workload": desc, "sentence_pairs": ns, "source_tokens": int(n_tokens), "queries_per_gpu": int(Q), "query_tokens_per_gpu": int(T),
+            "rule_shapes": "ab, Xab, abX, XabX, aXb, XaXb, aXbX, aXbXc (the reference's full set; superset of the quoted 1-gap)",
+            "samples": [300, 65, 70], "parallelism": "query-sharded x%d, index broadcast once" % world,
+            "l2": "explicit 256 MB flush between steps; the index working set (88 B per token pair) is far larger than the 126 MB L2"}
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -231,7 +265,6 @@ def reference_arm(args):
     times = [one_step() for _ in range(args.steps)]
     total = sum(times)
     value = sample_q * args.steps / total
-    desc = WORKLOADS[args.workload][3]
     sample = ("%d queries per step (%d processes x %d), each process one oracle batch against the full corpus index; "
               "the reference has no CPU matcher/extractor, so the path is the oracle port; suffix array by the reference's SuffixArray.c"
               % (sample_q, workers, per_worker))
@@ -239,8 +272,8 @@ def reference_arm(args):
         "impl": "reference", "metric": "query sentences/sec (grammar extraction)", "value": value, "unit": "query sentences/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": desc, "queries_per_step": sample_q, "source_tokens": int(lay["n"])},
-        "cpu_baseline": {"value": value, "unit": "query sentences/s", "cores": workers, "kind": "port", "sample": sample,
+        "config": config_of(args.workload, int(lay["n"]), Q, len(lay["qry_tok"]), args.gpus),
+        "cpu_baseline": {"value": value, "unit": "query sentences/s", "cores": workers, "kind": "port", "sample": sample, "queries_per_step": sample_q,
                          "sa_build_s": sa_sec if sa_sec is not None else port_sa_s, "sa_build_kind": sa_kind},
         "e2e": {"value": value, "unit": "query sentences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -262,12 +295,86 @@ def result_bytes(ex):
     from cgx_b200._lib import Result
     r = Result()
     ex.L.cgx_result(ex.h, C.byref(r))
+    return result_bytes_of(r)
+
+
+def result_bytes_of(r):
     q1 = int(np.ctypeslib.as_array(r.q1_off, shape=(r.Q + 1,))[-1]) if r.Q else 0
     q2 = int(np.ctypeslib.as_array(r.q2_off, shape=(r.Q + 1,))[-1]) if r.Q else 0
     b = 4 * (r.T * 5 + r.G * 4 + r.D1 * 8 + r.D2 * 4 + 2 * (r.Q + 1) + q1 + q2)
     for k in range(3):
         b += 16 * r.n_rules[k] + (8 + 4) * r.n_ids[k]
     return int(b)
+
+
+def touch(r):
+    """Device->host read of a step's result: the rule counts and the last rule of every kind, from the host mirrors."""
+    tot = 0
+    for k in range(3):
+        n = int(r.n_rules[k])
+        tot += n
+        if n:
+            last = (C.c_char * 16).from_address(r.rules[k] + 16 * (n - 1))
+            tot += last.raw[0] & 0
+    return tot
+
+
+def run_c3(args, device):
+    """Second block: BASELINE.json configs[2].  10 M sentence pairs (~260 M source tokens), 100 k queries streamed in 10 k-query
+    batches through cgx_extract_begin (a batch whose hit lists exceed the 31-bit result indices is refused and halved, as
+    bin/strmatchcuda does).  One untimed warm-up batch (buffer growth), then one timed pass over all queries."""
+    import torch
+    from cgx_b200 import synth
+    from cgx_b200.extractor import GrammarExtractor
+    ns, nq, v, desc = WORKLOADS["c3"]
+    nq = min(nq, args.c3_queries)
+    t0 = time.time()
+    c = synth.generate(ns, nq, v_src=v, v_tgt=v, seed=1234, qry_seed=4321)
+    lay = synth.text_layout(c)
+    del c
+    gen_s = time.time() - t0
+    tok = np.ascontiguousarray(lay["qry_tok"], dtype=np.int32)
+    off = np.ascontiguousarray(lay["qry_off"], dtype=np.int32)
+    Q, T = len(off) - 1, len(tok)
+    log("c3: n=%d source tokens, Q=%d queries (T=%d tokens), lex=%d entries, generated in %.1f s" % (lay["n"], Q, T, len(lay["lex_f"]), gen_s))
+    ex = GrammarExtractor(device)
+    t0 = time.time()
+    info = ex.build_index(lay)
+    index_wall = time.time() - t0
+    n_tokens, src_max = int(lay["n"]), int(lay["str"][: lay["n"]].max())
+    log("c3 index: SA %.1f ms (%d rounds), auxiliary %.1f ms, %.2f GB resident, wall %.2f s" % (info["sa_build_ms"], info["sa_rounds"], info["aux_build_ms"],
+                                                                                           info["index_bytes"] / 1e9, index_wall))
+    del lay
+    w1 = min(Q, BATCH_QUERIES)
+    ex.extract_stream(tok[: off[w1]], off[: w1 + 1], batch_queries=BATCH_QUERIES)                 # warm-up: buffers grow to batch size
+    acc = {"rules": 0, "d2h": 0, "batches": 0}
+
+    def on_batch(a, b, r):
+        acc["rules"] += touch(r)
+        acc["d2h"] += result_bytes_of(r)
+        acc["batches"] += 1
+    ex.profile(True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    infos = ex.extract_stream(tok, off, batch_queries=BATCH_QUERIES, on_batch=on_batch)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    prof = ex.profile_report()
+    ex.profile(False)
+    ex.close()
+    dev_ms = sum(i["ms_total"] for i in infos)
+    kern = {k: {"ms": round(x["ms"], 3), "launches": x["launches"], "alg_bytes": x["bytes"], "gbs": (x["bytes"] / 1e9) / (x["ms"] / 1e3) if x["ms"] > 0 else None}
+            for k, x in prof.items()}
+    tot = {k: int(sum(i[k] for i in infos)) for k in ("hits1", "hits2", "samples", "n_ab", "n_1gap", "n_2gap", "launches")}
+    tot["rules"] = [int(sum(i["rules"][k] for i in infos)) for k in range(3)]
+    return {"workload": desc, "sentence_pairs": ns, "source_tokens": n_tokens, "source_vocabulary": src_max - 2, "queries": Q, "query_tokens": T,
+            "value": Q / (dev_ms / 1e3), "unit": "query sentences/s", "device_ms_total": dev_ms,
+            "e2e": {"value": Q / wall, "unit": "query sentences/s", "wall_s": wall, "h2d_bytes": 4 * (2 * T + Q + len(infos)), "d2h_bytes": acc["d2h"],
+                    "rules_read_back": acc["rules"], "api": "cgx_extract_begin + cgx_result_at per batch, host buffers"},
+            "batches": len(infos), "batch_queries": BATCH_QUERIES, "largest_batch_queries": max(i["q1"] - i["q0"] for i in infos),
+            "smallest_batch_queries": min(i["q1"] - i["q0"] for i in infos),
+            "sa_build": {"gpu_ms": info["sa_build_ms"], "rounds": info["sa_rounds"], "key_bits": info["sa_key_bits"], "aux_index_ms": info["aux_build_ms"]},
+            "index_bytes": int(info["index_bytes"]), "index_wall_s": index_wall, "corpus_generation_s": gen_s, "totals": tot, "kernels": kern}
 
 
 def bind_to_gpu_numa_node(local, rank):
@@ -305,8 +412,19 @@ def gpu_arm(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    lay = make_inputs(args.workload, rank)
-    Q, T = len(lay["qry_off"]) - 1, len(lay["qry_tok"])
+    # corpus and every rank's queries: generated once, on rank 0 (round 1 regenerated the 1 M-pair corpus on every rank)
+    lay, qsets = None, None
+    if rank == 0:
+        lay = make_inputs(args.workload, 0)
+        t0 = time.time()
+        qsets = make_query_sets(args.workload, lay, world)
+        log("query sets for %d rank(s) + %d-query strong-scaling set: %.1f s" % (world, STRONG_QUERIES, time.time() - t0))
+    if world > 1:
+        box = [qsets]
+        dist.broadcast_object_list(box, src=0)
+        qsets = box[0]
+    q_tok, q_off = qsets["weak"][rank]
+    Q, T = len(q_off) - 1, len(q_tok)
     ex = GrammarExtractor(local)             # raises when the CUDA library / device is missing: there is no fallback
     bcast_ms, bcast_bytes = 0.0, 0
     if rank == 0:
@@ -337,9 +455,9 @@ def gpu_arm(args):
         del str_d, sa_d
 
     # device-resident query batch (value) and pinned host copies (e2e)
-    qt_h = torch.from_numpy(np.ascontiguousarray(lay["qry_tok"], dtype=np.int32)).pin_memory()
-    qo_h = torch.from_numpy(np.ascontiguousarray(lay["qry_off"], dtype=np.int32)).pin_memory()
-    t2q = np.repeat(np.arange(Q, dtype=np.int32), np.diff(lay["qry_off"]))
+    qt_h = torch.from_numpy(np.ascontiguousarray(q_tok, dtype=np.int32)).pin_memory()
+    qo_h = torch.from_numpy(np.ascontiguousarray(q_off, dtype=np.int32)).pin_memory()
+    t2q = np.repeat(np.arange(Q, dtype=np.int32), np.diff(q_off))
     qt_d, qo_d, t2q_d = qt_h.to(dev), qo_h.to(dev), torch.from_numpy(t2q).to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
     qt_np, qo_np = qt_h.numpy(), qo_h.numpy()
@@ -361,17 +479,6 @@ def gpu_arm(args):
         t0 = time.perf_counter()
         binfo = ex.extract(qt_np, qo_np, fetch=False)    # cgx_extract: returns after every result array is on the host
         return time.perf_counter() - t0, binfo
-
-    def touch(r):
-        """Device->host read of a step's result: the rule counts and the last rule of every kind, from the host mirrors."""
-        tot = 0
-        for k in range(3):
-            n = int(r.n_rules[k])
-            tot += n
-            if n:
-                last = (C.c_char * 16).from_address(r.rules[k] + 16 * (n - 1))
-                tot += last.raw[0] & 0
-        return tot
 
     def run_e2e_pipelined(steps):
         """K batches through cgx_extract_begin: step i's D2H tail travels while step i+1 computes."""
@@ -417,13 +524,45 @@ def gpu_arm(args):
         dt, einfo = step_e2e()
         lat_s += dt
     barrier()
+    # ---- timed: strong scaling -- the fixed 80 k-query set, sharded (one warm pass, then `strong_passes` timed ones) ----------
+    stok, soff = qsets["strong"]
+    sq0, sq1 = cdist.shard_queries(soff, world, rank)
+    my_tok = np.ascontiguousarray(stok[soff[sq0]:soff[sq1]])
+    my_off = np.ascontiguousarray(soff[sq0:sq1 + 1] - soff[sq0])
+    strong_bytes = [0, 0]
+
+    def strong_pass():
+        rules = [0]
+
+        def on_batch(a, b, r):
+            rules[0] += touch(r)
+            strong_bytes[0] += result_bytes_of(r)
+            strong_bytes[1] += 1
+        barrier()
+        t0 = time.perf_counter()
+        infos = ex.extract_stream(my_tok, my_off, batch_queries=BATCH_QUERIES, on_batch=on_batch)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0, sum(i["ms_total"] for i in infos), len(infos), rules[0]
+
+    strong_pass()
+    strong_bytes = [0, 0]
+    strong_runs = [strong_pass() for _ in range(args.strong_passes)]
+    strong_s = sum(r[0] for r in strong_runs) / len(strong_runs)
+    strong_dev_ms = sum(r[1] for r in strong_runs) / len(strong_runs)
+    barrier()
     t_end = time.time()
     clocks = sampler.stop(t_begin, t_end) if sampler else None
 
-    tv = torch.tensor([dev_ms, e2e_s, wall_dev, lat_s], dtype=torch.float64, device=dev)
+    tv = torch.tensor([dev_ms, e2e_s, wall_dev, lat_s, strong_s, strong_dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tv, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_s_max, wall_dev_max, lat_s_max = (float(x) for x in tv.cpu())
+    dev_ms_max, e2e_s_max, wall_dev_max, lat_s_max, strong_s_max, strong_dev_ms_max = (float(x) for x in tv.cpu())
+    strong = {"queries": STRONG_QUERIES, "query_tokens": int(soff[-1]), "sharding": "cgx_b200.dist.shard_queries: contiguous, token-balanced, one shard per rank",
+              "batch_queries": BATCH_QUERIES, "passes": args.strong_passes, "value": STRONG_QUERIES / strong_s_max, "unit": "query sentences/s",
+              "ms_per_pass": 1e3 * strong_s_max, "device_value": STRONG_QUERIES / (strong_dev_ms_max / 1e3), "device_ms_per_pass": strong_dev_ms_max,
+              "rank0_shard_queries": int(sq1 - sq0), "rank0_batches_per_pass": strong_runs[0][2],
+              "rank0_d2h_bytes_per_pass": strong_bytes[0] // max(1, args.strong_passes),
+              "api": "cgx_extract_begin + cgx_result_at per batch (host buffers, every result array copied D2H), wall clock of the whole set, max over ranks"}
 
     if rank == 0:
         hbm_peak, peak_src = peaks()
@@ -452,15 +591,21 @@ def gpu_arm(args):
                 cpu = cpu_baseline_single(lay, args.cpu_budget)
             except Exception as e:  # the baseline is reported, never required
                 cpu = {"value": None, "unit": "query sentences/s", "cores": 1, "kind": "port", "sample": "failed: %r" % (e,)}
-        ns, nq, v, desc = WORKLOADS[args.workload]
+        c3 = None
+        if world == 1 and not args.no_c3 and args.workload == "c2":
+            ex.close()                                   # the C2 index leaves the GPU before the 260 M-token one is built
+            ex = None
+            del flush, qt_d, qo_d, t2q_d
+            torch.cuda.empty_cache()
+            try:
+                c3 = run_c3(args, local)
+            except Exception as e:  # the second block never costs the first its line
+                c3 = {"error": repr(e)}
         out = {
             "metric": "query sentences/sec (grammar extraction)", "value": world * Q * args.steps / (dev_ms_max / 1e3), "unit": "query sentences/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": desc, "sentence_pairs": ns, "source_tokens": int(lay["n"]), "queries_per_gpu": Q, "query_tokens_per_gpu": T,
-                       "rule_shapes": "ab, Xab, abX, XabX, aXb, XaXb, aXbX, aXbXc (the reference's full set; superset of the quoted 1-gap)",
-                       "samples": [300, 65, 70], "parallelism": "query-sharded x%d, index broadcast once" % world,
-                       "l2": "explicit 256 MB flush between steps; index working set %.2f GB >> 126 MB L2" % (info["index_bytes"] / 1e9)},
+            "config": config_of(args.workload, int(info["n"]), Q, T, world),
             "clocks": clocks,
             "e2e": {"value": world * Q * args.steps / e2e_s_max, "unit": "query sentences/s", "h2d_bytes_per_step": 4 * (2 * T + Q + 1),
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s_max / args.steps,
@@ -478,9 +623,13 @@ def gpu_arm(args):
                                            "ms_enum", "ms_join", "ms_extract", "ms_aggregate")},
             "kernels": kern,
             "wall_ms_per_step_incl_flush": 1e3 * wall_dev_max / args.steps,
+            "index_bytes": int(info["index_bytes"]),
+            "strong": strong,
+            "c3": c3,
         }
         print(json.dumps(out), flush=True)
-    ex.close()
+    if ex is not None:
+        ex.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -495,6 +644,9 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of single-thread CPU oracle work for cpu_baseline")
     ap.add_argument("--cpu-queries-per-core", type=int, default=1, help="--impl reference: queries per process and step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c3", action="store_true", help="skip the second block (BASELINE.json configs[2]: 10 M sentence pairs, 100 k queries; N = 1 only)")
+    ap.add_argument("--c3-queries", type=int, default=WORKLOADS["c3"][1], help="queries of the c3 block (default: all 100 k)")
+    ap.add_argument("--strong-passes", type=int, default=2, help="timed passes over the fixed strong-scaling query set")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cgx_b200" else max(args.warmup, 0)
     if args.impl == "reference":
