@@ -71,7 +71,7 @@ struct Batch {
     DevBuf ql_keys, ql_keys_tmp, q1_off, q1_ids, q2_off, q2_ids;
     int32_t enu1 = 0, D1 = 0;
     // joins
-    DevBuf j_tiles, j_bitmaps, j_aflag, j_aid, j_hash, pat1_ga, hit_keys, hit_keys_tmp, counters, missing;
+    DevBuf j_tiles, j_bitmaps, j_aflag, j_aid, j_hash, j_status, pat1_ga, hit_keys, hit_keys_tmp, counters, missing;
     int64_t hits1 = 0, hits2 = 0, j1_elems = 0;
     int pbits = 30;                        // position field width of the packed hit keys (bits needed for n)
     size_t hit_cap = 0;

@@ -322,6 +322,210 @@ __global__ void __launch_bounds__(JP_TILE) j1_pos_kernel(const JPArgs a) {
     if (lane == 0 && (lookups | elems)) { atomicAdd(&a.counter[1], (unsigned long long)lookups); atomicAdd(&a.counter[2], (unsigned long long)elems); }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Ordered emission (round 2).  Round 1 appended the hits with atomics in arbitrary order and put them in (pattern, position,
+// length) order with a stable radix sort over pattern AND position bits: six 8-bit passes over 2.4e8 keys at C2, seven at C3.
+// The position-major scan visits the corpus in position order anyway, so it can emit the hits in that order -- a tile's hits
+// are staged in shared memory in (position, length) order per pattern, tiles take their ids from a dynamic counter, and a
+// decoupled look-back over the per-tile hit counts (one 64-bit status word per tile, as in the onesweep pass) gives every tile
+// the exact offset of its hits in the output.  The stable sort then only has to cover the pattern bits: three passes
+// instead of six (seven).  The per-batch append counter and its ~10^6 atomics are gone as well.
+// ------------------------------------------------------------------------------------------------
+constexpr unsigned long long LB_PARTIAL = 1ull << 62, LB_INCLUSIVE = 2ull << 62, LB_VALUE = (1ull << 62) - 1ull;
+
+__device__ __forceinline__ unsigned long long lb_load(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void lb_store(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// Called by all 32 lanes of ONE warp of the CTA that owns `tile` (ids handed out in ascending order by a dynamic counter, so
+// every predecessor is running or done): publishes the tile's count and returns the sum of the counts of all tiles before it.
+__device__ __forceinline__ unsigned long long lb_exclusive_prefix(unsigned long long *__restrict__ status, uint32_t tile, unsigned long long count) {
+    const unsigned lane = threadIdx.x & 31;
+    if (lane == 0) lb_store(status + tile, (tile == 0 ? LB_INCLUSIVE : LB_PARTIAL) | count);
+    unsigned long long excl = 0;
+    if (tile > 0) {
+        long long end = (long long)tile - 1;                       // the window [end-31, end], lane 0 = nearest predecessor
+        while (true) {
+            const long long idx = end - (long long)lane;
+            unsigned long long v = idx >= 0 ? lb_load(status + idx) : LB_INCLUSIVE;
+            while (__any_sync(0xffffffffu, (v & (LB_PARTIAL | LB_INCLUSIVE)) == 0)) {
+                if ((v & (LB_PARTIAL | LB_INCLUSIVE)) == 0) { __nanosleep(40); v = lb_load(status + idx); }
+            }
+            const unsigned inc = __ballot_sync(0xffffffffu, (v & LB_INCLUSIVE) != 0);
+            const int first = inc ? __ffs(inc) - 1 : 31;             // nearest predecessor that already knows its inclusive prefix
+            unsigned long long mine = (int)lane <= first ? (v & LB_VALUE) : 0ull;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+            excl += mine;
+            if (inc) break;
+            end -= 32;
+        }
+        if (lane == 0) lb_store(status + tile, LB_INCLUSIVE | (excl + count));
+    }
+    return excl;
+}
+
+constexpr int JO_TILE = 256;          // positions per CTA (8 warps x 32 positions)
+constexpr int JO_CAP = 1024;          // staged hits per warp; a tile with a fuller warp is walked a second time, writing directly
+
+struct JOArgs {
+    JPArgs p;
+    unsigned long long *status;       // one look-back word per tile
+    uint32_t *tile_counter;
+    uint32_t num_tiles;
+    unsigned long long *total;        // grand total of hits (written by the last tile)
+};
+
+// One walk over the 32 positions of this warp.  DIRECT = false: hits go to the warp's shared-memory stage (pattern id +
+// position-in-tile/length word) while they fit, and are counted either way; the featureMissingCount side effect and the
+// statistics happen here.  DIRECT = true (second walk of a tile whose stage overflowed): hits are written to their final place.
+template <bool DIRECT>
+__device__ __forceinline__ unsigned jo_walk(const JPArgs &a, const int4 *__restrict__ s_win, int wrel, uint32_t P0, unsigned my_mask, const uint32_t my_aid[3],
+                                            uint32_t *__restrict__ st_pat, uint16_t *__restrict__ st_pl, unsigned long long out_base, unsigned &lookups,
+                                            unsigned &elems) {
+    const unsigned lane = threadIdx.x & 31, half = lane >> 4, h = lane & 15;
+    const int g = (int)h + 1;
+    unsigned count = 0;                                            // warp-uniform
+    for (int k = 0; k < 16; k++) {
+        const int src = 2 * k + (int)half;                         // half 0: even positions, half 1: odd ones -> pushes are in position order
+        const unsigned pm = __shfl_sync(0xffffffffu, my_mask, src);
+        const uint32_t a0 = __shfl_sync(0xffffffffu, my_aid[0], src), a1 = __shfl_sync(0xffffffffu, my_aid[1], src), a2 = __shfl_sync(0xffffffffu, my_aid[2], src);
+        if (!__any_sync(0xffffffffu, pm != 0)) continue;
+        const int rel = wrel + src;                                // tile-relative position p
+        const int p = (int)P0 + rel;
+#pragma unroll
+        for (int ls = 1; ls <= 3; ls++) {
+            const bool on = (pm >> (ls - 1)) & 1u;
+            if (!__any_sync(0xffffffffu, on)) continue;
+            const uint32_t av = ls == 1 ? a0 : ls == 2 ? a1 : a2;
+            const uint32_t ga = av & 0x7fffffffu;
+            const uint32_t w = on ? (uint32_t)s_win[rel + ls].w : 0u;
+            const int run = (int)((w >> 16) & 15u);
+            const bool live = on && g <= run && g <= CGX_MAX_RULE_SPAN - 1 - ls;
+            const bool ok = live && ((w >> (g - 1)) & 1u);
+            const bool miss = !DIRECT && live && !ok && (av >> 31);
+            const int qrel = rel + ls + g;
+            const uint32_t q = (uint32_t)(p + ls + g);
+            const int le_max = min(min(3, CGX_MAX_RULE_SYMBOLS - 1 - ls), CGX_MAX_RULE_SPAN - ls - g);
+            if (!DIRECT && h == 0 && on) elems++;
+            uint32_t ub[3];
+            bool cand[3];
+            const int4 wq = (ok || miss) ? s_win[qrel] : make_int4(0, 0, 0, 0);
+#pragma unroll
+            for (int le = 1; le <= 3; le++) {
+                cand[le - 1] = (ok && le <= le_max && q + (uint32_t)le <= a.n) || (miss && le == 1 && q < a.n);
+                ub[le - 1] = (uint32_t)(le == 1 ? wq.x : le == 2 ? wq.y : wq.z);
+            }
+#pragma unroll
+            for (int le = 1; le <= 3; le++)
+                if (cand[le - 1]) cand[le - 1] = bit_test((le == 1 && miss) ? a.bm_marker : a.bm[le - 1], ub[le - 1]);
+            ulonglong2 sv[3];
+            uint32_t ss[3];
+#pragma unroll
+            for (int le = 1; le <= 3; le++)
+                if (cand[le - 1]) { sv[le - 1] = ht_first(a.slots, a.mask, key1_of(ga, le, ub[le - 1]), &ss[le - 1]); if (!DIRECT) lookups++; }
+#pragma unroll
+            for (int le = 1; le <= 3; le++) {
+                if (!__any_sync(0xffffffffu, cand[le - 1])) continue;
+                uint64_t v = 0;
+                bool found = cand[le - 1] && ht_resolve(a.slots, a.mask, key1_of(ga, le, ub[le - 1]), ss[le - 1], sv[le - 1], &v);
+                if (found && miss) {
+                    if (v & 0x80000000u) atomicAdd(&a.missing[v & 0x7fffffffu], 1);
+                    found = false;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, found);
+                if (found) {
+                    const unsigned idx = count + __popc(m & lanemask_lt());
+                    const uint32_t pat = (uint32_t)(v & 0x7fffffffu);
+                    const int len = ls + g + le - 1;
+                    if (DIRECT) {
+                        const unsigned long long o = out_base + idx;
+                        if (o < a.cap) a.hits[o] = ((uint64_t)pat << a.pshift) | ((uint64_t)(uint32_t)p << 4) | (uint64_t)len;
+                    } else if (idx < (unsigned)JO_CAP) {
+                        st_pat[idx] = pat;
+                        st_pl[idx] = (uint16_t)((rel << 4) | len);
+                    }
+                }
+                count += __popc(m);
+            }
+        }
+    }
+    return count;
+}
+
+__global__ void __launch_bounds__(JO_TILE) j1_pos_ordered_kernel(const JOArgs o) {
+    const JPArgs &a = o.p;
+    __shared__ int4 s_win[JO_TILE + JP_HALO];
+    extern __shared__ __align__(16) unsigned char s_dyn[];          // per warp: JO_CAP pattern ids (u32), then JO_CAP position/length words (u16)
+    __shared__ unsigned s_wcount[JO_TILE / 32];
+    __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_tile;
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t *st_pat = reinterpret_cast<uint32_t *>(s_dyn) + (size_t)warp * JO_CAP;
+    uint16_t *st_pl = reinterpret_cast<uint16_t *>(s_dyn + sizeof(uint32_t) * JO_CAP * (JO_TILE / 32)) + (size_t)warp * JO_CAP;
+    if (tid == 0) s_tile = atomicAdd(o.tile_counter, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t P0 = tile * (uint32_t)JO_TILE;
+    for (int i = tid; i < JO_TILE + JP_HALO; i += JO_TILE) {
+        const uint32_t p = P0 + i;
+        s_win[i] = p < a.n ? __ldg(&a.jwin[p]) : make_int4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    // lane l of warp w tests "does a first phrase start at position 32 w + l" for the three lengths
+    const int wrel = (int)warp * 32;
+    const int4 mine = s_win[wrel + (int)lane];
+    uint32_t my_aid[3];
+    unsigned my_mask = 0;
+    const bool inside = P0 + (uint32_t)wrel + lane < a.n;
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+        const uint32_t ub = (uint32_t)(m == 0 ? mine.x : m == 1 ? mine.y : mine.z);
+        my_aid[m] = 0;
+        if (inside && bit_test(a.bma[m], ub)) { my_mask |= 1u << m; my_aid[m] = __ldg(&a.aid[m][ub]); }
+    }
+    unsigned lookups = 0, elems = 0;
+    const unsigned count = jo_walk<false>(a, s_win, wrel, P0, my_mask, my_aid, st_pat, st_pl, 0ull, lookups, elems);
+    if (lane == 0) s_wcount[warp] = count;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long tot = 0;
+#pragma unroll
+        for (int w = 0; w < JO_TILE / 32; w++) tot += s_wcount[w];
+        const unsigned long long excl = lb_exclusive_prefix(o.status, tile, tot);
+        if (lane == 0) {
+            s_base = excl;
+            if (tile == o.num_tiles - 1) *o.total = excl + tot;
+        }
+    }
+    __syncthreads();
+    unsigned long long base = s_base;
+    bool overflow = false;
+#pragma unroll
+    for (int w = 0; w < JO_TILE / 32; w++) {
+        const unsigned c = s_wcount[w];
+        if (w < (int)warp) base += c;
+        overflow |= c > (unsigned)JO_CAP;
+    }
+    if (!overflow) {
+        for (unsigned i = lane; i < count; i += 32) {
+            const unsigned long long dst = base + i;
+            const unsigned pl = st_pl[i];
+            if (dst < a.cap) a.hits[dst] = ((uint64_t)st_pat[i] << a.pshift) | ((uint64_t)(P0 + (pl >> 4)) << 4) | (uint64_t)(pl & 15u);
+        }
+    } else {
+        unsigned l2 = 0, e2 = 0;
+        jo_walk<true>(a, s_win, wrel, P0, my_mask, my_aid, st_pat, st_pl, base, l2, e2);
+    }
+    for (int off = 16; off; off >>= 1) { lookups += __shfl_xor_sync(0xffffffffu, lookups, off); elems += __shfl_xor_sync(0xffffffffu, elems, off); }
+    if (lane == 0 && (lookups | elems)) { atomicAdd(&a.counter[1], (unsigned long long)lookups); atomicAdd(&a.counter[2], (unsigned long long)elems); }
+}
+
 // per-pattern [start,count] in the sorted hit list
 __global__ void hit_ranges_kernel(const uint64_t *__restrict__ hits, size_t n, int shift, int32_t *__restrict__ start_count, int stride_ints) {
     size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -400,12 +604,31 @@ void stage_onegap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     for (int k = 0; k < 3; k++) { ap.bma[k] = bm + (size_t)(4 + k) * bm_words; ap.aid[k] = aid + (size_t)k * ix.n; ap.bm[k] = bm + (size_t)k * bm_words; }
     ap.bm_marker = bm + 3 * bm_words; ap.slots = slots; ap.mask = slots_n - 1; ap.pshift = b.pbits + 4; ap.counter = ctr; ap.missing = missing;
     unsigned long long host_ctr[3] = {0, 0, 0};
+    // position-major scans emit in position order (tile look-back): the sort below then covers the pattern bits only.
+    // CGX_JOIN_ORDERED=0 keeps round 1's unordered append + full (pattern, position) sort for that variant too.
+    bool ordered = position_major;
+    if (const char *e = getenv("CGX_JOIN_ORDERED")) { if (!strcmp(e, "0")) ordered = false; }
+    const uint32_t n_tiles = cgx_div_up(ix.n, JO_TILE);
+    JOArgs ao;
+    if (ordered) {
+        ao.status = b.j_status.get<unsigned long long>((size_t)n_tiles + 1);
+        ao.tile_counter = tot + 12;
+        ao.num_tiles = n_tiles;
+        ao.total = ctr;                                              // [0] hits, as the unordered variants count them
+        static bool attr_set = false;
+        if (!attr_set) { CUDA_CHECK(cudaFuncSetAttribute(j1_pos_ordered_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JO_TILE / 32 * JO_CAP * 6)); attr_set = true; }
+    }
     while (true) {
         a.hits = ap.hits = b.hit_keys.get<uint64_t>(b.hit_cap);
         a.cap = ap.cap = b.hit_cap;
         CUDA_CHECK(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long) * 3, stream));
         CUDA_CHECK(cudaMemsetAsync(missing, 0, sizeof(int32_t) * (size_t)D1, stream));
-        if (n_elems && position_major) PROF("join_onegap", 0.0, (j1_pos_kernel<<<cgx_div_up(ix.n, JP_TILE), JP_TILE, 0, stream>>>(ap)));
+        if (n_elems && ordered) {
+            ao.p = ap;
+            CUDA_CHECK(cudaMemsetAsync(ao.status, 0, sizeof(unsigned long long) * (size_t)n_tiles, stream));
+            CUDA_CHECK(cudaMemsetAsync(ao.tile_counter, 0, sizeof(uint32_t), stream));
+            PROF("join_onegap", 0.0, (j1_pos_ordered_kernel<<<n_tiles, JO_TILE, JO_TILE / 32 * JO_CAP * 6, stream>>>(ao)));
+        } else if (n_elems && position_major) PROF("join_onegap", 0.0, (j1_pos_kernel<<<cgx_div_up(ix.n, JP_TILE), JP_TILE, 0, stream>>>(ap)));
         else if (n_elems) PROF("join_onegap", 0.0, (j1_scan_kernel<<<cgx_div_up(n_elems, J1_BLOCK), J1_BLOCK, 0, stream>>>(a)));
         b.launches += 1;
         read_u64s(host_ctr, ctr, 3, stream);
@@ -427,7 +650,8 @@ void stage_onegap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     uint64_t *hs;
     // The sort is stable and hits of one (pattern, position) leave the scan in ascending length (one stage_push, lane = gap
     // width), so sorting on (pattern, position) alone yields (pattern, position, length) order: the 4 length bits are skipped.
-    radix_sort<uint64_t>(hits, tmp, nullptr, nullptr, H, 4, b.pbits + 4 + cgx_bits_for((uint64_t)D1), stream, b.radix, &hs, nullptr, &b.launches);
+    // Ordered emission left every pattern's hits in (position, length) order already: only the pattern bits are sorted on.
+    radix_sort<uint64_t>(hits, tmp, nullptr, nullptr, H, ordered ? b.pbits + 4 : 4, b.pbits + 4 + cgx_bits_for((uint64_t)D1), stream, b.radix, &hs, nullptr, &b.launches);
     // the buffer the sort ended in becomes hits1_sorted (buffers rotate instead of a 16 B/hit copy)
     std::swap(b.hits1_sorted, hs == hits ? b.hit_keys : b.hit_keys_tmp);
     uint64_t *dst = b.hits1_sorted.ptr<uint64_t>();
@@ -509,6 +733,103 @@ __global__ void __launch_bounds__(256) j2_scan_kernel(const uint64_t *__restrict
     if ((threadIdx.x & 31) == 0 && active) { atomicAdd(&counter[1], (unsigned long long)probes); atomicAdd(&counter[2], (unsigned long long)active); }
 }
 
+
+// Ordered form of j2_scan_kernel: thread k of a tile owns parent hit k of the (pattern, position, length)-sorted one-gap list; its
+// (up to 13) two-gap hits are parked in shared memory in ascending width, the tile's total goes through the same look-back as
+// above, and every thread writes its hits at base + (hits of the threads before it).  The output is therefore in (parent
+// pattern, position, length, width) order, a pattern aXbXc has ONE parent, so a stable sort on the two-gap pattern bits alone
+// yields (pattern, position, length, width) order: three passes instead of seven (eight at C3).
+constexpr int J2O_SLOTS = CGX_MAX_RULE_SPAN - 2;       // widths 1..13
+__global__ void __launch_bounds__(256) j2_ordered_kernel(const uint64_t *__restrict__ hits1, size_t H1, int pbits, const unsigned long long *__restrict__ child_sig,
+                                                         const int32_t *__restrict__ str, const uint32_t *__restrict__ gapw, const PackTab tab, int cbits,
+                                                         unsigned long long *__restrict__ counter, unsigned long long *__restrict__ status,
+                                                         uint32_t *__restrict__ tile_counter, uint32_t num_tiles, uint64_t *__restrict__ hits, size_t cap) {
+    __shared__ uint32_t s_d2[J2O_SLOTS][256];
+    __shared__ unsigned s_wsum[8];
+    __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_tile;
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const size_t k = (size_t)tile * 256 + tid;
+    unsigned active = 0, probes = 0;
+    uint32_t bits = 0, d1 = 0;
+    unsigned long long sig = 0;
+    int p = 0, L = 0;
+    if (k < H1) {
+        const uint64_t hk = hits1[k];
+        d1 = (uint32_t)(hk >> (pbits + 4));
+        sig = __ldg(&child_sig[d1]);
+        if (sig) {
+            p = (int)((hk >> 4) & ((1ull << pbits) - 1)); L = (int)(hk & 15);
+            const uint32_t w = __ldg(&gapw[p + L + 1]);
+            const int run = (int)((w >> 16) & 15u);
+            const int gmax = min(run, CGX_MAX_RULE_SPAN - 2 - L);
+            bits = gmax > 0 ? (w & ((1u << gmax) - 1u)) : 0u;
+            active = 1;
+        }
+    }
+    unsigned found_mask = 0, c = 0;                    // widths that hit (bit g2-1), their count
+    while (__any_sync(0xffffffffu, bits != 0)) {
+        int rr[4];
+        uint32_t cc[4], ss[4];
+        unsigned long long sv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            rr[u] = 0;
+            if (bits) { rr[u] = p + L + 1 + __ffs(bits); bits &= bits - 1; probes++; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (rr[u]) cc[u] = (uint32_t)__ldg(&str[rr[u]]);
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (rr[u] && !((sig >> sig_bit(cc[u])) & 1ull)) rr[u] = 0;
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (rr[u]) sv[u] = pt_first(tab, ((uint64_t)d1 << cbits) | (uint64_t)cc[u], &ss[u]);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (!__any_sync(0xffffffffu, rr[u] != 0)) continue;
+            uint64_t d2 = 0;
+            if (rr[u] && pt_resolve(tab, ((uint64_t)d1 << cbits) | (uint64_t)cc[u], ss[u], sv[u], &d2)) {
+                s_d2[c][tid] = (uint32_t)d2;                          // widths are visited in ascending order
+                found_mask |= 1u << (rr[u] - p - L - 2);
+                c++;
+            }
+        }
+    }
+    // exclusive prefix of c over the CTA
+    unsigned incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += t;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) tot += s_wsum[w];
+        const unsigned long long excl = lb_exclusive_prefix(status, tile, tot);
+        if (lane == 0) {
+            s_base = excl;
+            if (tile == num_tiles - 1) counter[0] = excl + tot;
+        }
+    }
+    __syncthreads();
+    unsigned long long o = s_base + (incl - c);
+#pragma unroll
+    for (int w = 0; w < 8; w++) if (w < (int)warp) o += s_wsum[w];
+    for (unsigned j = 0; j < c; j++) {
+        const int g2 = __ffs(found_mask);                             // j-th smallest width
+        found_mask &= found_mask - 1;
+        if (o + j < cap)
+            hits[o + j] = ((uint64_t)s_d2[j][tid] << (pbits + 8)) | ((uint64_t)(uint32_t)p << 8) | ((uint64_t)L << 4) | (uint64_t)(L + 1 + g2);
+    }
+    for (int off = 16; off; off >>= 1) { active += __shfl_xor_sync(0xffffffffu, active, off); probes += __shfl_xor_sync(0xffffffffu, probes, off); }
+    if (lane == 0 && active) { atomicAdd(&counter[1], (unsigned long long)probes); atomicAdd(&counter[2], (unsigned long long)active); }
+}
+
 void stage_twogap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     b.hits2 = 0;
     const int D2 = b.D2;
@@ -528,9 +849,19 @@ void stage_twogap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     b.launches++;
     const size_t H1 = (size_t)b.hits1;
     unsigned long long host_ctr[3] = {0, 0, 0};
+    bool ordered = true;                                   // CGX_JOIN_ORDERED=0: round 1's unordered append + full sort
+    if (const char *e = getenv("CGX_JOIN_ORDERED")) { if (!strcmp(e, "0")) ordered = false; }
+    const uint32_t n_tiles = cgx_div_up(H1, 256);
+    unsigned long long *status = ordered ? b.j_status.get<unsigned long long>((size_t)n_tiles + 1) : nullptr;
     while (true) {
         uint64_t *hits = b.hit_keys.get<uint64_t>(b.hit_cap);
         CUDA_CHECK(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long) * 3, stream));
+        if (ordered) {
+            CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(unsigned long long) * (size_t)n_tiles, stream));
+            CUDA_CHECK(cudaMemsetAsync(tot + 12, 0, sizeof(uint32_t), stream));
+            PROF("join_twogap", 0.0, (j2_ordered_kernel<<<n_tiles, 256, 0, stream>>>(b.hits1_sorted.ptr<uint64_t>(), H1, b.pbits, child_sig, ix.str.ptr<int32_t>(),
+                                                               ix.gapw.ptr<uint32_t>(), tab, cbits, ctr, status, tot + 12, n_tiles, hits, b.hit_cap)));
+        } else
         PROF("join_twogap", 0.0, (j2_scan_kernel<<<cgx_div_up(H1, 256), 256, 0, stream>>>(b.hits1_sorted.ptr<uint64_t>(), H1, b.pbits, child_sig, ix.str.ptr<int32_t>(),
                                                            ix.gapw.ptr<uint32_t>(), tab, cbits, ctr, hits, b.hit_cap)));
         b.launches += 1;
@@ -546,7 +877,7 @@ void stage_twogap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     uint64_t *hits = b.hit_keys.ptr<uint64_t>();
     uint64_t *tmp = b.hit_keys_tmp.get<uint64_t>(H);
     uint64_t *hs;
-    radix_sort<uint64_t>(hits, tmp, nullptr, nullptr, H, 0, b.pbits + 8 + cgx_bits_for((uint64_t)D2), stream, b.radix, &hs, nullptr, &b.launches);
+    radix_sort<uint64_t>(hits, tmp, nullptr, nullptr, H, ordered ? b.pbits + 8 : 0, b.pbits + 8 + cgx_bits_for((uint64_t)D2), stream, b.radix, &hs, nullptr, &b.launches);
     std::swap(b.hits2_sorted, hs == hits ? b.hit_keys : b.hit_keys_tmp);
     uint64_t *dst = b.hits2_sorted.ptr<uint64_t>();
     static_assert(sizeof(Pat2) == 16, "Pat2 layout");

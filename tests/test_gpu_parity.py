@@ -411,12 +411,14 @@ def test_radix_sort_matches_stable_reference(n, bits, with_vals):
         L.cgx_destroy(h)
 
 
-@pytest.mark.parametrize("mode", ["phrase", "position"])
-def test_join_variants_agree_with_oracle(mode, micro, micro_oracle, monkeypatch):
-    """Both one-gap join variants (walk of the first phrases' occurrence lists / one streamed pass over the corpus) must give
-    the oracle's hit list, two-gap hits and missing counts bit for bit."""
+@pytest.mark.parametrize("mode,ordered", [("phrase", "1"), ("position", "1"), ("position", "0"), ("phrase", "0")])
+def test_join_variants_agree_with_oracle(mode, ordered, micro, micro_oracle, monkeypatch):
+    """Every join variant -- walk of the first phrases' occurrence lists / one streamed pass over the corpus, hits emitted in
+    position order through the tile look-back (sort on the pattern bits only) / appended unordered (full sort) -- must give the
+    oracle's hit list, two-gap hits and missing counts bit for bit."""
     from cgx_b200.extractor import GrammarExtractor
     monkeypatch.setenv("CGX_JOIN_MODE", mode)
+    monkeypatch.setenv("CGX_JOIN_ORDERED", ordered)
     _, lay = micro
     ex = GrammarExtractor(0)
     try:
