@@ -71,10 +71,11 @@ struct Batch {
     DevBuf ql_keys, ql_keys_tmp, q1_off, q1_ids, q2_off, q2_ids;
     int32_t enu1 = 0, D1 = 0;
     // joins
-    DevBuf j_tiles, j_bitmaps, j_aflag, j_aid, j_hash, j_status, pat1_ga, hit_keys, hit_keys_tmp, counters, missing;
+    DevBuf j_tiles, j_bitmaps, j_aflag, j_aid, j_hash, j_status, j_segcnt, pat1_ga, hit_keys, hit_keys_tmp, counters, missing;
     int64_t hits1 = 0, hits2 = 0, j1_elems = 0;
     int pbits = 30;                        // position field width of the packed hit keys (bits needed for n)
     size_t hit_cap = 0;
+    bool j1_smem_opt_in = false;          // j1_pos_ordered_kernel's dynamic shared memory opted in on this device
     DevBuf hits1_sorted, hits2_sorted;     // uint64 keys: pattern << (pbits+4) | pos << 4 | len-1  /  pattern << (pbits+8) | pos << 8 | L << 4 | c-pos
     // two-gap enumeration
     DevBuf e2_count, e2_keys, e2_keys_tmp, e2_vals, e2_vals_tmp, e2_flags, pat2;

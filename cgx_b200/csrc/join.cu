@@ -326,59 +326,23 @@ __global__ void __launch_bounds__(JP_TILE) j1_pos_kernel(const JPArgs a) {
 // ------------------------------------------------------------------------------------------------
 // Ordered emission (round 2).  Round 1 appended the hits with atomics in arbitrary order and put them in (pattern, position,
 // length) order with a stable radix sort over pattern AND position bits: six 8-bit passes over 2.4e8 keys at C2, seven at C3.
-// The position-major scan visits the corpus in position order anyway, so it can emit the hits in that order -- a tile's hits
-// are staged in shared memory in (position, length) order per pattern, tiles take their ids from a dynamic counter, and a
-// decoupled look-back over the per-tile hit counts (one 64-bit status word per tile, as in the onesweep pass) gives every tile
-// the exact offset of its hits in the output.  The stable sort then only has to cover the pattern bits: three passes
-// instead of six (seven).  The per-batch append counter and its ~10^6 atomics are gone as well.
+// The position-major scan visits the corpus in position order anyway: a tile (256 positions) now stages ALL its hits in shared
+// memory in (position, length) order per pattern, takes one contiguous segment of the output with a single atomicAdd, and
+// records (segment start, count) under its tile number.  A prefix sum over the counts in tile order and one streaming copy
+// (16 B per hit, ~1 ms at C2) then lay the segments out in position order, so the stable sort only has to cover the pattern
+// bits: three passes instead of six (seven).  (First attempt, measured and dropped: a decoupled look-back over the per-tile
+// counts, as in the onesweep pass, so that tiles write straight to their final place.  A tile knows its count only when its
+// walk is finished and tile durations are heavy-tailed -- hits per tile vary by orders of magnitude -- so every tile behind
+// a slow one spun in the look-back holding its SM slot: join_onegap 13.0 -> 20.4 ms, join_twogap 11.0 -> 19.0 ms at C2.)
 // ------------------------------------------------------------------------------------------------
-constexpr unsigned long long LB_PARTIAL = 1ull << 62, LB_INCLUSIVE = 2ull << 62, LB_VALUE = (1ull << 62) - 1ull;
-
-__device__ __forceinline__ unsigned long long lb_load(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void lb_store(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-// Called by all 32 lanes of ONE warp of the CTA that owns `tile` (ids handed out in ascending order by a dynamic counter, so
-// every predecessor is running or done): publishes the tile's count and returns the sum of the counts of all tiles before it.
-__device__ __forceinline__ unsigned long long lb_exclusive_prefix(unsigned long long *__restrict__ status, uint32_t tile, unsigned long long count) {
-    const unsigned lane = threadIdx.x & 31;
-    if (lane == 0) lb_store(status + tile, (tile == 0 ? LB_INCLUSIVE : LB_PARTIAL) | count);
-    unsigned long long excl = 0;
-    if (tile > 0) {
-        long long end = (long long)tile - 1;                       // the window [end-31, end], lane 0 = nearest predecessor
-        while (true) {
-            const long long idx = end - (long long)lane;
-            unsigned long long v = idx >= 0 ? lb_load(status + idx) : LB_INCLUSIVE;
-            while (__any_sync(0xffffffffu, (v & (LB_PARTIAL | LB_INCLUSIVE)) == 0)) {
-                if ((v & (LB_PARTIAL | LB_INCLUSIVE)) == 0) { __nanosleep(40); v = lb_load(status + idx); }
-            }
-            const unsigned inc = __ballot_sync(0xffffffffu, (v & LB_INCLUSIVE) != 0);
-            const int first = inc ? __ffs(inc) - 1 : 31;             // nearest predecessor that already knows its inclusive prefix
-            unsigned long long mine = (int)lane <= first ? (v & LB_VALUE) : 0ull;
-#pragma unroll
-            for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-            excl += mine;
-            if (inc) break;
-            end -= 32;
-        }
-        if (lane == 0) lb_store(status + tile, LB_INCLUSIVE | (excl + count));
-    }
-    return excl;
-}
-
 constexpr int JO_TILE = 256;          // positions per CTA (8 warps x 32 positions)
 constexpr int JO_CAP = 1024;          // staged hits per warp; a tile with a fuller warp is walked a second time, writing directly
 
 struct JOArgs {
     JPArgs p;
-    unsigned long long *status;       // one look-back word per tile
-    uint32_t *tile_counter;
-    uint32_t num_tiles;
-    unsigned long long *total;        // grand total of hits (written by the last tile)
+    unsigned long long *seg_base;     // per tile: start of its segment in the (unordered) output
+    uint32_t *seg_count;              // per tile: hits
+    unsigned stage_cap;               // <= JO_CAP (tests lower it to drive tiles through the second, direct walk)
 };
 
 // One walk over the 32 positions of this warp.  DIRECT = false: hits go to the warp's shared-memory stage (pattern id +
@@ -386,8 +350,8 @@ struct JOArgs {
 // statistics happen here.  DIRECT = true (second walk of a tile whose stage overflowed): hits are written to their final place.
 template <bool DIRECT>
 __device__ __forceinline__ unsigned jo_walk(const JPArgs &a, const int4 *__restrict__ s_win, int wrel, uint32_t P0, unsigned my_mask, const uint32_t my_aid[3],
-                                            uint32_t *__restrict__ st_pat, uint16_t *__restrict__ st_pl, unsigned long long out_base, unsigned &lookups,
-                                            unsigned &elems) {
+                                            uint32_t *__restrict__ st_pat, uint16_t *__restrict__ st_pl, unsigned stage_cap, unsigned long long out_base,
+                                            unsigned &lookups, unsigned &elems) {
     const unsigned lane = threadIdx.x & 31, half = lane >> 4, h = lane & 15;
     const int g = (int)h + 1;
     unsigned count = 0;                                            // warp-uniform
@@ -446,7 +410,7 @@ __device__ __forceinline__ unsigned jo_walk(const JPArgs &a, const int4 *__restr
                     if (DIRECT) {
                         const unsigned long long o = out_base + idx;
                         if (o < a.cap) a.hits[o] = ((uint64_t)pat << a.pshift) | ((uint64_t)(uint32_t)p << 4) | (uint64_t)len;
-                    } else if (idx < (unsigned)JO_CAP) {
+                    } else if (idx < stage_cap) {
                         st_pat[idx] = pat;
                         st_pl[idx] = (uint16_t)((rel << 4) | len);
                     }
@@ -464,13 +428,10 @@ __global__ void __launch_bounds__(JO_TILE) j1_pos_ordered_kernel(const JOArgs o)
     extern __shared__ __align__(16) unsigned char s_dyn[];          // per warp: JO_CAP pattern ids (u32), then JO_CAP position/length words (u16)
     __shared__ unsigned s_wcount[JO_TILE / 32];
     __shared__ unsigned long long s_base;
-    __shared__ uint32_t s_tile;
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t *st_pat = reinterpret_cast<uint32_t *>(s_dyn) + (size_t)warp * JO_CAP;
     uint16_t *st_pl = reinterpret_cast<uint16_t *>(s_dyn + sizeof(uint32_t) * JO_CAP * (JO_TILE / 32)) + (size_t)warp * JO_CAP;
-    if (tid == 0) s_tile = atomicAdd(o.tile_counter, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
+    const uint32_t tile = blockIdx.x;
     const uint32_t P0 = tile * (uint32_t)JO_TILE;
     for (int i = tid; i < JO_TILE + JP_HALO; i += JO_TILE) {
         const uint32_t p = P0 + i;
@@ -490,18 +451,17 @@ __global__ void __launch_bounds__(JO_TILE) j1_pos_ordered_kernel(const JOArgs o)
         if (inside && bit_test(a.bma[m], ub)) { my_mask |= 1u << m; my_aid[m] = __ldg(&a.aid[m][ub]); }
     }
     unsigned lookups = 0, elems = 0;
-    const unsigned count = jo_walk<false>(a, s_win, wrel, P0, my_mask, my_aid, st_pat, st_pl, 0ull, lookups, elems);
+    const unsigned count = jo_walk<false>(a, s_win, wrel, P0, my_mask, my_aid, st_pat, st_pl, o.stage_cap, 0ull, lookups, elems);
     if (lane == 0) s_wcount[warp] = count;
     __syncthreads();
-    if (warp == 0) {
-        unsigned long long tot = 0;
+    if (tid == 0) {
+        unsigned tot = 0;
 #pragma unroll
         for (int w = 0; w < JO_TILE / 32; w++) tot += s_wcount[w];
-        const unsigned long long excl = lb_exclusive_prefix(o.status, tile, tot);
-        if (lane == 0) {
-            s_base = excl;
-            if (tile == o.num_tiles - 1) *o.total = excl + tot;
-        }
+        const unsigned long long seg = tot ? atomicAdd(&a.counter[0], (unsigned long long)tot) : 0ull;     // one atomic per tile
+        o.seg_base[tile] = seg;
+        o.seg_count[tile] = tot;
+        s_base = seg;
     }
     __syncthreads();
     unsigned long long base = s_base;
@@ -510,7 +470,7 @@ __global__ void __launch_bounds__(JO_TILE) j1_pos_ordered_kernel(const JOArgs o)
     for (int w = 0; w < JO_TILE / 32; w++) {
         const unsigned c = s_wcount[w];
         if (w < (int)warp) base += c;
-        overflow |= c > (unsigned)JO_CAP;
+        overflow |= c > o.stage_cap;
     }
     if (!overflow) {
         for (unsigned i = lane; i < count; i += 32) {
@@ -520,10 +480,20 @@ __global__ void __launch_bounds__(JO_TILE) j1_pos_ordered_kernel(const JOArgs o)
         }
     } else {
         unsigned l2 = 0, e2 = 0;
-        jo_walk<true>(a, s_win, wrel, P0, my_mask, my_aid, st_pat, st_pl, base, l2, e2);
+        jo_walk<true>(a, s_win, wrel, P0, my_mask, my_aid, st_pat, st_pl, o.stage_cap, base, l2, e2);
     }
     for (int off = 16; off; off >>= 1) { lookups += __shfl_xor_sync(0xffffffffu, lookups, off); elems += __shfl_xor_sync(0xffffffffu, elems, off); }
     if (lane == 0 && (lookups | elems)) { atomicAdd(&a.counter[1], (unsigned long long)lookups); atomicAdd(&a.counter[2], (unsigned long long)elems); }
+}
+
+// segments (one per tile, in arrival order) -> tile order: dst[seg_dst[t] + i] = src[seg_base[t] + i]
+__global__ void __launch_bounds__(256) seg_copy_kernel(const uint64_t *__restrict__ src, const unsigned long long *__restrict__ seg_base, const uint32_t *__restrict__ seg_dst,
+                                                       const uint32_t *__restrict__ seg_count, uint64_t *__restrict__ dst) {
+    const uint32_t t = blockIdx.x;
+    const uint32_t cnt = seg_count[t];
+    const uint64_t *s = src + seg_base[t];
+    uint64_t *d = dst + seg_dst[t];
+    for (uint32_t i = threadIdx.x; i < cnt; i += 256) d[i] = s[i];
 }
 
 // per-pattern [start,count] in the sorted hit list
@@ -604,19 +574,23 @@ void stage_onegap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     for (int k = 0; k < 3; k++) { ap.bma[k] = bm + (size_t)(4 + k) * bm_words; ap.aid[k] = aid + (size_t)k * ix.n; ap.bm[k] = bm + (size_t)k * bm_words; }
     ap.bm_marker = bm + 3 * bm_words; ap.slots = slots; ap.mask = slots_n - 1; ap.pshift = b.pbits + 4; ap.counter = ctr; ap.missing = missing;
     unsigned long long host_ctr[3] = {0, 0, 0};
-    // position-major scans emit in position order (tile look-back): the sort below then covers the pattern bits only.
+    // position-major scans emit in position order (tile segments + ordered copy): the sort below then covers the pattern bits only.
     // CGX_JOIN_ORDERED=0 keeps round 1's unordered append + full (pattern, position) sort for that variant too.
     bool ordered = position_major;
     if (const char *e = getenv("CGX_JOIN_ORDERED")) { if (!strcmp(e, "0")) ordered = false; }
     const uint32_t n_tiles = cgx_div_up(ix.n, JO_TILE);
     JOArgs ao;
+    uint32_t *seg_dst = nullptr;
     if (ordered) {
-        ao.status = b.j_status.get<unsigned long long>((size_t)n_tiles + 1);
-        ao.tile_counter = tot + 12;
-        ao.num_tiles = n_tiles;
-        ao.total = ctr;                                              // [0] hits, as the unordered variants count them
-        static bool attr_set = false;
-        if (!attr_set) { CUDA_CHECK(cudaFuncSetAttribute(j1_pos_ordered_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JO_TILE / 32 * JO_CAP * 6)); attr_set = true; }
+        ao.seg_base = b.j_status.get<unsigned long long>((size_t)n_tiles + 1);
+        ao.seg_count = b.j_segcnt.get<uint32_t>((size_t)2 * n_tiles + 2);
+        seg_dst = ao.seg_count + n_tiles + 1;
+        ao.stage_cap = JO_CAP;
+        if (const char *e = getenv("CGX_JOIN_STAGE_CAP")) { const unsigned v = (unsigned)strtoul(e, nullptr, 10); if (v >= 1 && v < (unsigned)JO_CAP) ao.stage_cap = v; }
+        if (!b.j1_smem_opt_in) {      // per context = per device: the opt-in is a per-device attribute of the kernel
+            CUDA_CHECK(cudaFuncSetAttribute(j1_pos_ordered_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JO_TILE / 32 * JO_CAP * 6));
+            b.j1_smem_opt_in = true;
+        }
     }
     while (true) {
         a.hits = ap.hits = b.hit_keys.get<uint64_t>(b.hit_cap);
@@ -625,8 +599,6 @@ void stage_onegap_join(const Index &ix, Batch &b, cudaStream_t stream) {
         CUDA_CHECK(cudaMemsetAsync(missing, 0, sizeof(int32_t) * (size_t)D1, stream));
         if (n_elems && ordered) {
             ao.p = ap;
-            CUDA_CHECK(cudaMemsetAsync(ao.status, 0, sizeof(unsigned long long) * (size_t)n_tiles, stream));
-            CUDA_CHECK(cudaMemsetAsync(ao.tile_counter, 0, sizeof(uint32_t), stream));
             PROF("join_onegap", 0.0, (j1_pos_ordered_kernel<<<n_tiles, JO_TILE, JO_TILE / 32 * JO_CAP * 6, stream>>>(ao)));
         } else if (n_elems && position_major) PROF("join_onegap", 0.0, (j1_pos_kernel<<<cgx_div_up(ix.n, JP_TILE), JP_TILE, 0, stream>>>(ap)));
         else if (n_elems) PROF("join_onegap", 0.0, (j1_scan_kernel<<<cgx_div_up(n_elems, J1_BLOCK), J1_BLOCK, 0, stream>>>(a)));
@@ -647,13 +619,19 @@ void stage_onegap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     const size_t H = (size_t)b.hits1;
     uint64_t *hits = b.hit_keys.ptr<uint64_t>();
     uint64_t *tmp = b.hit_keys_tmp.get<uint64_t>(H);
+    if (ordered) {      // the tiles' segments, in tile (= position) order
+        exclusive_scan_u32(ao.seg_count, seg_dst, (size_t)n_tiles, nullptr, stream, b.scan, 0, &b.launches);
+        PROF("join_seg_copy", 16.0 * (double)H, (seg_copy_kernel<<<n_tiles, 256, 0, stream>>>(hits, ao.seg_base, seg_dst, ao.seg_count, tmp)));
+        b.launches++;
+        std::swap(hits, tmp);
+    }
     uint64_t *hs;
-    // The sort is stable and hits of one (pattern, position) leave the scan in ascending length (one stage_push, lane = gap
-    // width), so sorting on (pattern, position) alone yields (pattern, position, length) order: the 4 length bits are skipped.
-    // Ordered emission left every pattern's hits in (position, length) order already: only the pattern bits are sorted on.
+    // The sort is stable and hits of one (pattern, position) leave the scan in ascending length (lane = gap width), so the 4
+    // length bits are never sorted on; after an ordered emission every pattern's hits are in (position, length) order already
+    // and only the pattern bits are.
     radix_sort<uint64_t>(hits, tmp, nullptr, nullptr, H, ordered ? b.pbits + 4 : 4, b.pbits + 4 + cgx_bits_for((uint64_t)D1), stream, b.radix, &hs, nullptr, &b.launches);
     // the buffer the sort ended in becomes hits1_sorted (buffers rotate instead of a 16 B/hit copy)
-    std::swap(b.hits1_sorted, hs == hits ? b.hit_keys : b.hit_keys_tmp);
+    std::swap(b.hits1_sorted, hs == b.hit_keys.ptr<uint64_t>() ? b.hit_keys : b.hit_keys_tmp);
     uint64_t *dst = b.hits1_sorted.ptr<uint64_t>();
     static_assert(sizeof(Pat1) == 32, "Pat1 layout");
     hit_ranges_kernel<<<cgx_div_up(H, 256), 256, 0, stream>>>(dst, H, b.pbits + 4, &b.pat1.ptr<int32_t>()[4], 8);
@@ -735,23 +713,21 @@ __global__ void __launch_bounds__(256) j2_scan_kernel(const uint64_t *__restrict
 
 
 // Ordered form of j2_scan_kernel: thread k of a tile owns parent hit k of the (pattern, position, length)-sorted one-gap list; its
-// (up to 13) two-gap hits are parked in shared memory in ascending width, the tile's total goes through the same look-back as
-// above, and every thread writes its hits at base + (hits of the threads before it).  The output is therefore in (parent
-// pattern, position, length, width) order, a pattern aXbXc has ONE parent, so a stable sort on the two-gap pattern bits alone
-// yields (pattern, position, length, width) order: three passes instead of seven (eight at C3).
+// (up to 13) two-gap hits are parked in shared memory in ascending width, the tile takes one segment of the output with a single
+// atomicAdd (as above), and every thread writes its hits at segment start + (hits of the threads before it).  After the segments
+// are copied into tile order the list is in (parent pattern, position, length, width) order; a pattern aXbXc has ONE parent, so a
+// stable sort on the two-gap pattern bits alone yields (pattern, position, length, width) order: three passes instead of seven
+// (eight at C3).
 constexpr int J2O_SLOTS = CGX_MAX_RULE_SPAN - 2;       // widths 1..13
 __global__ void __launch_bounds__(256) j2_ordered_kernel(const uint64_t *__restrict__ hits1, size_t H1, int pbits, const unsigned long long *__restrict__ child_sig,
                                                          const int32_t *__restrict__ str, const uint32_t *__restrict__ gapw, const PackTab tab, int cbits,
-                                                         unsigned long long *__restrict__ counter, unsigned long long *__restrict__ status,
-                                                         uint32_t *__restrict__ tile_counter, uint32_t num_tiles, uint64_t *__restrict__ hits, size_t cap) {
+                                                         unsigned long long *__restrict__ counter, unsigned long long *__restrict__ seg_base,
+                                                         uint32_t *__restrict__ seg_count, uint64_t *__restrict__ hits, size_t cap) {
     __shared__ uint32_t s_d2[J2O_SLOTS][256];
     __shared__ unsigned s_wsum[8];
     __shared__ unsigned long long s_base;
-    __shared__ uint32_t s_tile;
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
+    const uint32_t tile = blockIdx.x;
     const size_t k = (size_t)tile * 256 + tid;
     unsigned active = 0, probes = 0;
     uint32_t bits = 0, d1 = 0;
@@ -806,15 +782,14 @@ __global__ void __launch_bounds__(256) j2_ordered_kernel(const uint64_t *__restr
     }
     if (lane == 31) s_wsum[warp] = incl;
     __syncthreads();
-    if (warp == 0) {
-        unsigned long long tot = 0;
+    if (tid == 0) {
+        unsigned tot = 0;
 #pragma unroll
         for (int w = 0; w < 8; w++) tot += s_wsum[w];
-        const unsigned long long excl = lb_exclusive_prefix(status, tile, tot);
-        if (lane == 0) {
-            s_base = excl;
-            if (tile == num_tiles - 1) counter[0] = excl + tot;
-        }
+        const unsigned long long seg = tot ? atomicAdd(&counter[0], (unsigned long long)tot) : 0ull;
+        seg_base[tile] = seg;
+        seg_count[tile] = tot;
+        s_base = seg;
     }
     __syncthreads();
     unsigned long long o = s_base + (incl - c);
@@ -852,15 +827,15 @@ void stage_twogap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     bool ordered = true;                                   // CGX_JOIN_ORDERED=0: round 1's unordered append + full sort
     if (const char *e = getenv("CGX_JOIN_ORDERED")) { if (!strcmp(e, "0")) ordered = false; }
     const uint32_t n_tiles = cgx_div_up(H1, 256);
-    unsigned long long *status = ordered ? b.j_status.get<unsigned long long>((size_t)n_tiles + 1) : nullptr;
+    unsigned long long *seg_base = ordered ? b.j_status.get<unsigned long long>((size_t)n_tiles + 1) : nullptr;
+    uint32_t *seg_count = ordered ? b.j_segcnt.get<uint32_t>((size_t)2 * n_tiles + 2) : nullptr;
+    uint32_t *seg_dst = ordered ? seg_count + n_tiles + 1 : nullptr;
     while (true) {
         uint64_t *hits = b.hit_keys.get<uint64_t>(b.hit_cap);
         CUDA_CHECK(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long) * 3, stream));
         if (ordered) {
-            CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(unsigned long long) * (size_t)n_tiles, stream));
-            CUDA_CHECK(cudaMemsetAsync(tot + 12, 0, sizeof(uint32_t), stream));
             PROF("join_twogap", 0.0, (j2_ordered_kernel<<<n_tiles, 256, 0, stream>>>(b.hits1_sorted.ptr<uint64_t>(), H1, b.pbits, child_sig, ix.str.ptr<int32_t>(),
-                                                               ix.gapw.ptr<uint32_t>(), tab, cbits, ctr, status, tot + 12, n_tiles, hits, b.hit_cap)));
+                                                               ix.gapw.ptr<uint32_t>(), tab, cbits, ctr, seg_base, seg_count, hits, b.hit_cap)));
         } else
         PROF("join_twogap", 0.0, (j2_scan_kernel<<<cgx_div_up(H1, 256), 256, 0, stream>>>(b.hits1_sorted.ptr<uint64_t>(), H1, b.pbits, child_sig, ix.str.ptr<int32_t>(),
                                                            ix.gapw.ptr<uint32_t>(), tab, cbits, ctr, hits, b.hit_cap)));
@@ -876,9 +851,15 @@ void stage_twogap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     const size_t H = (size_t)b.hits2;
     uint64_t *hits = b.hit_keys.ptr<uint64_t>();
     uint64_t *tmp = b.hit_keys_tmp.get<uint64_t>(H);
+    if (ordered) {
+        exclusive_scan_u32(seg_count, seg_dst, (size_t)n_tiles, nullptr, stream, b.scan, 0, &b.launches);
+        PROF("join_seg_copy", 16.0 * (double)H, (seg_copy_kernel<<<n_tiles, 256, 0, stream>>>(hits, seg_base, seg_dst, seg_count, tmp)));
+        b.launches++;
+        std::swap(hits, tmp);
+    }
     uint64_t *hs;
     radix_sort<uint64_t>(hits, tmp, nullptr, nullptr, H, ordered ? b.pbits + 8 : 0, b.pbits + 8 + cgx_bits_for((uint64_t)D2), stream, b.radix, &hs, nullptr, &b.launches);
-    std::swap(b.hits2_sorted, hs == hits ? b.hit_keys : b.hit_keys_tmp);
+    std::swap(b.hits2_sorted, hs == b.hit_keys.ptr<uint64_t>() ? b.hit_keys : b.hit_keys_tmp);
     uint64_t *dst = b.hits2_sorted.ptr<uint64_t>();
     static_assert(sizeof(Pat2) == 16, "Pat2 layout");
     hit_ranges_kernel<<<cgx_div_up(H, 256), 256, 0, stream>>>(dst, H, b.pbits + 8, &b.pat2.ptr<int32_t>()[2], 4);

@@ -137,6 +137,32 @@ __device__ __forceinline__ void rs_st_status(uint64_t *p, uint64_t v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+
+// Decoupled look-back of one digit (one thread per digit): sum of the counts the preceding tiles published for this digit.
+// ncu of round 1's kernel put 38 % of all stall samples on this loop: it walked back one tile per DEPENDENT global load
+// (~9 tiles deep on average, every step a full L2 round trip).  Now the status words of the next RS_LB predecessors are
+// loaded together and consumed in order -- the chain is a quarter as long; a word that is not published yet is re-polled alone.
+constexpr int RS_LB = 4;
+template <typename S>
+__device__ __forceinline__ uint32_t rs_look_back(const S *__restrict__ status, uint32_t tile, unsigned digit) {
+    using ST = RsStatus<S>;
+    uint32_t excl = 0;
+    long long t = (long long)tile - 1;
+    while (t >= 0) {
+        S v[RS_LB];
+#pragma unroll
+        for (int k = 0; k < RS_LB; k++) v[k] = t - k >= 0 ? rs_ld_status(status + (size_t)(t - k) * RS_BINS + digit) : (S)ST::INCLUSIVE;
+#pragma unroll
+        for (int k = 0; k < RS_LB; k++) {
+            while ((v[k] & (ST::PARTIAL | ST::INCLUSIVE)) == 0) { __nanosleep(20); v[k] = rs_ld_status(status + (size_t)(t - k) * RS_BINS + digit); }
+            excl += (uint32_t)(v[k] & ST::VALUE_MASK);               // counts stay below 2^32 (n < 2^32)
+            if (v[k] & ST::INCLUSIVE) return excl;
+        }
+        t -= RS_LB;
+    }
+    return excl;
+}
+
 template <typename K>
 __global__ void __launch_bounds__(RS_BLOCK) rs_histogram_kernel(const K *__restrict__ keys, size_t n, RadixPlan plan,
                                                                 uint32_t *__restrict__ hist) {
@@ -270,15 +296,7 @@ __global__ void __launch_bounds__(RS_BLOCK, HAS_VALUES ? 3 : 4) rs_onesweep_kern
         // decoupled look-back over the preceding tiles' published counts
         uint32_t excl = 0;
         if (tile > 0) {
-            int t = (int)tile - 1;
-            while (true) {
-                const S *pst = status + (size_t)t * RS_BINS + tid;
-                S v = rs_ld_status(pst);
-                while ((v & (ST::PARTIAL | ST::INCLUSIVE)) == 0) { __nanosleep(20); v = rs_ld_status(pst); }
-                excl += (uint32_t)(v & ST::VALUE_MASK);          // counts stay below 2^32 (n < 2^32)
-                if (v & ST::INCLUSIVE) break;
-                t--;
-            }
+            excl = rs_look_back<S>(status, tile, tid);
             rs_st_status(status + (size_t)tile * RS_BINS + tid, (S)(excl + tile_count) | ST::INCLUSIVE);
         }
         s_global_base[tid] = digit_offset[tid] + excl - bin_start;
@@ -391,7 +409,6 @@ __global__ void __launch_bounds__(RS_BLOCK, HAS_VALUES ? 2 : 3) rs_onesweep_bulk
     __syncthreads();                                             // s_next read by everyone before thread 0 overwrites it
 
     while (tile < num_tiles) {
-        if (tid == 0) s_next = atomicAdd(tile_counter, 1u);
         for (int i = tid; i < RS_WARPS * RS_BINS / 2; i += RS_BLOCK) reinterpret_cast<uint32_t *>(&s_warp_hist[0][0])[i] = 0;
         const bool full = ((size_t)tile + 1) * RS_TILE <= n;     // all tiles but the last
         K *s_keys = reinterpret_cast<K *>(s_stages + (size_t)stage * STAGE_BYTES);
@@ -419,9 +436,7 @@ __global__ void __launch_bounds__(RS_BLOCK, HAS_VALUES ? 2 : 3) rs_onesweep_bulk
                 if (HAS_VALUES) val[i] = idx < n ? vals_in[idx] : 0u;
             }
         }
-        __syncthreads();                                         // keys are in registers: this stage is free for the exchange, the
-        const uint32_t next = s_next;                            // other one (last read before the barrier that ended the previous
-        if (tid == 0 && next < num_tiles && ((size_t)next + 1) * RS_TILE <= n) issue(next, stage ^ 1u);   // tile) for the refill
+        __syncthreads();                                         // keys are in registers: this stage is free for the exchange
         // ---- warp-level multisplit: stable rank of every key among the warp's keys with the same digit
 #pragma unroll
         for (int i = 0; i < RS_ITEMS; i++) {
@@ -461,22 +476,21 @@ __global__ void __launch_bounds__(RS_BLOCK, HAS_VALUES ? 2 : 3) rs_onesweep_bulk
             for (int w = 0; w < RS_BINS / 32; w++) pre += (w < (int)warp) ? s_scan_tot[w] : 0u;
             const uint32_t bin_start = pre + incl - tile_count;
             s_bin_start[tid] = bin_start;
+            // the next tile id is taken only here (its round trip overlaps the look-back): a CTA that held two ids from the start of
+            // a tile (round 2a) made every successor poll for a tile that had not begun -- 40 polls per tile in ncu
+            uint32_t nxt = 0;
+            if (tid == 0) nxt = atomicAdd(tile_counter, 1u);
             uint32_t excl = 0;
             if (tile > 0) {
-                int t = (int)tile - 1;
-                while (true) {
-                    const S *pst = status + (size_t)t * RS_BINS + tid;
-                    S v = rs_ld_status(pst);
-                    while ((v & (ST::PARTIAL | ST::INCLUSIVE)) == 0) { __nanosleep(20); v = rs_ld_status(pst); }
-                    excl += (uint32_t)(v & ST::VALUE_MASK);
-                    if (v & ST::INCLUSIVE) break;
-                    t--;
-                }
+                excl = rs_look_back<S>(status, tile, tid);
                 rs_st_status(status + (size_t)tile * RS_BINS + tid, (S)(excl + tile_count) | ST::INCLUSIVE);
             }
             s_global_base[tid] = __ldg(&digit_offset[tid]) + excl - bin_start;
+            if (tid == 0) s_next = nxt;
         }
         __syncthreads();
+        const uint32_t next = s_next;
+        if (tid == 0 && next < num_tiles && ((size_t)next + 1) * RS_TILE <= n) issue(next, stage ^ 1u);   // lands during the exchange and the stores
         // ---- staging position of every key, exchange through this tile's stage buffer
 #pragma unroll
         for (int i = 0; i < RS_ITEMS; i++) {
@@ -554,11 +568,12 @@ void radix_sort(K *keys, K *keys_tmp, uint32_t *vals, uint32_t *vals_tmp, size_t
     K *kin = keys, *kout = keys_tmp;
     uint32_t *vin = vals, *vout = vals_tmp;
     const size_t smem = rs_smem_bytes<K>(vals != nullptr);
-    // persistent cp.async.bulk form (default) or the one-tile-per-CTA form (CGX_RS_V1=1; also when a buffer is not 16-byte
-    // aligned, which bulk copies require)
-    static const bool force_v1 = getenv("CGX_RS_V1") != nullptr;
+    // one-tile-per-CTA form (default), or the persistent cp.async.bulk form (CGX_RS_BULK=1, 16-byte aligned buffers): measured on
+    // B200 the bulk form is the slower one (profiles/README.md r02): the pass is bound by the look-back chain and by issue slots,
+    // not by the latency of the key loads, and two 32-KB stages cost a quarter of the occupancy
+    static const bool want_bulk = getenv("CGX_RS_BULK") != nullptr;
     const bool aligned = (((uintptr_t)keys | (uintptr_t)keys_tmp | (uintptr_t)vals | (uintptr_t)vals_tmp) & 15u) == 0;
-    const bool bulk = !force_v1 && aligned;
+    const bool bulk = want_bulk && aligned;
     if (!bulk) {
         CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, true, uint32_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<K>(true)));
         CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<K, false, uint32_t, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes<K>(false)));

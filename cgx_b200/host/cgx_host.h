@@ -66,6 +66,9 @@ void cgxh_queries_free(cgxh_queries_t *q);
 int cgxh_write_grammars(const char *outdir, const cgx_result_t *res, const int32_t *qry_off, int32_t qid_base, const cgxh_side_t *src,
                         const cgxh_side_t *tgt, int n_threads);
 
+/* the writer's printf("%f") replacement for float-valued features (exactly glibc's digits; writer.c); returns the length */
+int cgxh_format_f6(float x, char *out);
+
 #define CGXH_DEFAULT_BATCH 10000
 typedef struct {
     const char *reffile, *qryfile, *reftargetfile, *align, *wordscdec, *destinationDirectory;   /* options_t, ComTypes.h:67-78 */

@@ -67,47 +67,87 @@ def _run_cli(files, out, extra=()):
     return r
 
 
-def test_c1_grammar_files_equal_oracle_and_reference_self_agreement(c1, c1_files, tmp_path):
-    """Drop-in CLI on the six C1 files: 100 % equal to the oracle (floats 1e-5), and at least as close to the reference
-    binary as the reference is to itself (two runs of the unmodified binary), minus 0.2 %."""
-    from _oracle import REF_BIN, Oracle
-    mine = tmp_path / "mine"
-    _run_cli(c1_files, mine)
-    o = Oracle.from_files(c1_files["f"], c1_files["e"], c1_files["a"], c1_files["lex"])
+def _product_and_oracle(files, n_qry, tmp):
+    from _oracle import Oracle
+    mine = tmp / "mine"
+    _run_cli(files, mine)
+    o = Oracle.from_files(files["f"], files["e"], files["a"], files["lex"])
     o.build_sa()
-    o.run_query_file(c1_files["q"])
-    orc = tmp_path / "orc"
+    o.run_query_file(files["q"])
+    orc = tmp / "orc"
     orc.mkdir()
     o.write_grammars(str(orc))
     c = gc.compare_dirs(str(mine), str(orc), rtol=1e-5, atol=2e-6)
-    assert c["files"] == C1["n_qry"] and c["only_a"] == 0 and c["only_b"] == 0 and c["float_mismatch"] == 0, c
-    if not os.path.exists(REF_BIN):
-        pytest.skip("oracle/_ref/strmatchcuda not present")
+    assert c["files"] == n_qry and c["only_a"] == 0 and c["only_b"] == 0 and c["float_mismatch"] == 0, c
+    return mine
+
+
+def _reference_twice(files, tmp):
+    """Two runs of the unmodified reference binary on the same files; None when it does not survive its own kernels."""
+    from _oracle import REF_BIN
     refs = []
     for name in ("ref_a", "ref_b"):
-        d = tmp_path / name
+        d = tmp / name
         d.mkdir()
-        r = subprocess.run([REF_BIN, c1_files["f"], c1_files["q"], c1_files["e"], c1_files["a"], c1_files["lex"], str(d)], capture_output=True, text=True,
-                           cwd=str(tmp_path))
-        assert "Start Printing Gappy Phrases" in r.stderr, r.stderr[-1500:]
+        r = subprocess.run([REF_BIN, files["f"], files["q"], files["e"], files["a"], files["lex"], str(d)], capture_output=True, text=True, cwd=str(tmp))
+        if "Start Printing Gappy Phrases" not in r.stderr:
+            return None, r.stderr[-600:]
         refs.append(d)
-    self_ = gc.compare_dirs(str(refs[0]), str(refs[1]))
-    prod = [gc.compare_dirs(str(mine), str(d)) for d in refs]
-    report = {"config": "C1 stand-in", "lines": prod[0]["n_b"], "reference_vs_reference": self_["frac_equal"],
-              "product_vs_reference": [p["frac_equal"] for p in prod],
-              "float_mismatch_by_feature": {"reference_vs_reference": self_["float_mismatch_by_feature"],
-                                            "product_vs_reference": prod[0]["float_mismatch_by_feature"]},
-              "line_diffs": {"reference_vs_reference": [self_["only_a"], self_["only_b"], self_["float_mismatch"]],
-                             "product_vs_reference": [prod[0]["only_a"], prod[0]["only_b"], prod[0]["float_mismatch"]]}}
+    return refs, ""
+
+
+# C1 first; the reference binary itself dies on it ("illegal memory access" in oneGapLookUpSA, GappyLook.cu:128 -- it has no
+# bounds checks, SURVEY.md 8c), so the self-agreement is then measured on the next configuration it survives.
+SELF_AGREEMENT_CONFIGS = [
+    ("C1 stand-in (10k pairs, V=2k, 100 queries)", C1),
+    ("100k pairs, V=20k, 60 queries", dict(n_sent=100_000, n_qry=60, v_src=20_000, v_tgt=20_000, seed=1234, qry_seed=4321)),
+    ("3k pairs, V=600, 24 queries", dict(n_sent=3000, n_qry=24, v_src=600, v_tgt=600, n_phrases=1200, seed=99, qry_seed=77)),
+]
+
+
+def test_c1_grammar_files_equal_oracle(c1, c1_files, tmp_path):
+    """Drop-in CLI on the six C1 files: every grammar line equal to the oracle's (strings and flags exact, floats 1e-5)."""
+    _product_and_oracle(c1_files, C1["n_qry"], tmp_path)
+
+
+def test_reference_self_agreement(tmp_path):
+    """The reference binary is nondeterministic (atomic append order, a comparator that is not a strict weak order,
+    SuffixArray.cu:51-67, the featureMissingCount race, GappyLook.cu:759): run it TWICE on the same input, measure how well it
+    agrees with itself, and require the product to agree with it at least that well (minus 0.2 %) and above the 90 % bar."""
+    from _oracle import REF_BIN
+    from cgx_b200 import synth
+    if not os.path.exists(REF_BIN):
+        pytest.skip("oracle/_ref/strmatchcuda not present")
+    report, crashed = None, []
+    for name, cfg in SELF_AGREEMENT_CONFIGS:
+        work = tmp_path / ("cfg%d" % len(crashed))
+        work.mkdir()
+        files = synth.write_text(synth.generate(**cfg), str(work), "corpus")
+        refs, err = _reference_twice(files, work)
+        if refs is None:
+            crashed.append({"config": name, "reference_stderr_tail": err})
+            continue
+        mine = _product_and_oracle(files, cfg["n_qry"], work)
+        self_ = gc.compare_dirs(str(refs[0]), str(refs[1]))
+        prod = [gc.compare_dirs(str(mine), str(d)) for d in refs]
+        report = {"config": name, "lines": prod[0]["n_b"], "reference_vs_reference": self_["frac_equal"],
+                  "product_vs_reference": [p["frac_equal"] for p in prod],
+                  "float_mismatch_by_feature": {"reference_vs_reference": self_["float_mismatch_by_feature"],
+                                                "product_vs_reference": prod[0]["float_mismatch_by_feature"]},
+                  "line_diffs_only_a_only_b_float": {"reference_vs_reference": [self_["only_a"], self_["only_b"], self_["float_mismatch"]],
+                                                     "product_vs_reference": [prod[0]["only_a"], prod[0]["only_b"], prod[0]["float_mismatch"]]},
+                  "reference_crashed_on": crashed}
+        break
+    assert report is not None, crashed
     print("REF_SELF_AGREEMENT " + json.dumps(report))
     out = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out, exist_ok=True)
-    with open(os.path.join(out, "ref_self_agreement_c1.json"), "w") as fh:
+    with open(os.path.join(out, "ref_self_agreement.json"), "w") as fh:
         json.dump(report, fh, indent=1)
-    assert self_["files"] == C1["n_qry"]
+    assert self_["files"] == cfg["n_qry"]
     for p in prod:
-        assert p["files"] == C1["n_qry"] and p["frac_equal"] >= 0.90                    # north-star bar
-        assert p["frac_equal"] >= self_["frac_equal"] - 0.002, report                   # as close to the reference as the reference itself
+        assert p["files"] == cfg["n_qry"] and p["frac_equal"] >= 0.90, report                # north-star bar
+        assert p["frac_equal"] >= self_["frac_equal"] - 0.002, report                         # as close to the reference as the reference itself
 
 
 def test_c2_full_batch_sampled_queries_equal_oracle(tmp_path):

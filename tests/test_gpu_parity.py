@@ -411,13 +411,16 @@ def test_radix_sort_matches_stable_reference(n, bits, with_vals):
         L.cgx_destroy(h)
 
 
-@pytest.mark.parametrize("mode,ordered", [("phrase", "1"), ("position", "1"), ("position", "0"), ("phrase", "0")])
+@pytest.mark.parametrize("mode,ordered", [("phrase", "1"), ("position", "1"), ("position", "0"), ("phrase", "0"), ("position", "direct")])
 def test_join_variants_agree_with_oracle(mode, ordered, micro, micro_oracle, monkeypatch):
     """Every join variant -- walk of the first phrases' occurrence lists / one streamed pass over the corpus, hits emitted in
     position order through the tile look-back (sort on the pattern bits only) / appended unordered (full sort) -- must give the
     oracle's hit list, two-gap hits and missing counts bit for bit."""
     from cgx_b200.extractor import GrammarExtractor
     monkeypatch.setenv("CGX_JOIN_MODE", mode)
+    if ordered == "direct":                                 # a 4-hit stage: most tiles overflow it and take the second, direct walk
+        monkeypatch.setenv("CGX_JOIN_STAGE_CAP", "4")
+        ordered = "1"
     monkeypatch.setenv("CGX_JOIN_ORDERED", ordered)
     _, lay = micro
     ex = GrammarExtractor(0)

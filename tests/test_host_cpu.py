@@ -169,3 +169,27 @@ int main(int argc, char **argv) {
     assert np.array_equal(mine["id"], ids)
     assert np.array_equal(mine["f"], idinfo[ids] & 0xFFFF) and np.array_equal(mine["fs"], idinfo[ids] >> 16)
 
+
+
+def test_writer_float_format_equals_printf(built):
+    """The grammar writer prints its five float features with a hand-rolled fixed-6 formatter (writer.c put_f6) instead of
+    snprintf("%f"): it must give glibc's digits for every float -- (double)x * 1e6 is exact for a 24-bit significand, so the
+    only rounding is rint()'s nearest-even, the one printf applies to the exact decimal expansion."""
+    from cgx_b200._lib import HOST_LIB_PATH
+    L = C.CDLL(HOST_LIB_PATH)
+    L.cgxh_format_f6.argtypes = [C.c_float, C.c_char_p]
+    L.cgxh_format_f6.restype = C.c_int
+    buf = C.create_string_buffer(64)
+    rng = np.random.default_rng(3)
+    vals = [0.0, -0.0, 1.0, -1.0, 99.0, 198.0, 0.5e-6, 1.5e-6, 2.5e-6, -0.4e-6, -0.5e-6, -0.6e-6, 0.0000005, 0.9999995, 0.9999994, 1e-7, 123456.789,
+            2.4771213, 0.30103, 16777216.0, 3.4e38, float("inf"), -float("inf")]
+    vals += list(rng.random(20000).astype(np.float32) * 5)
+    vals += list(-np.log10(rng.integers(1, 301, size=20000) / rng.integers(1, 301, size=20000), dtype=np.float32))
+    vals += list((rng.integers(0, 1 << 24, size=20000) * 5e-7).astype(np.float32))           # many values next to a half-way point
+    vals += list(np.frombuffer(rng.bytes(4 * 20000), dtype=np.float32))                      # arbitrary bit patterns
+    for v in vals:
+        x = float(np.float32(v))
+        if x != x:
+            continue
+        n = L.cgxh_format_f6(C.c_float(x), buf)
+        assert buf.value.decode() == "%f" % x and n == len(buf.value), (x, buf.value)

@@ -2,16 +2,24 @@
 # Scratch driver for one gpurun call of this round (development only).  Everything lands in gpurun_out/r2/.
 out=gpurun_out/r2; mkdir -p $out
 tag=${1:-a}
-timeout 180 python tools/sort_bench.py 24 23 0 3 1 > $out/sort_bulk_small_$tag.log 2>&1; rc=$?
-echo "sort bulk small rc=$rc" | tee -a $out/status_$tag.log
-if [ $rc -ne 0 ]; then export CGX_RS_V1=1; echo "falling back to CGX_RS_V1=1 for the rest" | tee -a $out/status_$tag.log; fi
-timeout 1800 python -m pytest tests -m gpu -q --durations=25 > $out/pytest_$tag.log 2>&1; echo "pytest rc=$?" | tee -a $out/status_$tag.log
-tail -45 $out/pytest_$tag.log
+for v in "" "CGX_RS_BULK=1"; do
+  for cfg in "27 48 0" "27 64 1"; do
+    echo "== $v sort_bench $cfg" >> $out/sort_$tag.log
+    env $v timeout 180 python tools/sort_bench.py $cfg 3 1 >> $out/sort_$tag.log 2>&1; echo "rc=$?" >> $out/sort_$tag.log
+  done
+done
+cat $out/sort_$tag.log
+timeout 1800 python -m pytest tests -m gpu -q --durations=12 > $out/pytest_$tag.log 2>&1; echo "pytest rc=$?" | tee -a $out/status_$tag.log
+tail -30 $out/pytest_$tag.log
 timeout 1200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $out/bench_$tag.json 2> $out/bench_$tag.err; echo "bench rc=$?" | tee -a $out/status_$tag.log
-tail -8 $out/bench_$tag.err
-# stall reasons of both onesweep forms (each command exits 0 without ncu right before its ncu run)
-timeout 180 python tools/sort_bench.py 27 48 0 2 0 > $out/sort_plain_$tag.log 2>&1 && \
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:rs_onesweep --launch-skip 6 --launch-count 2 -o $out/sort_bulk_$tag python tools/sort_bench.py 27 48 0 2 0 > $out/sort_ncu_$tag.log 2>&1
-CGX_RS_V1=1 timeout 180 python tools/sort_bench.py 27 48 0 2 0 >> $out/sort_plain_$tag.log 2>&1 && \
-CGX_RS_V1=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:rs_onesweep --launch-skip 6 --launch-count 2 -o $out/sort_v1_$tag python tools/sort_bench.py 27 48 0 2 0 >> $out/sort_ncu_$tag.log 2>&1
-cat $out/sort_plain_$tag.log; ls -la $out
+tail -6 $out/bench_$tag.err
+# where does the reference binary fault on the C1 stand-in?  (one compute-sanitizer tool in this call, no ncu)
+python - <<'PY' > $out/sanitize_gen_$tag.log 2>&1
+from cgx_b200 import synth
+c = synth.generate(10000, 100, v_src=2000, v_tgt=2000, seed=1234, qry_seed=4321)
+synth.write_text(c, "/tmp/cgx_san", "corpus")
+PY
+mkdir -p /tmp/cgx_san/out
+( cd /tmp/cgx_san && timeout 900 compute-sanitizer --tool memcheck --print-limit 5 $OLDPWD/oracle/_ref/strmatchcuda corpus.f corpus.q corpus.e corpus.a corpus.lex out ) > $out/sanitize_$tag.log 2>&1
+echo "sanitizer rc=$?" | tee -a $out/status_$tag.log
+grep -A12 "Invalid\|ERROR SUMMARY" $out/sanitize_$tag.log | head -60
