@@ -34,6 +34,12 @@ scoring) over the rank's query batch against the resident index.
            build, then all queries streamed in batches the way bin/strmatchcuda cuts them (a batch whose hit lists outgrow the
            31-bit result indices is refused and halved); device-resident and end-to-end rates, per-kernel table.  --no-c3 skips it.
 
+  gpu_reference : (N = 1 only) SURVEY.md 8(d)'s two reference legs, from the reference's own code on this box (tools/ref_timers.py,
+           oracle/_ref/strmatchcuda_dump = reference sources + timer hooks): its GPU binary's stage timers and its host
+           aggregation createLexicon*Fast (ExtractPair.c:515,664,939; one thread) on the largest configuration it survives here
+           (100 k sentence pairs, 60 queries: it faults at C1 and C2 sizes), with the product's CUDA-event stage times and the
+           drop-in CLI's wall clock (text files in, grammar files out) on the same six files.  --no-gpu-reference skips it.
+
 Multi-GPU (weak scaling): the corpus and every rank's queries are generated once, on rank 0; the index is built once on rank 0
 and broadcast over NVLink with NCCL; every rank then processes its own 10 k-query batch; there is no data-path collective.
 """
@@ -366,6 +372,7 @@ def run_c3(args, device):
     kern = {k: {"ms": round(x["ms"], 3), "launches": x["launches"], "alg_bytes": x["bytes"], "gbs": (x["bytes"] / 1e9) / (x["ms"] / 1e3) if x["ms"] > 0 else None}
             for k, x in prof.items()}
     tot = {k: int(sum(i[k] for i in infos)) for k in ("hits1", "hits2", "samples", "n_ab", "n_1gap", "n_2gap", "launches")}
+    stages = {k: round(float(sum(i[k] for i in infos)), 3) for k in ("ms_lookup", "ms_enum", "ms_join", "ms_extract", "ms_aggregate")}
     tot["rules"] = [int(sum(i["rules"][k] for i in infos)) for k in range(3)]
     return {"workload": desc, "sentence_pairs": ns, "source_tokens": n_tokens, "source_vocabulary": src_max - 2, "queries": Q, "query_tokens": T,
             "value": Q / (dev_ms / 1e3), "unit": "query sentences/s", "device_ms_total": dev_ms,
@@ -374,7 +381,65 @@ def run_c3(args, device):
             "batches": len(infos), "batch_queries": BATCH_QUERIES, "largest_batch_queries": max(i["q1"] - i["q0"] for i in infos),
             "smallest_batch_queries": min(i["q1"] - i["q0"] for i in infos),
             "sa_build": {"gpu_ms": info["sa_build_ms"], "rounds": info["sa_rounds"], "key_bits": info["sa_key_bits"], "aux_index_ms": info["aux_build_ms"]},
-            "index_bytes": int(info["index_bytes"]), "index_wall_s": index_wall, "corpus_generation_s": gen_s, "totals": tot, "kernels": kern}
+            "index_bytes": int(info["index_bytes"]), "index_wall_s": index_wall, "corpus_generation_s": gen_s, "totals": tot, "stage_ms": stages,
+            "per_batch": [{k: i[k] for k in ("q0", "q1", "hits1", "hits2", "ms_total", "ms_join", "ms_extract", "ms_aggregate")} for i in infos], "kernels": kern}
+
+
+REFERENCE_SURVIVES = ("mid100k", 100_000, 60, 20_000)      # name, sentence pairs, queries, vocabulary
+
+
+def gpu_reference_block(device):
+    """The reference's own binary and host aggregation next to the product, same files, same B200 (see the module docstring)."""
+    import re
+    import shutil
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import ref_timers
+    from cgx_b200.extractor import GrammarExtractor
+    from cgx_b200.host import HostCorpus
+    name, ns, nq, v = REFERENCE_SURVIVES
+    work = tempfile.mkdtemp(prefix="cgx_gpuref_")
+    try:
+        r = ref_timers.run(name, ns, nq, v, keep_dir=work)
+        ref = r.get("reference", {})
+        out = {"config": "synthetic %d sentence pairs (V=%d), %d queries: the largest configuration the unmodified reference survives on this box "
+                         "(it faults in oneGapLookUpSA at the C1 stand-in and cannot hold a C2 batch in its 60 M-hit preallocation, ComTypes.h:56)" % (ns, v, nq),
+               "source_tokens": r.get("source_tokens"), "queries": r.get("queries"), "reference": ref}
+        cli = r.get("product_cli", {})
+        m = re.search(r"loading ([0-9.]+) s, index ([0-9.]+) s, match\+extract ([0-9.]+) s .*?grammar writing ([0-9.]+) s, total ([0-9.]+) s; (\d+) rules", cli.get("stderr_tail", ""))
+        prod = {"cli_wall_s": cli.get("wall_s"), "cli_rc": cli.get("rc")}
+        if m:
+            prod.update({"cli_loading_s": float(m.group(1)), "cli_index_s": float(m.group(2)), "cli_match_extract_s": float(m.group(3)),
+                         "cli_grammar_writing_s": float(m.group(4)), "cli_total_s": float(m.group(5)), "cli_rules": int(m.group(6))})
+            if float(m.group(4)) > 0:
+                prod["cli_writer_rules_per_s"] = int(m.group(6)) / float(m.group(4))
+        # the product's per-stage CUDA-event times on the same files (second batch: buffers warm)
+        hc = HostCorpus(*(os.path.join(work, "corpus." + e) for e in ("f", "q", "e", "a", "lex")))
+        lay = hc.layout()
+        ex = GrammarExtractor(device)
+        info = ex.build_index(lay)
+        ex.extract(lay["qry_tok"], lay["qry_off"], fetch=False)
+        b = ex.extract(lay["qry_tok"], lay["qry_off"], fetch=False)
+        ex.close()
+        prod.update({"sa_build_ms": info["sa_build_ms"], "aux_index_ms": info["aux_build_ms"]})
+        prod.update({k: b[k] for k in ("ms_total", "ms_lookup", "ms_enum", "ms_join", "ms_extract", "ms_aggregate", "hits1", "hits2", "samples", "rules")})
+        out["product"] = prod
+        if ref.get("completed"):
+            g = lambda *ks: sum(ref.get(k, 0.0) for k in ks)
+            pairs = {"sa_build": (g("sa_construction_cpu_s"), info["sa_build_ms"] / 1e3),
+                     "lookup": (g("lookup_kernels_s"), b["ms_lookup"] / 1e3),
+                     "enumerate+join (kernels, sorts, host scans)": (g("precomputation_s", "onegap_enumeration_s", "onegap_enumeration_sort_s", "onegap_enumeration_cpu_s",
+                                                                       "onegap_lookup_kernel_s", "onegap_lookup_sort_s", "onegap_lookup_cpu_s", "twogap_enumeration_s",
+                                                                       "twogap_enumeration_sort_s", "twogap_enumeration_cpu_s", "twogap_lookup_kernel_s", "twogap_lookup_sort_s",
+                                                                       "twogap_lookup_cpu_s"), (b["ms_enum"] + b["ms_join"]) / 1e3),
+                     "extract (kernels + result sorts)": (g("extract_contig_kernel_s", "extract_twogap_kernel_s", "extract_onegap_kernel_s", "extract_result_sorts_s"), b["ms_extract"] / 1e3),
+                     "aggregate + lexical scoring (ExtractPair.c createLexicon*Fast + lexical task)": (g("extractpair_c_total_s", "lexical_task_s"), b["ms_aggregate"] / 1e3)}
+            out["stages_reference_s_vs_product_s"] = {k: {"reference_s": a, "product_s": c, "ratio": (a / c if c > 0 else None)} for k, (a, c) in pairs.items()}
+            if ref.get("wall_s") and prod.get("cli_wall_s"):
+                out["cli_wall_ratio"] = ref["wall_s"] / prod["cli_wall_s"]
+        return out
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
 
 
 def bind_to_gpu_numa_node(local, rank):
@@ -601,6 +666,20 @@ def gpu_arm(args):
                 c3 = run_c3(args, local)
             except Exception as e:  # the second block never costs the first its line
                 c3 = {"error": repr(e)}
+        gpu_ref = None
+        if world == 1 and not args.no_gpu_reference:
+            if ex is not None:
+                ex.close()
+                ex = None
+            try:
+                gpu_ref = gpu_reference_block(local)
+                if cpu is not None and gpu_ref.get("reference", {}).get("extractpair_c"):
+                    cpu["reference_leg"] = {"kind": "reference", "what": "createLexiconFast / GappyFast / TwoGapFast of the reference's ExtractPair.c (:515,664,939), one thread, "
+                                            "on the rule records its own GPU kernels produced for " + gpu_ref["config"].split(":")[0],
+                                            "cores": 1, "records": gpu_ref["reference"].get("extractpair_c_records"), "seconds": gpu_ref["reference"].get("extractpair_c_total_s"),
+                                            "product_aggregate_ms_same_files": gpu_ref.get("product", {}).get("ms_aggregate")}
+            except Exception as e:  # a reported baseline, never a requirement
+                gpu_ref = {"error": repr(e)}
         out = {
             "metric": "query sentences/sec (grammar extraction)", "value": world * Q * args.steps / (dev_ms_max / 1e3), "unit": "query sentences/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
@@ -626,6 +705,7 @@ def gpu_arm(args):
             "index_bytes": int(info["index_bytes"]),
             "strong": strong,
             "c3": c3,
+            "gpu_reference": gpu_ref,
         }
         print(json.dumps(out), flush=True)
     if ex is not None:
@@ -645,11 +725,15 @@ def main():
     ap.add_argument("--cpu-queries-per-core", type=int, default=1, help="--impl reference: queries per process and step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c3", action="store_true", help="skip the second block (BASELINE.json configs[2]: 10 M sentence pairs, 100 k queries; N = 1 only)")
+    ap.add_argument("--only-c3", action="store_true", help="development: run the c3 block alone and print it")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the reference-binary block (stage timers of oracle/_ref/strmatchcuda_dump; N = 1 only)")
     ap.add_argument("--c3-queries", type=int, default=WORKLOADS["c3"][1], help="queries of the c3 block (default: all 100 k)")
     ap.add_argument("--strong-passes", type=int, default=2, help="timed passes over the fixed strong-scaling query set")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cgx_b200" else max(args.warmup, 0)
-    if args.impl == "reference":
+    if args.only_c3:                        # development: the second block alone
+        print(json.dumps(run_c3(args, 0)), flush=True)
+    elif args.impl == "reference":
         reference_arm(args)
     else:
         gpu_arm(args)

@@ -105,6 +105,8 @@ def load():
     L.cgx_profile_report.restype = C.c_char_p
     L.cgx_index_broadcast.argtypes = [C.POINTER(vp), C.c_int]
     L.cgx_batch_info.argtypes = [vp, C.POINTER(BatchInfo)]
+    L.cgx_batch_advice.argtypes = [vp, C.c_int32]
+    L.cgx_batch_advice.restype = C.c_int32
     L.cgx_result.argtypes = [vp, C.POINTER(Result)]
     L.cgx_debug_fetch.argtypes = [vp, C.c_char_p, i32p, C.c_int64]
     L.cgx_debug_fetch.restype = C.c_int64
@@ -116,4 +118,4 @@ def load():
 EXPORTED_SYMBOLS = ("cgx_version", "cgx_create", "cgx_destroy", "cgx_last_error", "cgx_index_build", "cgx_lex_load", "cgx_index_info",
                     "cgx_sa_build_dev", "cgx_index_export", "cgx_index_alloc", "cgx_index_commit", "cgx_index_save", "cgx_index_load", "cgx_index_copy_sa", "cgx_index_copy_inv",
                     "cgx_index_copy_frequent", "cgx_extract", "cgx_extract_begin", "cgx_result_at", "cgx_extract_dev", "cgx_profile_enable", "cgx_profile_report",
-                    "cgx_index_broadcast", "cgx_batch_info", "cgx_result", "cgx_debug_fetch", "cgx_debug_sort_u64")
+                    "cgx_index_broadcast", "cgx_batch_info", "cgx_batch_advice", "cgx_result", "cgx_debug_fetch", "cgx_debug_sort_u64")

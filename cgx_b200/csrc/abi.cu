@@ -116,6 +116,7 @@ static void build_index_device(cgx_ctx *c) {
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     c->ws.release();                                  // the build workspace (32 B/token) is not needed at query time
     ix.built = true;
+    c->batch.adv_refused_q = c->batch.adv_ok_q = 0;   // batch-size advice belongs to the corpus
 }
 
 extern "C" int cgx_index_build(cgx_ctx_t *c, const int32_t *src, int64_t n, const int32_t *tgt, int64_t m, const uint32_t *RLP,
@@ -257,6 +258,7 @@ extern "C" int cgx_index_commit(cgx_ctx_t *c) {
         build_lex_hash(c->ix, c->stream);          // derived from the (broadcast) sorted lexical arrays
         build_jwin(c->ix, c->stream);              // derived from the (broadcast) bucket arrays, gap words, text and alignment arrays
         c->ix.built = true;
+        c->batch.adv_refused_q = c->batch.adv_ok_q = 0;
     });
 }
 
@@ -395,11 +397,18 @@ static void run_batch(cgx_ctx *c, int32_t Q, int32_t T, bool fetch, bool wait_co
     stage_phrases(ix, b, s);
     stage_onegap_enumerate(ix, b, s);
     CUDA_CHECK(cudaEventRecord(b.ev[2], s));
-    stage_onegap_join(ix, b, s);
-    CUDA_CHECK(cudaEventRecord(b.ev[3], s));
-    stage_twogap_enumerate(ix, b, s);
-    CUDA_CHECK(cudaEventRecord(b.ev[4], s));
-    stage_twogap_join(ix, b, s);
+    try {
+        stage_onegap_join(ix, b, s);
+        CUDA_CHECK(cudaEventRecord(b.ev[3], s));
+        stage_twogap_enumerate(ix, b, s);
+        CUDA_CHECK(cudaEventRecord(b.ev[4], s));
+        stage_twogap_join(ix, b, s);
+    } catch (const CgxError &e) {
+        if (e.code == 3 && (b.adv_refused_q == 0 || Q < b.adv_refused_q)) b.adv_refused_q = Q;      // cgx_batch_advice
+        throw;
+    }
+    b.adv_ok_q = Q;
+    b.adv_ok_hits = (double)std::max(b.hits1, b.hits2);
     CUDA_CHECK(cudaEventRecord(b.ev[5], s));
     if (fetch) {   // the pattern tables and phrase ids are final here: they travel while extraction and aggregation run
         int32_t *hp = b.h_phrase_id.get<int32_t>((size_t)T * CGX_LONGEST_SRC + 1);
@@ -548,6 +557,18 @@ extern "C" int cgx_batch_info(const cgx_ctx_t *c, cgx_batch_info_t *out) {
     return 0;
 }
 
+extern "C" int32_t cgx_batch_advice(const cgx_ctx_t *c, int32_t wanted) {
+    if (!c || wanted <= 1) return wanted;
+    const Batch &b = c->batch;
+    if (b.adv_refused_q == 0 || wanted < b.adv_refused_q) return wanted;       // nothing of this size has been refused yet
+    // Hits grow sublinearly with the batch (queries share patterns), so scaling the last finished batch linearly up to 90 % of
+    // the limit over-estimates: that size is safe.  Never less than half of the smallest refused batch -- the classic split.
+    double fit = (double)(b.adv_refused_q / 2);
+    if (b.adv_ok_q > 0 && b.adv_ok_hits > 0.0) fit = std::max(fit, (double)b.adv_ok_q * 0.9 * (double)hit_limit() / b.adv_ok_hits);
+    fit = std::min(fit, (double)(b.adv_refused_q - 1));
+    return fit < 1.0 ? 1 : (fit >= (double)wanted ? wanted : (int32_t)fit);
+}
+
 extern "C" int cgx_result_at(cgx_ctx_t *c, int age, cgx_result_t *o) {
     CGX_TRY(c, {
         CGX_REQUIRE(c && o && age >= 0 && age < CGX_RESULT_SETS, "bad argument (age must be 0..%d)", CGX_RESULT_SETS - 1);
@@ -632,7 +653,7 @@ extern "C" int64_t cgx_debug_fetch(cgx_ctx_t *c, const char *what, int32_t *out,
             if (H) CUDA_CHECK(cudaMemcpy(h.data(), two ? b.hits2_sorted.p : b.hits1_sorted.p, sizeof(uint64_t) * H, cudaMemcpyDeviceToHost));
             for (size_t i = 0; i < H; i++) {
                 const uint64_t pm = (1ull << b.pbits) - 1;
-                if (two) { out[4 * i] = (int32_t)(h[i] >> (b.pbits + 8)); out[4 * i + 1] = (int32_t)((h[i] >> 8) & pm); out[4 * i + 2] = (int32_t)((h[i] >> 4) & 15); out[4 * i + 3] = (int32_t)(h[i] & 15); }
+                if (two) { out[4 * i] = (int32_t)(h[i] >> (b.pbits + 8)); out[4 * i + 1] = (int32_t)((h[i] >> 8) & pm); out[4 * i + 2] = (int32_t)(h[i] & 15); out[4 * i + 3] = (int32_t)((h[i] & 15) + 1 + ((h[i] >> 4) & 15)); }
                 else { out[3 * i] = (int32_t)(h[i] >> (b.pbits + 4)); out[3 * i + 1] = (int32_t)((h[i] >> 4) & pm); out[3 * i + 2] = (int32_t)(h[i] & 15); }
             }
             return (int64_t)(H * cols);

@@ -75,8 +75,11 @@ struct Batch {
     int64_t hits1 = 0, hits2 = 0, j1_elems = 0;
     int pbits = 30;                        // position field width of the packed hit keys (bits needed for n)
     size_t hit_cap = 0;
+    int32_t adv_refused_q = 0, adv_ok_q = 0;   // cgx_batch_advice: smallest batch refused so far, size and hits of the last finished one
+    double adv_ok_hits = 0.0;
+    uint32_t j1_buckets = 0;              // buckets of the last one-gap pattern table (kept when a batch had to grow it)
     bool j1_smem_opt_in = false;          // j1_pos_ordered_kernel's dynamic shared memory opted in on this device
-    DevBuf hits1_sorted, hits2_sorted;     // uint64 keys: pattern << (pbits+4) | pos << 4 | len-1  /  pattern << (pbits+8) | pos << 8 | L << 4 | c-pos
+    DevBuf hits1_sorted, hits2_sorted;     // uint64 keys: pattern << (pbits+4) | pos << 4 | len-1  /  pattern << (pbits+8) | pos << 8 | g2 << 4 | L  (g2 = width of the second gap: c at pos+L+1+g2)
     // two-gap enumeration
     DevBuf e2_count, e2_keys, e2_keys_tmp, e2_vals, e2_vals_tmp, e2_flags, pat2;
     int32_t enu2 = 0, D2 = 0;
@@ -145,6 +148,14 @@ static inline void rotate_results(Batch &b) {
     swap_results(b, b.parked[0]);          // current = old parked[0], parked[0] = the batch that just finished
     swap_results(b, b.parked[1]);          // current = old parked[1], parked[1] = old parked[0]
     if (b.done_ev) CUDA_CHECK(cudaEventSynchronize(b.done_ev));
+}
+
+// hits per batch and kind: hit_start / hit_count of the pattern tables are int32.  CGX_HIT_LIMIT lowers it (tests of the
+// callers' batch splitting).
+static inline unsigned long long hit_limit() {
+    unsigned long long lim = (1ull << 31) - 1;
+    if (const char *e = getenv("CGX_HIT_LIMIT")) { unsigned long long v = strtoull(e, nullptr, 10); if (v && v < lim) lim = v; }
+    return lim;
 }
 
 // stages (each enqueues on `stream`; those that need a count on the host synchronise once)

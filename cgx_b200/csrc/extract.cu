@@ -34,24 +34,32 @@
 namespace cgx {
 
 // xw[k] = RLP[k] | 1 for a word (token >= 2), 0 at EOS / padding: the extension loops test "is a word" and read its aligned
-// span with ONE load (the reference reads str[k], then RLP[k]: two dependent random sectors); lr[j] = {L_tar[j], R_tar[j]}.
+// span with ONE load (the reference reads str[k], then RLP[k]: two dependent random sectors); lrq[j] = range-minimum table over {L_tar, R_tar} (index.cu).
 // RLP itself is only read for the target offset stored at the previous EOS.
 struct ExtractIdx {
     const int32_t *sa;
     const uint32_t *xw, *RLP;
-    const uchar2 *lr;
+    const uint2 *lrq;
     int n;
 };
 
-// ExtractPair.cu:103-133 consistent
+// ExtractPair.cu:103-133 consistent: min L_tar / max R_tar over the target window [start, end] (unaligned tokens skipped) must
+// be exactly the source span [start_chk, end_chk].  The window is the union of two entries of the range-minimum table lrq
+// (index.cu): two independent 8-byte loads.  Callers never pass more than CGX_MAX_RULE_SPAN tokens; longer windows take the loop.
+__device__ __forceinline__ unsigned lrq_level(uint2 v, int k) { return ((k & 2) ? v.y : v.x) >> (16 * (k & 1)); }
 __device__ __forceinline__ bool consistent(const ExtractIdx &x, int start, int end, int start_chk, int end_chk, int startpos_source) {
     unsigned mn = 255, mx = 0;
-    for (int k = start; k <= end; k++) {
-        const uchar2 v = __ldg(&x.lr[k]);
-        const unsigned L = v.x, R = v.y;
-        if (L == 255 || R == 255) continue;
-        mn = min(mn, L);
-        mx = max(mx, R);
+    const int len = end - start + 1;
+    if (len > 0) {
+        const int k = min(3, 31 - __clz(len)), step = 1 << k;
+        const uint2 a = __ldg(&x.lrq[start]), b = __ldg(&x.lrq[end - step + 1]);
+        const unsigned wa = lrq_level(a, k), wb = lrq_level(b, k);
+        mn = min(wa & 0xFFu, wb & 0xFFu);
+        mx = max((wa >> 8) & 0xFFu, (wb >> 8) & 0xFFu);
+        for (int j = start + step; j <= end - step; j += step) {                     // runs only when len > 15
+            const unsigned w = lrq_level(__ldg(&x.lrq[j]), k);
+            mn = min(mn, w & 0xFFu); mx = max(mx, (w >> 8) & 0xFFu);
+        }
     }
     return !(startpos_source + (int)mn != start_chk || startpos_source + (int)mx != end_chk);
 }
@@ -415,7 +423,7 @@ __global__ void __launch_bounds__(128) extract_twogap_kernel(ExtractIdx x, const
     const int occ = sample_index((int)(slot - slot_off[d]), p2.hit_count, CGX_SAMPLER_TWOGAP, 1.0f / (float)CGX_SAMPLER_TWOGAP);
     if (occ < 0) return;
     const uint64_t hk = hits2[(size_t)p2.hit_start + occ];
-    const int current_str = (int)((hk >> 8) & ((1ull << pbits) - 1)), firstEnd = (int)((hk >> 4) & 15), secondEnd = (int)(hk & 15);
+    const int current_str = (int)((hk >> 8) & ((1ull << pbits) - 1)), firstEnd = (int)(hk & 15), secondEnd = firstEnd + 1 + (int)((hk >> 4) & 15);   // key: width of the second gap, then length
     const Pat1 p1 = pat1[p2.pat1];
     unsigned mnL, mxR;
     int stb, ti;
@@ -436,7 +444,7 @@ void stage_extract(const Index &ix, Batch &b, cudaStream_t stream) {
     b.n_slots[0] = b.n_slots[1] = b.n_slots[2] = 0;
     b.samples = 0;
     if (G == 0) return;
-    ExtractIdx x{ix.sa.ptr<int32_t>(), ix.xw.ptr<uint32_t>(), ix.RLP.ptr<uint32_t>(), ix.lr.ptr<uchar2>(), (int)ix.n};
+    ExtractIdx x{ix.sa.ptr<int32_t>(), ix.xw.ptr<uint32_t>(), ix.RLP.ptr<uint32_t>(), ix.lr.ptr<uint2>(), (int)ix.n};
     uint32_t *tot = b.counters.get<uint32_t>(32);
     // slot offsets: G+1 / D1+1 / D2+1 entries (the last one = total), also read by the aggregation
     uint32_t *so0 = b.slot_off[0].get<uint32_t>((size_t)G + 2);

@@ -99,12 +99,30 @@ __global__ void ix_jwin_kernel(const int32_t *__restrict__ b1, const int32_t *__
 }
 
 // extraction views: xw[k] = RLP[k] | 1 where the source token is a word (>= 2), else 0 (EOS, padding; n+3 entries like str);
-// lr[j] = {L_tar[j], R_tar[j]}.  The window loops of extract.cu then touch one array per side instead of two.
+// lrq[j] = range-minimum table of the target side for consistent() (ExtractPair.cu:103-133), which needs min L_tar / max R_tar
+// over a target window of at most 15 tokens, unaligned tokens skipped: level k (bits 16k..16k+15) holds {min L, max R} over
+// tokens j .. j+2^k-1, k = 0..3, with an unaligned token entered as {255, 0} (the identities of min and max).  Any window is
+// the union of two level-floor(log2 len) entries: two independent 8-byte loads instead of a loop of <= 15 dependent 2-byte ones.
 __global__ void ix_extract_views_kernel(const int32_t *__restrict__ str, const uint32_t *__restrict__ RLP, size_t n, const uint8_t *__restrict__ L_tar,
-                                        const uint8_t *__restrict__ R_tar, size_t m, uint32_t *__restrict__ xw, uchar2 *__restrict__ lr) {
+                                        const uint8_t *__restrict__ R_tar, size_t m, uint32_t *__restrict__ xw, uint2 *__restrict__ lrq) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n + 3) xw[i] = (i < n && str[i] >= 2) ? (RLP[i] | 1u) : 0u;
-    if (i < m) lr[i] = make_uchar2(L_tar[i], R_tar[i]);
+    if (i < m) {
+        unsigned mn = 255, mx = 0;
+        uint32_t w[2] = {0, 0};
+        int t = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            for (; t < (1 << k); t++) {
+                if (i + t >= m) continue;
+                const unsigned L = L_tar[i + t], R = R_tar[i + t];
+                if (L == 255 || R == 255) continue;
+                mn = min(mn, L); mx = max(mx, R);
+            }
+            w[k >> 1] |= (mn | (mx << 8)) << (16 * (k & 1));
+        }
+        lrq[i] = make_uint2(w[0], w[1]);
+    }
 }
 
 void build_jwin(Index &ix, cudaStream_t stream) {
@@ -112,7 +130,7 @@ void build_jwin(Index &ix, cudaStream_t stream) {
                                                             ix.gapw.ptr<uint32_t>(), ix.n, ix.jwin.get<int4>(ix.n));
     const size_t cnt = ix.n + 3 > ix.m ? ix.n + 3 : ix.m;
     ix_extract_views_kernel<<<cgx_div_up(cnt, 256), 256, 0, stream>>>(ix.str.ptr<int32_t>(), ix.RLP.ptr<uint32_t>(), ix.n, ix.L_tar.ptr<uint8_t>(),
-                                                                     ix.R_tar.ptr<uint8_t>(), ix.m, ix.xw.get<uint32_t>(ix.n + 3), ix.lr.get<uchar2>(ix.m));
+                                                                     ix.R_tar.ptr<uint8_t>(), ix.m, ix.xw.get<uint32_t>(ix.n + 3), ix.lr.get<uint2>(ix.m));
     CUDA_CHECK(cudaStreamSynchronize(stream));
 }
 

@@ -40,7 +40,7 @@ void build_suffix_array(const int32_t *d_str, size_t n, int32_t maxtok, int32_t 
 //   jwin    int4  [n]     {bkt[1], bkt[2], bkt[3], gapw} of every position interleaved: the position-major join streams it once
 //                         through shared memory (derived locally from bkt[] and gapw, like lex_hash)
 //   xw      uint32 [n+3]  extraction view of the source side: RLP | 1 where the token is a word (>= 2), 0 at EOS / padding
-//   lr      uchar2 [m]    {L_tar, R_tar} interleaved (both derived locally, like jwin)
+//   lr      uint2 [m]     range-minimum table {min L_tar, max R_tar} over 1/2/4/8 target tokens (index.cu; derived locally, like jwin)
 //   tok_start int32 [maxtok+2]  SA bucket start of every token id (1-gram intervals in O(1))
 //   RLP     uint32 [n]    (L<<24)|(R<<16)|(P<<8) per source token; target sentence offset at EOS
 //   L_tar/R_tar uint8 [m] min/max aligned source index per target token (255 = unaligned)

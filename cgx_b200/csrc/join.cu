@@ -38,8 +38,10 @@
 
 namespace cgx {
 
-__device__ __forceinline__ uint64_t key1_of(uint32_t phrase_a, int le, uint32_t bucket_b) {
-    return ((uint64_t)phrase_a << 32) | ((uint64_t)le << 30) | (uint64_t)bucket_b;
+// key of a one-gap pattern in the per-batch table: (first phrase id, length of the second phrase, its canonical m-gram id),
+// packed into bits_for(G) + 2 + pbits bits (pbits = bits of a corpus position)
+__device__ __forceinline__ uint64_t key1_of(uint32_t phrase_a, int le, uint32_t bucket_b, int pbits) {
+    return ((((uint64_t)phrase_a << 2) | (uint64_t)le) << pbits) | (uint64_t)bucket_b;
 }
 
 // Hits are staged per warp in shared memory and flushed with ONE global atomic per ~200 hits (a single counter
@@ -74,7 +76,7 @@ __device__ __forceinline__ bool bit_test(const uint32_t *__restrict__ bm, uint32
 // aflag[g]: bit 0 = phrase g is the first phrase of some pattern; bit 1 = it is a single top-100 token (only then
 // can a pattern be a "marker pair" of the reference's frequent-pair table)
 __global__ void j1_setup_kernel(const Pat1 *__restrict__ pat, const Pat1Dev *__restrict__ patd, const int32_t *__restrict__ pat_ga, int D1,
-                                const int32_t *__restrict__ str, const uint8_t *__restrict__ freq_rank, ulonglong2 *__restrict__ slots, uint32_t mask,
+                                const int32_t *__restrict__ str, const uint8_t *__restrict__ freq_rank, const QTab tab, int pbits, uint32_t *__restrict__ overflow,
                                 uint32_t *__restrict__ bm1, uint32_t *__restrict__ bm2, uint32_t *__restrict__ bm3, uint32_t *__restrict__ bm_marker,
                                 uint32_t *__restrict__ aflag, uint32_t *__restrict__ bma, size_t bm_words, uint32_t *__restrict__ aid, size_t n) {
     int d = blockIdx.x * blockDim.x + threadIdx.x;
@@ -82,7 +84,7 @@ __global__ void j1_setup_kernel(const Pat1 *__restrict__ pat, const Pat1Dev *__r
     const Pat1 p = pat[d];
     const uint32_t ub = (uint32_t)patd[d].up_b;
     const uint32_t ga = (uint32_t)pat_ga[d];
-    ht_insert(slots, mask, key1_of(ga, p.le, ub), (uint32_t)d | (p.marker_pair >= 0 ? 0x80000000u : 0u));
+    if (!qt_insert(tab, key1_of(ga, p.le, ub, pbits), ((uint64_t)d << 1) | (p.marker_pair >= 0 ? 1u : 0u))) *overflow = 1u;   // value: pattern id, marker-pair flag
     uint32_t *bm = p.le == 1 ? bm1 : p.le == 2 ? bm2 : bm3;
     atomicOr(&bm[ub >> 5], 1u << (ub & 31));
     if (p.marker_pair >= 0) atomicOr(&bm_marker[ub >> 5], 1u << (ub & 31));
@@ -125,9 +127,8 @@ struct J1Args {
     const uint32_t *gapw;
     const uint32_t *bm[3];
     const uint32_t *bm_marker;
-    const ulonglong2 *slots;
-    uint32_t mask;
-    int pshift;                      // hit key = pattern << pshift | position << 4 | (length-1)
+    QTab tab;
+    int pshift;                      // hit key = pattern << pshift | position << 4 | (length-1); pshift - 4 = bits of a position
     uint32_t n;
     unsigned long long *counter;     // [0] hits, [1] bucket words read (algorithmic-byte account)
     uint64_t *hits;
@@ -180,21 +181,21 @@ __global__ void __launch_bounds__(J1_BLOCK) j1_scan_kernel(const J1Args a) {
 #pragma unroll
         for (int le = 1; le <= 3; le++)
             if (cand[le - 1]) cand[le - 1] = bit_test((le == 1 && miss) ? a.bm_marker : a.bm[le - 1], ub[le - 1]);
-        ulonglong2 sv[3];
         uint32_t ss[3];
+        uint64_t sw[3];
 #pragma unroll
         for (int le = 1; le <= 3; le++)
-            if (cand[le - 1]) sv[le - 1] = ht_first(a.slots, a.mask, key1_of((uint32_t)ga, le, ub[le - 1]), &ss[le - 1]);
+            if (cand[le - 1]) qt_touch(a.tab, key1_of((uint32_t)ga, le, ub[le - 1], a.pshift - 4), &ss[le - 1], &sw[le - 1]);
 #pragma unroll
         for (int le = 1; le <= 3; le++) {
             if (!__any_sync(0xffffffffu, cand[le - 1])) continue;          // warp-uniform
             uint64_t v = 0;
-            bool found = cand[le - 1] && ht_resolve(a.slots, a.mask, key1_of((uint32_t)ga, le, ub[le - 1]), ss[le - 1], sv[le - 1], &v);
+            bool found = cand[le - 1] && qt_resolve(a.tab, ss[le - 1], sw[le - 1], &v);
             if (found && miss) {                                           // only le == 1 reaches here with miss set
-                if (v & 0x80000000u) atomicAdd(&a.missing[v & 0x7fffffffu], 1);
+                if (v & 1u) atomicAdd(&a.missing[v >> 1], 1);
                 found = false;
             }
-            const uint64_t key = ((uint64_t)(v & 0x7fffffffu) << a.pshift) | ((uint64_t)(uint32_t)p << 4) | (uint64_t)(ls + g + le - 1);
+            const uint64_t key = ((v >> 1) << a.pshift) | ((uint64_t)(uint32_t)p << 4) | (uint64_t)(ls + g + le - 1);
             stage_push(found, key, stage, staged);
         }
         if (staged > ST_CAP - 96) stage_flush(stage, staged, &a.counter[0], a.hits, a.cap);
@@ -227,8 +228,7 @@ struct JPArgs {
     const uint32_t *aid[3];          // bucket -> phrase id | frequent-single-token flag << 31
     const uint32_t *bm[3];
     const uint32_t *bm_marker;
-    const ulonglong2 *slots;
-    uint32_t mask;
+    QTab tab;
     int pshift;
     unsigned long long *counter;     // [0] hits, [1] table lookups, [2] elements
     uint64_t *hits;
@@ -297,21 +297,21 @@ __global__ void __launch_bounds__(JP_TILE) j1_pos_kernel(const JPArgs a) {
 #pragma unroll
             for (int le = 1; le <= 3; le++)
                 if (cand[le - 1]) cand[le - 1] = bit_test((le == 1 && miss) ? a.bm_marker : a.bm[le - 1], ub[le - 1]);
-            ulonglong2 sv[3];
-            uint32_t ss[3];
+                uint32_t ss[3];
+            uint64_t sw[3];
 #pragma unroll
             for (int le = 1; le <= 3; le++)
-                if (cand[le - 1]) { sv[le - 1] = ht_first(a.slots, a.mask, key1_of(ga, le, ub[le - 1]), &ss[le - 1]); lookups++; }
+                if (cand[le - 1]) { qt_touch(a.tab, key1_of(ga, le, ub[le - 1], a.pshift - 4), &ss[le - 1], &sw[le - 1]); lookups++; }
 #pragma unroll
             for (int le = 1; le <= 3; le++) {
                 if (!__any_sync(0xffffffffu, cand[le - 1])) continue;
                 uint64_t v = 0;
-                bool found = cand[le - 1] && ht_resolve(a.slots, a.mask, key1_of(ga, le, ub[le - 1]), ss[le - 1], sv[le - 1], &v);
+                bool found = cand[le - 1] && qt_resolve(a.tab, ss[le - 1], sw[le - 1], &v);
                 if (found && miss) {
-                    if (v & 0x80000000u) atomicAdd(&a.missing[v & 0x7fffffffu], 1);
+                    if (v & 1u) atomicAdd(&a.missing[v >> 1], 1);
                     found = false;
                 }
-                const uint64_t key = ((uint64_t)(v & 0x7fffffffu) << a.pshift) | ((uint64_t)(uint32_t)p << 4) | (uint64_t)(ls + g + le - 1);
+                const uint64_t key = ((v >> 1) << a.pshift) | ((uint64_t)(uint32_t)p << 4) | (uint64_t)(ls + g + le - 1);
                 stage_push(found, key, stage, staged);
             }
             if (staged > ST_CAP - 96) stage_flush(stage, staged, &a.counter[0], a.hits, a.cap);
@@ -388,24 +388,24 @@ __device__ __forceinline__ unsigned jo_walk(const JPArgs &a, const int4 *__restr
 #pragma unroll
             for (int le = 1; le <= 3; le++)
                 if (cand[le - 1]) cand[le - 1] = bit_test((le == 1 && miss) ? a.bm_marker : a.bm[le - 1], ub[le - 1]);
-            ulonglong2 sv[3];
-            uint32_t ss[3];
+                uint32_t ss[3];
+            uint64_t sw[3];
 #pragma unroll
             for (int le = 1; le <= 3; le++)
-                if (cand[le - 1]) { sv[le - 1] = ht_first(a.slots, a.mask, key1_of(ga, le, ub[le - 1]), &ss[le - 1]); if (!DIRECT) lookups++; }
+                if (cand[le - 1]) { qt_touch(a.tab, key1_of(ga, le, ub[le - 1], a.pshift - 4), &ss[le - 1], &sw[le - 1]); if (!DIRECT) lookups++; }
 #pragma unroll
             for (int le = 1; le <= 3; le++) {
                 if (!__any_sync(0xffffffffu, cand[le - 1])) continue;
                 uint64_t v = 0;
-                bool found = cand[le - 1] && ht_resolve(a.slots, a.mask, key1_of(ga, le, ub[le - 1]), ss[le - 1], sv[le - 1], &v);
+                bool found = cand[le - 1] && qt_resolve(a.tab, ss[le - 1], sw[le - 1], &v);
                 if (found && miss) {
-                    if (v & 0x80000000u) atomicAdd(&a.missing[v & 0x7fffffffu], 1);
+                    if (v & 1u) atomicAdd(&a.missing[v >> 1], 1);
                     found = false;
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, found);
                 if (found) {
                     const unsigned idx = count + __popc(m & lanemask_lt());
-                    const uint32_t pat = (uint32_t)(v & 0x7fffffffu);
+                    const uint32_t pat = (uint32_t)(v >> 1);
                     const int len = ls + g + le - 1;
                     if (DIRECT) {
                         const unsigned long long o = out_base + idx;
@@ -516,14 +516,6 @@ __global__ void j1_missing_kernel(Pat1 *__restrict__ pat, const int32_t *__restr
     if (d < D1) pat[d].fs_extra = missing[d];
 }
 
-// hits per batch and kind: hit_start / hit_count of the pattern tables are int32.  CGX_HIT_LIMIT lowers it (tests of the
-// caller's batch splitting).
-static unsigned long long hit_limit() {
-    unsigned long long lim = (1ull << 31) - 1;
-    if (const char *e = getenv("CGX_HIT_LIMIT")) { unsigned long long v = strtoull(e, nullptr, 10); if (v && v < lim) lim = v; }
-    return lim;
-}
-
 static void read_u64s(unsigned long long *dst, const unsigned long long *d, int count, cudaStream_t stream) {
     cgx_read_back(dst, d, sizeof(unsigned long long) * count, stream);
 }
@@ -543,27 +535,44 @@ void stage_onegap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     uint32_t *aid = b.j_aid.get<uint32_t>(3 * ix.n);                   // bucket -> first-phrase id, valid where the first-phrase bit is set
     uint32_t *aflag = b.j_aflag.get<uint32_t>((size_t)G + 1);
     uint32_t *eoff = b.j_tiles.get<uint32_t>((size_t)G + 2);
-    const uint32_t slots_n = ht_slots_for((size_t)D1);
-    ulonglong2 *slots = b.j_hash.get<ulonglong2>(slots_n);
+    // per-batch pattern table (hash.cuh QTab): key = (first phrase id, le, m-gram id of the second phrase), value = pattern id, marker flag
+    const int kbits_raw = cgx_bits_for((uint64_t)G) + 2 + b.pbits, vbits = cgx_bits_for((uint64_t)D1) + 1;
+    uint32_t buckets = qt_buckets_for((size_t)D1);
+    if (b.j1_buckets > buckets && b.j1_buckets <= 4 * buckets) buckets = b.j1_buckets;       // an earlier batch of this size needed more room
     uint32_t *tot = b.counters.get<uint32_t>(32);
     unsigned long long *ctr = (unsigned long long *)(tot + 4);         // [0] hits [1] bucket words read
-    CUDA_CHECK(cudaMemsetAsync(bm, 0, sizeof(uint32_t) * 7 * bm_words, stream));
-    CUDA_CHECK(cudaMemsetAsync(aflag, 0, sizeof(uint32_t) * ((size_t)G + 1), stream));
-    CUDA_CHECK(cudaMemsetAsync(slots, 0xff, sizeof(ulonglong2) * (size_t)slots_n, stream));
-        PROF("join_setup", (double)D1 * (32 + 16 + 4 + 16), (j1_setup_kernel<<<cgx_div_up(D1, 256), 256, 0, stream>>>(b.pat1.ptr<Pat1>(), b.pat1_dev.ptr<Pat1Dev>(), b.pat1_ga.ptr<int32_t>(), D1, ix.str.ptr<int32_t>(),
-                                                                ix.freq_flag.ptr<uint8_t>(), slots, slots_n - 1, bm, bm + bm_words, bm + 2 * bm_words, bm + 3 * bm_words, aflag,
-                                                                bm + 4 * bm_words, bm_words, aid, ix.n)));
-    j1_counts_kernel<<<cgx_div_up(G, 256), 256, 0, stream>>>(b.phrases.ptr<int32_t>(), aflag, G, eoff);
-    exclusive_scan_u32(eoff, eoff, (size_t)G, tot, stream, b.scan, 0, &b.launches);
-    b.launches += 2;
+    QTab tab;
     uint32_t n_elems = 0;
-    cgx_read_back(&n_elems, tot, sizeof(uint32_t), stream);
+    while (true) {
+        const int lb = qt_log2(buckets);
+        tab.kb = std::max(kbits_raw, lb + 8);                                                  // at least 8 remainder bits
+        tab.rb = tab.kb - lb; tab.vbits = vbits; tab.bmask = buckets - 1;
+        CGX_REQUIRE_BATCH(tab.rb + 3 + vbits <= 63, "%d one-gap patterns over %d phrases do not fit the packed pattern table", D1, G);
+        tab.slots = b.j_hash.get<unsigned long long>((size_t)buckets * 4);
+        CUDA_CHECK(cudaMemsetAsync(bm, 0, sizeof(uint32_t) * 7 * bm_words, stream));
+        CUDA_CHECK(cudaMemsetAsync(aflag, 0, sizeof(uint32_t) * ((size_t)G + 1), stream));
+        CUDA_CHECK(cudaMemsetAsync(tab.slots, 0xff, sizeof(unsigned long long) * (size_t)buckets * 4, stream));
+        CUDA_CHECK(cudaMemsetAsync(tot + 1, 0, sizeof(uint32_t), stream));
+        PROF("join_setup", (double)D1 * (32 + 16 + 4 + 8), (j1_setup_kernel<<<cgx_div_up(D1, 256), 256, 0, stream>>>(b.pat1.ptr<Pat1>(), b.pat1_dev.ptr<Pat1Dev>(), b.pat1_ga.ptr<int32_t>(), D1, ix.str.ptr<int32_t>(),
+                                                                ix.freq_flag.ptr<uint8_t>(), tab, b.pbits, tot + 1, bm, bm + bm_words, bm + 2 * bm_words, bm + 3 * bm_words, aflag,
+                                                                bm + 4 * bm_words, bm_words, aid, ix.n)));
+        j1_counts_kernel<<<cgx_div_up(G, 256), 256, 0, stream>>>(b.phrases.ptr<int32_t>(), aflag, G, eoff);
+        exclusive_scan_u32(eoff, eoff, (size_t)G, tot, stream, b.scan, 0, &b.launches);
+        b.launches += 2;
+        uint32_t back[2] = {0, 0};                                                             // [0] elements, [1] an insert found no room
+        cgx_read_back(back, tot, sizeof(back), stream);
+        n_elems = back[0];
+        if (!back[1]) break;
+        buckets *= 2;                                                                          // (a cluster of full buckets: rare at <= 3 entries per bucket)
+        CGX_REQUIRE(buckets <= (1u << 28), "one-gap pattern table does not settle");
+    }
+    b.j1_buckets = buckets;
     int32_t *missing = b.missing.get<int32_t>((size_t)D1);
     if (b.hit_cap == 0) b.hit_cap = 1u << 22;
     J1Args a;
     a.phrases = b.phrases.ptr<int32_t>(); a.aflag = aflag; a.elem_off = eoff; a.G = G; a.n_elems = n_elems;
     for (int k = 0; k < 3; k++) { a.inv[k] = ix.inv[k].ptr<int32_t>(); a.bkt[k] = ix.bkt[k].ptr<int32_t>(); a.bm[k] = bm + (size_t)k * bm_words; }
-    a.gapw = ix.gapw.ptr<uint32_t>(); a.bm_marker = bm + 3 * bm_words; a.slots = slots; a.mask = slots_n - 1;
+    a.gapw = ix.gapw.ptr<uint32_t>(); a.bm_marker = bm + 3 * bm_words; a.tab = tab;
     a.pshift = b.pbits + 4; a.n = (uint32_t)ix.n; a.counter = ctr; a.missing = missing;
     // variant: stream the whole corpus once (position-major) when the first phrases cover a good part of it, else walk
     // the occurrence lists (phrase-major).  CGX_JOIN_MODE=phrase|position forces one (tests exercise both).
@@ -572,7 +581,7 @@ void stage_onegap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     JPArgs ap;
     ap.jwin = ix.jwin.ptr<int4>(); ap.n = (uint32_t)ix.n;
     for (int k = 0; k < 3; k++) { ap.bma[k] = bm + (size_t)(4 + k) * bm_words; ap.aid[k] = aid + (size_t)k * ix.n; ap.bm[k] = bm + (size_t)k * bm_words; }
-    ap.bm_marker = bm + 3 * bm_words; ap.slots = slots; ap.mask = slots_n - 1; ap.pshift = b.pbits + 4; ap.counter = ctr; ap.missing = missing;
+    ap.bm_marker = bm + 3 * bm_words; ap.tab = tab; ap.pshift = b.pbits + 4; ap.counter = ctr; ap.missing = missing;
     unsigned long long host_ctr[3] = {0, 0, 0};
     // position-major scans emit in position order (tile segments + ordered copy): the sort below then covers the pattern bits only.
     // CGX_JOIN_ORDERED=0 keeps round 1's unordered append + full (pattern, position) sort for that variant too.
@@ -609,8 +618,8 @@ void stage_onegap_join(const Index &ix, Batch &b, cudaStream_t stream) {
         b.hit_cap = (size_t)host_ctr[0] + (size_t)host_ctr[0] / 8 + 1024;        // grow once to the exact need and redo the scan
     }
     // algorithmic bytes.  phrase-major: per element its position + gap word, every bucket word read, every hit
-    // written; position-major: the window array streamed once, the phrase id per element, one 16-byte slot per table lookup, hits
-    if (position_major) prof_add_bytes("join_onegap", 16.0 * (double)ix.n + 4.0 * (double)host_ctr[2] + 16.0 * (double)host_ctr[1] + 8.0 * (double)host_ctr[0]);
+    // written; position-major: the window array streamed once, the phrase id per element, one 8-byte slot per table lookup, hits
+    if (position_major) prof_add_bytes("join_onegap", 16.0 * (double)ix.n + 4.0 * (double)host_ctr[2] + 8.0 * (double)host_ctr[1] + 8.0 * (double)host_ctr[0]);
     else prof_add_bytes("join_onegap", 8.0 * (double)n_elems + 4.0 * (double)host_ctr[1] + 8.0 * (double)host_ctr[0]);
     b.j1_elems = (int64_t)n_elems;
     j1_missing_kernel<<<cgx_div_up(D1, 256), 256, 0, stream>>>(b.pat1.ptr<Pat1>(), missing, D1);
@@ -701,7 +710,7 @@ __global__ void __launch_bounds__(256) j2_scan_kernel(const uint64_t *__restrict
             if (!__any_sync(0xffffffffu, rr[u] != 0)) continue;
             uint64_t d2 = 0;
             const bool found = rr[u] && pt_resolve(tab, ((uint64_t)d1 << cbits) | (uint64_t)cc[u], ss[u], sv[u], &d2);
-            const uint64_t key = (d2 << (pbits + 8)) | ((uint64_t)(uint32_t)p << 8) | ((uint64_t)L << 4) | (uint64_t)(rr[u] - p);
+            const uint64_t key = (d2 << (pbits + 8)) | ((uint64_t)(uint32_t)p << 8) | ((uint64_t)(rr[u] - p - L - 1) << 4) | (uint64_t)L;   // (pattern, position, width, length)
             stage_push(found, key, stage, staged);
         }
         if (staged > ST_CAP - 128) stage_flush(stage, staged, &counter[0], hits, cap);
@@ -712,31 +721,47 @@ __global__ void __launch_bounds__(256) j2_scan_kernel(const uint64_t *__restrict
 }
 
 
-// Ordered form of j2_scan_kernel: thread k of a tile owns parent hit k of the (pattern, position, length)-sorted one-gap list; its
-// (up to 13) two-gap hits are parked in shared memory in ascending width, the tile takes one segment of the output with a single
-// atomicAdd (as above), and every thread writes its hits at segment start + (hits of the threads before it).  After the segments
-// are copied into tile order the list is in (parent pattern, position, length, width) order; a pattern aXbXc has ONE parent, so a
-// stable sort on the two-gap pattern bits alone yields (pattern, position, length, width) order: three passes instead of seven
-// (eight at C3).
+// Ordered form of j2_scan_kernel: a thread owns one parent hit of the (pattern, position, length)-sorted one-gap list; its (up
+// to 13) two-gap hits are parked in shared memory by ascending width, the tile takes one segment of the output with a single
+// atomicAdd (as above), and the hits are written in (parent pattern, position, WIDTH, LENGTH) order: the parents of one
+// (pattern, position) -- a "run" of at most 13 adjacent threads, ascending length -- interleave their hits width-major.  That
+// is the order twoGapLookUpSA's lock-step warp hands out places in (lanes = adjacent parents, loop variable = width), which
+// thrust's stable sort on (pattern, position) keeps (oracle/cgx_oracle.c cmp_hit4).  After the segments are copied into tile
+// order a stable sort on the two-gap pattern bits alone (a pattern aXbXc has ONE parent) yields (pattern, position, width,
+// length): three passes instead of seven (eight at C3).
+// Tiles are cut on run boundaries: a tile is nominally J2O_STRIDE parents; its first parents are skipped when they continue
+// the previous tile's last run, and threads J2O_STRIDE..255 take the parents that continue its own last run.
 constexpr int J2O_SLOTS = CGX_MAX_RULE_SPAN - 2;       // widths 1..13
+constexpr int J2O_STRIDE = 240;                        // 256 - 16 >= 256 - (longest run - 1)
 __global__ void __launch_bounds__(256) j2_ordered_kernel(const uint64_t *__restrict__ hits1, size_t H1, int pbits, const unsigned long long *__restrict__ child_sig,
                                                          const int32_t *__restrict__ str, const uint32_t *__restrict__ gapw, const PackTab tab, int cbits,
                                                          unsigned long long *__restrict__ counter, unsigned long long *__restrict__ seg_base,
                                                          uint32_t *__restrict__ seg_count, uint64_t *__restrict__ hits, size_t cap) {
     __shared__ uint32_t s_d2[J2O_SLOTS][256];
+    __shared__ uint16_t s_mask[256], s_excl[256];
+    __shared__ uint8_t s_head[257];
     __shared__ unsigned s_wsum[8];
     __shared__ unsigned long long s_base;
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tile = blockIdx.x;
-    const size_t k = (size_t)tile * 256 + tid;
+    const size_t base = (size_t)tile * J2O_STRIDE;
+    const size_t k = base + tid;
     unsigned active = 0, probes = 0;
     uint32_t bits = 0, d1 = 0;
     unsigned long long sig = 0;
     int p = 0, L = 0;
+    bool mine = false, head = true;
     if (k < H1) {
         const uint64_t hk = hits1[k];
-        d1 = (uint32_t)(hk >> (pbits + 4));
-        sig = __ldg(&child_sig[d1]);
+        const uint64_t run_key = hk >> 4;                                      // (pattern, position)
+        const uint64_t before = base ? hits1[base - 1] >> 4 : ~0ull;           // last parent of the previous tile's nominal range
+        mine = run_key != before;                                              // not a continuation of the previous tile's last run
+        if (tid >= J2O_STRIDE) mine = mine && run_key == (hits1[base + J2O_STRIDE - 1] >> 4);
+        head = !mine || tid == 0 || run_key != (hits1[k - 1] >> 4);
+        if (mine) {
+            d1 = (uint32_t)(hk >> (pbits + 4));
+            sig = __ldg(&child_sig[d1]);
+        }
         if (sig) {
             p = (int)((hk >> 4) & ((1ull << pbits) - 1)); L = (int)(hk & 15);
             const uint32_t w = __ldg(&gapw[p + L + 1]);
@@ -773,6 +798,9 @@ __global__ void __launch_bounds__(256) j2_ordered_kernel(const uint64_t *__restr
             }
         }
     }
+    s_mask[tid] = (uint16_t)found_mask;
+    s_head[tid] = head ? 1 : 0;
+    if (tid == 0) s_head[256] = 1;
     // exclusive prefix of c over the CTA
     unsigned incl = c;
 #pragma unroll
@@ -782,6 +810,10 @@ __global__ void __launch_bounds__(256) j2_ordered_kernel(const uint64_t *__restr
     }
     if (lane == 31) s_wsum[warp] = incl;
     __syncthreads();
+    unsigned excl = incl - c;
+#pragma unroll
+    for (int w = 0; w < 8; w++) if (w < (int)warp) excl += s_wsum[w];
+    s_excl[tid] = (uint16_t)excl;
     if (tid == 0) {
         unsigned tot = 0;
 #pragma unroll
@@ -792,14 +824,29 @@ __global__ void __launch_bounds__(256) j2_ordered_kernel(const uint64_t *__restr
         s_base = seg;
     }
     __syncthreads();
-    unsigned long long o = s_base + (incl - c);
-#pragma unroll
-    for (int w = 0; w < 8; w++) if (w < (int)warp) o += s_wsum[w];
-    for (unsigned j = 0; j < c; j++) {
-        const int g2 = __ffs(found_mask);                             // j-th smallest width
-        found_mask &= found_mask - 1;
-        if (o + j < cap)
-            hits[o + j] = ((uint64_t)s_d2[j][tid] << (pbits + 8)) | ((uint64_t)(uint32_t)p << 8) | ((uint64_t)L << 4) | (uint64_t)(L + 1 + g2);
+    if (c) {
+        const bool alone = head && s_head[tid + 1];                   // the run is this thread only: its hits are consecutive
+        int rs = (int)tid, re = (int)tid;                             // run = threads rs..re
+        if (!alone) {
+            while (!s_head[rs]) rs--;
+            while (!s_head[re + 1]) re++;
+        }
+        const unsigned long long o = s_base + s_excl[rs];
+        for (unsigned j = 0; j < c; j++) {
+            const int g = __ffs(found_mask) - 1;                      // j-th smallest width of this thread, 0-based
+            found_mask &= found_mask - 1;
+            unsigned at = j;
+            if (!alone) {
+                at = 0;
+                const unsigned below = (1u << g) - 1u;
+                for (int m = rs; m <= re; m++) {
+                    const unsigned mm = s_mask[m];
+                    at += __popc(mm & below) + ((m < (int)tid) ? ((mm >> g) & 1u) : 0u);
+                }
+            }
+            if (o + at < cap)
+                hits[o + at] = ((uint64_t)s_d2[j][tid] << (pbits + 8)) | ((uint64_t)(uint32_t)p << 8) | ((uint64_t)(g + 1) << 4) | (uint64_t)L;
+        }
     }
     for (int off = 16; off; off >>= 1) { active += __shfl_xor_sync(0xffffffffu, active, off); probes += __shfl_xor_sync(0xffffffffu, probes, off); }
     if (lane == 0 && active) { atomicAdd(&counter[1], (unsigned long long)probes); atomicAdd(&counter[2], (unsigned long long)active); }
@@ -826,7 +873,7 @@ void stage_twogap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     unsigned long long host_ctr[3] = {0, 0, 0};
     bool ordered = true;                                   // CGX_JOIN_ORDERED=0: round 1's unordered append + full sort
     if (const char *e = getenv("CGX_JOIN_ORDERED")) { if (!strcmp(e, "0")) ordered = false; }
-    const uint32_t n_tiles = cgx_div_up(H1, 256);
+    const uint32_t n_tiles = cgx_div_up(H1, J2O_STRIDE);
     unsigned long long *seg_base = ordered ? b.j_status.get<unsigned long long>((size_t)n_tiles + 1) : nullptr;
     uint32_t *seg_count = ordered ? b.j_segcnt.get<uint32_t>((size_t)2 * n_tiles + 2) : nullptr;
     uint32_t *seg_dst = ordered ? seg_count + n_tiles + 1 : nullptr;

@@ -322,6 +322,10 @@ class GrammarExtractor:
         infos, prev = [], None
         while todo:
             q0, q1 = todo.pop()
+            fit = int(self.L.cgx_batch_advice(self.h, q1 - q0))       # from the hits per query of the last batch: at most one refusal per stream
+            if fit < q1 - q0:
+                todo.append((q0 + fit, q1))
+                q1 = q0 + fit
             t = qt[qo[q0]:qo[q1]] if qo[q1] > qo[q0] else np.zeros(1, dtype=np.int32)
             o = np.ascontiguousarray(qo[q0:q1 + 1] - qo[q0])
             rc = self.L.cgx_extract_begin(self.h, _p(np.ascontiguousarray(t), C.c_int32), _p(o, C.c_int32), q1 - q0)

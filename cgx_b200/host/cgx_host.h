@@ -66,6 +66,10 @@ void cgxh_queries_free(cgxh_queries_t *q);
 int cgxh_write_grammars(const char *outdir, const cgx_result_t *res, const int32_t *qry_off, int32_t qid_base, const cgxh_side_t *src,
                         const cgxh_side_t *tgt, int n_threads);
 
+/* the same with gzip_level 1..9: <outdir>/grammar.<qid>.s.gz, the form cdec reads its per-sentence grammars in (zlib; 0 = plain text) */
+int cgxh_write_grammars_ex(const char *outdir, const cgx_result_t *res, const int32_t *qry_off, int32_t qid_base, const cgxh_side_t *src,
+                           const cgxh_side_t *tgt, int n_threads, int gzip_level);
+
 /* the writer's printf("%f") replacement for float-valued features (exactly glibc's digits; writer.c); returns the length */
 int cgxh_format_f6(float x, char *out);
 
@@ -79,6 +83,9 @@ typedef struct {
     int writer_threads;
     int quiet;
     const char *index_file;   /* extension: persisted GPU index (cgx_index_load when it exists, else build + cgx_index_save) */
+    int serve;           /* extension (-S): after the command line's query file, serve "<query file> <output dir>" requests from stdin
+                            against the resident index until EOF or "quit" */
+    int gzip_level;      /* extension (-z [level]): grammar.<qid>.s.gz instead of plain text */
 } cgxh_options_t;
 int cgxh_run(const cgxh_options_t *opt);
 

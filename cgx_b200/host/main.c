@@ -2,7 +2,9 @@
  * exactly six positionals (source, query, target, alignment, lex file, output directory), help + exit(0)
  * otherwise.  Extensions that do not disturb the contract: -g <gpus>, -b <queries per batch>,
  * -w <writer threads>, -q (quiet), -i <index file> (persisted GPU index: loaded when the file exists -- alignment and
- * lexical files are then not parsed and no suffix array is built -- else built and saved there). */
+ * lexical files are then not parsed and no suffix array is built -- else built and saved there), -z <level> (gzip'd grammar
+ * files, grammar.<qid>.s.gz), -S (server: after the command line's query file, "<query file> <output dir>" requests are read
+ * from stdin and served against the resident index; one "done ..." line per request on stdout). */
 #include "cgx_host.h"
 #include <stdio.h>
 #include <stdlib.h>
@@ -10,7 +12,7 @@
 
 static void print_help(void) {
     printf("\nGPU source codes for gappy extraction. Please check your input arguments.\n\n"
-           "usage: strmatchcuda [-l minmatchlen] [-t fingerlen] [-s timefile] [-g gpus] [-b batch] [-w threads] [-i index_file] [-q]\n"
+           "usage: strmatchcuda [-l minmatchlen] [-t fingerlen] [-s timefile] [-g gpus] [-b batch] [-w threads] [-i index_file] [-z level] [-S] [-q]\n"
            "       <source_corpus> <query_file> <target_corpus> <alignment_file> <lex_file> <output_dir>\n");
     exit(0);
 }
@@ -19,8 +21,8 @@ int main(int argc, char **argv) {
     cgxh_options_t o;
     int ch, errflg = 0;
     o.reffile = o.qryfile = o.reftargetfile = o.align = o.wordscdec = o.destinationDirectory = o.timefile = NULL;
-    o.minmatchlen = 1; o.fingerlen = 10; o.n_gpus = 1; o.batch_queries = 0; o.writer_threads = 1; o.quiet = 0; o.index_file = NULL;
-    while (!errflg && (ch = getopt(argc, argv, "hl:t:s:g:b:w:i:q")) != -1) {
+    o.minmatchlen = 1; o.fingerlen = 10; o.n_gpus = 1; o.batch_queries = 0; o.writer_threads = 1; o.quiet = 0; o.index_file = NULL; o.serve = 0; o.gzip_level = 0;
+    while (!errflg && (ch = getopt(argc, argv, "hl:t:s:g:b:w:i:z:Sq")) != -1) {
         switch (ch) {
         case 'h': print_help(); break;
         case 'l': o.minmatchlen = atoi(optarg); break;
@@ -31,6 +33,8 @@ int main(int argc, char **argv) {
         case 'w': o.writer_threads = atoi(optarg); break;
         case 'i': o.index_file = optarg; break;
         case 'q': o.quiet = 1; break;
+        case 'z': o.gzip_level = atoi(optarg); break;
+        case 'S': o.serve = 1; break;
         case '?': fprintf(stderr, "Unknown option %c\n", optopt); errflg = 1; break;
         default: errflg = 1; break;
         }

@@ -40,7 +40,7 @@ typedef struct {
 static void *writer_main(void *arg) {
     wtask_t *t = (wtask_t *)arg;
     double t0 = now_s();
-    t->rc = cgxh_write_grammars(t->w->opt->destinationDirectory, &t->res, t->off, t->q0, t->w->src, t->w->tgt, t->w->opt->writer_threads);
+    t->rc = cgxh_write_grammars_ex(t->w->opt->destinationDirectory, &t->res, t->off, t->q0, t->w->src, t->w->tgt, t->w->opt->writer_threads, t->w->opt->gzip_level);
     t->t_write = now_s() - t0;
     return NULL;
 }
@@ -76,6 +76,12 @@ static void *worker_main(void *arg) {
         while (top > 0 && !w->rc) {
             top--;
             q0 = stack[top][0]; q1 = stack[top][1];
+            int32_t fit = cgx_batch_advice(w->ctx, q1 - q0);          /* from the hits per query of the last batch: at most one refusal per stream */
+            if (fit < q1 - q0) {
+                if (top + 1 > cap) { cap *= 2; stack = (int32_t (*)[2])realloc(stack, sizeof(int32_t[2]) * (size_t)cap); }
+                stack[top][0] = q0 + fit; stack[top][1] = q1; top++;
+                q1 = q0 + fit;
+            }
             int32_t nq = q1 - q0, base = q->off[q0];
             int32_t *off = (int32_t *)malloc(sizeof(int32_t) * ((size_t)nq + 1));
             for (int32_t i = 0; i <= nq; i++) off[i] = q->off[q0 + i] - base;
@@ -118,18 +124,74 @@ static void *worker_main(void *arg) {
         if (cgx_result_at(w->ctx, 0, &wt.res)) { fprintf(stderr, "cgx_result_at: %s\n", cgx_last_error(w->ctx)); w->rc = 1; }
         w->t_gpu += now_s() - t0;
         t0 = now_s();
-        if (!w->rc && cgxh_write_grammars(w->opt->destinationDirectory, &wt.res, prev_off, prev_q0, w->src, w->tgt, w->opt->writer_threads)) w->rc = 1;
+        if (!w->rc && cgxh_write_grammars_ex(w->opt->destinationDirectory, &wt.res, prev_off, prev_q0, w->src, w->tgt, w->opt->writer_threads, w->opt->gzip_level)) w->rc = 1;
         w->t_write += now_s() - t0;
     }
     free(prev_off);
     return NULL;
 }
 
+/* one query file against the resident index: load the queries, run the batches on the GPUs, write the grammars */
+typedef struct {
+    const cgxh_options_t *opt;
+    cgx_ctx_t **ctx;
+    int n_gpus;
+    const cgxh_side_t *src, *tgt;
+    double t_load, t_index, t_begin;
+    int last_Q;
+} serve_t;
+
+static int serve_one(serve_t *sv, const char *qryfile, const char *outdir) {
+    const cgxh_options_t *opt = sv->opt;
+    cgxh_options_t o = *opt;                 /* the workers read the output directory from their options */
+    o.destinationDirectory = outdir;
+    const int n_gpus = sv->n_gpus;
+    cgxh_queries_t qry;
+    if (cgxh_queries_load(qryfile, sv->src, &qry)) return 1;
+    fprintf(stderr, "\nMax length of queries is %d\n", qry.max_len);
+    sv->last_Q = qry.Q;
+    double t2 = now_s();
+    fprintf(stderr, "Start Extract Pair\n");
+    /* queries per batch: -b, else an even split over the GPUs capped at CGXH_DEFAULT_BATCH (the per-batch hit lists grow
+     * with corpus size x batch size; the reference needs <= ~5 k queries per process at its preallocation sizes, SURVEY 8c) */
+    int batch = opt->batch_queries > 0 ? opt->batch_queries : (qry.Q > 0 ? (qry.Q + n_gpus - 1) / n_gpus : 1);
+    if (opt->batch_queries <= 0 && batch > CGXH_DEFAULT_BATCH) batch = CGXH_DEFAULT_BATCH;
+    worker_t *w = (worker_t *)calloc((size_t)n_gpus, sizeof(worker_t));
+    pthread_t *th = (pthread_t *)calloc((size_t)n_gpus, sizeof(pthread_t));
+    for (int g = 0; g < n_gpus; g++) {
+        w[g].ctx = sv->ctx[g]; w[g].opt = &o; w[g].qry = &qry; w[g].src = sv->src; w[g].tgt = sv->tgt; w[g].gpu = g; w[g].n_gpus = n_gpus; w[g].batch = batch;
+        if (n_gpus == 1) worker_main(&w[g]); else pthread_create(&th[g], NULL, worker_main, &w[g]);
+    }
+    int rc = 0;
+    double t_gpu = 0, t_write = 0;
+    int64_t rules = 0;
+    for (int g = 0; g < n_gpus; g++) {
+        if (n_gpus > 1) pthread_join(th[g], NULL);
+        rc |= w[g].rc;
+        if (w[g].t_gpu > t_gpu) t_gpu = w[g].t_gpu;
+        if (w[g].t_write > t_write) t_write = w[g].t_write;
+        rules += w[g].rules;
+    }
+    double t3 = now_s();
+    fprintf(stderr, "Start Printing Gappy Phrases...\n");   /* the reference's completion marker (README.md:76-79) */
+    fprintf(stderr, "loading %.3f s, index %.3f s, match+extract %.3f s (max over %d GPU%s), grammar writing %.3f s, total %.3f s; %lld rules; %.1f query sentences/s\n",
+            sv->t_load, sv->t_index, t_gpu, n_gpus, n_gpus > 1 ? "s" : "", t_write, t3 - sv->t_begin, (long long)rules, qry.Q / (t3 - t2 > 0 ? t3 - t2 : 1e-9));
+    if (opt->timefile) {
+        FILE *fh = fopen(opt->timefile, "a");
+        if (fh) {
+            fprintf(fh, "total: %f , load: %f , index: %f , extract: %f , write: %f , gpus: %d , queries: %d\n", t3 - sv->t_begin, sv->t_load, sv->t_index, t_gpu, t_write, n_gpus, qry.Q);
+            fclose(fh);
+        }
+    }
+    free(w); free(th);
+    cgxh_queries_free(&qry);
+    return rc;
+}
+
 int cgxh_run(const cgxh_options_t *opt) {
     cgxh_side_t src, tgt;
     cgxh_align_t al;
     cgxh_lex_t lex;
-    cgxh_queries_t qry;
     double t0 = now_s();
     fprintf(stderr, "\nLoading the reference\n");
     if (cgxh_corpus_load(opt->reffile, 1, &src)) return 1;
@@ -144,8 +206,6 @@ int cgxh_run(const cgxh_options_t *opt) {
         if (cgxh_lex_load(opt->wordscdec, &src, &tgt, &lex)) return 1;
         fprintf(stderr, "Lex File Word Possibility COUNTER: %lld\n", (long long)lex.count);
     }
-    if (cgxh_queries_load(opt->qryfile, &src, &qry)) return 1;
-    fprintf(stderr, "\nMax length of queries is %d\n", qry.max_len);
     if (!have_index && cgxh_alignment_load(opt->align, &src, &tgt, &al)) return 1;
     double t1 = now_s();
 
@@ -172,40 +232,32 @@ int cgxh_run(const cgxh_options_t *opt) {
     if (n_gpus > 1 && cgx_index_broadcast(ctx, n_gpus)) { fprintf(stderr, "cgx_index_broadcast: %s\n", cgx_last_error(ctx[0])); return 1; }
     double t2 = now_s();
 
-    fprintf(stderr, "Start Extract Pair\n");
-    /* queries per batch: -b, else an even split over the GPUs capped at CGXH_DEFAULT_BATCH (the per-batch hit lists grow
-     * with corpus size x batch size; the reference needs <= ~5 k queries per process at its preallocation sizes, SURVEY 8c) */
-    int batch = opt->batch_queries > 0 ? opt->batch_queries : (qry.Q > 0 ? (qry.Q + n_gpus - 1) / n_gpus : 1);
-    if (opt->batch_queries <= 0 && batch > CGXH_DEFAULT_BATCH) batch = CGXH_DEFAULT_BATCH;
-    worker_t *w = (worker_t *)calloc((size_t)n_gpus, sizeof(worker_t));
-    pthread_t *th = (pthread_t *)calloc((size_t)n_gpus, sizeof(pthread_t));
-    for (int g = 0; g < n_gpus; g++) {
-        w[g].ctx = ctx[g]; w[g].opt = opt; w[g].qry = &qry; w[g].src = &src; w[g].tgt = &tgt; w[g].gpu = g; w[g].n_gpus = n_gpus; w[g].batch = batch;
-        if (n_gpus == 1) worker_main(&w[g]); else pthread_create(&th[g], NULL, worker_main, &w[g]);
-    }
-    int rc = 0;
-    double t_gpu = 0, t_write = 0;
-    int64_t rules = 0;
-    for (int g = 0; g < n_gpus; g++) {
-        if (n_gpus > 1) pthread_join(th[g], NULL);
-        rc |= w[g].rc;
-        if (w[g].t_gpu > t_gpu) t_gpu = w[g].t_gpu;
-        if (w[g].t_write > t_write) t_write = w[g].t_write;
-        rules += w[g].rules;
-    }
-    double t3 = now_s();
-    fprintf(stderr, "Start Printing Gappy Phrases...\n");   /* the reference's completion marker (README.md:76-79) */
-    fprintf(stderr, "loading %.3f s, index %.3f s, match+extract %.3f s (max over %d GPU%s), grammar writing %.3f s, total %.3f s; %lld rules; %.1f query sentences/s\n",
-            t1 - t0, t2 - t1, t_gpu, n_gpus, n_gpus > 1 ? "s" : "", t_write, t3 - t0, (long long)rules, qry.Q / (t3 - t2 > 0 ? t3 - t2 : 1e-9));
-    if (opt->timefile) {
-        FILE *fh = fopen(opt->timefile, "a");
-        if (fh) {
-            fprintf(fh, "total: %f , load: %f , index: %f , extract: %f , write: %f , gpus: %d , queries: %d\n", t3 - t0, t1 - t0, t2 - t1, t_gpu, t_write, n_gpus, qry.Q);
-            fclose(fh);
+    /* the query file of the command line, then -- in server mode (-S) -- one request per line of stdin: "<query file> <output dir>",
+     * answered on stdout when its grammar files are written.  The corpus, the suffix array and the lexical table stay resident in
+     * HBM between requests (the reference reloads and rebuilds everything for every query file, Start.cu:488-629). */
+    serve_t sv;
+    sv.opt = opt; sv.ctx = ctx; sv.n_gpus = n_gpus; sv.src = &src; sv.tgt = &tgt; sv.t_load = t1 - t0; sv.t_index = t2 - t1; sv.t_begin = t0;
+    int rc = serve_one(&sv, opt->qryfile, opt->destinationDirectory);
+    if (opt->serve) {
+        char *line = NULL;
+        size_t cap_line = 0;
+        sv.t_load = sv.t_index = 0.0;
+        while (getline(&line, &cap_line, stdin) > 0) {
+            char *save = NULL;
+            char *qf = strtok_r(line, " \t\r\n", &save), *od = strtok_r(NULL, " \t\r\n", &save);
+            if (!qf) continue;                                   /* empty line */
+            if (!strcmp(qf, "quit")) break;
+            if (!od) { printf("error %s: expected \"<query file> <output dir>\"\n", qf); fflush(stdout); continue; }
+            sv.t_begin = now_s();
+            int r1 = serve_one(&sv, qf, od);
+            if (r1) printf("error %s\n", qf);
+            else printf("done %s %d queries %.3f s\n", qf, sv.last_Q, now_s() - sv.t_begin);
+            fflush(stdout);
         }
+        free(line);
     }
     for (int g = 0; g < n_gpus; g++) cgx_destroy(ctx[g]);
-    free(ctx); free(w); free(th);
-    cgxh_side_free(&src); cgxh_side_free(&tgt); cgxh_align_free(&al); cgxh_lex_free(&lex); cgxh_queries_free(&qry);
+    free(ctx);
+    cgxh_side_free(&src); cgxh_side_free(&tgt); cgxh_align_free(&al); cgxh_lex_free(&lex);
     return rc;
 }

@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <zlib.h>
 
 typedef struct {
     const char *outdir;
@@ -16,6 +17,7 @@ typedef struct {
     int32_t qid_base;
     const cgxh_side_t *src, *tgt;
     int32_t q_begin, q_end;
+    int gzip_level;
     int rc;
 } wjob_t;
 
@@ -186,6 +188,26 @@ static void *write_range(void *arg) {
         }
         for (int32_t k = r->q2_off[q]; k < r->q2_off[q + 1]; k++)
             put_group(&out, r, j->src, j->tgt, 2, r->G + r->q2_ids[k], &srcbuf);        /* aXbXc */
+        if (j->gzip_level > 0) {
+            char mode[16];
+            snprintf(fn, sizeof fn, "%s/grammar.%d.s.gz", j->outdir, j->qid_base + q);
+            snprintf(mode, sizeof mode, "wb%d", j->gzip_level > 9 ? 9 : j->gzip_level);
+            gzFile gz = gzopen(fn, mode);
+            if (!gz) {
+                fprintf(stderr, "Please check your file directory address for grammar rule files output. It is not valid. Program Exits.\n");
+                j->rc = 1;
+                break;
+            }
+            size_t done = 0;
+            while (done < out.n) {                                                     /* gzwrite takes an unsigned length */
+                const size_t piece = out.n - done > (1u << 30) ? (1u << 30) : out.n - done;
+                if (gzwrite(gz, out.p + done, (unsigned)piece) <= 0) { j->rc = 1; break; }
+                done += piece;
+            }
+            if (gzclose(gz) != Z_OK) j->rc = 1;
+            if (j->rc) break;
+            continue;
+        }
         snprintf(fn, sizeof fn, "%s/grammar.%d.s", j->outdir, j->qid_base + q);         /* PrintResults.c:437 */
         FILE *fp = fopen(fn, "w");
         if (!fp) {
@@ -202,13 +224,18 @@ static void *write_range(void *arg) {
 
 int cgxh_write_grammars(const char *outdir, const cgx_result_t *res, const int32_t *qry_off, int32_t qid_base, const cgxh_side_t *src,
                         const cgxh_side_t *tgt, int n_threads) {
+    return cgxh_write_grammars_ex(outdir, res, qry_off, qid_base, src, tgt, n_threads, 0);
+}
+
+int cgxh_write_grammars_ex(const char *outdir, const cgx_result_t *res, const int32_t *qry_off, int32_t qid_base, const cgxh_side_t *src,
+                           const cgxh_side_t *tgt, int n_threads, int gzip_level) {
     if (n_threads < 1) n_threads = 1;
     if (n_threads > res->Q) n_threads = res->Q > 0 ? res->Q : 1;
     wjob_t *jobs = (wjob_t *)calloc((size_t)n_threads, sizeof(wjob_t));
     pthread_t *th = (pthread_t *)calloc((size_t)n_threads, sizeof(pthread_t));
     int rc = 0;
     for (int i = 0; i < n_threads; i++) {
-        jobs[i].outdir = outdir; jobs[i].res = res; jobs[i].qry_off = qry_off; jobs[i].qid_base = qid_base; jobs[i].src = src; jobs[i].tgt = tgt;
+        jobs[i].outdir = outdir; jobs[i].res = res; jobs[i].qry_off = qry_off; jobs[i].qid_base = qid_base; jobs[i].src = src; jobs[i].tgt = tgt; jobs[i].gzip_level = gzip_level;
         jobs[i].q_begin = (int32_t)((int64_t)res->Q * i / n_threads);
         jobs[i].q_end = (int32_t)((int64_t)res->Q * (i + 1) / n_threads);
         if (n_threads == 1) write_range(&jobs[i]);

@@ -144,6 +144,13 @@ typedef struct {
 } cgx_batch_info_t;
 int cgx_batch_info(const cgx_ctx_t *ctx, cgx_batch_info_t *out);
 
+/* Queries to put into the next batch of a stream, at most `wanted`.  The hit lists of a batch grow with corpus size x batch
+ * size and are indexed with 31 bits; a batch beyond that is refused (CGX_E_BATCH_TOO_LARGE) only after its join scan has run
+ * and the caller halves it.  This remembers the smallest size refused so far and the hits of the last finished batch, so
+ * that a stream pays for a refusal once, not once per batch.  (The reference preallocates 60 M hits, ComTypes.h:56, and fails
+ * beyond; its callers run ~5 k queries per process, README.md:76-79.) */
+int32_t cgx_batch_advice(const cgx_ctx_t *ctx, int32_t wanted);
+
 /* A distinct scored rule (red_dup_t, ComTypes.h:244-255), packed into 16 bytes: a C2 batch returns 7e7 of them and the
  * device-to-host copy of the rules is most of what a batch sends back (8 ranks on one host share its ingest bandwidth).
  * The converted id of a rule (ExtractPair.c:723-729 / :999-1006) is the `updown` range it sits in; the two per-id counts

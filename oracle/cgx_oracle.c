@@ -676,9 +676,20 @@ static int cmp_hit3(const void *a, const void *b) {
     for (int i = 0; i < 3; i++) if (x[i] != y[i]) return x[i] < y[i] ? -1 : 1;
     return 0;
 }
+/* Two-gap hits: (pattern, position) as twoGapSACompare (SuffixArray.cu:81-89) orders them; hits that tie on both keep the
+ * order in which twoGapLookUpSA's atomicAdd cursor handed out their places (thrust's merge sort is stable).  The parents of
+ * one (pattern, position) are adjacent entries of the one-gap list, i.e. adjacent lanes of one warp, and a warp that walks
+ * `move` in lock step emits them by (move, lane) = (width of the second gap, length of the parent).  Measured against the
+ * reference on a B200 (tools/ref_dump_config.py small: 284 962 hits, 48 535 tie groups): the hit SETS are identical; tie groups
+ * whose parents come from the sorted one-gap list (GappyLook.cu:656-737) have exactly this order (530 of 530); groups whose
+ * parents come from the frequent-pair list (:575-654) follow the warp scheduler (77 % this order, 63 % the (length, width)
+ * order the oracle used before) -- they are the remaining disagreement of the gappy sample sets. */
 static int cmp_hit4(const void *a, const void *b) {
     const int32_t *x = (const int32_t *)a, *y = (const int32_t *)b;
-    for (int i = 0; i < 4; i++) if (x[i] != y[i]) return x[i] < y[i] ? -1 : 1;
+    for (int i = 0; i < 2; i++) if (x[i] != y[i]) return x[i] < y[i] ? -1 : 1;
+    const int mx = x[3] - x[2], my = y[3] - y[2];
+    if (mx != my) return mx < my ? -1 : 1;
+    for (int i = 2; i < 4; i++) if (x[i] != y[i]) return x[i] < y[i] ? -1 : 1;
     return 0;
 }
 

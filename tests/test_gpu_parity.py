@@ -188,6 +188,36 @@ def test_edge_cases(micro):
             assert len(res.rules[k]) == len(o.rules(k))
 
 
+def test_queries_longer_than_128_tokens(micro):
+    """SURVEY.md 8f, lifted limit: the reference's lookup kernel gives a query 128 threads, one per token (SuffixArray.cu:402-419),
+    so it never sees token 129 of a sentence.  Neither the product nor the oracle has that bound: a 300-token query (the batch's
+    queries concatenated, OOV tokens included) goes through every stage bit-exact, and its tail -- beyond token 128 -- yields rules."""
+    from _oracle import Oracle
+    from _parity import assert_full_parity
+    from cgx_b200.extractor import GrammarExtractor
+    _, lay = micro
+    q = lay["qry_tok"]
+    long_q = np.concatenate([q, q[::-1], q])[:300].astype(np.int32)
+    assert len(long_q) == 300
+    tok = np.concatenate([long_q, q[:9]]).astype(np.int32)
+    off = np.array([0, 300, 309], np.int32)
+    ex = GrammarExtractor(0)
+    try:
+        ex.build_index(lay)
+        res = ex.extract(tok, off)
+        o = Oracle.from_layout(lay)
+        o.build_sa()
+        o.run(tok, off)
+        assert_full_parity(ex, res, lay, o)
+        tail = ex.extract(long_q[128:].copy(), np.array([0, 300 - 128], np.int32))
+        assert tail.G > 0 and len(tail.rules[1]) > 0
+        # phrases of the tail are phrases of the long query: nothing past token 128 was dropped
+        up_len = {(int(p[0]), int(p[2])) for p in res.phrases}
+        assert all((int(p[0]), int(p[2])) in up_len for p in tail.phrases)
+    finally:
+        ex.close()
+
+
 def test_batching_is_transparent(micro):
     """Per-query output does not depend on batch composition: one batch == two batches, query by query."""
     from cgx_b200.extractor import GrammarExtractor
@@ -252,6 +282,42 @@ def test_cli_pipelined_batches_write_the_same_grammars(micro, micro_files, tmp_p
         outs.append(out)
     c = gc.compare_dirs(str(outs[0]), str(outs[1]), rtol=0, atol=0)
     assert c["files"] == micro[0].n_qry and c["only_a"] == 0 and c["only_b"] == 0 and c["float_mismatch"] == 0, c
+
+
+def test_cli_server_mode_and_gzip(micro, micro_files, tmp_path):
+    """strmatchcuda -S keeps the index resident and serves "<query file> <output dir>" requests from stdin (the
+    reference reloads the corpus and rebuilds its suffix array for every query file); -z writes grammar.<qid>.s.gz.  Every
+    request's grammar files equal those of a one-shot run on the same query file."""
+    import gzip
+    cli = os.path.join(ROOT, "bin", "strmatchcuda")
+    q_lines = open(micro_files["q"]).read().splitlines()
+    half = tmp_path / "half.q"                                   # a second, different query file: the last half, reversed
+    half.write_text("".join(x + "\n" for x in q_lines[len(q_lines) // 2:][::-1]))
+    args = [micro_files["e"], micro_files["a"], micro_files["lex"]]
+    ref_full, ref_half = tmp_path / "ref_full", tmp_path / "ref_half"
+    for out, qf in ((ref_full, micro_files["q"]), (ref_half, str(half))):
+        out.mkdir()
+        r = subprocess.run([cli, "-q", micro_files["f"], qf] + args + [str(out)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+    s0, s1, s2 = tmp_path / "s0", tmp_path / "s1", tmp_path / "s2"
+    for d in (s0, s1, s2):
+        d.mkdir()
+    req = "%s %s\n\n%s %s\n%s\nquit\n" % (half, s1, micro_files["q"], s2, "lonely_field")
+    r = subprocess.run([cli, "-q", "-S", "-z", "6", micro_files["f"], micro_files["q"]] + args + [str(s0)], input=req, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    answers = r.stdout.strip().splitlines()
+    assert len(answers) == 3 and answers[0].startswith("done %s %d queries" % (half, len(q_lines) - len(q_lines) // 2)), answers
+    assert answers[1].startswith("done %s %d queries" % (micro_files["q"], len(q_lines))) and answers[2].startswith("error lonely_field"), answers
+    assert r.stderr.count("SA Construction") == 1 and r.stderr.count("Start Printing Gappy Phrases") == 3      # one index, three query files
+    for served, want in ((s0, ref_full), (s1, ref_half), (s2, ref_full)):
+        plain = tmp_path / (served.name + "_plain")
+        plain.mkdir()
+        names = sorted(os.listdir(served))
+        assert names and all(n.endswith(".s.gz") for n in names)
+        for n in names:
+            (plain / n[:-3]).write_bytes(gzip.open(served / n).read())
+        c = gc.compare_dirs(str(plain), str(want), rtol=0, atol=0)
+        assert c["files"] == len(os.listdir(want)) and c["only_a"] == 0 and c["only_b"] == 0 and c["float_mismatch"] == 0 and c["missing_files"] == 0, c
 
 
 def test_oversized_batches_are_split(micro, micro_files, tmp_path, monkeypatch):

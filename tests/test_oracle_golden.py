@@ -104,15 +104,26 @@ def test_twogap_patterns_and_hits(micro_oracle, golden):
     assert len(p2) == len(r2)
     assert np.array_equal(p2[:, 1], rp2["pattern"][r2["position"], 0])
     h, rh = o.twogap_hits(), g["twoGapSA"]
-    ref = np.stack([rh[k].astype(np.int64) for k in ("position", "str_position", "length", "length2")], 1)
-    ref = ref[np.lexsort((ref[:, 3], ref[:, 2], ref[:, 1], ref[:, 0]))]
+    ref = np.stack([rh[k].astype(np.int64) for k in ("position", "str_position", "length", "length2")], 1)     # the reference's own order
     mine_cnt = np.bincount(h[:, 0], minlength=len(p2))
     ref_cnt = np.bincount(ref[:, 0], minlength=len(p2))
     bad = set(np.nonzero(mine_cnt != ref_cnt)[0].tolist())
     assert len(bad) <= max(4, len(p2) // 500)
-    keep_m = np.array([x not in bad for x in h[:, 0]])
-    keep_r = np.array([x not in bad for x in ref[:, 0]])
-    assert np.array_equal(h[keep_m].astype(np.int64), ref[keep_r])
+    mine = h[np.array([x not in bad for x in h[:, 0]])].astype(np.int64)
+    ref = ref[np.array([x not in bad for x in ref[:, 0]])]
+    # (1) the hit SET is the reference's, and so is the order of the (pattern, position) groups
+    canon = lambda a: a[np.lexsort((a[:, 3], a[:, 2], a[:, 1], a[:, 0]))]
+    assert np.array_equal(canon(mine), canon(ref))
+    assert np.array_equal(mine[:, :2], ref[:, :2])
+    # (2) inside a group (hits that tie on the reference's sort key) the reference keeps its atomicAdd arrival order, which is
+    # the warp scheduler's; the oracle's (width, length) order is the lock-step one and agrees with it on most groups -- the
+    # (length, width) order used before round 2 agrees on far fewer (measured here on the reference's own dump)
+    starts = np.nonzero(np.r_[True, (np.diff(ref[:, 0]) != 0) | (np.diff(ref[:, 1]) != 0)])[0]
+    ends = np.r_[starts[1:], len(ref)]
+    groups = [(a, b) for a, b in zip(starts, ends) if b - a > 1]
+    same = sum(np.array_equal(mine[a:b], ref[a:b]) for a, b in groups)
+    old = sum(np.array_equal(canon(ref[a:b]), ref[a:b]) for a, b in groups)
+    assert len(groups) > 500 and same >= 0.9 * len(groups) and same > old * 1.5, (len(groups), same, old)
 
 
 def test_extraction_records(micro_oracle, golden):
