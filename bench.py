@@ -34,6 +34,9 @@ scoring) over the rank's query batch against the resident index.
            build, then all queries streamed in batches the way bin/strmatchcuda cuts them (a batch whose hit lists outgrow the
            31-bit result indices is refused and halved); device-resident and end-to-end rates, per-kernel table.  --no-c3 skips it.
 
+  sweep  : BASELINE.json configs[4] -- the first 1 k / 10 k / 100 k / 1 M queries of one fixed set of the same corpus, sharded
+           over the ranks like `strong` and streamed in 10 k-query batches; end-to-end wall clock (host buffers, every result
+           array copied D2H), max over ranks.  --no-sweep skips it.
   gpu_reference : (N = 1 only) SURVEY.md 8(d)'s two reference legs, from the reference's own code on this box (tools/ref_timers.py,
            oracle/_ref/strmatchcuda_dump = reference sources + timer hooks): its GPU binary's stage timers and its host
            aggregation createLexicon*Fast (ExtractPair.c:515,664,939; one thread) on the largest configuration it survives here
@@ -69,6 +72,8 @@ WORKLOADS = {
 STRONG_QUERIES = 80_000          # fixed query set of the strong-scaling block (8 shards of one 10 k batch at N = 8)
 STRONG_SEED = 8765
 BATCH_QUERIES = 10_000           # queries per batch of a stream (run.c's CGXH_DEFAULT_BATCH)
+SWEEP_QUERIES = (1_000, 10_000, 100_000, 1_000_000)      # BASELINE.json configs[4]: query sweep 1 k .. 1 M sentences
+SWEEP_SEED = 2468
 
 
 def log(*a):
@@ -97,7 +102,9 @@ def make_query_sets(workload: str, lay, world: int):
         weak.append((synth.query_ids(lay["src_names"], w), off.astype(np.int32)))
     w, off = synth.generate_queries(ns, STRONG_QUERIES, v_src=v, v_tgt=v, seed=1234, qry_seed=STRONG_SEED)
     strong = (synth.query_ids(lay["src_names"], w), off.astype(np.int32))
-    return {"weak": weak, "strong": strong, "n": int(lay["n"])}
+    w, off = synth.generate_queries(ns, max(SWEEP_QUERIES), v_src=v, v_tgt=v, seed=1234, qry_seed=SWEEP_SEED)
+    sweep = (synth.query_ids(lay["src_names"], w), off.astype(np.int32))
+    return {"weak": weak, "strong": strong, "sweep": sweep, "n": int(lay["n"])}
 
 
 def config_of(workload: str, n_tokens: int, Q: int, T: int, world: int):
@@ -351,8 +358,10 @@ def run_c3(args, device):
     log("c3 index: SA %.1f ms (%d rounds), auxiliary %.1f ms, %.2f GB resident, wall %.2f s" % (info["sa_build_ms"], info["sa_rounds"], info["aux_build_ms"],
                                                                                            info["index_bytes"] / 1e9, index_wall))
     del lay
-    w1 = min(Q, BATCH_QUERIES)
-    ex.extract_stream(tok[: off[w1]], off[: w1 + 1], batch_queries=BATCH_QUERIES)                 # warm-up: buffers grow to batch size
+    # warm-up: the device buffers and the pinned mirrors of all three result sets grow to batch size (pinning ~2 GB of host
+    # memory per set takes over a second); the first 10 k-query batch is refused and the advice settles on the batch size
+    w1 = min(Q, 2 * BATCH_QUERIES)
+    ex.extract_stream(tok[: off[w1]], off[: w1 + 1], batch_queries=BATCH_QUERIES)
     acc = {"rules": 0, "d2h": 0, "batches": 0}
 
     def on_batch(a, b, r):
@@ -617,6 +626,31 @@ def gpu_arm(args):
     barrier()
     t_end = time.time()
     clocks = sampler.stop(t_begin, t_end) if sampler else None
+    # ---- query sweep (configs[4]): prefixes of one fixed set, sharded like the strong block
+    sweep_rows = []
+    if not args.no_sweep and "sweep" in qsets:
+        wtok, woff = qsets["sweep"]
+        for nq in SWEEP_QUERIES:
+            if nq > len(woff) - 1:
+                break
+            sub_off = woff[: nq + 1]
+            a0, a1 = cdist.shard_queries(sub_off, world, rank)
+            mt = np.ascontiguousarray(wtok[sub_off[a0]:sub_off[a1]])
+            mo = np.ascontiguousarray(sub_off[a0:a1 + 1] - sub_off[a0])
+            seen = [0]
+
+            def on_sweep_batch(a, b, r, seen=seen):
+                seen[0] += touch(r)
+            barrier()
+            t0 = time.perf_counter()
+            infos = ex.extract_stream(mt, mo, batch_queries=BATCH_QUERIES, on_batch=on_sweep_batch) if a1 > a0 else []
+            torch.cuda.synchronize()
+            tw = torch.tensor([time.perf_counter() - t0, sum(i["ms_total"] for i in infos) / 1e3], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+            sweep_rows.append({"queries": nq, "value": nq / float(tw[0]), "unit": "query sentences/s", "wall_s": float(tw[0]), "device_s": float(tw[1]),
+                               "rank0_batches": len(infos)})
+        barrier()
 
     tv = torch.tensor([dev_ms, e2e_s, wall_dev, lat_s, strong_s, strong_dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -704,6 +738,9 @@ def gpu_arm(args):
             "wall_ms_per_step_incl_flush": 1e3 * wall_dev_max / args.steps,
             "index_bytes": int(info["index_bytes"]),
             "strong": strong,
+            "sweep": {"workload": "BASELINE.json configs[4] on the c2 corpus: the first N queries of one fixed 1 M-query set, sharded over the ranks "
+                                  "(cgx_b200.dist.shard_queries), 10 k-query batches, end to end (host buffers, all results D2H); sample sizes 300/65/70",
+                      "rows": sweep_rows} if sweep_rows else None,
             "c3": c3,
             "gpu_reference": gpu_ref,
         }
@@ -725,6 +762,7 @@ def main():
     ap.add_argument("--cpu-queries-per-core", type=int, default=1, help="--impl reference: queries per process and step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c3", action="store_true", help="skip the second block (BASELINE.json configs[2]: 10 M sentence pairs, 100 k queries; N = 1 only)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the query-count sweep (BASELINE.json configs[4])")
     ap.add_argument("--only-c3", action="store_true", help="development: run the c3 block alone and print it")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the reference-binary block (stage timers of oracle/_ref/strmatchcuda_dump; N = 1 only)")
     ap.add_argument("--c3-queries", type=int, default=WORKLOADS["c3"][1], help="queries of the c3 block (default: all 100 k)")

@@ -560,7 +560,7 @@ extern "C" int cgx_batch_info(const cgx_ctx_t *c, cgx_batch_info_t *out) {
 extern "C" int32_t cgx_batch_advice(const cgx_ctx_t *c, int32_t wanted) {
     if (!c || wanted <= 1) return wanted;
     const Batch &b = c->batch;
-    if (b.adv_refused_q == 0 || wanted < b.adv_refused_q) return wanted;       // nothing of this size has been refused yet
+    if (b.adv_refused_q == 0) return wanted;                                   // nothing has been refused yet
     // Hits grow sublinearly with the batch (queries share patterns), so scaling the last finished batch linearly up to 90 % of
     // the limit over-estimates: that size is safe.  Never less than half of the smallest refused batch -- the classic split.
     double fit = (double)(b.adv_refused_q / 2);

@@ -88,72 +88,83 @@ __device__ __forceinline__ bool pt_resolve(const PackTab t, uint64_t key, uint32
         w = __ldg(&t.slots[s]);
     }
 }
+__device__ __forceinline__ bool pt_find(const PackTab t, uint64_t key, uint64_t *val) {
+    uint32_t s;
+    const unsigned long long w = pt_first(t, key, &s);
+    return pt_resolve(t, key, s, w, val);
+}
 #endif
 
-// ---- quotient table: 8-byte slots in 32-byte buckets (one sector), for keys too wide for PackTab.  The kb-bit key goes through
-// a BIJECTION of the kb-bit integers (odd multiplies and xor-shifts); its top bits choose the home bucket and only the
-// remaining low bits are stored, so (bucket, remainder) still identifies the key exactly.  An entry that finds its home
-// bucket full moves on to the next one (at most QT_MAX_DISP buckets away) and records how far it went, so the remainder is
-// read against the right home.  slot = remainder << (3 + vbits) | displacement << vbits | value; a bucket with an empty slot
-// has never overflowed, which ends an unsuccessful lookup after one sector.  At <= 3 entries per 4-slot bucket the one-gap
-// pattern table of a C2 batch (5.9e6 patterns) is 67 MB instead of the 268 MB of the 16-byte form: it stays in the 126 MB L2.
+// ---- quotient table: 8-byte slots in 32-byte buckets (one sector), for keys too wide for PackTab.  A key is a pair (A, B) of
+// abits + bbits bits; it goes through a BIJECTION of that many bits built from 32-bit operations (add a multiple of B to A, odd
+// multiplies and xor-shifts of A inside abits bits, then xor B with bits of the result); the top bits of the image choose the
+// home bucket and only the remaining low bits -- the remainder, <= 28 bits -- are stored, so (bucket, remainder) still
+// identifies the key exactly.  An entry that finds its home bucket full moves on to the next one (at most QT_MAX_DISP buckets
+// away) and records how far it went, so its remainder is read against the right home.
+//   slot = (remainder << 3 | displacement) << 32 | value          (value < 2^31, so no slot equals HT_EMPTY)
+// A bucket with an empty slot has never overflowed, which ends an unsuccessful lookup after one sector.  At <= 3 entries per
+// 4-slot bucket the one-gap pattern table of a C2 batch (5.9e6 patterns) is 67 MB instead of the 268 MB of the 16-byte form.
 struct QTab {
     unsigned long long *slots;
     uint32_t bmask;        // buckets - 1
-    int kb, rb, vbits;     // key bits, remainder bits (kb - log2 buckets), value bits
+    int abits, bbits, rb;  // widths of the key halves; remainder bits = abits + bbits - log2(buckets), <= 28 (tag word < 2^31: never an empty slot's)
 };
 constexpr int QT_MAX_DISP = 7;
 
-static inline uint32_t qt_buckets_for(size_t entries) {       // power of two, <= 3 entries per 4-slot bucket
+static inline int qt_log2(uint32_t pow2) { int l = 0; while ((1u << l) < pow2) l++; return l; }
+// power of two; <= 3 entries per 4-slot bucket and enough buckets for the remainder to fit 28 bits
+static inline uint32_t qt_buckets_for(size_t entries, int key_bits) {
     uint32_t b = 256;
-    while ((size_t)b * 3 < entries) b <<= 1;
+    while ((size_t)b * 3 < entries || key_bits - qt_log2(b) > 28) b <<= 1;
     return b;
 }
-static inline int qt_log2(uint32_t pow2) { int l = 0; while ((1u << l) < pow2) l++; return l; }
 
 #ifdef __CUDACC__
-__device__ __forceinline__ uint64_t qt_mix(uint64_t k, int kb) {       // bijection on [0, 2^kb)
-    const uint64_t M = (1ull << kb) - 1ull;
-    const int s = kb >> 1;
-    k = (k * 0x9E3779B97F4A7C15ull) & M;
-    k ^= k >> s;
-    k = (k * 0xD6E8FEB86659FD93ull) & M;
-    k ^= k >> s;
-    return k;
+__device__ __forceinline__ uint64_t qt_mix(const QTab t, uint32_t A, uint32_t B) {      // bijection on abits + bbits bits
+    const uint32_t MA = (1u << t.abits) - 1u;
+    const int s = max(1, t.abits >> 1);
+    A = (A + B * 0x9E3779B1u) & MA;
+    A = (A * 0x85EBCA77u) & MA;
+    A ^= A >> s;
+    A = (A * 0xC2B2AE3Du) & MA;
+    A ^= A >> s;
+    B ^= (A * 0x27D4EB2Fu) >> (32 - t.bbits);
+    return ((uint64_t)A << t.bbits) | (uint64_t)B;
 }
 // false: no free slot within QT_MAX_DISP buckets of the home bucket (the caller rebuilds the table with more buckets)
-__device__ __forceinline__ bool qt_insert(const QTab t, uint64_t key, uint64_t val) {
-    const uint64_t x = qt_mix(key, t.kb);
+__device__ __forceinline__ bool qt_insert(const QTab t, uint32_t A, uint32_t B, uint32_t val) {
+    const uint64_t x = qt_mix(t, A, B);
     const uint32_t home = (uint32_t)(x >> t.rb);
-    const uint64_t rem = x & ((1ull << t.rb) - 1ull);
+    const uint32_t tag = (uint32_t)(x & ((1ull << t.rb) - 1ull)) << 3;
     for (int d = 0; d <= QT_MAX_DISP; d++) {
         unsigned long long *bk = t.slots + (size_t)((home + d) & t.bmask) * 4;
-        const unsigned long long w = (rem << (3 + t.vbits)) | ((unsigned long long)d << t.vbits) | val;
+        const unsigned long long w = ((unsigned long long)(tag | (uint32_t)d) << 32) | val;
         for (int i = 0; i < 4; i++) {
             const unsigned long long prev = atomicCAS(&bk[i], (unsigned long long)HT_EMPTY, w);
-            if (prev == HT_EMPTY || (prev >> t.vbits) == (w >> t.vbits)) return true;
+            if (prev == HT_EMPTY || (uint32_t)(prev >> 32) == (tag | (uint32_t)d)) return true;
         }
     }
     return false;
 }
 // two-step lookup for memory-level parallelism: qt_touch computes the home bucket of a key and asks for its sector
-// (prefetch: no destination registers -- three lookups in flight per lane cost 9 registers, not 27); qt_resolve reads it
-__device__ __forceinline__ void qt_touch(const QTab t, uint64_t key, uint32_t *home, uint64_t *want) {
-    const uint64_t x = qt_mix(key, t.kb);
+// (prefetch: no destination registers); qt_resolve reads it
+__device__ __forceinline__ void qt_touch(const QTab t, uint32_t A, uint32_t B, uint32_t *home, uint32_t *tag) {
+    const uint64_t x = qt_mix(t, A, B);
     *home = (uint32_t)(x >> t.rb);
-    *want = (x & ((1ull << t.rb) - 1ull)) << 3;                         // remainder | displacement 0
+    *tag = (uint32_t)(x & ((1ull << t.rb) - 1ull)) << 3;                // remainder | displacement 0
     asm volatile("prefetch.global.L1 [%0];" ::"l"(t.slots + (size_t)(*home & t.bmask) * 4));
 }
-__device__ __forceinline__ bool qt_resolve(const QTab t, uint32_t home, uint64_t want, uint64_t *val) {
+__device__ __forceinline__ bool qt_resolve(const QTab t, uint32_t home, uint32_t tag, uint32_t *val) {
     for (int d = 0;; d++) {
-        const ulonglong2 *bk = reinterpret_cast<const ulonglong2 *>(t.slots + (size_t)((home + d) & t.bmask) * 4);
-        const ulonglong2 lo = __ldg(bk), hi = __ldg(bk + 1);
-        const uint64_t key = want | (uint64_t)d;
-        if ((lo.x >> t.vbits) == key) { *val = lo.x & ((1ull << t.vbits) - 1ull); return true; }
-        if ((lo.y >> t.vbits) == key) { *val = lo.y & ((1ull << t.vbits) - 1ull); return true; }
-        if ((hi.x >> t.vbits) == key) { *val = hi.x & ((1ull << t.vbits) - 1ull); return true; }
-        if ((hi.y >> t.vbits) == key) { *val = hi.y & ((1ull << t.vbits) - 1ull); return true; }
-        const bool full = lo.x != HT_EMPTY && lo.y != HT_EMPTY && hi.x != HT_EMPTY && hi.y != HT_EMPTY;
+        const uint4 *bk = reinterpret_cast<const uint4 *>(t.slots + (size_t)((home + d) & t.bmask) * 4);
+        const uint4 lo = __ldg(bk), hi = __ldg(bk + 1);              // slots: (lo.x, lo.y) (lo.z, lo.w) (hi.x, hi.y) (hi.z, hi.w), tag in the odd word
+        const uint32_t key = tag | (uint32_t)d;
+        if (lo.y == key) { *val = lo.x; return true; }
+        if (lo.w == key) { *val = lo.z; return true; }
+        if (hi.y == key) { *val = hi.x; return true; }
+        if (hi.w == key) { *val = hi.z; return true; }
+        // an empty slot has value word 0xFFFFFFFF; a stored value is < 2^31
+        const bool full = (int32_t)(lo.x | lo.z | hi.x | hi.z) >= 0;
         if (!full || d == QT_MAX_DISP) return false;
     }
 }

@@ -38,11 +38,9 @@
 
 namespace cgx {
 
-// key of a one-gap pattern in the per-batch table: (first phrase id, length of the second phrase, its canonical m-gram id),
-// packed into bits_for(G) + 2 + pbits bits (pbits = bits of a corpus position)
-__device__ __forceinline__ uint64_t key1_of(uint32_t phrase_a, int le, uint32_t bucket_b, int pbits) {
-    return ((((uint64_t)phrase_a << 2) | (uint64_t)le) << pbits) | (uint64_t)bucket_b;
-}
+// key of a one-gap pattern in the per-batch table (hash.cuh QTab): A = canonical m-gram id of the second phrase (a corpus
+// position: pbits bits), B = first phrase id << 2 | length of the second phrase (bits_for(G) + 2 bits)
+__device__ __forceinline__ uint32_t key1_b(uint32_t phrase_a, int le) { return (phrase_a << 2) | (uint32_t)le; }
 
 // Hits are staged per warp in shared memory and flushed with ONE global atomic per ~200 hits (a single counter
 // hit by one atomic per few hits serialises the whole grid: 56 % of the stall samples of round 1b's kernel).
@@ -84,7 +82,7 @@ __global__ void j1_setup_kernel(const Pat1 *__restrict__ pat, const Pat1Dev *__r
     const Pat1 p = pat[d];
     const uint32_t ub = (uint32_t)patd[d].up_b;
     const uint32_t ga = (uint32_t)pat_ga[d];
-    if (!qt_insert(tab, key1_of(ga, p.le, ub, pbits), ((uint64_t)d << 1) | (p.marker_pair >= 0 ? 1u : 0u))) *overflow = 1u;   // value: pattern id, marker-pair flag
+    if (!qt_insert(tab, ub, key1_b(ga, p.le), ((uint32_t)d << 1) | (p.marker_pair >= 0 ? 1u : 0u))) *overflow = 1u;   // value: pattern id, marker-pair flag
     uint32_t *bm = p.le == 1 ? bm1 : p.le == 2 ? bm2 : bm3;
     atomicOr(&bm[ub >> 5], 1u << (ub & 31));
     if (p.marker_pair >= 0) atomicOr(&bm_marker[ub >> 5], 1u << (ub & 31));
@@ -182,20 +180,20 @@ __global__ void __launch_bounds__(J1_BLOCK) j1_scan_kernel(const J1Args a) {
         for (int le = 1; le <= 3; le++)
             if (cand[le - 1]) cand[le - 1] = bit_test((le == 1 && miss) ? a.bm_marker : a.bm[le - 1], ub[le - 1]);
         uint32_t ss[3];
-        uint64_t sw[3];
+        uint32_t sw[3];
 #pragma unroll
         for (int le = 1; le <= 3; le++)
-            if (cand[le - 1]) qt_touch(a.tab, key1_of((uint32_t)ga, le, ub[le - 1], a.pshift - 4), &ss[le - 1], &sw[le - 1]);
+            if (cand[le - 1]) qt_touch(a.tab, ub[le - 1], key1_b((uint32_t)ga, le), &ss[le - 1], &sw[le - 1]);
 #pragma unroll
         for (int le = 1; le <= 3; le++) {
             if (!__any_sync(0xffffffffu, cand[le - 1])) continue;          // warp-uniform
-            uint64_t v = 0;
+            uint32_t v = 0;
             bool found = cand[le - 1] && qt_resolve(a.tab, ss[le - 1], sw[le - 1], &v);
             if (found && miss) {                                           // only le == 1 reaches here with miss set
                 if (v & 1u) atomicAdd(&a.missing[v >> 1], 1);
                 found = false;
             }
-            const uint64_t key = ((v >> 1) << a.pshift) | ((uint64_t)(uint32_t)p << 4) | (uint64_t)(ls + g + le - 1);
+            const uint64_t key = ((uint64_t)(v >> 1) << a.pshift) | ((uint64_t)(uint32_t)p << 4) | (uint64_t)(ls + g + le - 1);
             stage_push(found, key, stage, staged);
         }
         if (staged > ST_CAP - 96) stage_flush(stage, staged, &a.counter[0], a.hits, a.cap);
@@ -298,20 +296,20 @@ __global__ void __launch_bounds__(JP_TILE) j1_pos_kernel(const JPArgs a) {
             for (int le = 1; le <= 3; le++)
                 if (cand[le - 1]) cand[le - 1] = bit_test((le == 1 && miss) ? a.bm_marker : a.bm[le - 1], ub[le - 1]);
                 uint32_t ss[3];
-            uint64_t sw[3];
+            uint32_t sw[3];
 #pragma unroll
             for (int le = 1; le <= 3; le++)
-                if (cand[le - 1]) { qt_touch(a.tab, key1_of(ga, le, ub[le - 1], a.pshift - 4), &ss[le - 1], &sw[le - 1]); lookups++; }
+                if (cand[le - 1]) { qt_touch(a.tab, ub[le - 1], key1_b(ga, le), &ss[le - 1], &sw[le - 1]); lookups++; }
 #pragma unroll
             for (int le = 1; le <= 3; le++) {
                 if (!__any_sync(0xffffffffu, cand[le - 1])) continue;
-                uint64_t v = 0;
+                uint32_t v = 0;
                 bool found = cand[le - 1] && qt_resolve(a.tab, ss[le - 1], sw[le - 1], &v);
                 if (found && miss) {
                     if (v & 1u) atomicAdd(&a.missing[v >> 1], 1);
                     found = false;
                 }
-                const uint64_t key = ((v >> 1) << a.pshift) | ((uint64_t)(uint32_t)p << 4) | (uint64_t)(ls + g + le - 1);
+                const uint64_t key = ((uint64_t)(v >> 1) << a.pshift) | ((uint64_t)(uint32_t)p << 4) | (uint64_t)(ls + g + le - 1);
                 stage_push(found, key, stage, staged);
             }
             if (staged > ST_CAP - 96) stage_flush(stage, staged, &a.counter[0], a.hits, a.cap);
@@ -347,14 +345,67 @@ struct JOArgs {
 
 // One walk over the 32 positions of this warp.  DIRECT = false: hits go to the warp's shared-memory stage (pattern id +
 // position-in-tile/length word) while they fit, and are counted either way; the featureMissingCount side effect and the
-// statistics happen here.  DIRECT = true (second walk of a tile whose stage overflowed): hits are written to their final place.
+// statistics happen here.  DIRECT = true (second walk of a warp whose stage overflowed): hits are written to their final place.
+//
+// Candidates -- (position, first phrase, gap width, second phrase) combinations that passed the gap word and the bitmaps -- are not
+// probed where they are found (8 of 32 lanes active there, and a third of the kernel's stall samples sat on those loads:
+// profiles/r02a) but queued per warp in shared memory, in the order the walk finds them, and probed 32 at a time in two steps:
+// a batch's bucket sectors are requested when it leaves the queue and read when the NEXT batch leaves it, so their latency
+// hides behind the walk in between.  Hits are staged in queue order = (position, first-phrase length, second-phrase length,
+// gap width) order; two hits of ONE pattern differ in position or width only, so every pattern's hits stay in (position, length) order.
+struct JQueue {
+    uint32_t *a, *b;      // table key halves (QTab): m-gram id of the second phrase / first phrase id << 2 | le
+    uint16_t *m;          // tile-relative position << 4 | length - 1 ... bit 15: "miss" candidate (featureMissingCount)
+};
+constexpr int JQ_CAP = 64;
+
 template <bool DIRECT>
 __device__ __forceinline__ unsigned jo_walk(const JPArgs &a, const int4 *__restrict__ s_win, int wrel, uint32_t P0, unsigned my_mask, const uint32_t my_aid[3],
                                             uint32_t *__restrict__ st_pat, uint16_t *__restrict__ st_pl, unsigned stage_cap, unsigned long long out_base,
-                                            unsigned &lookups, unsigned &elems) {
+                                            const JQueue q, unsigned &lookups, unsigned &elems) {
     const unsigned lane = threadIdx.x & 31, half = lane >> 4, h = lane & 15;
     const int g = (int)h + 1;
-    unsigned count = 0;                                            // warp-uniform
+    unsigned count = 0, queued = 0;                                // warp-uniform
+    uint32_t pend_home = 0, pend_tag = 0, pend_meta = 0;           // this lane's probe in flight
+    bool pend = false;
+    auto resolve_pending = [&]() {                                 // all lanes call
+        uint32_t v = 0;
+        bool found = pend && qt_resolve(a.tab, pend_home, pend_tag, &v);
+        if (found && (pend_meta & 0x8000u)) {                      // frequent single-token pair failing only the alignment check
+            if (!DIRECT && (v & 1u)) atomicAdd(&a.missing[v >> 1], 1);
+            found = false;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, found);
+        if (found) {
+            const unsigned idx = count + __popc(m & lanemask_lt());
+            const uint32_t pat = v >> 1;
+            if (DIRECT) {
+                const unsigned long long o = out_base + idx;
+                if (o < a.cap) a.hits[o] = ((uint64_t)pat << a.pshift) | ((uint64_t)(P0 + ((pend_meta & 0x7fffu) >> 4)) << 4) | (uint64_t)(pend_meta & 15u);
+            } else if (idx < stage_cap) {
+                st_pat[idx] = pat;
+                st_pl[idx] = (uint16_t)(pend_meta & 0x7fffu);
+            }
+        }
+        count += __popc(m);
+        pend = false;
+    };
+    auto drain = [&](unsigned n_take) {                            // all lanes call; n_take <= 32 entries leave the queue
+        resolve_pending();
+        if (lane < n_take) {
+            qt_touch(a.tab, q.a[lane], q.b[lane], &pend_home, &pend_tag);
+            pend_meta = q.m[lane];
+            pend = true;
+        }
+        __syncwarp();
+        const unsigned rest = queued - n_take;
+        uint32_t ta = 0, tb = 0; uint16_t tm = 0;
+        if (lane < rest) { ta = q.a[n_take + lane]; tb = q.b[n_take + lane]; tm = q.m[n_take + lane]; }
+        __syncwarp();
+        if (lane < rest) { q.a[lane] = ta; q.b[lane] = tb; q.m[lane] = tm; }
+        __syncwarp();
+        queued = rest;
+    };
     for (int k = 0; k < 16; k++) {
         const int src = 2 * k + (int)half;                         // half 0: even positions, half 1: odd ones -> pushes are in position order
         const unsigned pm = __shfl_sync(0xffffffffu, my_mask, src);
@@ -374,7 +425,7 @@ __device__ __forceinline__ unsigned jo_walk(const JPArgs &a, const int4 *__restr
             const bool ok = live && ((w >> (g - 1)) & 1u);
             const bool miss = !DIRECT && live && !ok && (av >> 31);
             const int qrel = rel + ls + g;
-            const uint32_t q = (uint32_t)(p + ls + g);
+            const uint32_t qpos = (uint32_t)(p + ls + g);
             const int le_max = min(min(3, CGX_MAX_RULE_SYMBOLS - 1 - ls), CGX_MAX_RULE_SPAN - ls - g);
             if (!DIRECT && h == 0 && on) elems++;
             uint32_t ub[3];
@@ -382,43 +433,31 @@ __device__ __forceinline__ unsigned jo_walk(const JPArgs &a, const int4 *__restr
             const int4 wq = (ok || miss) ? s_win[qrel] : make_int4(0, 0, 0, 0);
 #pragma unroll
             for (int le = 1; le <= 3; le++) {
-                cand[le - 1] = (ok && le <= le_max && q + (uint32_t)le <= a.n) || (miss && le == 1 && q < a.n);
+                cand[le - 1] = (ok && le <= le_max && qpos + (uint32_t)le <= a.n) || (miss && le == 1 && qpos < a.n);
                 ub[le - 1] = (uint32_t)(le == 1 ? wq.x : le == 2 ? wq.y : wq.z);
             }
 #pragma unroll
             for (int le = 1; le <= 3; le++)
                 if (cand[le - 1]) cand[le - 1] = bit_test((le == 1 && miss) ? a.bm_marker : a.bm[le - 1], ub[le - 1]);
-                uint32_t ss[3];
-            uint64_t sw[3];
-#pragma unroll
-            for (int le = 1; le <= 3; le++)
-                if (cand[le - 1]) { qt_touch(a.tab, key1_of(ga, le, ub[le - 1], a.pshift - 4), &ss[le - 1], &sw[le - 1]); if (!DIRECT) lookups++; }
 #pragma unroll
             for (int le = 1; le <= 3; le++) {
-                if (!__any_sync(0xffffffffu, cand[le - 1])) continue;
-                uint64_t v = 0;
-                bool found = cand[le - 1] && qt_resolve(a.tab, ss[le - 1], sw[le - 1], &v);
-                if (found && miss) {
-                    if (v & 1u) atomicAdd(&a.missing[v >> 1], 1);
-                    found = false;
+                const unsigned m = __ballot_sync(0xffffffffu, cand[le - 1]);
+                if (!m) continue;                                  // warp-uniform
+                if (cand[le - 1]) {
+                    const unsigned at = queued + __popc(m & lanemask_lt());
+                    q.a[at] = ub[le - 1];
+                    q.b[at] = key1_b(ga, le);
+                    q.m[at] = (uint16_t)((rel << 4) | (ls + g + le - 1) | (miss ? 0x8000 : 0));
+                    if (!DIRECT) lookups++;
                 }
-                const unsigned m = __ballot_sync(0xffffffffu, found);
-                if (found) {
-                    const unsigned idx = count + __popc(m & lanemask_lt());
-                    const uint32_t pat = (uint32_t)(v >> 1);
-                    const int len = ls + g + le - 1;
-                    if (DIRECT) {
-                        const unsigned long long o = out_base + idx;
-                        if (o < a.cap) a.hits[o] = ((uint64_t)pat << a.pshift) | ((uint64_t)(uint32_t)p << 4) | (uint64_t)len;
-                    } else if (idx < stage_cap) {
-                        st_pat[idx] = pat;
-                        st_pl[idx] = (uint16_t)((rel << 4) | len);
-                    }
-                }
-                count += __popc(m);
+                queued += __popc(m);
+                __syncwarp();
+                if (queued >= 32) drain(32);
             }
         }
     }
+    if (queued) drain(queued);
+    resolve_pending();
     return count;
 }
 
@@ -426,9 +465,10 @@ __global__ void __launch_bounds__(JO_TILE) j1_pos_ordered_kernel(const JOArgs o)
     const JPArgs &a = o.p;
     __shared__ int4 s_win[JO_TILE + JP_HALO];
     extern __shared__ __align__(16) unsigned char s_dyn[];          // per warp: JO_CAP pattern ids (u32), then JO_CAP position/length words (u16)
-    __shared__ unsigned s_wcount[JO_TILE / 32];
-    __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_qa[JO_TILE / 32][JQ_CAP], s_qb[JO_TILE / 32][JQ_CAP];
+    __shared__ uint16_t s_qm[JO_TILE / 32][JQ_CAP];
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const JQueue jq{s_qa[warp], s_qb[warp], s_qm[warp]};
     uint32_t *st_pat = reinterpret_cast<uint32_t *>(s_dyn) + (size_t)warp * JO_CAP;
     uint16_t *st_pl = reinterpret_cast<uint16_t *>(s_dyn + sizeof(uint32_t) * JO_CAP * (JO_TILE / 32)) + (size_t)warp * JO_CAP;
     const uint32_t tile = blockIdx.x;
@@ -437,7 +477,7 @@ __global__ void __launch_bounds__(JO_TILE) j1_pos_ordered_kernel(const JOArgs o)
         const uint32_t p = P0 + i;
         s_win[i] = p < a.n ? __ldg(&a.jwin[p]) : make_int4(0, 0, 0, 0);
     }
-    __syncthreads();
+    __syncthreads();                                                // the only CTA-wide barrier: the warps are independent from here on
     // lane l of warp w tests "does a first phrase start at position 32 w + l" for the three lengths
     const int wrel = (int)warp * 32;
     const int4 mine = s_win[wrel + (int)lane];
@@ -451,49 +491,42 @@ __global__ void __launch_bounds__(JO_TILE) j1_pos_ordered_kernel(const JOArgs o)
         if (inside && bit_test(a.bma[m], ub)) { my_mask |= 1u << m; my_aid[m] = __ldg(&a.aid[m][ub]); }
     }
     unsigned lookups = 0, elems = 0;
-    const unsigned count = jo_walk<false>(a, s_win, wrel, P0, my_mask, my_aid, st_pat, st_pl, o.stage_cap, 0ull, lookups, elems);
-    if (lane == 0) s_wcount[warp] = count;
-    __syncthreads();
-    if (tid == 0) {
-        unsigned tot = 0;
-#pragma unroll
-        for (int w = 0; w < JO_TILE / 32; w++) tot += s_wcount[w];
-        const unsigned long long seg = tot ? atomicAdd(&a.counter[0], (unsigned long long)tot) : 0ull;     // one atomic per tile
-        o.seg_base[tile] = seg;
-        o.seg_count[tile] = tot;
-        s_base = seg;
+    const unsigned count = jo_walk<false>(a, s_win, wrel, P0, my_mask, my_aid, st_pat, st_pl, o.stage_cap, 0ull, jq, lookups, elems);
+    // one output segment per WARP (32 positions), taken with one atomicAdd and recorded under the warp's number.  (Round 2a took one
+    // per tile: the warps of a tile then met at a barrier to add their counts up, and since hits per warp are heavy-tailed, 15 %
+    // of the kernel's stall samples were warps waiting there for the slowest of the eight.)
+    const uint32_t seg = tile * (JO_TILE / 32) + warp;
+    unsigned long long base = 0;
+    if (lane == 0) {
+        base = count ? atomicAdd(&a.counter[0], (unsigned long long)count) : 0ull;
+        o.seg_base[seg] = base;
+        o.seg_count[seg] = count;
     }
-    __syncthreads();
-    unsigned long long base = s_base;
-    bool overflow = false;
-#pragma unroll
-    for (int w = 0; w < JO_TILE / 32; w++) {
-        const unsigned c = s_wcount[w];
-        if (w < (int)warp) base += c;
-        overflow |= c > o.stage_cap;
-    }
-    if (!overflow) {
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (count <= o.stage_cap) {
+        __syncwarp();
         for (unsigned i = lane; i < count; i += 32) {
             const unsigned long long dst = base + i;
             const unsigned pl = st_pl[i];
             if (dst < a.cap) a.hits[dst] = ((uint64_t)st_pat[i] << a.pshift) | ((uint64_t)(P0 + (pl >> 4)) << 4) | (uint64_t)(pl & 15u);
         }
-    } else {
+    } else {                                                        // the stage overflowed: walk again, writing straight to the segment
         unsigned l2 = 0, e2 = 0;
-        jo_walk<true>(a, s_win, wrel, P0, my_mask, my_aid, st_pat, st_pl, o.stage_cap, base, l2, e2);
+        jo_walk<true>(a, s_win, wrel, P0, my_mask, my_aid, st_pat, st_pl, o.stage_cap, base, jq, l2, e2);
     }
     for (int off = 16; off; off >>= 1) { lookups += __shfl_xor_sync(0xffffffffu, lookups, off); elems += __shfl_xor_sync(0xffffffffu, elems, off); }
     if (lane == 0 && (lookups | elems)) { atomicAdd(&a.counter[1], (unsigned long long)lookups); atomicAdd(&a.counter[2], (unsigned long long)elems); }
 }
 
-// segments (one per tile, in arrival order) -> tile order: dst[seg_dst[t] + i] = src[seg_base[t] + i]
+// segments (in arrival order) -> their own order: dst[seg_dst[t] + i] = src[seg_base[t] + i]; one warp per segment
 __global__ void __launch_bounds__(256) seg_copy_kernel(const uint64_t *__restrict__ src, const unsigned long long *__restrict__ seg_base, const uint32_t *__restrict__ seg_dst,
-                                                       const uint32_t *__restrict__ seg_count, uint64_t *__restrict__ dst) {
-    const uint32_t t = blockIdx.x;
+                                                       const uint32_t *__restrict__ seg_count, uint32_t n_segs, uint64_t *__restrict__ dst) {
+    const uint32_t t = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (t >= n_segs) return;
     const uint32_t cnt = seg_count[t];
     const uint64_t *s = src + seg_base[t];
     uint64_t *d = dst + seg_dst[t];
-    for (uint32_t i = threadIdx.x; i < cnt; i += 256) d[i] = s[i];
+    for (uint32_t i = threadIdx.x & 31; i < cnt; i += 32) d[i] = s[i];
 }
 
 // per-pattern [start,count] in the sorted hit list
@@ -536,18 +569,17 @@ void stage_onegap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     uint32_t *aflag = b.j_aflag.get<uint32_t>((size_t)G + 1);
     uint32_t *eoff = b.j_tiles.get<uint32_t>((size_t)G + 2);
     // per-batch pattern table (hash.cuh QTab): key = (first phrase id, le, m-gram id of the second phrase), value = pattern id, marker flag
-    const int kbits_raw = cgx_bits_for((uint64_t)G) + 2 + b.pbits, vbits = cgx_bits_for((uint64_t)D1) + 1;
-    uint32_t buckets = qt_buckets_for((size_t)D1);
+    QTab tab;
+    tab.abits = std::max(b.pbits, 10); tab.bbits = cgx_bits_for((uint64_t)G) + 2;
+    CGX_REQUIRE_BATCH(tab.bbits <= 24 && D1 < (1 << 30), "%d phrases / %d one-gap patterns exceed the pattern-table fields", G, D1);
+    uint32_t buckets = qt_buckets_for((size_t)D1, tab.abits + tab.bbits);
     if (b.j1_buckets > buckets && b.j1_buckets <= 4 * buckets) buckets = b.j1_buckets;       // an earlier batch of this size needed more room
     uint32_t *tot = b.counters.get<uint32_t>(32);
     unsigned long long *ctr = (unsigned long long *)(tot + 4);         // [0] hits [1] bucket words read
-    QTab tab;
     uint32_t n_elems = 0;
     while (true) {
-        const int lb = qt_log2(buckets);
-        tab.kb = std::max(kbits_raw, lb + 8);                                                  // at least 8 remainder bits
-        tab.rb = tab.kb - lb; tab.vbits = vbits; tab.bmask = buckets - 1;
-        CGX_REQUIRE_BATCH(tab.rb + 3 + vbits <= 63, "%d one-gap patterns over %d phrases do not fit the packed pattern table", D1, G);
+        tab.rb = tab.abits + tab.bbits - qt_log2(buckets); tab.bmask = buckets - 1;
+        CGX_REQUIRE(tab.rb >= 1 && tab.rb <= 28, "one-gap pattern table: %d remainder bits", tab.rb);
         tab.slots = b.j_hash.get<unsigned long long>((size_t)buckets * 4);
         CUDA_CHECK(cudaMemsetAsync(bm, 0, sizeof(uint32_t) * 7 * bm_words, stream));
         CUDA_CHECK(cudaMemsetAsync(aflag, 0, sizeof(uint32_t) * ((size_t)G + 1), stream));
@@ -587,13 +619,13 @@ void stage_onegap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     // CGX_JOIN_ORDERED=0 keeps round 1's unordered append + full (pattern, position) sort for that variant too.
     bool ordered = position_major;
     if (const char *e = getenv("CGX_JOIN_ORDERED")) { if (!strcmp(e, "0")) ordered = false; }
-    const uint32_t n_tiles = cgx_div_up(ix.n, JO_TILE);
+    const uint32_t n_tiles = cgx_div_up(ix.n, JO_TILE), n_segs = n_tiles * (JO_TILE / 32);       // one output segment per warp
     JOArgs ao;
     uint32_t *seg_dst = nullptr;
     if (ordered) {
-        ao.seg_base = b.j_status.get<unsigned long long>((size_t)n_tiles + 1);
-        ao.seg_count = b.j_segcnt.get<uint32_t>((size_t)2 * n_tiles + 2);
-        seg_dst = ao.seg_count + n_tiles + 1;
+        ao.seg_base = b.j_status.get<unsigned long long>((size_t)n_segs + 1);
+        ao.seg_count = b.j_segcnt.get<uint32_t>((size_t)2 * n_segs + 2);
+        seg_dst = ao.seg_count + n_segs + 1;
         ao.stage_cap = JO_CAP;
         if (const char *e = getenv("CGX_JOIN_STAGE_CAP")) { const unsigned v = (unsigned)strtoul(e, nullptr, 10); if (v >= 1 && v < (unsigned)JO_CAP) ao.stage_cap = v; }
         if (!b.j1_smem_opt_in) {      // per context = per device: the opt-in is a per-device attribute of the kernel
@@ -629,8 +661,8 @@ void stage_onegap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     uint64_t *hits = b.hit_keys.ptr<uint64_t>();
     uint64_t *tmp = b.hit_keys_tmp.get<uint64_t>(H);
     if (ordered) {      // the tiles' segments, in tile (= position) order
-        exclusive_scan_u32(ao.seg_count, seg_dst, (size_t)n_tiles, nullptr, stream, b.scan, 0, &b.launches);
-        PROF("join_seg_copy", 16.0 * (double)H, (seg_copy_kernel<<<n_tiles, 256, 0, stream>>>(hits, ao.seg_base, seg_dst, ao.seg_count, tmp)));
+        exclusive_scan_u32(ao.seg_count, seg_dst, (size_t)n_segs, nullptr, stream, b.scan, 0, &b.launches);
+        PROF("join_seg_copy", 16.0 * (double)H, (seg_copy_kernel<<<cgx_div_up(n_segs, 8), 256, 0, stream>>>(hits, ao.seg_base, seg_dst, ao.seg_count, n_segs, tmp)));
         b.launches++;
         std::swap(hits, tmp);
     }
@@ -737,8 +769,11 @@ __global__ void __launch_bounds__(256) j2_ordered_kernel(const uint64_t *__restr
                                                          const int32_t *__restrict__ str, const uint32_t *__restrict__ gapw, const PackTab tab, int cbits,
                                                          unsigned long long *__restrict__ counter, unsigned long long *__restrict__ seg_base,
                                                          uint32_t *__restrict__ seg_count, uint64_t *__restrict__ hits, size_t cap) {
-    __shared__ uint32_t s_d2[J2O_SLOTS][256];
-    __shared__ uint16_t s_mask[256], s_excl[256];
+    __shared__ uint32_t s_d2[J2O_SLOTS][256];           // hits parked by [width - 1][owner thread]
+    __shared__ unsigned s_mask[256];
+    __shared__ uint16_t s_excl[256];
+    __shared__ uint32_t s_qtok[8][64];                  // per-warp candidate queue: token / owner lane << 4 | width - 1
+    __shared__ uint16_t s_qown[8][64];
     __shared__ uint8_t s_head[257];
     __shared__ unsigned s_wsum[8];
     __shared__ unsigned long long s_base;
@@ -771,34 +806,59 @@ __global__ void __launch_bounds__(256) j2_ordered_kernel(const uint64_t *__restr
             active = 1;
         }
     }
-    unsigned found_mask = 0, c = 0;                    // widths that hit (bit g2-1), their count
-    while (__any_sync(0xffffffffu, bits != 0)) {
-        int rr[4];
-        uint32_t cc[4], ss[4];
-        unsigned long long sv[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            rr[u] = 0;
-            if (bits) { rr[u] = p + L + 1 + __ffs(bits); bits &= bits - 1; probes++; }
+    // Candidate tokens: every lane walks its admissible widths (two per round), reads the token there and tests it against the
+    // parent's child signature.  The ~0.7 candidates per parent that pass are queued per warp in shared memory (owner lane, width,
+    // token) and the pattern table is probed for 32 of them at a time -- in place the probes ran with 3 of 32 lanes active and a
+    // third of the kernel's stall samples sat on their loads (profiles/r02a).  A hit is parked under its owner and WIDTH
+    // (s_d2[width][owner], s_mask[owner] bit), so the order in which probes complete does not matter.
+    uint32_t *q_tok = s_qtok[warp];
+    uint16_t *q_own = s_qown[warp];
+    s_mask[tid] = 0;
+    __syncwarp();
+    unsigned queued = 0;                                // warp-uniform
+    auto drain = [&](unsigned n_take) {                 // probe the first n_take (<= 32) queue entries, shift the rest down
+        const bool on = lane < n_take;
+        const unsigned own = on ? q_own[lane] : 0u;     // owner lane << 4 | width - 1
+        const uint32_t tokc = on ? q_tok[lane] : 0u;
+        const uint32_t d1o = __shfl_sync(0xffffffffu, d1, own >> 4);
+        uint64_t d2 = 0;
+        if (on && pt_find(tab, ((uint64_t)d1o << cbits) | (uint64_t)tokc, &d2)) {
+            const unsigned ot = (tid & ~31u) + (own >> 4);
+            s_d2[own & 15u][ot] = (uint32_t)d2;
+            atomicOr(&s_mask[ot], 1u << (own & 15u));
         }
+        __syncwarp();
+        const unsigned rest = queued - n_take;
+        uint32_t t2 = 0; uint16_t o2 = 0;
+        if (lane < rest) { t2 = q_tok[n_take + lane]; o2 = q_own[n_take + lane]; }
+        __syncwarp();
+        if (lane < rest) { q_tok[lane] = t2; q_own[lane] = o2; }
+        __syncwarp();
+        queued = rest;
+    };
+    while (__any_sync(0xffffffffu, bits != 0)) {
 #pragma unroll
-        for (int u = 0; u < 4; u++) if (rr[u]) cc[u] = (uint32_t)__ldg(&str[rr[u]]);
-#pragma unroll
-        for (int u = 0; u < 4; u++) if (rr[u] && !((sig >> sig_bit(cc[u])) & 1ull)) rr[u] = 0;
-#pragma unroll
-        for (int u = 0; u < 4; u++) if (rr[u]) sv[u] = pt_first(tab, ((uint64_t)d1 << cbits) | (uint64_t)cc[u], &ss[u]);
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            if (!__any_sync(0xffffffffu, rr[u] != 0)) continue;
-            uint64_t d2 = 0;
-            if (rr[u] && pt_resolve(tab, ((uint64_t)d1 << cbits) | (uint64_t)cc[u], ss[u], sv[u], &d2)) {
-                s_d2[c][tid] = (uint32_t)d2;                          // widths are visited in ascending order
-                found_mask |= 1u << (rr[u] - p - L - 2);
-                c++;
+        for (int u = 0; u < 2; u++) {
+            int g = -1;
+            if (bits) { g = __ffs(bits) - 1; bits &= bits - 1; probes++; }
+            uint32_t tokc = 0;
+            if (g >= 0) tokc = (uint32_t)__ldg(&str[p + L + 2 + g]);
+            const bool cand = g >= 0 && ((sig >> sig_bit(tokc)) & 1ull);
+            const unsigned m = __ballot_sync(0xffffffffu, cand);
+            if (cand) {
+                const unsigned at = queued + __popc(m & lanemask_lt());
+                q_tok[at] = tokc;
+                q_own[at] = (uint16_t)((lane << 4) | (unsigned)g);
             }
+            queued += __popc(m);
+            __syncwarp();
+            if (queued >= 32) drain(32);
         }
     }
-    s_mask[tid] = (uint16_t)found_mask;
+    if (queued) drain(queued);
+    __syncwarp();
+    unsigned found_mask = s_mask[tid];
+    const unsigned c = __popc(found_mask);              // widths that hit (bit g2-1), their count
     s_head[tid] = head ? 1 : 0;
     if (tid == 0) s_head[256] = 1;
     // exclusive prefix of c over the CTA
@@ -845,7 +905,7 @@ __global__ void __launch_bounds__(256) j2_ordered_kernel(const uint64_t *__restr
                 }
             }
             if (o + at < cap)
-                hits[o + at] = ((uint64_t)s_d2[j][tid] << (pbits + 8)) | ((uint64_t)(uint32_t)p << 8) | ((uint64_t)(g + 1) << 4) | (uint64_t)L;
+                hits[o + at] = ((uint64_t)s_d2[g][tid] << (pbits + 8)) | ((uint64_t)(uint32_t)p << 8) | ((uint64_t)(g + 1) << 4) | (uint64_t)L;
         }
     }
     for (int off = 16; off; off >>= 1) { active += __shfl_xor_sync(0xffffffffu, active, off); probes += __shfl_xor_sync(0xffffffffu, probes, off); }
@@ -900,7 +960,7 @@ void stage_twogap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     uint64_t *tmp = b.hit_keys_tmp.get<uint64_t>(H);
     if (ordered) {
         exclusive_scan_u32(seg_count, seg_dst, (size_t)n_tiles, nullptr, stream, b.scan, 0, &b.launches);
-        PROF("join_seg_copy", 16.0 * (double)H, (seg_copy_kernel<<<n_tiles, 256, 0, stream>>>(hits, seg_base, seg_dst, seg_count, tmp)));
+        PROF("join_seg_copy", 16.0 * (double)H, (seg_copy_kernel<<<cgx_div_up(n_tiles, 8), 256, 0, stream>>>(hits, seg_base, seg_dst, seg_count, n_tiles, tmp)));
         b.launches++;
         std::swap(hits, tmp);
     }

@@ -197,7 +197,7 @@ def test_queries_longer_than_128_tokens(micro):
     from cgx_b200.extractor import GrammarExtractor
     _, lay = micro
     q = lay["qry_tok"]
-    long_q = np.concatenate([q, q[::-1], q])[:300].astype(np.int32)
+    long_q = np.tile(np.concatenate([q, q[::-1]]), 3)[:300].astype(np.int32)
     assert len(long_q) == 300
     tok = np.concatenate([long_q, q[:9]]).astype(np.int32)
     off = np.array([0, 300, 309], np.int32)

@@ -11,7 +11,7 @@ python tools/ncu_step.py c2 2 > $out/step_plain.log 2>&1 || { echo "ncu_step fai
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $out/launches_c2.csv python tools/ncu_step.py c2 2 > $out/step_ncu.log 2>&1
 cp profiles/dram_traffic.json $out/dram_traffic.json 2>/dev/null
 # second batch of the step: lookup, j1, j2, the three extractions, the aggregation of the largest kind (+ the next)
-ncu --set full --clock-control none --import-source on -k regex:"j1_pos|j1_scan|j2_scan|agg_hash|agg_group|agg_rules|extract_|lookup_kernel" --launch-skip 16 --launch-count 13 \
+ncu --set full --clock-control none --import-source on -k regex:"j1_pos|j1_scan|j2_ordered|j2_scan|agg_hash|agg_group|agg_rules|extract_|lookup_kernel" --launch-skip 16 --launch-count 13 \
     -o $out/step python tools/ncu_step.py c2 2 > $out/step_full.log 2>&1
 python tools/ncu_summary.py $out/step.ncu-rep $out/step_full.md $out/dram_traffic.json > /dev/null 2>&1
 # the onesweep pass on its own: 2^27 random 48-bit keys (the shape of the hit sorts), one warm sort skipped
