@@ -631,8 +631,7 @@ def gpu_arm(args):
     if not args.no_sweep and "sweep" in qsets:
         wtok, woff = qsets["sweep"]
         for nq in SWEEP_QUERIES:
-            if nq > len(woff) - 1:
-                break
+            nq = min(nq, len(woff) - 1)             # (the generator drops empty sentences: the 1 M set is a few short)
             sub_off = woff[: nq + 1]
             a0, a1 = cdist.shard_queries(sub_off, world, rank)
             mt = np.ascontiguousarray(wtok[sub_off[a0]:sub_off[a1]])

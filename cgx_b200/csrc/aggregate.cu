@@ -220,6 +220,14 @@ __device__ __forceinline__ void lex_get(const ulonglong2 *__restrict__ slots, ui
     else { *v1 = 0.f; *v2 = 0.f; }
 }
 
+// asks for the sector lex_get(f, e) will read first (prefetch: no destination register), so that the probes of one target
+// terminal are in flight together; issued back to back with their loads they waited for one another (50 % of the kernel's
+// stall samples, profiles/r02a), and holding their first slots in registers cost more than it hid
+__device__ __forceinline__ void lex_touch(const ulonglong2 *__restrict__ slots, uint32_t mask, int f, int e) {
+    const uint64_t k = ((uint64_t)(uint32_t)(f + 1) << 32) | (uint64_t)(uint32_t)(e + 1);
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(slots + (ht_mix(k) & mask)));
+}
+
 // head_cell[r] = cell of the first record of rule r (excl = exclusive scan of the head flags)
 __global__ void agg_head_cell_kernel(const uint32_t *__restrict__ excl, uint32_t cells, uint32_t n_rules, uint32_t *__restrict__ head_cell) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -271,6 +279,9 @@ __global__ void __launch_bounds__(128) agg_rules_kernel(AggIdx a, int kind, cons
         tmask &= tmask - 1;
         const int e = __ldg(&a.tgt[ts + jj]);
         float mx = 0.f;
+        if (nf > 0) lex_touch(lex, lex_mask, -1, e);
+#pragma unroll
+        for (int j = 0; j < 5; j++) if (j < nf) lex_touch(lex, lex_mask, F[j], e);
         if (nf > 0) { lex_get(lex, lex_mask, -1, e, &v1, &v2); mx = fmaxf(mx, v1); }
 #pragma unroll
         for (int j = 0; j < 5; j++) {                                       // nf <= 5 (CGX_LONGEST_SRC / MAX_rule_symbols)
@@ -282,6 +293,10 @@ __global__ void __launch_bounds__(128) agg_rules_kernel(AggIdx a, int kind, cons
         egivenf += mx > 0.f ? -__log10f(mx) : CGX_MAXSCORE;
     }
     float fgivene = 0.f;
+    if (any_e) {
+#pragma unroll
+        for (int j = 0; j < 5; j++) if (j < nf) lex_touch(lex, lex_mask, F[j], -1);
+    }
 #pragma unroll
     for (int j = 0; j < 5; j++) {
         if (j >= nf) break;
