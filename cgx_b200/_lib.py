@@ -19,7 +19,7 @@ class IndexInfo(C.Structure):
 
 
 class IndexArrays(C.Structure):
-    _fields_ = [("n", C.c_int64), ("m", C.c_int64), ("lex_count", C.c_int64), ("max_token", C.c_int32), ("freq_list", C.c_int32 * 100)] + \
+    _fields_ = [("n", C.c_int64), ("m", C.c_int64), ("lex_count", C.c_int64), ("max_token", C.c_int32), ("freq_list", C.c_int32 * 100), ("wide", C.c_int32)] + \
                [(k, C.c_void_p) for k in ("str", "sa", "inv1", "inv2", "inv3", "bkt1", "bkt2", "bkt3", "tok_start", "RLP", "L_tar", "R_tar", "tgt", "freq_flag", "gapw",
                                          "lex_key", "lex_v1", "lex_v2")]
 
@@ -31,6 +31,8 @@ class IndexArrays(C.Structure):
         for k, size, dim in self.ARRAYS:
             if k == name:
                 cnt = {"n": self.n, "n3": self.n + 3, "m": self.m, "m3": self.m + 3, "nt": self.max_token + 2, "lex1": self.lex_count + 1}[dim]
+                if self.wide and name in ("RLP", "L_tar", "R_tar"):      # 16-bit alignment fields: twice the bytes
+                    size *= 2
                 return int(cnt) * size
         raise KeyError(name)
 
@@ -85,6 +87,7 @@ def load():
     L.cgx_last_error.argtypes = [vp]
     L.cgx_last_error.restype = C.c_char_p
     L.cgx_index_build.argtypes = [vp, i32p, C.c_int64, i32p, C.c_int64, u32p, u8p, u8p]
+    L.cgx_index_build_wide.argtypes = [vp, i32p, C.c_int64, i32p, C.c_int64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint16), C.POINTER(C.c_uint16)]
     L.cgx_lex_load.argtypes = [vp, i32p, i32p, f32p, f32p, C.c_int64]
     L.cgx_index_info.argtypes = [vp, C.POINTER(IndexInfo)]
     L.cgx_sa_build_dev.argtypes = [vp, vp, C.c_int64, C.c_int32, vp, i32p, f32p]
@@ -115,7 +118,7 @@ def load():
     return L
 
 
-EXPORTED_SYMBOLS = ("cgx_version", "cgx_create", "cgx_destroy", "cgx_last_error", "cgx_index_build", "cgx_lex_load", "cgx_index_info",
+EXPORTED_SYMBOLS = ("cgx_version", "cgx_create", "cgx_destroy", "cgx_last_error", "cgx_index_build", "cgx_index_build_wide", "cgx_lex_load", "cgx_index_info",
                     "cgx_sa_build_dev", "cgx_index_export", "cgx_index_alloc", "cgx_index_commit", "cgx_index_save", "cgx_index_load", "cgx_index_copy_sa", "cgx_index_copy_inv",
                     "cgx_index_copy_frequent", "cgx_extract", "cgx_extract_begin", "cgx_result_at", "cgx_extract_dev", "cgx_profile_enable", "cgx_profile_report",
                     "cgx_index_broadcast", "cgx_batch_info", "cgx_batch_advice", "cgx_result", "cgx_debug_fetch", "cgx_debug_sort_u64")

@@ -119,22 +119,45 @@ static void build_index_device(cgx_ctx *c) {
     c->batch.adv_refused_q = c->batch.adv_ok_q = 0;   // batch-size advice belongs to the corpus
 }
 
+static void index_build_host(cgx_ctx *c, const int32_t *src, int64_t n, const int32_t *tgt, int64_t m, const void *RLP, const void *L_tar, const void *R_tar,
+                             bool wide) {
+    CGX_REQUIRE(c && src && tgt && RLP && L_tar && R_tar, "null argument");
+    CGX_REQUIRE(n >= 4 && m >= 1, "empty corpus");
+    CUDA_CHECK(cudaSetDevice(c->device));
+    Index &ix = c->ix;
+    ix.n = (size_t)n; ix.m = (size_t)m; ix.wide = wide;
+    ix.maxtok = max_token_of(src, n);
+    CGX_REQUIRE(src[n] == 0 && src[n + 1] == 0 && src[n + 2] == 0, "source text must be followed by three zeros (Start.cu:354)");
+    const size_t wb = wide ? 8 : 4, lb = wide ? 2 : 1;                 // bytes per RLP word / per L_tar, R_tar entry (align_fields.cuh)
+    CUDA_CHECK(cudaMemcpyAsync(ix.str.get<int32_t>(ix.n + 3), src, sizeof(int32_t) * (ix.n + 3), cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(ix.tgt.get<int32_t>(ix.m + 3), tgt, sizeof(int32_t) * (ix.m + 3), cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(ix.RLP.get<uint8_t>(ix.n * wb), RLP, ix.n * wb, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(ix.L_tar.get<uint8_t>(ix.m * lb), L_tar, ix.m * lb, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(ix.R_tar.get<uint8_t>(ix.m * lb), R_tar, ix.m * lb, cudaMemcpyHostToDevice, c->stream));
+    build_index_device(c);
+}
+
+extern "C" int cgx_index_build_wide(cgx_ctx_t *c, const int32_t *src, int64_t n, const int32_t *tgt, int64_t m, const uint64_t *RLP64,
+                                    const uint16_t *L_tar16, const uint16_t *R_tar16) {
+    CGX_TRY(c, index_build_host(c, src, n, tgt, m, RLP64, L_tar16, R_tar16, true));
+}
+
 extern "C" int cgx_index_build(cgx_ctx_t *c, const int32_t *src, int64_t n, const int32_t *tgt, int64_t m, const uint32_t *RLP,
                                const uint8_t *L_tar, const uint8_t *R_tar) {
     CGX_TRY(c, {
-        CGX_REQUIRE(c && src && tgt && RLP && L_tar && R_tar, "null argument");
-        CGX_REQUIRE(n >= 4 && m >= 1, "empty corpus");
-        CUDA_CHECK(cudaSetDevice(c->device));
-        Index &ix = c->ix;
-        ix.n = (size_t)n; ix.m = (size_t)m;
-        ix.maxtok = max_token_of(src, n);
-        CGX_REQUIRE(src[n] == 0 && src[n + 1] == 0 && src[n + 2] == 0, "source text must be followed by three zeros (Start.cu:354)");
-        CUDA_CHECK(cudaMemcpyAsync(ix.str.get<int32_t>(ix.n + 3), src, sizeof(int32_t) * (ix.n + 3), cudaMemcpyHostToDevice, c->stream));
-        CUDA_CHECK(cudaMemcpyAsync(ix.tgt.get<int32_t>(ix.m + 3), tgt, sizeof(int32_t) * (ix.m + 3), cudaMemcpyHostToDevice, c->stream));
-        CUDA_CHECK(cudaMemcpyAsync(ix.RLP.get<uint32_t>(ix.n), RLP, sizeof(uint32_t) * ix.n, cudaMemcpyHostToDevice, c->stream));
-        CUDA_CHECK(cudaMemcpyAsync(ix.L_tar.get<uint8_t>(ix.m), L_tar, ix.m, cudaMemcpyHostToDevice, c->stream));
-        CUDA_CHECK(cudaMemcpyAsync(ix.R_tar.get<uint8_t>(ix.m), R_tar, ix.m, cudaMemcpyHostToDevice, c->stream));
-        build_index_device(c);
+        const char *force = getenv("CGX_FORCE_WIDE");
+        if (force && force[0] == '1' && c && src && tgt && RLP && L_tar && R_tar && n >= 4 && m >= 1) {     // tests: the 16-bit layout on an 8-bit corpus
+            std::vector<uint64_t> w((size_t)n);
+            std::vector<uint16_t> l((size_t)m), r((size_t)m);
+            for (int64_t i = 0; i < n; i++) {
+                const uint32_t x = RLP[i];
+                const bool eos = src[i] < 2;                            // the word at an EOS is the target sentence offset
+                const uint64_t L = (x >> 24) & 0xFF, R = (x >> 16) & 0xFF, P = (x >> 8) & 0xFF;
+                w[(size_t)i] = eos ? (uint64_t)x : (((L == 255 ? 65535ull : L) << 48) | ((R == 255 ? 65535ull : R) << 32) | (P << 16));
+            }
+            for (int64_t i = 0; i < m; i++) { l[(size_t)i] = L_tar[i] == 255 ? 65535 : L_tar[i]; r[(size_t)i] = R_tar[i] == 255 ? 65535 : R_tar[i]; }
+            index_build_host(c, src, n, tgt, m, w.data(), l.data(), r.data(), true);
+        } else index_build_host(c, src, n, tgt, m, RLP, L_tar, R_tar, false);
     });
 }
 
@@ -222,7 +245,7 @@ extern "C" int cgx_index_export(cgx_ctx_t *c, cgx_index_arrays_t *o) {
     CGX_TRY(c, {
         CGX_REQUIRE(c && o && c->ix.built, "index not built");
         Index &ix = c->ix;
-        o->n = (int64_t)ix.n; o->m = (int64_t)ix.m; o->lex_count = (int64_t)ix.lex_count; o->max_token = ix.maxtok;
+        o->n = (int64_t)ix.n; o->m = (int64_t)ix.m; o->lex_count = (int64_t)ix.lex_count; o->max_token = ix.maxtok; o->wide = ix.wide ? 1 : 0;
         memcpy(o->freq_list, ix.freq_list, sizeof(ix.freq_list));
         o->str = ix.str.p; o->sa = ix.sa.p; o->inv1 = ix.inv[0].p; o->inv2 = ix.inv[1].p; o->inv3 = ix.inv[2].p; o->bkt1 = ix.bkt[0].p; o->bkt2 = ix.bkt[1].p; o->bkt3 = ix.bkt[2].p; o->tok_start = ix.tok_start.p;
         o->RLP = ix.RLP.p; o->L_tar = ix.L_tar.p; o->R_tar = ix.R_tar.p; o->tgt = ix.tgt.p; o->freq_flag = ix.freq_flag.p; o->gapw = ix.gapw.p;
@@ -235,12 +258,12 @@ extern "C" int cgx_index_alloc(cgx_ctx_t *c, const cgx_index_arrays_t *s, cgx_in
         CGX_REQUIRE(c && s && o, "null argument");
         CUDA_CHECK(cudaSetDevice(c->device));
         Index &ix = c->ix;
-        ix.n = (size_t)s->n; ix.m = (size_t)s->m; ix.lex_count = (size_t)s->lex_count; ix.maxtok = s->max_token;
+        ix.n = (size_t)s->n; ix.m = (size_t)s->m; ix.lex_count = (size_t)s->lex_count; ix.maxtok = s->max_token; ix.wide = s->wide != 0;
         memcpy(ix.freq_list, s->freq_list, sizeof(ix.freq_list));
         size_t nt = (size_t)ix.maxtok + 2;
         ix.str.get<int32_t>(ix.n + 3); ix.sa.get<int32_t>(ix.n);
         for (int k = 0; k < 3; k++) { ix.inv[k].get<int32_t>(ix.n); ix.bkt[k].get<int32_t>(ix.n); }
-        ix.tok_start.get<int32_t>(nt); ix.RLP.get<uint32_t>(ix.n); ix.L_tar.get<uint8_t>(ix.m); ix.R_tar.get<uint8_t>(ix.m);
+        ix.tok_start.get<int32_t>(nt); ix.RLP.get<uint8_t>(ix.n * (ix.wide ? 8 : 4)); ix.L_tar.get<uint8_t>(ix.m * (ix.wide ? 2 : 1)); ix.R_tar.get<uint8_t>(ix.m * (ix.wide ? 2 : 1));
         ix.tgt.get<int32_t>(ix.m + 3); ix.freq_flag.get<uint8_t>(nt); ix.gapw.get<uint32_t>(ix.n);
         ix.lex_key.get<uint64_t>(ix.lex_count + 1); ix.lex_v1.get<float>(ix.lex_count + 1); ix.lex_v2.get<float>(ix.lex_count + 1);
         ix.built = false;
@@ -266,14 +289,14 @@ extern "C" int cgx_index_commit(cgx_ctx_t *c) {
 struct IndexFileHeader {
     char magic[8];                 // "CGXIDX01"
     int64_t n, m, lex_count;
-    int32_t max_token, sa_rounds, sa_key_bits, reserved;
+    int32_t max_token, sa_rounds, sa_key_bits, wide;      // wide: 16-bit alignment fields (0 in files written before the field existed)
     int32_t freq_list[CGX_PRECOMP];
 };
 struct IndexArrayRef { void *p; size_t bytes; };
 static int index_array_refs(const cgx_index_arrays_t &a, IndexArrayRef out[18]) {
     const size_t n = (size_t)a.n, m = (size_t)a.m, nt = (size_t)a.max_token + 2, lx = (size_t)a.lex_count + 1;
     const IndexArrayRef r[18] = {{a.str, 4 * (n + 3)}, {a.sa, 4 * n}, {a.inv1, 4 * n}, {a.inv2, 4 * n}, {a.inv3, 4 * n}, {a.bkt1, 4 * n}, {a.bkt2, 4 * n}, {a.bkt3, 4 * n},
-                                 {a.tok_start, 4 * nt}, {a.RLP, 4 * n}, {a.L_tar, m}, {a.R_tar, m}, {a.tgt, 4 * (m + 3)}, {a.freq_flag, nt}, {a.gapw, 4 * n},
+                                 {a.tok_start, 4 * nt}, {a.RLP, (a.wide ? 8 : 4) * n}, {a.L_tar, (a.wide ? 2 : 1) * m}, {a.R_tar, (a.wide ? 2 : 1) * m}, {a.tgt, 4 * (m + 3)}, {a.freq_flag, nt}, {a.gapw, 4 * n},
                                  {a.lex_key, 8 * lx}, {a.lex_v1, 4 * lx}, {a.lex_v2, 4 * lx}};
     for (int i = 0; i < 18; i++) out[i] = r[i];
     return 18;
@@ -287,12 +310,13 @@ extern "C" int cgx_index_save(cgx_ctx_t *c, const char *path) {
         CUDA_CHECK(cudaSetDevice(c->device));
         cgx_index_arrays_t a;
         CGX_REQUIRE(cgx_index_export(c, &a) == 0, "export failed");
-        fh = fopen(path, "wb");
-        CGX_REQUIRE(fh, "cannot open %s for writing", path);
+        const std::string tmp_path = std::string(path) + ".tmp";       // written beside the target and renamed when complete: a failed save leaves no truncated index behind
+        fh = fopen(tmp_path.c_str(), "wb");
+        CGX_REQUIRE(fh, "cannot open %s for writing", tmp_path.c_str());
         IndexFileHeader h;
         memset(&h, 0, sizeof h);
         memcpy(h.magic, "CGXIDX01", 8);
-        h.n = a.n; h.m = a.m; h.lex_count = a.lex_count; h.max_token = a.max_token; h.sa_rounds = c->ix.sa_stats.rounds; h.sa_key_bits = c->ix.sa_stats.key_bits;
+        h.n = a.n; h.m = a.m; h.lex_count = a.lex_count; h.max_token = a.max_token; h.sa_rounds = c->ix.sa_stats.rounds; h.sa_key_bits = c->ix.sa_stats.key_bits; h.wide = a.wide;
         memcpy(h.freq_list, a.freq_list, sizeof h.freq_list);
         CGX_REQUIRE(fwrite(&h, sizeof h, 1, fh) == 1, "write failed");
         const size_t piece = (size_t)64 << 20;
@@ -306,7 +330,11 @@ extern "C" int cgx_index_save(cgx_ctx_t *c, const char *path) {
                 CGX_REQUIRE(fwrite(stage, 1, len, fh) == len, "write failed (disk full?)");
             }
         cudaFreeHost(stage);
-        CGX_REQUIRE(fclose(fh) == 0, "close failed");
+        stage = nullptr;
+        FILE *done = fh;
+        fh = nullptr;
+        CGX_REQUIRE(fclose(done) == 0, "close failed");
+        CGX_REQUIRE(rename(tmp_path.c_str(), path) == 0, "cannot rename %s to %s", tmp_path.c_str(), path);
         return 0;
     } catch (const CgxError &e) {
         if (fh) fclose(fh);
@@ -329,7 +357,7 @@ extern "C" int cgx_index_load(cgx_ctx_t *c, const char *path) {
         CGX_REQUIRE(h.n >= 4 && h.m >= 1 && h.lex_count >= 0 && h.max_token >= 1, "%s: corrupt header", path);
         cgx_index_arrays_t shape, a;
         memset(&shape, 0, sizeof shape);
-        shape.n = h.n; shape.m = h.m; shape.lex_count = h.lex_count; shape.max_token = h.max_token;
+        shape.n = h.n; shape.m = h.m; shape.lex_count = h.lex_count; shape.max_token = h.max_token; shape.wide = h.wide;
         memcpy(shape.freq_list, h.freq_list, sizeof h.freq_list);
         CGX_REQUIRE(cgx_index_alloc(c, &shape, &a) == 0, "%s", c->err.c_str());
         const size_t piece = (size_t)64 << 20;

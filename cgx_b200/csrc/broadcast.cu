@@ -61,8 +61,8 @@ extern "C" int cgx_index_broadcast(cgx_ctx_t **ctxs, int n) {
             {offsetof(cgx_index_arrays_t, inv1), (size_t)shape.n * 4}, {offsetof(cgx_index_arrays_t, inv2), (size_t)shape.n * 4},
             {offsetof(cgx_index_arrays_t, inv3), (size_t)shape.n * 4}, {offsetof(cgx_index_arrays_t, bkt1), (size_t)shape.n * 4},
             {offsetof(cgx_index_arrays_t, bkt2), (size_t)shape.n * 4}, {offsetof(cgx_index_arrays_t, bkt3), (size_t)shape.n * 4}, {offsetof(cgx_index_arrays_t, tok_start), nt * 4},
-            {offsetof(cgx_index_arrays_t, RLP), (size_t)shape.n * 4}, {offsetof(cgx_index_arrays_t, L_tar), (size_t)shape.m},
-            {offsetof(cgx_index_arrays_t, R_tar), (size_t)shape.m}, {offsetof(cgx_index_arrays_t, tgt), (size_t)(shape.m + 3) * 4},
+            {offsetof(cgx_index_arrays_t, RLP), (size_t)shape.n * (shape.wide ? 8 : 4)}, {offsetof(cgx_index_arrays_t, L_tar), (size_t)shape.m * (shape.wide ? 2 : 1)},
+            {offsetof(cgx_index_arrays_t, R_tar), (size_t)shape.m * (shape.wide ? 2 : 1)}, {offsetof(cgx_index_arrays_t, tgt), (size_t)(shape.m + 3) * 4},
             {offsetof(cgx_index_arrays_t, freq_flag), nt}, {offsetof(cgx_index_arrays_t, gapw), (size_t)shape.n * 4}, {offsetof(cgx_index_arrays_t, lex_key), (size_t)(shape.lex_count + 1) * 8},
             {offsetof(cgx_index_arrays_t, lex_v1), (size_t)(shape.lex_count + 1) * 4}, {offsetof(cgx_index_arrays_t, lex_v2), (size_t)(shape.lex_count + 1) * 4}};
         for (const Item &it : items) {

@@ -29,6 +29,7 @@
 // of 32 slots in shared memory and run the extension phase on 32 of them at a time: extract_onegap 9.8 -> 23.8 ms, extract_contig
 // 6.1 -> 6.8 ms (every full warp then waits for its longest extension chain).  The one-thread-per-occurrence form stays.
 #include "batch.h"
+#include "align_fields.cuh"
 #include "prof.h"
 
 namespace cgx {
@@ -36,29 +37,32 @@ namespace cgx {
 // xw[k] = RLP[k] | 1 for a word (token >= 2), 0 at EOS / padding: the extension loops test "is a word" and read its aligned
 // span with ONE load (the reference reads str[k], then RLP[k]: two dependent random sectors); lrq[j] = range-minimum table over {L_tar, R_tar} (index.cu).
 // RLP itself is only read for the target offset stored at the previous EOS.
+template <class A>
 struct ExtractIdx {
     const int32_t *sa;
-    const uint32_t *xw, *RLP;
-    const uint2 *lrq;
+    const typename A::word_t *xw, *RLP;
+    const typename A::lrq_t *lrq;
     int n;
 };
 
 // ExtractPair.cu:103-133 consistent: min L_tar / max R_tar over the target window [start, end] (unaligned tokens skipped) must
 // be exactly the source span [start_chk, end_chk].  The window is the union of two entries of the range-minimum table lrq
 // (index.cu): two independent 8-byte loads.  Callers never pass more than CGX_MAX_RULE_SPAN tokens; longer windows take the loop.
-__device__ __forceinline__ unsigned lrq_level(uint2 v, int k) { return ((k & 2) ? v.y : v.x) >> (16 * (k & 1)); }
-__device__ __forceinline__ bool consistent(const ExtractIdx &x, int start, int end, int start_chk, int end_chk, int startpos_source) {
-    unsigned mn = 255, mx = 0;
+template <class A>
+__device__ __forceinline__ bool consistent(const ExtractIdx<A> &x, int start, int end, int start_chk, int end_chk, int startpos_source) {
+    unsigned mn = A::UNAL, mx = 0;
     const int len = end - start + 1;
     if (len > 0) {
         const int k = min(3, 31 - __clz(len)), step = 1 << k;
-        const uint2 a = __ldg(&x.lrq[start]), b = __ldg(&x.lrq[end - step + 1]);
-        const unsigned wa = lrq_level(a, k), wb = lrq_level(b, k);
-        mn = min(wa & 0xFFu, wb & 0xFFu);
-        mx = max((wa >> 8) & 0xFFu, (wb >> 8) & 0xFFu);
+        const typename A::lrq_t a = __ldg(&x.lrq[start]), b = __ldg(&x.lrq[end - step + 1]);
+        unsigned mna, mxa, mnb, mxb;
+        A::lrq_get(a, k, mna, mxa);
+        A::lrq_get(b, k, mnb, mxb);
+        mn = min(mna, mnb);
+        mx = max(mxa, mxb);
         for (int j = start + step; j <= end - step; j += step) {                     // runs only when len > 15
-            const unsigned w = lrq_level(__ldg(&x.lrq[j]), k);
-            mn = min(mn, w & 0xFFu); mx = max(mx, (w >> 8) & 0xFFu);
+            A::lrq_get(__ldg(&x.lrq[j]), k, mna, mxa);
+            mn = min(mn, mna); mx = max(mx, mxa);
         }
     }
     return !(startpos_source + (int)mn != start_chk || startpos_source + (int)mx != end_chk);
@@ -99,7 +103,8 @@ __global__ void slots_contig_kernel(const int32_t *__restrict__ phrases, int G, 
     if (g < G) cnt[g] = (uint32_t)min(phrases[g * 4 + 1] - phrases[g * 4] + 1, CGX_SAMPLER);
 }
 
-__global__ void __launch_bounds__(128) extract_contig_kernel(ExtractIdx x, const int32_t *__restrict__ phrases, int G, const uint32_t *__restrict__ slot_off,
+template <class A>
+__global__ void __launch_bounds__(128) extract_contig_kernel(ExtractIdx<A> x, const int32_t *__restrict__ phrases, int G, const uint32_t *__restrict__ slot_off,
                                                              uint32_t n_slots, RuleRec *__restrict__ rec_ab, RuleRec *__restrict__ rec_Xab,
                                                              RuleRec *__restrict__ rec_abX, RuleRec *__restrict__ rec_XabX) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -112,25 +117,26 @@ __global__ void __launch_bounds__(128) extract_contig_kernel(ExtractIdx x, const
     const int globalc = G;
     const int SPAN = CGX_MAX_RULE_SPAN;
 
-    unsigned L, R, temp;
+    unsigned L, R;
+    typename A::word_t temp;
     int sen_target_begin = -1, tempind = 0;
-    unsigned min_L = 255, max_R = 0;
+    unsigned min_L = A::UNAL, max_R = 0;
     unsigned gap1_start = 0, gap1_end = 0, gap2_start = 0, gap2_end = 0, target_start = 0, target_end = 0;
     bool next = true, abX = true, Xab = true, XabX = true, ab = true, XabNoSuccess = true, abXNoSuccess = true;
     int XabCount = 0, abXCount = 0;
-    unsigned min_L_Xab = 255, max_R_Xab = 0, min_L_abX = 255, max_R_abX = 0, min_L_XabX = 255, max_R_XabX = 0;
+    unsigned min_L_Xab = A::UNAL, max_R_Xab = 0, min_L_abX = A::UNAL, max_R_abX = 0, min_L_XabX = A::UNAL, max_R_XabX = 0;
 
     for (int k = current_str; k < current_str + longestmatch; k++) {
         temp = __ldg(&x.xw[k]);
-        L = (temp >> 24) & 0xFF; R = (temp >> 16) & 0xFF;
+        L = A::L(temp); R = A::R(temp);
         if (k == current_str) {
-            tempind = k - (int)((temp >> 8) & 0xFF) - 1;
-            sen_target_begin = tempind == -1 ? 0 : (int)__ldg(&x.RLP[tempind]);
+            tempind = k - (int)A::P(temp) - 1;
+            sen_target_begin = tempind == -1 ? 0 : (int)(uint32_t)__ldg(&x.RLP[tempind]);
         }
-        if ((L == 255 || R == 255) && (k == current_str || k == current_str + longestmatch - 1)) {
+        if ((L == A::UNAL || R == A::UNAL) && (k == current_str || k == current_str + longestmatch - 1)) {
             ab = false;
             if (k == current_str) abXNoSuccess = false; else XabNoSuccess = false;
-        } else if (L == 255 || R == 255) {
+        } else if (L == A::UNAL || R == A::UNAL) {
         } else { min_L = min(min_L, L); max_R = max(max_R, R); }
     }
     if (min_L > max_R || max_R - min_L >= (unsigned)SPAN) { abX = false; Xab = false; XabX = false; ab = false; }
@@ -146,8 +152,8 @@ __global__ void __launch_bounds__(128) extract_contig_kernel(ExtractIdx x, const
         temp = (Xab && current_str - i >= 0) ? __ldg(&x.xw[current_str - i]) : 0u;
         if (temp & 1u) {
             next = true;
-            L = (temp >> 24) & 0xFF; R = (temp >> 16) & 0xFF;
-            if (L == 255 || R == 255) { next = false; if (i == 1) { Xab = false; XabX = false; } }
+            L = A::L(temp); R = A::R(temp);
+            if (L == A::UNAL || R == A::UNAL) { next = false; if (i == 1) { Xab = false; XabX = false; } }
             else { min_L_Xab = min(min_L_Xab, L); max_R_Xab = max(max_R_Xab, R); }
             if (next && min_L_Xab > max_R_Xab) return;
             if ((int)max_R_Xab - (int)min_L_Xab >= SPAN) { next = false; Xab = false; }
@@ -171,8 +177,8 @@ __global__ void __launch_bounds__(128) extract_contig_kernel(ExtractIdx x, const
         temp = abX ? __ldg(&x.xw[ender + i]) : 0u;
         if (temp & 1u) {
             next = true;
-            L = (temp >> 24) & 0xFF; R = (temp >> 16) & 0xFF;
-            if (L == 255 || R == 255) { next = false; if (i == 1) { abX = false; XabX = false; } }
+            L = A::L(temp); R = A::R(temp);
+            if (L == A::UNAL || R == A::UNAL) { next = false; if (i == 1) { abX = false; XabX = false; } }
             else { min_L_abX = min(min_L_abX, L); max_R_abX = max(max_R_abX, R); }
             if (next && min_L_abX > max_R_abX) return;
             if ((int)max_R_abX - (int)min_L_abX >= SPAN) { next = false; abX = false; }
@@ -195,13 +201,13 @@ __global__ void __launch_bounds__(128) extract_contig_kernel(ExtractIdx x, const
         // ---- XabX ----
         if (XabX && (abX || Xab)) {
             if (XabCount == i) {          // left gap just validated; look for the smallest valid right gap
-                min_L_XabX = 255; max_R_XabX = 0;
+                min_L_XabX = A::UNAL; max_R_XabX = 0;
                 for (int icount = 1; XabX && icount <= abXCount; icount++) {
                     next = true;
                     if (icount + XabCount + longestmatch <= SPAN) {
                         temp = __ldg(&x.xw[ender + icount]);
-                        L = (temp >> 24) & 0xFF; R = (temp >> 16) & 0xFF;
-                        if (L == 255 || R == 255) { next = false; if (i == 1) return; }
+                        L = A::L(temp); R = A::R(temp);
+                        if (L == A::UNAL || R == A::UNAL) { next = false; if (i == 1) return; }
                         else { min_L_XabX = min(min_L_XabX, L); max_R_XabX = max(max_R_XabX, R); }
                     } else { next = false; icount = abXCount + 1; }
                     if (next && (int)max_R_XabX - (int)min_L_XabX >= SPAN) { next = false; icount = abXCount + 1; }
@@ -224,13 +230,13 @@ __global__ void __launch_bounds__(128) extract_contig_kernel(ExtractIdx x, const
                 }
             }
             if (XabX && abXCount == i) {  // right gap just validated; look for the smallest valid left gap
-                min_L_XabX = 255; max_R_XabX = 0;
+                min_L_XabX = A::UNAL; max_R_XabX = 0;
                 for (int icount = 1; XabX && icount <= XabCount; icount++) {
                     next = true;
                     if (icount + abXCount + longestmatch <= SPAN) {
                         temp = __ldg(&x.xw[current_str - icount]);
-                        L = (temp >> 24) & 0xFF; R = (temp >> 16) & 0xFF;
-                        if (L == 255 || R == 255) { next = false; if (i == 1) return; }
+                        L = A::L(temp); R = A::R(temp);
+                        if (L == A::UNAL || R == A::UNAL) { next = false; if (i == 1) return; }
                         else { min_L_XabX = min(min_L_XabX, L); max_R_XabX = max(max_R_XabX, R); }
                     } else { icount = XabCount + 1; next = false; }
                     if (next && (int)max_R_XabX - (int)min_L_XabX >= SPAN) { icount = XabCount + 1; next = false; }
@@ -264,18 +270,19 @@ __global__ void __launch_bounds__(128) extract_contig_kernel(ExtractIdx x, const
 // boundary helpers for the gappy seeds
 // ------------------------------------------------------------------------------------------------
 // ExtractPair.cu:135-194 checkBoundaryFast / :196-250 checkBoundaryFast2 (same scan; Fast2 reports absolute target span)
-__device__ __forceinline__ bool boundary_fast(const ExtractIdx &x, int start, int ender, unsigned *min_LL, unsigned *max_RR, int *sen_target_begin,
+template <class A>
+__device__ __forceinline__ bool boundary_fast(const ExtractIdx<A> &x, int start, int ender, unsigned *min_LL, unsigned *max_RR, int *sen_target_begin,
                                               int *tempind) {
-    unsigned min_L = 255, max_R = 0;
+    unsigned min_L = A::UNAL, max_R = 0;
     *sen_target_begin = -1; *tempind = 0;
     for (int k = start; k <= ender; k++) {
-        uint32_t w = __ldg(&x.xw[k]);
-        unsigned L = (w >> 24) & 0xFF, R = (w >> 16) & 0xFF;
-        if ((L == 255 || R == 255) && (k == start || k == ender)) return false;
-        if (L == 255 || R == 255) continue;
+        typename A::word_t w = __ldg(&x.xw[k]);
+        unsigned L = A::L(w), R = A::R(w);
+        if ((L == A::UNAL || R == A::UNAL) && (k == start || k == ender)) return false;
+        if (L == A::UNAL || R == A::UNAL) continue;
         if (k == start) {
-            *tempind = k - (int)((w >> 8) & 0xFF) - 1;
-            *sen_target_begin = (*tempind == -1) ? 0 : (int)__ldg(&x.RLP[*tempind]);
+            *tempind = k - (int)A::P(w) - 1;
+            *sen_target_begin = (*tempind == -1) ? 0 : (int)(uint32_t)__ldg(&x.RLP[*tempind]);
         }
         min_L = min(min_L, L); max_R = max(max_R, R);
     }
@@ -285,16 +292,17 @@ __device__ __forceinline__ bool boundary_fast(const ExtractIdx &x, int start, in
 }
 
 // ExtractPair.cu:252-342 checkBoundary: 0 normal false, 1 ok, 2 first token unaligned, 3 last, 4 both
-__device__ __forceinline__ int check_boundary(const ExtractIdx &x, int start, int ender, unsigned *target_start, unsigned *target_end) {
-    unsigned min_L = 255, max_R = 0;
+template <class A>
+__device__ __forceinline__ int check_boundary(const ExtractIdx<A> &x, int start, int ender, unsigned *target_start, unsigned *target_end) {
+    unsigned min_L = A::UNAL, max_R = 0;
     int sen_target_begin = -1, tempind = 0, wrong = 0;
     for (int k = start; k <= ender; k++) {
-        uint32_t w = __ldg(&x.xw[k]);
-        unsigned L = (w >> 24) & 0xFF, R = (w >> 16) & 0xFF;
-        bool un = (L == 255 || R == 255);
+        typename A::word_t w = __ldg(&x.xw[k]);
+        unsigned L = A::L(w), R = A::R(w);
+        bool un = (L == A::UNAL || R == A::UNAL);
         if (k == start) {
-            tempind = k - (int)((w >> 8) & 0xFF) - 1;
-            sen_target_begin = tempind == -1 ? 0 : (int)__ldg(&x.RLP[tempind]);
+            tempind = k - (int)A::P(w) - 1;
+            sen_target_begin = tempind == -1 ? 0 : (int)(uint32_t)__ldg(&x.RLP[tempind]);
         }
         if (un && (k == start || k == ender)) {
             if (start == ender && wrong == 0) wrong = 4;
@@ -320,7 +328,8 @@ __global__ void slots_pat1_kernel(const Pat1 *__restrict__ pat, int D1, uint32_t
     if (d < D1) cnt[d] = (uint32_t)min(pat[d].hit_count, CGX_SAMPLER_ONEGAP);
 }
 
-__global__ void __launch_bounds__(128) extract_onegap_kernel(ExtractIdx x, const Pat1 *__restrict__ pat, int D1, const uint64_t *__restrict__ hits1,
+template <class A>
+__global__ void __launch_bounds__(128) extract_onegap_kernel(ExtractIdx<A> x, const Pat1 *__restrict__ pat, int D1, const uint64_t *__restrict__ hits1,
                                                              const uint32_t *__restrict__ slot_off, uint32_t n_slots, int G, int D2, int pbits,
                                                              RuleRec *__restrict__ rec_aXb, RuleRec *__restrict__ rec_XaXb,
                                                              RuleRec *__restrict__ rec_aXbX) {
@@ -342,8 +351,8 @@ __global__ void __launch_bounds__(128) extract_onegap_kernel(ExtractIdx x, const
     unsigned target_start = 0, target_end = 0;
     bool next = true, left = true, right = true;
     int re = check_boundary(x, current_str, ender, &target_start, &target_end);
-    min_L = (target_start - (unsigned)sen_target_begin) & 0xFF;
-    max_R = (target_end - (unsigned)sen_target_begin) & 0xFF;
+    min_L = (target_start - (unsigned)sen_target_begin) & A::UNAL;
+    max_R = (target_end - (unsigned)sen_target_begin) & A::UNAL;
     if (re == 0) next = false;
     else if (re == 2) { next = false; right = false; }
     else if (re == 3) { next = false; left = false; }
@@ -352,13 +361,14 @@ __global__ void __launch_bounds__(128) extract_onegap_kernel(ExtractIdx x, const
     if (next) emit(rec_aXb, slot, 2 * G + d, target_start, target_end, (int)gap1_start, (int)gap1_end, -1, -1);
     if (startLen + endLen + 2 > CGX_MAX_RULE_SYMBOLS) return;
     const unsigned originalGapStart = gap1_start, originalGapEnd = gap1_end;
-    unsigned min_XaXb = 255, max_XaXb = 0, min_aXbX = 255, max_aXbX = 0, L, R, temp;
+    unsigned min_XaXb = A::UNAL, max_XaXb = 0, min_aXbX = A::UNAL, max_aXbX = 0, L, R;
+    typename A::word_t temp;
     for (int i = 1; firstEnd + 1 + i <= SPAN && (left || right); i++) {
         temp = (left && current_str - i >= 0) ? __ldg(&x.xw[current_str - i]) : 0u;
         if (temp & 1u) {
             next = true;
-            L = (temp >> 24) & 0xFF; R = (temp >> 16) & 0xFF;
-            if (L == 255 || R == 255) { next = false; if (i == 1) left = false; }
+            L = A::L(temp); R = A::R(temp);
+            if (L == A::UNAL || R == A::UNAL) { next = false; if (i == 1) left = false; }
             else { min_XaXb = min(min_XaXb, L); max_XaXb = max(max_XaXb, R); }
             if (next && min_XaXb > max_XaXb) return;
             if ((int)max_XaXb - (int)min_XaXb >= SPAN) { next = false; left = false; }
@@ -381,8 +391,8 @@ __global__ void __launch_bounds__(128) extract_onegap_kernel(ExtractIdx x, const
         temp = right ? __ldg(&x.xw[ender + i]) : 0u;
         if (temp & 1u) {
             next = true;
-            L = (temp >> 24) & 0xFF; R = (temp >> 16) & 0xFF;
-            if (L == 255 || R == 255) { next = false; if (i == 1) right = false; }
+            L = A::L(temp); R = A::R(temp);
+            if (L == A::UNAL || R == A::UNAL) { next = false; if (i == 1) right = false; }
             else { min_aXbX = min(min_aXbX, L); max_aXbX = max(max_aXbX, R); }
             if (next && min_aXbX > max_aXbX) return;
             if ((int)max_aXbX - (int)min_aXbX >= SPAN) { next = false; right = false; }
@@ -413,7 +423,8 @@ __global__ void slots_pat2_kernel(const Pat2 *__restrict__ pat, int D2, uint32_t
     if (d < D2) cnt[d] = (uint32_t)min(pat[d].hit_count, CGX_SAMPLER_TWOGAP);
 }
 
-__global__ void __launch_bounds__(128) extract_twogap_kernel(ExtractIdx x, const Pat2 *__restrict__ pat2, const Pat1 *__restrict__ pat1, int D2,
+template <class A>
+__global__ void __launch_bounds__(128) extract_twogap_kernel(ExtractIdx<A> x, const Pat2 *__restrict__ pat2, const Pat1 *__restrict__ pat1, int D2,
                                                              const uint64_t *__restrict__ hits2, const uint32_t *__restrict__ slot_off, uint32_t n_slots,
                                                              int G, int pbits, RuleRec *__restrict__ rec_aXbXc) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -437,6 +448,17 @@ __global__ void __launch_bounds__(128) extract_twogap_kernel(ExtractIdx x, const
         emit(rec_aXbXc, slot, G + d, ts, te, (int)g1s, (int)g1e, (int)g2s, (int)g2e);
 }
 
+// the three kernels of one batch on one field layout (align_fields.cuh)
+template <class A>
+static void launch_extract(const Index &ix, Batch &b, cudaStream_t stream, const uint32_t *ns, const uint32_t *so0, const uint32_t *so1, const uint32_t *so2,
+                           RuleRec *r0, RuleRec *r1, RuleRec *r2) {
+    const int G = b.G, D1 = b.D1, D2 = b.D2;
+    ExtractIdx<A> x{ix.sa.ptr<int32_t>(), ix.xw.ptr<typename A::word_t>(), ix.RLP.ptr<typename A::word_t>(), ix.lr.ptr<typename A::lrq_t>(), (int)ix.n};
+    if (ns[0]) PROF("extract_contig", (double)ns[0] * 56, (extract_contig_kernel<A><<<cgx_div_up(ns[0], 128), 128, 0, stream>>>(x, b.phrases.ptr<int32_t>(), G, so0, ns[0], r0, r1, r1 + ns[0], r2)));
+    if (ns[2]) PROF("extract_twogap", (double)ns[2] * 56, (extract_twogap_kernel<A><<<cgx_div_up(ns[2], 128), 128, 0, stream>>>(x, b.pat2.ptr<Pat2>(), b.pat1.ptr<Pat1>(), D2, b.hits2_sorted.ptr<uint64_t>(), so2, ns[2], G, b.pbits, r2 + ns[0])));
+    if (ns[1]) PROF("extract_onegap", (double)ns[1] * 56, (extract_onegap_kernel<A><<<cgx_div_up(ns[1], 128), 128, 0, stream>>>(x, b.pat1.ptr<Pat1>(), D1, b.hits1_sorted.ptr<uint64_t>(), so1, ns[1], G, D2, b.pbits, r1 + (size_t)2 * ns[0], r2 + (size_t)ns[0] + ns[2], r2 + (size_t)ns[0] + ns[2] + ns[1])));
+}
+
 void stage_extract(const Index &ix, Batch &b, cudaStream_t stream) {
     const int G = b.G, D1 = b.D1, D2 = b.D2;
     b.n_rec[0] = b.n_rec[1] = b.n_rec[2] = 0;
@@ -444,7 +466,6 @@ void stage_extract(const Index &ix, Batch &b, cudaStream_t stream) {
     b.n_slots[0] = b.n_slots[1] = b.n_slots[2] = 0;
     b.samples = 0;
     if (G == 0) return;
-    ExtractIdx x{ix.sa.ptr<int32_t>(), ix.xw.ptr<uint32_t>(), ix.RLP.ptr<uint32_t>(), ix.lr.ptr<uint2>(), (int)ix.n};
     uint32_t *tot = b.counters.get<uint32_t>(32);
     // slot offsets: G+1 / D1+1 / D2+1 entries (the last one = total), also read by the aggregation
     uint32_t *so0 = b.slot_off[0].get<uint32_t>((size_t)G + 2);
@@ -480,9 +501,8 @@ void stage_extract(const Index &ix, Batch &b, cudaStream_t stream) {
     // algorithmic bytes (SURVEY 8d B_ext, lower bound): per sampled occurrence its SA / hit entry and slot owner (8 B), the
     // RLP + text words of the smallest source window it must inspect (phrase + one extension token per side: 8 B x 5)
     // and the L/R bytes of a 4-token target window (2 x 4) = 56 B; emitted cells are not counted
-    if (ns[0]) PROF("extract_contig", (double)ns[0] * 56, (extract_contig_kernel<<<cgx_div_up(ns[0], 128), 128, 0, stream>>>(x, b.phrases.ptr<int32_t>(), G, so0, ns[0], r0, r1, r1 + ns[0], r2)));
-    if (ns[2]) PROF("extract_twogap", (double)ns[2] * 56, (extract_twogap_kernel<<<cgx_div_up(ns[2], 128), 128, 0, stream>>>(x, b.pat2.ptr<Pat2>(), b.pat1.ptr<Pat1>(), D2, b.hits2_sorted.ptr<uint64_t>(), so2, ns[2], G, b.pbits, r2 + ns[0])));
-    if (ns[1]) PROF("extract_onegap", (double)ns[1] * 56, (extract_onegap_kernel<<<cgx_div_up(ns[1], 128), 128, 0, stream>>>(x, b.pat1.ptr<Pat1>(), D1, b.hits1_sorted.ptr<uint64_t>(), so1, ns[1], G, D2, b.pbits, r1 + (size_t)2 * ns[0], r2 + (size_t)ns[0] + ns[2], r2 + (size_t)ns[0] + ns[2] + ns[1])));
+    if (ix.wide) launch_extract<AlignWide>(ix, b, stream, ns, so0, so1, so2, r0, r1, r2);
+    else launch_extract<AlignNarrow>(ix, b, stream, ns, so0, so1, so2, r0, r1, r2);
     b.launches += 3;
 }
 

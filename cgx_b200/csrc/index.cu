@@ -1,5 +1,6 @@
 // cgx-b200: auxiliary index arrays built once per corpus, on the GPU, after the suffix array.
 #include "index.h"
+#include "align_fields.cuh"
 #include "hash.cuh"
 #include <algorithm>
 #include <vector>
@@ -52,8 +53,9 @@ __global__ void ix_bucket_scatter_kernel(const uint64_t *__restrict__ keys, cons
 // GappyLook.cu:43-126 checkBoundaryGap = first and last token aligned; target span [min L, max R] of the
 // aligned tokens narrower than 15; and, over that target span, min L_tar / max R_tar map back exactly onto the
 // source span.  The source-side min/max is maintained incrementally while g grows.
-__global__ void ix_gap_words_kernel(const int32_t *__restrict__ str, const uint32_t *__restrict__ RLP, const uint8_t *__restrict__ L_tar,
-                                    const uint8_t *__restrict__ R_tar, size_t n, size_t m, uint32_t *__restrict__ gapw) {
+template <class A>
+__global__ void ix_gap_words_kernel(const int32_t *__restrict__ str, const typename A::word_t *__restrict__ RLP, const typename A::lr_t *__restrict__ L_tar,
+                                    const typename A::lr_t *__restrict__ R_tar, size_t n, size_t m, uint32_t *__restrict__ gapw) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t word = 0;
@@ -61,28 +63,28 @@ __global__ void ix_gap_words_kernel(const int32_t *__restrict__ str, const uint3
         int run = 1;
         while (run < 15 && str[i + run] >= 2) run++;
         word = (uint32_t)run << 16;
-        const uint32_t w0 = RLP[i];
-        const unsigned L0 = (w0 >> 24) & 0xFF, R0 = (w0 >> 16) & 0xFF;
+        const typename A::word_t w0 = RLP[i];
+        const unsigned L0 = A::L(w0), R0 = A::R(w0);
         // the unique final symbol at n-1 (Start.cu:324-326) has no alignment record and is never matched by a query
-        if (L0 != 255 && R0 != 255 && i + 1 < n) {
-            const int eos_prev = (int)i - (int)((w0 >> 8) & 0xFF) - 1;
-            const int tgt_base = eos_prev < 0 ? 0 : (int)RLP[eos_prev];
+        if (L0 != A::UNAL && R0 != A::UNAL && i + 1 < n) {
+            const int eos_prev = (int)i - (int)A::P(w0) - 1;
+            const int tgt_base = eos_prev < 0 ? 0 : (int)(uint32_t)RLP[eos_prev];
             const int src_base = eos_prev + 1;
             unsigned mn = L0, mx = R0;
             const int gmax = run < 13 ? run : 13;
             for (int g = 1; g <= gmax; g++) {
                 if (g > 1) {
-                    const uint32_t w = RLP[i + g - 1];
-                    const unsigned L = (w >> 24) & 0xFF, R = (w >> 16) & 0xFF;
-                    if (L == 255 || R == 255) continue;          // last token unaligned: this g fails, larger g may pass
+                    const typename A::word_t w = RLP[i + g - 1];
+                    const unsigned L = A::L(w), R = A::R(w);
+                    if (L == A::UNAL || R == A::UNAL) continue;          // last token unaligned: this g fails, larger g may pass
                     mn = min(mn, L); mx = max(mx, R);
                 }
                 if (mx - mn >= CGX_MAX_RULE_SPAN) break;           // the span only grows with g
                 if (tgt_base < 0 || (size_t)tgt_base + mx >= m) break;   // malformed alignment record: never consistent
-                unsigned tmn = 255, tmx = 0;
+                unsigned tmn = A::UNAL, tmx = 0;
                 for (int k = tgt_base + (int)mn; k <= tgt_base + (int)mx; k++) {
                     const unsigned L = L_tar[k], R = R_tar[k];
-                    if (L == 255 || R == 255) continue;
+                    if (L == A::UNAL || R == A::UNAL) continue;
                     tmn = min(tmn, L); tmx = max(tmx, R);
                 }
                 if (src_base + (int)tmn == (int)i && src_base + (int)tmx == (int)i + g - 1) word |= 1u << (g - 1);
@@ -100,37 +102,45 @@ __global__ void ix_jwin_kernel(const int32_t *__restrict__ b1, const int32_t *__
 
 // extraction views: xw[k] = RLP[k] | 1 where the source token is a word (>= 2), else 0 (EOS, padding; n+3 entries like str);
 // lrq[j] = range-minimum table of the target side for consistent() (ExtractPair.cu:103-133), which needs min L_tar / max R_tar
-// over a target window of at most 15 tokens, unaligned tokens skipped: level k (bits 16k..16k+15) holds {min L, max R} over
-// tokens j .. j+2^k-1, k = 0..3, with an unaligned token entered as {255, 0} (the identities of min and max).  Any window is
+// over a target window of at most 15 tokens, unaligned tokens skipped: level k holds {min L, max R} over tokens j .. j+2^k-1,
+// k = 0..3 (packing: align_fields.cuh), with an unaligned token entered as {UNAL, 0} (the identities of min and max).  Any window is
 // the union of two level-floor(log2 len) entries: two independent 8-byte loads instead of a loop of <= 15 dependent 2-byte ones.
-__global__ void ix_extract_views_kernel(const int32_t *__restrict__ str, const uint32_t *__restrict__ RLP, size_t n, const uint8_t *__restrict__ L_tar,
-                                        const uint8_t *__restrict__ R_tar, size_t m, uint32_t *__restrict__ xw, uint2 *__restrict__ lrq) {
+template <class A>
+__global__ void ix_extract_views_kernel(const int32_t *__restrict__ str, const typename A::word_t *__restrict__ RLP, size_t n,
+                                        const typename A::lr_t *__restrict__ L_tar, const typename A::lr_t *__restrict__ R_tar, size_t m,
+                                        typename A::word_t *__restrict__ xw, typename A::lrq_t *__restrict__ lrq) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n + 3) xw[i] = (i < n && str[i] >= 2) ? (RLP[i] | 1u) : 0u;
     if (i < m) {
-        unsigned mn = 255, mx = 0;
-        uint32_t w[2] = {0, 0};
+        unsigned mn = A::UNAL, mx = 0, lmn[4], lmx[4];
         int t = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             for (; t < (1 << k); t++) {
                 if (i + t >= m) continue;
                 const unsigned L = L_tar[i + t], R = R_tar[i + t];
-                if (L == 255 || R == 255) continue;
+                if (L == A::UNAL || R == A::UNAL) continue;
                 mn = min(mn, L); mx = max(mx, R);
             }
-            w[k >> 1] |= (mn | (mx << 8)) << (16 * (k & 1));
+            lmn[k] = mn; lmx[k] = mx;
         }
-        lrq[i] = make_uint2(w[0], w[1]);
+        lrq[i] = A::lrq_make(lmn, lmx);
     }
+}
+
+template <class A>
+static void build_views_t(Index &ix, cudaStream_t stream) {
+    using W = typename A::word_t;
+    using LR = typename A::lr_t;
+    const size_t cnt = ix.n + 3 > ix.m ? ix.n + 3 : ix.m;
+    ix_extract_views_kernel<A><<<cgx_div_up(cnt, 256), 256, 0, stream>>>(ix.str.ptr<int32_t>(), ix.RLP.ptr<W>(), ix.n, ix.L_tar.ptr<LR>(), ix.R_tar.ptr<LR>(), ix.m,
+                                                                          ix.xw.get<W>(ix.n + 3), ix.lr.get<typename A::lrq_t>(ix.m));
 }
 
 void build_jwin(Index &ix, cudaStream_t stream) {
     ix_jwin_kernel<<<cgx_div_up(ix.n, 256), 256, 0, stream>>>(ix.bkt[0].ptr<int32_t>(), ix.bkt[1].ptr<int32_t>(), ix.bkt[2].ptr<int32_t>(),
                                                             ix.gapw.ptr<uint32_t>(), ix.n, ix.jwin.get<int4>(ix.n));
-    const size_t cnt = ix.n + 3 > ix.m ? ix.n + 3 : ix.m;
-    ix_extract_views_kernel<<<cgx_div_up(cnt, 256), 256, 0, stream>>>(ix.str.ptr<int32_t>(), ix.RLP.ptr<uint32_t>(), ix.n, ix.L_tar.ptr<uint8_t>(),
-                                                                     ix.R_tar.ptr<uint8_t>(), ix.m, ix.xw.get<uint32_t>(ix.n + 3), ix.lr.get<uint2>(ix.m));
+    if (ix.wide) build_views_t<AlignWide>(ix, stream); else build_views_t<AlignNarrow>(ix, stream);
     CUDA_CHECK(cudaStreamSynchronize(stream));
 }
 
@@ -182,7 +192,9 @@ void build_index_aux(Index &ix, SaWorkspace &ws, cudaStream_t stream, int *launc
     pick_frequent(counts, ix.maxtok, ix.freq_list, flag);
     CUDA_CHECK(cudaMemcpyAsync(ix.freq_flag.get<uint8_t>(nt), flag.data(), nt, cudaMemcpyHostToDevice, stream));
     exclusive_scan_u32(ts, ts, nt, nullptr, stream, ws.scan, 0, launches);
-    ix_gap_words_kernel<<<cgx_div_up(n, 128), 128, 0, stream>>>(str, ix.RLP.ptr<uint32_t>(), ix.L_tar.ptr<uint8_t>(), ix.R_tar.ptr<uint8_t>(), n, ix.m,
+    if (ix.wide) ix_gap_words_kernel<AlignWide><<<cgx_div_up(n, 128), 128, 0, stream>>>(str, ix.RLP.ptr<uint64_t>(), ix.L_tar.ptr<uint16_t>(), ix.R_tar.ptr<uint16_t>(), n, ix.m,
+                                                              ix.gapw.get<uint32_t>(n));
+    else ix_gap_words_kernel<AlignNarrow><<<cgx_div_up(n, 128), 128, 0, stream>>>(str, ix.RLP.ptr<uint32_t>(), ix.L_tar.ptr<uint8_t>(), ix.R_tar.ptr<uint8_t>(), n, ix.m,
                                                               ix.gapw.get<uint32_t>(n));
     if (launches) *launches += 1;
     // position-sorted occurrence lists of every 1-, 2- and 3-gram

@@ -212,11 +212,18 @@ class GrammarExtractor:
     def build_index(self, layout):
         s = np.ascontiguousarray(layout["str"], dtype=np.int32)
         t = np.ascontiguousarray(layout["tgt"], dtype=np.int32)
-        rlp = np.ascontiguousarray(layout["RLP"], dtype=np.uint32)
-        lt = np.ascontiguousarray(layout["L_tar"], dtype=np.uint8)
-        rt = np.ascontiguousarray(layout["R_tar"], dtype=np.uint8)
-        self._check(self.L.cgx_index_build(self.h, _p(s, C.c_int32), int(layout["n"]), _p(t, C.c_int32), int(layout["m"]), _p(rlp, C.c_uint32),
-                                           _p(lt, C.c_uint8), _p(rt, C.c_uint8)), "cgx_index_build")
+        if layout.get("wide"):        # 16-bit alignment fields: a sentence of 255 tokens or more (include/cgx_b200.h cgx_index_build_wide)
+            rlp = np.ascontiguousarray(layout["RLP"], dtype=np.uint64)
+            lt = np.ascontiguousarray(layout["L_tar"], dtype=np.uint16)
+            rt = np.ascontiguousarray(layout["R_tar"], dtype=np.uint16)
+            self._check(self.L.cgx_index_build_wide(self.h, _p(s, C.c_int32), int(layout["n"]), _p(t, C.c_int32), int(layout["m"]), _p(rlp, C.c_uint64),
+                                                    _p(lt, C.c_uint16), _p(rt, C.c_uint16)), "cgx_index_build_wide")
+        else:
+            rlp = np.ascontiguousarray(layout["RLP"], dtype=np.uint32)
+            lt = np.ascontiguousarray(layout["L_tar"], dtype=np.uint8)
+            rt = np.ascontiguousarray(layout["R_tar"], dtype=np.uint8)
+            self._check(self.L.cgx_index_build(self.h, _p(s, C.c_int32), int(layout["n"]), _p(t, C.c_int32), int(layout["m"]), _p(rlp, C.c_uint32),
+                                               _p(lt, C.c_uint8), _p(rt, C.c_uint8)), "cgx_index_build")
         if "lex_f" in layout:
             self.load_lex(layout["lex_f"], layout["lex_e"], layout["lex_v1"], layout["lex_v2"])
         return self.index_info()

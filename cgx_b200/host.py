@@ -18,7 +18,8 @@ class Side(C.Structure):
 
 
 class Align(C.Structure):
-    _fields_ = [("RLP", C.POINTER(C.c_uint32)), ("L_tar", C.POINTER(C.c_uint8)), ("R_tar", C.POINTER(C.c_uint8))]
+    _fields_ = [("RLP", C.POINTER(C.c_uint32)), ("L_tar", C.POINTER(C.c_uint8)), ("R_tar", C.POINTER(C.c_uint8)), ("wide", C.c_int),
+                ("RLP64", C.POINTER(C.c_uint64)), ("L_tar16", C.POINTER(C.c_uint16)), ("R_tar16", C.POINTER(C.c_uint16))]
 
 
 class Lex(C.Structure):
@@ -83,8 +84,13 @@ class HostCorpus:
 
     def layout(self):
         n, m = int(self.src.n), int(self.tgt.n)
+        wide = bool(self.al.wide)
+        if wide:      # a sentence of 255 tokens or more: 16-bit alignment fields (cgx_index_build_wide)
+            align = dict(RLP=_arr(self.al.RLP64, n, np.uint64), L_tar=_arr(self.al.L_tar16, m, np.uint16), R_tar=_arr(self.al.R_tar16, m, np.uint16))
+        else:
+            align = dict(RLP=_arr(self.al.RLP, n, np.uint32), L_tar=_arr(self.al.L_tar, m, np.uint8), R_tar=_arr(self.al.R_tar, m, np.uint8))
         return dict(str=_arr(self.src.tok, n + 3, np.int32), n=n, tgt=_arr(self.tgt.tok, m + 3, np.int32), m=m, P=_arr(self.src.P, n, np.uint8),
-                    RLP=_arr(self.al.RLP, n, np.uint32), L_tar=_arr(self.al.L_tar, m, np.uint8), R_tar=_arr(self.al.R_tar, m, np.uint8),
+                    wide=wide, **align,
                     src_sentenceind=_arr(self.src.sentenceind, self.src.n_sent + 1, np.int32),
                     tgt_sentenceind=_arr(self.tgt.sentenceind, self.tgt.n_sent + 1, np.int32),
                     lex_f=_arr(self.lex.f, int(self.lex.count), np.int32), lex_e=_arr(self.lex.e, int(self.lex.count), np.int32),

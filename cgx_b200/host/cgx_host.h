@@ -33,6 +33,9 @@ typedef struct {
 typedef struct {
     uint32_t *RLP;       /* n */
     uint8_t *L_tar, *R_tar; /* m */
+    int wide;            /* 1: the corpus has a sentence the 8-bit fields cannot hold; the three arrays below are set instead */
+    uint64_t *RLP64;     /* n: L << 48 | R << 32 | P << 16 (65535 = unaligned), target sentence offset at an EOS */
+    uint16_t *L_tar16, *R_tar16; /* m */
 } cgxh_align_t;
 
 typedef struct {

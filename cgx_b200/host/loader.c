@@ -144,18 +144,24 @@ void cgxh_side_free(cgxh_side_t *s) {
     memset(s, 0, sizeof(*s));
 }
 
-/* ExtractPair.cu:2639-2739 */
+/* ExtractPair.cu:2639-2739.  The reference keeps the aligned spans and the position in the sentence in 8 bits and exits on an
+ * alignment point at index 255 or beyond ("Not possible, too long sentence", :2683).  Here the spans are collected in 16 bits;
+ * a corpus that fits the reference's layout gets exactly that layout (out->wide = 0: RLP, L_tar, R_tar), any other the 16-bit
+ * one (out->wide = 1: RLP64 = L << 48 | R << 32 | P << 16, L_tar16, R_tar16, 65535 = unaligned; cgx_index_build_wide). */
 int cgxh_alignment_load(const char *path, const cgxh_side_t *src, const cgxh_side_t *tgt, cgxh_align_t *out) {
     memset(out, 0, sizeof(*out));
     FILE *fh = fopen(path, "r");
     if (!fh) { fprintf(stderr, "Can not open reference file \"%s\"\n", path); return 1; }
     const int64_t n = src->n, m = tgt->n;
-    uint8_t *Lt = (uint8_t *)malloc((size_t)m), *Rt = (uint8_t *)malloc((size_t)m);
-    uint8_t *Ls = (uint8_t *)malloc((size_t)n), *Rs = (uint8_t *)malloc((size_t)n);
-    memset(Lt, 255, (size_t)m); memset(Rt, 255, (size_t)m); memset(Ls, 255, (size_t)n); memset(Rs, 255, (size_t)n);
+    uint16_t *Lt = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)m), *Rt = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)m);
+    uint16_t *Ls = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)n), *Rs = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)n);
+    memset(Lt, 255, sizeof(uint16_t) * (size_t)m); memset(Rt, 255, sizeof(uint16_t) * (size_t)m);
+    memset(Ls, 255, sizeof(uint16_t) * (size_t)n); memset(Rs, 255, sizeof(uint16_t) * (size_t)n);
     char *line = NULL; size_t cap = 0;
     int32_t qcount = -1;
-    int rc = 0;
+    int rc = 0, wide = 0;
+    for (int32_t q = 0; q < src->n_sent; q++)                      /* a sentence the 8-bit position counter cannot count (Start.cu:269,300) */
+        if (src->sentenceind[q + 1] - src->sentenceind[q] - 1 > 255) wide = 1;
     while (getline(&line, &cap, fh) != -1) {
         qcount++;
         if (qcount >= src->n_sent || qcount >= tgt->n_sent) { fprintf(stderr, "alignment file has more lines than the corpus; ignoring the rest\n"); break; }
@@ -167,38 +173,57 @@ int cgxh_alignment_load(const char *path, const cgxh_side_t *src, const cgxh_sid
             t = strtok(NULL, " -");
             if (!t) { fprintf(stderr, "Not possible!\n"); rc = 2; goto done; }
             int t_no = atoi(t);
-            if (s_no >= 255 || t_no >= 255 || s_no < 0 || t_no < 0) { fprintf(stderr, "Not possible, too long sentence\n"); rc = 3; goto done; }
+            if (s_no >= 65535 || t_no >= 65535 || s_no < 0 || t_no < 0) { fprintf(stderr, "Not possible, too long sentence\n"); rc = 3; goto done; }
+            if (s_no >= 255 || t_no >= 255) wide = 1;
             int64_t si = (int64_t)src->sentenceind[qcount] + s_no, ti = (int64_t)tgt->sentenceind[qcount] + t_no;
             if (si >= n || ti >= m) { fprintf(stderr, "alignment point outside the corpus at line %d\n", qcount); rc = 4; goto done; }
-            if (Ls[si] == 255 || Rs[si] == 255) { Ls[si] = (uint8_t)t_no; Rs[si] = (uint8_t)t_no; }
-            else if (t_no > Rs[si]) Rs[si] = (uint8_t)t_no;
-            else if (t_no < Ls[si]) Ls[si] = (uint8_t)t_no;
-            if (Lt[ti] == 255 || Rt[ti] == 255) { Lt[ti] = (uint8_t)s_no; Rt[ti] = (uint8_t)s_no; }
-            else if (s_no > Rt[ti]) Rt[ti] = (uint8_t)s_no;
-            else if (s_no < Lt[ti]) Lt[ti] = (uint8_t)s_no;
+            if (Ls[si] == 65535 || Rs[si] == 65535) { Ls[si] = (uint16_t)t_no; Rs[si] = (uint16_t)t_no; }
+            else if (t_no > Rs[si]) Rs[si] = (uint16_t)t_no;
+            else if (t_no < Ls[si]) Ls[si] = (uint16_t)t_no;
+            if (Lt[ti] == 65535 || Rt[ti] == 65535) { Lt[ti] = (uint16_t)s_no; Rt[ti] = (uint16_t)s_no; }
+            else if (s_no > Rt[ti]) Rt[ti] = (uint16_t)s_no;
+            else if (s_no < Lt[ti]) Lt[ti] = (uint16_t)s_no;
             t = strtok(NULL, " -");
         }
     }
-    {
+    out->wide = wide;
+    if (wide) {
+        uint64_t *RLP = (uint64_t *)calloc((size_t)n, sizeof(uint64_t));
+        int32_t q = 1;
+        int64_t sent_start = 0;
+        for (int64_t i = 0; i < n - 1; i++) {
+            if (q <= src->n_sent && i == (int64_t)src->sentenceind[q] - 1) {
+                RLP[i] = (uint64_t)(uint32_t)(q <= tgt->n_sent ? tgt->sentenceind[q] : tgt->sentenceind[tgt->n_sent]);
+                sent_start = src->sentenceind[q];
+                q++;
+            } else {
+                const int64_t P = q <= src->n_sent ? i - sent_start : 0;      /* the trailer after the last sentence counts from 0 (Start.cu:324) */
+                RLP[i] = ((uint64_t)Ls[i] << 48) | ((uint64_t)Rs[i] << 32) | ((uint64_t)(P & 0xFFFF) << 16);
+            }
+        }
+        out->RLP64 = RLP; out->L_tar16 = Lt; out->R_tar16 = Rt;
+        Lt = Rt = NULL;
+    } else {
         uint32_t *RLP = (uint32_t *)calloc((size_t)n, sizeof(uint32_t));
+        uint8_t *Lt8 = (uint8_t *)malloc((size_t)m), *Rt8 = (uint8_t *)malloc((size_t)m);
+        for (int64_t j = 0; j < m; j++) { Lt8[j] = (uint8_t)(Lt[j] == 65535 ? 255 : Lt[j]); Rt8[j] = (uint8_t)(Rt[j] == 65535 ? 255 : Rt[j]); }
         int32_t q = 1;
         for (int64_t i = 0; i < n - 1; i++) {                    /* :2721-2731 */
             if (q <= src->n_sent && i == (int64_t)src->sentenceind[q] - 1) {
                 RLP[i] = (uint32_t)(q <= tgt->n_sent ? tgt->sentenceind[q] : tgt->sentenceind[tgt->n_sent]);
                 q++;
             } else {
-                RLP[i] = ((uint32_t)Ls[i] << 24) | ((uint32_t)Rs[i] << 16) | ((uint32_t)src->P[i] << 8);
+                const uint32_t L8 = Ls[i] == 65535 ? 255u : Ls[i], R8 = Rs[i] == 65535 ? 255u : Rs[i];
+                RLP[i] = (L8 << 24) | (R8 << 16) | ((uint32_t)src->P[i] << 8);
             }
         }
-        out->RLP = RLP; out->L_tar = Lt; out->R_tar = Rt;
-        Lt = Rt = NULL;
+        out->RLP = RLP; out->L_tar = Lt8; out->R_tar = Rt8;
     }
 done:
     free(line); fclose(fh); free(Ls); free(Rs); free(Lt); free(Rt);
     return rc;
 }
-
-void cgxh_align_free(cgxh_align_t *a) { free(a->RLP); free(a->L_tar); free(a->R_tar); memset(a, 0, sizeof(*a)); }
+void cgxh_align_free(cgxh_align_t *a) { free(a->RLP); free(a->L_tar); free(a->R_tar); free(a->RLP64); free(a->L_tar16); free(a->R_tar16); memset(a, 0, sizeof(*a)); }
 
 /* ExtractPair.cu:2463-2519: four white-space separated columns; words unknown to the corpus are skipped
  * unless they are the literal NULL, which maps to id -1. */

@@ -217,7 +217,9 @@ int cgxh_run(const cgxh_options_t *opt) {
         if (cgx_index_load(ctx[0], opt->index_file)) { fprintf(stderr, "cgx_index_load: %s\n", cgx_last_error(ctx[0])); return 1; }
         fprintf(stderr, "index loaded from %s\n", opt->index_file);
     } else {
-        if (cgx_index_build(ctx[0], src.tok, src.n, tgt.tok, tgt.n, al.RLP, al.L_tar, al.R_tar)) { fprintf(stderr, "cgx_index_build: %s\n", cgx_last_error(ctx[0])); return 1; }
+        if (al.wide) fprintf(stderr, "sentences of 255 tokens and more: 16-bit alignment fields\n");
+        if (al.wide ? cgx_index_build_wide(ctx[0], src.tok, src.n, tgt.tok, tgt.n, al.RLP64, al.L_tar16, al.R_tar16)
+                    : cgx_index_build(ctx[0], src.tok, src.n, tgt.tok, tgt.n, al.RLP, al.L_tar, al.R_tar)) { fprintf(stderr, "cgx_index_build: %s\n", cgx_last_error(ctx[0])); return 1; }
         if (cgx_lex_load(ctx[0], lex.f, lex.e, lex.v1, lex.v2, lex.count)) { fprintf(stderr, "cgx_lex_load: %s\n", cgx_last_error(ctx[0])); return 1; }
         if (opt->index_file) {
             if (cgx_index_save(ctx[0], opt->index_file)) { fprintf(stderr, "cgx_index_save: %s\n", cgx_last_error(ctx[0])); return 1; }

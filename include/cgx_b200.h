@@ -49,6 +49,15 @@ int cgx_version(void);
 int cgx_index_build(cgx_ctx_t *ctx, const int32_t *src, int64_t n, const int32_t *tgt, int64_t m,
                     const uint32_t *RLP, const uint8_t *L_tar, const uint8_t *R_tar);
 
+/* The same for corpora with sentences of 255 tokens and more, which the reference refuses ("Not possible, too long sentence",
+ * ExtractPair.cu:2683; uint8_t position counters, Start.cu:269).  The alignment fields are 16 bits wide:
+ *   RLP64[i] = L << 48 | R << 32 | P << 16 for a source token (65535 = unaligned), the target sentence offset at an EOS;
+ *   L_tar16 / R_tar16 = min / max aligned source index per target token (65535 = unaligned).
+ * Same algorithm, same results as cgx_index_build on a corpus that fits 8 bits (lifted limit).
+ * CGX_FORCE_WIDE=1 makes cgx_index_build widen its input and take this path (tests). */
+int cgx_index_build_wide(cgx_ctx_t *ctx, const int32_t *src, int64_t n, const int32_t *tgt, int64_t m, const uint64_t *RLP64,
+                         const uint16_t *L_tar16, const uint16_t *R_tar16);
+
 /* Replaces initWordPossibilityIntKey (ExtractPair.cu:2442-2554): f/e ids (-1 = NULL word), v1 feeds
  * MaxLexEgivenF, v2 feeds MaxLexFgivenE.  Sorted on the GPU by (f, e). */
 int cgx_lex_load(cgx_ctx_t *ctx, const int32_t *f, const int32_t *e, const float *v1, const float *v2, int64_t count);
@@ -74,6 +83,7 @@ typedef struct {
     int64_t n, m, lex_count;
     int32_t max_token;
     int32_t freq_list[100];
+    int32_t wide;             /* 1: 16-bit alignment fields (cgx_index_build_wide): RLP is 8 bytes per token, L_tar / R_tar 2 bytes */
     void *str, *sa, *inv1, *inv2, *inv3, *bkt1, *bkt2, *bkt3, *tok_start, *RLP, *L_tar, *R_tar, *tgt, *freq_flag, *gapw, *lex_key, *lex_v1, *lex_v2;
 } cgx_index_arrays_t;
 int cgx_index_export(cgx_ctx_t *ctx, cgx_index_arrays_t *out);            /* pointers stay owned by ctx */

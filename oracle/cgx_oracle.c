@@ -17,6 +17,25 @@
 #include <string.h>
 #include <ctype.h>
 
+/* Width of the alignment fields.  The reference keeps the aligned span of a token and its position in the sentence in 8 bits
+ * each (255 = unaligned; RLP = L << 24 | R << 16 | P << 8) and exits on any sentence of 255 tokens or more
+ * (ExtractPair.cu:2683, Start.cu:269).  Built with -DORC_WIDE the SAME algorithm runs on 16-bit fields (65535 = unaligned,
+ * RLP = L << 48 | R << 32 | P << 16; the word at an EOS still holds the target sentence offset): SURVEY.md 8f, lifted limit.
+ * On a corpus the narrow build accepts, both builds give identical results (tests/test_host_cpu.py). */
+#ifdef ORC_WIDE
+#define UNAL 65535
+#define RLP_L(t) ((lr_t)(((t) >> 48) & 0xFFFF))
+#define RLP_R(t) ((lr_t)(((t) >> 32) & 0xFFFF))
+#define RLP_P(t) ((int)(((t) >> 16) & 0xFFFF))
+#define RLP_PACK(L, R, P) (((rlp_t)(L) << 48) | ((rlp_t)(R) << 32) | ((rlp_t)(P) << 16))
+#else
+#define UNAL 255
+#define RLP_L(t) ((lr_t)(((t) >> 24) & 0xFF))
+#define RLP_R(t) ((lr_t)(((t) >> 16) & 0xFF))
+#define RLP_P(t) ((int)(((t) >> 8) & 0xFF))
+#define RLP_PACK(L, R, P) (((rlp_t)(L) << 24) | ((rlp_t)(R) << 16) | ((rlp_t)(P) << 8))
+#endif
+
 /* ------------------------------------------------------------------------------------------ */
 /* small utilities                                                                              */
 /* ------------------------------------------------------------------------------------------ */
@@ -76,7 +95,7 @@ static void rv_push(rvec *a, rec_t r) {
 struct orc_s {
     int32_t n, m;
     int32_t *str, *tgt;
-    uint32_t *RLP; uint8_t *L_tar, *R_tar;
+    rlp_t *RLP; lr_t *L_tar, *R_tar;
     int32_t *sa;
     /* text-mode extras */
     char **svocab, **tvocab; int32_t sv, tv;      /* id -> name */
@@ -117,7 +136,7 @@ struct orc_s {
 /* Start.cu:240-380 initRefSet / :142-238 initRefTargetSet.  ids = 2 + first appearance,
  * EOS = 1 after every line, trailer "1, last+1", three zeros. */
 static int load_side(const char *path, smap *map, char ***vocab_out, int32_t *nvocab, int32_t **tok_out, int32_t *n_out,
-                     uint8_t **P_out, int32_t **sent_out, int32_t *nsent_out) {
+                     lr_t **P_out, int32_t **sent_out, int32_t *nsent_out) {
     FILE *fh = fopen(path, "r");
     if (!fh) { fprintf(stderr, "oracle: cannot open %s\n", path); return 0; }
     ivec tok = {0}, sent = {0}; ivec Pv = {0};
@@ -141,7 +160,7 @@ static int load_side(const char *path, smap *map, char ***vocab_out, int32_t *nv
                 if (id >= vcap) { vocab = (char **)realloc(vocab, sizeof(char *) * vcap * 2); memset(vocab + vcap, 0, sizeof(char *) * vcap); vcap *= 2; }
                 vocab[id] = cp;
             }
-            iv_push(&tok, id); iv_push(&Pv, local & 0xFF); local++;
+            iv_push(&tok, id); iv_push(&Pv, local & UNAL); local++;
             t = strtok(NULL, " ");
         }
         iv_push(&tok, 1); iv_push(&Pv, 0);
@@ -154,7 +173,7 @@ static int load_side(const char *path, smap *map, char ***vocab_out, int32_t *nv
     int32_t n = (int32_t)tok.n;
     iv_push(&tok, 0); iv_push(&tok, 0); iv_push(&tok, 0);
     *tok_out = tok.v; *n_out = n;
-    if (P_out) { uint8_t *P = (uint8_t *)malloc(n); for (int32_t i = 0; i < n; i++) P[i] = (uint8_t)Pv.v[i]; *P_out = P; }
+    if (P_out) { lr_t *P = (lr_t *)malloc(sizeof(lr_t) * (size_t)n); for (int32_t i = 0; i < n; i++) P[i] = (lr_t)Pv.v[i]; *P_out = P; }
     iv_free(&Pv);
     *sent_out = sent.v; *nsent_out = (int32_t)sent.n - 1;
     *vocab_out = vocab; *nvocab = (int32_t)map->cnt + 2;
@@ -162,12 +181,12 @@ static int load_side(const char *path, smap *map, char ***vocab_out, int32_t *nv
 }
 
 /* ExtractPair.cu:2639-2739 initAlignment */
-static int load_alignment(const char *path, int32_t n, int32_t m, const uint8_t *P, const int32_t *ssent, int32_t ns,
-                          const int32_t *tsent, int32_t nt, uint32_t **RLP_out, uint8_t **L_out, uint8_t **R_out) {
+static int load_alignment(const char *path, int32_t n, int32_t m, const lr_t *P, const int32_t *ssent, int32_t ns,
+                          const int32_t *tsent, int32_t nt, rlp_t **RLP_out, lr_t **L_out, lr_t **R_out) {
     FILE *fh = fopen(path, "r");
     if (!fh) { fprintf(stderr, "oracle: cannot open %s\n", path); return 0; }
-    uint8_t *Lt = (uint8_t *)malloc(m), *Rt = (uint8_t *)malloc(m), *Ls = (uint8_t *)malloc(n), *Rs = (uint8_t *)malloc(n);
-    memset(Lt, 255, m); memset(Rt, 255, m); memset(Ls, 255, n); memset(Rs, 255, n);
+    lr_t *Lt = (lr_t *)malloc(sizeof(lr_t) * (size_t)m), *Rt = (lr_t *)malloc(sizeof(lr_t) * (size_t)m), *Ls = (lr_t *)malloc(sizeof(lr_t) * (size_t)n), *Rs = (lr_t *)malloc(sizeof(lr_t) * (size_t)n);
+    memset(Lt, 255, sizeof(lr_t) * (size_t)m); memset(Rt, 255, sizeof(lr_t) * (size_t)m); memset(Ls, 255, sizeof(lr_t) * (size_t)n); memset(Rs, 255, sizeof(lr_t) * (size_t)n);
     char *line = NULL; size_t cap = 0; int qcount = -1;
     while (getline(&line, &cap, fh) != -1) {
         qcount++;
@@ -180,23 +199,23 @@ static int load_alignment(const char *path, int32_t n, int32_t m, const uint8_t 
             t = strtok(NULL, " -");
             if (!t) { fprintf(stderr, "oracle: odd alignment line %d\n", qcount); return 0; }
             int t_no = atoi(t);
-            if (s_no >= 255 || t_no >= 255 || s_no < 0 || t_no < 0) { fprintf(stderr, "oracle: sentence too long\n"); return 0; }
+            if (s_no >= UNAL || t_no >= UNAL || s_no < 0 || t_no < 0) { fprintf(stderr, "oracle: sentence too long\n"); return 0; }
             int si = ssent[qcount] + s_no, ti = tsent[qcount] + t_no;
-            if (Ls[si] == 255 || Rs[si] == 255) { Ls[si] = (uint8_t)t_no; Rs[si] = (uint8_t)t_no; }
-            else if (t_no > Rs[si]) Rs[si] = (uint8_t)t_no;
-            else if (t_no < Ls[si]) Ls[si] = (uint8_t)t_no;
-            if (Lt[ti] == 255 || Rt[ti] == 255) { Lt[ti] = (uint8_t)s_no; Rt[ti] = (uint8_t)s_no; }
-            else if (s_no > Rt[ti]) Rt[ti] = (uint8_t)s_no;
-            else if (s_no < Lt[ti]) Lt[ti] = (uint8_t)s_no;
+            if (Ls[si] == UNAL || Rs[si] == UNAL) { Ls[si] = (lr_t)t_no; Rs[si] = (lr_t)t_no; }
+            else if (t_no > Rs[si]) Rs[si] = (lr_t)t_no;
+            else if (t_no < Ls[si]) Ls[si] = (lr_t)t_no;
+            if (Lt[ti] == UNAL || Rt[ti] == UNAL) { Lt[ti] = (lr_t)s_no; Rt[ti] = (lr_t)s_no; }
+            else if (s_no > Rt[ti]) Rt[ti] = (lr_t)s_no;
+            else if (s_no < Lt[ti]) Lt[ti] = (lr_t)s_no;
             t = strtok(NULL, " -");
         }
     }
     free(line); fclose(fh);
-    uint32_t *RLP = (uint32_t *)calloc(n, sizeof(uint32_t));
+    rlp_t *RLP = (rlp_t *)calloc(n, sizeof(rlp_t));
     int q = 1;
     for (int32_t i = 0; i < n - 1; i++) {                         /* :2721 */
-        if (q <= ns && i == ssent[q] - 1) { RLP[i] = (uint32_t)tsent[q]; q++; }
-        else RLP[i] = ((uint32_t)Ls[i] << 24) | ((uint32_t)Rs[i] << 16) | ((uint32_t)P[i] << 8);
+        if (q <= ns && i == ssent[q] - 1) { RLP[i] = (rlp_t)(uint32_t)tsent[q]; q++; }
+        else RLP[i] = RLP_PACK(Ls[i], Rs[i], P[i]);
     }
     free(Ls); free(Rs);
     *RLP_out = RLP; *L_out = Lt; *R_out = Rt;
@@ -254,24 +273,26 @@ static float lex_get(const orc_t *o, int32_t f, int32_t e, int one) {
     return 0.0f;
 }
 
+int orc_is_wide(void) { return UNAL != 255; }
+
 /* ------------------------------------------------------------------------------------------ */
-orc_t *orc_create(const int32_t *str, int32_t n, const int32_t *tgt, int32_t m, const uint32_t *RLP, const uint8_t *L_tar,
-                  const uint8_t *R_tar, const int32_t *lex_f, const int32_t *lex_e, const float *lex_v1, const float *lex_v2,
+orc_t *orc_create(const int32_t *str, int32_t n, const int32_t *tgt, int32_t m, const rlp_t *RLP, const lr_t *L_tar,
+                  const lr_t *R_tar, const int32_t *lex_f, const int32_t *lex_e, const float *lex_v1, const float *lex_v2,
                   int32_t lex_count) {
     orc_t *o = (orc_t *)calloc(1, sizeof(orc_t));
     o->n = n; o->m = m;
     o->str = (int32_t *)malloc(sizeof(int32_t) * ((size_t)n + 3)); memcpy(o->str, str, sizeof(int32_t) * ((size_t)n + 3));
     o->tgt = (int32_t *)malloc(sizeof(int32_t) * ((size_t)m + 3)); memcpy(o->tgt, tgt, sizeof(int32_t) * ((size_t)m + 3));
-    o->RLP = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)n); memcpy(o->RLP, RLP, sizeof(uint32_t) * (size_t)n);
-    o->L_tar = (uint8_t *)malloc(m); memcpy(o->L_tar, L_tar, m);
-    o->R_tar = (uint8_t *)malloc(m); memcpy(o->R_tar, R_tar, m);
+    o->RLP = (rlp_t *)malloc(sizeof(rlp_t) * (size_t)n); memcpy(o->RLP, RLP, sizeof(rlp_t) * (size_t)n);
+    o->L_tar = (lr_t *)malloc(sizeof(lr_t) * (size_t)m); memcpy(o->L_tar, L_tar, sizeof(lr_t) * (size_t)m);
+    o->R_tar = (lr_t *)malloc(sizeof(lr_t) * (size_t)m); memcpy(o->R_tar, R_tar, sizeof(lr_t) * (size_t)m);
     set_lex(o, lex_f, lex_e, lex_v1, lex_v2, lex_count);
     return o;
 }
 
 orc_t *orc_create_from_files(const char *src, const char *tgt, const char *align, const char *lex) {
     orc_t *o = (orc_t *)calloc(1, sizeof(orc_t));
-    uint8_t *P = NULL; int32_t *ssent = NULL, *tsent = NULL; int32_t ns = 0, nt = 0;
+    lr_t *P = NULL; int32_t *ssent = NULL, *tsent = NULL; int32_t ns = 0, nt = 0;
     if (!load_side(src, &o->smap_src, &o->svocab, &o->sv, &o->str, &o->n, &P, &ssent, &ns)) return NULL;
     if (!load_side(tgt, &o->smap_tgt, &o->tvocab, &o->tv, &o->tgt, &o->m, NULL, &tsent, &nt)) return NULL;
     o->have_vocab = 1;
@@ -328,16 +349,16 @@ void orc_build_sa(orc_t *o) {
 /* ------------------------------------------------------------------------------------------ */
 /* alignment-consistency helpers                                                                */
 /* ------------------------------------------------------------------------------------------ */
-#define RL(o, k) (((o)->RLP[k] >> 24) & 0xFF)
-#define RR(o, k) (((o)->RLP[k] >> 16) & 0xFF)
-#define RP(o, k) (((o)->RLP[k] >> 8) & 0xFF)
+#define RL(o, k) RLP_L((o)->RLP[k])
+#define RR(o, k) RLP_R((o)->RLP[k])
+#define RP(o, k) RLP_P((o)->RLP[k])
 
 /* ExtractPair.cu:103-133 consistent */
 static int consistent(const orc_t *o, int start, int end, int start_chk, int end_chk, int startpos_source) {
-    unsigned char min_L = 255, max_R = 0;
+    lr_t min_L = UNAL, max_R = 0;
     for (int k = start; k <= end; k++) {
-        unsigned char L = o->L_tar[k], R = o->R_tar[k];
-        if (L == 255 || R == 255) { }
+        lr_t L = o->L_tar[k], R = o->R_tar[k];
+        if (L == UNAL || R == UNAL) { }
         else if (k == start) { min_L = L; max_R = R; }
         else { if (min_L > L) min_L = L; if (max_R < R) max_R = R; }
     }
@@ -347,13 +368,13 @@ static int consistent(const orc_t *o, int start, int end, int start_chk, int end
 
 /* GappyLook.cu:43-126 checkBoundaryGap */
 static int checkBoundaryGap(const orc_t *o, unsigned int start, unsigned int ender) {
-    unsigned char L, R, min_L = 255, max_R = 0; int sen_target_begin = -1, tempind = 0;
+    lr_t L, R, min_L = UNAL, max_R = 0; int sen_target_begin = -1, tempind = 0;
     for (int k = (int)start; k <= (int)ender; k++) {
-        uint32_t temp = o->RLP[k]; L = (temp >> 24) & 0xFF; R = (temp >> 16) & 0xFF;
-        if ((L == 255 || R == 255) && (k == (int)start || k == (int)ender)) return 0;
-        else if (L == 255 || R == 255) { }
+        rlp_t temp = o->RLP[k]; L = RLP_L(temp); R = RLP_R(temp);
+        if ((L == UNAL || R == UNAL) && (k == (int)start || k == (int)ender)) return 0;
+        else if (L == UNAL || R == UNAL) { }
         else if (k == (int)start) {
-            tempind = k - (int)((temp >> 8) & 0xFF) - 1;
+            tempind = k - RLP_P(temp) - 1;
             sen_target_begin = tempind == -1 ? 0 : (int)o->RLP[tempind];
             min_L = L; max_R = R;
         } else { if (min_L > L) min_L = L; if (max_R < R) max_R = R; }
@@ -361,10 +382,10 @@ static int checkBoundaryGap(const orc_t *o, unsigned int start, unsigned int end
     if (min_L <= max_R && max_R - min_L < ORC_MAX_RULE_SPAN) {
         tempind++;
         int target_start = min_L + sen_target_begin, target_end = max_R + sen_target_begin;
-        min_L = 255; max_R = 0;
+        min_L = UNAL; max_R = 0;
         for (int k = target_start; k <= target_end; k++) {
             L = o->L_tar[k]; R = o->R_tar[k];
-            if (L == 255 || R == 255) { }
+            if (L == UNAL || R == UNAL) { }
             else if (k == target_start) { min_L = L; max_R = R; }
             else { if (min_L > L) min_L = L; if (max_R < R) max_R = R; }
         }
@@ -375,16 +396,16 @@ static int checkBoundaryGap(const orc_t *o, unsigned int start, unsigned int end
 }
 
 /* ExtractPair.cu:135-194 checkBoundaryFast */
-static int checkBoundaryFast(const orc_t *o, unsigned int start, unsigned int ender, unsigned char *min_LL, unsigned char *max_RR,
+static int checkBoundaryFast(const orc_t *o, unsigned int start, unsigned int ender, lr_t *min_LL, lr_t *max_RR,
                              int *sen_target_begin, int *tempind) {
-    unsigned char L, R, min_L = 255, max_R = 0;
+    lr_t L, R, min_L = UNAL, max_R = 0;
     *sen_target_begin = -1; *tempind = 0;
     for (int k = (int)start; k <= (int)ender; k++) {
-        uint32_t temp = o->RLP[k]; L = (temp >> 24) & 0xFF; R = (temp >> 16) & 0xFF;
-        if ((L == 255 || R == 255) && (k == (int)start || k == (int)ender)) return 0;
-        else if (L == 255 || R == 255) { }
+        rlp_t temp = o->RLP[k]; L = RLP_L(temp); R = RLP_R(temp);
+        if ((L == UNAL || R == UNAL) && (k == (int)start || k == (int)ender)) return 0;
+        else if (L == UNAL || R == UNAL) { }
         else if (k == (int)start) {
-            *tempind = k - (int)((temp >> 8) & 0xFF) - 1;
+            *tempind = k - RLP_P(temp) - 1;
             *sen_target_begin = (*tempind == -1) ? 0 : (int)o->RLP[*tempind];
             min_L = L; max_R = R;
         } else { if (min_L > L) min_L = L; if (max_R < R) max_R = R; }
@@ -395,13 +416,13 @@ static int checkBoundaryFast(const orc_t *o, unsigned int start, unsigned int en
 
 /* ExtractPair.cu:196-250 checkBoundaryFast2 */
 static int checkBoundaryFast2(const orc_t *o, unsigned int start, unsigned int ender, unsigned int *target_start, unsigned int *target_end) {
-    unsigned char L, R, min_L = 255, max_R = 0; int sen_target_begin = -1, tempind = 0;
+    lr_t L, R, min_L = UNAL, max_R = 0; int sen_target_begin = -1, tempind = 0;
     for (int k = (int)start; k <= (int)ender; k++) {
-        uint32_t temp = o->RLP[k]; L = (temp >> 24) & 0xFF; R = (temp >> 16) & 0xFF;
-        if ((L == 255 || R == 255) && (k == (int)start || k == (int)ender)) return 0;
-        else if (L == 255 || R == 255) { }
+        rlp_t temp = o->RLP[k]; L = RLP_L(temp); R = RLP_R(temp);
+        if ((L == UNAL || R == UNAL) && (k == (int)start || k == (int)ender)) return 0;
+        else if (L == UNAL || R == UNAL) { }
         else if (k == (int)start) {
-            tempind = k - (int)((temp >> 8) & 0xFF) - 1;
+            tempind = k - RLP_P(temp) - 1;
             sen_target_begin = tempind == -1 ? 0 : (int)o->RLP[tempind];
             min_L = L; max_R = R;
         } else { if (min_L > L) min_L = L; if (max_R < R) max_R = R; }
@@ -413,21 +434,21 @@ static int checkBoundaryFast2(const orc_t *o, unsigned int start, unsigned int e
 
 /* ExtractPair.cu:252-342 checkBoundary (error codes 0..4) */
 static int checkBoundary(const orc_t *o, unsigned int start, unsigned int ender, unsigned int *target_start, unsigned int *target_end) {
-    unsigned char L, R, min_L = 255, max_R = 0; int sen_target_begin = -1, tempind = 0; int wrong = 0;
+    lr_t L, R, min_L = UNAL, max_R = 0; int sen_target_begin = -1, tempind = 0; int wrong = 0;
     for (int k = (int)start; k <= (int)ender; k++) {
-        uint32_t temp = o->RLP[k]; L = (temp >> 24) & 0xFF; R = (temp >> 16) & 0xFF;
-        if ((L == 255 || R == 255) && (k == (int)start || k == (int)ender)) {
+        rlp_t temp = o->RLP[k]; L = RLP_L(temp); R = RLP_R(temp);
+        if ((L == UNAL || R == UNAL) && (k == (int)start || k == (int)ender)) {
             if (start == ender && wrong == 0) wrong = 4;
             else if (wrong == 0 && k == (int)start) wrong = 2;
             else if (wrong == 0 && k == (int)ender) wrong = 3;
             else if (wrong != 0) wrong = 4;
             if (k == (int)start) {
-                tempind = k - (int)((temp >> 8) & 0xFF) - 1;
+                tempind = k - RLP_P(temp) - 1;
                 sen_target_begin = tempind == -1 ? 0 : (int)o->RLP[tempind];
             }
-        } else if (L == 255 || R == 255) { }
+        } else if (L == UNAL || R == UNAL) { }
         else if (k == (int)start) {
-            tempind = k - (int)((temp >> 8) & 0xFF) - 1;
+            tempind = k - RLP_P(temp) - 1;
             sen_target_begin = tempind == -1 ? 0 : (int)o->RLP[tempind];
             min_L = L; max_R = R;
         } else { if (min_L > L) min_L = L; if (max_R < R) max_R = R; }
@@ -907,23 +928,23 @@ static int sampled(int32_t j, int32_t n, int S) {
  * thread's strided occurrences). */
 static int gappy_body(orc_t *o, int bnum, int globalc, int current, int longestmatch) {
     const int32_t *refstr = o->str;
-    int k, current_str; unsigned char L, R; int sen_target_begin = -1; unsigned char min_L = 255, max_R = 0; int tempind = 0; unsigned int temp;
-    unsigned char i = 1; unsigned int gap1_start = 0, gap1_end = 0, gap2_start = 0, gap2_end = 0, target_start = 0, target_end = 0;
+    int k, current_str; lr_t L, R; int sen_target_begin = -1; lr_t min_L = UNAL, max_R = 0; int tempind = 0; rlp_t temp;
+    lr_t i = 1; unsigned int gap1_start = 0, gap1_end = 0, gap2_start = 0, gap2_end = 0, target_start = 0, target_end = 0;
     int next = 1; int ender;
     int abX = 1, Xab = 1, XabX = 1, ab = 1, XabNoSuccess = 1, abXNoSuccess = 1; uint8_t XabCount = 0, abXCount = 0;
-    unsigned char min_L_Xab = 255, max_R_Xab = 0, min_L_abX = 255, max_R_abX = 0, min_L_XabX = 255, max_R_XabX = 0;
+    lr_t min_L_Xab = UNAL, max_R_Xab = 0, min_L_abX = UNAL, max_R_abX = 0, min_L_XabX = UNAL, max_R_XabX = 0;
 
     current_str = o->sa[current];
     for (k = current_str; k < current_str + longestmatch; k++) {
-        temp = o->RLP[k]; L = (temp >> 24) & 0xFF; R = (temp >> 16) & 0xFF;
+        temp = o->RLP[k]; L = RLP_L(temp); R = RLP_R(temp);
         if (k == current_str) {
-            tempind = k - (int)((temp >> 8) & 0xFF) - 1;
+            tempind = k - RLP_P(temp) - 1;
             sen_target_begin = tempind == -1 ? 0 : (int)o->RLP[tempind];
         }
-        if ((L == 255 || R == 255) && (k == current_str || k == current_str + longestmatch - 1)) {
+        if ((L == UNAL || R == UNAL) && (k == current_str || k == current_str + longestmatch - 1)) {
             ab = 0;
             if (k == current_str) abXNoSuccess = 0; else XabNoSuccess = 0;
-        } else if (L == 255 || R == 255) { }
+        } else if (L == UNAL || R == UNAL) { }
         else { if (min_L > L) min_L = L; if (max_R < R) max_R = R; }
     }
     if (min_L > max_R || max_R - min_L >= ORC_MAX_RULE_SPAN) { abX = 0; Xab = 0; XabX = 0; ab = 0; }
@@ -942,8 +963,8 @@ static int gappy_body(orc_t *o, int bnum, int globalc, int current, int longestm
         /* ---- left X ---- :1282-1398 */
         if (Xab && current_str - i >= 0 && refstr[current_str - i] >= 2) {
             next = 1;
-            temp = o->RLP[current_str - i]; L = (temp >> 24) & 0xFF; R = (temp >> 16) & 0xFF;
-            if (L == 255 || R == 255) { next = 0; if (i == 1) { Xab = 0; XabX = 0; } }
+            temp = o->RLP[current_str - i]; L = RLP_L(temp); R = RLP_R(temp);
+            if (L == UNAL || R == UNAL) { next = 0; if (i == 1) { Xab = 0; XabX = 0; } }
             else { if (min_L_Xab > L) min_L_Xab = L; if (max_R_Xab < R) max_R_Xab = R; }
             if (next && min_L_Xab > max_R_Xab) return 1;
             if (max_R_Xab - min_L_Xab >= ORC_MAX_RULE_SPAN) { next = 0; Xab = 0; }
@@ -965,8 +986,8 @@ static int gappy_body(orc_t *o, int bnum, int globalc, int current, int longestm
         /* ---- right X ---- :1403-1509 */
         if (abX && refstr[ender + i] >= 2) {
             next = 1;
-            temp = o->RLP[ender + i]; L = (temp >> 24) & 0xFF; R = (temp >> 16) & 0xFF;
-            if (L == 255 || R == 255) { next = 0; if (i == 1) { abX = 0; XabX = 0; } }
+            temp = o->RLP[ender + i]; L = RLP_L(temp); R = RLP_R(temp);
+            if (L == UNAL || R == UNAL) { next = 0; if (i == 1) { abX = 0; XabX = 0; } }
             else { if (min_L_abX > L) min_L_abX = L; if (max_R_abX < R) max_R_abX = R; }
             if (next && min_L_abX > max_R_abX) return 1;
             if (max_R_abX - min_L_abX >= ORC_MAX_RULE_SPAN) { next = 0; abX = 0; }
@@ -988,12 +1009,12 @@ static int gappy_body(orc_t *o, int bnum, int globalc, int current, int longestm
         /* ---- XabX ---- :1514-1777 */
         if (XabX && (abX || Xab)) {
             if (XabCount == i) {
-                min_L_XabX = 255; max_R_XabX = 0;
+                min_L_XabX = UNAL; max_R_XabX = 0;
                 for (uint8_t icount = 1; XabX && icount <= abXCount; icount++) {
                     next = 1;
                     if (icount + XabCount + longestmatch <= ORC_MAX_RULE_SPAN) {
-                        temp = o->RLP[ender + icount]; L = (temp >> 24) & 0xFF; R = (temp >> 16) & 0xFF;
-                        if (L == 255 || R == 255) { next = 0; if (i == 1) return 1; }
+                        temp = o->RLP[ender + icount]; L = RLP_L(temp); R = RLP_R(temp);
+                        if (L == UNAL || R == UNAL) { next = 0; if (i == 1) return 1; }
                         else { if (min_L_XabX > L) min_L_XabX = L; if (max_R_XabX < R) max_R_XabX = R; }
                     } else { next = 0; icount = abXCount + 1; }
                     if (next && max_R_XabX - min_L_XabX >= ORC_MAX_RULE_SPAN) { next = 0; icount = abXCount + 1; }
@@ -1019,12 +1040,12 @@ static int gappy_body(orc_t *o, int bnum, int globalc, int current, int longestm
                 }
             }
             if (XabX && abXCount == i) {
-                min_L_XabX = 255; max_R_XabX = 0;
+                min_L_XabX = UNAL; max_R_XabX = 0;
                 for (uint8_t icount = 1; XabX && icount <= XabCount; icount++) {
                     next = 1;
                     if (icount + abXCount + longestmatch <= ORC_MAX_RULE_SPAN) {
-                        temp = o->RLP[current_str - icount]; L = (temp >> 24) & 0xFF; R = (temp >> 16) & 0xFF;
-                        if (L == 255 || R == 255) { next = 0; if (i == 1) return 1; }
+                        temp = o->RLP[current_str - icount]; L = RLP_L(temp); R = RLP_R(temp);
+                        if (L == UNAL || R == UNAL) { next = 0; if (i == 1) return 1; }
                         else { if (min_L_XabX > L) min_L_XabX = L; if (max_R_XabX < R) max_R_XabX = R; }
                     } else { icount = XabCount + 1; next = 0; }
                     if (next && max_R_XabX - min_L_XabX >= ORC_MAX_RULE_SPAN) { icount = XabCount + 1; next = 0; }
@@ -1099,11 +1120,11 @@ static void extract_twogap(orc_t *o) {
 }
 
 /* ExtractPair.cu:351-889 extractConsistentPairs_OneGap, one sampled hit; returns 1 on thread `return` */
-static int onegap_body(orc_t *o, int oneBlockId, unsigned int current_str, unsigned char firstEnd, int startLen, int endLen) {
+static int onegap_body(orc_t *o, int oneBlockId, unsigned int current_str, lr_t firstEnd, int startLen, int endLen) {
     const int32_t *refstr = o->str;
     unsigned int gap1_start = 0, gap1_end = 0, target_start = 0, target_end = 0, gap2_start = 0, gap2_end = 0;
     int next = 1, firstGap = 1, left = 1, right = 1; unsigned int ender; uint8_t i = 1; int reNext;
-    unsigned char min_L = 255, max_R = 0; int sen_target_begin = -1, tempind = -1;
+    lr_t min_L = UNAL, max_R = 0; int sen_target_begin = -1, tempind = -1;
     if ((int64_t)current_str + firstEnd - endLen > o->n) return 1;
     ender = current_str + firstEnd;
     firstGap = checkBoundaryFast(o, current_str + (unsigned)startLen, ender - (unsigned)endLen, &min_L, &max_R, &sen_target_begin, &tempind);
@@ -1111,21 +1132,21 @@ static int onegap_body(orc_t *o, int oneBlockId, unsigned int current_str, unsig
     if (tempind == -1 || sen_target_begin == -1 || min_L > max_R) return 1;
     gap1_start = (unsigned)(min_L + sen_target_begin); gap1_end = (unsigned)(max_R + sen_target_begin);
     reNext = checkBoundary(o, current_str, ender, &target_start, &target_end);
-    min_L = (unsigned char)(target_start - (unsigned)sen_target_begin); max_R = (unsigned char)(target_end - (unsigned)sen_target_begin);
+    min_L = (lr_t)(target_start - (unsigned)sen_target_begin); max_R = (lr_t)(target_end - (unsigned)sen_target_begin);
     if (reNext == 0) next = 0; else if (reNext == 1) next = 1; else if (reNext == 2) { next = 0; right = 0; }
     else if (reNext == 3) { next = 0; left = 0; } else if (reNext == 4) { next = 0; left = 0; right = 0; }
     if ((target_start == 0 && target_end == 0) || (min_L > max_R) || gap1_start < target_start || gap1_end > target_end) return 1;   /* :591-595 */
     if (next && firstGap) EMIT1(oneBlockId, target_start, target_end, gap1_start, gap1_end);
-    unsigned int originalGapStart, originalGapEnd, temp; unsigned char L, R;
-    unsigned char min_XaXb = 255, max_XaXb = 0, min_aXbX = 255, max_aXbX = 0;
+    unsigned int originalGapStart, originalGapEnd; rlp_t temp; lr_t L, R;
+    lr_t min_XaXb = UNAL, max_XaXb = 0, min_aXbX = UNAL, max_aXbX = 0;
     if (firstGap && startLen + endLen + 1 + 1 <= ORC_MAX_RULE_SYMBOLS) {
         target_start = 0; target_end = 0; i = 1;
         originalGapStart = gap1_start; originalGapEnd = gap1_end; gap1_start = 0; gap1_end = 0;
         while (firstEnd + 1 + i <= ORC_MAX_RULE_SPAN && (left || right)) {
             if (left && (int)(current_str - i) >= 0 && refstr[current_str - i] >= 2) {
                 target_start = 0; target_end = 0; gap1_start = 0; gap1_end = 0; next = 1;
-                temp = o->RLP[current_str - i]; L = (temp >> 24) & 0xFF; R = (temp >> 16) & 0xFF;
-                if (L == 255 || R == 255) { next = 0; if (i == 1) left = 0; }
+                temp = o->RLP[current_str - i]; L = RLP_L(temp); R = RLP_R(temp);
+                if (L == UNAL || R == UNAL) { next = 0; if (i == 1) left = 0; }
                 else { if (min_XaXb > L) min_XaXb = L; if (max_XaXb < R) max_XaXb = R; }
                 if (next && min_XaXb > max_XaXb) return 1;
                 if (max_XaXb - min_XaXb >= ORC_MAX_RULE_SPAN) { next = 0; left = 0; }
@@ -1144,8 +1165,8 @@ static int onegap_body(orc_t *o, int oneBlockId, unsigned int current_str, unsig
             } else left = 0;
             if (right && refstr[ender + i] >= 2) {
                 target_start = 0; target_end = 0; next = 1; gap2_start = 0; gap2_end = 0;
-                temp = o->RLP[ender + i]; L = (temp >> 24) & 0xFF; R = (temp >> 16) & 0xFF;
-                if (L == 255 || R == 255) { next = 0; if (i == 1) right = 0; }
+                temp = o->RLP[ender + i]; L = RLP_L(temp); R = RLP_R(temp);
+                if (L == UNAL || R == UNAL) { next = 0; if (i == 1) right = 0; }
                 else { if (min_aXbX > L) min_aXbX = L; if (max_aXbX < R) max_aXbX = R; }
                 if (next && min_aXbX > max_aXbX) return 1;
                 if (max_aXbX - min_aXbX >= ORC_MAX_RULE_SPAN) { next = 0; right = 0; }
@@ -1185,9 +1206,9 @@ static void extract_onegap(orc_t *o) {
             int tid = j % ORC_THREADS;
             if (dead[tid]) continue;
             if (!sampled(j, dis, ORC_SAMPLER_ONEGAP)) continue;
-            unsigned int cs; unsigned char fe;
-            if (pre) { cs = (unsigned)o->plist[2 * (base + j)]; fe = (unsigned char)o->plist[2 * (base + j) + 1]; }
-            else { cs = (unsigned)o->h1[3 * (base + j) + 1]; fe = (unsigned char)o->h1[3 * (base + j) + 2]; }
+            unsigned int cs; lr_t fe;
+            if (pre) { cs = (unsigned)o->plist[2 * (base + j)]; fe = (lr_t)o->plist[2 * (base + j) + 1]; }
+            else { cs = (unsigned)o->h1[3 * (base + j) + 1]; fe = (lr_t)o->h1[3 * (base + j) + 2]; }
             if (onegap_body(o, d, cs, fe, startLen, endLen)) dead[tid] = 1;
         }
     }
@@ -1408,7 +1429,7 @@ int orc_run_query_file(orc_t *o, const char *path) {
     iv_push(&off, 0);
     while (getline(&line, &cap, fh) != -1) {
         char *t = strtok(line, " ");
-        while (t != NULL && !isspace((unsigned char)*t)) {
+        while (t != NULL && !isspace((lr_t)*t)) {
             size_t tl = strlen(t);
             if (tl && t[tl - 1] == '\n') t[tl - 1] = 0;
             iv_push(&tok, smap_get(&o->smap_src, t));

@@ -33,12 +33,21 @@ extern "C" {
 #define ORC_THREADS 512               /* ExtractPair.cu:9 THREADS_PER_BLOCK (matters for the early-return quirks) */
 
 typedef struct orc_s orc_t;
+/* alignment fields: 8 bits like the reference, or 16 bits with -DORC_WIDE (libcgx_oracle_wide.so; see cgx_oracle.c) */
+#ifdef ORC_WIDE
+typedef uint16_t lr_t;
+typedef uint64_t rlp_t;
+#else
+typedef uint8_t lr_t;
+typedef uint32_t rlp_t;
+#endif
+int orc_is_wide(void);
 
 /* ---- construction ------------------------------------------------------------------------- */
 /* From the integer layouts of the reference loaders (Start.cu:240-380, ExtractPair.cu:2639-2739).
  * str: n+3 ints (3 trailing zeros), tgt: m+3 ints.  All arrays are copied. */
 orc_t *orc_create(const int32_t *str, int32_t n, const int32_t *tgt, int32_t m,
-                  const uint32_t *RLP, const uint8_t *L_tar, const uint8_t *R_tar,
+                  const rlp_t *RLP, const lr_t *L_tar, const lr_t *R_tar,
                   const int32_t *lex_f, const int32_t *lex_e, const float *lex_v1, const float *lex_v2,
                   int32_t lex_count);
 /* From the six strmatchcuda text inputs (Main.c:55-60).  NULL on failure. */

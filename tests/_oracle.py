@@ -14,6 +14,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 LIB_PATH = os.path.join(ORACLE_DIR, "_build", "libcgx_oracle.so")
+WIDE_LIB_PATH = os.path.join(ORACLE_DIR, "_build", "libcgx_oracle_wide.so")      # the same algorithm on 16-bit alignment fields
 CLI_PATH = os.path.join(ORACLE_DIR, "_build", "cgx_oracle_cli")
 REF_SA_PATH = os.path.join(ORACLE_DIR, "_ref", "libref_sa.so")
 REF_BIN = os.path.join(ORACLE_DIR, "_ref", "strmatchcuda")
@@ -34,18 +35,23 @@ class Counts(C.Structure):
 RULE_DTYPE = np.dtype([("id", "<i4"), ("rec", "<i4", (6,)), ("f", "<i4"), ("fs", "<i4"), ("pc", "<i4"),
                        ("aa", "<f4"), ("score", "<f4"), ("bb", "<f4"), ("mlfe", "<f4"), ("mlef", "<f4")])
 
-_lib = None
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        if not os.path.exists(LIB_PATH):
+def lib(wide=False):
+    """The oracle library: the reference's 8-bit alignment fields, or (wide) the -DORC_WIDE build of the same source with 16-bit
+    fields for corpora with sentences of 255 tokens and more."""
+    if wide not in _libs:
+        path = WIDE_LIB_PATH if wide else LIB_PATH
+        if not os.path.exists(path):
             build_oracle()
-        L = C.CDLL(LIB_PATH)
-        vp, i32p, u32p, u8p, f32p = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint8), C.POINTER(C.c_float)
+        L = C.CDLL(path)
+        vp, i32p, f32p = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_float)
+        rlp_p, lr_p = (C.POINTER(C.c_uint64), C.POINTER(C.c_uint16)) if wide else (C.POINTER(C.c_uint32), C.POINTER(C.c_uint8))
+        L.orc_is_wide.restype = C.c_int
+        assert bool(L.orc_is_wide()) == bool(wide)
         L.orc_create.restype = vp
-        L.orc_create.argtypes = [i32p, C.c_int32, i32p, C.c_int32, u32p, u8p, u8p, i32p, i32p, f32p, f32p, C.c_int32]
+        L.orc_create.argtypes = [i32p, C.c_int32, i32p, C.c_int32, rlp_p, lr_p, lr_p, i32p, i32p, f32p, f32p, C.c_int32]
         L.orc_create_from_files.restype = vp
         L.orc_create_from_files.argtypes = [C.c_char_p] * 4
         L.orc_destroy.argtypes = [vp]
@@ -64,8 +70,8 @@ def lib():
         L.orc_records.argtypes = [vp, C.c_int, C.POINTER(i32p)]
         L.orc_rules.restype = C.c_int32
         L.orc_rules.argtypes = [vp, C.c_int, C.POINTER(vp)]
-        _lib = L
-    return _lib
+        _libs[wide] = L
+    return _libs[wide]
 
 
 def _p(a, t):
@@ -80,31 +86,48 @@ def _arr(ptr, n, cols=None):
 
 
 class Oracle:
-    def __init__(self, handle):
+    def __init__(self, handle, wide=False):
         if not handle:
             raise RuntimeError("oracle construction failed")
         self.h = handle
-        self.L = lib()
+        self.L = lib(wide)
+        self.wide = wide
 
     @classmethod
-    def from_layout(cls, lay):
-        L = lib()
+    def from_layout(cls, lay, wide=None):
+        """wide=None: as the layout says; True on an 8-bit layout widens it (the wide build must then agree with the narrow one)."""
+        lay_wide = bool(lay.get("wide", False))
+        wide = lay_wide if wide is None else bool(wide)
+        L = lib(wide)
         s = np.ascontiguousarray(lay["str"], dtype=np.int32)
         t = np.ascontiguousarray(lay["tgt"], dtype=np.int32)
-        rlp = np.ascontiguousarray(lay["RLP"], dtype=np.uint32)
-        lt = np.ascontiguousarray(lay["L_tar"], dtype=np.uint8)
-        rt = np.ascontiguousarray(lay["R_tar"], dtype=np.uint8)
+        rlp, lt, rt = np.asarray(lay["RLP"]), np.asarray(lay["L_tar"]), np.asarray(lay["R_tar"])
+        if wide and not lay_wide:
+            x = rlp.astype(np.uint64)
+            Lf, Rf, Pf = (x >> 24) & 0xFF, (x >> 16) & 0xFF, (x >> 8) & 0xFF
+            Lf[Lf == 255] = 65535
+            Rf[Rf == 255] = 65535
+            eos = s[: len(x)] < 2                       # the word at an EOS is the target sentence offset
+            rlp = np.where(eos, x, (Lf << 48) | (Rf << 32) | (Pf << 16))
+            lt = np.where(lt == 255, 65535, lt.astype(np.uint16))
+            rt = np.where(rt == 255, 65535, rt.astype(np.uint16))
+        elif lay_wide and not wide:
+            raise ValueError("a 16-bit layout needs the wide oracle")
+        rlp = np.ascontiguousarray(rlp, dtype=np.uint64 if wide else np.uint32)
+        lt = np.ascontiguousarray(lt, dtype=np.uint16 if wide else np.uint8)
+        rt = np.ascontiguousarray(rt, dtype=np.uint16 if wide else np.uint8)
+        ct_rlp, ct_lr = (C.c_uint64, C.c_uint16) if wide else (C.c_uint32, C.c_uint8)
         lf = np.ascontiguousarray(lay["lex_f"], dtype=np.int32)
         le = np.ascontiguousarray(lay["lex_e"], dtype=np.int32)
         v1 = np.ascontiguousarray(lay["lex_v1"], dtype=np.float32)
         v2 = np.ascontiguousarray(lay["lex_v2"], dtype=np.float32)
-        h = L.orc_create(_p(s, C.c_int32), int(lay["n"]), _p(t, C.c_int32), int(lay["m"]), _p(rlp, C.c_uint32), _p(lt, C.c_uint8),
-                         _p(rt, C.c_uint8), _p(lf, C.c_int32), _p(le, C.c_int32), _p(v1, C.c_float), _p(v2, C.c_float), len(lf))
-        return cls(h)
+        h = L.orc_create(_p(s, C.c_int32), int(lay["n"]), _p(t, C.c_int32), int(lay["m"]), _p(rlp, ct_rlp), _p(lt, ct_lr),
+                         _p(rt, ct_lr), _p(lf, C.c_int32), _p(le, C.c_int32), _p(v1, C.c_float), _p(v2, C.c_float), len(lf))
+        return cls(h, wide)
 
     @classmethod
-    def from_files(cls, src, tgt, align, lex):
-        return cls(lib().orc_create_from_files(src.encode(), tgt.encode(), align.encode(), lex.encode()))
+    def from_files(cls, src, tgt, align, lex, wide=False):
+        return cls(lib(wide).orc_create_from_files(src.encode(), tgt.encode(), align.encode(), lex.encode()), wide)
 
     def close(self):
         if self.h:

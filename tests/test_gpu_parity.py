@@ -504,3 +504,81 @@ def test_join_variants_agree_with_oracle(mode, ordered, micro, micro_oracle, mon
             assert len(res.rules[k]) == len(o.rules(k))
     finally:
         ex.close()
+
+
+LONG = dict(n_sent=400, n_qry=8, v_src=300, v_tgt=300, n_phrases=600, mean_len=150.0, sd_len=90.0, max_len=600, qry_mean_len=12.0, seed=5, qry_seed=6)
+
+
+def test_forced_wide_fields_equal_narrow(micro, monkeypatch):
+    """SURVEY.md 8f, lifted limit: the 16-bit alignment layout (align_fields.cuh, cgx_index_build_wide) on a corpus that fits
+    the reference's 8 bits -- CGX_FORCE_WIDE=1 widens the input of cgx_index_build -- gives byte-identical results."""
+    from cgx_b200.extractor import GrammarExtractor
+    _, lay = micro
+    a = GrammarExtractor(0)
+    a.build_index(lay)
+    monkeypatch.setenv("CGX_FORCE_WIDE", "1")
+    b = GrammarExtractor(0)
+    b.build_index(lay)
+    monkeypatch.delenv("CGX_FORCE_WIDE")
+    try:
+        ra, rb = a.extract(lay["qry_tok"], lay["qry_off"]), b.extract(lay["qry_tok"], lay["qry_off"])
+        assert ra.info["hits1"] == rb.info["hits1"] and ra.info["hits2"] == rb.info["hits2"] and ra.info["hits1"] > 0
+        for k in range(3):
+            assert len(ra.rules[k]) > 0 and ra.rules[k].tobytes() == rb.rules[k].tobytes(), k
+        for name, cnt, cols in (("rec_ab", "n_ab", 7), ("rec_1", "n_1gap", 7), ("rec_2", "n_2gap", 7), ("hits1", "hits1", 3), ("hits2", "hits2", 4)):
+            assert np.array_equal(a.debug_fetch(name, int(ra.info[cnt]) * cols, cols), b.debug_fetch(name, int(rb.info[cnt]) * cols, cols)), name
+    finally:
+        a.close()
+        b.close()
+
+
+def test_sentences_of_255_tokens_and_more(tmp_path):
+    """SURVEY.md 8f, lifted limit.  The reference exits on a sentence of 255 tokens ("Not possible, too long sentence",
+    ExtractPair.cu:2683; 8-bit position counters, Start.cu:269).  Here the C loaders switch to the 16-bit alignment layout, the
+    index is built with cgx_index_build_wide, and every stage equals the wide build of the oracle (the same algorithm on 16-bit
+    fields): stage by stage through the C ABI, and grammar file by grammar file through the drop-in CLI -- also from a persisted
+    index (-i), whose file records the layout."""
+    from _oracle import Oracle
+    from _parity import assert_full_parity
+    from cgx_b200 import synth
+    from cgx_b200.extractor import GrammarExtractor
+    from cgx_b200.host import HostCorpus
+    files = synth.write_text(synth.generate(**LONG), str(tmp_path), "corpus")
+    assert max(len(l.split()) for l in open(files["f"])) >= 300
+    hc = HostCorpus(files["f"], files["q"], files["e"], files["a"], files["lex"])
+    lay = hc.layout()
+    assert lay["wide"]
+    o = Oracle.from_layout(lay)
+    assert o.wide
+    o.build_sa()
+    o.run(lay["qry_tok"], lay["qry_off"])
+    ex = GrammarExtractor(0)
+    try:
+        ex.build_index(lay)
+        res = ex.extract(lay["qry_tok"], lay["qry_off"])
+        assert res.info["hits1"] > 10_000 and len(res.rules[2]) > 1000
+        assert_full_parity(ex, res, lay, o)
+    finally:
+        ex.close()
+    # rules that lie beyond token 255 of their sentence exist (the part the 8-bit layout could not address)
+    r1 = o.records(1)
+    sent_start = np.concatenate([[0], np.cumsum([len(l.split()) + 1 for l in open(files["e"])])])
+    rel = r1[:, 1] - sent_start[np.searchsorted(sent_start, r1[:, 1], side="right") - 1]
+    assert (rel >= 255).sum() > 100
+    # the drop-in CLI: text files in, grammar files out; then the same from the persisted index
+    of = Oracle.from_files(files["f"], files["e"], files["a"], files["lex"], wide=True)
+    of.build_sa()
+    of.run_query_file(files["q"])
+    orc = tmp_path / "orc"
+    orc.mkdir()
+    of.write_grammars(str(orc))
+    cli = os.path.join(ROOT, "bin", "strmatchcuda")
+    idx = str(tmp_path / "corpus.idx")
+    for name in ("first", "second"):
+        out = tmp_path / name
+        out.mkdir()
+        r = subprocess.run([cli, "-q", "-i", idx, files["f"], files["q"], files["e"], files["a"], files["lex"], str(out)], capture_output=True, text=True)
+        assert r.returncode == 0 and "Start Printing Gappy Phrases" in r.stderr, r.stderr[-2000:]
+        assert ("index loaded from" in r.stderr) == (name == "second")
+        c = gc.compare_dirs(str(out), str(orc), rtol=1e-5, atol=2e-6)
+        assert c["files"] == LONG["n_qry"] and c["only_a"] == 0 and c["only_b"] == 0 and c["float_mismatch"] == 0, c

@@ -193,3 +193,61 @@ def test_writer_float_format_equals_printf(built):
             continue
         n = L.cgxh_format_f6(C.c_float(x), buf)
         assert buf.value.decode() == "%f" % x and n == len(buf.value), (x, buf.value)
+
+
+LONG = dict(n_sent=400, n_qry=8, v_src=300, v_tgt=300, n_phrases=600, mean_len=150.0, sd_len=90.0, max_len=600, qry_mean_len=12.0, seed=5, qry_seed=6)
+
+
+def test_wide_oracle_equals_narrow_on_a_corpus_that_fits_8_bits(micro):
+    """SURVEY.md 8f, lifted limit.  oracle/cgx_oracle.c built with -DORC_WIDE runs the same algorithm on 16-bit alignment fields
+    (sentences of 255 tokens and more, which the reference refuses: ExtractPair.cu:2683).  On a corpus the 8-bit layout holds,
+    both builds must give the same records and rules."""
+    from _oracle import Oracle
+    _, lay = micro
+    outs = []
+    for wide in (False, True):
+        o = Oracle.from_layout(lay, wide=wide)
+        o.build_sa()
+        c = o.run(lay["qry_tok"], lay["qry_off"])
+        outs.append(((c.G, c.D1, c.D2, c.hits1, c.hits2), [o.records(k).tobytes() for k in range(3)], [o.rules(k).tobytes() for k in range(3)]))
+        o.close()
+    assert outs[0] == outs[1]
+
+
+def test_long_sentences_load_into_the_16_bit_layout(tmp_path, built):
+    """The C loaders on a corpus with sentences of up to ~400 tokens: the 16-bit alignment layout (wide = 1) is chosen, its fields
+    equal a numpy parse of the same alignment file, and the narrow oracle refuses the corpus while the wide one runs it."""
+    from _oracle import Oracle
+    from cgx_b200 import synth
+    from cgx_b200.host import HostCorpus
+    files = synth.write_text(synth.generate(**LONG), str(tmp_path), "corpus")
+    src_len = [len(l.split()) for l in open(files["f"])]
+    tgt_len = [len(l.split()) for l in open(files["e"])]
+    assert max(src_len) >= 300
+    lay = HostCorpus(files["f"], files["q"], files["e"], files["a"], files["lex"]).layout()
+    assert lay["wide"] and lay["RLP"].dtype == np.uint64 and lay["L_tar"].dtype == np.uint16
+    s_off = np.concatenate([[0], np.cumsum(np.array(src_len) + 1)])
+    t_off = np.concatenate([[0], np.cumsum(np.array(tgt_len) + 1)])
+    n, m = lay["n"], lay["m"]
+    L = np.full(n, 65535, np.int64); R = np.full(n, 65535, np.int64); Lt = np.full(m, 65535, np.int64); Rt = np.full(m, 65535, np.int64)
+    for q, line in enumerate(open(files["a"])):
+        for pair in line.split():
+            a, b = (int(x) for x in pair.split("-"))
+            si, ti = s_off[q] + a, t_off[q] + b
+            L[si], R[si] = (b, b) if L[si] == 65535 else (min(L[si], b), max(R[si], b))
+            Lt[ti], Rt[ti] = (a, a) if Lt[ti] == 65535 else (min(Lt[ti], a), max(Rt[ti], a))
+    assert np.array_equal(lay["L_tar"], Lt.astype(np.uint16)) and np.array_equal(lay["R_tar"], Rt.astype(np.uint16))
+    rlp = lay["RLP"]
+    for q in range(len(src_len)):
+        a, b = s_off[q], s_off[q + 1] - 1                                           # tokens a..b-1, EOS at b
+        w = rlp[a:b]
+        assert np.array_equal((w >> 48) & 0xFFFF, L[a:b]) and np.array_equal((w >> 32) & 0xFFFF, R[a:b])
+        assert np.array_equal((w >> 16) & 0xFFFF, np.arange(b - a))                  # position in the sentence, not wrapped at 256
+        assert int(rlp[b]) == t_off[q + 1]                                          # the word at the EOS: offset of the next target sentence
+    with pytest.raises(RuntimeError):
+        Oracle.from_files(files["f"], files["e"], files["a"], files["lex"])          # 8-bit fields: "sentence too long", like the reference
+    o = Oracle.from_files(files["f"], files["e"], files["a"], files["lex"], wide=True)
+    o.build_sa()
+    o.run_query_file(files["q"])
+    assert o.counts().G > 100 and len(o.rules(1)) > 1000
+    o.close()
