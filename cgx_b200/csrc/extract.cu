@@ -492,7 +492,9 @@ void stage_extract(const Index &ix, Batch &b, cudaStream_t stream) {
     for (int k = 0; k < 3; k++) b.n_slots[k] = ns[k];
     // one cell per (shape, slot)
     const size_t c0 = ns[0], c1 = (size_t)2 * ns[0] + ns[1], c2 = (size_t)ns[0] + ns[2] + (size_t)2 * ns[1];
-    CGX_REQUIRE_BATCH(c2 < (1ull << 32), "%zu record cells exceed the 32-bit cell index", c2);
+    // slot totals come from 32-bit scans: the three kinds are bounded separately (a sum that wrapped would be smaller than a part)
+    CGX_REQUIRE_BATCH((uint64_t)ns[0] + ns[1] + ns[2] < (1ull << 31) && c1 < (1ull << 32) && c2 < (1ull << 32),
+                      "%zu / %zu record cells exceed the 32-bit cell index", c1, c2);
     b.rec_cells[0] = c0; b.rec_cells[1] = c1; b.rec_cells[2] = c2;
     RuleRec *r0 = b.rec[0].get<RuleRec>(c0 + 1), *r1 = b.rec[1].get<RuleRec>(c1 + 1), *r2 = b.rec[2].get<RuleRec>(c2 + 1);
     CUDA_CHECK(cudaMemsetAsync(r0, 0xff, sizeof(RuleRec) * c0, stream));

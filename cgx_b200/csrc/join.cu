@@ -463,7 +463,7 @@ __device__ __forceinline__ unsigned jo_walk(const JPArgs &a, const int4 *__restr
 
 __global__ void __launch_bounds__(JO_TILE) j1_pos_ordered_kernel(const JOArgs o) {
     const JPArgs &a = o.p;
-    __shared__ int4 s_win[JO_TILE + JP_HALO];
+    __shared__ __align__(16) int4 s_win[JO_TILE + JP_HALO];
     extern __shared__ __align__(16) unsigned char s_dyn[];          // per warp: JO_CAP pattern ids (u32), then JO_CAP position/length words (u16)
     __shared__ uint32_t s_qa[JO_TILE / 32][JQ_CAP], s_qb[JO_TILE / 32][JQ_CAP];
     __shared__ uint16_t s_qm[JO_TILE / 32][JQ_CAP];
@@ -473,11 +473,20 @@ __global__ void __launch_bounds__(JO_TILE) j1_pos_ordered_kernel(const JOArgs o)
     uint16_t *st_pl = reinterpret_cast<uint16_t *>(s_dyn + sizeof(uint32_t) * JO_CAP * (JO_TILE / 32)) + (size_t)warp * JO_CAP;
     const uint32_t tile = blockIdx.x;
     const uint32_t P0 = tile * (uint32_t)JO_TILE;
-    for (int i = tid; i < JO_TILE + JP_HALO; i += JO_TILE) {
-        const uint32_t p = P0 + i;
-        s_win[i] = p < a.n ? __ldg(&a.jwin[p]) : make_int4(0, 0, 0, 0);
+    // the tile's window -- 273 consecutive 16-byte position records, 4.4 KB -- arrives by ONE bulk copy (cp.async.bulk, the TMA
+    // unit's 1-D form; SASS UBLKCP) issued by one thread and signalled on an mbarrier, instead of 273 LDG.128 + STS.128 with
+    // their address arithmetic; positions beyond the corpus are zero-filled by the threads meanwhile
+    __shared__ uint64_t s_bar;
+    const unsigned n_valid = min((unsigned)(JO_TILE + JP_HALO), a.n - P0);
+    if (tid == 0) { rs_mbar_init(&s_bar, 1); rs_fence_mbar_init(); }
+    __syncthreads();
+    if (tid == 0) {
+        rs_mbar_expect_tx(&s_bar, n_valid * (unsigned)sizeof(int4));
+        rs_bulk_g2s(s_win, a.jwin + P0, n_valid * (unsigned)sizeof(int4), &s_bar);
     }
-    __syncthreads();                                                // the only CTA-wide barrier: the warps are independent from here on
+    for (unsigned i = n_valid + tid; i < (unsigned)(JO_TILE + JP_HALO); i += JO_TILE) s_win[i] = make_int4(0, 0, 0, 0);
+    rs_mbar_wait(&s_bar, 0);
+    __syncthreads();                                                // the last CTA-wide barrier: the warps are independent from here on
     // lane l of warp w tests "does a first phrase start at position 32 w + l" for the three lengths
     const int wrel = (int)warp * 32;
     const int4 mine = s_win[wrel + (int)lane];

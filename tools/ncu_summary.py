@@ -80,7 +80,8 @@ if out_json:
         d = json.load(open(out_json))
     except (OSError, ValueError):
         d = {}
-    alias = {"j1_scan_kernel": "join_onegap", "j1_pos_kernel": "join_onegap", "j2_scan_kernel": "join_twogap", "agg_group_kernel": "agg_group", "agg_rules_kernel": "agg_rules",
+    alias = {"j1_scan_kernel": "join_onegap", "j1_pos_kernel": "join_onegap", "j1_pos_ordered_kernel": "join_onegap", "j2_scan_kernel": "join_twogap",
+             "j2_ordered_kernel": "join_twogap", "agg_group_kernel": "agg_group", "agg_rules_kernel": "agg_rules",
              "agg_hash_kernel": "agg_hash", "extract_onegap_kernel": "extract_onegap", "extract_contig_kernel": "extract_contig",
              "extract_twogap_kernel": "extract_twogap", "rs_onesweep_kernel": "radix_onesweep", "lookup_kernel": "lookup"}
     for name, v in traffic.items():
