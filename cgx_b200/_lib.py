@@ -118,7 +118,7 @@ def load():
     return L
 
 
-EXPORTED_SYMBOLS = ("cgx_version", "cgx_create", "cgx_destroy", "cgx_last_error", "cgx_index_build", "cgx_index_build_wide", "cgx_lex_load", "cgx_index_info",
+EXPORTED_SYMBOLS = ("cgx_version", "cgx_create", "cgx_destroy", "cgx_last_error", "cgx_index_build", "cgx_index_build_wide", "cgx_index_matches", "cgx_lex_load", "cgx_index_info",
                     "cgx_sa_build_dev", "cgx_index_export", "cgx_index_alloc", "cgx_index_commit", "cgx_index_save", "cgx_index_load", "cgx_index_copy_sa", "cgx_index_copy_inv",
                     "cgx_index_copy_frequent", "cgx_extract", "cgx_extract_begin", "cgx_result_at", "cgx_extract_dev", "cgx_profile_enable", "cgx_profile_report",
                     "cgx_index_broadcast", "cgx_batch_info", "cgx_batch_advice", "cgx_result", "cgx_debug_fetch", "cgx_debug_sort_u64")

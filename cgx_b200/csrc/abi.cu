@@ -119,6 +119,11 @@ static void build_index_device(cgx_ctx *c) {
     c->batch.adv_refused_q = c->batch.adv_ok_q = 0;   // batch-size advice belongs to the corpus
 }
 
+static uint64_t fnv1a_words(const int32_t *w, size_t count, uint64_t h = 1469598103934665603ull) {
+    for (size_t i = 0; i < count; i++) { h ^= (uint32_t)w[i]; h *= 1099511628211ull; }
+    return h ? h : 1;
+}
+
 static void index_build_host(cgx_ctx *c, const int32_t *src, int64_t n, const int32_t *tgt, int64_t m, const void *RLP, const void *L_tar, const void *R_tar,
                              bool wide) {
     CGX_REQUIRE(c && src && tgt && RLP && L_tar && R_tar, "null argument");
@@ -135,6 +140,8 @@ static void index_build_host(cgx_ctx *c, const int32_t *src, int64_t n, const in
     CUDA_CHECK(cudaMemcpyAsync(ix.L_tar.get<uint8_t>(ix.m * lb), L_tar, ix.m * lb, cudaMemcpyHostToDevice, c->stream));
     CUDA_CHECK(cudaMemcpyAsync(ix.R_tar.get<uint8_t>(ix.m * lb), R_tar, ix.m * lb, cudaMemcpyHostToDevice, c->stream));
     build_index_device(c);
+    ix.src_sum = fnv1a_words(src, ix.n + 3);
+    ix.tgt_sum = fnv1a_words(tgt, ix.m + 3);
 }
 
 extern "C" int cgx_index_build_wide(cgx_ctx_t *c, const int32_t *src, int64_t n, const int32_t *tgt, int64_t m, const uint64_t *RLP64,
@@ -287,10 +294,11 @@ extern "C" int cgx_index_commit(cgx_ctx_t *c) {
 
 // ---- persisted index (the reference only has the dead sa_precomp.txt stub, SuffixArray.c:208-230) --------------
 struct IndexFileHeader {
-    char magic[8];                 // "CGXIDX01"
+    char magic[8];                 // "CGXIDX02"
     int64_t n, m, lex_count;
     int32_t max_token, sa_rounds, sa_key_bits, wide;      // wide: 16-bit alignment fields (0 in files written before the field existed)
     int32_t freq_list[CGX_PRECOMP];
+    uint64_t src_sum, tgt_sum;     // FNV-1a of the source / target token arrays (0 = not recorded)
 };
 struct IndexArrayRef { void *p; size_t bytes; };
 static int index_array_refs(const cgx_index_arrays_t &a, IndexArrayRef out[18]) {
@@ -315,8 +323,9 @@ extern "C" int cgx_index_save(cgx_ctx_t *c, const char *path) {
         CGX_REQUIRE(fh, "cannot open %s for writing", tmp_path.c_str());
         IndexFileHeader h;
         memset(&h, 0, sizeof h);
-        memcpy(h.magic, "CGXIDX01", 8);
+        memcpy(h.magic, "CGXIDX02", 8);
         h.n = a.n; h.m = a.m; h.lex_count = a.lex_count; h.max_token = a.max_token; h.sa_rounds = c->ix.sa_stats.rounds; h.sa_key_bits = c->ix.sa_stats.key_bits; h.wide = a.wide;
+        h.src_sum = c->ix.src_sum; h.tgt_sum = c->ix.tgt_sum;
         memcpy(h.freq_list, a.freq_list, sizeof h.freq_list);
         CGX_REQUIRE(fwrite(&h, sizeof h, 1, fh) == 1, "write failed");
         const size_t piece = (size_t)64 << 20;
@@ -353,7 +362,7 @@ extern "C" int cgx_index_load(cgx_ctx_t *c, const char *path) {
         fh = fopen(path, "rb");
         CGX_REQUIRE(fh, "cannot open %s", path);
         IndexFileHeader h;
-        CGX_REQUIRE(fread(&h, sizeof h, 1, fh) == 1 && memcmp(h.magic, "CGXIDX01", 8) == 0, "%s is not a cgx-b200 index file", path);
+        CGX_REQUIRE(fread(&h, sizeof h, 1, fh) == 1 && memcmp(h.magic, "CGXIDX02", 8) == 0, "%s is not a cgx-b200 index file of this version", path);
         CGX_REQUIRE(h.n >= 4 && h.m >= 1 && h.lex_count >= 0 && h.max_token >= 1, "%s: corrupt header", path);
         cgx_index_arrays_t shape, a;
         memset(&shape, 0, sizeof shape);
@@ -375,6 +384,7 @@ extern "C" int cgx_index_load(cgx_ctx_t *c, const char *path) {
         fclose(fh);
         fh = nullptr;
         c->ix.sa_stats.rounds = h.sa_rounds; c->ix.sa_stats.key_bits = h.sa_key_bits; c->ix.sa_stats.ms = 0.f; c->ix.sa_stats.launches = 0;
+        c->ix.src_sum = h.src_sum; c->ix.tgt_sum = h.tgt_sum;
         c->aux_ms = 0.f;
         CGX_REQUIRE(cgx_index_commit(c) == 0, "%s", c->err.c_str());
         return 0;
@@ -384,6 +394,14 @@ extern "C" int cgx_index_load(cgx_ctx_t *c, const char *path) {
         if (c) c->err = e.msg;
         return e.code;
     }
+}
+
+extern "C" int cgx_index_matches(const cgx_ctx_t *c, const int32_t *src, int64_t n, const int32_t *tgt, int64_t m) {
+    if (!c || !src || !tgt || !c->ix.built) return 0;
+    const Index &ix = c->ix;
+    if ((int64_t)ix.n != n || (int64_t)ix.m != m) return 0;
+    if (ix.src_sum == 0 || ix.tgt_sum == 0) return 1;                     // (an index adopted from a broadcast carries no checksums)
+    return fnv1a_words(src, (size_t)n + 3) == ix.src_sum && fnv1a_words(tgt, (size_t)m + 3) == ix.tgt_sum;
 }
 
 extern "C" int cgx_index_copy_sa(cgx_ctx_t *c, int32_t *out) {
@@ -431,12 +449,6 @@ static void run_batch(cgx_ctx *c, int32_t Q, int32_t T, bool fetch, bool wait_co
         stage_twogap_enumerate(ix, b, s);
         CUDA_CHECK(cudaEventRecord(b.ev[4], s));
         stage_twogap_join(ix, b, s);
-    } catch (const CgxError &e) {
-        if (e.code == 3 && (b.adv_refused_q == 0 || Q < b.adv_refused_q)) b.adv_refused_q = Q;      // cgx_batch_advice
-        throw;
-    }
-    b.adv_ok_q = Q;
-    b.adv_ok_hits = (double)std::max(b.hits1, b.hits2);
     CUDA_CHECK(cudaEventRecord(b.ev[5], s));
     if (fetch) {   // the pattern tables and phrase ids are final here: they travel while extraction and aggregation run
         int32_t *hp = b.h_phrase_id.get<int32_t>((size_t)T * CGX_LONGEST_SRC + 1);
@@ -451,6 +463,12 @@ static void run_batch(cgx_ctx *c, int32_t Q, int32_t T, bool fetch, bool wait_co
     stage_extract(ix, b, s);
     CUDA_CHECK(cudaEventRecord(b.ev[6], s));
     stage_aggregate(ix, b, s);
+    } catch (const CgxError &e) {                       // refused (hit / cell indices, or device memory): remembered for cgx_batch_advice
+        if (e.code == 3 && (b.adv_refused_q == 0 || Q < b.adv_refused_q)) b.adv_refused_q = Q;
+        throw;
+    }
+    b.adv_ok_q = Q;
+    b.adv_ok_hits = (double)std::max(b.hits1, b.hits2);
     if (fetch) {   // the batch ends when the last result byte is on the host
         CUDA_CHECK(cudaEventRecord(b.done_ev, b.copy_stream));
         if (wait_copies) CUDA_CHECK(cudaStreamWaitEvent(s, b.done_ev, 0));

@@ -64,8 +64,23 @@ struct DevBuf {
         size_t bytes = count * sizeof(T);
         if (bytes > cap) {
             if (p && owned) CUDA_CHECK(cudaFree(p));
+            p = nullptr;
+            cap = 0;
             size_t want = bytes + bytes / 4 + 256;
-            CUDA_CHECK(cudaMalloc(&p, want));
+            cudaError_t e = cudaMalloc(&p, want);
+            if (e == cudaErrorMemoryAllocation) {                  // without the slack, then give up: the caller's batch is too large for
+                (void)cudaGetLastError();                          // what the index leaves of the HBM -- CGX_E_BATCH_TOO_LARGE, callers split it
+                want = bytes + 256;
+                e = cudaMalloc(&p, want);
+                if (e == cudaErrorMemoryAllocation) {
+                    (void)cudaGetLastError();
+                    p = nullptr;
+                    char b_[160];
+                    snprintf(b_, sizeof b_, "batch too large: out of device memory (%zu MB buffer)", want >> 20);
+                    throw CgxError{b_, 3};
+                }
+            }
+            CUDA_CHECK(e);
             cap = want;
             owned = true;
         }

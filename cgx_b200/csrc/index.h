@@ -62,6 +62,7 @@ struct Index {
     uint32_t lex_hash_mask = 0;
     int32_t freq_list[CGX_PRECOMP];
     bool built = false;
+    uint64_t src_sum = 0, tgt_sum = 0;     // FNV-1a of the token arrays the index was built from (cgx_index_matches; 0 = unknown)
     bool wide = false;          // 16-bit alignment fields (align_fields.cuh): RLP / xw are uint64, L_tar / R_tar uint16, lr uint4
     SaStats sa_stats;
 };

@@ -228,7 +228,7 @@ int cgxh_run(const cgxh_options_t *opt) {
     }
     cgx_index_info_t ii;
     cgx_index_info(ctx[0], &ii);
-    if (ii.n != src.n || ii.m != tgt.n) { fprintf(stderr, "index file %s was built from another corpus (%lld / %lld tokens, corpus has %lld / %lld)\n", opt->index_file ? opt->index_file : "?", (long long)ii.n, (long long)ii.m, (long long)src.n, (long long)tgt.n); return 1; }
+    if (ii.n != src.n || ii.m != tgt.n || !cgx_index_matches(ctx[0], src.tok, src.n, tgt.tok, tgt.n)) { fprintf(stderr, "index file %s was built from another corpus (%lld / %lld tokens, corpus has %lld / %lld)\n", opt->index_file ? opt->index_file : "?", (long long)ii.n, (long long)ii.m, (long long)src.n, (long long)tgt.n); return 1; }
     fprintf(stderr, "SA Construction %.4f sec (GPU prefix doubling, %d rounds, %d-bit keys); auxiliary index %.4f sec; %.1f MB resident\n",
             ii.sa_build_ms / 1e3, ii.sa_rounds, ii.sa_key_bits, ii.aux_build_ms / 1e3, (double)ii.index_bytes / 1048576.0);
     if (n_gpus > 1 && cgx_index_broadcast(ctx, n_gpus)) { fprintf(stderr, "cgx_index_broadcast: %s\n", cgx_last_error(ctx[0])); return 1; }

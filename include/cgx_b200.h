@@ -103,6 +103,9 @@ int cgx_index_broadcast(cgx_ctx_t **ctxs, int n);
  * promises separating the one-time costs).  cgx_index_load replaces cgx_index_build + cgx_lex_load. */
 int cgx_index_save(cgx_ctx_t *ctx, const char *path);
 int cgx_index_load(cgx_ctx_t *ctx, const char *path);
+/* 1 when the resident index was built from exactly these token arrays (same lengths, same FNV-1a checksums, which the index
+ * file records); 0 otherwise.  strmatchcuda -i refuses an index file that belongs to another corpus of the same length. */
+int cgx_index_matches(const cgx_ctx_t *ctx, const int32_t *src, int64_t n, const int32_t *tgt, int64_t m);
 
 /* parity helpers: copy index arrays to the host */
 int cgx_index_copy_sa(cgx_ctx_t *ctx, int32_t *sa_out);                    /* n ints */

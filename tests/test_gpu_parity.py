@@ -408,6 +408,20 @@ def test_persisted_index_round_trip(micro, micro_files, tmp_path):
         outs.append(out)
     cmp = gc.compare_dirs(str(outs[0]), str(outs[1]), rtol=0, atol=0)
     assert cmp["files"] == micro[0].n_qry and cmp["only_a"] == 0 and cmp["only_b"] == 0 and cmp["float_mismatch"] == 0, cmp
+    # an index file of ANOTHER corpus with the same token counts (one source word replaced by its neighbour) is refused: the
+    # file records checksums of the token arrays it was built from (cgx_index_matches)
+    words = open(micro_files["f"]).read().split("\n")
+    first = words[0].split()
+    k = next(i for i in range(len(first) - 1) if first[i] != first[i + 1])
+    first[k + 1] = first[k]
+    other = tmp_path / "other.f"
+    other.write_text("\n".join([" ".join(first)] + words[1:]))
+    out = tmp_path / "third"
+    out.mkdir()
+    r = subprocess.run([os.path.join(ROOT, "bin", "strmatchcuda"), "-i", str(idx), str(other), micro_files["q"], micro_files["e"], micro_files["a"],
+                        micro_files["lex"], str(out)], capture_output=True, text=True)
+    assert r.returncode != 0 and "was built from another corpus" in r.stderr, r.stderr[-1500:]
+    assert not os.path.exists(str(idx) + ".tmp")                       # saves go through <file>.tmp + rename
 
 
 def test_medium_scale_properties():

@@ -23,8 +23,8 @@ from cgx_b200.extractor import GrammarExtractor  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_040_000_000
 V = int(sys.argv[2]) if len(sys.argv) > 2 else 50_000
-NQ = int(sys.argv[3]) if len(sys.argv) > 3 else 2000
-BATCH = int(sys.argv[4]) if len(sys.argv) > 4 else 500
+NQ = int(sys.argv[3]) if len(sys.argv) > 3 else 1000
+BATCH = int(sys.argv[4]) if len(sys.argv) > 4 else 200
 SENT = 26                                    # 25 tokens + EOS
 n = (n // SENT) * SENT + 2                   # whole sentences + the reference's trailer "1, V+2" (Start.cu:321-330)
 dev = torch.device("cuda", 0)
@@ -64,8 +64,8 @@ e = (f.astype(np.int64) * 7919 % V + 2).astype(np.int32)
 lay.update(lex_f=np.concatenate([f, f, np.full_like(f, -1)]), lex_e=np.concatenate([e, np.full_like(e, -1), e]),
            lex_v1=np.concatenate([np.full(len(f), 0.5, np.float32), np.full(len(f), 0.01, np.float32), np.full(len(f), 0.02, np.float32)]),
            lex_v2=np.concatenate([np.full(len(f), 0.4, np.float32), np.full(len(f), 0.03, np.float32), np.full(len(f), 0.04, np.float32)]))
-del idx, P, eos, aligned, L, rlp, lt, tgt
-torch.cuda.empty_cache()
+del idx, P, eos, aligned, L, rlp, lt, tgt, s
+torch.cuda.empty_cache()                     # the corpus lives on the host from here; HBM belongs to the index and the batches
 print("corpus: %d tokens synthesised in %.1f s" % (n, time.time() - t0), flush=True)
 
 ex = GrammarExtractor(0)

@@ -1,9 +1,6 @@
 #!/bin/bash
-# Scratch driver for one gpurun call of this round (development only).  Everything lands in gpurun_out/r2/.
 out=gpurun_out/r2; mkdir -p $out
 tag=${1:-a}
-timeout 2400 python -m pytest tests -m gpu -q --durations=8 > $out/pytest_$tag.log 2>&1; echo "pytest rc=$?" | tee -a $out/status_$tag.log
-tail -14 $out/pytest_$tag.log
-/usr/bin/time -v timeout 2400 python bench.py > $out/bench_$tag.json 2> $out/bench_$tag.err; echo "bench rc=$?" | tee -a $out/status_$tag.log
-grep -v "^\s" $out/bench_$tag.err | tail -12; grep "Elapsed (wall" $out/bench_$tag.err
-python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke_$tag.log 2>&1; echo "smoke rc=$?" | tee -a $out/status_$tag.log
+t0=$(date +%s)
+timeout 1500 python tools/c4_probe.py 1040000000 50000 1000 200 > $out/c4_probe_$tag.log 2>&1; echo "c4 rc=$? in $(( $(date +%s) - t0 )) s" | tee -a $out/status_$tag.log
+tail -16 $out/c4_probe_$tag.log
