@@ -71,13 +71,13 @@ struct Batch {
     DevBuf ql_keys, ql_keys_tmp, q1_off, q1_ids, q2_off, q2_ids;
     int32_t enu1 = 0, D1 = 0;
     // joins
-    DevBuf j_tiles, j_bitmaps, j_aflag, j_aid, j_hash, j_status, j_segcnt, pat1_ga, hit_keys, hit_keys_tmp, counters, missing;
+    DevBuf j_tiles, j_bitmaps, j_aflag, j_aid, j_hash, j_status, j_segcnt, j_flags, pat1_ga, hit_keys, hit_keys_tmp, counters, missing;
     int64_t hits1 = 0, hits2 = 0, j1_elems = 0;
     int pbits = 30;                        // position field width of the packed hit keys (bits needed for n)
     size_t hit_cap = 0;
     int32_t adv_refused_q = 0, adv_ok_q = 0;   // cgx_batch_advice: smallest batch refused so far, size and hits of the last finished one
     double adv_ok_hits = 0.0;
-    uint32_t j1_buckets = 0;              // buckets of the last one-gap pattern table (kept when a batch had to grow it)
+    uint32_t j1_buckets = 0, j2_buckets = 0;              // buckets of the last one-gap pattern table (kept when a batch had to grow it)
     bool j1_smem_opt_in = false;          // j1_pos_ordered_kernel's dynamic shared memory opted in on this device
     DevBuf hits1_sorted, hits2_sorted;     // uint64 keys: pattern << (pbits+4) | pos << 4 | len-1  /  pattern << (pbits+8) | pos << 8 | g2 << 4 | L  (g2 = width of the second gap: c at pos+L+1+g2)
     // two-gap enumeration

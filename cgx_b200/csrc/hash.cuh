@@ -97,25 +97,26 @@ __device__ __forceinline__ bool pt_find(const PackTab t, uint64_t key, uint64_t 
 
 // ---- quotient table: 8-byte slots in 32-byte buckets (one sector), for keys too wide for PackTab.  A key is a pair (A, B) of
 // abits + bbits bits; it goes through a BIJECTION of that many bits built from 32-bit operations (add a multiple of B to A, odd
-// multiplies and xor-shifts of A inside abits bits, then xor B with bits of the result); the top bits of the image choose the
-// home bucket and only the remaining low bits -- the remainder, <= 28 bits -- are stored, so (bucket, remainder) still
+// multiplies and xor-shifts of A inside abits bits, then xor B with bits of the result; callers put the WIDER half in A, whose
+// top bits become the bucket number -- with the narrow half there, keys sharing it pile up in a few buckets); the top bits of the image choose the
+// home bucket and only the remaining low bits -- the remainder, <= 27 bits -- are stored, so (bucket, remainder) still
 // identifies the key exactly.  An entry that finds its home bucket full moves on to the next one (at most QT_MAX_DISP buckets
 // away) and records how far it went, so its remainder is read against the right home.
-//   slot = (remainder << 3 | displacement) << 32 | value          (value < 2^31, so no slot equals HT_EMPTY)
+//   slot = (remainder << 4 | displacement) << 32 | value          (value < 2^31, so no slot equals HT_EMPTY)
 // A bucket with an empty slot has never overflowed, which ends an unsuccessful lookup after one sector.  At <= 3 entries per
 // 4-slot bucket the one-gap pattern table of a C2 batch (5.9e6 patterns) is 67 MB instead of the 268 MB of the 16-byte form.
 struct QTab {
     unsigned long long *slots;
     uint32_t bmask;        // buckets - 1
-    int abits, bbits, rb;  // widths of the key halves; remainder bits = abits + bbits - log2(buckets), <= 28 (tag word < 2^31: never an empty slot's)
+    int abits, bbits, rb;  // widths of the key halves; remainder bits = abits + bbits - log2(buckets), <= 27 (tag word < 2^31: never an empty slot's)
 };
-constexpr int QT_MAX_DISP = 7;
+constexpr int QT_MAX_DISP = 15;
 
 static inline int qt_log2(uint32_t pow2) { int l = 0; while ((1u << l) < pow2) l++; return l; }
-// power of two; <= 3 entries per 4-slot bucket and enough buckets for the remainder to fit 28 bits
+// power of two; <= 3 entries per 4-slot bucket and enough buckets for the remainder to fit 27 bits
 static inline uint32_t qt_buckets_for(size_t entries, int key_bits) {
     uint32_t b = 256;
-    while ((size_t)b * 3 < entries || key_bits - qt_log2(b) > 28) b <<= 1;
+    while ((size_t)b * 3 < entries || key_bits - qt_log2(b) > 27) b <<= 1;
     return b;
 }
 
@@ -135,7 +136,7 @@ __device__ __forceinline__ uint64_t qt_mix(const QTab t, uint32_t A, uint32_t B)
 __device__ __forceinline__ bool qt_insert(const QTab t, uint32_t A, uint32_t B, uint32_t val) {
     const uint64_t x = qt_mix(t, A, B);
     const uint32_t home = (uint32_t)(x >> t.rb);
-    const uint32_t tag = (uint32_t)(x & ((1ull << t.rb) - 1ull)) << 3;
+    const uint32_t tag = (uint32_t)(x & ((1ull << t.rb) - 1ull)) << 4;
     for (int d = 0; d <= QT_MAX_DISP; d++) {
         unsigned long long *bk = t.slots + (size_t)((home + d) & t.bmask) * 4;
         const unsigned long long w = ((unsigned long long)(tag | (uint32_t)d) << 32) | val;
@@ -151,7 +152,7 @@ __device__ __forceinline__ bool qt_insert(const QTab t, uint32_t A, uint32_t B, 
 __device__ __forceinline__ void qt_touch(const QTab t, uint32_t A, uint32_t B, uint32_t *home, uint32_t *tag) {
     const uint64_t x = qt_mix(t, A, B);
     *home = (uint32_t)(x >> t.rb);
-    *tag = (uint32_t)(x & ((1ull << t.rb) - 1ull)) << 3;                // remainder | displacement 0
+    *tag = (uint32_t)(x & ((1ull << t.rb) - 1ull)) << 4;                // remainder | displacement 0
     asm volatile("prefetch.global.L1 [%0];" ::"l"(t.slots + (size_t)(*home & t.bmask) * 4));
 }
 __device__ __forceinline__ bool qt_resolve(const QTab t, uint32_t home, uint32_t tag, uint32_t *val) {

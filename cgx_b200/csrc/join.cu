@@ -334,14 +334,38 @@ __global__ void __launch_bounds__(JP_TILE) j1_pos_kernel(const JPArgs a) {
 // a slow one spun in the look-back holding its SM slot: join_onegap 13.0 -> 20.4 ms, join_twogap 11.0 -> 19.0 ms at C2.)
 // ------------------------------------------------------------------------------------------------
 constexpr int JO_TILE = 256;          // positions per CTA (8 warps x 32 positions)
-constexpr int JO_CAP = 1024;          // staged hits per warp; a tile with a fuller warp is walked a second time, writing directly
+constexpr int JO_CAP = 1024;          // most staged hits per warp the kernel may be given (6 bytes of dynamic shared memory each)
+constexpr int JO_CAP_DEFAULT = 512;   // default: 24 KB per CTA, five CTAs per SM; a fuller stage is flushed as one more chunk of the warp
 
 struct JOArgs {
     JPArgs p;
-    unsigned long long *seg_base;     // per tile: start of its segment in the (unordered) output
-    uint32_t *seg_count;              // per tile: hits
-    unsigned stage_cap;               // <= JO_CAP (tests lower it to drive tiles through the second, direct walk)
+    uint32_t *seg_base;               // per (warp, chunk): start of the chunk in the (unordered) output
+    uint32_t *seg_count;              // per (warp, chunk): hits (zeroed before the launch)
+    unsigned chunks_per_warp;         // chunk records per warp: enough for the most hits 32 positions can have
+    const uint8_t *flags;             // per position: first- / second-phrase bits (j1_flags_kernel)
+    unsigned stage_cap;               // staged hits per chunk, 32..JO_CAP (tests lower it to drive warps through many chunks)
 };
+
+// Per-batch position flags for the ordered scan: bit m-1 (m = 1..3) = the m-gram at this position is the first phrase of some
+// pattern, bit 2+m = it is the second phrase of some pattern, bit 6 = it is the second token of a frequent-pair pattern.  One
+// streamed pass (16 B read, 1 B written per position, seven L2-resident bitmap probes with every lane busy) takes the bitmap
+// probes out of the walk, where each was a dependent load in front of the table probe (11 % of its stall samples, r02b).
+__global__ void __launch_bounds__(256) j1_flags_kernel(const int4 *__restrict__ jwin, uint32_t n, const uint32_t *__restrict__ bma0, const uint32_t *__restrict__ bma1,
+                                                       const uint32_t *__restrict__ bma2, const uint32_t *__restrict__ bm0, const uint32_t *__restrict__ bm1,
+                                                       const uint32_t *__restrict__ bm2, const uint32_t *__restrict__ bm_marker, uint8_t *__restrict__ flags) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int4 w = __ldg(&jwin[p]);
+    unsigned f = 0;
+    f |= bit_test(bma0, (uint32_t)w.x) ? 1u : 0u;
+    f |= bit_test(bma1, (uint32_t)w.y) ? 2u : 0u;
+    f |= bit_test(bma2, (uint32_t)w.z) ? 4u : 0u;
+    f |= bit_test(bm0, (uint32_t)w.x) ? 8u : 0u;
+    f |= bit_test(bm1, (uint32_t)w.y) ? 16u : 0u;
+    f |= bit_test(bm2, (uint32_t)w.z) ? 32u : 0u;
+    f |= bit_test(bm_marker, (uint32_t)w.x) ? 64u : 0u;
+    flags[p] = (uint8_t)f;
+}
 
 // One walk over the 32 positions of this warp.  DIRECT = false: hits go to the warp's shared-memory stage (pattern id +
 // position-in-tile/length word) while they fit, and are counted either way; the featureMissingCount side effect and the
@@ -359,35 +383,58 @@ struct JQueue {
 };
 constexpr int JQ_CAP = 64;
 
-template <bool DIRECT>
-__device__ __forceinline__ unsigned jo_walk(const JPArgs &a, const int4 *__restrict__ s_win, int wrel, uint32_t P0, unsigned my_mask, const uint32_t my_aid[3],
-                                            uint32_t *__restrict__ st_pat, uint16_t *__restrict__ st_pl, unsigned stage_cap, unsigned long long out_base,
-                                            const JQueue q, unsigned &lookups, unsigned &elems) {
+// where a warp's hits go: a stage in shared memory that is flushed to the output as one CHUNK whenever the next batch of probes
+// might not fit -- a chunk takes its place in the output with one atomicAdd and is recorded as (start, count) under
+// (warp number, chunk number); chunks are later copied into (warp, chunk) order, i.e. position order
+struct JStage {
+    uint32_t *pat;                   // staged pattern ids
+    uint16_t *pl;                    // staged tile-relative position << 4 | length - 1
+    unsigned cap;                    // staged hits per chunk at most (>= 32)
+    uint32_t *seg_base, *seg_count;  // this warp's chunk records (chunks_per_warp of each)
+};
+
+__device__ __forceinline__ unsigned jo_walk(const JPArgs &a, const int4 *__restrict__ s_win, const uint8_t *__restrict__ s_flags, int wrel, uint32_t P0, unsigned my_mask, const uint32_t my_aid[3],
+                                            const JStage st, const JQueue q, unsigned &lookups, unsigned &elems) {
     const unsigned lane = threadIdx.x & 31, half = lane >> 4, h = lane & 15;
     const int g = (int)h + 1;
-    unsigned count = 0, queued = 0;                                // warp-uniform
+    unsigned count = 0, staged = 0, chunk = 0, queued = 0;         // warp-uniform
     uint32_t pend_home = 0, pend_tag = 0, pend_meta = 0;           // this lane's probe in flight
     bool pend = false;
+    auto flush = [&]() {                                           // all lanes call: the stage becomes the warp's next chunk
+        if (staged == 0) return;
+        unsigned long long base = 0;
+        if (lane == 0) {
+            base = atomicAdd(&a.counter[0], (unsigned long long)staged);
+            st.seg_base[chunk] = (uint32_t)base;                   // hits per batch < 2^31 (hit_limit); a batch beyond is refused before its list is read
+            st.seg_count[chunk] = staged;
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        __syncwarp();
+        for (unsigned i = lane; i < staged; i += 32) {
+            const unsigned long long dst = base + i;
+            const unsigned pl = st.pl[i];
+            if (dst < a.cap) a.hits[dst] = ((uint64_t)st.pat[i] << a.pshift) | ((uint64_t)(P0 + (pl >> 4)) << 4) | (uint64_t)(pl & 15u);
+        }
+        __syncwarp();
+        count += staged;
+        staged = 0;
+        chunk++;
+    };
     auto resolve_pending = [&]() {                                 // all lanes call
         uint32_t v = 0;
         bool found = pend && qt_resolve(a.tab, pend_home, pend_tag, &v);
         if (found && (pend_meta & 0x8000u)) {                      // frequent single-token pair failing only the alignment check
-            if (!DIRECT && (v & 1u)) atomicAdd(&a.missing[v >> 1], 1);
+            if (v & 1u) atomicAdd(&a.missing[v >> 1], 1);
             found = false;
         }
         const unsigned m = __ballot_sync(0xffffffffu, found);
+        if (staged + __popc(m) > st.cap) flush();
         if (found) {
-            const unsigned idx = count + __popc(m & lanemask_lt());
-            const uint32_t pat = v >> 1;
-            if (DIRECT) {
-                const unsigned long long o = out_base + idx;
-                if (o < a.cap) a.hits[o] = ((uint64_t)pat << a.pshift) | ((uint64_t)(P0 + ((pend_meta & 0x7fffu) >> 4)) << 4) | (uint64_t)(pend_meta & 15u);
-            } else if (idx < stage_cap) {
-                st_pat[idx] = pat;
-                st_pl[idx] = (uint16_t)(pend_meta & 0x7fffu);
-            }
+            const unsigned idx = staged + __popc(m & lanemask_lt());
+            st.pat[idx] = v >> 1;
+            st.pl[idx] = (uint16_t)(pend_meta & 0x7fffu);
         }
-        count += __popc(m);
+        staged += __popc(m);
         pend = false;
     };
     auto drain = [&](unsigned n_take) {                            // all lanes call; n_take <= 32 entries leave the queue
@@ -423,11 +470,11 @@ __device__ __forceinline__ unsigned jo_walk(const JPArgs &a, const int4 *__restr
             const int run = (int)((w >> 16) & 15u);
             const bool live = on && g <= run && g <= CGX_MAX_RULE_SPAN - 1 - ls;
             const bool ok = live && ((w >> (g - 1)) & 1u);
-            const bool miss = !DIRECT && live && !ok && (av >> 31);
+            const bool miss = live && !ok && (av >> 31);
             const int qrel = rel + ls + g;
             const uint32_t qpos = (uint32_t)(p + ls + g);
             const int le_max = min(min(3, CGX_MAX_RULE_SYMBOLS - 1 - ls), CGX_MAX_RULE_SPAN - ls - g);
-            if (!DIRECT && h == 0 && on) elems++;
+            if (h == 0 && on) elems++;
             uint32_t ub[3];
             bool cand[3];
             const int4 wq = (ok || miss) ? s_win[qrel] : make_int4(0, 0, 0, 0);
@@ -436,9 +483,10 @@ __device__ __forceinline__ unsigned jo_walk(const JPArgs &a, const int4 *__restr
                 cand[le - 1] = (ok && le <= le_max && qpos + (uint32_t)le <= a.n) || (miss && le == 1 && qpos < a.n);
                 ub[le - 1] = (uint32_t)(le == 1 ? wq.x : le == 2 ? wq.y : wq.z);
             }
+            const unsigned qf = (ok || miss) ? (unsigned)s_flags[qrel] : 0u;      // "second phrase of some pattern" bits of position q
 #pragma unroll
             for (int le = 1; le <= 3; le++)
-                if (cand[le - 1]) cand[le - 1] = bit_test((le == 1 && miss) ? a.bm_marker : a.bm[le - 1], ub[le - 1]);
+                cand[le - 1] = cand[le - 1] && ((qf >> ((le == 1 && miss) ? 6 : 2 + le)) & 1u);
 #pragma unroll
             for (int le = 1; le <= 3; le++) {
                 const unsigned m = __ballot_sync(0xffffffffu, cand[le - 1]);
@@ -448,7 +496,7 @@ __device__ __forceinline__ unsigned jo_walk(const JPArgs &a, const int4 *__restr
                     q.a[at] = ub[le - 1];
                     q.b[at] = key1_b(ga, le);
                     q.m[at] = (uint16_t)((rel << 4) | (ls + g + le - 1) | (miss ? 0x8000 : 0));
-                    if (!DIRECT) lookups++;
+                    lookups++;
                 }
                 queued += __popc(m);
                 __syncwarp();
@@ -458,19 +506,21 @@ __device__ __forceinline__ unsigned jo_walk(const JPArgs &a, const int4 *__restr
     }
     if (queued) drain(queued);
     resolve_pending();
+    flush();
     return count;
 }
 
 __global__ void __launch_bounds__(JO_TILE) j1_pos_ordered_kernel(const JOArgs o) {
     const JPArgs &a = o.p;
     __shared__ __align__(16) int4 s_win[JO_TILE + JP_HALO];
-    extern __shared__ __align__(16) unsigned char s_dyn[];          // per warp: JO_CAP pattern ids (u32), then JO_CAP position/length words (u16)
+    extern __shared__ __align__(16) unsigned char s_dyn[];          // per warp: stage_cap pattern ids (u32); then per warp stage_cap position/length words (u16)
+    __shared__ uint8_t s_flags[JO_TILE + JP_HALO + 7];
     __shared__ uint32_t s_qa[JO_TILE / 32][JQ_CAP], s_qb[JO_TILE / 32][JQ_CAP];
     __shared__ uint16_t s_qm[JO_TILE / 32][JQ_CAP];
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const JQueue jq{s_qa[warp], s_qb[warp], s_qm[warp]};
-    uint32_t *st_pat = reinterpret_cast<uint32_t *>(s_dyn) + (size_t)warp * JO_CAP;
-    uint16_t *st_pl = reinterpret_cast<uint16_t *>(s_dyn + sizeof(uint32_t) * JO_CAP * (JO_TILE / 32)) + (size_t)warp * JO_CAP;
+    uint32_t *st_pat = reinterpret_cast<uint32_t *>(s_dyn) + (size_t)warp * o.stage_cap;
+    uint16_t *st_pl = reinterpret_cast<uint16_t *>(s_dyn + sizeof(uint32_t) * o.stage_cap * (JO_TILE / 32)) + (size_t)warp * o.stage_cap;
     const uint32_t tile = blockIdx.x;
     const uint32_t P0 = tile * (uint32_t)JO_TILE;
     // the tile's window -- 273 consecutive 16-byte position records, 4.4 KB -- arrives by ONE bulk copy (cp.async.bulk, the TMA
@@ -485,11 +535,13 @@ __global__ void __launch_bounds__(JO_TILE) j1_pos_ordered_kernel(const JOArgs o)
         rs_bulk_g2s(s_win, a.jwin + P0, n_valid * (unsigned)sizeof(int4), &s_bar);
     }
     for (unsigned i = n_valid + tid; i < (unsigned)(JO_TILE + JP_HALO); i += JO_TILE) s_win[i] = make_int4(0, 0, 0, 0);
+    for (unsigned i = tid; i < (unsigned)(JO_TILE + JP_HALO); i += JO_TILE) s_flags[i] = i < n_valid ? __ldg(&o.flags[P0 + i]) : (uint8_t)0;
     rs_mbar_wait(&s_bar, 0);
     __syncthreads();                                                // the last CTA-wide barrier: the warps are independent from here on
     // lane l of warp w tests "does a first phrase start at position 32 w + l" for the three lengths
     const int wrel = (int)warp * 32;
     const int4 mine = s_win[wrel + (int)lane];
+    const unsigned my_flags = s_flags[wrel + (int)lane];
     uint32_t my_aid[3];
     unsigned my_mask = 0;
     const bool inside = P0 + (uint32_t)wrel + lane < a.n;
@@ -497,45 +549,35 @@ __global__ void __launch_bounds__(JO_TILE) j1_pos_ordered_kernel(const JOArgs o)
     for (int m = 0; m < 3; m++) {
         const uint32_t ub = (uint32_t)(m == 0 ? mine.x : m == 1 ? mine.y : mine.z);
         my_aid[m] = 0;
-        if (inside && bit_test(a.bma[m], ub)) { my_mask |= 1u << m; my_aid[m] = __ldg(&a.aid[m][ub]); }
+        if (inside && ((my_flags >> m) & 1u)) { my_mask |= 1u << m; my_aid[m] = __ldg(&a.aid[m][ub]); }
     }
     unsigned lookups = 0, elems = 0;
-    const unsigned count = jo_walk<false>(a, s_win, wrel, P0, my_mask, my_aid, st_pat, st_pl, o.stage_cap, 0ull, jq, lookups, elems);
-    // one output segment per WARP (32 positions), taken with one atomicAdd and recorded under the warp's number.  (Round 2a took one
-    // per tile: the warps of a tile then met at a barrier to add their counts up, and since hits per warp are heavy-tailed, 15 %
-    // of the kernel's stall samples were warps waiting there for the slowest of the eight.)
-    const uint32_t seg = tile * (JO_TILE / 32) + warp;
-    unsigned long long base = 0;
-    if (lane == 0) {
-        base = count ? atomicAdd(&a.counter[0], (unsigned long long)count) : 0ull;
-        o.seg_base[seg] = base;
-        o.seg_count[seg] = count;
-    }
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (count <= o.stage_cap) {
-        __syncwarp();
-        for (unsigned i = lane; i < count; i += 32) {
-            const unsigned long long dst = base + i;
-            const unsigned pl = st_pl[i];
-            if (dst < a.cap) a.hits[dst] = ((uint64_t)st_pat[i] << a.pshift) | ((uint64_t)(P0 + (pl >> 4)) << 4) | (uint64_t)(pl & 15u);
-        }
-    } else {                                                        // the stage overflowed: walk again, writing straight to the segment
-        unsigned l2 = 0, e2 = 0;
-        jo_walk<true>(a, s_win, wrel, P0, my_mask, my_aid, st_pat, st_pl, o.stage_cap, base, jq, l2, e2);
-    }
+    // output chunks are per WARP (32 positions).  (Round 2a took one segment per tile: the warps of a tile then met at a barrier to add
+    // their counts up, and since hits per warp are heavy-tailed, 15 % of the kernel's stall samples were warps waiting there for
+    // the slowest of the eight.  Round 2b staged a whole warp and walked a second time, writing directly, when the stage
+    // overflowed: 1024-hit stages cost occupancy, 512-hit stages cost second walks -- 10.1 vs 13.6 ms.)
+    const size_t seg = ((size_t)tile * (JO_TILE / 32) + warp) * o.chunks_per_warp;
+    const JStage st{st_pat, st_pl, o.stage_cap, o.seg_base + seg, o.seg_count + seg};
+    jo_walk(a, s_win, s_flags, wrel, P0, my_mask, my_aid, st, jq, lookups, elems);
     for (int off = 16; off; off >>= 1) { lookups += __shfl_xor_sync(0xffffffffu, lookups, off); elems += __shfl_xor_sync(0xffffffffu, elems, off); }
     if (lane == 0 && (lookups | elems)) { atomicAdd(&a.counter[1], (unsigned long long)lookups); atomicAdd(&a.counter[2], (unsigned long long)elems); }
 }
 
-// segments (in arrival order) -> their own order: dst[seg_dst[t] + i] = src[seg_base[t] + i]; one warp per segment
-__global__ void __launch_bounds__(256) seg_copy_kernel(const uint64_t *__restrict__ src, const unsigned long long *__restrict__ seg_base, const uint32_t *__restrict__ seg_dst,
-                                                       const uint32_t *__restrict__ seg_count, uint32_t n_segs, uint64_t *__restrict__ dst) {
-    const uint32_t t = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
-    if (t >= n_segs) return;
-    const uint32_t cnt = seg_count[t];
-    const uint64_t *s = src + seg_base[t];
-    uint64_t *d = dst + seg_dst[t];
-    for (uint32_t i = threadIdx.x & 31; i < cnt; i += 32) d[i] = s[i];
+// segments (in arrival order) -> their own order: dst[seg_dst[t] + i] = src[seg_base[t] + i].  One warp per group of `per`
+// consecutive segment records (the chunks of one scanning warp, filled in order: the first empty one ends the group)
+template <class BaseT>
+__global__ void __launch_bounds__(256) seg_copy_kernel(const uint64_t *__restrict__ src, const BaseT *__restrict__ seg_base, const uint32_t *__restrict__ seg_dst,
+                                                       const uint32_t *__restrict__ seg_count, uint32_t n_groups, uint32_t per, uint64_t *__restrict__ dst) {
+    const uint32_t grp = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (grp >= n_groups) return;
+    for (uint32_t k = 0; k < per; k++) {
+        const size_t t = (size_t)grp * per + k;
+        const uint32_t cnt = seg_count[t];
+        if (cnt == 0) { if (per > 1) break; else return; }
+        const uint64_t *s = src + seg_base[t];
+        uint64_t *d = dst + seg_dst[t];
+        for (uint32_t i = threadIdx.x & 31; i < cnt; i += 32) d[i] = s[i];
+    }
 }
 
 // per-pattern [start,count] in the sorted hit list
@@ -588,7 +630,7 @@ void stage_onegap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     uint32_t n_elems = 0;
     while (true) {
         tab.rb = tab.abits + tab.bbits - qt_log2(buckets); tab.bmask = buckets - 1;
-        CGX_REQUIRE(tab.rb >= 1 && tab.rb <= 28, "one-gap pattern table: %d remainder bits", tab.rb);
+        CGX_REQUIRE(tab.rb >= 1 && tab.rb <= 27, "one-gap pattern table: %d remainder bits", tab.rb);
         tab.slots = b.j_hash.get<unsigned long long>((size_t)buckets * 4);
         CUDA_CHECK(cudaMemsetAsync(bm, 0, sizeof(uint32_t) * 7 * bm_words, stream));
         CUDA_CHECK(cudaMemsetAsync(aflag, 0, sizeof(uint32_t) * ((size_t)G + 1), stream));
@@ -628,15 +670,20 @@ void stage_onegap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     // CGX_JOIN_ORDERED=0 keeps round 1's unordered append + full (pattern, position) sort for that variant too.
     bool ordered = position_major;
     if (const char *e = getenv("CGX_JOIN_ORDERED")) { if (!strcmp(e, "0")) ordered = false; }
-    const uint32_t n_tiles = cgx_div_up(ix.n, JO_TILE), n_segs = n_tiles * (JO_TILE / 32);       // one output segment per warp
+    const uint32_t n_tiles = cgx_div_up(ix.n, JO_TILE);
     JOArgs ao;
     uint32_t *seg_dst = nullptr;
+    size_t n_segs = 0;                                                                         // chunk records: warps x chunks per warp
     if (ordered) {
-        ao.seg_base = b.j_status.get<unsigned long long>((size_t)n_segs + 1);
-        ao.seg_count = b.j_segcnt.get<uint32_t>((size_t)2 * n_segs + 2);
+        ao.stage_cap = JO_CAP_DEFAULT;
+        if (const char *e = getenv("CGX_JOIN_STAGE_CAP")) { const unsigned v = (unsigned)strtoul(e, nullptr, 10); if (v >= 32 && v <= (unsigned)JO_CAP) ao.stage_cap = v; }
+        // a chunk leaves the stage with at least cap - 31 hits; 32 positions have at most 32 x 3 x 13 x 3 candidates
+        ao.chunks_per_warp = (32u * 3u * 13u * 3u) / (ao.stage_cap - 31u) + 2u;
+        n_segs = (size_t)n_tiles * (JO_TILE / 32) * ao.chunks_per_warp;
+        CGX_REQUIRE_BATCH(n_segs < (1ull << 32), "%zu output chunks", n_segs);
+        ao.seg_base = b.j_status.get<uint32_t>(n_segs + 1);
+        ao.seg_count = b.j_segcnt.get<uint32_t>(2 * n_segs + 2);
         seg_dst = ao.seg_count + n_segs + 1;
-        ao.stage_cap = JO_CAP;
-        if (const char *e = getenv("CGX_JOIN_STAGE_CAP")) { const unsigned v = (unsigned)strtoul(e, nullptr, 10); if (v >= 1 && v < (unsigned)JO_CAP) ao.stage_cap = v; }
         if (!b.j1_smem_opt_in) {      // per context = per device: the opt-in is a per-device attribute of the kernel
             CUDA_CHECK(cudaFuncSetAttribute(j1_pos_ordered_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JO_TILE / 32 * JO_CAP * 6));
             b.j1_smem_opt_in = true;
@@ -649,7 +696,13 @@ void stage_onegap_join(const Index &ix, Batch &b, cudaStream_t stream) {
         CUDA_CHECK(cudaMemsetAsync(missing, 0, sizeof(int32_t) * (size_t)D1, stream));
         if (n_elems && ordered) {
             ao.p = ap;
-            PROF("join_onegap", 0.0, (j1_pos_ordered_kernel<<<n_tiles, JO_TILE, JO_TILE / 32 * JO_CAP * 6, stream>>>(ao)));
+            uint8_t *fl = b.j_flags.get<uint8_t>((size_t)ix.n + 64);
+            PROF("join_setup", 17.0 * (double)ix.n, (j1_flags_kernel<<<cgx_div_up(ix.n, 256), 256, 0, stream>>>(ap.jwin, ap.n, ap.bma[0], ap.bma[1], ap.bma[2], ap.bm[0], ap.bm[1], ap.bm[2],
+                                                                                                   ap.bm_marker, fl)));
+            b.launches++;
+            ao.flags = fl;
+            CUDA_CHECK(cudaMemsetAsync(ao.seg_count, 0, sizeof(uint32_t) * n_segs, stream));        // unused chunk records count zero hits
+            PROF("join_onegap", 0.0, (j1_pos_ordered_kernel<<<n_tiles, JO_TILE, (size_t)(JO_TILE / 32) * ao.stage_cap * 6, stream>>>(ao)));
         } else if (n_elems && position_major) PROF("join_onegap", 0.0, (j1_pos_kernel<<<cgx_div_up(ix.n, JP_TILE), JP_TILE, 0, stream>>>(ap)));
         else if (n_elems) PROF("join_onegap", 0.0, (j1_scan_kernel<<<cgx_div_up(n_elems, J1_BLOCK), J1_BLOCK, 0, stream>>>(a)));
         b.launches += 1;
@@ -670,8 +723,9 @@ void stage_onegap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     uint64_t *hits = b.hit_keys.ptr<uint64_t>();
     uint64_t *tmp = b.hit_keys_tmp.get<uint64_t>(H);
     if (ordered) {      // the tiles' segments, in tile (= position) order
-        exclusive_scan_u32(ao.seg_count, seg_dst, (size_t)n_segs, nullptr, stream, b.scan, 0, &b.launches);
-        PROF("join_seg_copy", 16.0 * (double)H, (seg_copy_kernel<<<cgx_div_up(n_segs, 8), 256, 0, stream>>>(hits, ao.seg_base, seg_dst, ao.seg_count, n_segs, tmp)));
+        exclusive_scan_u32(ao.seg_count, seg_dst, n_segs, nullptr, stream, b.scan, 0, &b.launches);
+        PROF("join_seg_copy", 16.0 * (double)H, (seg_copy_kernel<uint32_t><<<cgx_div_up(n_segs / ao.chunks_per_warp, 8), 256, 0, stream>>>(hits, ao.seg_base, seg_dst, ao.seg_count,
+                                                                                                                                  (uint32_t)(n_segs / ao.chunks_per_warp), ao.chunks_per_warp, tmp)));
         b.launches++;
         std::swap(hits, tmp);
     }
@@ -698,17 +752,17 @@ void stage_onegap_join(const Index &ix, Batch &b, cudaStream_t stream) {
 // they cost a probe of the pattern table (round 1c: every admissible width of every parent hit probed the table).
 __device__ __forceinline__ unsigned sig_bit(uint32_t c) { return (c * 0x9E3779B1u) >> 26; }
 
-__global__ void j2_setup_kernel(const Pat2 *__restrict__ pat2, int D2, PackTab tab, int cbits, unsigned long long *__restrict__ child_sig) {
+__global__ void j2_setup_kernel(const Pat2 *__restrict__ pat2, int D2, QTab tab, uint32_t *__restrict__ overflow, unsigned long long *__restrict__ child_sig) {
     int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= D2) return;
     const Pat2 p = pat2[d];
-    pt_insert(tab, ((uint64_t)(uint32_t)p.pat1 << cbits) | (uint64_t)(uint32_t)p.ctok, (uint64_t)d);
+    if (!qt_insert(tab, (uint32_t)p.pat1, (uint32_t)p.ctok, (uint32_t)d)) *overflow = 1u;      // key: (parent pattern, token c) -> two-gap pattern id
     atomicOr(&child_sig[p.pat1], 1ull << sig_bit((uint32_t)p.ctok));
 }
 
 __global__ void __launch_bounds__(256) j2_scan_kernel(const uint64_t *__restrict__ hits1, size_t H1, int pbits, const unsigned long long *__restrict__ child_sig,
                                                       const int32_t *__restrict__ str, const uint32_t *__restrict__ gapw,
-                                                      const PackTab tab, int cbits,
+                                                      const QTab tab,
                                                       unsigned long long *__restrict__ counter, uint64_t *__restrict__ hits, size_t cap) {
     __shared__ uint64_t s_stage[256 / 32][ST_CAP];
     uint64_t *stage = s_stage[threadIdx.x >> 5];
@@ -734,7 +788,7 @@ __global__ void __launch_bounds__(256) j2_scan_kernel(const uint64_t *__restrict
     while (__any_sync(0xffffffffu, bits != 0)) {       // every round each lane tries its next (up to) four admissible widths:
         int rr[4];                                     // tokens, then first table probes, issued together
         uint32_t cc[4], ss[4];
-        unsigned long long sv[4];
+        uint32_t st[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             rr[u] = 0;
@@ -745,13 +799,13 @@ __global__ void __launch_bounds__(256) j2_scan_kernel(const uint64_t *__restrict
 #pragma unroll
         for (int u = 0; u < 4; u++) if (rr[u] && !((sig >> sig_bit(cc[u])) & 1ull)) rr[u] = 0;      // not a child token of this parent
 #pragma unroll
-        for (int u = 0; u < 4; u++) if (rr[u]) sv[u] = pt_first(tab, ((uint64_t)d1 << cbits) | (uint64_t)cc[u], &ss[u]);
+        for (int u = 0; u < 4; u++) if (rr[u]) qt_touch(tab, d1, cc[u], &ss[u], &st[u]);
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             if (!__any_sync(0xffffffffu, rr[u] != 0)) continue;
-            uint64_t d2 = 0;
-            const bool found = rr[u] && pt_resolve(tab, ((uint64_t)d1 << cbits) | (uint64_t)cc[u], ss[u], sv[u], &d2);
-            const uint64_t key = (d2 << (pbits + 8)) | ((uint64_t)(uint32_t)p << 8) | ((uint64_t)(rr[u] - p - L - 1) << 4) | (uint64_t)L;   // (pattern, position, width, length)
+            uint32_t d2 = 0;
+            const bool found = rr[u] && qt_resolve(tab, ss[u], st[u], &d2);
+            const uint64_t key = ((uint64_t)d2 << (pbits + 8)) | ((uint64_t)(uint32_t)p << 8) | ((uint64_t)(rr[u] - p - L - 1) << 4) | (uint64_t)L;   // (pattern, position, width, length)
             stage_push(found, key, stage, staged);
         }
         if (staged > ST_CAP - 128) stage_flush(stage, staged, &counter[0], hits, cap);
@@ -775,7 +829,7 @@ __global__ void __launch_bounds__(256) j2_scan_kernel(const uint64_t *__restrict
 constexpr int J2O_SLOTS = CGX_MAX_RULE_SPAN - 2;       // widths 1..13
 constexpr int J2O_STRIDE = 240;                        // 256 - 16 >= 256 - (longest run - 1)
 __global__ void __launch_bounds__(256) j2_ordered_kernel(const uint64_t *__restrict__ hits1, size_t H1, int pbits, const unsigned long long *__restrict__ child_sig,
-                                                         const int32_t *__restrict__ str, const uint32_t *__restrict__ gapw, const PackTab tab, int cbits,
+                                                         const int32_t *__restrict__ str, const uint32_t *__restrict__ gapw, const QTab tab,
                                                          unsigned long long *__restrict__ counter, unsigned long long *__restrict__ seg_base,
                                                          uint32_t *__restrict__ seg_count, uint64_t *__restrict__ hits, size_t cap) {
     __shared__ uint32_t s_d2[J2O_SLOTS][256];           // hits parked by [width - 1][owner thread]
@@ -825,17 +879,24 @@ __global__ void __launch_bounds__(256) j2_ordered_kernel(const uint64_t *__restr
     s_mask[tid] = 0;
     __syncwarp();
     unsigned queued = 0;                                // warp-uniform
-    auto drain = [&](unsigned n_take) {                 // probe the first n_take (<= 32) queue entries, shift the rest down
+    uint32_t pend_home = 0, pend_tag = 0, pend_own = 0;
+    bool pend = false;
+    auto resolve_pending = [&]() {                      // the probes requested by the previous drain: their sectors have had the walk in between to arrive
+        uint32_t d2 = 0;
+        if (pend && qt_resolve(tab, pend_home, pend_tag, &d2)) {
+            const unsigned ot = (tid & ~31u) + (pend_own >> 4);
+            s_d2[pend_own & 15u][ot] = d2;
+            atomicOr(&s_mask[ot], 1u << (pend_own & 15u));
+        }
+        pend = false;
+    };
+    auto drain = [&](unsigned n_take) {                 // the first n_take (<= 32) queue entries leave the queue: request their buckets, shift the rest down
+        resolve_pending();
         const bool on = lane < n_take;
         const unsigned own = on ? q_own[lane] : 0u;     // owner lane << 4 | width - 1
         const uint32_t tokc = on ? q_tok[lane] : 0u;
         const uint32_t d1o = __shfl_sync(0xffffffffu, d1, own >> 4);
-        uint64_t d2 = 0;
-        if (on && pt_find(tab, ((uint64_t)d1o << cbits) | (uint64_t)tokc, &d2)) {
-            const unsigned ot = (tid & ~31u) + (own >> 4);
-            s_d2[own & 15u][ot] = (uint32_t)d2;
-            atomicOr(&s_mask[ot], 1u << (own & 15u));
-        }
+        if (on) { qt_touch(tab, d1o, tokc, &pend_home, &pend_tag); pend_own = own; pend = true; }
         __syncwarp();
         const unsigned rest = queued - n_take;
         uint32_t t2 = 0; uint16_t o2 = 0;
@@ -865,6 +926,7 @@ __global__ void __launch_bounds__(256) j2_ordered_kernel(const uint64_t *__restr
         }
     }
     if (queued) drain(queued);
+    resolve_pending();
     __syncwarp();
     unsigned found_mask = s_mask[tid];
     const unsigned c = __popc(found_mask);              // widths that hit (bit g2-1), their count
@@ -926,18 +988,34 @@ void stage_twogap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     const int D2 = b.D2;
     if (D2 == 0 || b.hits1 == 0) return;
     CGX_REQUIRE(cgx_bits_for((uint64_t)D2) + b.pbits + 8 <= 64, "two-gap join: %d distinct patterns exceed the hit-key field", D2);
-    // corpus tokens never exceed maxtok, so (parent id, token) fits dbits1 + cbits
-    const int cbits = cgx_bits_for((uint64_t)ix.maxtok), d2bits = cgx_bits_for((uint64_t)D2);
-    CGX_REQUIRE_BATCH(cgx_bits_for((uint64_t)b.D1) + cbits + d2bits <= 63, "%d x %d patterns do not fit the packed two-gap pattern table", b.D1, D2);
-    const uint32_t slots_n = pt_slots_for((size_t)D2);
-    PackTab tab{b.j_hash.get<unsigned long long>(slots_n), slots_n - 1, d2bits};
+    // per-batch table of the two-gap patterns (hash.cuh QTab): key = (parent one-gap pattern, token c), value = pattern id.  Buckets
+    // of four 8-byte slots: a probe is one sector, and a miss -- one in ten tokens passes the child signature without being a
+    // child -- ends at the first bucket that is not full (the packed linear-probing table of round 1 walked ~6 slots for a miss
+    // at its load factor: a fifth of the kernel's stall samples, r02b)
+    QTab tab;
+    tab.abits = std::max(cgx_bits_for((uint64_t)b.D1), 10); tab.bbits = cgx_bits_for((uint64_t)ix.maxtok);      // the wider half first (hash.cuh)
+    CGX_REQUIRE_BATCH(tab.bbits <= 24 && tab.bbits >= 1 && D2 < (1 << 30), "%d x %d patterns exceed the two-gap pattern-table fields", b.D1, D2);
+    uint32_t buckets = qt_buckets_for((size_t)D2, tab.abits + tab.bbits);
+    if (b.j2_buckets > buckets && b.j2_buckets <= 4 * buckets) buckets = b.j2_buckets;
     unsigned long long *child_sig = b.j_aflag.get<unsigned long long>((size_t)b.D1 + 1);
     uint32_t *tot = b.counters.get<uint32_t>(32);
     unsigned long long *ctr = (unsigned long long *)(tot + 4);
-    CUDA_CHECK(cudaMemsetAsync(tab.slots, 0xff, sizeof(unsigned long long) * (size_t)slots_n, stream));
-    CUDA_CHECK(cudaMemsetAsync(child_sig, 0, sizeof(unsigned long long) * (size_t)b.D1, stream));
-    PROF("join_setup", (double)D2 * (16 + 8), (j2_setup_kernel<<<cgx_div_up(D2, 256), 256, 0, stream>>>(b.pat2.ptr<Pat2>(), D2, tab, cbits, child_sig)));
-    b.launches++;
+    while (true) {
+        tab.rb = tab.abits + tab.bbits - qt_log2(buckets); tab.bmask = buckets - 1;
+        CGX_REQUIRE(tab.rb >= 1 && tab.rb <= 27, "two-gap pattern table: %d remainder bits", tab.rb);
+        tab.slots = b.j_hash.get<unsigned long long>((size_t)buckets * 4);
+        CUDA_CHECK(cudaMemsetAsync(tab.slots, 0xff, sizeof(unsigned long long) * (size_t)buckets * 4, stream));
+        CUDA_CHECK(cudaMemsetAsync(child_sig, 0, sizeof(unsigned long long) * (size_t)b.D1, stream));
+        CUDA_CHECK(cudaMemsetAsync(tot + 1, 0, sizeof(uint32_t), stream));
+        PROF("join_setup", (double)D2 * (16 + 8), (j2_setup_kernel<<<cgx_div_up(D2, 256), 256, 0, stream>>>(b.pat2.ptr<Pat2>(), D2, tab, tot + 1, child_sig)));
+        b.launches++;
+        uint32_t over = 0;
+        cgx_read_back(&over, tot + 1, sizeof(over), stream);
+        if (!over) break;
+        buckets *= 2;
+        CGX_REQUIRE(buckets <= (1u << 28), "two-gap pattern table does not settle");
+    }
+    b.j2_buckets = buckets;
     const size_t H1 = (size_t)b.hits1;
     unsigned long long host_ctr[3] = {0, 0, 0};
     bool ordered = true;                                   // CGX_JOIN_ORDERED=0: round 1's unordered append + full sort
@@ -951,10 +1029,10 @@ void stage_twogap_join(const Index &ix, Batch &b, cudaStream_t stream) {
         CUDA_CHECK(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long) * 3, stream));
         if (ordered) {
             PROF("join_twogap", 0.0, (j2_ordered_kernel<<<n_tiles, 256, 0, stream>>>(b.hits1_sorted.ptr<uint64_t>(), H1, b.pbits, child_sig, ix.str.ptr<int32_t>(),
-                                                               ix.gapw.ptr<uint32_t>(), tab, cbits, ctr, seg_base, seg_count, hits, b.hit_cap)));
+                                                               ix.gapw.ptr<uint32_t>(), tab, ctr, seg_base, seg_count, hits, b.hit_cap)));
         } else
         PROF("join_twogap", 0.0, (j2_scan_kernel<<<cgx_div_up(H1, 256), 256, 0, stream>>>(b.hits1_sorted.ptr<uint64_t>(), H1, b.pbits, child_sig, ix.str.ptr<int32_t>(),
-                                                           ix.gapw.ptr<uint32_t>(), tab, cbits, ctr, hits, b.hit_cap)));
+                                                           ix.gapw.ptr<uint32_t>(), tab, ctr, hits, b.hit_cap)));
         b.launches += 1;
         read_u64s(host_ctr, ctr, 3, stream);
         CGX_REQUIRE_BATCH(host_ctr[0] < hit_limit(), "%llu two-gap hits", host_ctr[0]);
@@ -969,7 +1047,7 @@ void stage_twogap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     uint64_t *tmp = b.hit_keys_tmp.get<uint64_t>(H);
     if (ordered) {
         exclusive_scan_u32(seg_count, seg_dst, (size_t)n_tiles, nullptr, stream, b.scan, 0, &b.launches);
-        PROF("join_seg_copy", 16.0 * (double)H, (seg_copy_kernel<<<cgx_div_up(n_tiles, 8), 256, 0, stream>>>(hits, seg_base, seg_dst, seg_count, n_tiles, tmp)));
+        PROF("join_seg_copy", 16.0 * (double)H, (seg_copy_kernel<unsigned long long><<<cgx_div_up(n_tiles, 8), 256, 0, stream>>>(hits, seg_base, seg_dst, seg_count, n_tiles, 1u, tmp)));
         b.launches++;
         std::swap(hits, tmp);
     }

@@ -327,6 +327,7 @@ class GrammarExtractor:
         Q = len(qo) - 1
         todo = [(a, min(Q, a + batch_queries)) for a in range(0, Q, batch_queries)][::-1]
         infos, prev = [], None
+        self.stream_refusals = 0                                      # batches refused (and split) by this stream
         while todo:
             q0, q1 = todo.pop()
             fit = int(self.L.cgx_batch_advice(self.h, q1 - q0))       # from the hits per query of the last batch: at most one refusal per stream
@@ -337,6 +338,7 @@ class GrammarExtractor:
             o = np.ascontiguousarray(qo[q0:q1 + 1] - qo[q0])
             rc = self.L.cgx_extract_begin(self.h, _p(np.ascontiguousarray(t), C.c_int32), _p(o, C.c_int32), q1 - q0)
             if rc == 3 and q1 - q0 > 1:
+                self.stream_refusals += 1
                 mid = (q0 + q1) // 2
                 todo += [(mid, q1), (q0, mid)]
                 continue

@@ -351,6 +351,13 @@ def test_oversized_batches_are_split(micro, micro_files, tmp_path, monkeypatch):
 
     infos = ex.extract_stream(tok, off, batch_queries=full.Q, on_batch=on_batch)
     assert len(infos) >= 3 and [got[q] for q in range(full.Q)] == want
+    # cgx_batch_advice: the refusals of that stream are remembered -- the same queries again, asked for in one batch, are cut to a
+    # size expected to fit before anything runs, so the second stream pays for fewer refused scans (none, when the queries are alike)
+    first_refusals = ex.stream_refusals
+    assert first_refusals >= 1 and ex.L.cgx_batch_advice(ex.h, full.Q) < full.Q
+    got.clear()
+    infos2 = ex.extract_stream(tok, off, batch_queries=full.Q, on_batch=on_batch)
+    assert ex.stream_refusals <= max(0, first_refusals - 1) and len(infos2) >= 2 and [got[q] for q in range(full.Q)] == want
     outs = []
     for name in ("plain", "split"):
         out = tmp_path / name
@@ -498,8 +505,8 @@ def test_join_variants_agree_with_oracle(mode, ordered, micro, micro_oracle, mon
     oracle's hit list, two-gap hits and missing counts bit for bit."""
     from cgx_b200.extractor import GrammarExtractor
     monkeypatch.setenv("CGX_JOIN_MODE", mode)
-    if ordered == "direct":                                 # a 4-hit stage: most tiles overflow it and take the second, direct walk
-        monkeypatch.setenv("CGX_JOIN_STAGE_CAP", "4")
+    if ordered == "direct":                                 # a 40-hit stage: most warps flush it several times (many chunks per warp)
+        monkeypatch.setenv("CGX_JOIN_STAGE_CAP", "40")
         ordered = "1"
     monkeypatch.setenv("CGX_JOIN_ORDERED", ordered)
     _, lay = micro
