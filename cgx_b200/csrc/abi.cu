@@ -66,7 +66,7 @@ extern "C" void cgx_destroy(cgx_ctx_t *c) {
                     &b.phrases, &b.e1_count, &b.e1_inst, &b.e1_keys, &b.e1_keys_tmp, &b.e1_vals, &b.e1_vals_tmp, &b.e1_flags, &b.e1_pid, &b.pat1,
                     &b.pat1_dev, &b.pat1_pos, &b.ql_keys, &b.ql_keys_tmp, &b.q1_off, &b.q1_ids, &b.q2_off, &b.q2_ids, &b.j_tiles, &b.j_bitmaps, &b.j_aflag, &b.j_aid, &b.j_hash, &b.j_status, &b.j_segcnt, &b.j_flags, &b.pat1_ga, &b.hit_keys,
                     &b.hit_keys_tmp, &b.counters, &b.missing, &b.hits1_sorted, &b.hits2_sorted, &b.e2_count, &b.e2_keys, &b.e2_keys_tmp, &b.e2_vals,
-                    &b.e2_vals_tmp, &b.e2_flags, &b.pat2, &b.rec_hash, &b.rec_tag, &b.rec_live, &b.rec_flags, &b.rec_meta, &b.rec_cnt,
+                    &b.e2_vals_tmp, &b.e2_flags, &b.pat2, &b.rec_hash, &b.rec_tag, &b.rec_live, &b.rec_list, &b.slot_hint, &b.rec_flags, &b.rec_meta, &b.rec_cnt,
                     &b.scratch, &b.scratch2, &b.rule_head, &b.rule_id, &b.radix.hist, &b.radix.status, &b.radix.counters};
     for (auto *x : bb) x->release();
     for (int k = 0; k < 3; k++) { b.slot_off[k].release(); b.rec[k].release(); b.rules[k].release(); b.updown[k].release(); b.idinfo[k].release(); b.id_count[k].release(); }

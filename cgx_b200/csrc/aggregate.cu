@@ -130,15 +130,27 @@ __device__ __forceinline__ bool same_target(const int32_t *__restrict__ tgt, con
 //   so heads need no forward scan of the segment for their paircount (round 1b: heads, 60 % of the records, scanned the
 //   whole segment twice; 8 of 32 lanes active on average).  The backward scan reads the 4-byte tags (shared with the
 //   neighbouring threads: L1 broadcast) four at a time and stops at the first equal cell.
+// (Three quarters of the cells are empty -- a slot emits a record of a shape or not -- and round 1 ran this kernel over all of them
+// with 8 of 32 lanes alive.  Since round 2 the live cells are listed first (agg_live_list_kernel: the exclusive scan of the live
+// flags is needed for the f counts anyway) and thread j takes the j-th live cell: full warps, neighbouring lanes in one segment.)
+__global__ void __launch_bounds__(256) agg_live_list_kernel(const uint64_t *__restrict__ hash, const uint32_t *__restrict__ live_before, uint32_t cells,
+                                                            uint32_t *__restrict__ live_list, uint32_t *__restrict__ flags) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cells) return;
+    if (hash[i] != 0) live_list[live_before[i]] = i;
+    else flags[i] = 0;                                       // an empty cell heads no rule
+}
+
 __global__ void __launch_bounds__(256) agg_group_kernel(AggLayout lay, const RuleRec *__restrict__ rec, const uint64_t *__restrict__ hash,
                                                         const uint32_t *__restrict__ tag, const uint32_t *__restrict__ live_before,
+                                                        const uint32_t *__restrict__ live_list,
                                                         const int32_t *__restrict__ tgt, uint32_t *__restrict__ flags,
                                                         unsigned long long *__restrict__ acc_best, uint32_t *__restrict__ acc_cnt,
                                                         int *__restrict__ collision) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= lay.cells) return;
+    const uint32_t j0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j0 >= live_before[lay.cells]) return;                // live_before[cells] = number of live cells
+    const uint32_t i = live_list[j0];
     const uint64_t h = hash[i];
-    if (h == 0) { flags[i] = 0; return; }
     const uint32_t t = (uint32_t)h;
     const RuleRec r = rec[i];
     int reg = 0;
@@ -361,7 +373,10 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
             PROF("agg_hash", (double)N * 44, (agg_hash_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(rec, N, ix.tgt.ptr<int32_t>(), seed, hash, tag, live, acc_best, acc_cnt)));
             exclusive_scan_u32(live, live, N, tot + 16, stream, b.scan, 0, &b.launches);          // live[N] = total below
             CUDA_CHECK(cudaMemcpyAsync(live + N, tot + 16, sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
-            PROF("agg_group", (double)N * (8 + 4), (agg_group_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(lay[kind], rec, hash, tag, live, ix.tgt.ptr<int32_t>(), flags, acc_best, acc_cnt, collision)));
+            uint32_t *live_list = b.rec_list.get<uint32_t>((size_t)N + 2);
+            PROF("agg_group", (double)N * (8 + 4 + 4), (agg_live_list_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(hash, live, N, live_list, flags)));
+            PROF("agg_group", 0.0, (agg_group_kernel<<<cgx_div_up(N, 256), 256, 0, stream>>>(lay[kind], rec, hash, tag, live, live_list, ix.tgt.ptr<int32_t>(), flags, acc_best, acc_cnt, collision)));
+            b.launches++;
             exclusive_scan_u32(flags, flags, N, tot, stream, b.scan, 0, &b.launches);
             b.launches += 2;
             uint32_t hostv[20];

@@ -84,7 +84,7 @@ struct Batch {
     DevBuf e2_count, e2_keys, e2_keys_tmp, e2_vals, e2_vals_tmp, e2_flags, pat2;
     int32_t enu2 = 0, D2 = 0;
     // extraction
-    DevBuf slot_off[3], rec[3], rec_hash, rec_tag, rec_live, rec_flags, rec_meta, rec_cnt;   // rec[k]: slot-indexed cells (extract.cu), empty cells have id = -1
+    DevBuf slot_off[3], slot_hint, rec[3], rec_hash, rec_tag, rec_live, rec_list, rec_flags, rec_meta, rec_cnt;   // rec[k]: slot-indexed cells (extract.cu), empty cells have id = -1
     size_t rec_cells[3] = {0, 0, 0};       // cells per kind
     int64_t n_slots[3] = {0, 0, 0};        // sampled-occurrence slots: contiguous / one-gap / two-gap
     int64_t n_rec[3] = {0, 0, 0};          // non-empty cells per kind
