@@ -700,7 +700,7 @@ extern "C" int64_t cgx_debug_fetch(cgx_ctx_t *c, const char *what, int32_t *out,
             for (size_t i = 0; i < H; i++) {
                 const uint64_t pm = (1ull << b.pbits) - 1;
                 if (two) { out[4 * i] = (int32_t)(h[i] >> (b.pbits + 8)); out[4 * i + 1] = (int32_t)((h[i] >> 8) & pm); out[4 * i + 2] = (int32_t)(h[i] & 15); out[4 * i + 3] = (int32_t)((h[i] & 15) + 1 + ((h[i] >> 4) & 15)); }
-                else { out[3 * i] = (int32_t)(h[i] >> (b.pbits + 4)); out[3 * i + 1] = (int32_t)((h[i] >> 4) & pm); out[3 * i + 2] = (int32_t)(h[i] & 15); }
+                else { out[3 * i] = (int32_t)((h[i] >> (b.pbits + 4)) & ((1ull << cgx_bits_for((uint64_t)b.D1)) - 1ull)); out[3 * i + 1] = (int32_t)((h[i] >> 4) & pm); out[3 * i + 2] = (int32_t)(h[i] & 15); }
             }
             return (int64_t)(H * cols);
         }

@@ -75,6 +75,7 @@ struct Batch {
     int64_t hits1 = 0, hits2 = 0, j1_elems = 0;
     int pbits = 30;                        // position field width of the packed hit keys (bits needed for n)
     size_t hit_cap = 0;
+    bool h1_mask = false;                  // the one-gap hit keys of this batch carry the second-gap word in their top 10 bits (join.cu H1_MASK_SHIFT)
     int32_t adv_refused_q = 0, adv_ok_q = 0;   // cgx_batch_advice: smallest batch refused so far, size and hits of the last finished one
     double adv_ok_hits = 0.0;
     uint32_t j1_buckets = 0, j2_buckets = 0;              // buckets of the last one-gap pattern table (kept when a batch had to grow it)

@@ -228,6 +228,7 @@ struct JPArgs {
     const uint32_t *bm_marker;
     QTab tab;
     int pshift;
+    int mask_shift;                  // bit of the key where the 10-bit second-gap word goes (H1_MASK_SHIFT), 64 = not carried
     unsigned long long *counter;     // [0] hits, [1] table lookups, [2] elements
     uint64_t *hits;
     size_t cap;
@@ -337,6 +338,11 @@ constexpr int JO_TILE = 256;          // positions per CTA (8 warps x 32 positio
 constexpr int JO_CAP = 1024;          // most staged hits per warp the kernel may be given (6 bytes of dynamic shared memory each)
 constexpr int JO_CAP_DEFAULT = 512;   // default: 24 KB per CTA, five CTAs per SM; a fuller stage is flushed as one more chunk of the warp
 
+// A one-gap hit key: [second-gap word : 10][...][pattern : dbits][position : pbits][length - 1 : 4].  The top 10 bits carry the
+// admissible widths 1..10 of a gap that would follow the hit (what gapw[p + L + 1] says, cut to the rule span) when the pattern,
+// position and length fields leave room for them (Batch::h1_mask); the two-gap join reads them instead of gathering the word.
+constexpr int H1_MASK_SHIFT = 54;
+
 struct JOArgs {
     JPArgs p;
     uint32_t *seg_base;               // per (warp, chunk): start of the chunk in the (unordered) output
@@ -387,8 +393,8 @@ constexpr int JQ_CAP = 64;
 // might not fit -- a chunk takes its place in the output with one atomicAdd and is recorded as (start, count) under
 // (warp number, chunk number); chunks are later copied into (warp, chunk) order, i.e. position order
 struct JStage {
-    uint32_t *pat;                   // staged pattern ids
-    uint16_t *pl;                    // staged tile-relative position << 4 | length - 1
+    uint32_t *pat;                   // staged pattern ids (< 2^26); bits 26..31: high 6 bits of the second-gap word (H1_MASK_SHIFT)
+    uint16_t *pl;                    // staged tile-relative position << 4 | length - 1; bits 12..15: low 4 bits of the second-gap word
     unsigned cap;                    // staged hits per chunk at most (>= 32)
     uint32_t *seg_base, *seg_count;  // this warp's chunk records (chunks_per_warp of each)
 };
@@ -413,7 +419,9 @@ __device__ __forceinline__ unsigned jo_walk(const JPArgs &a, const int4 *__restr
         for (unsigned i = lane; i < staged; i += 32) {
             const unsigned long long dst = base + i;
             const unsigned pl = st.pl[i];
-            if (dst < a.cap) a.hits[dst] = ((uint64_t)st.pat[i] << a.pshift) | ((uint64_t)(P0 + (pl >> 4)) << 4) | (uint64_t)(pl & 15u);
+            const uint32_t pt = st.pat[i];
+            const uint64_t mk = (uint64_t)(((pt >> 26) << 4) | (pl >> 12));          // second-gap word (0 when not carried)
+            if (dst < a.cap) a.hits[dst] = (a.mask_shift < 64 ? mk << a.mask_shift : 0ull) | ((uint64_t)(a.mask_shift < 64 ? pt & 0x3FFFFFFu : pt) << a.pshift) | ((uint64_t)(P0 + ((pl >> 4) & 0xFFu)) << 4) | (uint64_t)(pl & 15u);
         }
         __syncwarp();
         count += staged;
@@ -431,8 +439,18 @@ __device__ __forceinline__ unsigned jo_walk(const JPArgs &a, const int4 *__restr
         if (staged + __popc(m) > st.cap) flush();
         if (found) {
             const unsigned idx = staged + __popc(m & lanemask_lt());
-            st.pat[idx] = v >> 1;
-            st.pl[idx] = (uint16_t)(pend_meta & 0x7fffu);
+            // the gap word behind the hit is in the window: the two-gap join then needs no gather for it (at C3 that gather, one
+            // random DRAM sector per parent hit, was half of what bound j2_ordered_kernel).  It rides in the spare bits of the two
+            // stage words (mask_shift = 64: no room in the key, nothing carried).
+            const unsigned len_ = pend_meta & 15u;
+            unsigned mk = 0;
+            if (a.mask_shift < 64) {
+                const uint32_t w2 = (uint32_t)s_win[((pend_meta & 0x7fffu) >> 4) + len_ + 1].w;
+                const int gmax = min((int)((w2 >> 16) & 15u), CGX_MAX_RULE_SPAN - 2 - (int)len_);
+                mk = gmax > 0 ? (w2 & ((1u << gmax) - 1u) & 0x3FFu) : 0u;
+            }
+            st.pat[idx] = (v >> 1) | ((mk >> 4) << 26);
+            st.pl[idx] = (uint16_t)((pend_meta & 0x0fffu) | ((mk & 15u) << 12));
         }
         staged += __popc(m);
         pend = false;
@@ -460,7 +478,7 @@ __device__ __forceinline__ unsigned jo_walk(const JPArgs &a, const int4 *__restr
         if (!__any_sync(0xffffffffu, pm != 0)) continue;
         const int rel = wrel + src;                                // tile-relative position p
         const int p = (int)P0 + rel;
-#pragma unroll
+#pragma unroll 1
         for (int ls = 1; ls <= 3; ls++) {
             const bool on = (pm >> (ls - 1)) & 1u;
             if (!__any_sync(0xffffffffu, on)) continue;
@@ -581,12 +599,12 @@ __global__ void __launch_bounds__(256) seg_copy_kernel(const uint64_t *__restric
 }
 
 // per-pattern [start,count] in the sorted hit list
-__global__ void hit_ranges_kernel(const uint64_t *__restrict__ hits, size_t n, int shift, int32_t *__restrict__ start_count, int stride_ints) {
+__global__ void hit_ranges_kernel(const uint64_t *__restrict__ hits, size_t n, int shift, uint32_t dmask, int32_t *__restrict__ start_count, int stride_ints) {
     size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    uint32_t d = (uint32_t)(hits[k] >> shift);
-    if (k == 0 || (uint32_t)(hits[k - 1] >> shift) != d) start_count[(size_t)d * stride_ints + 0] = (int32_t)k;
-    if (k == n - 1 || (uint32_t)(hits[k + 1] >> shift) != d) start_count[(size_t)d * stride_ints + 1] = (int32_t)k;   // end; fixed up below
+    uint32_t d = (uint32_t)(hits[k] >> shift) & dmask;
+    if (k == 0 || ((uint32_t)(hits[k - 1] >> shift) & dmask) != d) start_count[(size_t)d * stride_ints + 0] = (int32_t)k;
+    if (k == n - 1 || ((uint32_t)(hits[k + 1] >> shift) & dmask) != d) start_count[(size_t)d * stride_ints + 1] = (int32_t)k;   // end; fixed up below
 }
 __global__ void hit_ranges_fix_kernel(int32_t *__restrict__ start_count, int n_pat, int stride_ints) {
     int d = blockIdx.x * blockDim.x + threadIdx.x;
@@ -665,6 +683,7 @@ void stage_onegap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     ap.jwin = ix.jwin.ptr<int4>(); ap.n = (uint32_t)ix.n;
     for (int k = 0; k < 3; k++) { ap.bma[k] = bm + (size_t)(4 + k) * bm_words; ap.aid[k] = aid + (size_t)k * ix.n; ap.bm[k] = bm + (size_t)k * bm_words; }
     ap.bm_marker = bm + 3 * bm_words; ap.tab = tab; ap.pshift = b.pbits + 4; ap.counter = ctr; ap.missing = missing;
+    ap.mask_shift = 64;
     unsigned long long host_ctr[3] = {0, 0, 0};
     // position-major scans emit in position order (tile segments + ordered copy): the sort below then covers the pattern bits only.
     // CGX_JOIN_ORDERED=0 keeps round 1's unordered append + full (pattern, position) sort for that variant too.
@@ -694,7 +713,11 @@ void stage_onegap_join(const Index &ix, Batch &b, cudaStream_t stream) {
         a.cap = ap.cap = b.hit_cap;
         CUDA_CHECK(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long) * 3, stream));
         CUDA_CHECK(cudaMemsetAsync(missing, 0, sizeof(int32_t) * (size_t)D1, stream));
+        b.h1_mask = false;
         if (n_elems && ordered) {
+            b.h1_mask = cgx_bits_for((uint64_t)D1) + b.pbits + 4 <= H1_MASK_SHIFT && cgx_bits_for((uint64_t)D1) <= 26;
+            if (const char *e = getenv("CGX_JOIN_CARRY_GAPW")) { if (!strcmp(e, "0")) b.h1_mask = false; }
+            ap.mask_shift = b.h1_mask ? H1_MASK_SHIFT : 64;
             ao.p = ap;
             uint8_t *fl = b.j_flags.get<uint8_t>((size_t)ix.n + 64);
             PROF("join_setup", 17.0 * (double)ix.n, (j1_flags_kernel<<<cgx_div_up(ix.n, 256), 256, 0, stream>>>(ap.jwin, ap.n, ap.bma[0], ap.bma[1], ap.bma[2], ap.bm[0], ap.bm[1], ap.bm[2],
@@ -738,7 +761,7 @@ void stage_onegap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     std::swap(b.hits1_sorted, hs == b.hit_keys.ptr<uint64_t>() ? b.hit_keys : b.hit_keys_tmp);
     uint64_t *dst = b.hits1_sorted.ptr<uint64_t>();
     static_assert(sizeof(Pat1) == 32, "Pat1 layout");
-    hit_ranges_kernel<<<cgx_div_up(H, 256), 256, 0, stream>>>(dst, H, b.pbits + 4, &b.pat1.ptr<int32_t>()[4], 8);
+    hit_ranges_kernel<<<cgx_div_up(H, 256), 256, 0, stream>>>(dst, H, b.pbits + 4, (1u << cgx_bits_for((uint64_t)D1)) - 1u, &b.pat1.ptr<int32_t>()[4], 8);
     hit_ranges_fix_kernel<<<cgx_div_up(D1, 256), 256, 0, stream>>>(&b.pat1.ptr<int32_t>()[4], D1, 8);
     b.launches += 2;
 }
@@ -762,7 +785,7 @@ __global__ void j2_setup_kernel(const Pat2 *__restrict__ pat2, int D2, QTab tab,
 
 __global__ void __launch_bounds__(256) j2_scan_kernel(const uint64_t *__restrict__ hits1, size_t H1, int pbits, const unsigned long long *__restrict__ child_sig,
                                                       const int32_t *__restrict__ str, const uint32_t *__restrict__ gapw,
-                                                      const QTab tab,
+                                                      const QTab tab, uint32_t dmask,
                                                       unsigned long long *__restrict__ counter, uint64_t *__restrict__ hits, size_t cap) {
     __shared__ uint64_t s_stage[256 / 32][ST_CAP];
     uint64_t *stage = s_stage[threadIdx.x >> 5];
@@ -774,7 +797,7 @@ __global__ void __launch_bounds__(256) j2_scan_kernel(const uint64_t *__restrict
     int p = 0, L = 0;
     if (k < H1) {
         const uint64_t hk = hits1[k];
-        d1 = (uint32_t)(hk >> (pbits + 4));
+        d1 = (uint32_t)(hk >> (pbits + 4)) & dmask;
         sig = __ldg(&child_sig[d1]);
         if (sig) {
             p = (int)((hk >> 4) & ((1ull << pbits) - 1)); L = (int)(hk & 15);
@@ -829,7 +852,7 @@ __global__ void __launch_bounds__(256) j2_scan_kernel(const uint64_t *__restrict
 constexpr int J2O_SLOTS = CGX_MAX_RULE_SPAN - 2;       // widths 1..13
 constexpr int J2O_STRIDE = 240;                        // 256 - 16 >= 256 - (longest run - 1)
 __global__ void __launch_bounds__(256) j2_ordered_kernel(const uint64_t *__restrict__ hits1, size_t H1, int pbits, const unsigned long long *__restrict__ child_sig,
-                                                         const int32_t *__restrict__ str, const uint32_t *__restrict__ gapw, const QTab tab,
+                                                         const int32_t *__restrict__ str, const uint32_t *__restrict__ gapw, const QTab tab, uint32_t dmask, int carried,
                                                          unsigned long long *__restrict__ counter, unsigned long long *__restrict__ seg_base,
                                                          uint32_t *__restrict__ seg_count, uint64_t *__restrict__ hits, size_t cap) {
     __shared__ uint32_t s_d2[J2O_SLOTS][256];           // hits parked by [width - 1][owner thread]
@@ -850,22 +873,26 @@ __global__ void __launch_bounds__(256) j2_ordered_kernel(const uint64_t *__restr
     int p = 0, L = 0;
     bool mine = false, head = true;
     if (k < H1) {
+        const uint64_t kmask = carried ? (1ull << H1_MASK_SHIFT) - 1ull : ~0ull;          // the key without the carried second-gap word
         const uint64_t hk = hits1[k];
-        const uint64_t run_key = hk >> 4;                                      // (pattern, position)
-        const uint64_t before = base ? hits1[base - 1] >> 4 : ~0ull;           // last parent of the previous tile's nominal range
+        const uint64_t run_key = (hk & kmask) >> 4;                            // (pattern, position)
+        const uint64_t before = base ? (hits1[base - 1] & kmask) >> 4 : ~0ull;  // last parent of the previous tile's nominal range
         mine = run_key != before;                                              // not a continuation of the previous tile's last run
-        if (tid >= J2O_STRIDE) mine = mine && run_key == (hits1[base + J2O_STRIDE - 1] >> 4);
-        head = !mine || tid == 0 || run_key != (hits1[k - 1] >> 4);
+        if (tid >= J2O_STRIDE) mine = mine && run_key == ((hits1[base + J2O_STRIDE - 1] & kmask) >> 4);
+        head = !mine || tid == 0 || run_key != ((hits1[k - 1] & kmask) >> 4);
         if (mine) {
-            d1 = (uint32_t)(hk >> (pbits + 4));
+            d1 = (uint32_t)(hk >> (pbits + 4)) & dmask;
             sig = __ldg(&child_sig[d1]);
         }
         if (sig) {
             p = (int)((hk >> 4) & ((1ull << pbits) - 1)); L = (int)(hk & 15);
-            const uint32_t w = __ldg(&gapw[p + L + 1]);
-            const int run = (int)((w >> 16) & 15u);
-            const int gmax = min(run, CGX_MAX_RULE_SPAN - 2 - L);
-            bits = gmax > 0 ? (w & ((1u << gmax) - 1u)) : 0u;
+            if (carried && L > 2) bits = (uint32_t)(hk >> H1_MASK_SHIFT);      // admissible widths 1..10: all there are for L >= 3
+            else {                                                             // (L = 2 may admit an 11th width: read the word itself)
+                const uint32_t w = __ldg(&gapw[p + L + 1]);
+                const int run = (int)((w >> 16) & 15u);
+                const int gmax = min(run, CGX_MAX_RULE_SPAN - 2 - L);
+                bits = gmax > 0 ? (w & ((1u << gmax) - 1u)) : 0u;
+            }
             active = 1;
         }
     }
@@ -1029,18 +1056,18 @@ void stage_twogap_join(const Index &ix, Batch &b, cudaStream_t stream) {
         CUDA_CHECK(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long) * 3, stream));
         if (ordered) {
             PROF("join_twogap", 0.0, (j2_ordered_kernel<<<n_tiles, 256, 0, stream>>>(b.hits1_sorted.ptr<uint64_t>(), H1, b.pbits, child_sig, ix.str.ptr<int32_t>(),
-                                                               ix.gapw.ptr<uint32_t>(), tab, ctr, seg_base, seg_count, hits, b.hit_cap)));
+                                                               ix.gapw.ptr<uint32_t>(), tab, (1u << cgx_bits_for((uint64_t)b.D1)) - 1u, b.h1_mask ? 1 : 0, ctr, seg_base, seg_count, hits, b.hit_cap)));
         } else
         PROF("join_twogap", 0.0, (j2_scan_kernel<<<cgx_div_up(H1, 256), 256, 0, stream>>>(b.hits1_sorted.ptr<uint64_t>(), H1, b.pbits, child_sig, ix.str.ptr<int32_t>(),
-                                                           ix.gapw.ptr<uint32_t>(), tab, ctr, hits, b.hit_cap)));
+                                                           ix.gapw.ptr<uint32_t>(), tab, (1u << cgx_bits_for((uint64_t)b.D1)) - 1u, ctr, hits, b.hit_cap)));
         b.launches += 1;
         read_u64s(host_ctr, ctr, 3, stream);
         CGX_REQUIRE_BATCH(host_ctr[0] < hit_limit(), "%llu two-gap hits", host_ctr[0]);
         if (host_ctr[0] <= b.hit_cap) { b.hits2 = (int64_t)host_ctr[0]; break; }
         b.hit_cap = (size_t)host_ctr[0] + (size_t)host_ctr[0] / 8 + 1024;
     }
-    // algorithmic bytes: every parent hit read, gap word of the active ones, each candidate token, each hit written
-    prof_add_bytes("join_twogap", 8.0 * (double)H1 + 4.0 * (double)host_ctr[2] + 4.0 * (double)host_ctr[1] + 8.0 * (double)host_ctr[0]);
+    // algorithmic bytes: every parent hit read, gap word of the active ones (unless the hit keys carry it), each candidate token, each hit written
+    prof_add_bytes("join_twogap", 8.0 * (double)H1 + (b.h1_mask ? 0.0 : 4.0 * (double)host_ctr[2]) + 4.0 * (double)host_ctr[1] + 8.0 * (double)host_ctr[0]);
     if (b.hits2 == 0) return;
     const size_t H = (size_t)b.hits2;
     uint64_t *hits = b.hit_keys.ptr<uint64_t>();
@@ -1056,7 +1083,7 @@ void stage_twogap_join(const Index &ix, Batch &b, cudaStream_t stream) {
     std::swap(b.hits2_sorted, hs == b.hit_keys.ptr<uint64_t>() ? b.hit_keys : b.hit_keys_tmp);
     uint64_t *dst = b.hits2_sorted.ptr<uint64_t>();
     static_assert(sizeof(Pat2) == 16, "Pat2 layout");
-    hit_ranges_kernel<<<cgx_div_up(H, 256), 256, 0, stream>>>(dst, H, b.pbits + 8, &b.pat2.ptr<int32_t>()[2], 4);
+    hit_ranges_kernel<<<cgx_div_up(H, 256), 256, 0, stream>>>(dst, H, b.pbits + 8, 0xffffffffu, &b.pat2.ptr<int32_t>()[2], 4);
     hit_ranges_fix_kernel<<<cgx_div_up(D2, 256), 256, 0, stream>>>(&b.pat2.ptr<int32_t>()[2], D2, 4);
     b.launches += 2;
 }
