@@ -850,18 +850,19 @@ __global__ void __launch_bounds__(256) j2_scan_kernel(const uint64_t *__restrict
 // Tiles are cut on run boundaries: a tile is nominally J2O_STRIDE parents; its first parents are skipped when they continue
 // the previous tile's last run, and threads J2O_STRIDE..255 take the parents that continue its own last run.
 constexpr int J2O_SLOTS = CGX_MAX_RULE_SPAN - 2;       // widths 1..13
-constexpr int J2O_STRIDE = 240;                        // 256 - 16 >= 256 - (longest run - 1)
-__global__ void __launch_bounds__(256) j2_ordered_kernel(const uint64_t *__restrict__ hits1, size_t H1, int pbits, const unsigned long long *__restrict__ child_sig,
+constexpr int J2O_BLOCK = 256;                         // threads per tile (128, to shorten the waits at the tile's two barriers, measured slower: 7.8 -> 9.0 ms at C2)
+constexpr int J2O_STRIDE = J2O_BLOCK - 16;             // >= J2O_BLOCK - (longest run - 1)
+__global__ void __launch_bounds__(J2O_BLOCK) j2_ordered_kernel(const uint64_t *__restrict__ hits1, size_t H1, int pbits, const unsigned long long *__restrict__ child_sig,
                                                          const int32_t *__restrict__ str, const uint32_t *__restrict__ gapw, const QTab tab, uint32_t dmask, int carried,
                                                          unsigned long long *__restrict__ counter, unsigned long long *__restrict__ seg_base,
                                                          uint32_t *__restrict__ seg_count, uint64_t *__restrict__ hits, size_t cap) {
-    __shared__ uint32_t s_d2[J2O_SLOTS][256];           // hits parked by [width - 1][owner thread]
-    __shared__ unsigned s_mask[256];
-    __shared__ uint16_t s_excl[256];
-    __shared__ uint32_t s_qtok[8][64];                  // per-warp candidate queue: token / owner lane << 4 | width - 1
-    __shared__ uint16_t s_qown[8][64];
-    __shared__ uint8_t s_head[257];
-    __shared__ unsigned s_wsum[8];
+    __shared__ uint32_t s_d2[J2O_SLOTS][J2O_BLOCK];           // hits parked by [width - 1][owner thread]
+    __shared__ unsigned s_mask[J2O_BLOCK];
+    __shared__ uint16_t s_excl[J2O_BLOCK];
+    __shared__ uint32_t s_qtok[J2O_BLOCK / 32][64];                  // per-warp candidate queue: token / owner lane << 4 | width - 1
+    __shared__ uint16_t s_qown[J2O_BLOCK / 32][64];
+    __shared__ uint8_t s_head[J2O_BLOCK + 1];
+    __shared__ unsigned s_wsum[J2O_BLOCK / 32];
     __shared__ unsigned long long s_base;
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tile = blockIdx.x;
@@ -958,7 +959,7 @@ __global__ void __launch_bounds__(256) j2_ordered_kernel(const uint64_t *__restr
     unsigned found_mask = s_mask[tid];
     const unsigned c = __popc(found_mask);              // widths that hit (bit g2-1), their count
     s_head[tid] = head ? 1 : 0;
-    if (tid == 0) s_head[256] = 1;
+    if (tid == 0) s_head[J2O_BLOCK] = 1;
     // exclusive prefix of c over the CTA
     unsigned incl = c;
 #pragma unroll
@@ -970,12 +971,12 @@ __global__ void __launch_bounds__(256) j2_ordered_kernel(const uint64_t *__restr
     __syncthreads();
     unsigned excl = incl - c;
 #pragma unroll
-    for (int w = 0; w < 8; w++) if (w < (int)warp) excl += s_wsum[w];
+    for (int w = 0; w < J2O_BLOCK / 32; w++) if (w < (int)warp) excl += s_wsum[w];
     s_excl[tid] = (uint16_t)excl;
     if (tid == 0) {
         unsigned tot = 0;
 #pragma unroll
-        for (int w = 0; w < 8; w++) tot += s_wsum[w];
+        for (int w = 0; w < J2O_BLOCK / 32; w++) tot += s_wsum[w];
         const unsigned long long seg = tot ? atomicAdd(&counter[0], (unsigned long long)tot) : 0ull;
         seg_base[tile] = seg;
         seg_count[tile] = tot;
@@ -1055,7 +1056,7 @@ void stage_twogap_join(const Index &ix, Batch &b, cudaStream_t stream) {
         uint64_t *hits = b.hit_keys.get<uint64_t>(b.hit_cap);
         CUDA_CHECK(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long) * 3, stream));
         if (ordered) {
-            PROF("join_twogap", 0.0, (j2_ordered_kernel<<<n_tiles, 256, 0, stream>>>(b.hits1_sorted.ptr<uint64_t>(), H1, b.pbits, child_sig, ix.str.ptr<int32_t>(),
+            PROF("join_twogap", 0.0, (j2_ordered_kernel<<<n_tiles, J2O_BLOCK, 0, stream>>>(b.hits1_sorted.ptr<uint64_t>(), H1, b.pbits, child_sig, ix.str.ptr<int32_t>(),
                                                                ix.gapw.ptr<uint32_t>(), tab, (1u << cgx_bits_for((uint64_t)b.D1)) - 1u, b.h1_mask ? 1 : 0, ctr, seg_base, seg_count, hits, b.hit_cap)));
         } else
         PROF("join_twogap", 0.0, (j2_scan_kernel<<<cgx_div_up(H1, 256), 256, 0, stream>>>(b.hits1_sorted.ptr<uint64_t>(), H1, b.pbits, child_sig, ix.str.ptr<int32_t>(),
