@@ -314,9 +314,9 @@ def result_bytes(ex):
 def result_bytes_of(r):
     q1 = int(np.ctypeslib.as_array(r.q1_off, shape=(r.Q + 1,))[-1]) if r.Q else 0
     q2 = int(np.ctypeslib.as_array(r.q2_off, shape=(r.Q + 1,))[-1]) if r.Q else 0
-    b = 4 * (r.T * 5 + r.G * 4 + r.D1 * 8 + r.D2 * 4 + 2 * (r.Q + 1) + q1 + q2)
+    b = 4 * (r.T * 5 + r.G * 4 + r.D1 * 4 + r.D2 * 2 + 2 * (r.Q + 1) + q1 + q2)
     for k in range(3):
-        b += 16 * r.n_rules[k] + (8 + 4) * r.n_ids[k]
+        b += 16 * r.n_rules[k] + (4 + 4) * r.n_ids[k]
     return int(b)
 
 

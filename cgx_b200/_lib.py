@@ -54,7 +54,7 @@ class BatchInfo(C.Structure):
 RULE_DTYPE = np.dtype([("id", "<i4"), ("tgt_start", "<i4"), ("end", "u1"), ("gap1", "u1"), ("gap1_1", "u1"), ("gap2", "u1"), ("gap2_1", "u1"),
                        ("pad", "u1"), ("f", "<u2"), ("fs", "<u2"), ("pc", "<u2"), ("mlfe", "<f4"), ("mlef", "<f4")])
 assert RULE_DTYPE.itemsize == 28
-# wire format (cgx_rule_t, 16 bytes); BatchResult decodes it into RULE_DTYPE with id / f / fs from updown and idinfo
+# wire format (cgx_rule_t, 16 bytes); BatchResult decodes it into RULE_DTYPE with id / f / fs from first and idinfo
 RULE_WIRE_DTYPE = np.dtype([("tgt_start", "<i4"), ("span", "<u4"), ("mlfe", "<f4"), ("mlef", "<f4")])
 assert RULE_WIRE_DTYPE.itemsize == 16
 
@@ -63,7 +63,7 @@ class Result(C.Structure):
     _fields_ = [("Q", C.c_int32), ("T", C.c_int32), ("G", C.c_int32), ("D1", C.c_int32), ("D2", C.c_int32),
                 ("phrase_id", C.POINTER(C.c_int32)), ("phrases", C.POINTER(C.c_int32)), ("pat1", C.POINTER(C.c_int32)), ("pat2", C.POINTER(C.c_int32)),
                 ("q1_off", C.POINTER(C.c_int32)), ("q1_ids", C.POINTER(C.c_int32)), ("q2_off", C.POINTER(C.c_int32)), ("q2_ids", C.POINTER(C.c_int32)),
-                ("rules", C.c_void_p * 3), ("n_rules", C.c_int32 * 3), ("updown", C.POINTER(C.c_int32) * 3), ("n_ids", C.c_int32 * 3),
+                ("rules", C.c_void_p * 3), ("n_rules", C.c_int32 * 3), ("first", C.POINTER(C.c_int32) * 3), ("n_ids", C.c_int32 * 3),
                 ("idinfo", C.POINTER(C.c_uint32) * 3)]
 
 

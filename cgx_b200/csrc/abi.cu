@@ -453,12 +453,12 @@ static void run_batch(cgx_ctx *c, int32_t Q, int32_t T, bool fetch, bool wait_co
     if (fetch) {   // the pattern tables and phrase ids are final here: they travel while extraction and aggregation run
         int32_t *hp = b.h_phrase_id.get<int32_t>((size_t)T * CGX_LONGEST_SRC + 1);
         int32_t *hph = b.h_phrases.get<int32_t>((size_t)b.G * 4 + 1);
-        int32_t *h1 = b.h_pat1.get<int32_t>((size_t)b.D1 * 8 + 1);
-        int32_t *h2 = b.h_pat2.get<int32_t>((size_t)b.D2 * 4 + 1);
+        int32_t *h1 = b.h_pat1.get<int32_t>((size_t)b.D1 * 4 + 1);       // host view: {a_pos, ls, b_pos, le} of the 32-byte device record
+        int32_t *h2 = b.h_pat2.get<int32_t>((size_t)b.D2 * 2 + 1);       // host view: {pat1, ctok} of the 16-byte device record
         fetch_async(b, hp, b.phrase_id.p, sizeof(int32_t) * (size_t)T * CGX_LONGEST_SRC, s);
         fetch_async(b, hph, b.phrases.p, sizeof(int32_t) * (size_t)b.G * 4, s);
-        fetch_async(b, h1, b.pat1.p, sizeof(int32_t) * (size_t)b.D1 * 8, s);
-        fetch_async(b, h2, b.pat2.p, sizeof(int32_t) * (size_t)b.D2 * 4, s);
+        fetch_async_2d(b, h1, 16, b.pat1.p, sizeof(Pat1), (size_t)b.D1, s);      // the hit ranges, marker and featureMissingCount stay on the device
+        fetch_async_2d(b, h2, 8, b.pat2.p, sizeof(Pat2), (size_t)b.D2, s);
     }
     stage_extract(ix, b, s);
     CUDA_CHECK(cudaEventRecord(b.ev[6], s));
@@ -629,7 +629,7 @@ extern "C" int cgx_result_at(cgx_ctx_t *c, int age, cgx_result_t *o) {
             o->q1_off = b.h_q1_off.ptr<int32_t>(); o->q1_ids = b.h_q1_ids.ptr<int32_t>(); o->q2_off = b.h_q2_off.ptr<int32_t>(); o->q2_ids = b.h_q2_ids.ptr<int32_t>();
             for (int k = 0; k < 3; k++) {
                 o->rules[k] = b.h_rules[k].ptr<cgx_rule_t>(); o->n_rules[k] = b.n_rules[k];
-                o->updown[k] = b.h_updown[k].ptr<int32_t>(); o->n_ids[k] = b.n_ids[k];
+                o->first[k] = b.h_updown[k].ptr<int32_t>(); o->n_ids[k] = b.n_ids[k];
                 o->idinfo[k] = b.h_idinfo[k].ptr<uint32_t>();
             }
         } else {
@@ -641,7 +641,7 @@ extern "C" int cgx_result_at(cgx_ctx_t *c, int age, cgx_result_t *o) {
             o->q1_off = r.h_q1_off.ptr<int32_t>(); o->q1_ids = r.h_q1_ids.ptr<int32_t>(); o->q2_off = r.h_q2_off.ptr<int32_t>(); o->q2_ids = r.h_q2_ids.ptr<int32_t>();
             for (int k = 0; k < 3; k++) {
                 o->rules[k] = r.h_rules[k].ptr<cgx_rule_t>(); o->n_rules[k] = r.n_rules[k];
-                o->updown[k] = r.h_updown[k].ptr<int32_t>(); o->n_ids[k] = r.n_ids[k];
+                o->first[k] = r.h_updown[k].ptr<int32_t>(); o->n_ids[k] = r.n_ids[k];
                 o->idinfo[k] = r.h_idinfo[k].ptr<uint32_t>();
             }
         }
@@ -690,6 +690,8 @@ extern "C" int64_t cgx_debug_fetch(cgx_ctx_t *c, const char *what, int32_t *out,
         if (w == "longest") return copy_i32(b.longest.p, (size_t)b.T);
         if (w == "intervals") return copy_i32(b.iv.p, (size_t)b.T * CGX_LONGEST_SRC * 2);
         if (w == "pat1_dev") return copy_i32(b.pat1_dev.p, (size_t)b.D1 * 4);
+        if (w == "pat1_full") return copy_i32(b.pat1.p, (size_t)b.D1 * 8);      // {a_pos, ls, b_pos, le, hit_start, hit_count, marker_pair, fs_extra}
+        if (w == "pat2_full") return copy_i32(b.pat2.p, (size_t)b.D2 * 4);      // {pat1, ctok, hit_start, hit_count}
         if (w == "hits1" || w == "hits2") {
             bool two = w == "hits2";
             size_t H = (size_t)(two ? b.hits2 : b.hits1);

@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(128) agg_rules_kernel(AggIdx a, int kind, cons
     int fs = fsample_of(a, kind, best.id);
     fs = fs > CGX_SAMPLER ? CGX_SAMPLER : fs;                                           // ExtractPair.c:638,910,1249
     rule_id[r] = best.id;
-    idinfo[best.id] = (cw >> 16) | ((uint32_t)fs << 16);       // f | fs << 16: every rule of the id writes the same word
+    idinfo[best.id] = (cw >> 16) | ((uint32_t)fs << 9);        // f | fs << 9 (both <= 300): every rule of the id writes the same word; the rule count is added later
     // ---- lexicalTaskMaxEF (ExtractPair.cu:2144-2432): for every source terminal the best MaxLexFgivenE over the target
     // terminals (and NULL), for every target terminal the best MaxLexEgivenF over the source terminals (and NULL).  One
     // table probe serves both directions of a (f, e) pair.
@@ -321,13 +321,15 @@ __global__ void __launch_bounds__(128) agg_rules_kernel(AggIdx a, int kind, cons
     rules[r] = out;
 }
 
-// per converted id: [first rule, last rule]  (globalOnPairsUpDown*, ExtractPair.cu:3745-3756, :3805-3816, :2082)
-__global__ void agg_updown_kernel(const int32_t *__restrict__ rule_id, uint32_t n_rules, int32_t *__restrict__ updown) {
+// per converted id: index of its first rule (the rules come out in ascending id order, so an id's rules are consecutive:
+// globalOnPairsUpDown*, ExtractPair.cu:3745-3756, :3805-3816, :2082) and, in bits 18..26 of its idinfo word, how many there are.
+// The count is last - first + 1 < 512, added modulo 512 in two halves by the threads at the two ends of the id's run.
+__global__ void agg_updown_kernel(const int32_t *__restrict__ rule_id, uint32_t n_rules, int32_t *__restrict__ first, uint32_t *__restrict__ idinfo) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rules) return;
-    int id = rule_id[r];
-    if (r == 0 || rule_id[r - 1] != id) updown[2 * id] = (int32_t)r;
-    if (r == n_rules - 1 || rule_id[r + 1] != id) updown[2 * id + 1] = (int32_t)r;
+    const int32_t id = rule_id[r];
+    if (r == 0 || rule_id[r - 1] != id) { first[id] = (int32_t)r; atomicAdd(&idinfo[id], ((513u - (r & 511u)) & 511u) << 18); }
+    if (r == n_rules - 1 || rule_id[r + 1] != id) atomicAdd(&idinfo[id], (r & 511u) << 18);
 }
 
 void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
@@ -349,11 +351,11 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
         for (int k = lay[kind].n_regions; k < 4; k++) lay[kind].r[k] = lay[kind].r[0];
         b.n_ids[kind] = nids[kind];
         b.n_rules[kind] = 0;
-        int32_t *h_ud = b.h_updown[kind].get<int32_t>((size_t)2 * nids[kind] + 2);
+        int32_t *h_ud = b.h_updown[kind].get<int32_t>((size_t)nids[kind] + 2);
         uint32_t *h_ii = b.h_idinfo[kind].get<uint32_t>((size_t)nids[kind] + 1);
         b.h_rules[kind].get<cgx_rule_t>(1);
         if (N == 0 || nids[kind] == 0) {
-            memset(h_ud, 0xff, sizeof(int32_t) * 2 * (size_t)nids[kind]);
+            memset(h_ud, 0xff, sizeof(int32_t) * (size_t)nids[kind]);
             memset(h_ii, 0, sizeof(uint32_t) * (size_t)nids[kind]);
             continue;
         }
@@ -364,7 +366,7 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
         uint32_t *acc_cnt = b.rec_cnt.get<uint32_t>((size_t)N);
         uint32_t *tag = b.rec_tag.get<uint32_t>((size_t)N + 8);
         uint32_t *live = b.rec_live.get<uint32_t>((size_t)N + 2);
-        int32_t *updown = b.updown[kind].get<int32_t>((size_t)2 * nids[kind]);
+        int32_t *updown = b.updown[kind].get<int32_t>((size_t)nids[kind] + 1);      // first rule of every id (-1: none)
         uint32_t *idinfo = b.idinfo[kind].get<uint32_t>((size_t)nids[kind] + 1);
         uint64_t seed = 0x243f6a8885a308d3ULL;
         uint32_t R = 0;
@@ -399,8 +401,8 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
                 // L2-resident and the kernel is bound by instruction issue, not by the probe latency)
                 PROF("agg_rules", (double)R * (4 + 8 + 16 + 16 + 4) + (double)R * 13 * 16, (agg_rules_kernel<<<cgx_div_up(R, 128), 128, 0, stream>>>(a, kind, rec, head_cell, acc_best, acc_cnt, R,
                                                                        ix.lex_hash.ptr<ulonglong2>(), ix.lex_hash_mask, rules, rule_id, idinfo)));
-                CUDA_CHECK(cudaMemsetAsync(updown, 0xff, sizeof(int32_t) * 2 * (size_t)nids[kind], stream));
-                agg_updown_kernel<<<cgx_div_up(R, 256), 256, 0, stream>>>(rule_id, R, updown);
+                CUDA_CHECK(cudaMemsetAsync(updown, 0xff, sizeof(int32_t) * (size_t)nids[kind], stream));
+                agg_updown_kernel<<<cgx_div_up(R, 256), 256, 0, stream>>>(rule_id, R, updown, idinfo);
                 b.launches += 3;
                 break;
             }
@@ -410,8 +412,8 @@ void stage_aggregate(const Index &ix, Batch &b, cudaStream_t stream) {
         if (b.fetch_results) {
             cgx_rule_t *h_r = b.h_rules[kind].get<cgx_rule_t>((size_t)R + 1);
             if (R) fetch_async(b, h_r, b.rules[kind].ptr<cgx_rule_t>(), sizeof(cgx_rule_t) * R, stream);
-            if (R) fetch_async(b, h_ud, updown, sizeof(int32_t) * 2 * (size_t)nids[kind], stream);
-            else memset(h_ud, 0xff, sizeof(int32_t) * 2 * (size_t)nids[kind]);      // no rule at all: every range empty
+            if (R) fetch_async(b, h_ud, updown, sizeof(int32_t) * (size_t)nids[kind], stream);
+            else memset(h_ud, 0xff, sizeof(int32_t) * (size_t)nids[kind]);          // no rule at all: every id empty
             if (R) fetch_async(b, h_ii, idinfo, sizeof(uint32_t) * (size_t)nids[kind], stream);
             else memset(h_ii, 0, sizeof(uint32_t) * (size_t)nids[kind]);
         }

@@ -2,6 +2,7 @@
 #pragma once
 #include "../../include/cgx_b200.h"
 #include "index.h"
+#include <algorithm>
 #include <utility>
 
 namespace cgx {
@@ -127,6 +128,17 @@ static inline void fetch_async(Batch &b, void *dst, const void *src, size_t byte
     static const size_t piece = [] { const char *e = getenv("CGX_D2H_PIECE"); size_t v = e ? strtoull(e, nullptr, 10) : 0; return v ? v : (size_t)4 << 20; }();
     for (size_t o = 0; o < bytes; o += piece)
         CUDA_CHECK(cudaMemcpyAsync((char *)dst + o, (const char *)src + o, bytes - o < piece ? bytes - o : piece, cudaMemcpyDeviceToHost, b.copy_stream));
+}
+
+// the same for the first `width` bytes of every `spitch`-byte record (the host needs less of a record than the device keeps)
+static inline void fetch_async_2d(Batch &b, void *dst, size_t width, const void *src, size_t spitch, size_t rows, cudaStream_t stream) {
+    if (!rows) return;
+    CUDA_CHECK(cudaEventRecord(b.copy_ev, stream));
+    CUDA_CHECK(cudaStreamWaitEvent(b.copy_stream, b.copy_ev, 0));
+    const size_t piece = std::max<size_t>(1, ((size_t)4 << 20) / width);           // rows per piece (~4 MB, see fetch_async)
+    for (size_t r = 0; r < rows; r += piece)
+        CUDA_CHECK(cudaMemcpy2DAsync((char *)dst + r * width, width, (const char *)src + r * spitch, spitch, width, rows - r < piece ? rows - r : piece,
+                                     cudaMemcpyDeviceToHost, b.copy_stream));
 }
 
 // current result arrays <-> a parked set (pointer swaps only)

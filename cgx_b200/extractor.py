@@ -31,7 +31,7 @@ def _np(ptr, n, dtype=np.int32):
 
 def decode_rules(wire, updown, idinfo):
     """cgx_rule_t wire records (16 B, include/cgx_b200.h) -> RULE_DTYPE rows with the converted id, f and fs filled in:
-    the id of a rule is the updown range it sits in; f and fs travel once per id in idinfo."""
+    the id of a rule is the [first, last] range it sits in; f and fs travel once per id in idinfo."""
     n = len(wire)
     out = np.zeros(n, dtype=RULE_DTYPE)
     if n == 0:
@@ -51,8 +51,8 @@ def decode_rules(wire, updown, idinfo):
     assert np.array_equal(hi - lo + 1, np.bincount(seg, minlength=len(ids))), "updown ranges do not tile the rules"
     rid = ids[seg].astype(np.int32)
     out["id"] = rid
-    out["f"] = idinfo[rid] & 0xFFFF
-    out["fs"] = idinfo[rid] >> 16
+    out["f"] = idinfo[rid] & 0x1FF                        # CGX_ID_F / CGX_ID_FS of include/cgx_b200.h
+    out["fs"] = (idinfo[rid] >> 9) & 0x1FF
     return out
 
 
@@ -66,8 +66,8 @@ class BatchResult:
         self.qry_off = np.asarray(qry_off, dtype=np.int32)
         self.phrase_id = _np(r.phrase_id, self.T * 5).reshape(self.T, 5)
         self.phrases = _np(r.phrases, self.G * 4).reshape(self.G, 4)
-        self.pat1 = _np(r.pat1, self.D1 * 8).reshape(self.D1, 8)
-        self.pat2 = _np(r.pat2, self.D2 * 4).reshape(self.D2, 4)
+        self.pat1 = _np(r.pat1, self.D1 * 4).reshape(self.D1, 4)          # {a_pos, ls, b_pos, le}
+        self.pat2 = _np(r.pat2, self.D2 * 2).reshape(self.D2, 2)          # {pat1, ctok}
         self.q1_off = _np(r.q1_off, self.Q + 1)
         self.q1_ids = _np(r.q1_ids, int(self.q1_off[-1]) if self.Q else 0)
         self.q2_off = _np(r.q2_off, self.Q + 1)
@@ -75,8 +75,10 @@ class BatchResult:
         self.rules, self.updown, self.idinfo = [], [], []
         for k in range(3):
             n = r.n_rules[k]
-            ud = _np(r.updown[k], 2 * r.n_ids[k]).reshape(-1, 2)
+            first = _np(r.first[k], r.n_ids[k])
             ii = _np(r.idinfo[k], r.n_ids[k], dtype=np.uint32) if r.n_ids[k] else np.zeros(0, dtype=np.uint32)
+            # [first, last] rule of every id (-1, -1 when it has none): first[id] and CGX_ID_RULES(idinfo[id])
+            ud = np.stack([first, np.where(first >= 0, first + ((ii >> 18) & 0x1FF).astype(np.int32) - 1, -1)], axis=1).astype(np.int32)
             self.updown.append(ud)
             self.idinfo.append(ii)
             if n:

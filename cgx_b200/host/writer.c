@@ -85,22 +85,23 @@ static void source_string(sbuf *b, const cgx_result_t *r, const cgxh_side_t *src
     if (kind == 1) {
         if (cid < G) { sb_puts(b, "[X,1] "); put_phrase(b, src, r->phrases[4 * cid + 3], r->phrases[4 * cid + 2]); }
         else if (cid < 2 * G) { int32_t g = cid - G; put_phrase(b, src, r->phrases[4 * g + 3], r->phrases[4 * g + 2]); sb_puts(b, " [X,1]"); }
-        else put_pat1(b, src, &r->pat1[8 * (cid - 2 * G)], "[X,1]");
+        else put_pat1(b, src, &r->pat1[4 * (cid - 2 * G)], "[X,1]");
         return;
     }
     if (cid < G) { sb_puts(b, "[X,1] "); put_phrase(b, src, r->phrases[4 * cid + 3], r->phrases[4 * cid + 2]); sb_puts(b, " [X,2]"); }
     else if (cid < G + D2) {
-        const int32_t *p2 = &r->pat2[4 * (cid - G)];
-        put_pat1(b, src, &r->pat1[8 * p2[0]], "[X,1]");
+        const int32_t *p2 = &r->pat2[2 * (cid - G)];
+        put_pat1(b, src, &r->pat1[4 * p2[0]], "[X,1]");
         sb_puts(b, " [X,2] "); sb_puts(b, cgxh_vocab_name(src->vocab, p2[1]));
-    } else if (cid < G + D2 + D1) { sb_puts(b, "[X,1] "); put_pat1(b, src, &r->pat1[8 * (cid - G - D2)], "[X,2]"); }
-    else { put_pat1(b, src, &r->pat1[8 * (cid - G - D2 - D1)], "[X,1]"); sb_puts(b, " [X,2]"); }
+    } else if (cid < G + D2 + D1) { sb_puts(b, "[X,1] "); put_pat1(b, src, &r->pat1[4 * (cid - G - D2)], "[X,2]"); }
+    else { put_pat1(b, src, &r->pat1[4 * (cid - G - D2 - D1)], "[X,1]"); sb_puts(b, " [X,2]"); }
 }
 
 static void put_group(sbuf *b, const cgx_result_t *r, const cgxh_side_t *src, const cgxh_side_t *tgt, int kind, int32_t cid, sbuf *srcbuf) {
     if (cid < 0 || cid >= r->n_ids[kind]) return;
-    int32_t lo = r->updown[kind][2 * cid], hi = r->updown[kind][2 * cid + 1];
-    if (lo < 0 || hi < 0) return;
+    const int32_t lo = r->first[kind][cid];
+    if (lo < 0) return;
+    const int32_t hi = lo + CGX_ID_RULES(r->idinfo[kind][cid]) - 1;
     srcbuf->n = 0;
     source_string(srcbuf, r, src, kind, cid);
     sb_reserve(srcbuf, 1);

@@ -166,8 +166,9 @@ int32_t cgx_batch_advice(const cgx_ctx_t *ctx, int32_t wanted);
 
 /* A distinct scored rule (red_dup_t, ComTypes.h:244-255), packed into 16 bytes: a C2 batch returns 7e7 of them and the
  * device-to-host copy of the rules is most of what a batch sends back (8 ranks on one host share its ingest bandwidth).
- * The converted id of a rule (ExtractPair.c:723-729 / :999-1006) is the `updown` range it sits in; the two per-id counts
- * (f, all_suffix_fsample) travel once per id in `idinfo` instead of once per rule. */
+ * The converted id of a rule (ExtractPair.c:723-729 / :999-1006) is the range it sits in -- rules come in ascending id order,
+ * `first[id]` is the id's first rule and its idinfo word says how many follow -- and the two per-id counts (f,
+ * all_suffix_fsample) travel once per id in `idinfo` instead of once per rule. */
 typedef struct {
     int32_t tgt_start;     /* representative target span: start in the target text */
     uint32_t span;         /* bits 0-3 end (inclusive length-1); 4-7 gap1, 8-11 gap1_1, 12-15 gap2, 16-19 gap2_1: target gaps as offsets
@@ -181,18 +182,21 @@ typedef struct {
 #define CGX_RULE_GAP2(r) ((int)(((r)->span >> 12) & 15u))
 #define CGX_RULE_GAP2_END(r) ((int)(((r)->span >> 16) & 15u))
 #define CGX_RULE_PC(r) ((int)(((r)->span >> 20) & 511u))
-/* idinfo word of a converted id: extracted pairs with this source id (-> IsSingletonF) and all_suffix_fsample capped at 300
- * (-> SampleCountF); 0 for an id without rules */
-#define CGX_ID_F(w) ((int)((w) & 0xffffu))
-#define CGX_ID_FS(w) ((int)((w) >> 16))
+/* idinfo word of a converted id: extracted pairs with this source id (-> IsSingletonF), all_suffix_fsample capped at 300
+ * (-> SampleCountF) and the number of distinct rules of the id (each <= 300: nine bits); 0 for an id without rules */
+#define CGX_ID_F(w) ((int)((w) & 0x1ffu))
+#define CGX_ID_FS(w) ((int)(((w) >> 9) & 0x1ffu))
+#define CGX_ID_RULES(w) ((int)(((w) >> 18) & 0x1ffu))
 
 /* Host views of the batch results (valid until the next cgx_extract; see cgx_extract_begin for the pipelined form):
  *   phrase_id : T*5 ints, id of the contiguous phrase q[t..t+len) for len = 1..5, -1 when absent
  *   phrases   : G x {sa_up, sa_down, len, corpus_pos}      (saind_t, ComTypes.h:342)
- *   pat1      : D1 x {a_pos, ls, b_pos, le, hit_start, hit_count, marker_pair(-1|0..9999), fs_extra}
- *   pat2      : D2 x {pat1_id, c_token, hit_start, hit_count}
+ *   pat1      : D1 x {a_pos, ls, b_pos, le}      (what the printer needs of gappy_search; hit ranges, marker and
+ *                                                 featureMissingCount stay on the device: cgx_debug_fetch "pat1_full")
+ *   pat2      : D2 x {pat1_id, c_token}          (cgx_debug_fetch "pat2_full" adds the hit range)
  *   q1_off/q1_ids, q2_off/q2_ids : per-query lists of one-gap / two-gap pattern ids (ascending id)
- *   rules[k], n_rules[k], and per converted id the [first,last] rule range (updown, -1 when empty) and its idinfo word */
+ *   rules[k], n_rules[k], and per converted id the index of its first rule (first, -1 when it has none; the rules of id are
+ *   first[id] .. first[id] + CGX_ID_RULES(idinfo[id]) - 1 -- globalOnPairsUpDown*, ExtractPair.cu:3745-3756) and its idinfo word */
 typedef struct {
     int32_t Q, T, G, D1, D2;
     const int32_t *phrase_id;
@@ -202,7 +206,7 @@ typedef struct {
     const int32_t *q1_off, *q1_ids, *q2_off, *q2_ids;
     const cgx_rule_t *rules[3];
     int32_t n_rules[3];
-    const int32_t *updown[3];
+    const int32_t *first[3];
     int32_t n_ids[3];
     const uint32_t *idinfo[3];
 } cgx_result_t;
@@ -211,7 +215,7 @@ int cgx_result_at(cgx_ctx_t *ctx, int age, cgx_result_t *out);      /* see cgx_e
 
 /* parity helpers (tests): intermediate arrays of the last batch, copied to the host.
  *   what = "longest" (T ints, capped at 5), "intervals" (T*5*2 ints), "hits1" (hits1 x 3: id,pos,len),
- *          "hits2" (hits2 x 4), "rec_ab"/"rec_1"/"rec_2" (7 ints per record, converted ids)
+ *          "hits2" (hits2 x 4), "rec_ab"/"rec_1"/"rec_2" (7 ints per record, converted ids), "pat1_full" (D1 x 8), "pat2_full" (D2 x 4)
  * Returns the number of int32 written (<= cap) or a negative error. */
 int64_t cgx_debug_fetch(cgx_ctx_t *ctx, const char *what, int32_t *out, int64_t cap);
 

@@ -74,8 +74,10 @@ def assert_full_parity(ex, res, lay, o):
     assert np.array_equal(ex.debug_fetch("hits1", int(res.info["hits1"]) * 3, 3), expand_marker_hits(o)), "one-gap hit list"
     assert np.array_equal(ex.debug_fetch("hits2", int(res.info["hits2"]) * 4, 4), o.twogap_hits()), "two-gap hit list"
     miss = o.feature_missing()
-    mk = (p1[:, 6] >= 0) & (p1[:, 5] > 0)
-    assert np.array_equal(p1[mk, 7], miss[p1[mk, 6]]), "featureMissingCount"
+    pf = ex.debug_fetch("pat1_full", res.D1 * 8, 8)             # device records: + hit_start, hit_count, marker_pair, fs_extra
+    assert np.array_equal(pf[:, :4], p1)
+    mk = (pf[:, 6] >= 0) & (pf[:, 5] > 0)
+    assert np.array_equal(pf[mk, 7], miss[pf[mk, 6]]), "featureMissingCount"
     for k, (name, cnt) in enumerate((("rec_ab", "n_ab"), ("rec_1", "n_1gap"), ("rec_2", "n_2gap"))):
         mine_r = ex.debug_fetch(name, int(res.info[cnt]) * 7, 7)
         orc_r = remap_ids(o.records(k), res, o, k)

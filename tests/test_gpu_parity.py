@@ -80,9 +80,11 @@ def test_patterns_and_hits(ex_micro, micro_oracle, micro):
     assert np.array_equal(ex.debug_fetch("hits1", int(res.info["hits1"]) * 3, 3), expand_marker_hits(o))
     assert np.array_equal(ex.debug_fetch("hits2", int(res.info["hits2"]) * 4, 4), o.twogap_hits())
     miss = o.feature_missing()
+    pf = ex.debug_fetch("pat1_full", res.D1 * 8, 8)             # device records: + hit_start, hit_count, marker_pair, fs_extra
+    assert np.array_equal(pf[:, :4], res.pat1) and np.array_equal(ex.debug_fetch("pat2_full", res.D2 * 4, 4)[:, :2], res.pat2)
     for d in range(res.D1):
-        if res.pat1[d, 6] >= 0 and res.pat1[d, 5] > 0:
-            assert int(res.pat1[d, 7]) == int(miss[res.pat1[d, 6]])
+        if pf[d, 6] >= 0 and pf[d, 5] > 0:
+            assert int(pf[d, 7]) == int(miss[pf[d, 6]])
 
 
 def test_extraction_records_bit_exact(ex_micro, micro_oracle):
@@ -518,9 +520,10 @@ def test_join_variants_agree_with_oracle(mode, ordered, micro, micro_oracle, mon
         assert np.array_equal(ex.debug_fetch("hits1", int(res.info["hits1"]) * 3, 3), expand_marker_hits(o))
         assert np.array_equal(ex.debug_fetch("hits2", int(res.info["hits2"]) * 4, 4), o.twogap_hits())
         miss = o.feature_missing()
+        pf = ex.debug_fetch("pat1_full", res.D1 * 8, 8)
         for d in range(res.D1):
-            if res.pat1[d, 6] >= 0 and res.pat1[d, 5] > 0:
-                assert int(res.pat1[d, 7]) == int(miss[res.pat1[d, 6]])
+            if pf[d, 6] >= 0 and pf[d, 5] > 0:
+                assert int(pf[d, 7]) == int(miss[pf[d, 6]])
         for k in range(3):
             assert len(res.rules[k]) == len(o.rules(k))
     finally:

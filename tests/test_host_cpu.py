@@ -123,7 +123,7 @@ def test_rule_wire_format_macros_agree_with_python_decode(tmp_path):
         if cnt == 0:
             continue
         updown[cid] = (len(rows), len(rows) + cnt - 1)
-        idinfo[cid] = int(rng.integers(1, 301)) | (int(rng.integers(1, 301)) << 16)
+        idinfo[cid] = int(rng.integers(1, 301)) | (int(rng.integers(1, 301)) << 9) | (cnt << 18)
         for _ in range(cnt):
             end = int(rng.integers(0, 15))
             g = sorted(rng.integers(0, end + 1, size=4).tolist())
@@ -149,8 +149,8 @@ int main(int argc, char **argv) {
     while (fread(&r, sizeof r, 1, f) == 1)
         printf("%d %d %d %d %d %d %d\n", r.tgt_start, CGX_RULE_END(&r), CGX_RULE_GAP1(&r), CGX_RULE_GAP1_END(&r), CGX_RULE_GAP2(&r),
                CGX_RULE_GAP2_END(&r), CGX_RULE_PC(&r));
-    unsigned w = 0x012c0007u;
-    printf("%d %d %d\n", CGX_ID_F(w), CGX_ID_FS(w), CGX_RULE_NOGAP);
+    unsigned w = 7u | 300u << 9 | 211u << 18;
+    printf("%d %d %d %d\n", CGX_ID_F(w), CGX_ID_FS(w), CGX_ID_RULES(w), CGX_RULE_NOGAP);
     return 0;
 }
 """)
@@ -158,7 +158,7 @@ int main(int argc, char **argv) {
     raw.write_bytes(wire.tobytes())
     subprocess.run(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
     out = subprocess.run([str(exe), str(raw)], capture_output=True, text=True, check=True).stdout.split("\n")
-    assert out[len(wire)].split() == ["7", "300", "15"]
+    assert out[len(wire)].split() == ["7", "300", "211", "15"]
     for i, line in enumerate(out[:len(wire)]):
         ts, end, g1, g1e, g2, g2e, pc = (int(x) for x in line.split())
         m = mine[i]
@@ -167,7 +167,7 @@ int main(int argc, char **argv) {
                (int(m["tgt_start"]), int(m["end"]), int(m["gap1"]), int(m["gap1_1"]), int(m["gap2"]), int(m["gap2_1"]), int(m["pc"])), i
     ids = np.repeat(np.arange(n_ids), np.where(updown[:, 0] >= 0, updown[:, 1] - updown[:, 0] + 1, 0))
     assert np.array_equal(mine["id"], ids)
-    assert np.array_equal(mine["f"], idinfo[ids] & 0xFFFF) and np.array_equal(mine["fs"], idinfo[ids] >> 16)
+    assert np.array_equal(mine["f"], idinfo[ids] & 0x1FF) and np.array_equal(mine["fs"], (idinfo[ids] >> 9) & 0x1FF)
 
 
 

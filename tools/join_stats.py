@@ -16,7 +16,7 @@ ex.build_index(lay)
 res = ex.extract(lay["qry_tok"], lay["qry_off"])
 D1, D2 = res.D1, res.D2
 pd = ex.debug_fetch("pat1_dev", D1 * 4, 4)
-p1 = res.pat1
+p1 = ex.debug_fetch("pat1_full", D1 * 8, 8)
 nA = pd[:, 1] - pd[:, 0] + 1
 nB = pd[:, 3] - pd[:, 2] + 1
 W = np.minimum(nA, nB).astype(np.int64)

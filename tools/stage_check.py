@@ -91,9 +91,10 @@ def main():
     # featureMissingCount of marker patterns
     miss = o.feature_missing()
     okm = True
+    pf = ex.debug_fetch("pat1_full", res.D1 * 8, 8)
     for d in range(res.D1):
-        if res.pat1[d, 6] >= 0 and res.pat1[d, 5] > 0:
-            okm &= int(res.pat1[d, 7]) == int(miss[res.pat1[d, 6]])
+        if pf[d, 6] >= 0 and pf[d, 5] > 0:
+            okm &= int(pf[d, 7]) == int(miss[pf[d, 6]])
     check("featureMissingCount of frequent-pair patterns", okm)
     check("enu2/D2", res.info["enu2"] == oc.enu2 and res.D2 == oc.D2)
     if res.D2 == oc.D2:
