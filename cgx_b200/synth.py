@@ -349,28 +349,38 @@ def write_text(c: SynthCorpus, outdir: str, prefix: str = "corpus") -> dict:
     lay = text_layout(c)
     paths = {k: os.path.join(outdir, f"{prefix}.{k}") for k in ("f", "q", "e", "a", "lex")}
 
-    def dump_sentences(path, words, off, tag):
-        strs = np.char.add(tag, words.astype(str))
+    def dump_lines(path, strs, off):
+        """One line per [off[k], off[k+1]) run of strs, blank-separated; empty runs give empty lines.  Vectorised: every
+        string gets its separator appended (a blank, or as many newlines as lines end after it) and the lot is joined once."""
+        off = np.asarray(off, dtype=np.int64)
+        n_lines, n = len(off) - 1, len(strs)
         with open(path, "w") as fh:
-            for k in range(len(off) - 1):
-                fh.write(" ".join(strs[off[k]:off[k + 1]]))
-                fh.write("\n")
+            if n == 0:
+                fh.write("\n" * n_lines)
+                return
+            line_of = np.searchsorted(off, np.arange(n), side="right") - 1          # line of every string
+            ends_here = np.bincount(line_of, minlength=n_lines)                     # strings per line
+            last = off[1:][ends_here > 0] - 1                                       # last string of every non-empty line
+            nonempty = np.nonzero(ends_here > 0)[0]
+            nxt = np.append(nonempty[1:], n_lines)                                  # next non-empty line (or the end)
+            sep = np.full(n, " ", dtype=object)
+            sep[last] = ["\n" * int(k) for k in (nxt - nonempty)]
+            fh.write("\n" * int(nonempty[0]))
+            step = 1 << 22
+            for a in range(0, n, step):
+                fh.write("".join(map(str.__add__, strs[a:a + step].tolist(), sep[a:a + step].tolist())))
 
-    dump_sentences(paths["f"], c.src_words, c.src_off, "s")
-    dump_sentences(paths["e"], c.tgt_words, c.tgt_off, "t")
-    qstr = np.where(c.qry_words >= 0, np.char.add("s", c.qry_words.astype(str)), "OOV" + "x")
-    with open(paths["q"], "w") as fh:
-        for k in range(len(c.qry_off) - 1):
-            fh.write(" ".join(qstr[c.qry_off[k]:c.qry_off[k + 1]]))
-            fh.write("\n")
+    def names(tag, words):                                     # "<tag><word>" through a table of the distinct words
+        top = int(words.max()) + 1 if len(words) else 0
+        return np.char.add(tag, np.arange(top).astype(str))[words]
+
+    dump_lines(paths["f"], names("s", c.src_words), c.src_off)
+    dump_lines(paths["e"], names("t", c.tgt_words), c.tgt_off)
+    dump_lines(paths["q"], np.where(c.qry_words >= 0, names("s", np.maximum(c.qry_words, 0)), "OOV" + "x"), c.qry_off)
     order = np.argsort(c.link_sent, kind="stable")
     ls, lsrc, ltgt = c.link_sent[order], c.link_s[order], c.link_t[order]
     bounds = np.searchsorted(ls, np.arange(c.n_sent + 1))
-    with open(paths["a"], "w") as fh:
-        for k in range(c.n_sent):
-            a, b = bounds[k], bounds[k + 1]
-            fh.write(" ".join(f"{s}-{t}" for s, t in zip(lsrc[a:b], ltgt[a:b])))
-            fh.write("\n")
+    dump_lines(paths["a"], np.char.add(names("", lsrc), names("-", ltgt)), bounds)
     sname = lambda i: "NULL" if i < 0 else "s%d" % lay["src_names"][i - 2]
     tname = lambda i: "NULL" if i < 0 else "t%d" % lay["tgt_names"][i - 2]
     with open(paths["lex"], "w") as fh:
