@@ -324,6 +324,7 @@ __global__ void __launch_bounds__(128) agg_rules_kernel(AggIdx a, int kind, cons
 // per converted id: index of its first rule (the rules come out in ascending id order, so an id's rules are consecutive:
 // globalOnPairsUpDown*, ExtractPair.cu:3745-3756, :3805-3816, :2082) and, in bits 18..26 of its idinfo word, how many there are.
 // The count is last - first + 1 < 512, added modulo 512 in two halves by the threads at the two ends of the id's run.
+static_assert(CGX_SAMPLER < 512, "idinfo packs f, fs and the rule count of an id in nine bits each: all three are bounded by the sampler");
 __global__ void agg_updown_kernel(const int32_t *__restrict__ rule_id, uint32_t n_rules, int32_t *__restrict__ first, uint32_t *__restrict__ idinfo) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rules) return;

@@ -51,6 +51,7 @@ def load():
     H.cgxh_vocab_size.argtypes = [C.c_void_p]
     H.cgxh_vocab_size.restype = C.c_int32
     H.cgxh_alignment_load.argtypes = [C.c_char_p, C.POINTER(Side), C.POINTER(Side), C.POINTER(Align)]
+    H.cgxh_load_files.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(Side), C.POINTER(Side), C.POINTER(Align), C.POINTER(Lex)]
     H.cgxh_lex_load.argtypes = [C.c_char_p, C.POINTER(Side), C.POINTER(Side), C.POINTER(Lex)]
     H.cgxh_queries_load.argtypes = [C.c_char_p, C.POINTER(Side), C.POINTER(Queries)]
     H.cgxh_write_grammars.argtypes = [C.c_char_p, C.POINTER(Result), C.POINTER(C.c_int32), C.c_int32, C.POINTER(Side), C.POINTER(Side), C.c_int]
@@ -71,16 +72,13 @@ class HostCorpus:
         H = load()
         self.H = H
         self.src, self.tgt, self.al, self.lex, self.qry = Side(), Side(), Align(), Lex(), Queries()
-        if H.cgxh_corpus_load(src.encode(), 1, C.byref(self.src)):
-            raise RuntimeError("cannot load " + src)
-        if H.cgxh_corpus_load(tgt.encode(), 0, C.byref(self.tgt)):
-            raise RuntimeError("cannot load " + tgt)
-        if H.cgxh_lex_load(lex.encode(), C.byref(self.src), C.byref(self.tgt), C.byref(self.lex)):
-            raise RuntimeError("cannot load " + lex)
+        # the loaders the command line runs (run.c): source || target, then alignment || lexical file
+        rc = H.cgxh_load_files(src.encode(), tgt.encode(), align.encode(), lex.encode(), C.byref(self.src), C.byref(self.tgt), C.byref(self.al),
+                               C.byref(self.lex))
+        if rc:
+            raise RuntimeError("cannot load the corpus files (%s, %s, %s, %s): code %d" % (src, tgt, align, lex, rc))
         if H.cgxh_queries_load(qry.encode(), C.byref(self.src), C.byref(self.qry)):
             raise RuntimeError("cannot load " + qry)
-        if H.cgxh_alignment_load(align.encode(), C.byref(self.src), C.byref(self.tgt), C.byref(self.al)):
-            raise RuntimeError("cannot load " + align)
 
     def layout(self):
         n, m = int(self.src.n), int(self.tgt.n)

@@ -61,6 +61,10 @@ int cgxh_alignment_load(const char *path, const cgxh_side_t *src, const cgxh_sid
 void cgxh_align_free(cgxh_align_t *a);
 int cgxh_lex_load(const char *path, const cgxh_side_t *src, const cgxh_side_t *tgt, cgxh_lex_t *out);
 void cgxh_lex_free(cgxh_lex_t *l);
+/* the four loaders above over all the files of a corpus, two threads at a time (source || target, then alignment || lexical file);
+ * align_path / lex_path NULL = not parsed (*al / *lex zeroed).  Returns the first loader's non-zero code. */
+int cgxh_load_files(const char *src_path, const char *tgt_path, const char *align_path, const char *lex_path, cgxh_side_t *src,
+                    cgxh_side_t *tgt, cgxh_align_t *al, cgxh_lex_t *lex);
 int cgxh_queries_load(const char *path, const cgxh_side_t *src, cgxh_queries_t *out);
 void cgxh_queries_free(cgxh_queries_t *q);
 

@@ -188,33 +188,50 @@ static int serve_one(serve_t *sv, const char *qryfile, const char *outdir) {
     return rc;
 }
 
+/* device side of the start-up, run beside the text loaders: the CUDA contexts (a few hundred ms of driver start-up) and, when a
+ * persisted index exists, reading it into HBM */
+typedef struct {
+    const cgxh_options_t *opt;
+    cgx_ctx_t **ctx;
+    int n_gpus, have_index, rc;
+    char err[600];
+} gpu_open_t;
+static void *gpu_open_main(void *arg) {
+    gpu_open_t *g = (gpu_open_t *)arg;
+    for (int d = 0; d < g->n_gpus; d++)
+        if (cgx_create(d, &g->ctx[d])) { snprintf(g->err, sizeof g->err, "cgx_create(%d): %s", d, cgx_last_error(NULL)); g->rc = 1; return NULL; }
+    if (g->have_index && cgx_index_load(g->ctx[0], g->opt->index_file)) {
+        snprintf(g->err, sizeof g->err, "cgx_index_load: %s", cgx_last_error(g->ctx[0]));
+        g->rc = 1;
+    }
+    return NULL;
+}
+
 int cgxh_run(const cgxh_options_t *opt) {
     cgxh_side_t src, tgt;
     cgxh_align_t al;
     cgxh_lex_t lex;
     double t0 = now_s();
-    fprintf(stderr, "\nLoading the reference\n");
-    if (cgxh_corpus_load(opt->reffile, 1, &src)) return 1;
-    fprintf(stderr, "Reference toklen number is %lld HASH_COUNT %d\n", (long long)src.n, cgxh_vocab_size(src.vocab) - 2);
-    if (cgxh_corpus_load(opt->reftargetfile, 0, &tgt)) return 1;
-    fprintf(stderr, "Target Reference toklen number is %lld HASH_COUNT TARGET %d\n", (long long)tgt.n, cgxh_vocab_size(tgt.vocab) - 2);
     int have_index = 0;
     if (opt->index_file) { FILE *fh = fopen(opt->index_file, "rb"); if (fh) { have_index = 1; fclose(fh); } }
-    memset(&lex, 0, sizeof lex);
-    memset(&al, 0, sizeof al);
-    if (!have_index) {
-        if (cgxh_lex_load(opt->wordscdec, &src, &tgt, &lex)) return 1;
-        fprintf(stderr, "Lex File Word Possibility COUNTER: %lld\n", (long long)lex.count);
-    }
-    if (!have_index && cgxh_alignment_load(opt->align, &src, &tgt, &al)) return 1;
-    double t1 = now_s();
-
     int n_gpus = opt->n_gpus > 0 ? opt->n_gpus : 1;
     cgx_ctx_t **ctx = (cgx_ctx_t **)calloc((size_t)n_gpus, sizeof(cgx_ctx_t *));
-    for (int g = 0; g < n_gpus; g++)
-        if (cgx_create(g, &ctx[g])) { fprintf(stderr, "cgx_create(%d): %s\n", g, cgx_last_error(NULL)); return 1; }
+    gpu_open_t go;
+    memset(&go, 0, sizeof go);
+    go.opt = opt; go.ctx = ctx; go.n_gpus = n_gpus; go.have_index = have_index;
+    pthread_t go_th;
+    const int go_threaded = pthread_create(&go_th, NULL, gpu_open_main, &go) == 0;
+    fprintf(stderr, "\nLoading the reference\n");
+    /* source || target, then alignment || lexical file; with a persisted index the last two are not parsed */
+    const int load_rc = cgxh_load_files(opt->reffile, opt->reftargetfile, have_index ? NULL : opt->align, have_index ? NULL : opt->wordscdec, &src, &tgt, &al, &lex);
+    double t1 = now_s();
+    if (go_threaded) pthread_join(go_th, NULL); else gpu_open_main(&go);
+    if (load_rc) return 1;
+    fprintf(stderr, "Reference toklen number is %lld HASH_COUNT %d\n", (long long)src.n, cgxh_vocab_size(src.vocab) - 2);
+    fprintf(stderr, "Target Reference toklen number is %lld HASH_COUNT TARGET %d\n", (long long)tgt.n, cgxh_vocab_size(tgt.vocab) - 2);
+    if (!have_index) fprintf(stderr, "Lex File Word Possibility COUNTER: %lld\n", (long long)lex.count);
+    if (go.rc) { fprintf(stderr, "%s\n", go.err); return 1; }
     if (have_index) {
-        if (cgx_index_load(ctx[0], opt->index_file)) { fprintf(stderr, "cgx_index_load: %s\n", cgx_last_error(ctx[0])); return 1; }
         fprintf(stderr, "index loaded from %s\n", opt->index_file);
     } else {
         if (al.wide) fprintf(stderr, "sentences of 255 tokens and more: 16-bit alignment fields\n");

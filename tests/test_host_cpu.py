@@ -89,6 +89,117 @@ def test_loader_edge_cases(tmp_path, built):
     assert sorted(zip(h["lex_f"].tolist(), h["lex_e"].tolist())) == [(-1, -1), (-1, 2), (2, 2), (3, -1)]
 
 
+def _strtok_walk(line, delims=" "):
+    """The reference's walk over a line (Start.cu:270-310): one trailing newline stripped, tokens = maximal runs of characters outside
+    `delims`, the walk ends at the first token that begins with white space."""
+    if line.endswith("\n"):
+        line = line[:-1]
+    out = []
+    for t in re.split("[" + re.escape(delims) + "]+", line):
+        if t == "":
+            continue
+        if t[0] in " \t\r\v\f\n":
+            break
+        out.append(t)
+    return out
+
+
+def _atoi(t):
+    m = re.match(r"[ \t\r\v\f\n]*\+?([0-9]*)", t)
+    return int(m.group(1)) if m.group(1) else 0
+
+
+def test_loaders_on_ragged_text_equal_a_python_restatement(tmp_path, built):
+    """Leading / doubled / trailing blanks, tabs and carriage returns inside tokens, a token that begins with a tab (the rest of the line
+    is dropped), empty lines, files without a final newline, alignment lines with stray blanks, lexical fields split over lines:
+    the C loaders (two threads at a time, cgxh_load_files) against a line-by-line Python restatement of Start.cu:50-132, :240-380,
+    ExtractPair.cu:2463-2519 and :2639-2739."""
+    import random
+    from cgx_b200.host import HostCorpus
+    rnd = random.Random(11)
+    for final_newline in (True, False):
+        src, tgt, al = [], [], []
+        for k in range(300):
+            ns, nt = rnd.randint(1, 30), rnd.randint(1, 30)
+            s, t = ["s%d" % rnd.randint(0, 40) for _ in range(ns)], ["t%d" % rnd.randint(0, 40) for _ in range(nt)]
+            mode = k % 10
+            if mode == 3 and ns > 3:
+                s[2] = "a\tb"
+            if mode == 4 and ns > 3:
+                s[rnd.randrange(1, ns)] = "\tzz"
+            sl, tl = " ".join(s), " ".join(t)
+            if mode == 1:
+                sl = "  " + sl.replace(" ", "   ", 2) + "  "
+            if mode == 2:
+                sl, tl = sl + "\r", tl + "\r"
+            if mode == 7:
+                tl = ""
+            ns_eff, nt_eff = len(_strtok_walk(sl)), len(_strtok_walk(tl))
+            links = sorted({(rnd.randrange(ns_eff), rnd.randrange(nt_eff)) for _ in range(rnd.randint(0, 40))}) if ns_eff and nt_eff else []
+            a = " ".join("%d-%d" % l for l in links)
+            if mode == 5:
+                a = a.replace(" ", "  ") + " "
+            if mode == 6:
+                a = " " + a
+            if mode == 8:
+                a = ""
+            if mode == 9 and links:
+                a = a.replace("-", " - ", 1)
+            src.append(sl); tgt.append(tl); al.append(a)
+        lexl = []
+        for i in range(2000):
+            f = rnd.choice(["NULL", "s%d" % rnd.randint(0, 60), "unk%d" % i])
+            e = rnd.choice(["NULL", "t%d" % rnd.randint(0, 60), "unk"])
+            lexl.append(f + rnd.choice([" ", "  ", "\t", " \n"]) + e + " %.6g %g" % (rnd.random(), rnd.random() * 1e-3))
+        qry = [" ".join(rnd.choice(["s%d" % rnd.randint(0, 50), "oov"]) for _ in range(rnd.randint(0, 40))) for _ in range(40)]
+        qry[3], qry[5], qry[7] = "  " + qry[3] + "  ", qry[5] + "\r", "s1 \ts2 s3"
+        end = "\n" if final_newline else ""
+        for name, lines in (("f", src), ("e", tgt), ("a", al), ("lex", lexl), ("q", qry)):
+            (tmp_path / name).write_text("\n".join(lines) + end)
+        h = HostCorpus(*(str(tmp_path / k) for k in ("f", "q", "e", "a", "lex"))).layout()
+
+        def side(lines):
+            ids, tok, sent, pos = {}, [], [0], []
+            for line in lines:
+                for j, w in enumerate(_strtok_walk(line)):
+                    tok.append(ids.setdefault(w, len(ids) + 2))
+                    pos.append(j & 255)
+                tok.append(1); pos.append(0); sent.append(len(tok))
+            last = len(ids) + 2                          # one past the id added last
+            return ids, tok + [1, last, 0, 0, 0], sent, pos + [0, 0]
+        sid, stok, ssent, spos = side(src)
+        tid, ttok, tsent, _ = side(tgt)
+        assert h["str"].tolist() == stok and h["tgt"].tolist() == ttok
+        assert h["src_sentenceind"].tolist() == ssent and h["tgt_sentenceind"].tolist() == tsent and h["P"].tolist() == spos
+        qt, qo = [], [0]
+        for line in qry:
+            qt += [sid.get(w, -1) for w in _strtok_walk(line)]
+            qo.append(len(qt))
+        assert h["qry_tok"].tolist() == qt and h["qry_off"].tolist() == qo
+        n, m = h["n"], h["m"]
+        Ls, Rs, Lt, Rt = [255] * n, [255] * n, [255] * m, [255] * m
+        for k, line in enumerate(al):
+            nums = [_atoi(t) for t in _strtok_walk(line, " -")]
+            for s_no, t_no in zip(nums[0::2], nums[1::2]):
+                si, ti = ssent[k] + s_no, tsent[k] + t_no
+                Ls[si], Rs[si] = (t_no, t_no) if Ls[si] == 255 else (min(Ls[si], t_no), max(Rs[si], t_no))
+                Lt[ti], Rt[ti] = (s_no, s_no) if Lt[ti] == 255 else (min(Lt[ti], s_no), max(Rt[ti], s_no))
+        assert h["L_tar"].tolist() == Lt and h["R_tar"].tolist() == Rt
+        eos = set(x - 1 for x in ssent[1:])
+        got = h["RLP"]
+        for i in range(n - 1):
+            if i not in eos:
+                assert (int(got[i]) >> 24, (int(got[i]) >> 16) & 255, (int(got[i]) >> 8) & 255) == (Ls[i], Rs[i], spos[i]), i
+        fields = " ".join(lexl).split()
+        want = []
+        for f, e, x, y in zip(fields[0::4], fields[1::4], fields[2::4], fields[3::4]):
+            fi, ei = sid.get(f, -1), tid.get(e, -1)
+            if (fi < 0 and f != "NULL") or (ei < 0 and e != "NULL"):
+                continue
+            want.append((fi, ei, np.float32(x), np.float32(y)))
+        assert list(zip(h["lex_f"].tolist(), h["lex_e"].tolist(), h["lex_v1"], h["lex_v2"])) == want
+
+
 def test_cli_usage_contract(built):
     """Exactly six positionals, otherwise help and exit 0 (Main.c:46-48)."""
     exe = os.path.join(ROOT, "bin", "strmatchcuda")
