@@ -293,8 +293,12 @@ extern "C" int cgx_index_commit(cgx_ctx_t *c) {
 }
 
 // ---- persisted index (the reference only has the dead sa_precomp.txt stub, SuffixArray.c:208-230) --------------
+// The file holds what cannot be recomputed on the device -- the two token arrays, the alignment arrays and the sorted lexical table
+// (18 bytes per token pair at C2) -- and a load rebuilds the suffix array and the auxiliary arrays from them (30 ms at C2).  Round 2
+// first saved every resident array (88 bytes per token pair): reading 2.3 GB took 1.3 s from the page cache and 3-5 s from disk,
+// longer than parsing the text files and building from scratch.
 struct IndexFileHeader {
-    char magic[8];                 // "CGXIDX02"
+    char magic[8];                 // "CGXIDX03"
     int64_t n, m, lex_count;
     int32_t max_token, sa_rounds, sa_key_bits, wide;      // wide: 16-bit alignment fields (0 in files written before the field existed)
     int32_t freq_list[CGX_PRECOMP];
@@ -309,6 +313,8 @@ static int index_array_refs(const cgx_index_arrays_t &a, IndexArrayRef out[18]) 
     for (int i = 0; i < 18; i++) out[i] = r[i];
     return 18;
 }
+// the arrays of index_array_refs that a file holds: str, RLP, L_tar, R_tar, tgt, lex_key, lex_v1, lex_v2
+static const int kPersisted[8] = {0, 9, 10, 11, 12, 15, 16, 17};
 
 extern "C" int cgx_index_save(cgx_ctx_t *c, const char *path) {
     FILE *fh = nullptr;
@@ -323,7 +329,7 @@ extern "C" int cgx_index_save(cgx_ctx_t *c, const char *path) {
         CGX_REQUIRE(fh, "cannot open %s for writing", tmp_path.c_str());
         IndexFileHeader h;
         memset(&h, 0, sizeof h);
-        memcpy(h.magic, "CGXIDX02", 8);
+        memcpy(h.magic, "CGXIDX03", 8);
         h.n = a.n; h.m = a.m; h.lex_count = a.lex_count; h.max_token = a.max_token; h.sa_rounds = c->ix.sa_stats.rounds; h.sa_key_bits = c->ix.sa_stats.key_bits; h.wide = a.wide;
         h.src_sum = c->ix.src_sum; h.tgt_sum = c->ix.tgt_sum;
         memcpy(h.freq_list, a.freq_list, sizeof h.freq_list);
@@ -331,8 +337,8 @@ extern "C" int cgx_index_save(cgx_ctx_t *c, const char *path) {
         const size_t piece = (size_t)64 << 20;
         CUDA_CHECK(cudaMallocHost(&stage, piece));
         IndexArrayRef r[18];
-        const int k = index_array_refs(a, r);
-        for (int i = 0; i < k; i++)
+        index_array_refs(a, r);
+        for (int i : kPersisted)
             for (size_t o = 0; o < r[i].bytes; o += piece) {
                 const size_t len = std::min(piece, r[i].bytes - o);
                 CUDA_CHECK(cudaMemcpy(stage, (const char *)r[i].p + o, len, cudaMemcpyDeviceToHost));
@@ -362,7 +368,7 @@ extern "C" int cgx_index_load(cgx_ctx_t *c, const char *path) {
         fh = fopen(path, "rb");
         CGX_REQUIRE(fh, "cannot open %s", path);
         IndexFileHeader h;
-        CGX_REQUIRE(fread(&h, sizeof h, 1, fh) == 1 && memcmp(h.magic, "CGXIDX02", 8) == 0, "%s is not a cgx-b200 index file of this version", path);
+        CGX_REQUIRE(fread(&h, sizeof h, 1, fh) == 1 && memcmp(h.magic, "CGXIDX03", 8) == 0, "%s is not a cgx-b200 index file of this version", path);
         CGX_REQUIRE(h.n >= 4 && h.m >= 1 && h.lex_count >= 0 && h.max_token >= 1, "%s: corrupt header", path);
         cgx_index_arrays_t shape, a;
         memset(&shape, 0, sizeof shape);
@@ -372,21 +378,22 @@ extern "C" int cgx_index_load(cgx_ctx_t *c, const char *path) {
         const size_t piece = (size_t)64 << 20;
         CUDA_CHECK(cudaMallocHost(&stage, piece));
         IndexArrayRef r[18];
-        const int k = index_array_refs(a, r);
-        for (int i = 0; i < k; i++)
+        index_array_refs(a, r);
+        for (int i : kPersisted)
             for (size_t o = 0; o < r[i].bytes; o += piece) {
                 const size_t len = std::min(piece, r[i].bytes - o);
                 CGX_REQUIRE(fread(stage, 1, len, fh) == len, "%s: truncated", path);
                 CUDA_CHECK(cudaMemcpy((char *)r[i].p + o, stage, len, cudaMemcpyHostToDevice));
             }
+        CGX_REQUIRE(fgetc(fh) == EOF, "%s: longer than its header says", path);
         cudaFreeHost(stage);
         stage = nullptr;
         fclose(fh);
         fh = nullptr;
-        c->ix.sa_stats.rounds = h.sa_rounds; c->ix.sa_stats.key_bits = h.sa_key_bits; c->ix.sa_stats.ms = 0.f; c->ix.sa_stats.launches = 0;
+        build_index_device(c);                     // suffix array + auxiliary arrays from the token and alignment arrays just read
+        build_lex_hash(c->ix, c->stream);          // derived from the sorted lexical arrays
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
         c->ix.src_sum = h.src_sum; c->ix.tgt_sum = h.tgt_sum;
-        c->aux_ms = 0.f;
-        CGX_REQUIRE(cgx_index_commit(c) == 0, "%s", c->err.c_str());
         return 0;
     } catch (const CgxError &e) {
         if (fh) fclose(fh);

@@ -97,10 +97,12 @@ int cgx_index_commit(cgx_ctx_t *ctx);                                      /* ma
  * their own communicator instead (cgx_index_export / cgx_index_alloc / cgx_index_commit). */
 int cgx_index_broadcast(cgx_ctx_t **ctxs, int n);
 
-/* Persisted index: every resident index array (text, suffix array, occurrence lists, bucket ids, alignment arrays, gap
- * words, sorted lexical table) written to / read from one file, so that later runs on the same corpus skip the loaders'
- * GPU work and the SA build.  The reference only has a dead stub of this (SuffixArray.c:208-230 "sa_precomp.txt"; README.md:85
- * promises separating the one-time costs).  cgx_index_load replaces cgx_index_build + cgx_lex_load. */
+/* Persisted index: the index inputs as the loaders laid them out (the two token arrays, the alignment arrays, the sorted lexical
+ * table: 18 bytes per token pair) written to / read from one file, so that later runs on the same corpus skip parsing the
+ * alignment and lexical files.  A load rebuilds the suffix array and the auxiliary arrays on the device (30 ms at 26 M tokens:
+ * cheaper than reading them back, which is what the first form of this file did).  The reference only has a dead stub of this
+ * (SuffixArray.c:208-230 "sa_precomp.txt"; README.md:85 promises separating the one-time costs).  cgx_index_load replaces
+ * cgx_index_build + cgx_lex_load. */
 int cgx_index_save(cgx_ctx_t *ctx, const char *path);
 int cgx_index_load(cgx_ctx_t *ctx, const char *path);
 /* 1 when the resident index was built from exactly these token arrays (same lengths, same FNV-1a checksums, which the index
