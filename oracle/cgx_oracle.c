@@ -230,12 +230,14 @@ static int cmp_ki(const void *x, const void *y) {
 }
 static void set_lex(orc_t *o, const int32_t *f, const int32_t *e, const float *v1, const float *v2, int32_t cnt) {
     /* sort by (ch, eng) -- ExtractPair.cu:28-35,2537 */
-    ki_t *a = (ki_t *)malloc(sizeof(ki_t) * (size_t)(cnt ? cnt : 1));
+    if (cnt < 0) cnt = 0;
+    const size_t room = cnt > 0 ? (size_t)cnt : 1;
+    ki_t *a = (ki_t *)malloc(sizeof(ki_t) * room);
     for (int32_t i = 0; i < cnt; i++) { a[i].k = ((int64_t)f[i] << 32) + (int64_t)e[i] + (1LL << 31); a[i].i = i; }
     qsort(a, (size_t)cnt, sizeof(ki_t), cmp_ki);
-    o->lex_key = (int64_t *)malloc(sizeof(int64_t) * (size_t)(cnt ? cnt : 1));
-    o->lex_v1 = (float *)malloc(sizeof(float) * (size_t)(cnt ? cnt : 1));
-    o->lex_v2 = (float *)malloc(sizeof(float) * (size_t)(cnt ? cnt : 1));
+    o->lex_key = (int64_t *)malloc(sizeof(int64_t) * room);
+    o->lex_v1 = (float *)malloc(sizeof(float) * room);
+    o->lex_v2 = (float *)malloc(sizeof(float) * room);
     for (int32_t i = 0; i < cnt; i++) { o->lex_key[i] = a[i].k; o->lex_v1[i] = v1[a[i].i]; o->lex_v2[i] = v2[a[i].i]; }
     o->lex_count = cnt;
     free(a);
@@ -1551,6 +1553,11 @@ const int32_t *orc_frequent(const orc_t *o) { return o->freq; }
 const int32_t *orc_feature_missing(const orc_t *o) { return o->missing; }
 const int32_t *orc_precomp_index(const orc_t *o) { return o->pidx; }
 const int32_t *orc_precomp_list(const orc_t *o) { return o->plist; }
+int32_t orc_query_list(const orc_t *o, int which, int32_t qi, const int32_t **out) {
+    if (qi < 0 || qi >= o->Q) { *out = NULL; return 0; }
+    const ivec *v = which == 0 ? &o->qryglobal[qi] : which == 1 ? &o->q1[qi] : &o->q2[qi];
+    *out = v->v; return (int32_t)v->n;
+}
 int32_t orc_records(const orc_t *o, int kind, const int32_t **out) {
     const rvec *v = kind == 0 ? &o->rec_ab : kind == 1 ? &o->rec_1 : &o->rec_2;
     *out = (const int32_t *)v->v; return (int32_t)v->n;

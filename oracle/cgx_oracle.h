@@ -102,6 +102,10 @@ const int32_t *orc_twogap_hits(const orc_t *o);
 /* top-100 frequent tokens (ascending id) and featureMissingCount[100*100] */
 const int32_t *orc_frequent(const orc_t *o);
 const int32_t *orc_feature_missing(const orc_t *o);
+/* Per-query id lists in the order the writer walks them (PrintResults.c:451-570): which = 0 distinct contiguous phrases of query qi
+ * in first-appearance order (GenerateBlocks), 1 its one-gap patterns, 2 its two-gap patterns.  Returns the count. */
+int32_t orc_query_list(const orc_t *o, int which, int32_t qi, const int32_t **out);
+
 /* precomputed pair lists: index[100*100] x {start,end} and list[precomp_count] x {start,len} */
 const int32_t *orc_precomp_index(const orc_t *o);
 const int32_t *orc_precomp_list(const orc_t *o);

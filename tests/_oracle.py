@@ -68,6 +68,8 @@ def lib(wide=False):
         L.orc_interval.argtypes = [vp, C.c_int32, C.c_int32, i32p, i32p]
         L.orc_records.restype = C.c_int32
         L.orc_records.argtypes = [vp, C.c_int, C.POINTER(i32p)]
+        L.orc_query_list.restype = C.c_int32
+        L.orc_query_list.argtypes = [vp, C.c_int, C.c_int32, C.POINTER(i32p)]
         L.orc_rules.restype = C.c_int32
         L.orc_rules.argtypes = [vp, C.c_int, C.POINTER(vp)]
         _libs[wide] = L
@@ -220,6 +222,12 @@ class Oracle:
 
     def precomp_list(self):
         return _arr(self.L.orc_precomp_list(self.h), self.counts().precomp_count, 2)
+
+    def query_list(self, which, qi):
+        """ids the writer walks for query qi: which = 0 contiguous phrases (first-appearance order), 1 one-gap, 2 two-gap patterns"""
+        p = C.POINTER(C.c_int32)()
+        n = self.L.orc_query_list(self.h, which, qi, C.byref(p))
+        return _arr(p, n)
 
     def records(self, kind):
         p = C.POINTER(C.c_int32)()

@@ -200,6 +200,106 @@ def test_loaders_on_ragged_text_equal_a_python_restatement(tmp_path, built):
         assert list(zip(h["lex_f"].tolist(), h["lex_e"].tolist(), h["lex_v1"], h["lex_v2"])) == want
 
 
+def test_writer_prints_the_oracles_results_exactly_like_the_oracle(micro, micro_files, tmp_path, built):
+    """cgx_b200/host/writer.c on the CPU: a cgx_result_t assembled from the oracle's own arrays (distinct phrases, pattern tables,
+    per-query id lists, distinct rules packed into the 16-byte wire records + first / idinfo words) must print, through the C
+    writer and the C loaders' vocabularies, the grammar files the oracle's writer prints -- every line, every feature digit
+    (PrintResults.c:339-577).  Plain and gzip'd, one and three writer threads."""
+    import gzip
+    from _oracle import Oracle
+    from cgx_b200 import grammar_compare as gc
+    from cgx_b200._lib import RULE_WIRE_DTYPE, Result
+    from cgx_b200.host import HostCorpus
+    o = Oracle.from_files(micro_files["f"], micro_files["e"], micro_files["a"], micro_files["lex"])
+    o.build_sa()
+    oc = o.run_query_file(micro_files["q"])
+    hc = HostCorpus(*(micro_files[k] for k in ("f", "q", "e", "a", "lex")))
+    lay = hc.layout()
+    s, qoff = lay["str"], lay["qry_off"]
+    Q, T, G, D1, D2 = len(qoff) - 1, int(qoff[-1]), oc.G, oc.D1, oc.D2
+    blocks = o.blocks()                                                        # {up, down, len, corpus position}, ids = first appearance
+    bid = {(int(b[0]), int(b[2])): g for g, b in enumerate(blocks)}
+    iv = o.intervals(5)
+    phrase_id = np.full((T, 5), -1, dtype=np.int32)
+    for t in range(T):
+        for m in range(5):
+            if iv[t, m, 0] >= 0:
+                phrase_id[t, m] = bid[(int(iv[t, m, 0]), m + 1)]
+    # a corpus position spelling every 1..3-gram (the writer spells a pattern's halves from the text)
+    where = {}
+    for m in (1, 2, 3):
+        for p in range(lay["n"] - m, -1, -1):
+            where[tuple(s[p:p + m].tolist())] = p
+    op1 = o.onegap_patterns()
+    pat1 = np.zeros((D1, 4), dtype=np.int32)
+    for d in range(D1):
+        ls, le = int(op1[d, 6]), int(op1[d, 7])
+        pat1[d] = (where[tuple(op1[d, :ls].tolist())], ls, where[tuple(op1[d, ls + 1:ls + 1 + le].tolist())], le)
+    pat2 = np.ascontiguousarray(o.twogap_patterns()[:, :2], dtype=np.int32)
+    lists = [[o.query_list(w, q) for q in range(Q)] for w in (0, 1, 2)]
+    # GenerateBlocks order = the order the writer derives from phrase_id
+    for q in range(Q):
+        seen, order = set(), []
+        for g in phrase_id[qoff[q]:qoff[q + 1]].ravel().tolist():
+            if g >= 0 and g not in seen:
+                seen.add(g)
+                order.append(g)
+        assert order == lists[0][q].tolist(), q
+    offs = [np.concatenate([[0], np.cumsum([len(x) for x in lists[w]])]).astype(np.int32) for w in (1, 2)]
+    ids = [np.concatenate(lists[w] + [np.zeros(0, np.int32)]).astype(np.int32) for w in (1, 2)]
+    n_ids = [G, 2 * G + D1, G + D2 + 2 * D1]
+    keep = []                                                                  # ctypes holds raw pointers
+    res = Result()
+    res.Q, res.T, res.G, res.D1, res.D2 = Q, T, G, D1, D2
+    ptr = lambda a, t=C.c_int32: a.ctypes.data_as(C.POINTER(t))
+    for name, a in (("phrase_id", phrase_id), ("phrases", np.ascontiguousarray(blocks, dtype=np.int32)), ("pat1", pat1), ("pat2", pat2),
+                    ("q1_off", offs[0]), ("q1_ids", ids[0]), ("q2_off", offs[1]), ("q2_ids", ids[1])):
+        a = np.ascontiguousarray(a)
+        keep.append(a)
+        setattr(res, name, ptr(a))
+    total = 0
+    for k in range(3):
+        r = o.rules(k)
+        r = r[np.argsort(r["id"], kind="stable")]
+        rec = r["rec"].reshape(-1, 6)                                          # tgt_start, end, gap1, gap1_1, gap2, gap2_1 (-1: no such gap)
+        g = lambda v: np.where(v < 0, 15, v).astype(np.uint32)
+        wire = np.zeros(len(r), dtype=RULE_WIRE_DTYPE)
+        wire["tgt_start"], wire["mlfe"], wire["mlef"] = rec[:, 0], r["mlfe"], r["mlef"]
+        assert rec[:, 1].max(initial=0) < 15 and rec[:, 2:].max(initial=0) < 15
+        wire["span"] = (rec[:, 1].astype(np.uint32) | g(rec[:, 2]) << 4 | g(rec[:, 3]) << 8 | g(rec[:, 4]) << 12 | g(rec[:, 5]) << 16 |
+                        r["pc"].astype(np.uint32) << 20)
+        first = np.full(n_ids[k], -1, dtype=np.int32)
+        idinfo = np.zeros(n_ids[k], dtype=np.uint32)
+        uid, start, cnt = np.unique(r["id"], return_index=True, return_counts=True)
+        first[uid] = start
+        idinfo[uid] = r["f"][start].astype(np.uint32) | r["fs"][start].astype(np.uint32) << 9 | cnt.astype(np.uint32) << 18
+        assert cnt.max(initial=0) <= 300 and r["f"].max(initial=0) <= 300 and r["fs"].max(initial=0) <= 300
+        keep += [wire, first, idinfo]
+        res.rules[k], res.n_rules[k], res.n_ids[k] = wire.ctypes.data, len(wire), n_ids[k]
+        res.first[k], res.idinfo[k] = ptr(first), ptr(idinfo, C.c_uint32)
+        total += len(wire)
+    assert total > 5000
+    orc = tmp_path / "orc"
+    orc.mkdir()
+    o.write_grammars(str(orc))
+    qo = np.ascontiguousarray(qoff, dtype=np.int32)
+    hc.H.cgxh_write_grammars_ex.argtypes = [C.c_char_p, C.POINTER(Result), C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    for threads, gz in ((1, 0), (3, 0), (2, 6)):
+        out = tmp_path / ("mine_%d_%d" % (threads, gz))
+        out.mkdir()
+        assert hc.H.cgxh_write_grammars_ex(str(out).encode(), C.byref(res), ptr(qo), 0, C.byref(hc.src), C.byref(hc.tgt), threads, gz) == 0
+        if gz:
+            for q in range(Q):
+                (out / ("grammar.%d.s" % q)).write_bytes(gzip.open(out / ("grammar.%d.s.gz" % q)).read())
+                os.remove(out / ("grammar.%d.s.gz" % q))
+        c = gc.compare_dirs(str(out), str(orc), rtol=0, atol=0)
+        assert c["files"] == Q and c["only_a"] == 0 and c["only_b"] == 0 and c["float_mismatch"] == 0, (threads, gz, c)
+        # same sequence of rule groups (source sides) in every file
+        for q in range(Q):
+            seq = lambda path: [k for k, _ in __import__("itertools").groupby(line.split(" ||| ")[1] for line in open(path))]
+            assert seq(out / ("grammar.%d.s" % q)) == seq(orc / ("grammar.%d.s" % q)), q
+
+
 def test_cli_usage_contract(built):
     """Exactly six positionals, otherwise help and exit 0 (Main.c:46-48)."""
     exe = os.path.join(ROOT, "bin", "strmatchcuda")
