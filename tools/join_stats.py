@@ -46,7 +46,7 @@ for F in (128, 256, 512, 1024, 2048, 4096, 8192):
     m = single & (ra < F) & (rb < F)
     print("single-token pairs with both ranks < %5d: %9d patterns  W %.3e  hits %.3e ; rest W %.3e (max W %d)" % (F, m.sum(), W[m].sum(), hc[m].sum(), W[~m].sum(), W[~m].max()))
 # two-gap
-p2 = res.pat2
+p2 = ex.debug_fetch("pat2_full", res.D2 * 4, 4)     # device records: {pat1, ctok, hit_start, hit_count}
 nH = p1[p2[:, 0], 5].astype(np.int64)
 nC = cnt[p2[:, 1]].astype(np.int64)
 W2 = np.minimum(nH, nC)
