@@ -300,6 +300,30 @@ def test_writer_prints_the_oracles_results_exactly_like_the_oracle(micro, micro_
             assert seq(out / ("grammar.%d.s" % q)) == seq(orc / ("grammar.%d.s" % q)), q
 
 
+def test_threaded_loader_equals_the_four_loaders_one_by_one(micro_files, tmp_path, built):
+    """cgxh_load_files (source || target, then alignment || lexical file) fills the same arrays as the four loaders called in turn;
+    a missing file is reported, not survived."""
+    from cgx_b200.host import Align, HostCorpus, Lex, Side, load
+    H = load()
+    hc = HostCorpus(*(micro_files[k] for k in ("f", "q", "e", "a", "lex")))
+    par = hc.layout()
+    src, tgt, al, lex = Side(), Side(), Align(), Lex()
+    assert H.cgxh_corpus_load(micro_files["f"].encode(), 1, C.byref(src)) == 0
+    assert H.cgxh_corpus_load(micro_files["e"].encode(), 0, C.byref(tgt)) == 0
+    assert H.cgxh_lex_load(micro_files["lex"].encode(), C.byref(src), C.byref(tgt), C.byref(lex)) == 0
+    assert H.cgxh_alignment_load(micro_files["a"].encode(), C.byref(src), C.byref(tgt), C.byref(al)) == 0
+    seq = HostCorpus.__new__(HostCorpus)
+    seq.H, seq.src, seq.tgt, seq.al, seq.lex, seq.qry = H, src, tgt, al, lex, hc.qry
+    one = seq.layout()
+    for k, v in par.items():
+        assert np.array_equal(v, one[k]) if isinstance(v, np.ndarray) else v == one[k], k
+    for missing in ("f", "e", "a", "lex"):
+        paths = dict(micro_files)
+        paths[missing] = str(tmp_path / "absent")
+        with pytest.raises(RuntimeError):
+            HostCorpus(*(paths[k] for k in ("f", "q", "e", "a", "lex")))
+
+
 def test_cli_usage_contract(built):
     """Exactly six positionals, otherwise help and exit 0 (Main.c:46-48)."""
     exe = os.path.join(ROOT, "bin", "strmatchcuda")
