@@ -271,7 +271,7 @@ def test_reference_hit_lists_differ_only_in_tie_order(tmp_path):
         try:
             compare(run_reference(attempt))
             break
-        except AssertionError:
+        except Exception:                # AssertionError of the comparison, or a dump the reference left incomplete
             if attempt == 2:
                 raise
 
